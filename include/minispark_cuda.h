@@ -1,0 +1,265 @@
+/* minispark_cuda.h -- C-ABI of libminispark_cuda.so, the B200 (sm_100a) operator library behind
+ * `CudaExecutionEngine`.
+ *
+ * The reference (david-westreicher/minispark) has no FFI: its native path is a code-generated Zig
+ * executable driven over stdin/stdout (src/mini_spark/jobs.py:45-79, zig-src/src/job.zig:11-51,
+ * src/mini_spark/execution.py:198-219).  This header therefore defines the boundary a maintainer
+ * would bind instead: one entry point per *operator* of the reference's hot path, each citing the
+ * reference code it replaces.  Everything is `extern "C"`, plain pointers and sizes, opaque
+ * handles, `int` return (0 = ok, <0 = error; text via msc_last_error).  No exceptions cross the
+ * boundary.  Host buffers are caller-owned, device buffers are library-owned unless stated.
+ *
+ * Thread model: one host thread per msc_ctx; a ctx owns one device, one compute stream and two
+ * copy streams.  Multi-GPU = one process (rank) per GPU, each with its own ctx; the exchange step
+ * between ranks moves the buffers produced by msc_partition() (torch.distributed / NCCL).
+ */
+#ifndef MINISPARK_CUDA_H
+#define MINISPARK_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MSC_API __attribute__((visibility("default")))
+#else
+#define MSC_API
+#endif
+
+/* ---- error codes ------------------------------------------------------------------------ */
+#define MSC_OK 0
+#define MSC_ERR_CUDA (-1)      /* a CUDA runtime call failed */
+#define MSC_ERR_IO (-2)        /* file open/read/write failed or malformed BlockFile */
+#define MSC_ERR_ARG (-3)       /* invalid argument / program */
+#define MSC_ERR_DIV_ZERO (-4)  /* a row divided by zero (reference: ZeroDivisionError in sql.py:262-266) */
+#define MSC_ERR_OVERFLOW (-5)  /* INT result does not fit i32 on write (reference: io.py:87-90) */
+#define MSC_ERR_COLLISION (-6) /* unresolved 64-bit string-hash collision in a dictionary */
+#define MSC_ERR_STRLEN (-7)    /* string longer than 255 bytes (BlockFile limit, io.py:42-44) */
+
+/* ---- logical column types: the BlockFile schema ordinals (constants.py:18-23) ------------- */
+#define MSC_T_INTEGER 0
+#define MSC_T_STRING 1
+#define MSC_T_FLOAT 2
+#define MSC_T_TIMESTAMP 3
+
+/* ---- physical (device) element types ---------------------------------------------------- */
+#define MSC_P_U8 0   /* dictionary code, <=256 entries / bool flags */
+#define MSC_P_U16 1  /* dictionary code, <=65536 entries */
+#define MSC_P_U32 2  /* dictionary code / row index */
+#define MSC_P_I32 3  /* INTEGER as stored on disk */
+#define MSC_P_I64 4  /* TIMESTAMP (microseconds); INTEGER in the wide layout; computed INTEGER */
+#define MSC_P_F32 5  /* FLOAT as stored on disk */
+#define MSC_P_F64 6  /* FLOAT in the wide layout; computed FLOAT */
+
+/* ---- device layouts for msc_table_load --------------------------------------------------- */
+#define MSC_LAYOUT_NATIVE 0 /* disk widths: i32 / f32 / i64 / narrowest dictionary code */
+#define MSC_LAYOUT_WIDE 1   /* BASELINE.json north_star widths: i64 / f64 / i64 / u32 code */
+
+/* ---- expression program opcodes (one u32 per instruction: op | depth<<8 | arg<<16) -------- *
+ * The program is a postfix stack machine whose stack depth at every instruction is static and
+ * encoded in the instruction, so each stack slot is a fixed register of the scan kernel.
+ * It replaces the reference's per-row tree interpreter (`Col.execute_row`, sql.py:127-128,
+ * 192-194,262-266,371-372) and the generated Zig condition/projection functions
+ * (templates/plan.zig:62-75,80-103).  Python parses this enum (minispark_b200/native.py).   */
+enum msc_opcode {
+  MSC_OP_END = 0,
+  /* push a column value of the current row; arg = staged column slot */
+  MSC_OP_LOAD_U8 = 1, MSC_OP_LOAD_U16 = 2, MSC_OP_LOAD_U32 = 3, MSC_OP_LOAD_I32 = 4,
+  MSC_OP_LOAD_I64 = 5, MSC_OP_LOAD_F32 = 6, MSC_OP_LOAD_F64 = 7,
+  /* push column[index[row]]; arg = staged index slot | gather column slot << 8 (late-materialised join) */
+  MSC_OP_LOADG_U8 = 8, MSC_OP_LOADG_U16 = 9, MSC_OP_LOADG_U32 = 10, MSC_OP_LOADG_I32 = 11,
+  MSC_OP_LOADG_I64 = 12, MSC_OP_LOADG_F32 = 13, MSC_OP_LOADG_F64 = 14,
+  MSC_OP_CONST = 15, /* push consts[arg] (64-bit pattern: i64 or f64) */
+  MSC_OP_I2F = 16,   /* top: i64 -> f64 (INT->FLOAT coercion, sql.py:277-290) */
+  MSC_OP_I2F_1 = 17, /* second-from-top: i64 -> f64 */
+  MSC_OP_ADD_F = 18, MSC_OP_SUB_F = 19, MSC_OP_MUL_F = 20, MSC_OP_DIV_F = 21,
+  MSC_OP_FLOORDIV_F = 22, MSC_OP_MOD_F = 23,
+  MSC_OP_ADD_I = 24, MSC_OP_SUB_I = 25, MSC_OP_MUL_I = 26, MSC_OP_FLOORDIV_I = 27, MSC_OP_MOD_I = 28,
+  MSC_OP_LT_F = 29, MSC_OP_LE_F = 30, MSC_OP_GT_F = 31, MSC_OP_GE_F = 32, MSC_OP_EQ_F = 33, MSC_OP_NE_F = 34,
+  MSC_OP_LT_I = 35, MSC_OP_LE_I = 36, MSC_OP_GT_I = 37, MSC_OP_GE_I = 38, MSC_OP_EQ_I = 39, MSC_OP_NE_I = 40,
+  MSC_OP_AND = 41, MSC_OP_OR = 42,
+  MSC_OP_LUT8 = 43,  /* top = luts[arg][top] (u8 table: LIKE / IN over dictionary codes) */
+  MSC_OP_LUT32 = 44, /* top = luts[arg][top] (u32 table: code translation between dictionaries) */
+  MSC_OP_TEE = 45,   /* temps[arg] = top (no pop): common sub-expression */
+  MSC_OP_GET = 46,   /* push temps[arg] */
+  MSC_OP_FILTER = 47, /* pop; row stays valid only if non-zero (FilterTask, tasks.py:167-177) */
+  MSC_OP_GROUP = 48,  /* pop; group id (dense mode) or 64-bit group key (hash mode) */
+  /* pop and fold into accumulator slot `arg` of the row's group (AggregateTask.fill_aggregators, tasks.py:293-310) */
+  MSC_OP_AGG_SUM_F = 49, MSC_OP_AGG_SUM_I = 50, MSC_OP_AGG_MIN_F = 51, MSC_OP_AGG_MAX_F = 52,
+  MSC_OP_AGG_MIN_I = 53, MSC_OP_AGG_MAX_I = 54,
+  MSC_OP_AGG_COUNT = 55, /* no pop: accumulator += 1 (Functions.count = SUM(Lit 1), sql.py:463-464) */
+  MSC_OP_RANK = 56,      /* project mode: compute each valid row's stable output position */
+  MSC_OP_STORE_I64 = 57, MSC_OP_STORE_F64 = 58, MSC_OP_STORE_U32 = 59, /* pop -> out column arg */
+  MSC_OP__COUNT = 60
+};
+
+#define MSC_VM_MAX_DEPTH 6   /* stack slots */
+#define MSC_VM_MAX_TEMPS 2   /* TEE/GET temporaries */
+#define MSC_VM_MAX_CODE 192  /* instructions */
+#define MSC_VM_MAX_CONSTS 32
+#define MSC_VM_MAX_STAGED 12 /* directly scanned columns (incl. index vectors) */
+#define MSC_VM_MAX_GATHER 16 /* columns read through an index vector */
+#define MSC_VM_MAX_LUTS 8
+#define MSC_VM_MAX_AGGS 16
+#define MSC_VM_MAX_OUT 16
+
+/* aggregate kinds for msc_scan_aggregate */
+#define MSC_AGG_SUM_F 0
+#define MSC_AGG_SUM_I 1
+#define MSC_AGG_MIN_F 2
+#define MSC_AGG_MAX_F 3
+#define MSC_AGG_MIN_I 4
+#define MSC_AGG_MAX_I 5
+
+typedef struct msc_ctx msc_ctx;
+typedef struct msc_table msc_table; /* an opened BlockFile (path or host memory image) */
+typedef struct msc_rel msc_rel;     /* device-resident relation: N rows x columns */
+typedef struct msc_dict msc_dict;   /* device-resident string dictionary of one STRING column */
+
+/* A column bound to a scan: device pointer + physical type. */
+typedef struct msc_colbind {
+  const void* data;
+  int32_t phys;
+  int32_t _pad;
+} msc_colbind;
+
+/* One fused scan over `nrows` rows.  staged[] columns are read row-aligned (bulk async copies
+ * into shared memory, tile by tile); gather[] columns are read through staged index vectors. */
+typedef struct msc_scan_desc {
+  uint64_t nrows;
+  int32_t nstaged;
+  int32_t ngather;
+  msc_colbind staged[MSC_VM_MAX_STAGED];
+  msc_colbind gather[MSC_VM_MAX_GATHER];
+  int32_t ncode;
+  int32_t nconsts;
+  uint32_t code[MSC_VM_MAX_CODE];
+  int64_t consts[MSC_VM_MAX_CONSTS];
+  int32_t nluts;
+  int32_t _pad;
+  const void* luts[MSC_VM_MAX_LUTS];
+} msc_scan_desc;
+
+typedef struct msc_stats {
+  double last_kernel_ms;    /* device time of the last scan/aggregate launch sequence (CUDA events) */
+  double last_ingest_ms;    /* wall time of the last msc_table_load */
+  uint64_t last_ingest_bytes; /* bytes copied host->device by the last msc_table_load */
+  uint64_t launches;        /* kernels launched by this ctx since creation */
+  uint64_t device_bytes;    /* bytes currently allocated by this ctx */
+} msc_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+MSC_API int msc_abi_version(void);
+MSC_API int msc_create(int device, msc_ctx** out);
+MSC_API void msc_destroy(msc_ctx* ctx);
+MSC_API const char* msc_last_error(msc_ctx* ctx);
+MSC_API int msc_sync(msc_ctx* ctx);
+MSC_API int msc_get_stats(msc_ctx* ctx, msc_stats* out);
+/* pinned host memory for callers that stage BlockFile images themselves */
+MSC_API int msc_host_alloc(msc_ctx* ctx, size_t nbytes, void** out);
+MSC_API int msc_host_free(msc_ctx* ctx, void* p);
+/* raw device scratch for the host side (exchange buffers) */
+MSC_API int msc_dev_alloc(msc_ctx* ctx, size_t nbytes, void** out);
+MSC_API int msc_dev_free(msc_ctx* ctx, void* p);
+MSC_API int msc_memcpy_d2h(msc_ctx* ctx, void* host_dst, const void* dev_src, size_t nbytes);
+MSC_API int msc_memcpy_h2d(msc_ctx* ctx, void* dev_dst, const void* host_src, size_t nbytes);
+
+/* ---- BlockFile ingest: replaces BlockFile._deserialize_block (io.py:112-163), LoadTableBlockTask
+ * (tasks.py:117-121) and zig ColumnData.readColumn / LoadTableBlockProducer
+ * (block_file.zig:225-268, tasks.zig:212-222).  Only the requested columns are read. -------- */
+MSC_API int msc_table_open(msc_ctx* ctx, const char* path, msc_table** out);
+MSC_API int msc_table_open_mem(msc_ctx* ctx, const void* image, size_t nbytes, msc_table** out);
+MSC_API void msc_table_close(msc_table* t);
+MSC_API int msc_table_info(msc_table* t, int32_t* ncols, int32_t* nblocks, uint64_t* nrows);
+MSC_API int msc_table_col_info(msc_table* t, int32_t col, int32_t* type, char* name, int32_t name_cap);
+MSC_API int msc_table_block_rows(msc_table* t, int32_t block, uint32_t* rows);
+/* Load `ncols` columns of `nblocks` blocks (concatenated in the order given) into a new relation.
+ * STRING columns are dictionary-encoded on the device; dicts[i] is in/out: pass NULL to create a
+ * dictionary, or an existing one to keep encoding against it.  Non-string slots are ignored. */
+MSC_API int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, int32_t ncols,
+                   const int32_t* blocks, int32_t nblocks, int32_t layout,
+                   msc_dict** dicts, msc_rel** out);
+
+/* ---- relations -------------------------------------------------------------------------- */
+MSC_API int msc_rel_info(msc_rel* r, uint64_t* nrows, int32_t* ncols);
+MSC_API int msc_rel_col(msc_rel* r, int32_t col, void** dev_ptr, int32_t* phys);
+MSC_API void msc_rel_free(msc_rel* r);
+/* wrap caller-owned device memory (e.g. exchange receive buffers) as a relation; not freed */
+MSC_API int msc_rel_wrap(msc_ctx* ctx, uint64_t nrows, const msc_colbind* cols, int32_t ncols, msc_rel** out);
+
+/* ---- fused scan -> filter -> project -> aggregate: replaces FilterTask.execute
+ * (tasks.py:167-177), ProjectTask.execute (tasks.py:79-84), AggregateTask.execute
+ * (tasks.py:270-310) and the generated Zig consumers (templates/plan.zig:113-253). ----------- */
+/* Dense mode (ngroups > 0): GROUP pops a group id in [0, ngroups).  Hash mode (ngroups == 0):
+ * GROUP pops an arbitrary 64-bit key; `hash_capacity_hint` bounds the number of distinct keys
+ * (0 = nrows).  Output relation: column 0 = group id (U32) or key (I64), columns 1..naggs =
+ * accumulators (I64 / F64), one row per group that received at least one row. */
+MSC_API int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups,
+                       const int32_t* agg_kinds, int32_t naggs, uint64_t hash_capacity_hint,
+                       msc_rel** out);
+/* Filter + project with stable compaction (output keeps input order, tasks.py:177).  Output
+ * column i is written by the program's STORE_* with arg i; out_phys[i] in {I64,F64,U32}. */
+MSC_API int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* out_phys,
+                     int32_t nout, msc_rel** out);
+
+/* ---- string dictionaries (STRING = u8-length-prefixed bytes on disk, io.py:100-104) ------- */
+MSC_API int msc_dict_create(msc_ctx* ctx, msc_dict** out);
+MSC_API void msc_dict_free(msc_dict* d);
+MSC_API int msc_dict_size(msc_dict* d, uint32_t* nentries, uint64_t* nbytes);
+/* code of a host string; insert=1 adds it when missing, else *code = -1 when missing */
+MSC_API int msc_dict_lookup(msc_ctx* ctx, msc_dict* d, const char* s, size_t len, int32_t insert, int64_t* code);
+/* u8 LUT over the dictionary entries: 1 where the entry matches the LIKE pattern
+ * (LikeColumn, sql.py:178-179,192-194; zig-regex call at templates/plan.zig:66-68) */
+MSC_API int msc_dict_like(msc_ctx* ctx, msc_dict* d, const char* pattern, size_t len, void** lut_dev);
+/* u32 LUT translating codes of `from` into codes of `to` (insert=1 extends `to`;
+ * otherwise missing entries map to 0xFFFFFFFF) */
+MSC_API int msc_dict_translate(msc_ctx* ctx, msc_dict* from, msc_dict* to, int32_t insert, void** lut_dev);
+/* copy the dictionary to the host: lens[nentries] (u32) and concatenated bytes */
+MSC_API int msc_dict_export(msc_ctx* ctx, msc_dict* d, uint32_t* lens, uint8_t* bytes);
+/* STRING '+' STRING (sql.py:331-333, zig concatStrings utils.zig:118-131): per-row concatenation
+ * of `nparts` parts; part i is a code column (codes[i] != NULL, with its dictionary) or a literal.
+ * Result: new U32 code column (1-column relation) over dictionary `out_dict`. */
+typedef struct msc_concat_part {
+  msc_colbind codes;      /* data == NULL -> literal */
+  msc_dict* dict;
+  const char* literal;
+  uint64_t literal_len;
+} msc_concat_part;
+MSC_API int msc_str_concat(msc_ctx* ctx, const msc_concat_part* parts, int32_t nparts, uint64_t nrows,
+                   msc_dict* out_dict, msc_rel** out);
+
+/* ---- hash join: replaces BroadcastHashJoinTask.generate_chunks (tasks.py:201-240) and zig
+ * JoinProducer (tasks.zig:21-196).  Keys are 64-bit (INTEGER/TIMESTAMP value, FLOAT bits or a
+ * code in a shared dictionary).  Output: 2-column relation of U32 row indices (left, right),
+ * one row per matching pair, right-row major like the reference. ---------------------------- */
+MSC_API int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nleft,
+                  const int64_t* right_keys, uint64_t nright, msc_rel** out_pairs);
+
+/* ---- shuffle partitioning: replaces WriteToShufflePartitions.write (tasks.py:347-375) and zig
+ * fill_buckets (task_utils.zig:53-98).  Rows are routed by hash(key) % nparts; every column is
+ * scattered into partition-contiguous order.  counts[nparts] (host) receives rows per partition.
+ * Output relation has the same columns, permuted. ------------------------------------------- */
+MSC_API int msc_partition(msc_ctx* ctx, msc_rel* rel, int32_t key_col, int32_t nparts, uint64_t* counts,
+                  msc_rel** out);
+
+/* ---- results: replaces WriteToLocalFileTask.write (tasks.py:399-410) / zig BlockFile.appendData
+ * (block_file.zig:413-456).  INTEGER narrows to i32 (error on overflow), FLOAT to f32. ------- */
+MSC_API int msc_rel_copy_column(msc_ctx* ctx, msc_rel* r, int32_t col, void* host_dst, size_t cap_bytes);
+typedef struct msc_out_col {
+  const char* name;
+  int32_t type;      /* MSC_T_* */
+  int32_t rel_col;   /* column of the relation */
+  msc_dict* dict;    /* for MSC_T_STRING */
+} msc_out_col;
+MSC_API int msc_write_blockfile(msc_ctx* ctx, msc_rel* r, const msc_out_col* cols, int32_t ncols,
+                        const char* path, uint32_t rows_per_block);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINISPARK_CUDA_H */

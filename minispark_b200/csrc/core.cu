@@ -1,0 +1,194 @@
+// core.cu -- context lifetime, stream-ordered device memory, error word, relation handles.
+#include "common.cuh"
+
+int msc_alloc(msc_ctx* ctx, size_t nbytes, void** out) {
+  if (nbytes == 0) nbytes = 16;
+  MSC_CUDA(ctx, cudaMallocAsync(out, nbytes, ctx->stream));
+  ctx->stats.device_bytes += nbytes;
+  return MSC_OK;
+}
+
+int msc_free(msc_ctx* ctx, void* p, size_t nbytes) {
+  if (!p) return MSC_OK;
+  if (nbytes == 0) nbytes = 16;
+  ctx->stats.device_bytes -= nbytes;
+  MSC_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+  return MSC_OK;
+}
+
+int msc_alloc_rows(msc_ctx* ctx, uint64_t nrows, size_t width, void** out, size_t* bytes_out) {
+  const size_t bytes = static_cast<size_t>(msc_round_up(nrows ? nrows : 1, MSC_ROW_PAD)) * width + 256;
+  MSC_TRY(msc_alloc(ctx, bytes, out));
+  // the padding is bulk-copied by the scan kernel; keep it defined (rows past nrows are masked)
+  const size_t used = static_cast<size_t>(nrows) * width;
+  MSC_CUDA(ctx, cudaMemsetAsync(static_cast<char*>(*out) + used, 0, bytes - used, ctx->stream));
+  if (bytes_out) *bytes_out = bytes;
+  return MSC_OK;
+}
+
+int msc_check_device_error(msc_ctx* ctx) {
+  MSC_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int e = *ctx->h_err;
+  if (e == 0) return MSC_OK;
+  MSC_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  if (e & MSC_DEVERR_DIV_ZERO) return ctx->fail(MSC_ERR_DIV_ZERO, "division by zero");
+  if (e & MSC_DEVERR_OVERFLOW) return ctx->fail(MSC_ERR_OVERFLOW, "int too big to convert");
+  if (e & MSC_DEVERR_COLLISION) return ctx->fail(MSC_ERR_COLLISION, "string hash collision in dictionary");
+  if (e & MSC_DEVERR_STRLEN) return ctx->fail(MSC_ERR_STRLEN, "string longer than 255 bytes");
+  return ctx->fail(MSC_ERR_ARG, "hash table full");
+}
+
+extern "C" int msc_abi_version(void) { return MSC_ABI_VERSION; }
+
+extern "C" int msc_create(int device, msc_ctx** out) {
+  if (!out) return MSC_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MSC_ERR_CUDA;
+  msc_ctx* ctx = new msc_ctx();
+  ctx->device = device;
+  auto bail = [&](const char* what) {
+    fprintf(stderr, "msc_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return MSC_ERR_CUDA;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail("cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    fprintf(stderr, "msc_create: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
+    delete ctx;
+    return MSC_ERR_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
+  for (auto& s : ctx->copy)
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
+  if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) return bail("cudaEventCreate");
+  for (auto& e : ctx->ring_ev)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail("cudaEventCreate");
+  // keep freed blocks in the pool: relations are created and dropped on every query
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t threshold = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  if (cudaMalloc(&ctx->d_err, sizeof(int)) != cudaSuccess) return bail("cudaMalloc");
+  if (cudaMemset(ctx->d_err, 0, sizeof(int)) != cudaSuccess) return bail("cudaMemset");
+  if (cudaHostAlloc(&ctx->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
+  *out = ctx;
+  return MSC_OK;
+}
+
+extern "C" void msc_destroy(msc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->ring)
+    if (r) cudaFreeHost(r);
+  for (auto& e : ctx->ring_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->d_err) cudaFree(ctx->d_err);
+  if (ctx->h_err) cudaFreeHost(ctx->h_err);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  for (auto& s : ctx->copy)
+    if (s) cudaStreamDestroy(s);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* msc_last_error(msc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int msc_sync(msc_ctx* ctx) {
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MSC_OK;
+}
+
+extern "C" int msc_get_stats(msc_ctx* ctx, msc_stats* out) {
+  if (!ctx || !out) return MSC_ERR_ARG;
+  *out = ctx->stats;
+  return MSC_OK;
+}
+
+extern "C" int msc_host_alloc(msc_ctx* ctx, size_t nbytes, void** out) {
+  MSC_CUDA(ctx, cudaHostAlloc(out, nbytes ? nbytes : 16, cudaHostAllocDefault));
+  return MSC_OK;
+}
+
+extern "C" int msc_host_free(msc_ctx* ctx, void* p) {
+  MSC_CUDA(ctx, cudaFreeHost(p));
+  return MSC_OK;
+}
+
+extern "C" int msc_dev_alloc(msc_ctx* ctx, size_t nbytes, void** out) {
+  MSC_TRY(msc_alloc(ctx, nbytes ? nbytes : 16, out));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MSC_OK;
+}
+
+extern "C" int msc_dev_free(msc_ctx* ctx, void* p) {
+  if (!p) return MSC_OK;
+  MSC_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+  return MSC_OK;
+}
+
+extern "C" int msc_memcpy_d2h(msc_ctx* ctx, void* host_dst, const void* dev_src, size_t nbytes) {
+  if (nbytes == 0) return MSC_OK;
+  MSC_CUDA(ctx, cudaMemcpyAsync(host_dst, dev_src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MSC_OK;
+}
+
+extern "C" int msc_memcpy_h2d(msc_ctx* ctx, void* dev_dst, const void* host_src, size_t nbytes) {
+  if (nbytes == 0) return MSC_OK;
+  MSC_CUDA(ctx, cudaMemcpyAsync(dev_dst, host_src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MSC_OK;
+}
+
+// ---- relations -----------------------------------------------------------------------------------
+extern "C" int msc_rel_info(msc_rel* r, uint64_t* nrows, int32_t* ncols) {
+  if (!r) return MSC_ERR_ARG;
+  if (nrows) *nrows = r->nrows;
+  if (ncols) *ncols = static_cast<int32_t>(r->cols.size());
+  return MSC_OK;
+}
+
+extern "C" int msc_rel_col(msc_rel* r, int32_t col, void** dev_ptr, int32_t* phys) {
+  if (!r || col < 0 || col >= static_cast<int32_t>(r->cols.size())) return MSC_ERR_ARG;
+  if (dev_ptr) *dev_ptr = r->cols[col].data;
+  if (phys) *phys = r->cols[col].phys;
+  return MSC_OK;
+}
+
+extern "C" void msc_rel_free(msc_rel* r) {
+  if (!r) return;
+  for (auto& c : r->cols)
+    if (c.owned && c.data) msc_free(r->ctx, c.data, c.bytes);
+  delete r;
+}
+
+extern "C" int msc_rel_wrap(msc_ctx* ctx, uint64_t nrows, const msc_colbind* cols, int32_t ncols, msc_rel** out) {
+  if (!ctx || !out || ncols < 0) return MSC_ERR_ARG;
+  msc_rel* r = new msc_rel();
+  r->ctx = ctx;
+  r->nrows = nrows;
+  for (int i = 0; i < ncols; ++i) {
+    msc_col c;
+    c.data = const_cast<void*>(cols[i].data);
+    c.phys = cols[i].phys;
+    c.owned = false;
+    r->cols.push_back(c);
+  }
+  *out = r;
+  return MSC_OK;
+}
+
+extern "C" int msc_rel_copy_column(msc_ctx* ctx, msc_rel* r, int32_t col, void* host_dst, size_t cap_bytes) {
+  if (!r || col < 0 || col >= static_cast<int32_t>(r->cols.size())) return ctx->fail(MSC_ERR_ARG, "bad column");
+  const size_t need = static_cast<size_t>(r->nrows) * msc_phys_width(r->cols[col].phys);
+  if (need > cap_bytes) return ctx->fail(MSC_ERR_ARG, "host buffer too small");
+  return msc_memcpy_d2h(ctx, host_dst, r->cols[col].data, need);
+}

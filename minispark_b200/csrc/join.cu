@@ -1,0 +1,274 @@
+// join.cu -- device hash join (build + probe) and shuffle partitioning.
+//
+// msc_hash_join replaces BroadcastHashJoinTask.generate_chunks (src/mini_spark/tasks.py:201-240:
+// dict key -> [left row idx], then per right row emit left-cols ++ right-cols) and the Zig
+// JoinProducer (zig-src/src/tasks.zig:21-196).  It is late-materialising: the result is a pair of
+// row-index vectors, and the columns of both sides are gathered by the scan kernel (LOADG_*) only
+// where a later operator needs them.  Unlike the reference (whose row indices restart per chunk,
+// tasks.py:216-218) the build side may be of any size.
+//
+// msc_partition replaces WriteToShufflePartitions.write (tasks.py:347-375) / zig fill_buckets
+// (task_utils.zig:53-98): rows are routed by hash(key) % nparts into partition-contiguous order,
+// ready for an all-to-all between ranks.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long J_EMPTY = 0x8000000000000000ULL;
+constexpr uint32_t NIL = 0xFFFFFFFFu;
+
+__device__ __forceinline__ unsigned long long norm_key(long long k) {
+  return (static_cast<unsigned long long>(k) == J_EMPTY) ? 0ULL : static_cast<unsigned long long>(k);
+}
+
+__global__ void join_init_kernel(unsigned long long* hkeys, uint32_t* head, uint64_t cap) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < cap;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    hkeys[i] = J_EMPTY;
+    head[i] = NIL;
+  }
+}
+
+// build: key -> chain of left rows (head[slot] -> next[row] -> ...)
+__global__ void join_build_kernel(const long long* keys, uint32_t n, unsigned long long* hkeys, uint32_t* head,
+                                  uint32_t* next, uint64_t cap) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = norm_key(keys[i]);
+  const uint64_t mask = cap - 1;
+  uint64_t pos = msc_mix64(k) & mask;
+  while (true) {
+    const unsigned long long cur = hkeys[pos];
+    if (cur == k) break;
+    if (cur == J_EMPTY) {
+      const unsigned long long prev = atomicCAS(hkeys + pos, J_EMPTY, k);
+      if (prev == J_EMPTY || prev == k) break;
+    }
+    pos = (pos + 1) & mask;
+  }
+  next[i] = atomicExch(head + pos, i);
+}
+
+__device__ __forceinline__ uint32_t join_find(const unsigned long long* hkeys, const uint32_t* head, uint64_t cap,
+                                              unsigned long long k) {
+  const uint64_t mask = cap - 1;
+  uint64_t pos = msc_mix64(k) & mask;
+  while (true) {
+    const unsigned long long cur = hkeys[pos];
+    if (cur == k) return head[pos];
+    if (cur == J_EMPTY) return NIL;
+    pos = (pos + 1) & mask;
+  }
+}
+
+__global__ void join_count_kernel(const long long* rkeys, uint32_t nr, const unsigned long long* hkeys,
+                                  const uint32_t* head, const uint32_t* next, uint64_t cap, uint32_t* counts) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nr) return;
+  uint32_t c = 0;
+  for (uint32_t l = join_find(hkeys, head, cap, norm_key(rkeys[j])); l != NIL; l = next[l]) ++c;
+  counts[j] = c;
+}
+
+__global__ void join_emit_kernel(const long long* rkeys, uint32_t nr, const unsigned long long* hkeys,
+                                 const uint32_t* head, const uint32_t* next, uint64_t cap, const uint64_t* offsets,
+                                 uint32_t* out_l, uint32_t* out_r) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nr) return;
+  uint64_t o = offsets[j];
+  for (uint32_t l = join_find(hkeys, head, cap, norm_key(rkeys[j])); l != NIL; l = next[l]) {
+    out_l[o] = l;
+    out_r[o] = j;
+    ++o;
+  }
+}
+
+// ---- partitioning ---------------------------------------------------------------------------------
+constexpr int PBLOCK = 4096;  // rows per histogram block
+constexpr int PTHREADS = 256;
+constexpr int MAX_PARTS = 64;
+
+__device__ __forceinline__ long long read_key(const void* col, int phys, uint64_t i) {
+  switch (phys) {
+    case MSC_P_U8: return static_cast<const uint8_t*>(col)[i];
+    case MSC_P_U16: return static_cast<const uint16_t*>(col)[i];
+    case MSC_P_U32: return static_cast<const uint32_t*>(col)[i];
+    case MSC_P_I32: return static_cast<const int*>(col)[i];
+    case MSC_P_F32: return __double_as_longlong(static_cast<double>(static_cast<const float*>(col)[i]));
+    default: return static_cast<const long long*>(col)[i];
+  }
+}
+
+// partition id from the HIGH hash bits: the aggregation / join tables index with the low bits
+__device__ __forceinline__ int part_of(long long key, int nparts) {
+  return static_cast<int>((msc_mix64(norm_key(key)) >> 32) % static_cast<unsigned>(nparts));
+}
+
+__global__ void part_hist_kernel(const void* key, int phys, uint64_t n, int nparts, uint32_t nblocks, uint32_t* hist) {
+  __shared__ uint32_t h[MAX_PARTS];
+  if (threadIdx.x < MAX_PARTS) h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * PBLOCK;
+  for (int i = threadIdx.x; i < PBLOCK; i += PTHREADS) {
+    const uint64_t r = base + i;
+    if (r < n) atomicAdd(&h[part_of(read_key(key, phys, r), nparts)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nparts) hist[static_cast<uint64_t>(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void part_pos_kernel(const void* key, int phys, uint64_t n, int nparts, uint32_t nblocks,
+                                const uint64_t* offsets, uint32_t* pos) {
+  __shared__ unsigned long long cursor[MAX_PARTS];
+  if (threadIdx.x < nparts) cursor[threadIdx.x] = offsets[static_cast<uint64_t>(threadIdx.x) * nblocks + blockIdx.x];
+  __syncthreads();
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * PBLOCK;
+  for (int i = threadIdx.x; i < PBLOCK; i += PTHREADS) {
+    const uint64_t r = base + i;
+    if (r < n) {
+      const int p = part_of(read_key(key, phys, r), nparts);
+      pos[r] = static_cast<uint32_t>(atomicAdd(&cursor[p], 1ULL));
+    }
+  }
+}
+
+template <class T>
+__global__ void scatter_kernel(const T* in, T* out, const uint32_t* pos, uint64_t n) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    out[pos[i]] = in[i];
+}
+
+inline unsigned grid_for(uint64_t n, int block) { return static_cast<unsigned>((n + block - 1) / block); }
+
+}  // namespace
+
+extern "C" int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nleft, const int64_t* right_keys,
+                             uint64_t nright, msc_rel** out_pairs) {
+  if (!ctx || !out_pairs) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  if (nleft >= NIL || nright >= NIL) return ctx->fail(MSC_ERR_ARG, "join side exceeds 2^32-1 rows");
+  msc_rel* rel = new msc_rel();
+  rel->ctx = ctx;
+  auto finish_empty = [&]() {
+    for (int i = 0; i < 2; ++i) {
+      msc_col c;
+      c.phys = MSC_P_U32;
+      msc_alloc_rows(ctx, 0, 4, &c.data, &c.bytes);
+      rel->cols.push_back(c);
+    }
+    *out_pairs = rel;
+    return MSC_OK;
+  };
+  if (nleft == 0 || nright == 0) return finish_empty();
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  uint64_t cap = 64;
+  while (cap < nleft * 2) cap <<= 1;
+  DevTmp hkeys(ctx), head(ctx), next(ctx), counts(ctx), offsets(ctx);
+  auto fail = [&](int rc) {
+    msc_rel_free(rel);
+    return rc;
+  };
+  int rc;
+  if ((rc = hkeys.alloc(cap * 8)) != MSC_OK || (rc = head.alloc(cap * 4)) != MSC_OK || (rc = next.alloc(nleft * 4)) != MSC_OK ||
+      (rc = counts.alloc(nright * 4)) != MSC_OK || (rc = offsets.alloc((nright + 1) * 8)) != MSC_OK)
+    return fail(rc);
+  const uint32_t nl = static_cast<uint32_t>(nleft), nr = static_cast<uint32_t>(nright);
+  join_init_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(hkeys.as<unsigned long long>(), head.as<uint32_t>(), cap);
+  join_build_kernel<<<grid_for(nl, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(left_keys), nl,
+                                                               hkeys.as<unsigned long long>(), head.as<uint32_t>(), next.as<uint32_t>(), cap);
+  join_count_kernel<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(right_keys), nr,
+                                                               hkeys.as<unsigned long long>(), head.as<uint32_t>(), next.as<uint32_t>(), cap,
+                                                               counts.as<uint32_t>());
+  ctx->stats.launches += 3;
+  if ((rc = msc_exclusive_scan_u32_u64(ctx, counts.as<uint32_t>(), offsets.as<uint64_t>(), nright)) != MSC_OK) return fail(rc);
+  uint64_t npairs = 0;
+  if ((rc = msc_memcpy_d2h(ctx, &npairs, offsets.as<uint64_t>() + nright, 8)) != MSC_OK) return fail(rc);
+  if (npairs >= NIL) return fail(ctx->fail(MSC_ERR_ARG, "join result exceeds 2^32-1 rows"));
+  rel->nrows = npairs;
+  for (int i = 0; i < 2; ++i) {
+    msc_col c;
+    c.phys = MSC_P_U32;
+    if ((rc = msc_alloc_rows(ctx, npairs, 4, &c.data, &c.bytes)) != MSC_OK) return fail(rc);
+    rel->cols.push_back(c);
+  }
+  if (npairs) {
+    join_emit_kernel<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(right_keys), nr,
+                                                                hkeys.as<unsigned long long>(), head.as<uint32_t>(), next.as<uint32_t>(), cap,
+                                                                offsets.as<uint64_t>(), static_cast<uint32_t*>(rel->cols[0].data),
+                                                                static_cast<uint32_t*>(rel->cols[1].data));
+    ctx->stats.launches += 1;
+  }
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MSC_CUDA(ctx, cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  ctx->stats.last_kernel_ms = ms;
+  *out_pairs = rel;
+  return MSC_OK;
+}
+
+extern "C" int msc_partition(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t nparts, uint64_t* counts_host, msc_rel** out) {
+  if (!ctx || !in || !out || !counts_host || nparts < 1 || nparts > MAX_PARTS || key_col < 0 ||
+      key_col >= static_cast<int32_t>(in->cols.size()))
+    return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  const uint64_t n = in->nrows;
+  msc_rel* rel = new msc_rel();
+  rel->ctx = ctx;
+  rel->nrows = n;
+  auto fail = [&](int rc) {
+    msc_rel_free(rel);
+    return rc;
+  };
+  int rc;
+  for (auto& src : in->cols) {
+    msc_col c;
+    c.phys = src.phys;
+    if ((rc = msc_alloc_rows(ctx, n, msc_phys_width(c.phys), &c.data, &c.bytes)) != MSC_OK) return fail(rc);
+    rel->cols.push_back(c);
+  }
+  for (int p = 0; p < nparts; ++p) counts_host[p] = 0;
+  if (n == 0) {
+    *out = rel;
+    return MSC_OK;
+  }
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  const uint32_t nblocks = static_cast<uint32_t>((n + PBLOCK - 1) / PBLOCK);
+  const uint64_t cells = static_cast<uint64_t>(nblocks) * nparts;
+  DevTmp hist(ctx), offsets(ctx), pos(ctx);
+  if ((rc = hist.alloc(cells * 4)) != MSC_OK || (rc = offsets.alloc((cells + 1) * 8)) != MSC_OK || (rc = pos.alloc(n * 4)) != MSC_OK)
+    return fail(rc);
+  const msc_col& key = in->cols[key_col];
+  part_hist_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, hist.as<uint32_t>());
+  ctx->stats.launches += 1;
+  if ((rc = msc_exclusive_scan_u32_u64(ctx, hist.as<uint32_t>(), offsets.as<uint64_t>(), cells)) != MSC_OK) return fail(rc);
+  part_pos_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, offsets.as<uint64_t>(), pos.as<uint32_t>());
+  ctx->stats.launches += 1;
+  const unsigned grid = static_cast<unsigned>(ctx->sm_count * 8);
+  for (size_t c = 0; c < in->cols.size(); ++c) {
+    const void* src = in->cols[c].data;
+    void* dst = rel->cols[c].data;
+    switch (msc_phys_width(in->cols[c].phys)) {
+      case 1: scatter_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pos.as<uint32_t>(), n); break;
+      case 2: scatter_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), pos.as<uint32_t>(), n); break;
+      case 4: scatter_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), pos.as<uint32_t>(), n); break;
+      default: scatter_kernel<uint64_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const uint64_t*>(src), static_cast<uint64_t*>(dst), pos.as<uint32_t>(), n); break;
+    }
+    ctx->stats.launches += 1;
+  }
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  // rows per partition = difference of the partition-major offsets
+  std::vector<uint64_t> bounds(nparts + 1);
+  for (int p = 0; p <= nparts; ++p) {
+    const uint64_t idx = static_cast<uint64_t>(p) * nblocks;
+    MSC_CUDA(ctx, cudaMemcpyAsync(&bounds[p], offsets.as<uint64_t>() + idx, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MSC_CUDA(ctx, cudaGetLastError());
+  for (int p = 0; p < nparts; ++p) counts_host[p] = bounds[p + 1] - bounds[p];
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  ctx->stats.last_kernel_ms = ms;
+  *out = rel;
+  return MSC_OK;
+}
