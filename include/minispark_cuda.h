@@ -151,6 +151,11 @@ typedef struct msc_stats {
   uint64_t last_ingest_bytes; /* bytes copied host->device by the last msc_table_load */
   uint64_t launches;        /* kernels launched by this ctx since creation */
   uint64_t device_bytes;    /* bytes currently allocated by this ctx */
+  double last_scan_ms;      /* device time of the last fused scan kernel alone (CUDA events on its stream) */
+  int32_t last_scan_grid;   /* CTAs of that launch */
+  int32_t last_scan_stages; /* shared-memory ring depth */
+  int32_t last_scan_smem;   /* dynamic shared memory bytes per CTA */
+  int32_t last_scan_rows_per_thread;
 } msc_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

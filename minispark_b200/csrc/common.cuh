@@ -22,6 +22,7 @@ struct msc_ctx {
   cudaStream_t stream = nullptr;      // compute
   cudaStream_t copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // bracket the fused scan kernel alone
   int* d_err = nullptr;               // device error word (bit flags written by kernels)
   int* h_err = nullptr;               // pinned mirror
   std::string err;

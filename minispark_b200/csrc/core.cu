@@ -66,6 +66,7 @@ extern "C" int msc_create(int device, msc_ctx** out) {
   for (auto& s : ctx->copy)
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
   if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) return bail("cudaEventCreate");
+  if (cudaEventCreate(&ctx->ev_s0) != cudaSuccess || cudaEventCreate(&ctx->ev_s1) != cudaSuccess) return bail("cudaEventCreate");
   for (auto& e : ctx->ring_ev)
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail("cudaEventCreate");
   // keep freed blocks in the pool: relations are created and dropped on every query
@@ -93,6 +94,8 @@ extern "C" void msc_destroy(msc_ctx* ctx) {
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_s0) cudaEventDestroy(ctx->ev_s0);
+  if (ctx->ev_s1) cudaEventDestroy(ctx->ev_s1);
   for (auto& s : ctx->copy)
     if (s) cudaStreamDestroy(s);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -1023,8 +1023,14 @@ int launch_scan(msc_ctx* ctx, LaunchPlan* lp) {
   if (static_cast<uint32_t>(grid) > lp->p.ntiles) grid = static_cast<int>(lp->p.ntiles);
   if (grid < 1) grid = 1;
   lp->grid = grid;
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s0, ctx->stream));
   kern<<<grid, NT, lp->smem, ctx->stream>>>(lp->p);
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s1, ctx->stream));
   ctx->stats.launches += 1;
+  ctx->stats.last_scan_grid = grid;
+  ctx->stats.last_scan_stages = static_cast<int32_t>(lp->p.nstages);
+  ctx->stats.last_scan_smem = static_cast<int32_t>(lp->smem);
+  ctx->stats.last_scan_rows_per_thread = R;
   MSC_CUDA(ctx, cudaGetLastError());
   return MSC_OK;
 }
@@ -1139,6 +1145,7 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
     ctx->stats.last_kernel_ms = ms;
+  if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
     int drc = msc_check_device_error(ctx);
     if (drc != MSC_OK) {
       msc_rel_free(rel);
@@ -1204,6 +1211,7 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
   ctx->stats.last_kernel_ms = ms;
+  if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
   *out = rel;
   return MSC_OK;
 }
@@ -1265,6 +1273,7 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
   ctx->stats.last_kernel_ms = ms;
+  if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
   int drc = msc_check_device_error(ctx);
   if (drc != MSC_OK) {
     msc_rel_free(rel);

@@ -1,0 +1,699 @@
+"""Execution engines: the ``ExecutionEngine`` contract and the B200 ``CudaExecutionEngine``.
+
+``ExecutionEngine`` mirrors the reference's abstract base (``src/mini_spark/execution.py:40-62``):
+``execute_full_task(task) -> list[JobResult]``, ``collect_results``, ``sql`` and the context-manager
+protocol.  ``CudaExecutionEngine`` is the drop-in third engine next to the reference's
+``PythonExecutionEngine`` (``execution.py:65-93``) and ``ThreadEngine`` (``execution.py:96-123``):
+
+    with CudaExecutionEngine() as engine:
+        rows = DataFrame(engine).table(path).group_by(Col("k")).agg(F.count()).collect()
+
+It lowers the task tree (:mod:`minispark_b200.lowering`) and drives the CUDA operators of
+``libminispark_cuda.so`` through ctypes.  Every row-level operation runs on the GPU; there is no CPU
+execution path (construction fails without the library and a B200).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import shutil
+import tempfile
+import time
+import uuid
+from abc import ABC, abstractmethod
+from contextlib import AbstractContextManager
+from copy import deepcopy
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import TYPE_CHECKING, Any, Iterable, Optional
+
+from . import lowering as L
+from . import native as N
+from .constants import ColumnType, Row, Schema
+from .io import BlockFile
+from .jobs import JobResult, OutputFile
+
+if TYPE_CHECKING:
+    from .dataframe import DataFrame
+
+
+class ExecutionError(Exception):
+    def __init__(self, message: str = "Execution failed") -> None:
+        super().__init__(message)
+
+
+class ExecutionEngine(AbstractContextManager, ABC):
+    """The plugin interface a ``DataFrame`` talks to (reference ``execution.py:40-62``)."""
+
+    @abstractmethod
+    def execute_full_task(self, full_task: Any) -> list[JobResult]: ...
+
+    def collect_results(self, results: list[JobResult], limit: float = math.inf) -> Iterable[Row]:
+        seen: set[OutputFile] = set()
+        for result in results:
+            for out in result.output_files:
+                if out in seen:
+                    continue
+                seen.add(out)
+                for row in BlockFile(out.file_path).read_data_rows():
+                    yield row
+                    limit -= 1
+                    if limit <= 0:
+                        return
+
+    def sql(self, query: str) -> "DataFrame":
+        from .parser import parse_sql  # noqa: PLC0415
+
+        df = parse_sql(query)
+        df.engine = self
+        return df
+
+
+# ------------------------------------------------------------------------------------------------
+# device-side objects
+# ------------------------------------------------------------------------------------------------
+class DictHandle:
+    """A device string dictionary plus host-side caches of the tables derived from it."""
+
+    def __init__(self, ctx: N.Context, handle: Optional[int] = None) -> None:
+        self.ctx = ctx
+        if handle is None:
+            h = C.c_void_p()
+            ctx.call("msc_dict_create", C.byref(h))
+            handle = h.value
+        self.handle = handle
+        self._luts: dict[tuple, int] = {}
+        self._codes: dict[tuple, int] = {}
+
+    @property
+    def size(self) -> int:
+        n = C.c_uint32()
+        nb = C.c_uint64()
+        self.ctx.check(self.ctx.lib.msc_dict_size(C.c_void_p(self.handle), C.byref(n), C.byref(nb)))
+        return n.value
+
+    def literal_code(self, text: str, insert: bool = False) -> int:
+        key = (text, self.size)
+        if key not in self._codes or insert:
+            raw = text.encode("utf-8")
+            code = C.c_int64()
+            self.ctx.call("msc_dict_lookup", C.c_void_p(self.handle), raw, len(raw), int(insert), C.byref(code))
+            self._codes[(text, self.size)] = code.value
+            return code.value
+        return self._codes[key]
+
+    def like_lut(self, pattern: str) -> int:
+        key = ("like", pattern, self.size)
+        if key not in self._luts:
+            raw = pattern.encode("utf-8")
+            out = C.c_void_p()
+            self.ctx.call("msc_dict_like", C.c_void_p(self.handle), raw, len(raw), C.byref(out))
+            self._luts[key] = out.value
+        return self._luts[key]
+
+    def translate_lut(self, target: "DictHandle", insert: bool = False) -> int:
+        """u32 LUT mapping this dictionary's codes to ``target``'s codes."""
+        key = ("tr", id(target), self.size, target.size, insert)
+        if key not in self._luts or insert:
+            out = C.c_void_p()
+            self.ctx.call("msc_dict_translate", C.c_void_p(self.handle), C.c_void_p(target.handle), int(insert), C.byref(out))
+            self._luts[("tr", id(target), self.size, target.size, insert)] = out.value
+            return out.value
+        return self._luts[key]
+
+    def export(self) -> list[str]:
+        import numpy as np  # noqa: PLC0415
+
+        n = self.size
+        if n == 0:
+            return []
+        nb = C.c_uint64()
+        self.ctx.check(self.ctx.lib.msc_dict_size(C.c_void_p(self.handle), None, C.byref(nb)))
+        lens = np.zeros(n, dtype=np.uint32)
+        raw = np.zeros(max(nb.value, 1), dtype=np.uint8)
+        self.ctx.call("msc_dict_export", C.c_void_p(self.handle), lens.ctypes.data_as(C.c_void_p), raw.ctypes.data_as(C.c_void_p))
+        out, pos, blob = [], 0, raw.tobytes()
+        for ln in lens.tolist():
+            out.append(blob[pos:pos + ln].decode("utf-8"))
+            pos += ln
+        return out
+
+    def free(self) -> None:
+        if self.handle:
+            for ptr in self._luts.values():
+                self.ctx.dev_free(ptr)
+            self._luts.clear()
+            self.ctx.lib.msc_dict_free(C.c_void_p(self.handle))
+            self.handle = None
+
+
+@dataclass
+class DeviceColumn:
+    ptr: int
+    phys: int
+    ltype: str                      # lowering type tag: I / F / T / S / B
+    dict: Optional[DictHandle] = None
+    via: Optional[int] = None       # index-vector id (virtual join relation) or None for direct
+
+
+class DeviceRel:
+    """A device-resident relation (owned ``msc_rel`` handle) with host-side column metadata."""
+
+    def __init__(self, ctx: N.Context, handle: Optional[int], nrows: int, cols: list[DeviceColumn],
+                 keep: Optional[list] = None) -> None:
+        self.ctx = ctx
+        self.handle = handle
+        self.nrows = nrows
+        self.cols = cols
+        self.keep = keep or []  # relations / dictionaries whose memory these columns reference
+
+    @classmethod
+    def from_handle(cls, ctx: N.Context, handle: int, ltypes: list[str], dicts: list[Optional[DictHandle]]) -> "DeviceRel":
+        nrows = C.c_uint64()
+        ncols = C.c_int32()
+        ctx.check(ctx.lib.msc_rel_info(C.c_void_p(handle), C.byref(nrows), C.byref(ncols)))
+        cols = []
+        for i in range(ncols.value):
+            ptr = C.c_void_p()
+            phys = C.c_int32()
+            ctx.check(ctx.lib.msc_rel_col(C.c_void_p(handle), i, C.byref(ptr), C.byref(phys)))
+            cols.append(DeviceColumn(ptr.value or 0, phys.value, ltypes[i], dicts[i]))
+        return cls(ctx, handle, nrows.value, cols)
+
+    def free(self) -> None:
+        if self.handle:
+            self.ctx.lib.msc_rel_free(C.c_void_p(self.handle))
+            self.handle = None
+
+    def column_numpy(self, i: int):  # noqa: ANN201
+        """Full-precision host copy of one column (f64 / i64 / codes): the 1e-9 parity hook."""
+        import numpy as np  # noqa: PLC0415
+
+        col = self.cols[i]
+        arr = np.zeros(self.nrows, dtype=N.PHYS_NUMPY[col.phys])
+        if self.nrows:
+            self.ctx.call("msc_memcpy_d2h", arr.ctypes.data_as(C.c_void_p), C.c_void_p(col.ptr), arr.nbytes)
+        return arr
+
+
+@dataclass
+class TableEntry:
+    path: Path
+    stamp: tuple
+    handle: int
+    schema: Schema
+    blocks: list[int]
+    nrows: int
+    columns: dict[int, DeviceColumn] = field(default_factory=dict)
+    rels: list[DeviceRel] = field(default_factory=list)
+    keepalive: Any = None  # pinned image for in-memory tables
+
+
+class _Source:
+    """Input of one fused scan: ``nrows`` rows whose column ``i`` is ``columns[i]``."""
+
+    def __init__(self, nrows: int, columns: dict[int, DeviceColumn], index_vectors: Optional[list[DeviceColumn]] = None,
+                 keep: Optional[list] = None) -> None:
+        self.nrows = nrows
+        self.columns = columns
+        self.index_vectors = index_vectors or []
+        self.keep = keep or []
+
+
+class _ScanResolver:
+    """Allocates staged / gather / LUT slots of one ``msc_scan_desc`` while the program compiles."""
+
+    def __init__(self, engine: "CudaExecutionEngine", source: _Source, translate_targets: Optional[dict[str, DictHandle]] = None) -> None:
+        self.engine = engine
+        self.source = source
+        self.staged: list[DeviceColumn] = []
+        self.gather: list[DeviceColumn] = []
+        self.luts: list[int] = []
+        self._staged_slot: dict[int, int] = {}
+        self._gather_slot: dict[int, int] = {}
+        self._bindings: dict[int, L.Binding] = {}
+        self.translate_targets = translate_targets or {}
+
+    def _stage(self, col: DeviceColumn) -> int:
+        if col.ptr not in self._staged_slot:
+            if len(self.staged) >= N.K["MSC_VM_MAX_STAGED"]:
+                raise L.LoweringError("query reads more columns than one scan can stage")
+            self._staged_slot[col.ptr] = len(self.staged)
+            self.staged.append(col)
+        return self._staged_slot[col.ptr]
+
+    def binding(self, index: int) -> L.Binding:
+        if index not in self._bindings:
+            col = self.source.columns[index]
+            if col.via is None:
+                b = L.Binding(col.phys, staged=self._stage(col), dict_id=col.dict)
+            else:
+                if col.ptr not in self._gather_slot:
+                    if len(self.gather) >= N.K["MSC_VM_MAX_GATHER"]:
+                        raise L.LoweringError("query gathers more columns than one scan supports")
+                    self._gather_slot[col.ptr] = len(self.gather)
+                    self.gather.append(col)
+                b = L.Binding(col.phys, gather=self._gather_slot[col.ptr], index=self._stage(self.source.index_vectors[col.via]),
+                              dict_id=col.dict)
+            self._bindings[index] = b
+        return self._bindings[index]
+
+    def _lut(self, ptr: int) -> int:
+        if ptr not in self.luts:
+            if len(self.luts) >= N.K["MSC_VM_MAX_LUTS"]:
+                raise L.LoweringError("too many string predicates in one scan")
+            self.luts.append(ptr)
+        return self.luts.index(ptr)
+
+    def literal_code(self, dict_id: DictHandle, text: str) -> int:
+        return dict_id.literal_code(text)
+
+    def like_lut(self, dict_id: DictHandle, pattern: str) -> int:
+        return self._lut(dict_id.like_lut(pattern))
+
+    def same_dict(self, a: DictHandle, b: DictHandle) -> bool:
+        return a is b
+
+    def recode_lut(self, src: DictHandle, dst: DictHandle) -> int:
+        return self._lut(src.translate_lut(dst, insert=False))
+
+    def translate_lut(self, dict_id: DictHandle, token: str) -> tuple[int, DictHandle]:
+        target = self.translate_targets[token]
+        if target is dict_id:
+            return -1, target
+        return self._lut(dict_id.translate_lut(target, insert=False)), target
+
+    def desc(self, program: L.Program) -> N.ScanDesc:
+        d = N.ScanDesc()
+        d.nrows = self.source.nrows
+        if not self.staged and self.source.nrows:
+            # a program without column reads (e.g. COUNT(*) over a constant) still needs the row count only
+            pass
+        d.nstaged = len(self.staged)
+        d.ngather = len(self.gather)
+        for i, col in enumerate(self.staged):
+            d.staged[i].data = col.ptr
+            d.staged[i].phys = col.phys
+        for i, col in enumerate(self.gather):
+            d.gather[i].data = col.ptr
+            d.gather[i].phys = col.phys
+        words = program.words()
+        d.ncode = len(words)
+        for i, w in enumerate(words):
+            d.code[i] = w
+        d.nconsts = len(program.consts)
+        for i, c in enumerate(program.consts):
+            d.consts[i] = c
+        d.nluts = len(self.luts)
+        for i, ptr in enumerate(self.luts):
+            d.luts[i] = ptr
+        return d
+
+
+_LTYPE_OF = {ColumnType.INTEGER: L.INT, ColumnType.FLOAT: L.FLOAT, ColumnType.TIMESTAMP: L.TS, ColumnType.STRING: L.STR}
+_MSC_TYPE = {ColumnType.INTEGER: N.K["MSC_T_INTEGER"], ColumnType.STRING: N.K["MSC_T_STRING"],
+             ColumnType.FLOAT: N.K["MSC_T_FLOAT"], ColumnType.TIMESTAMP: N.K["MSC_T_TIMESTAMP"]}
+# (groups + 1 trash) x (aggregates + 1 hidden counter) cells of per-thread shared-memory accumulators
+DENSE_MAX_CELLS = 96
+
+
+class CudaExecutionEngine(ExecutionEngine):
+    """B200 engine: BlockFile ingest -> device columns -> fused scan kernels -> result BlockFile.
+
+    Parameters (all optional, so ``CudaExecutionEngine()`` works like the reference engines):
+      device       CUDA device ordinal (default: ``LOCAL_RANK`` or 0)
+      work_folder  where result BlockFiles are written (default: a fresh temp dir, removed on exit)
+      layout       ``"native"`` (i32/f32/i64/narrow codes, the disk widths) or ``"wide"`` (i64/f64)
+      shard        ``(rank, world)``: this engine only ingests row-blocks ``b % world == rank``
+    """
+
+    def __init__(self, device: Optional[int] = None, work_folder: Optional[Path] = None, layout: str = "native",
+                 shard: tuple[int, int] = (0, 1)) -> None:
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.ctx = N.Context(device)  # raises when the library or the GPU is missing: no fallback
+        self.device = device
+        self.layout = N.K["MSC_LAYOUT_WIDE"] if layout == "wide" else N.K["MSC_LAYOUT_NATIVE"]
+        self.shard = shard
+        self._own_work = work_folder is None
+        self.work_folder = Path(work_folder) if work_folder is not None else Path(tempfile.mkdtemp(prefix="minispark_cuda_"))
+        self.work_folder.mkdir(parents=True, exist_ok=True)
+        self._tables: dict[str, TableEntry] = {}
+        self._query_rels: list[DeviceRel] = []
+        self._query_dicts: list[DictHandle] = []
+        self._table_dicts: list[DictHandle] = []
+        self._result_files: list[Path] = []
+        self.last_stats: dict[str, Any] = {}
+
+    # ---- ExecutionEngine contract ---------------------------------------------------------------
+    def execute_full_task(self, full_task: Any) -> list[JobResult]:
+        rel, schema = self.execute_to_device(full_task)
+        try:
+            job = JobResult(str(uuid.uuid4()), f"cuda:{self.device}", [])
+            if rel.nrows > 0:  # empty result -> no output file (reference tasks.py:405-406)
+                path = self.work_folder / f"result_{job.job_id}.bin"
+                self.write_blockfile(rel, schema, path)
+                self._result_files.append(path)
+                job.output_files.append(OutputFile(path))
+            return [job]
+        finally:
+            self.release_query()
+
+    def __exit__(self, exc_type, exc_value, traceback) -> None:  # noqa: ANN001
+        self.close()
+
+    def close(self) -> None:
+        if getattr(self, "ctx", None) is None:
+            return
+        self.release_query()
+        for entry in self._tables.values():
+            for rel in entry.rels:
+                rel.free()
+            self.ctx.lib.msc_table_close(C.c_void_p(entry.handle))
+        self._tables.clear()
+        for d in self._table_dicts:
+            d.free()
+        self._table_dicts.clear()
+        for path in self._result_files:
+            path.unlink(missing_ok=True)
+        self._result_files.clear()
+        if self._own_work:
+            shutil.rmtree(self.work_folder, ignore_errors=True)
+        self.ctx.close()
+        self.ctx = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- public extras ----------------------------------------------------------------------------
+    def execute_to_device(self, full_task: Any) -> tuple[DeviceRel, Schema]:
+        """Run the query and leave the (full-precision) result on the device."""
+        try:
+            task = deepcopy(full_task)  # planning mutates the tree (reference plan.py:181-204)
+            task.validate_schema()      # the reference's own validation and its errors
+            plan = L.lower_task(task)
+            self.last_plan = plan
+            t0 = time.perf_counter()
+            rel = self._run(plan)
+            self.last_stats["query_s"] = time.perf_counter() - t0
+            return rel, plan.schema
+        except N.NativeError as e:
+            self.release_query()
+            raise ExecutionError(str(e)) from e
+        except Exception:
+            self.release_query()
+            raise
+
+    def release_query(self) -> None:
+        for rel in self._query_rels:
+            rel.free()
+        self._query_rels.clear()
+        for d in self._query_dicts:
+            d.free()
+        self._query_dicts.clear()
+
+    def write_blockfile(self, rel: DeviceRel, schema: Schema, path: Path) -> None:
+        from . import io as _io  # noqa: PLC0415
+
+        cols = (N.OutCol * len(schema))()
+        names = []
+        for i, (name, ctype) in enumerate(schema):
+            raw = name.encode("utf-8")
+            names.append(raw)
+            cols[i].name = raw
+            cols[i].type = _MSC_TYPE[ctype]
+            cols[i].rel_col = i
+            cols[i].dict = rel.cols[i].dict.handle if rel.cols[i].dict is not None else None
+        try:
+            self.ctx.call("msc_write_blockfile", C.c_void_p(rel.handle), cols, len(schema), str(path).encode(), _io.ROWS_PER_BLOCK)
+        except N.NativeError as e:
+            if e.code == N.K["MSC_ERR_OVERFLOW"]:
+                raise OverflowError("int too big to convert") from e  # what the reference raises (io.py:90)
+            raise ExecutionError(str(e)) from e
+
+    def register_table_image(self, name: str, image_ptr: int, nbytes: int, keepalive: Any = None) -> None:
+        """Expose a BlockFile image in (pinned) host memory under a table name (used by the bench)."""
+        h = C.c_void_p()
+        self.ctx.call("msc_table_open_mem", C.c_void_p(image_ptr), nbytes, C.byref(h))
+        self._tables[name] = self._make_entry(Path(name), ("mem", image_ptr, nbytes), h.value, keepalive)
+
+    def drop_table_cache(self, name: Optional[str] = None) -> None:
+        """Forget device-resident columns (all tables, or one) so the next query ingests again."""
+        for key, entry in list(self._tables.items()):
+            if name is not None and key != name:
+                continue
+            for rel in entry.rels:
+                rel.free()
+            entry.rels.clear()
+            entry.columns.clear()
+
+    # ---- tables -----------------------------------------------------------------------------------
+    def _make_entry(self, path: Path, stamp: tuple, handle: int, keepalive: Any = None) -> TableEntry:
+        ncols, nblocks, nrows = C.c_int32(), C.c_int32(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.msc_table_info(C.c_void_p(handle), C.byref(ncols), C.byref(nblocks), C.byref(nrows)))
+        schema: Schema = []
+        for c in range(ncols.value):
+            ty = C.c_int32()
+            buf = C.create_string_buffer(256)
+            self.ctx.check(self.ctx.lib.msc_table_col_info(C.c_void_p(handle), c, C.byref(ty), buf, 256))
+            schema.append((buf.value.decode("utf-8"), ColumnType.from_ordinal(ty.value)))
+        rank, world = self.shard
+        blocks = [b for b in range(nblocks.value) if b % world == rank]
+        local_rows = 0
+        for b in blocks:
+            rows = C.c_uint32()
+            self.ctx.check(self.ctx.lib.msc_table_block_rows(C.c_void_p(handle), b, C.byref(rows)))
+            local_rows += rows.value
+        return TableEntry(path, stamp, handle, schema, blocks, local_rows, keepalive=keepalive)
+
+    def _table(self, path: Path) -> TableEntry:
+        key = str(path)
+        entry = self._tables.get(key)
+        if entry is not None and entry.stamp[0] == "mem":
+            return entry
+        st = os.stat(path)
+        stamp = (st.st_mtime_ns, st.st_size)
+        if entry is not None and entry.stamp == stamp:
+            return entry
+        if entry is not None:
+            for rel in entry.rels:
+                rel.free()
+            self.ctx.lib.msc_table_close(C.c_void_p(entry.handle))
+        h = C.c_void_p()
+        self.ctx.call("msc_table_open", str(path).encode(), C.byref(h))
+        entry = self._make_entry(Path(path), stamp, h.value)
+        self._tables[key] = entry
+        return entry
+
+    def _ensure_columns(self, entry: TableEntry, needed: Iterable[int]) -> None:
+        missing = sorted(set(needed) - set(entry.columns))
+        if not missing:
+            return
+        cols = N.int32_array(missing)
+        blocks = N.int32_array(entry.blocks)
+        dict_slots = (C.c_void_p * len(missing))()
+        out = C.c_void_p()
+        self.ctx.call("msc_table_load", C.c_void_p(entry.handle), cols, len(missing), blocks, len(entry.blocks), self.layout,
+                      dict_slots, C.byref(out))
+        ltypes = [_LTYPE_OF[entry.schema[c][1]] for c in missing]
+        dicts: list[Optional[DictHandle]] = []
+        for i, c in enumerate(missing):
+            if entry.schema[c][1] == ColumnType.STRING:
+                d = DictHandle(self.ctx, dict_slots[i])
+                self._table_dicts.append(d)
+                dicts.append(d)
+            else:
+                dicts.append(None)
+        rel = DeviceRel.from_handle(self.ctx, out.value, ltypes, dicts)
+        entry.rels.append(rel)
+        for i, c in enumerate(missing):
+            entry.columns[c] = rel.cols[i]
+        st = self.ctx.stats()
+        self.last_stats["ingest_ms"] = st.last_ingest_ms
+        self.last_stats["ingest_bytes"] = st.last_ingest_bytes
+
+    # ---- plan execution -----------------------------------------------------------------------------
+    def _track(self, rel: DeviceRel) -> DeviceRel:
+        self._query_rels.append(rel)
+        return rel
+
+    def _run(self, node: L.LNode) -> DeviceRel:
+        if isinstance(node, L.LSelect):
+            return self._run_select(node)
+        if isinstance(node, L.LAggregate):
+            return self._run_aggregate(node)
+        return self._run_select(L.identity_select(node))
+
+    def _source(self, node: L.LNode, needed: set[int]) -> _Source:
+        if isinstance(node, L.LTable):
+            entry = self._table(node.path)
+            self._ensure_columns(entry, needed)
+            return _Source(entry.nrows, {i: entry.columns[i] for i in needed})
+        if isinstance(node, L.LJoin):
+            return self._join_source(node, needed)
+        rel = self._run(node)
+        return _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel])
+
+    def _prepare(self, base: L.LNode, exprs: list[L.Expr]) -> tuple[_Source, list[L.Expr]]:
+        """Resolve the scan input and materialise string concatenations the program cannot compute."""
+        needed: set[int] = set()
+        for e in exprs:
+            needed |= L.expr_inputs(e)
+        source = self._source(base, needed)
+        concats: dict[L.EConcat, int] = {}
+
+        def rewrite(e: L.Expr) -> L.Expr:
+            if isinstance(e, L.EConcat):
+                if e not in concats:
+                    concats[e] = self._materialise_concat(source, e)
+                return L.EInput(L.STR, concats[e])
+            if isinstance(e, L.EBin):
+                return L.EBin(e.type, e.op, rewrite(e.left), rewrite(e.right))
+            if isinstance(e, L.ECast):
+                return L.ECast(e.type, rewrite(e.child))
+            if isinstance(e, L.ELike):
+                return L.ELike(e.type, rewrite(e.child), e.pattern)
+            if isinstance(e, L.ETranslate):
+                return L.ETranslate(e.type, rewrite(e.child), e.token)
+            if isinstance(e, L.ECode):
+                return L.ECode(e.type, rewrite(e.child))
+            return e
+
+        return source, [rewrite(e) for e in exprs]
+
+    def _materialise_concat(self, source: _Source, e: L.EConcat) -> int:
+        """Evaluate ``a + b + ...`` over every source row with msc_str_concat; returns the new column index."""
+        parts = (N.ConcatPart * len(e.parts))()
+        keep = []
+        for i, part in enumerate(e.parts):
+            if isinstance(part, L.EConst):
+                raw = str(part.value).encode("utf-8")
+                keep.append(raw)
+                parts[i].literal = raw
+                parts[i].literal_len = len(raw)
+                continue
+            if not isinstance(part, L.EInput):
+                raise L.LoweringError("string concatenation operands must be columns or literals")
+            col = source.columns[part.index]
+            if col.via is not None:  # virtual (joined) rows: gather the codes into a row-aligned column first
+                col = self._gather_column(source, part.index)
+            parts[i].codes.data = col.ptr
+            parts[i].codes.phys = col.phys
+            parts[i].dict = col.dict.handle
+        out_dict = DictHandle(self.ctx)
+        self._query_dicts.append(out_dict)
+        out = C.c_void_p()
+        self.ctx.call("msc_str_concat", parts, len(e.parts), source.nrows, C.c_void_p(out_dict.handle), C.byref(out))
+        rel = self._track(DeviceRel.from_handle(self.ctx, out.value, [L.STR], [out_dict]))
+        index = max(list(source.columns) + [-1]) + 1
+        source.columns[index] = rel.cols[0]
+        return index
+
+    def _gather_column(self, source: _Source, index: int) -> DeviceColumn:
+        col = source.columns[index]
+        resolver = _ScanResolver(self, source)
+        prog = L.compile_project(resolver, [], [L.EInput(col.ltype, index)])
+        rel = self._scan_project(resolver, prog, [col.ltype])
+        return rel.cols[0]
+
+    def _scan_project(self, resolver: _ScanResolver, prog: L.ProjectProgram, ltypes: list[str]) -> DeviceRel:
+        desc = resolver.desc(prog.program)
+        out = C.c_void_p()
+        phys = N.int32_array(prog.out_phys)
+        self.ctx.call("msc_scan_project", C.byref(desc), phys, len(prog.out_phys), C.byref(out))
+        self._note_kernel()
+        return self._track(DeviceRel.from_handle(self.ctx, out.value, ltypes, prog.out_dicts))
+
+    def _note_kernel(self) -> None:
+        st = self.ctx.stats()
+        self.last_stats["kernel_ms"] = st.last_kernel_ms
+        self.last_stats["scan_ms"] = st.last_scan_ms
+        self.last_stats["scan_grid"] = st.last_scan_grid
+        self.last_stats["scan_stages"] = st.last_scan_stages
+        self.last_stats["scan_smem"] = st.last_scan_smem
+        self.last_stats["launches"] = st.launches
+
+    def _run_select(self, sel: L.LSelect, translate_targets: Optional[dict[str, DictHandle]] = None) -> DeviceRel:
+        nf = len(sel.filters)
+        source, exprs = self._prepare(sel.child, [*sel.filters, *sel.outputs])
+        filters, outputs = exprs[:nf], exprs[nf:]
+        resolver = _ScanResolver(self, source, translate_targets)
+        prog = L.compile_project(resolver, filters, outputs)
+        rel = self._scan_project(resolver, prog, [e.type for e in outputs])
+        rel.keep.extend(source.keep)
+        return rel
+
+    def _run_aggregate(self, agg: L.LAggregate) -> DeviceRel:
+        child = agg.child
+        if isinstance(child, L.LSelect):  # fuse the filter / projection below the aggregate into the same scan
+            filters = list(child.filters)
+            group = L.substitute(agg.group, child.outputs)
+            aggs = [(k, L.substitute(e, child.outputs)) for k, e in agg.aggs]
+            base = child.child
+        else:
+            filters, group, aggs, base = [], agg.group, list(agg.aggs), child
+        exprs = [*filters, group, *[e for _, e in aggs]]
+        source, exprs = self._prepare(base, exprs)
+        nf = len(filters)
+        filters, group = exprs[:nf], exprs[nf]
+        aggs = [(k, e) for (k, _), e in zip(aggs, exprs[nf + 1:])]
+        resolver = _ScanResolver(self, source)
+        prog = L.compile_aggregate(resolver, filters, group, aggs)
+        ngroups = 0
+        hint = 0
+        if prog.group_dict is not None:
+            size = prog.group_dict.size
+            if size > 0 and (size + 1) * (len(prog.agg_kinds) + 1) <= DENSE_MAX_CELLS:
+                ngroups = size
+            hint = max(size, 1)
+        desc = resolver.desc(prog.program)
+        kinds = N.int32_array(prog.agg_kinds)
+        out = C.c_void_p()
+        self.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), hint, C.byref(out))
+        self._note_kernel()
+        self.last_stats["agg_mode"] = "dense" if ngroups else "hash"
+        # raw result: key + one column per unique accumulator slot; expose it in the aggregate's schema order
+        slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog.agg_kinds]
+        raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
+        key = raw.cols[0]
+        if group.type == L.FLOAT and key.phys == N.P_I64:
+            key = DeviceColumn(key.ptr, N.P_F64, L.FLOAT)  # hash mode stores the f64 bit pattern
+        cols = [key] + [raw.cols[1 + s] for s in prog.slot_of]
+        return DeviceRel(self.ctx, None, raw.nrows, cols, keep=[raw, *source.keep])
+
+    def _join_source(self, join: L.LJoin, needed: set[int]) -> _Source:
+        nl = len(join.left.schema)
+        left_needed = sorted(i for i in needed if i < nl)
+        right_needed = sorted(i - nl for i in needed if i >= nl)
+
+        def side(node: L.LNode, idxs: list[int], key: L.Expr, targets: Optional[dict[str, DictHandle]]) -> DeviceRel:
+            outs = [L.EInput(_LTYPE_OF[node.schema[i][1]], i) for i in idxs]
+            key_out = L.ECode(L.INT, key) if key.type == L.STR else key
+            schema = [node.schema[i] for i in idxs] + [("__key", ColumnType.INTEGER)]
+            sel = L.fuse_selects(L.LSelect(schema, node, [], [*outs, key_out]))
+            return self._run_select(sel, targets)
+
+        lrel = side(join.left, left_needed, join.left_key, None)
+        targets = None
+        rkey = join.right_key
+        if rkey.type == L.STR:  # both sides must be coded in one dictionary: recode the right key into the left's
+            targets = {"join": lrel.cols[-1].dict}
+            rkey = L.ETranslate(L.STR, rkey, "join")
+        rrel = side(join.right, right_needed, rkey, targets)
+        pairs = C.c_void_p()
+        self.ctx.call("msc_hash_join", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.c_void_p(rrel.cols[-1].ptr), rrel.nrows, C.byref(pairs))
+        self._note_kernel()
+        prel = self._track(DeviceRel.from_handle(self.ctx, pairs.value, [L.INT, L.INT], [None, None]))
+        columns: dict[int, DeviceColumn] = {}
+        for pos, i in enumerate(left_needed):
+            c = lrel.cols[pos]
+            columns[i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via=0)
+        for pos, i in enumerate(right_needed):
+            c = rrel.cols[pos]
+            columns[nl + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via=1)
+        return _Source(prel.nrows, columns, index_vectors=[prel.cols[0], prel.cols[1]], keep=[lrel, rrel, prel])
