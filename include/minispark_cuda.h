@@ -60,47 +60,51 @@ extern "C" {
 #define MSC_LAYOUT_NATIVE 0 /* disk widths: i32 / f32 / i64 / narrowest dictionary code */
 #define MSC_LAYOUT_WIDE 1   /* BASELINE.json north_star widths: i64 / f64 / i64 / u32 code */
 
-/* ---- expression program opcodes (one u32 per instruction: op | depth<<8 | arg<<16) -------- *
- * The program is a postfix stack machine whose stack depth at every instruction is static and
- * encoded in the instruction, so each stack slot is a fixed register of the scan kernel.
- * It replaces the reference's per-row tree interpreter (`Col.execute_row`, sql.py:127-128,
- * 192-194,262-266,371-372) and the generated Zig condition/projection functions
- * (templates/plan.zig:62-75,80-103).  Python parses this enum (minispark_b200/native.py).   */
+/* ---- expression program ----------------------------------------------------------------- *
+ * A scan evaluates a short three-address program for every row.  It replaces the reference's
+ * per-row tree interpreter (`Col.execute_row`, sql.py:127-128,192-194,262-266,371-372) and the
+ * generated Zig condition/projection functions (templates/plan.zig:62-75,80-103).
+ *
+ * One instruction is two u32 words:
+ *   w0 = op | dst_kind << 8 | tee << 12 | dst_index << 16
+ *   w1 = operand A | operand B << 16        operand = index | src_kind << 12 | i2f << 15
+ * result = op(A, B); it goes to `dst` and, when tee != 0, also to temporary tee-1.
+ * Values are 64-bit: i64 (INTEGER, TIMESTAMP, booleans, dictionary codes) or f64 (FLOAT).
+ * Temporaries are per-thread slots in shared memory, so no interpreter state lives in registers
+ * between instructions.  Python parses these names (minispark_b200/native.py).               */
 enum msc_opcode {
   MSC_OP_END = 0,
-  /* push a column value of the current row; arg = staged column slot */
-  MSC_OP_LOAD_U8 = 1, MSC_OP_LOAD_U16 = 2, MSC_OP_LOAD_U32 = 3, MSC_OP_LOAD_I32 = 4,
-  MSC_OP_LOAD_I64 = 5, MSC_OP_LOAD_F32 = 6, MSC_OP_LOAD_F64 = 7,
-  /* push column[index[row]]; arg = staged index slot | gather column slot << 8 (late-materialised join) */
-  MSC_OP_LOADG_U8 = 8, MSC_OP_LOADG_U16 = 9, MSC_OP_LOADG_U32 = 10, MSC_OP_LOADG_I32 = 11,
-  MSC_OP_LOADG_I64 = 12, MSC_OP_LOADG_F32 = 13, MSC_OP_LOADG_F64 = 14,
-  MSC_OP_CONST = 15, /* push consts[arg] (64-bit pattern: i64 or f64) */
-  MSC_OP_I2F = 16,   /* top: i64 -> f64 (INT->FLOAT coercion, sql.py:277-290) */
-  MSC_OP_I2F_1 = 17, /* second-from-top: i64 -> f64 */
-  MSC_OP_ADD_F = 18, MSC_OP_SUB_F = 19, MSC_OP_MUL_F = 20, MSC_OP_DIV_F = 21,
-  MSC_OP_FLOORDIV_F = 22, MSC_OP_MOD_F = 23,
-  MSC_OP_ADD_I = 24, MSC_OP_SUB_I = 25, MSC_OP_MUL_I = 26, MSC_OP_FLOORDIV_I = 27, MSC_OP_MOD_I = 28,
-  MSC_OP_LT_F = 29, MSC_OP_LE_F = 30, MSC_OP_GT_F = 31, MSC_OP_GE_F = 32, MSC_OP_EQ_F = 33, MSC_OP_NE_F = 34,
-  MSC_OP_LT_I = 35, MSC_OP_LE_I = 36, MSC_OP_GT_I = 37, MSC_OP_GE_I = 38, MSC_OP_EQ_I = 39, MSC_OP_NE_I = 40,
-  MSC_OP_AND = 41, MSC_OP_OR = 42,
-  MSC_OP_LUT8 = 43,  /* top = luts[arg][top] (u8 table: LIKE / IN over dictionary codes) */
-  MSC_OP_LUT32 = 44, /* top = luts[arg][top] (u32 table: code translation between dictionaries) */
-  MSC_OP_TEE = 45,   /* temps[arg] = top (no pop): common sub-expression */
-  MSC_OP_GET = 46,   /* push temps[arg] */
-  MSC_OP_FILTER = 47, /* pop; row stays valid only if non-zero (FilterTask, tasks.py:167-177) */
-  MSC_OP_GROUP = 48,  /* pop; group id (dense mode) or 64-bit group key (hash mode) */
-  /* pop and fold into accumulator slot `arg` of the row's group (AggregateTask.fill_aggregators, tasks.py:293-310) */
-  MSC_OP_AGG_SUM_F = 49, MSC_OP_AGG_SUM_I = 50, MSC_OP_AGG_MIN_F = 51, MSC_OP_AGG_MAX_F = 52,
-  MSC_OP_AGG_MIN_I = 53, MSC_OP_AGG_MAX_I = 54,
-  MSC_OP_AGG_COUNT = 55, /* no pop: accumulator += 1 (Functions.count = SUM(Lit 1), sql.py:463-464) */
-  MSC_OP_RANK = 56,      /* project mode: compute each valid row's stable output position */
-  MSC_OP_STORE_I64 = 57, MSC_OP_STORE_F64 = 58, MSC_OP_STORE_U32 = 59, /* pop -> out column arg */
-  MSC_OP__COUNT = 60
+  MSC_OP_MOV = 1, /* result = A */
+  MSC_OP_ADD_F = 2, MSC_OP_SUB_F = 3, MSC_OP_MUL_F = 4, MSC_OP_DIV_F = 5, MSC_OP_FLOORDIV_F = 6, MSC_OP_MOD_F = 7,
+  MSC_OP_ADD_I = 8, MSC_OP_SUB_I = 9, MSC_OP_MUL_I = 10, MSC_OP_FLOORDIV_I = 11, MSC_OP_MOD_I = 12,
+  MSC_OP_LT_F = 13, MSC_OP_LE_F = 14, MSC_OP_GT_F = 15, MSC_OP_GE_F = 16, MSC_OP_EQ_F = 17, MSC_OP_NE_F = 18,
+  MSC_OP_LT_I = 19, MSC_OP_LE_I = 20, MSC_OP_GT_I = 21, MSC_OP_GE_I = 22, MSC_OP_EQ_I = 23, MSC_OP_NE_I = 24,
+  MSC_OP_AND = 25, MSC_OP_OR = 26,
+  MSC_OP_LUT8 = 27,  /* result = luts[B.index][A]  (u8 table: LIKE over dictionary codes) */
+  MSC_OP_LUT32 = 28, /* result = luts[B.index][A]  (u32 table: code translation between dictionaries) */
+  MSC_OP_RANK = 29,  /* no operands: fix each surviving row's stable output position (project scans) */
+  MSC_OP__COUNT = 30
 };
 
-#define MSC_VM_MAX_DEPTH 6   /* stack slots */
-#define MSC_VM_MAX_TEMPS 2   /* TEE/GET temporaries */
-#define MSC_VM_MAX_CODE 192  /* instructions */
+/* operand (source) kinds */
+#define MSC_SRC_NONE 0
+#define MSC_SRC_TEMP 1   /* temporary `index` */
+#define MSC_SRC_STAGED 2 /* staged column `index` of the current row (converted from its physical type) */
+#define MSC_SRC_CONST 3  /* consts[index] */
+#define MSC_SRC_GATHER 4 /* gather column (index & 63) read through staged index vector (index >> 6) */
+#define MSC_SRC_LUT 5    /* luts[index]: only as operand B of LUT8 / LUT32 */
+#define MSC_SRC_I2F 8    /* flag: convert the fetched i64 to f64 (INT->FLOAT coercion, sql.py:277-290) */
+
+/* destination kinds */
+#define MSC_DST_TEMP 0   /* temporary dst_index */
+#define MSC_DST_FILTER 1 /* row stays valid only if result != 0 (FilterTask, tasks.py:167-177) */
+#define MSC_DST_GROUP 2  /* result is the dense group id, or the 64-bit group key in hash mode */
+#define MSC_DST_AGG 3    /* fold result into accumulator dst_index of the row's group (tasks.py:293-310) */
+#define MSC_DST_OUT 4    /* write result to output column dst_index at the row's output position */
+#define MSC_DST_NONE 5
+
+#define MSC_VM_MAX_TEMPS 8
+#define MSC_VM_MAX_CODE 192  /* u32 words = 96 instructions */
 #define MSC_VM_MAX_CONSTS 32
 #define MSC_VM_MAX_STAGED 12 /* directly scanned columns (incl. index vectors) */
 #define MSC_VM_MAX_GATHER 16 /* columns read through an index vector */
@@ -136,12 +140,12 @@ typedef struct msc_scan_desc {
   int32_t ngather;
   msc_colbind staged[MSC_VM_MAX_STAGED];
   msc_colbind gather[MSC_VM_MAX_GATHER];
-  int32_t ncode;
+  int32_t ncode;   /* u32 words, two per instruction */
   int32_t nconsts;
   uint32_t code[MSC_VM_MAX_CODE];
   int64_t consts[MSC_VM_MAX_CONSTS];
   int32_t nluts;
-  int32_t _pad;
+  int32_t ntemps;  /* temporaries the program uses */
   const void* luts[MSC_VM_MAX_LUTS];
 } msc_scan_desc;
 
@@ -200,15 +204,15 @@ MSC_API int msc_rel_wrap(msc_ctx* ctx, uint64_t nrows, const msc_colbind* cols, 
 /* ---- fused scan -> filter -> project -> aggregate: replaces FilterTask.execute
  * (tasks.py:167-177), ProjectTask.execute (tasks.py:79-84), AggregateTask.execute
  * (tasks.py:270-310) and the generated Zig consumers (templates/plan.zig:113-253). ----------- */
-/* Dense mode (ngroups > 0): GROUP pops a group id in [0, ngroups).  Hash mode (ngroups == 0):
- * GROUP pops an arbitrary 64-bit key; `hash_capacity_hint` bounds the number of distinct keys
+/* Dense mode (ngroups > 0): MSC_DST_GROUP receives a group id in [0, ngroups).  Hash mode
+ * (ngroups == 0): it receives an arbitrary 64-bit key; `hash_capacity_hint` bounds the distinct keys
  * (0 = nrows).  Output relation: column 0 = group id (U32) or key (I64), columns 1..naggs =
  * accumulators (I64 / F64), one row per group that received at least one row. */
 MSC_API int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups,
                        const int32_t* agg_kinds, int32_t naggs, uint64_t hash_capacity_hint,
                        msc_rel** out);
 /* Filter + project with stable compaction (output keeps input order, tasks.py:177).  Output
- * column i is written by the program's STORE_* with arg i; out_phys[i] in {I64,F64,U32}. */
+ * column i is written by the instructions whose destination is MSC_DST_OUT i; out_phys[i] in {I64,F64,U32}. */
 MSC_API int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* out_phys,
                      int32_t nout, msc_rel** out);
 

@@ -18,8 +18,6 @@
 namespace {
 
 constexpr int NT = 128;  // threads per CTA
-constexpr int D = MSC_VM_MAX_DEPTH;
-constexpr int T = MSC_VM_MAX_TEMPS;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_HEADER = 128;  // mbarriers [0,64) + block-scan scratch [64,128)
 
@@ -29,6 +27,8 @@ struct StagedCol {
   const unsigned char* base;
   uint32_t width;
   uint32_t smem_off;
+  int phys;
+  int _pad;
 };
 
 struct ScanParams {
@@ -37,8 +37,10 @@ struct ScanParams {
   uint32_t nstages;
   uint32_t stage_bytes;
   uint32_t nstaged;
+  uint32_t ntemps;
   StagedCol staged[MSC_VM_MAX_STAGED];
   const void* gather[MSC_VM_MAX_GATHER];
+  int gather_phys[MSC_VM_MAX_GATHER];
   const void* luts[MSC_VM_MAX_LUTS];
   uint32_t code[MSC_VM_MAX_CODE];
   long long consts[MSC_VM_MAX_CONSTS];
@@ -57,6 +59,7 @@ struct ScanParams {
   uint32_t* tile_counts;
   const uint64_t* tile_offsets;  // nullptr: no filter, output position = row
   void* out[MSC_VM_MAX_OUT];
+  int out_phys[MSC_VM_MAX_OUT];
 };
 
 constexpr unsigned long long HASH_EMPTY = 0x8000000000000000ULL;
@@ -342,17 +345,6 @@ __device__ __forceinline__ void atomic_fold(int kind, unsigned long long* addr, 
   }
 }
 
-// per-thread shared-memory accumulators: acc[(g * naggs + a) * NT + tid]
-template <int R, int KIND>
-__device__ __forceinline__ void agg_dense(long long* acc, int naggs, int a, int tid, const int (&grp)[R],
-                                          const long long (&v)[R]) {
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    long long* q = acc + (grp[r] * naggs + a) * NT + tid;
-    *q = agg_combine(KIND, *q, v[r]);
-  }
-}
-
 template <int R, int KIND>
 __device__ __forceinline__ void agg_hash(unsigned long long* haccs, uint64_t hcap, int a, const int (&grp)[R],
                                          const long long (&v)[R]) {
@@ -416,37 +408,116 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-op helpers: every array argument is a stack slot selected with a compile-time index
+// instruction pieces: fetch operands -> compute -> store.  All per-row arrays are indexed with
+// unrolled compile-time constants, so they are registers that live for one instruction only.
 // ------------------------------------------------------------------------------------------------
 template <int R>
-__device__ __forceinline__ void op_const(long long (&dst)[R], long long c) {
+__device__ __forceinline__ void fetch(const ScanParams& p, const unsigned char* sbase, const long long* temps,
+                                      uint32_t operand, int tid, uint32_t vmask, long long (&v)[R]) {
+  const int kind = (operand >> 12) & 7;
+  const int idx = operand & 0xfff;
+  switch (kind) {
+    case MSC_SRC_TEMP: {
+      const long long* t = temps + (idx * R) * NT + tid;
 #pragma unroll
-  for (int r = 0; r < R; ++r) dst[r] = c;
-}
-template <int R>
-__device__ __forceinline__ void op_copy(long long (&dst)[R], const long long (&src)[R]) {
+      for (int r = 0; r < R; ++r) v[r] = t[r * NT];
+    } break;
+    case MSC_SRC_STAGED: {
+      const unsigned char* col = sbase + p.staged[idx].smem_off;
+      switch (p.staged[idx].phys) {
+        case MSC_P_U8: load_staged<R, MSC_P_U8>(col, tid, v); break;
+        case MSC_P_U16: load_staged<R, MSC_P_U16>(col, tid, v); break;
+        case MSC_P_U32: load_staged<R, MSC_P_U32>(col, tid, v); break;
+        case MSC_P_I32: load_staged<R, MSC_P_I32>(col, tid, v); break;
+        case MSC_P_F32: load_staged<R, MSC_P_F32>(col, tid, v); break;
+        default: load_staged<R, MSC_P_I64>(col, tid, v); break;  // I64 and F64: raw 64-bit pattern
+      }
+    } break;
+    case MSC_SRC_CONST: {
+      const long long c = p.consts[idx];
 #pragma unroll
-  for (int r = 0; r < R; ++r) dst[r] = src[r];
-}
-template <int R>
-__device__ __forceinline__ void op_i2f(long long (&x)[R]) {
+      for (int r = 0; r < R; ++r) v[r] = c;
+    } break;
+    case MSC_SRC_GATHER: {
+      const unsigned char* ix = sbase + p.staged[idx >> 6].smem_off;
+      const void* col = p.gather[idx & 63];
+      switch (p.gather_phys[idx & 63]) {
+        case MSC_P_U8: load_gather<R, MSC_P_U8>(ix, col, tid, vmask, v); break;
+        case MSC_P_U16: load_gather<R, MSC_P_U16>(ix, col, tid, vmask, v); break;
+        case MSC_P_U32: load_gather<R, MSC_P_U32>(ix, col, tid, vmask, v); break;
+        case MSC_P_I32: load_gather<R, MSC_P_I32>(ix, col, tid, vmask, v); break;
+        case MSC_P_F32: load_gather<R, MSC_P_F32>(ix, col, tid, vmask, v); break;
+        default: load_gather<R, MSC_P_I64>(ix, col, tid, vmask, v); break;
+      }
+    } break;
+    default: {
 #pragma unroll
-  for (int r = 0; r < R; ++r) x[r] = d2l(static_cast<double>(x[r]));
+      for (int r = 0; r < R; ++r) v[r] = 0;
+    } break;
+  }
+  if (operand & 0x8000u) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = d2l(static_cast<double>(v[r]));
+  }
 }
+
 template <int R, class TLut>
 __device__ __forceinline__ void op_lut(long long (&x)[R], const TLut* lut, uint32_t vmask) {
 #pragma unroll
   for (int r = 0; r < R; ++r) x[r] = ((vmask >> r) & 1u) ? static_cast<long long>(__ldg(lut + x[r])) : 0;
 }
+
 template <int R>
-__device__ __forceinline__ void op_filter(const long long (&x)[R], uint32_t& vmask) {
+__device__ __forceinline__ void store_temp(long long* temps, int idx, int tid, const long long (&v)[R]) {
+  long long* t = temps + (idx * R) * NT + tid;
 #pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (x[r] == 0) vmask &= ~(1u << r);
+  for (int r = 0; r < R; ++r) t[r * NT] = v[r];
 }
+
+// dense aggregation: per-thread shared-memory accumulators acc[(g * naggs + a) * NT + tid]
 template <int R>
-__device__ __forceinline__ void op_group_dense(const long long (&x)[R], uint32_t vmask, int ngroups, int naggs,
-                                               long long* acc, int tid, int (&grp)[R]) {
+__device__ __forceinline__ void agg_dense(long long* acc, int naggs, int a, int kind, int tid, const int (&grp)[R],
+                                          const long long (&v)[R]) {
+  switch (kind) {
+#define DENSE_CASE(KIND)                                       \
+  case KIND: {                                                 \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) {            \
+      long long* q = acc + (grp[r] * naggs + a) * NT + tid;    \
+      *q = agg_combine(KIND, *q, v[r]);                        \
+    }                                                          \
+  } break;
+    DENSE_CASE(MSC_AGG_SUM_F)
+    DENSE_CASE(MSC_AGG_SUM_I)
+    DENSE_CASE(MSC_AGG_MIN_F)
+    DENSE_CASE(MSC_AGG_MAX_F)
+    DENSE_CASE(MSC_AGG_MIN_I)
+    default: {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        long long* q = acc + (grp[r] * naggs + a) * NT + tid;
+        *q = agg_combine(MSC_AGG_MAX_I, *q, v[r]);
+      }
+    } break;
+#undef DENSE_CASE
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void agg_hash_any(unsigned long long* haccs, uint64_t hcap, int a, int kind, const int (&grp)[R],
+                                             const long long (&v)[R]) {
+  switch (kind) {
+    case MSC_AGG_SUM_F: agg_hash<R, MSC_AGG_SUM_F>(haccs, hcap, a, grp, v); break;
+    case MSC_AGG_SUM_I: agg_hash<R, MSC_AGG_SUM_I>(haccs, hcap, a, grp, v); break;
+    case MSC_AGG_MIN_F: agg_hash<R, MSC_AGG_MIN_F>(haccs, hcap, a, grp, v); break;
+    case MSC_AGG_MAX_F: agg_hash<R, MSC_AGG_MAX_F>(haccs, hcap, a, grp, v); break;
+    case MSC_AGG_MIN_I: agg_hash<R, MSC_AGG_MIN_I>(haccs, hcap, a, grp, v); break;
+    default: agg_hash<R, MSC_AGG_MAX_I>(haccs, hcap, a, grp, v); break;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void group_dense(const long long (&x)[R], uint32_t vmask, int ngroups, int naggs, long long* acc,
+                                            int tid, int (&grp)[R]) {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int g = ngroups;  // rows that failed the filter fold into a trash group that is never exported
@@ -458,9 +529,10 @@ __device__ __forceinline__ void op_group_dense(const long long (&x)[R], uint32_t
     acc[(g * naggs + (naggs - 1)) * NT + tid] += 1;  // hidden per-group row counter
   }
 }
+
 template <int R>
-__device__ __forceinline__ void op_group_hash(const long long (&x)[R], uint32_t vmask, unsigned long long* hkeys,
-                                              uint64_t hcap, int* err, int (&grp)[R]) {
+__device__ __forceinline__ void group_hash(const long long (&x)[R], uint32_t vmask, unsigned long long* hkeys, uint64_t hcap,
+                                           int* err, int (&grp)[R]) {
   long long prev_key = 0;
   int prev_slot = -1;
 #pragma unroll
@@ -476,19 +548,16 @@ __device__ __forceinline__ void op_group_hash(const long long (&x)[R], uint32_t 
     grp[r] = slot;
   }
 }
-template <int R>
-__device__ __forceinline__ void op_rank_project(uint32_t vmask, uint64_t pos, uint64_t (&rank)[R]) {
+
+template <int R, class TOut>
+__device__ __forceinline__ void store_out(const long long (&x)[R], TOut* out, uint64_t pos, uint32_t vmask) {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    rank[r] = pos;
-    pos += (vmask >> r) & 1u;
+    if ((vmask >> r) & 1u) {
+      out[pos] = static_cast<TOut>(x[r]);
+      ++pos;
+    }
   }
-}
-template <int R, class TOut>
-__device__ __forceinline__ void op_store(const long long (&x)[R], TOut* out, const uint64_t (&rank)[R], uint32_t vmask) {
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if ((vmask >> r) & 1u) out[rank[r]] = static_cast<TOut>(x[r]);
 }
 
 template <int R>
@@ -507,53 +576,16 @@ __device__ __forceinline__ void issue_tile(const ScanParams& p, unsigned char* s
 }
 
 // ------------------------------------------------------------------------------------------------
-// depth dispatch: turns the runtime stack depth into compile-time slot indices
-// ------------------------------------------------------------------------------------------------
-#define MSC_PUSH_CASE(N, ...) \
-  case N: {                   \
-    constexpr int DD = N;     \
-    __VA_ARGS__;              \
-  } break;
-#define SW_PUSH(...)                                                                          \
-  switch (d) {                                                                                \
-    MSC_PUSH_CASE(0, __VA_ARGS__) MSC_PUSH_CASE(1, __VA_ARGS__) MSC_PUSH_CASE(2, __VA_ARGS__) \
-    MSC_PUSH_CASE(3, __VA_ARGS__) MSC_PUSH_CASE(4, __VA_ARGS__) MSC_PUSH_CASE(5, __VA_ARGS__) \
-    default: break;                                                                           \
-  }
-#define MSC_TOP_CASE(N, ...)  \
-  case N: {                   \
-    constexpr int DD = N - 1; \
-    __VA_ARGS__;              \
-  } break;
-#define SW_TOP(...)                                                                        \
-  switch (d) {                                                                             \
-    MSC_TOP_CASE(1, __VA_ARGS__) MSC_TOP_CASE(2, __VA_ARGS__) MSC_TOP_CASE(3, __VA_ARGS__) \
-    MSC_TOP_CASE(4, __VA_ARGS__) MSC_TOP_CASE(5, __VA_ARGS__) MSC_TOP_CASE(6, __VA_ARGS__) \
-    default: break;                                                                        \
-  }
-#define MSC_BIN_CASE(N, ...)  \
-  case N: {                   \
-    constexpr int DA = N - 2; \
-    constexpr int DB = N - 1; \
-    __VA_ARGS__;              \
-  } break;
-#define SW_BIN(...)                                                                        \
-  switch (d) {                                                                             \
-    MSC_BIN_CASE(2, __VA_ARGS__) MSC_BIN_CASE(3, __VA_ARGS__) MSC_BIN_CASE(4, __VA_ARGS__) \
-    MSC_BIN_CASE(5, __VA_ARGS__) MSC_BIN_CASE(6, __VA_ARGS__)                              \
-    default: break;                                                                        \
-  }
-
-// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int R, int MODE>
-__global__ void __launch_bounds__(NT, (R <= 4 ? 3 : 2)) scan_kernel(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + 64);
   unsigned char* stages = smem + SMEM_HEADER;
-  long long* acc = reinterpret_cast<long long*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);
+  long long* temps = reinterpret_cast<long long*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);
+  long long* acc = temps + static_cast<size_t>(p.ntemps) * R * NT;
   constexpr int TILE = NT * R;
   const int tid = threadIdx.x;
 
@@ -573,15 +605,6 @@ __global__ void __launch_bounds__(NT, (R <= 4 ? 3 : 2)) scan_kernel(const __grid
     for (uint32_t k = 0; k < pre; ++k) issue_tile<R>(p, stages, full, k);
   }
 
-  long long s[D][R];
-  long long t[T][R];
-  int grp[R];
-  uint64_t rank[R];
-#pragma unroll
-  for (int i = 0; i < D; ++i) op_const<R>(s[i], 0);
-#pragma unroll
-  for (int i = 0; i < T; ++i) op_const<R>(t[i], 0);
-
   for (uint32_t k = 0; k < ntiles_cta; ++k) {
     const uint32_t stage = k % p.nstages;
     const uint32_t parity = (k / p.nstages) & 1u;
@@ -591,127 +614,68 @@ __global__ void __launch_bounds__(NT, (R <= 4 ? 3 : 2)) scan_kernel(const __grid
     }
     const uint64_t row0 = tile * TILE + static_cast<uint64_t>(tid) * R;
     uint32_t vmask = 0;
+    int grp[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (row0 + r < p.nrows) vmask |= 1u << r;
       grp[r] = (MODE == MODE_DENSE) ? p.ngroups : -1;
-      rank[r] = row0 + r;
     }
+    uint64_t out_pos = row0;  // project: output position of this thread's first surviving row
 
-    for (int pc = 0;; ++pc) {
-      const uint32_t w = p.code[pc];
-      const int op = w & 0xff;
-      const int d = (w >> 8) & 0xff;
-      const int a = w >> 16;
+    for (int pc = 0;; pc += 2) {
+      const uint32_t w0 = p.code[pc];
+      const int op = w0 & 0xff;
       if (op == MSC_OP_END) break;
-      switch (op) {
-#define LOAD_CASE(OP, PHYS) \
-  case OP: SW_PUSH(load_staged<R, PHYS>(sbase + p.staged[a].smem_off, tid, s[DD])) break;
-        LOAD_CASE(MSC_OP_LOAD_U8, MSC_P_U8)
-        LOAD_CASE(MSC_OP_LOAD_U16, MSC_P_U16)
-        LOAD_CASE(MSC_OP_LOAD_U32, MSC_P_U32)
-        LOAD_CASE(MSC_OP_LOAD_I32, MSC_P_I32)
-        LOAD_CASE(MSC_OP_LOAD_I64, MSC_P_I64)
-        LOAD_CASE(MSC_OP_LOAD_F32, MSC_P_F32)
-        LOAD_CASE(MSC_OP_LOAD_F64, MSC_P_F64)
-#undef LOAD_CASE
-#define LOADG_CASE(OP, PHYS)                                                                                  \
-  case OP:                                                                                                    \
-    SW_PUSH(load_gather<R, PHYS>(sbase + p.staged[a & 0xff].smem_off, p.gather[(a >> 8) & 0xff], tid, vmask, \
-                                 s[DD]))                                                                      \
-    break;
-        LOADG_CASE(MSC_OP_LOADG_U8, MSC_P_U8)
-        LOADG_CASE(MSC_OP_LOADG_U16, MSC_P_U16)
-        LOADG_CASE(MSC_OP_LOADG_U32, MSC_P_U32)
-        LOADG_CASE(MSC_OP_LOADG_I32, MSC_P_I32)
-        LOADG_CASE(MSC_OP_LOADG_I64, MSC_P_I64)
-        LOADG_CASE(MSC_OP_LOADG_F32, MSC_P_F32)
-        LOADG_CASE(MSC_OP_LOADG_F64, MSC_P_F64)
-#undef LOADG_CASE
-        case MSC_OP_CONST: SW_PUSH(op_const<R>(s[DD], p.consts[a])) break;
-        case MSC_OP_I2F: SW_TOP(op_i2f<R>(s[DD])) break;
-        case MSC_OP_I2F_1: SW_BIN(op_i2f<R>(s[DA])) break;
-        case MSC_OP_ADD_F: case MSC_OP_SUB_F: case MSC_OP_MUL_F: case MSC_OP_DIV_F:
-        case MSC_OP_FLOORDIV_F: case MSC_OP_MOD_F:
-        case MSC_OP_ADD_I: case MSC_OP_SUB_I: case MSC_OP_MUL_I: case MSC_OP_FLOORDIV_I: case MSC_OP_MOD_I:
-          SW_BIN(binop<R>(op, s[DA], s[DB], vmask, p.err))
-          break;
-        case MSC_OP_LT_F: case MSC_OP_LE_F: case MSC_OP_GT_F: case MSC_OP_GE_F: case MSC_OP_EQ_F: case MSC_OP_NE_F:
-        case MSC_OP_LT_I: case MSC_OP_LE_I: case MSC_OP_GT_I: case MSC_OP_GE_I: case MSC_OP_EQ_I: case MSC_OP_NE_I:
-        case MSC_OP_AND: case MSC_OP_OR:
-          SW_BIN(cmpop<R>(op, s[DA], s[DB]))
-          break;
-        case MSC_OP_LUT8: SW_TOP(op_lut<R, uint8_t>(s[DD], reinterpret_cast<const uint8_t*>(p.luts[a]), vmask)) break;
-        case MSC_OP_LUT32: SW_TOP(op_lut<R, uint32_t>(s[DD], reinterpret_cast<const uint32_t*>(p.luts[a]), vmask)) break;
-        case MSC_OP_TEE:
-          if (a == 0) {
-            SW_TOP(op_copy<R>(t[0], s[DD]))
-          } else {
-            SW_TOP(op_copy<R>(t[1], s[DD]))
-          }
-          break;
-        case MSC_OP_GET:
-          if (a == 0) {
-            SW_PUSH(op_copy<R>(s[DD], t[0]))
-          } else {
-            SW_PUSH(op_copy<R>(s[DD], t[1]))
-          }
-          break;
-        case MSC_OP_FILTER: SW_TOP(op_filter<R>(s[DD], vmask)) break;
-        case MSC_OP_GROUP:
-          if constexpr (MODE == MODE_DENSE) {
-            SW_TOP(op_group_dense<R>(s[DD], vmask, p.ngroups, p.naggs, acc, tid, grp))
-          } else if constexpr (MODE == MODE_HASH) {
-            SW_TOP(op_group_hash<R>(s[DD], vmask, p.hkeys, p.hcap, p.err, grp))
-          }
-          break;
-#define AGG_CASE(OP, KIND)                                           \
-  case OP:                                                           \
-    if constexpr (MODE == MODE_DENSE) {                              \
-      SW_TOP(agg_dense<R, KIND>(acc, p.naggs, a, tid, grp, s[DD]))   \
-    } else if constexpr (MODE == MODE_HASH) {                        \
-      SW_TOP(agg_hash<R, KIND>(p.haccs, p.hcap, a, grp, s[DD]))      \
-    }                                                                \
-    break;
-        AGG_CASE(MSC_OP_AGG_SUM_F, MSC_AGG_SUM_F)
-        AGG_CASE(MSC_OP_AGG_SUM_I, MSC_AGG_SUM_I)
-        AGG_CASE(MSC_OP_AGG_MIN_F, MSC_AGG_MIN_F)
-        AGG_CASE(MSC_OP_AGG_MAX_F, MSC_AGG_MAX_F)
-        AGG_CASE(MSC_OP_AGG_MIN_I, MSC_AGG_MIN_I)
-        AGG_CASE(MSC_OP_AGG_MAX_I, MSC_AGG_MAX_I)
-#undef AGG_CASE
-        case MSC_OP_AGG_COUNT:
-          if constexpr (MODE == MODE_DENSE) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[(grp[r] * p.naggs + a) * NT + tid] += 1;
-          } else if constexpr (MODE == MODE_HASH) {
-            long long ones[R];
-            op_const<R>(ones, 1);
-            agg_hash<R, MSC_AGG_SUM_I>(p.haccs, p.hcap, a, grp, ones);
-          }
-          break;
-        case MSC_OP_RANK:
-          if constexpr (MODE == MODE_COUNT) {
+      const uint32_t w1 = p.code[pc + 1];
+      if (op == MSC_OP_RANK) {
+        if constexpr (MODE == MODE_COUNT) {
+          uint32_t total;
+          (void)block_exclusive_scan(__popc(vmask), scratch, tid, &total);
+          if (tid == 0) p.tile_counts[tile] = total;
+        } else if constexpr (MODE == MODE_PROJECT) {
+          if (p.tile_offsets != nullptr) {
             uint32_t total;
-            (void)block_exclusive_scan(__popc(vmask), scratch, tid, &total);
-            if (tid == 0) p.tile_counts[tile] = total;
-          } else if constexpr (MODE == MODE_PROJECT) {
-            if (p.tile_offsets != nullptr) {
-              uint32_t total;
-              const uint32_t before = block_exclusive_scan(__popc(vmask), scratch, tid, &total);
-              op_rank_project<R>(vmask, p.tile_offsets[tile] + before, rank);
-            }
+            const uint32_t before = block_exclusive_scan(__popc(vmask), scratch, tid, &total);
+            out_pos = p.tile_offsets[tile] + before;
           }
+        }
+        continue;
+      }
+      long long a[R];
+      fetch<R>(p, sbase, temps, w1 & 0xffffu, tid, vmask, a);
+      if (op >= MSC_OP_ADD_F && op <= MSC_OP_OR) {
+        long long b[R];
+        fetch<R>(p, sbase, temps, w1 >> 16, tid, vmask, b);
+        if (op <= MSC_OP_MOD_I) binop<R>(op, a, b, vmask, p.err);
+        else cmpop<R>(op, a, b);
+      } else if (op == MSC_OP_LUT8) {
+        op_lut<R, uint8_t>(a, reinterpret_cast<const uint8_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
+      } else if (op == MSC_OP_LUT32) {
+        op_lut<R, uint32_t>(a, reinterpret_cast<const uint32_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
+      }
+      // ---- store -------------------------------------------------------------------------------
+      const int tee = (w0 >> 12) & 0xf;
+      if (tee) store_temp<R>(temps, tee - 1, tid, a);
+      const int dst = w0 >> 16;
+      switch ((w0 >> 8) & 0xf) {
+        case MSC_DST_TEMP: store_temp<R>(temps, dst, tid, a); break;
+        case MSC_DST_FILTER: {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (a[r] == 0) vmask &= ~(1u << r);
+        } break;
+        case MSC_DST_GROUP:
+          if constexpr (MODE == MODE_DENSE) group_dense<R>(a, vmask, p.ngroups, p.naggs, acc, tid, grp);
+          else if constexpr (MODE == MODE_HASH) group_hash<R>(a, vmask, p.hkeys, p.hcap, p.err, grp);
           break;
-        case MSC_OP_STORE_I64:
-        case MSC_OP_STORE_F64:
-          if constexpr (MODE == MODE_PROJECT) {
-            SW_TOP(op_store<R, long long>(s[DD], reinterpret_cast<long long*>(p.out[a]), rank, vmask))
-          }
+        case MSC_DST_AGG:
+          if constexpr (MODE == MODE_DENSE) agg_dense<R>(acc, p.naggs, dst, p.agg_kind[dst], tid, grp, a);
+          else if constexpr (MODE == MODE_HASH) agg_hash_any<R>(p.haccs, p.hcap, dst, p.agg_kind[dst], grp, a);
           break;
-        case MSC_OP_STORE_U32:
+        case MSC_DST_OUT:
           if constexpr (MODE == MODE_PROJECT) {
-            SW_TOP(op_store<R, uint32_t>(s[DD], reinterpret_cast<uint32_t*>(p.out[a]), rank, vmask))
+            if (p.out_phys[dst] == MSC_P_U32) store_out<R, uint32_t>(a, reinterpret_cast<uint32_t*>(p.out[dst]), out_pos, vmask);
+            else store_out<R, long long>(a, reinterpret_cast<long long*>(p.out[dst]), out_pos, vmask);
           }
           break;
         default: break;
@@ -923,53 +887,72 @@ struct LaunchPlan {
   int grid;
 };
 
+int validate_operand(msc_ctx* ctx, const msc_scan_desc* sd, uint32_t operand, bool allow_lut) {
+  const int kind = (operand >> 12) & 7, idx = operand & 0xfff;
+  switch (kind) {
+    case MSC_SRC_NONE: return MSC_OK;
+    case MSC_SRC_TEMP: return idx < sd->ntemps ? MSC_OK : ctx->fail(MSC_ERR_ARG, "operand: bad temporary");
+    case MSC_SRC_STAGED: return idx < sd->nstaged ? MSC_OK : ctx->fail(MSC_ERR_ARG, "operand: bad staged column");
+    case MSC_SRC_CONST: return idx < sd->nconsts ? MSC_OK : ctx->fail(MSC_ERR_ARG, "operand: bad constant");
+    case MSC_SRC_GATHER:
+      if ((idx & 63) >= sd->ngather || (idx >> 6) >= sd->nstaged) return ctx->fail(MSC_ERR_ARG, "operand: bad gather column");
+      if (sd->staged[idx >> 6].phys != MSC_P_U32) return ctx->fail(MSC_ERR_ARG, "operand: index vector must be U32");
+      return MSC_OK;
+    case MSC_SRC_LUT:
+      if (!allow_lut) return ctx->fail(MSC_ERR_ARG, "operand: LUT reference outside a LUT instruction");
+      return idx < sd->nluts ? MSC_OK : ctx->fail(MSC_ERR_ARG, "operand: bad LUT");
+    default: return ctx->fail(MSC_ERR_ARG, "operand: unknown kind");
+  }
+}
+
 int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, int naggs, int nout) {
   if (sd->ncode <= 0 || sd->ncode > MSC_VM_MAX_CODE) return ctx->fail(MSC_ERR_ARG, "program length out of range");
   if (sd->nstaged < 0 || sd->nstaged > MSC_VM_MAX_STAGED) return ctx->fail(MSC_ERR_ARG, "too many staged columns");
   if (sd->ngather < 0 || sd->ngather > MSC_VM_MAX_GATHER) return ctx->fail(MSC_ERR_ARG, "too many gather columns");
   if (sd->nconsts < 0 || sd->nconsts > MSC_VM_MAX_CONSTS) return ctx->fail(MSC_ERR_ARG, "too many constants");
   if (sd->nluts < 0 || sd->nluts > MSC_VM_MAX_LUTS) return ctx->fail(MSC_ERR_ARG, "too many LUTs");
+  if (sd->ntemps < 0 || sd->ntemps > MSC_VM_MAX_TEMPS) return ctx->fail(MSC_ERR_ARG, "too many temporaries");
   bool ended = false;
-  for (int pc = 0; pc < sd->ncode; ++pc) {
-    const uint32_t w = sd->code[pc];
-    const int op = w & 0xff, d = (w >> 8) & 0xff, a = w >> 16;
+  for (int pc = 0; pc < sd->ncode; pc += 2) {
+    const uint32_t w0 = sd->code[pc];
+    const int op = w0 & 0xff;
     if (op == MSC_OP_END) {
       ended = true;
       break;
     }
+    if (pc + 1 >= sd->ncode) return ctx->fail(MSC_ERR_ARG, "truncated instruction");
+    const uint32_t w1 = sd->code[pc + 1];
     if (op >= MSC_OP__COUNT) return ctx->fail(MSC_ERR_ARG, "unknown opcode");
-    int lo = 0, hi = D;  // valid depth range before the instruction
-    if ((op >= MSC_OP_LOAD_U8 && op <= MSC_OP_CONST) || op == MSC_OP_GET) hi = D - 1;
-    else if (op == MSC_OP_I2F || op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || op == MSC_OP_TEE || op == MSC_OP_FILTER ||
-             op == MSC_OP_GROUP || (op >= MSC_OP_AGG_SUM_F && op <= MSC_OP_AGG_MAX_I) ||
-             (op >= MSC_OP_STORE_I64 && op <= MSC_OP_STORE_U32))
-      lo = 1;
-    else if (op == MSC_OP_I2F_1 || (op >= MSC_OP_ADD_F && op <= MSC_OP_OR)) lo = 2;
-    if (d < lo || d > hi) return ctx->fail(MSC_ERR_ARG, "stack depth out of range in program");
-    if (op >= MSC_OP_LOAD_U8 && op <= MSC_OP_LOAD_F64) {
-      if (a >= sd->nstaged) return ctx->fail(MSC_ERR_ARG, "LOAD: bad staged column");
-      if (sd->staged[a].phys != op - MSC_OP_LOAD_U8) return ctx->fail(MSC_ERR_ARG, "LOAD: physical type mismatch");
+    if (op == MSC_OP_RANK) continue;
+    const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+    MSC_TRY(validate_operand(ctx, sd, w1 & 0xffffu, false));
+    MSC_TRY(validate_operand(ctx, sd, w1 >> 16, lut));
+    if (lut && ((w1 >> 28) & 7) != MSC_SRC_LUT) return ctx->fail(MSC_ERR_ARG, "LUT instruction needs a LUT operand");
+    const int tee = (w0 >> 12) & 0xf, dkind = (w0 >> 8) & 0xf, dst = w0 >> 16;
+    if (tee > sd->ntemps) return ctx->fail(MSC_ERR_ARG, "tee: bad temporary");
+    switch (dkind) {
+      case MSC_DST_TEMP:
+        if (dst >= sd->ntemps) return ctx->fail(MSC_ERR_ARG, "destination: bad temporary");
+        break;
+      case MSC_DST_FILTER: case MSC_DST_NONE: break;
+      case MSC_DST_GROUP:
+        if (mode != MODE_DENSE && mode != MODE_HASH) return ctx->fail(MSC_ERR_ARG, "GROUP outside an aggregate scan");
+        break;
+      case MSC_DST_AGG:
+        if (mode != MODE_DENSE && mode != MODE_HASH) return ctx->fail(MSC_ERR_ARG, "AGG outside an aggregate scan");
+        if (dst >= naggs) return ctx->fail(MSC_ERR_ARG, "AGG: bad accumulator");
+        break;
+      case MSC_DST_OUT:
+        if (dst >= nout) return ctx->fail(MSC_ERR_ARG, "OUT: bad column");
+        break;
+      default: return ctx->fail(MSC_ERR_ARG, "unknown destination kind");
     }
-    if (op >= MSC_OP_LOADG_U8 && op <= MSC_OP_LOADG_F64) {
-      const int si = a & 0xff, gi = (a >> 8) & 0xff;
-      if (si >= sd->nstaged || gi >= sd->ngather) return ctx->fail(MSC_ERR_ARG, "LOADG: bad column");
-      if (sd->staged[si].phys != MSC_P_U32) return ctx->fail(MSC_ERR_ARG, "LOADG: index vector must be U32");
-      if (sd->gather[gi].phys != op - MSC_OP_LOADG_U8) return ctx->fail(MSC_ERR_ARG, "LOADG: physical type mismatch");
-    }
-    if (op == MSC_OP_CONST && a >= sd->nconsts) return ctx->fail(MSC_ERR_ARG, "CONST: bad index");
-    if ((op == MSC_OP_LUT8 || op == MSC_OP_LUT32) && a >= sd->nluts) return ctx->fail(MSC_ERR_ARG, "LUT: bad index");
-    if ((op == MSC_OP_TEE || op == MSC_OP_GET) && a >= T) return ctx->fail(MSC_ERR_ARG, "TEE/GET: bad temp");
-    if (op >= MSC_OP_AGG_SUM_F && op <= MSC_OP_AGG_COUNT) {
-      if (mode != MODE_DENSE && mode != MODE_HASH) return ctx->fail(MSC_ERR_ARG, "AGG op outside aggregate scan");
-      if (a >= naggs) return ctx->fail(MSC_ERR_ARG, "AGG: bad slot");
-    }
-    if (op >= MSC_OP_STORE_I64 && op <= MSC_OP_STORE_U32 && a >= nout) return ctx->fail(MSC_ERR_ARG, "STORE: bad column");
   }
   if (!ended) return ctx->fail(MSC_ERR_ARG, "program has no END");
   return MSC_OK;
 }
 
-// Build kernel params + launch geometry.  extra_smem = bytes needed after the stage ring.
+// Build kernel params + launch geometry.  extra_smem = bytes needed after the stage ring and temporaries.
 int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem, LaunchPlan* lp) {
   ScanParams& p = lp->p;
   memset(&p, 0, sizeof(p));
@@ -977,6 +960,7 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
   p.nrows = sd->nrows;
   p.ntiles = static_cast<uint32_t>((sd->nrows + tile - 1) / tile);
   p.nstaged = sd->nstaged;
+  p.ntemps = sd->ntemps;
   uint32_t off = 0;
   for (int c = 0; c < sd->nstaged; ++c) {
     const size_t w = msc_phys_width(sd->staged[c].phys);
@@ -985,28 +969,32 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
     p.staged[c].base = static_cast<const unsigned char*>(sd->staged[c].data);
     p.staged[c].width = static_cast<uint32_t>(w);
     p.staged[c].smem_off = off;
+    p.staged[c].phys = sd->staged[c].phys;
     off += static_cast<uint32_t>(msc_round_up(w * tile, 128));
   }
   p.stage_bytes = off ? off : 128;
-  for (int c = 0; c < sd->ngather; ++c) p.gather[c] = sd->gather[c].data;
+  for (int c = 0; c < sd->ngather; ++c) {
+    if (msc_phys_width(sd->gather[c].phys) == 0 || sd->gather[c].data == nullptr) return ctx->fail(MSC_ERR_ARG, "bad gather column");
+    p.gather[c] = sd->gather[c].data;
+    p.gather_phys[c] = sd->gather[c].phys;
+  }
   for (int c = 0; c < sd->nluts; ++c) p.luts[c] = sd->luts[c];
   memcpy(p.code, sd->code, sizeof(uint32_t) * sd->ncode);
   if (sd->ncode < MSC_VM_MAX_CODE) p.code[sd->ncode] = MSC_OP_END;
   memcpy(p.consts, sd->consts, sizeof(int64_t) * sd->nconsts);
   p.err = ctx->d_err;
-  // stages: enough bytes in flight per SM (~3 CTAs x nstages x stage_bytes), within the smem budget
-  const size_t budget = 200 * 1024 / 3;  // per CTA when 3 CTAs share an SM
-  size_t avail = budget > extra_smem + SMEM_HEADER ? budget - extra_smem - SMEM_HEADER : 0;
-  uint32_t ns = static_cast<uint32_t>(avail / p.stage_bytes);
-  if (ns > MAX_STAGES) ns = MAX_STAGES;
+  const size_t temps_bytes = static_cast<size_t>(sd->ntemps) * tile * sizeof(long long);
+  const size_t fixed = SMEM_HEADER + temps_bytes + extra_smem;
+  // ring depth: target 3 CTAs per SM (about 72 KB each) and >= 2 stages; MSC_SCAN_STAGES overrides
+  static const int forced = getenv("MSC_SCAN_STAGES") ? atoi(getenv("MSC_SCAN_STAGES")) : 0;
+  const size_t budget = 72 * 1024;
+  uint32_t ns = budget > fixed ? static_cast<uint32_t>((budget - fixed) / p.stage_bytes) : 0;
+  if (ns > 4) ns = 4;
   if (ns < 2) ns = 2;
-  if (ns > 4 && static_cast<size_t>(ns) * p.stage_bytes > 40 * 1024) {
-    ns = static_cast<uint32_t>((40 * 1024) / p.stage_bytes);
-    if (ns < 4) ns = 4;
-  }
+  if (forced >= 1 && forced <= MAX_STAGES) ns = static_cast<uint32_t>(forced);
   p.nstages = ns;
   lp->R = R;
-  lp->smem = SMEM_HEADER + static_cast<size_t>(ns) * p.stage_bytes + extra_smem;
+  lp->smem = fixed + static_cast<size_t>(ns) * p.stage_bytes;
   if (lp->smem > 227 * 1024) return ctx->fail(MSC_ERR_ARG, "scan needs more shared memory than an SM has");
   lp->grid = 0;
   return MSC_OK;
@@ -1225,10 +1213,10 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
   const int R = pick_rows_per_thread();
   bool has_filter = false;
   int rank_pc = -1;
-  for (int pc = 0; pc < sd->ncode; ++pc) {
+  for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
     const int op = sd->code[pc] & 0xff;
     if (op == MSC_OP_END) break;
-    if (op == MSC_OP_FILTER) has_filter = true;
+    if (((sd->code[pc] >> 8) & 0xf) == MSC_DST_FILTER && op != MSC_OP_RANK) has_filter = true;
     if (op == MSC_OP_RANK) rank_pc = pc;
   }
   if (has_filter && rank_pc < 0) return ctx->fail(MSC_ERR_ARG, "filtered projection needs a RANK instruction");
@@ -1240,7 +1228,7 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
   if (has_filter && sd->nrows > 0) {
     // pass 1: rows surviving per tile (program truncated after RANK)
     LaunchPlan cp = lp;
-    cp.p.code[rank_pc + 1] = MSC_OP_END;
+    cp.p.code[rank_pc + 2] = MSC_OP_END;
     MSC_TRY(counts.alloc(sizeof(uint32_t) * cp.p.ntiles));
     MSC_TRY(offsets.alloc(sizeof(uint64_t) * (cp.p.ntiles + 1)));
     cp.p.tile_counts = counts.as<uint32_t>();
@@ -1260,6 +1248,7 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
       return rc;
     }
     lp.p.out[i] = rel->cols[i].data;
+    lp.p.out_phys[i] = out_phys[i];
   }
   if (sd->nrows > 0 && nout_rows > 0 && nout > 0) {
     int rc = launch_scan_r<MODE_PROJECT>(ctx, &lp);

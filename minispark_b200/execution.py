@@ -307,6 +307,7 @@ class _ScanResolver:
         for i, c in enumerate(program.consts):
             d.consts[i] = c
         d.nluts = len(self.luts)
+        d.ntemps = program.ntemps
         for i, ptr in enumerate(self.luts):
             d.luts[i] = ptr
         return d

@@ -505,51 +505,72 @@ class Resolver(Protocol):
     def recode_lut(self, src: Any, dst: Any) -> int: ...                  # LUT slot: codes of src -> codes of dst
 
 
-_LOAD = {P_U8: "LOAD_U8", P_U16: "LOAD_U16", P_U32: "LOAD_U32", P_I32: "LOAD_I32", P_I64: "LOAD_I64", P_F32: "LOAD_F32",
-         P_F64: "LOAD_F64"}
+MAX_TEMPS = K["MSC_VM_MAX_TEMPS"]
 _F_OPS = {"add": "ADD_F", "sub": "SUB_F", "mul": "MUL_F", "truediv": "DIV_F", "floordiv": "FLOORDIV_F", "mod": "MOD_F",
           "lt": "LT_F", "le": "LE_F", "gt": "GT_F", "ge": "GE_F", "eq": "EQ_F", "ne": "NE_F"}
 _I_OPS = {"add": "ADD_I", "sub": "SUB_I", "mul": "MUL_I", "floordiv": "FLOORDIV_I", "mod": "MOD_I",
           "lt": "LT_I", "le": "LE_I", "gt": "GT_I", "ge": "GE_I", "eq": "EQ_I", "ne": "NE_I", "and": "AND", "or": "OR"}
-MAX_DEPTH = K["MSC_VM_MAX_DEPTH"]
-MAX_TEMPS = K["MSC_VM_MAX_TEMPS"]
+SRC_TEMP, SRC_STAGED, SRC_CONST, SRC_GATHER, SRC_LUT = (K[f"MSC_SRC_{n}"] for n in ("TEMP", "STAGED", "CONST", "GATHER", "LUT"))
+SRC_I2F = K["MSC_SRC_I2F"]
+DST_TEMP, DST_FILTER, DST_GROUP, DST_AGG, DST_OUT, DST_NONE = (K[f"MSC_DST_{n}"] for n in ("TEMP", "FILTER", "GROUP", "AGG", "OUT", "NONE"))
+_DST_NAME = {DST_TEMP: "t", DST_FILTER: "filter", DST_GROUP: "group", DST_AGG: "agg", DST_OUT: "out", DST_NONE: "none"}
+_SRC_NAME = {SRC_TEMP: "t", SRC_STAGED: "col", SRC_CONST: "const", SRC_GATHER: "gather", SRC_LUT: "lut", 0: "-"}
 
 
 def f64_bits(x: float) -> int:
     return struct.unpack("<q", struct.pack("<d", float(x)))[0]
 
 
+def src(kind: int, index: int, i2f: bool = False) -> int:
+    if index < 0 or index > 0xFFF:
+        raise LoweringError("operand index out of range")
+    return index | (kind << 12) | ((SRC_I2F << 12) if i2f else 0)
+
+
 @dataclass
 class Program:
-    code: list[int] = field(default_factory=list)
+    code: list[int] = field(default_factory=list)    # u32 words, two per instruction
     consts: list[int] = field(default_factory=list)
-    text: list[str] = field(default_factory=list)  # disassembly, for explain/tests
+    ntemps: int = 0
+    text: list[str] = field(default_factory=list)    # disassembly, for explain/tests
 
     def words(self) -> list[int]:
         return list(self.code)
 
 
+def _fmt_operand(o: int) -> str:
+    kind, idx = (o >> 12) & 7, o & 0xFFF
+    if kind == 0:
+        return "-"
+    body = f"{_SRC_NAME[kind]}{idx & 63}[ix{idx >> 6}]" if kind == SRC_GATHER else f"{_SRC_NAME[kind]}{idx}"
+    return f"f64({body})" if o & 0x8000 else body
+
+
 class ProgramBuilder:
-    """Emits the postfix program, tracking the static stack depth of every instruction."""
+    """Emits three-address instructions; intermediates live in numbered temporaries (shared memory
+    slots of the scan kernel), repeated sub-expressions are computed once and kept in a temporary."""
 
     def __init__(self, resolver: Resolver) -> None:
         self.r = resolver
         self.p = Program()
-        self.depth = 0
-        self.temps: dict[Expr, int] = {}
-        self.temp_candidates: set[Expr] = set()
-        self.str_dict: dict[Expr, Any] = {}
+        self.free: list[int] = list(range(MAX_TEMPS))
+        self.cse: dict[Expr, int] = {}
+        self.uses_left: dict[Expr, int] = {}
+        self.candidates: dict[Expr, int] = {}
 
-    # -- emission helpers -----------------------------------------------------------------------
-    def emit(self, name: str, arg: int = 0, delta: int = 0) -> None:
-        op = OP[name]
-        if self.depth > MAX_DEPTH or (delta > 0 and self.depth + delta > MAX_DEPTH):
-            raise LoweringError(f"expression needs more than {MAX_DEPTH} stack slots")
-        if arg < 0 or arg > 0xFFFF:
-            raise LoweringError("instruction argument out of range")
-        self.p.code.append(op | (self.depth << 8) | (arg << 16))
-        self.p.text.append(f"{name} {arg}" if arg or name in ("CONST", "TEE", "GET", "LUT8", "LUT32") or name.startswith(("LOAD", "AGG", "STORE")) else name)
-        self.depth += delta
+    # -- low level ------------------------------------------------------------------------------
+    def alloc(self) -> int:
+        if not self.free:
+            raise LoweringError(f"expression needs more than {MAX_TEMPS} temporaries")
+        t = self.free.pop(0)
+        self.p.ntemps = max(self.p.ntemps, t + 1)
+        return t
+
+    def release(self, temps: Iterable[int]) -> None:
+        for t in temps:
+            if t not in self.free:
+                self.free.append(t)
+        self.free.sort()
 
     def const(self, bits: int) -> int:
         bits &= 0xFFFFFFFFFFFFFFFF
@@ -562,13 +583,22 @@ class ProgramBuilder:
         self.p.consts.append(bits)
         return len(self.p.consts) - 1
 
+    def emit(self, opname: str, a: int = 0, b: int = 0, dkind: int = DST_NONE, didx: int = 0, tee: int = 0) -> None:
+        if len(self.p.code) + 2 >= K["MSC_VM_MAX_CODE"]:
+            raise LoweringError("expression program too long")
+        self.p.code.append(OP[opname] | (dkind << 8) | (tee << 12) | (didx << 16))
+        self.p.code.append(a | (b << 16))
+        dst = _DST_NAME[dkind] + (str(didx) if dkind in (DST_TEMP, DST_AGG, DST_OUT) else "")
+        if tee:
+            dst += f",t{tee - 1}"
+        self.p.text.append(f"{dst} <- {opname}({_fmt_operand(a)}, {_fmt_operand(b)})")
+
     # -- CSE ------------------------------------------------------------------------------------
-    def plan_temps(self, roots: Iterable[Expr]) -> None:
-        """Pick up to MAX_TEMPS repeated non-trivial sub-expressions to keep in TEE/GET temporaries."""
+    def plan_cse(self, roots: Iterable[Expr]) -> None:
         counts: dict[Expr, int] = {}
 
         def walk(e: Expr) -> None:
-            if isinstance(e, (EInput, EConst)):
+            if isinstance(e, (EInput, EConst)) or (isinstance(e, ECast) and isinstance(e.child, (EInput, EConst))):
                 return
             counts[e] = counts.get(e, 0) + 1
             if counts[e] == 1:
@@ -577,118 +607,147 @@ class ProgramBuilder:
 
         for root in roots:
             walk(root)
+        self.candidates = {e: n for e, n in counts.items() if n > 1}
 
-        def cost(e: Expr) -> int:
-            return 1 + sum(cost(c) for c in expr_children(e))
+    def _take(self, e: Expr) -> tuple[int, list[int]]:
+        t = self.cse[e]
+        self.uses_left[e] -= 1
+        if self.uses_left[e] <= 0:
+            del self.cse[e]
+            return src(SRC_TEMP, t), [t]
+        return src(SRC_TEMP, t), []
 
-        repeated = sorted((e for e, n in counts.items() if n > 1 and e.type != STR and not isinstance(e, ECast)),
-                          key=lambda e: -cost(e) * (counts[e] - 1))
-        self.temp_candidates = set(repeated[:MAX_TEMPS])
-
-    # -- expression evaluation: leaves the value on the stack -------------------------------------
-    def value(self, e: Expr) -> None:
-        if e in self.temps:
-            self.emit("GET", self.temps[e], +1)
-            return
-        self._value(e)
-        if e in self.temp_candidates and e not in self.temps and len(self.temps) < MAX_TEMPS:
-            slot = len(self.temps)
-            self.temps[e] = slot
-            self.emit("TEE", slot, 0)
-
-    def _value(self, e: Expr) -> None:
+    # -- operands --------------------------------------------------------------------------------
+    def _leaf(self, e: Expr) -> Optional[int]:
         if isinstance(e, EInput):
             b = self.r.binding(e.index)
             if b.staged is not None:
-                self.emit(_LOAD[b.phys], b.staged, +1)
-            else:
-                self.emit(_LOAD[b.phys].replace("LOAD", "LOADG"), b.index | (b.gather << 8), +1)
-            return
+                return src(SRC_STAGED, b.staged)
+            return src(SRC_GATHER, b.gather | (b.index << 6))
         if isinstance(e, EConst):
             if e.type == STR:
-                raise LoweringError("a string literal is only supported as an operand of =, !=, + or as a selected column")
-            self.emit("CONST", self.const(f64_bits(e.value) if e.type == FLOAT else int(e.value)), +1)
-            return
+                raise LoweringError("a string literal is only supported as an operand of =, != or +")
+            return src(SRC_CONST, self.const(f64_bits(e.value) if e.type == FLOAT else int(e.value)))
         if isinstance(e, ECast):
-            if isinstance(e.child, EConst):  # fold float(int literal)
-                self.emit("CONST", self.const(f64_bits(float(e.child.value))), +1)
-                return
-            self.value(e.child)
-            self.emit("I2F")
-            return
-        if isinstance(e, ELike):
-            d = self.string(e.child)
-            self.emit("LUT8", self.r.like_lut(d, e.pattern))
-            return
-        if isinstance(e, (ETranslate, ECode)):
-            self.string(e.child if isinstance(e, ECode) else e)
-            return
-        if isinstance(e, EConcat):
-            raise LoweringError("internal: concat must be materialised before compilation")
-        if isinstance(e, EBin):
-            if e.left.type == STR or e.right.type == STR:
-                self._string_compare(e)
-                return
-            self.value(e.left)
-            self.value(e.right)
+            if isinstance(e.child, EConst):
+                return src(SRC_CONST, self.const(f64_bits(float(e.child.value))))
+            if isinstance(e.child, EInput):
+                return self._leaf(e.child) | (SRC_I2F << 12)
+        return None
+
+    def operand(self, e: Expr) -> tuple[int, list[int]]:
+        """Encoded operand holding ``e`` and the temporaries to release once it has been consumed."""
+        leaf = self._leaf(e)
+        if leaf is not None:
+            return leaf, []
+        if e in self.cse:
+            return self._take(e)
+        if isinstance(e, ECast):
+            enc, frees = self.operand(e.child)
+            return enc | (SRC_I2F << 12), frees
+        t = self.alloc()
+        self.materialize(e, DST_TEMP, t)
+        if e in self.cse:  # materialize registered it as a shared value
+            return self._take(e)
+        return src(SRC_TEMP, t), [t]
+
+    # -- strings ---------------------------------------------------------------------------------
+    def string_operand(self, e: Expr) -> tuple[int, list[int], Any]:
+        """(operand holding the dictionary code of a STR expression, temps to free, its dictionary)."""
+        if isinstance(e, ECode):
+            return self.string_operand(e.child)
+        if isinstance(e, EInput):
+            return self._leaf(e), [], self.r.binding(e.index).dict_id
+        if isinstance(e, ETranslate):
+            enc, frees, d = self.string_operand(e.child)
+            slot, target = self.r.translate_lut(d, e.token)
+            if slot < 0:
+                return enc, frees, target
+            t = self.alloc()
+            self.emit("LUT32", enc, src(SRC_LUT, slot), DST_TEMP, t)
+            self.release(frees)
+            return src(SRC_TEMP, t), [t], target
+        raise LoweringError(f"string expression {show(e)} must be materialised first")
+
+    def _string_compare(self, e: EBin) -> tuple[str, int, int, list[int]]:
+        left, right = e.left, e.right
+        if isinstance(left, EConst) and not isinstance(right, EConst):
+            left, right = right, left
+        opname = "EQ_I" if e.op == "eq" else "NE_I"
+        if isinstance(left, EConst):  # literal vs literal folds to a constant
+            truth = (left.value == right.value) == (e.op == "eq")
+            return "MOV", src(SRC_CONST, self.const(int(truth))), 0, []
+        a, frees, d = self.string_operand(left)
+        if isinstance(right, EConst):
+            return opname, a, src(SRC_CONST, self.const(self.r.literal_code(d, right.value))), frees  # -1 matches no code
+        b, frees_b, d2 = self.string_operand(right)
+        if not self.r.same_dict(d, d2):
+            t = self.alloc()
+            self.emit("LUT32", b, src(SRC_LUT, self.r.recode_lut(d2, d)), DST_TEMP, t)
+            self.release(frees_b)
+            b, frees_b = src(SRC_TEMP, t), [t]
+        return opname, a, b, frees + frees_b
+
+    # -- one expression root into a destination -------------------------------------------------
+    def materialize(self, e: Expr, dkind: int, didx: int = 0) -> Any:
+        """Evaluate ``e`` into the destination; returns the dictionary for STR-valued roots."""
+        if e in self.cse:
+            enc, frees = self._take(e)
+            self.emit("MOV", enc, 0, dkind, didx)
+            self.release(frees)
+            return None
+        dict_id = None
+        frees: list[int] = []
+        if e.type == STR or isinstance(e, ECode):
+            a, frees, dict_id = self.string_operand(e)
+            opname, b = "MOV", 0
+        elif isinstance(e, EBin) and (e.left.type == STR or e.right.type == STR):
+            opname, a, b, frees = self._string_compare(e)
+        elif isinstance(e, ELike):
+            a, frees, d = self.string_operand(e.child)
+            opname, b = "LUT8", src(SRC_LUT, self.r.like_lut(d, e.pattern))
+        elif isinstance(e, EBin):
+            a, fa = self.operand(e.left)
+            b, fb = self.operand(e.right)
+            frees = fa + fb
             is_float = (e.left.type == FLOAT) if e.op in _CMP else (e.type == FLOAT)
             table = _F_OPS if is_float else _I_OPS
             if e.op not in table:
                 raise LoweringError(f"operator {e.op} not available for type {e.type}")
-            self.emit(table[e.op], 0, -1)
-            return
-        raise LoweringError(f"cannot compile {e}")
-
-    def string(self, e: Expr) -> Any:
-        """Push the dictionary code of a STR expression; returns the dictionary it is coded in."""
-        if isinstance(e, EInput):
-            b = self.r.binding(e.index)
-            self._value(e)
-            return b.dict_id
-        if isinstance(e, ETranslate):
-            src = self.string(e.child)
-            slot, target = self.r.translate_lut(src, e.token)
-            if slot >= 0:
-                self.emit("LUT32", slot)
-            return target
-        raise LoweringError(f"string expression {show(e)} must be materialised first")
-
-    def _string_compare(self, e: EBin) -> None:
-        left, right = e.left, e.right
-        if isinstance(left, EConst) and not isinstance(right, EConst):
-            left, right = right, left
-        if isinstance(left, EConst):  # literal vs literal: fold
-            truth = (left.value == right.value) == (e.op == "eq")
-            self.emit("CONST", self.const(int(truth)), +1)
-            return
-        d = self.string(left)
-        if isinstance(right, EConst):
-            code = self.r.literal_code(d, right.value)
-            self.emit("CONST", self.const(code), +1)  # -1 never equals a code
-        else:
-            d2 = self.string(right)
-            if not self.r.same_dict(d, d2):
-                self.emit("LUT32", self.r.recode_lut(d2, d))
-        self.emit("EQ_I" if e.op == "eq" else "NE_I", 0, -1)
-
-    # -- statement-level helpers ------------------------------------------------------------------
-    def filter(self, e: Expr) -> None:
-        self.value(e)
-        self.emit("FILTER", 0, -1)
+            opname = table[e.op]
+        elif isinstance(e, EConcat):
+            raise LoweringError("internal: concat must be materialised before compilation")
+        else:  # leaf or cast
+            a, frees = self.operand(e)
+            opname, b = "MOV", 0
+        tee = 0
+        shared = self.candidates.get(e, 0)
+        if shared > 1 and e not in self.cse:
+            if dkind == DST_TEMP:
+                keep = didx
+            else:
+                keep = self.alloc()
+                tee = keep + 1
+            self.cse[e] = keep
+            self.uses_left[e] = shared  # every occurrence (including this one, if it is an operand) calls _take
+            if dkind != DST_TEMP:
+                self.uses_left[e] -= 1  # this occurrence went straight to its destination
+                if self.uses_left[e] <= 0:
+                    del self.cse[e]
+                    self.release([keep])
+                    tee = 0
+        self.emit(opname, a, b, dkind, didx, tee)
+        self.release(frees)
+        return dict_id
 
     def end(self) -> Program:
-        if self.depth != 0:
-            raise LoweringError("internal: unbalanced expression stack")
-        self.p.code.append(OP["END"])
+        self.p.code.extend([OP["END"], 0])
         self.p.text.append("END")
-        if len(self.p.code) > K["MSC_VM_MAX_CODE"]:
-            raise LoweringError("expression program too long")
         return self.p
 
 
-_AGG_OPS = {("sum", FLOAT): ("AGG_SUM_F", K["MSC_AGG_SUM_F"]), ("sum", INT): ("AGG_SUM_I", K["MSC_AGG_SUM_I"]),
-            ("min", FLOAT): ("AGG_MIN_F", K["MSC_AGG_MIN_F"]), ("max", FLOAT): ("AGG_MAX_F", K["MSC_AGG_MAX_F"]),
-            ("min", INT): ("AGG_MIN_I", K["MSC_AGG_MIN_I"]), ("max", INT): ("AGG_MAX_I", K["MSC_AGG_MAX_I"])}
+_AGG_KINDS = {("sum", FLOAT): K["MSC_AGG_SUM_F"], ("sum", INT): K["MSC_AGG_SUM_I"], ("min", FLOAT): K["MSC_AGG_MIN_F"],
+              ("max", FLOAT): K["MSC_AGG_MAX_F"], ("min", INT): K["MSC_AGG_MIN_I"], ("max", INT): K["MSC_AGG_MAX_I"]}
 
 
 @dataclass
@@ -702,36 +761,26 @@ class AggregateProgram:
 def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, aggs: Sequence[tuple[str, Expr]]) -> AggregateProgram:
     b = ProgramBuilder(resolver)
     norm = [(k, EConst(INT, 1) if k == "count" else (EBin(INT, "add", e, EConst(INT, 0)) if e.type == BOOL else e)) for k, e in aggs]
-    b.plan_temps([*filters, group, *[e for k, e in norm if k != "count"]])
-    for f in filters:
-        b.filter(f)
-    group_dict = None
-    if group.type == STR:
-        group_dict = b.string(group)
-    else:
-        b.value(group)
-    b.emit("GROUP", 0, -1)
-    slots: dict[tuple[str, Expr], int] = {}
-    kinds: list[int] = []
+    unique: dict[tuple[str, Expr], int] = {}
     slot_of: list[int] = []
-    for kind, e in norm:
-        key = (kind, e)
-        if key in slots:
-            slot_of.append(slots[key])
-            continue
-        slot = len(kinds)
-        if slot >= K["MSC_VM_MAX_AGGS"]:
-            raise LoweringError("too many aggregates in one GROUP BY")
-        slots[key] = slot
-        slot_of.append(slot)
+    for key in norm:
+        if key not in unique:
+            if len(unique) >= K["MSC_VM_MAX_AGGS"]:
+                raise LoweringError("too many aggregates in one GROUP BY")
+            unique[key] = len(unique)
+        slot_of.append(unique[key])
+    b.plan_cse([*filters, group, *[e for (k, e) in unique if k != "count"]])
+    for f in filters:
+        b.materialize(f, DST_FILTER)
+    group_dict = b.materialize(group, DST_GROUP)
+    kinds: list[int] = []
+    for (kind, e), slot in unique.items():
         if kind == "count":
             kinds.append(K["MSC_AGG_SUM_I"])
-            b.emit("AGG_COUNT", slot, 0)
+            b.emit("MOV", src(SRC_CONST, b.const(1)), 0, DST_AGG, slot)
             continue
-        opname, agg_kind = _AGG_OPS[(kind, FLOAT if e.type == FLOAT else INT)]
-        kinds.append(agg_kind)
-        b.value(e)
-        b.emit(opname, slot, -1)
+        kinds.append(_AGG_KINDS[(kind, FLOAT if e.type == FLOAT else INT)])
+        b.materialize(e, DST_AGG, slot)
     return AggregateProgram(b.end(), kinds, slot_of, group_dict)
 
 
@@ -744,31 +793,16 @@ class ProjectProgram:
 
 def compile_project(resolver: Resolver, filters: Sequence[Expr], outputs: Sequence[Expr]) -> ProjectProgram:
     b = ProgramBuilder(resolver)
-    b.plan_temps([*filters, *outputs])
+    b.plan_cse([*filters, *outputs])
     for f in filters:
-        b.filter(f)
+        b.materialize(f, DST_FILTER)
     if filters:
         b.emit("RANK")
-    out_phys: list[int] = []
-    out_dicts: list[Any] = []
     if len(outputs) > K["MSC_VM_MAX_OUT"]:
         raise LoweringError("too many output columns in one projection")
+    out_phys: list[int] = []
+    out_dicts: list[Any] = []
     for i, e in enumerate(outputs):
-        if e.type == STR:
-            out_dicts.append(b.string(e))
-            b.emit("STORE_U32", i, -1)
-            out_phys.append(P_U32)
-        elif isinstance(e, ECode):  # integer code of a string key; remember which dictionary it is coded in
-            out_dicts.append(b.string(e.child))
-            b.emit("STORE_I64", i, -1)
-            out_phys.append(P_I64)
-        else:
-            b.value(e)
-            out_dicts.append(None)
-            if e.type == FLOAT:
-                b.emit("STORE_F64", i, -1)
-                out_phys.append(P_F64)
-            else:
-                b.emit("STORE_I64", i, -1)
-                out_phys.append(P_I64)
+        out_dicts.append(b.materialize(e, DST_OUT, i))
+        out_phys.append(P_U32 if e.type == STR else (P_F64 if e.type == FLOAT else P_I64))
     return ProjectProgram(b.end(), out_phys, out_dicts)

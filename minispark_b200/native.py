@@ -56,7 +56,7 @@ class ScanDesc(C.Structure):
         ("code", C.c_uint32 * K["MSC_VM_MAX_CODE"]),
         ("consts", C.c_int64 * K["MSC_VM_MAX_CONSTS"]),
         ("nluts", C.c_int32),
-        ("_pad", C.c_int32),
+        ("ntemps", C.c_int32),
         ("luts", C.c_void_p * K["MSC_VM_MAX_LUTS"]),
     ]
 
