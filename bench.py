@@ -293,11 +293,14 @@ def cuda_arm(args: argparse.Namespace) -> None:
         slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog.agg_kinds]
         bytes_per_row = sum(N.PHYS_WIDTH[c.phys] for c in resolver.staged)
 
+        agg_launch: dict = {}
+
         def step() -> tuple[float, float]:
             out = C.c_void_p()
             engine.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), ngroups, C.byref(out))
             st = engine.ctx.stats()
             dev_ms, scan_ms = st.last_kernel_ms, st.last_scan_ms
+            agg_launch.update(grid=st.last_scan_grid, stages=st.last_scan_stages, smem=st.last_scan_smem, rows_per_thread=st.last_scan_rows_per_thread)
             raw = DeviceRel.from_handle(engine.ctx, out.value, [L.STR, *slot_types], [prog.group_dict] + [None] * len(slot_types))
             view_cols = [raw.cols[0]] + [raw.cols[1 + s] for s in prog.slot_of]
             from minispark_b200.execution import _Source
@@ -378,7 +381,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
                     "wall_ms_per_step": 1e3 * wall_max / args.steps, "parity_check": check,
                 },
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "kernel": "scan_kernel<R=%d, MODE_DENSE>" % engine.ctx.stats().last_scan_rows_per_thread,
+                             "kernel": "scan_kernel<R=%d, MODE_DENSE>" % agg_launch["rows_per_thread"], "launch": agg_launch,
+                             "program": prog.program.text,
                              "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": nrows_table * bytes_per_row, "peak_source": peak_src,
                              "north_star_layout_equiv_gbs": nrows_table * Q1_WIDE_BYTES_PER_ROW / (scan_ms * 1e-3) / 1e9 if args.layout == "native" else None},
                 "cpu_baseline": cpu,
@@ -386,8 +390,7 @@ def cuda_arm(args: argparse.Namespace) -> None:
                         "ms_per_step": 1e3 * e2e_s, "h2d_gbs": h2d_bytes / e2e_s / 1e9},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "clocks": clocks.summary(),
-                "setup": {"generate_s": gen_s, "scan_grid": engine.ctx.stats().last_scan_grid, "scan_stages": engine.ctx.stats().last_scan_stages,
-                          "scan_smem": engine.ctx.stats().last_scan_smem},
+                "setup": {"generate_s": gen_s},
             }
             print(json.dumps(line))
         engine.ctx.call("msc_host_free", pinned)

@@ -66,12 +66,15 @@ extern "C" {
  * generated Zig condition/projection functions (templates/plan.zig:62-75,80-103).
  *
  * One instruction is two u32 words:
- *   w0 = op | dst_kind << 8 | tee << 12 | dst_index << 16
+ *   w0 = op | dst_kind << 6 | tee << 9 | dst_index << 13 | fast << 20
  *   w1 = operand A | operand B << 16        operand = index | src_kind << 12 | i2f << 15
  * result = op(A, B); it goes to `dst` and, when tee != 0, also to temporary tee-1.
  * Values are 64-bit: i64 (INTEGER, TIMESTAMP, booleans, dictionary codes) or f64 (FLOAT).
  * Temporaries are per-thread slots in shared memory, so no interpreter state lives in registers
- * between instructions.  Python parses these names (minispark_b200/native.py).               */
+ * between instructions.  `fast` != 0 names a pre-compiled specialisation of exactly this
+ * instruction shape (operand kinds / physical types / destination baked in at C++ compile time,
+ * see MSC_FAST_*); the kernel dispatches it with one jump and falls back to the generic
+ * fetch/compute/store path when fast == 0.  Python parses these names (minispark_b200/native.py). */
 enum msc_opcode {
   MSC_OP_END = 0,
   MSC_OP_MOV = 1, /* result = A */
@@ -102,6 +105,32 @@ enum msc_opcode {
 #define MSC_DST_AGG 3    /* fold result into accumulator dst_index of the row's group (tasks.py:293-310) */
 #define MSC_DST_OUT 4    /* write result to output column dst_index at the row's output position */
 #define MSC_DST_NONE 5
+
+/* ---- fast shapes: `fast` field of w0 ------------------------------------------------------ *
+ * source kinds of a specialised handler */
+#define MSC_FK_F32 0   /* staged f32 column widened to f64 */
+#define MSC_FK_F64 1   /* staged f64 column */
+#define MSC_FK_TEMP 2  /* temporary */
+#define MSC_FK_CONST 3 /* constant */
+#define MSC_FK_I32F 4  /* staged i32 column converted to f64 */
+#define MSC_FK_I32 5   /* staged i32 column as i64 */
+#define MSC_FK_I64 6   /* staged i64 column */
+#define MSC_FK_U8 7    /* staged u8 dictionary code */
+#define MSC_FK_U16 8
+#define MSC_FK_U32 9
+#define MSC_FK__COUNT 10
+/* families: id = base + formula
+ *   ARITH  1 + ((opi*5 + ak)*5 + bk)*3 + dk   opi: 0 ADD_F 1 SUB_F 2 MUL_F; ak,bk in F32,F64,TEMP,CONST,I32F;
+ *                                             dk: 0 -> TEMP, 1 -> AGG (SUM_F), 2 -> AGG + tee TEMP
+ *   AGGMOV 256 + agg_kind*10 + fk             accumulator <- source
+ *   CMP    320 + cmpi*10 + fk                 FILTER <- source <cmp> CONST; cmpi: LT LE GT GE EQ NE
+ *   GROUP  384 + fk                           GROUP <- source
+ *   OUT    400 + fk*2 + (out is U32)          OUT column <- source */
+#define MSC_FAST_ARITH 1
+#define MSC_FAST_AGGMOV 256
+#define MSC_FAST_CMP 320
+#define MSC_FAST_GROUP 384
+#define MSC_FAST_OUT 400
 
 #define MSC_VM_MAX_TEMPS 8
 #define MSC_VM_MAX_CODE 192  /* u32 words = 96 instructions */

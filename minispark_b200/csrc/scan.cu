@@ -412,52 +412,68 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 // unrolled compile-time constants, so they are registers that live for one instruction only.
 // ------------------------------------------------------------------------------------------------
 template <int R>
+__device__ __forceinline__ void to_f64(long long (&v)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = d2l(static_cast<double>(v[r]));
+}
+
+template <int R>
+__device__ __forceinline__ void fetch_staged(const ScanParams& p, const unsigned char* sbase, int idx, int tid, long long (&v)[R]) {
+  const unsigned char* col = sbase + p.staged[idx].smem_off;
+  switch (p.staged[idx].phys) {
+    case MSC_P_U8: load_staged<R, MSC_P_U8>(col, tid, v); break;
+    case MSC_P_U16: load_staged<R, MSC_P_U16>(col, tid, v); break;
+    case MSC_P_U32: load_staged<R, MSC_P_U32>(col, tid, v); break;
+    case MSC_P_I32: load_staged<R, MSC_P_I32>(col, tid, v); break;
+    case MSC_P_F32: load_staged<R, MSC_P_F32>(col, tid, v); break;
+    default: load_staged<R, MSC_P_I64>(col, tid, v); break;  // I64 and F64: raw 64-bit pattern
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void fetch_gather(const ScanParams& p, const unsigned char* sbase, int idx, int tid, uint32_t vmask,
+                                             long long (&v)[R]) {
+  const unsigned char* ix = sbase + p.staged[idx >> 6].smem_off;
+  const void* col = p.gather[idx & 63];
+  switch (p.gather_phys[idx & 63]) {
+    case MSC_P_U8: load_gather<R, MSC_P_U8>(ix, col, tid, vmask, v); break;
+    case MSC_P_U16: load_gather<R, MSC_P_U16>(ix, col, tid, vmask, v); break;
+    case MSC_P_U32: load_gather<R, MSC_P_U32>(ix, col, tid, vmask, v); break;
+    case MSC_P_I32: load_gather<R, MSC_P_I32>(ix, col, tid, vmask, v); break;
+    case MSC_P_F32: load_gather<R, MSC_P_F32>(ix, col, tid, vmask, v); break;
+    default: load_gather<R, MSC_P_I64>(ix, col, tid, vmask, v); break;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void fetch_temp(const long long* temps, int idx, int tid, long long (&v)[R]) {
+  const long long* t = temps + (idx * R) * NT + tid;
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = t[r * NT];
+}
+
+// generic operand fetch: the i2f variants are separate switch targets (a flag test would be
+// if-converted into R predicated 64-bit conversions on every fetch)
+template <int R>
 __device__ __forceinline__ void fetch(const ScanParams& p, const unsigned char* sbase, const long long* temps,
                                       uint32_t operand, int tid, uint32_t vmask, long long (&v)[R]) {
-  const int kind = (operand >> 12) & 7;
   const int idx = operand & 0xfff;
-  switch (kind) {
-    case MSC_SRC_TEMP: {
-      const long long* t = temps + (idx * R) * NT + tid;
-#pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = t[r * NT];
-    } break;
-    case MSC_SRC_STAGED: {
-      const unsigned char* col = sbase + p.staged[idx].smem_off;
-      switch (p.staged[idx].phys) {
-        case MSC_P_U8: load_staged<R, MSC_P_U8>(col, tid, v); break;
-        case MSC_P_U16: load_staged<R, MSC_P_U16>(col, tid, v); break;
-        case MSC_P_U32: load_staged<R, MSC_P_U32>(col, tid, v); break;
-        case MSC_P_I32: load_staged<R, MSC_P_I32>(col, tid, v); break;
-        case MSC_P_F32: load_staged<R, MSC_P_F32>(col, tid, v); break;
-        default: load_staged<R, MSC_P_I64>(col, tid, v); break;  // I64 and F64: raw 64-bit pattern
-      }
-    } break;
+  switch ((operand >> 12) & 15) {
+    case MSC_SRC_TEMP: fetch_temp<R>(temps, idx, tid, v); break;
+    case MSC_SRC_TEMP | MSC_SRC_I2F: fetch_temp<R>(temps, idx, tid, v); to_f64<R>(v); break;
+    case MSC_SRC_STAGED: fetch_staged<R>(p, sbase, idx, tid, v); break;
+    case MSC_SRC_STAGED | MSC_SRC_I2F: fetch_staged<R>(p, sbase, idx, tid, v); to_f64<R>(v); break;
+    case MSC_SRC_GATHER: fetch_gather<R>(p, sbase, idx, tid, vmask, v); break;
+    case MSC_SRC_GATHER | MSC_SRC_I2F: fetch_gather<R>(p, sbase, idx, tid, vmask, v); to_f64<R>(v); break;
     case MSC_SRC_CONST: {
       const long long c = p.consts[idx];
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = c;
     } break;
-    case MSC_SRC_GATHER: {
-      const unsigned char* ix = sbase + p.staged[idx >> 6].smem_off;
-      const void* col = p.gather[idx & 63];
-      switch (p.gather_phys[idx & 63]) {
-        case MSC_P_U8: load_gather<R, MSC_P_U8>(ix, col, tid, vmask, v); break;
-        case MSC_P_U16: load_gather<R, MSC_P_U16>(ix, col, tid, vmask, v); break;
-        case MSC_P_U32: load_gather<R, MSC_P_U32>(ix, col, tid, vmask, v); break;
-        case MSC_P_I32: load_gather<R, MSC_P_I32>(ix, col, tid, vmask, v); break;
-        case MSC_P_F32: load_gather<R, MSC_P_F32>(ix, col, tid, vmask, v); break;
-        default: load_gather<R, MSC_P_I64>(ix, col, tid, vmask, v); break;
-      }
-    } break;
     default: {
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = 0;
     } break;
-  }
-  if (operand & 0x8000u) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = d2l(static_cast<double>(v[r]));
   }
 }
 
@@ -560,6 +576,177 @@ __device__ __forceinline__ void store_out(const long long (&x)[R], TOut* out, ui
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fast shapes: handlers specialised at C++ compile time on (operand kinds, op, destination).  The
+// host picks the shape id (`fast` field of w0, include/minispark_cuda.h MSC_FAST_*); one jump-table
+// dispatch replaces the generic path's four switches and its register merges.
+// ------------------------------------------------------------------------------------------------
+struct FastCtx {
+  const ScanParams& p;
+  const unsigned char* sbase;
+  long long* temps;
+  long long* acc;
+  int tid;
+};
+
+template <int R, int FK>
+__device__ __forceinline__ void ffetch(const FastCtx& c, int idx, long long (&v)[R]) {
+  if constexpr (FK == MSC_FK_TEMP) {
+    fetch_temp<R>(c.temps, idx, c.tid, v);
+  } else if constexpr (FK == MSC_FK_CONST) {
+    const long long k = c.p.consts[idx];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = k;
+  } else {
+    const unsigned char* col = c.sbase + c.p.staged[idx].smem_off;
+    if constexpr (FK == MSC_FK_F32) load_staged<R, MSC_P_F32>(col, c.tid, v);
+    else if constexpr (FK == MSC_FK_F64 || FK == MSC_FK_I64) load_staged<R, MSC_P_I64>(col, c.tid, v);
+    else if constexpr (FK == MSC_FK_I32) load_staged<R, MSC_P_I32>(col, c.tid, v);
+    else if constexpr (FK == MSC_FK_I32F) {
+      load_staged<R, MSC_P_I32>(col, c.tid, v);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = d2l(static_cast<double>(static_cast<int>(v[r])));
+    } else if constexpr (FK == MSC_FK_U8) load_staged<R, MSC_P_U8>(col, c.tid, v);
+    else if constexpr (FK == MSC_FK_U16) load_staged<R, MSC_P_U16>(col, c.tid, v);
+    else load_staged<R, MSC_P_U32>(col, c.tid, v);
+  }
+}
+
+template <int R, int MODE, int KIND>
+__device__ __forceinline__ void fast_agg(const FastCtx& c, int slot, const int (&grp)[R], const long long (&v)[R]) {
+  if constexpr (MODE == MODE_DENSE) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      long long* q = c.acc + (grp[r] * c.p.naggs + slot) * NT + c.tid;
+      *q = agg_combine(KIND, *q, v[r]);
+    }
+  } else if constexpr (MODE == MODE_HASH) {
+    agg_hash<R, KIND>(c.p.haccs, c.p.hcap, slot, grp, v);
+  }
+}
+
+// dst <- A (+|-|*) B on f64; DK: 0 TEMP, 1 AGG(SUM_F), 2 AGG(SUM_F) + tee TEMP
+template <int R, int MODE, int OPI, int AK, int BK, int DK>
+__device__ __forceinline__ void fast_arith(const FastCtx& c, uint32_t w0, uint32_t w1, const int (&grp)[R]) {
+  long long a[R], b[R];
+  ffetch<R, AK>(c, w1 & 0xfff, a);
+  ffetch<R, BK>(c, (w1 >> 16) & 0xfff, b);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double x = l2d(a[r]), y = l2d(b[r]);
+    a[r] = d2l(OPI == 0 ? x + y : (OPI == 1 ? x - y : x * y));
+  }
+  const int dst = (w0 >> 13) & 0x7f;
+  if constexpr (DK == 0) store_temp<R>(c.temps, dst, c.tid, a);
+  if constexpr (DK == 2) store_temp<R>(c.temps, static_cast<int>((w0 >> 9) & 0xf) - 1, c.tid, a);
+  if constexpr (DK >= 1) fast_agg<R, MODE, MSC_AGG_SUM_F>(c, dst, grp, a);
+}
+
+template <int R, int MODE, int KIND, int FK>
+__device__ __forceinline__ void fast_aggmov(const FastCtx& c, uint32_t w0, uint32_t w1, const int (&grp)[R]) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  fast_agg<R, MODE, KIND>(c, (w0 >> 13) & 0x7f, grp, a);
+}
+
+template <int R, int CMPI, int FK>
+__device__ __forceinline__ void fast_cmp_filter(const FastCtx& c, uint32_t w1, uint32_t& vmask) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  const long long k = c.p.consts[(w1 >> 16) & 0xfff];
+  constexpr bool is_f = FK == MSC_FK_F32 || FK == MSC_FK_F64 || FK == MSC_FK_I32F;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    bool t;
+    if constexpr (is_f) {
+      const double x = l2d(a[r]), y = l2d(k);
+      t = CMPI == 0 ? x < y : CMPI == 1 ? x <= y : CMPI == 2 ? x > y : CMPI == 3 ? x >= y : CMPI == 4 ? x == y : x != y;
+    } else {
+      const long long x = a[r];
+      t = CMPI == 0 ? x < k : CMPI == 1 ? x <= k : CMPI == 2 ? x > k : CMPI == 3 ? x >= k : CMPI == 4 ? x == k : x != k;
+    }
+    if (!t) vmask &= ~(1u << r);
+  }
+}
+
+template <int R, int MODE, int FK>
+__device__ __forceinline__ void fast_group(const FastCtx& c, uint32_t w1, uint32_t vmask, int (&grp)[R]) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  if constexpr (MODE == MODE_DENSE) group_dense<R>(a, vmask, c.p.ngroups, c.p.naggs, c.acc, c.tid, grp);
+  else if constexpr (MODE == MODE_HASH) group_hash<R>(a, vmask, c.p.hkeys, c.p.hcap, c.p.err, grp);
+}
+
+template <int R, int FK, int U32OUT>
+__device__ __forceinline__ void fast_out(const FastCtx& c, uint32_t w0, uint32_t w1, uint64_t out_pos, uint32_t vmask) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  void* out = c.p.out[(w0 >> 13) & 0x7f];
+  if constexpr (U32OUT) store_out<R, uint32_t>(a, reinterpret_cast<uint32_t*>(out), out_pos, vmask);
+  else store_out<R, long long>(a, reinterpret_cast<long long*>(out), out_pos, vmask);
+}
+
+// returns false when the id is not a compiled shape (the caller then runs the generic path)
+template <int R, int MODE>
+__device__ __forceinline__ bool run_fast(const FastCtx& c, int fast, uint32_t w0, uint32_t w1, uint32_t& vmask, int (&grp)[R],
+                                         uint64_t out_pos) {
+  constexpr bool AGG = MODE == MODE_DENSE || MODE == MODE_HASH;
+  switch (fast) {
+#define ARITH_ID(OPI, AK, BK, DK) (MSC_FAST_ARITH + (((OPI) * 5 + (AK)) * 5 + (BK)) * 3 + (DK))
+#define ARITH_CASE(OPI, AK, BK, DK)                                          \
+  case ARITH_ID(OPI, AK, BK, DK):                                            \
+    if constexpr (AGG || DK == 0) fast_arith<R, MODE, OPI, AK, BK, DK>(c, w0, w1, grp); \
+    return true;
+#define ARITH_DK(OPI, AK, BK) ARITH_CASE(OPI, AK, BK, 0) ARITH_CASE(OPI, AK, BK, 1) ARITH_CASE(OPI, AK, BK, 2)
+#define ARITH_BK(OPI, AK) ARITH_DK(OPI, AK, 0) ARITH_DK(OPI, AK, 1) ARITH_DK(OPI, AK, 2) ARITH_DK(OPI, AK, 3) ARITH_DK(OPI, AK, 4)
+#define ARITH_AK(OPI) ARITH_BK(OPI, 0) ARITH_BK(OPI, 1) ARITH_BK(OPI, 2) ARITH_BK(OPI, 3) ARITH_BK(OPI, 4)
+    ARITH_AK(0)
+    ARITH_AK(1)
+    ARITH_AK(2)
+#undef ARITH_AK
+#undef ARITH_BK
+#undef ARITH_DK
+#undef ARITH_CASE
+#undef ARITH_ID
+#define AGGMOV_CASE(KIND, FK)                                                          \
+  case MSC_FAST_AGGMOV + (KIND) * 10 + (FK):                                           \
+    if constexpr (AGG) fast_aggmov<R, MODE, KIND, FK>(c, w0, w1, grp);                 \
+    return true;
+    AGGMOV_CASE(MSC_AGG_SUM_F, MSC_FK_F32) AGGMOV_CASE(MSC_AGG_SUM_F, MSC_FK_F64) AGGMOV_CASE(MSC_AGG_SUM_F, MSC_FK_TEMP)
+    AGGMOV_CASE(MSC_AGG_SUM_F, MSC_FK_I32F)
+    AGGMOV_CASE(MSC_AGG_SUM_I, MSC_FK_CONST) AGGMOV_CASE(MSC_AGG_SUM_I, MSC_FK_I32) AGGMOV_CASE(MSC_AGG_SUM_I, MSC_FK_I64)
+    AGGMOV_CASE(MSC_AGG_SUM_I, MSC_FK_TEMP)
+    AGGMOV_CASE(MSC_AGG_MIN_F, MSC_FK_F32) AGGMOV_CASE(MSC_AGG_MIN_F, MSC_FK_F64) AGGMOV_CASE(MSC_AGG_MIN_F, MSC_FK_TEMP)
+    AGGMOV_CASE(MSC_AGG_MAX_F, MSC_FK_F32) AGGMOV_CASE(MSC_AGG_MAX_F, MSC_FK_F64) AGGMOV_CASE(MSC_AGG_MAX_F, MSC_FK_TEMP)
+    AGGMOV_CASE(MSC_AGG_MIN_I, MSC_FK_I32) AGGMOV_CASE(MSC_AGG_MIN_I, MSC_FK_I64) AGGMOV_CASE(MSC_AGG_MIN_I, MSC_FK_TEMP)
+    AGGMOV_CASE(MSC_AGG_MAX_I, MSC_FK_I32) AGGMOV_CASE(MSC_AGG_MAX_I, MSC_FK_I64) AGGMOV_CASE(MSC_AGG_MAX_I, MSC_FK_TEMP)
+#undef AGGMOV_CASE
+#define CMP_CASE(CMPI, FK) \
+  case MSC_FAST_CMP + (CMPI) * 10 + (FK): fast_cmp_filter<R, CMPI, FK>(c, w1, vmask); return true;
+#define CMP_ALL(CMPI)                                                                                              \
+  CMP_CASE(CMPI, MSC_FK_F32) CMP_CASE(CMPI, MSC_FK_F64) CMP_CASE(CMPI, MSC_FK_I32F) CMP_CASE(CMPI, MSC_FK_I32)     \
+  CMP_CASE(CMPI, MSC_FK_I64) CMP_CASE(CMPI, MSC_FK_U8) CMP_CASE(CMPI, MSC_FK_U16) CMP_CASE(CMPI, MSC_FK_U32)
+    CMP_ALL(0) CMP_ALL(1) CMP_ALL(2) CMP_ALL(3) CMP_ALL(4) CMP_ALL(5)
+#undef CMP_ALL
+#undef CMP_CASE
+#define GROUP_CASE(FK)                                                   \
+  case MSC_FAST_GROUP + (FK):                                            \
+    if constexpr (AGG) fast_group<R, MODE, FK>(c, w1, vmask, grp);       \
+    return true;
+    GROUP_CASE(MSC_FK_U8) GROUP_CASE(MSC_FK_U16) GROUP_CASE(MSC_FK_U32) GROUP_CASE(MSC_FK_I32) GROUP_CASE(MSC_FK_I64)
+    GROUP_CASE(MSC_FK_TEMP)
+#undef GROUP_CASE
+#define OUT_CASE(FK, U32OUT)                                                          \
+  case MSC_FAST_OUT + (FK) * 2 + (U32OUT):                                            \
+    if constexpr (MODE == MODE_PROJECT) fast_out<R, FK, U32OUT>(c, w0, w1, out_pos, vmask); \
+    return true;
+    OUT_CASE(MSC_FK_F32, 0) OUT_CASE(MSC_FK_F64, 0) OUT_CASE(MSC_FK_TEMP, 0) OUT_CASE(MSC_FK_I32, 0) OUT_CASE(MSC_FK_I64, 0)
+    OUT_CASE(MSC_FK_I32F, 0) OUT_CASE(MSC_FK_U8, 1) OUT_CASE(MSC_FK_U16, 1) OUT_CASE(MSC_FK_U32, 1) OUT_CASE(MSC_FK_TEMP, 1)
+#undef OUT_CASE
+    default: return false;
+  }
+}
+
 template <int R>
 __device__ __forceinline__ void issue_tile(const ScanParams& p, unsigned char* stages, uint64_t* full, uint32_t k) {
   constexpr uint32_t TILE = NT * R;
@@ -622,11 +809,14 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     }
     uint64_t out_pos = row0;  // project: output position of this thread's first surviving row
 
+    const FastCtx fc{p, sbase, temps, acc, tid};
     for (int pc = 0;; pc += 2) {
       const uint32_t w0 = p.code[pc];
-      const int op = w0 & 0xff;
+      const int op = w0 & 0x3f;
       if (op == MSC_OP_END) break;
       const uint32_t w1 = p.code[pc + 1];
+      const int fast = w0 >> 20;
+      if (fast != 0 && run_fast<R, MODE>(fc, fast, w0, w1, vmask, grp, out_pos)) continue;
       if (op == MSC_OP_RANK) {
         if constexpr (MODE == MODE_COUNT) {
           uint32_t total;
@@ -654,10 +844,10 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
         op_lut<R, uint32_t>(a, reinterpret_cast<const uint32_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
       }
       // ---- store -------------------------------------------------------------------------------
-      const int tee = (w0 >> 12) & 0xf;
+      const int tee = (w0 >> 9) & 0xf;
       if (tee) store_temp<R>(temps, tee - 1, tid, a);
-      const int dst = w0 >> 16;
-      switch ((w0 >> 8) & 0xf) {
+      const int dst = (w0 >> 13) & 0x7f;
+      switch ((w0 >> 6) & 7) {
         case MSC_DST_TEMP: store_temp<R>(temps, dst, tid, a); break;
         case MSC_DST_FILTER: {
 #pragma unroll
@@ -915,7 +1105,7 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, int naggs,
   bool ended = false;
   for (int pc = 0; pc < sd->ncode; pc += 2) {
     const uint32_t w0 = sd->code[pc];
-    const int op = w0 & 0xff;
+    const int op = w0 & 0x3f;
     if (op == MSC_OP_END) {
       ended = true;
       break;
@@ -928,7 +1118,7 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, int naggs,
     MSC_TRY(validate_operand(ctx, sd, w1 & 0xffffu, false));
     MSC_TRY(validate_operand(ctx, sd, w1 >> 16, lut));
     if (lut && ((w1 >> 28) & 7) != MSC_SRC_LUT) return ctx->fail(MSC_ERR_ARG, "LUT instruction needs a LUT operand");
-    const int tee = (w0 >> 12) & 0xf, dkind = (w0 >> 8) & 0xf, dst = w0 >> 16;
+    const int tee = (w0 >> 9) & 0xf, dkind = (w0 >> 6) & 7, dst = (w0 >> 13) & 0x7f;
     if (tee > sd->ntemps) return ctx->fail(MSC_ERR_ARG, "tee: bad temporary");
     switch (dkind) {
       case MSC_DST_TEMP:
@@ -1214,9 +1404,9 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
   bool has_filter = false;
   int rank_pc = -1;
   for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
-    const int op = sd->code[pc] & 0xff;
+    const int op = sd->code[pc] & 0x3f;
     if (op == MSC_OP_END) break;
-    if (((sd->code[pc] >> 8) & 0xf) == MSC_DST_FILTER && op != MSC_OP_RANK) has_filter = true;
+    if (((sd->code[pc] >> 6) & 7) == MSC_DST_FILTER && op != MSC_OP_RANK) has_filter = true;
     if (op == MSC_OP_RANK) rank_pc = pc;
   }
   if (has_filter && rank_pc < 0) return ctx->fail(MSC_ERR_ARG, "filtered projection needs a RANK instruction");

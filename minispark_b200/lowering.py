@@ -20,6 +20,7 @@ Nothing in this module touches the GPU, so it is unit-tested on CPU.
 from __future__ import annotations
 
 import operator as _op
+import os
 import struct
 from dataclasses import dataclass, field
 from datetime import datetime
@@ -506,6 +507,7 @@ class Resolver(Protocol):
 
 
 MAX_TEMPS = K["MSC_VM_MAX_TEMPS"]
+FAST_SHAPES = os.environ.get("MSC_SCAN_FAST", "1") != "0"  # 0: force the generic interpreter path (A/B testing)
 _F_OPS = {"add": "ADD_F", "sub": "SUB_F", "mul": "MUL_F", "truediv": "DIV_F", "floordiv": "FLOORDIV_F", "mod": "MOD_F",
           "lt": "LT_F", "le": "LE_F", "gt": "GT_F", "ge": "GE_F", "eq": "EQ_F", "ne": "NE_F"}
 _I_OPS = {"add": "ADD_I", "sub": "SUB_I", "mul": "MUL_I", "floordiv": "FLOORDIV_I", "mod": "MOD_I",
@@ -557,6 +559,7 @@ class ProgramBuilder:
         self.cse: dict[Expr, int] = {}
         self.uses_left: dict[Expr, int] = {}
         self.candidates: dict[Expr, int] = {}
+        self.staged_phys: dict[int, int] = {}
 
     # -- low level ------------------------------------------------------------------------------
     def alloc(self) -> int:
@@ -583,15 +586,66 @@ class ProgramBuilder:
         self.p.consts.append(bits)
         return len(self.p.consts) - 1
 
-    def emit(self, opname: str, a: int = 0, b: int = 0, dkind: int = DST_NONE, didx: int = 0, tee: int = 0) -> None:
+    def emit(self, opname: str, a: int = 0, b: int = 0, dkind: int = DST_NONE, didx: int = 0, tee: int = 0,
+             agg_kind: Optional[int] = None, out_u32: bool = False) -> None:
         if len(self.p.code) + 2 >= K["MSC_VM_MAX_CODE"]:
             raise LoweringError("expression program too long")
-        self.p.code.append(OP[opname] | (dkind << 8) | (tee << 12) | (didx << 16))
+        if didx < 0 or didx > 0x7F:
+            raise LoweringError("destination index out of range")
+        fast = self.fast_id(opname, a, b, dkind, tee, agg_kind, out_u32) if FAST_SHAPES else 0
+        self.p.code.append(OP[opname] | (dkind << 6) | (tee << 9) | (didx << 13) | (fast << 20))
         self.p.code.append(a | (b << 16))
         dst = _DST_NAME[dkind] + (str(didx) if dkind in (DST_TEMP, DST_AGG, DST_OUT) else "")
         if tee:
             dst += f",t{tee - 1}"
-        self.p.text.append(f"{dst} <- {opname}({_fmt_operand(a)}, {_fmt_operand(b)})")
+        self.p.text.append(f"{dst} <- {opname}({_fmt_operand(a)}, {_fmt_operand(b)})" + (f"  [fast {fast}]" if fast else ""))
+
+    # -- fast shapes (include/minispark_cuda.h MSC_FAST_*) ----------------------------------------
+    def _fk(self, operand: int) -> Optional[int]:
+        kind, idx, i2f = (operand >> 12) & 7, operand & 0xFFF, bool(operand & 0x8000)
+        if kind == SRC_TEMP and not i2f:
+            return K["MSC_FK_TEMP"]
+        if kind == SRC_CONST and not i2f:
+            return K["MSC_FK_CONST"]
+        if kind != SRC_STAGED:
+            return None
+        phys = self.staged_phys.get(idx)
+        if phys == P_I32:
+            return K["MSC_FK_I32F"] if i2f else K["MSC_FK_I32"]
+        if i2f:
+            return None
+        return {P_F32: K["MSC_FK_F32"], P_F64: K["MSC_FK_F64"], P_I64: K["MSC_FK_I64"], P_U8: K["MSC_FK_U8"],
+                P_U16: K["MSC_FK_U16"], P_U32: K["MSC_FK_U32"]}.get(phys)
+
+    def fast_id(self, opname: str, a: int, b: int, dkind: int, tee: int, agg_kind: Optional[int], out_u32: bool) -> int:
+        """Shape id of a pre-compiled specialisation of this instruction, or 0 (generic path)."""
+        fa, fb = self._fk(a), self._fk(b)
+        float_kinds = (K["MSC_FK_F32"], K["MSC_FK_F64"], K["MSC_FK_I32F"])
+        if opname in ("ADD_F", "SUB_F", "MUL_F") and fa is not None and fb is not None and fa <= 4 and fb <= 4:
+            if dkind == DST_TEMP and not tee:
+                dk = 0
+            elif dkind == DST_AGG and agg_kind == K["MSC_AGG_SUM_F"]:
+                dk = 2 if tee else 1
+            else:
+                return 0
+            opi = ("ADD_F", "SUB_F", "MUL_F").index(opname)
+            return K["MSC_FAST_ARITH"] + ((opi * 5 + fa) * 5 + fb) * 3 + dk
+        if tee or fa is None:
+            return 0
+        if opname == "MOV" and dkind == DST_AGG and agg_kind is not None:
+            return K["MSC_FAST_AGGMOV"] + agg_kind * 10 + fa
+        if dkind == DST_FILTER and fb == K["MSC_FK_CONST"] and opname[:2] in ("LT", "LE", "GT", "GE", "EQ", "NE") and len(opname) == 4:
+            is_f = opname.endswith("_F")
+            if fa in (K["MSC_FK_TEMP"], K["MSC_FK_CONST"]) or (fa in float_kinds) != is_f:
+                return 0
+            return K["MSC_FAST_CMP"] + ("LT", "LE", "GT", "GE", "EQ", "NE").index(opname[:2]) * 10 + fa
+        if opname == "MOV" and dkind == DST_GROUP and fa not in float_kinds and fa != K["MSC_FK_CONST"]:
+            return K["MSC_FAST_GROUP"] + fa
+        if opname == "MOV" and dkind == DST_OUT and fa != K["MSC_FK_CONST"]:
+            if out_u32 and fa in float_kinds:
+                return 0
+            return K["MSC_FAST_OUT"] + fa * 2 + int(out_u32)
+        return 0
 
     # -- CSE ------------------------------------------------------------------------------------
     def plan_cse(self, roots: Iterable[Expr]) -> None:
@@ -622,6 +676,7 @@ class ProgramBuilder:
         if isinstance(e, EInput):
             b = self.r.binding(e.index)
             if b.staged is not None:
+                self.staged_phys[b.staged] = b.phys
                 return src(SRC_STAGED, b.staged)
             return src(SRC_GATHER, b.gather | (b.index << 6))
         if isinstance(e, EConst):
@@ -689,11 +744,11 @@ class ProgramBuilder:
         return opname, a, b, frees + frees_b
 
     # -- one expression root into a destination -------------------------------------------------
-    def materialize(self, e: Expr, dkind: int, didx: int = 0) -> Any:
+    def materialize(self, e: Expr, dkind: int, didx: int = 0, agg_kind: Optional[int] = None, out_u32: bool = False) -> Any:
         """Evaluate ``e`` into the destination; returns the dictionary for STR-valued roots."""
         if e in self.cse:
             enc, frees = self._take(e)
-            self.emit("MOV", enc, 0, dkind, didx)
+            self.emit("MOV", enc, 0, dkind, didx, agg_kind=agg_kind, out_u32=out_u32)
             self.release(frees)
             return None
         dict_id = None
@@ -736,7 +791,7 @@ class ProgramBuilder:
                     del self.cse[e]
                     self.release([keep])
                     tee = 0
-        self.emit(opname, a, b, dkind, didx, tee)
+        self.emit(opname, a, b, dkind, didx, tee, agg_kind=agg_kind, out_u32=out_u32)
         self.release(frees)
         return dict_id
 
@@ -744,6 +799,22 @@ class ProgramBuilder:
         self.p.code.extend([OP["END"], 0])
         self.p.text.append("END")
         return self.p
+
+
+def split_conjunctions(filters: Sequence[Expr]) -> list[Expr]:
+    """`a AND b` as a filter is the same as filtering by a, then by b (each becomes one FILTER instruction)."""
+    out: list[Expr] = []
+
+    def walk(e: Expr) -> None:
+        if isinstance(e, EBin) and e.op == "and" and e.left.type == BOOL and e.right.type == BOOL:
+            walk(e.left)
+            walk(e.right)
+        else:
+            out.append(e)
+
+    for f in filters:
+        walk(f)
+    return out
 
 
 _AGG_KINDS = {("sum", FLOAT): K["MSC_AGG_SUM_F"], ("sum", INT): K["MSC_AGG_SUM_I"], ("min", FLOAT): K["MSC_AGG_MIN_F"],
@@ -769,6 +840,7 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
                 raise LoweringError("too many aggregates in one GROUP BY")
             unique[key] = len(unique)
         slot_of.append(unique[key])
+    filters = split_conjunctions(filters)
     b.plan_cse([*filters, group, *[e for (k, e) in unique if k != "count"]])
     for f in filters:
         b.materialize(f, DST_FILTER)
@@ -777,10 +849,10 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
     for (kind, e), slot in unique.items():
         if kind == "count":
             kinds.append(K["MSC_AGG_SUM_I"])
-            b.emit("MOV", src(SRC_CONST, b.const(1)), 0, DST_AGG, slot)
+            b.emit("MOV", src(SRC_CONST, b.const(1)), 0, DST_AGG, slot, agg_kind=K["MSC_AGG_SUM_I"])
             continue
         kinds.append(_AGG_KINDS[(kind, FLOAT if e.type == FLOAT else INT)])
-        b.materialize(e, DST_AGG, slot)
+        b.materialize(e, DST_AGG, slot, agg_kind=kinds[-1])
     return AggregateProgram(b.end(), kinds, slot_of, group_dict)
 
 
@@ -793,6 +865,7 @@ class ProjectProgram:
 
 def compile_project(resolver: Resolver, filters: Sequence[Expr], outputs: Sequence[Expr]) -> ProjectProgram:
     b = ProgramBuilder(resolver)
+    filters = split_conjunctions(filters)
     b.plan_cse([*filters, *outputs])
     for f in filters:
         b.materialize(f, DST_FILTER)
@@ -803,6 +876,6 @@ def compile_project(resolver: Resolver, filters: Sequence[Expr], outputs: Sequen
     out_phys: list[int] = []
     out_dicts: list[Any] = []
     for i, e in enumerate(outputs):
-        out_dicts.append(b.materialize(e, DST_OUT, i))
         out_phys.append(P_U32 if e.type == STR else (P_F64 if e.type == FLOAT else P_I64))
+        out_dicts.append(b.materialize(e, DST_OUT, i, out_u32=out_phys[-1] == P_U32))
     return ProjectProgram(b.end(), out_phys, out_dicts)
