@@ -122,15 +122,17 @@ enum msc_opcode {
 /* families: id = base + formula
  *   ARITH  1 + ((opi*5 + ak)*5 + bk)*3 + dk   opi: 0 ADD_F 1 SUB_F 2 MUL_F; ak,bk in F32,F64,TEMP,CONST,I32F;
  *                                             dk: 0 -> TEMP, 1 -> AGG (SUM_F), 2 -> AGG + tee TEMP
- *   AGGMOV 256 + agg_kind*10 + fk             accumulator <- source
- *   CMP    320 + cmpi*10 + fk                 FILTER <- source <cmp> CONST; cmpi: LT LE GT GE EQ NE
- *   GROUP  384 + fk                           GROUP <- source
- *   OUT    400 + fk*2 + (out is U32)          OUT column <- source */
+ *   AGGMOV 226 + agg_kind*10 + fk             accumulator <- source
+ *   CMP    286 + cmpi*10 + fk                 FILTER <- source <cmp> CONST; cmpi: LT LE GT GE EQ NE
+ *   GROUP  346 + fk                           GROUP <- source
+ *   OUT    356 + fk*2 + (out is U32)          OUT column <- source
+ * The ids are dense (1..375) so the kernel's dispatch is a single jump table.  For a fast
+ * instruction the library rewrites STAGED operand indices into shared-memory offsets / 16. */
 #define MSC_FAST_ARITH 1
-#define MSC_FAST_AGGMOV 256
-#define MSC_FAST_CMP 320
-#define MSC_FAST_GROUP 384
-#define MSC_FAST_OUT 400
+#define MSC_FAST_AGGMOV 226
+#define MSC_FAST_CMP 286
+#define MSC_FAST_GROUP 346
+#define MSC_FAST_OUT 356
 
 #define MSC_VM_MAX_TEMPS 8
 #define MSC_VM_MAX_CODE 192  /* u32 words = 96 instructions */

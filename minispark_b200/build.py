@@ -14,7 +14,8 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libminispark_cuda.so"
 OBJ_DIR = PKG / "build"
-SOURCES = ["core.cu", "scan.cu", "strings.cu", "ingest.cu", "join.cu", "result.cu"]
+SOURCES = ["scan_inst_r4_dense.cu", "scan_inst_r8_dense.cu", "scan_inst_r4_hash.cu", "scan_inst_r8_hash.cu", "scan_inst_r4_count.cu",
+           "scan_inst_r4_project.cu", "core.cu", "scan.cu", "strings.cu", "ingest.cu", "join.cu", "result.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--diag-suppress", "177",

@@ -1,0 +1,912 @@
+// scan_kernel.cuh -- the fused scan -> filter -> project -> aggregate kernel (device side).
+//
+// One persistent kernel walks the relation in warp tiles of 32 x R rows.  Every warp runs its own
+// pipeline: lane 0 bulk-copies the tile's column segments global->shared with cp.async.bulk (TMA
+// 1-D, mbarrier complete_tx) into a private multi-stage ring, so HBM latency is hidden by the ring
+// and warps never wait for each other.  Each lane owns R consecutive rows and evaluates the
+// three-address expression program (include/minispark_cuda.h) for them.  Temporaries are per-lane
+// slots in shared memory, so no interpreter state lives in registers between instructions; hot
+// instruction shapes run through handlers specialised at C++ compile time (run_fast), everything
+// else through the generic fetch / compute / store path.
+//
+// Replaces, in one pass and without materialising intermediates (reference file:line):
+//   FilterTask.execute      src/mini_spark/tasks.py:167-177   (templates/plan.zig:130-147, task_utils.zig:9-51)
+//   ProjectTask.execute     src/mini_spark/tasks.py:79-84     (templates/plan.zig:113-125)
+//   AggregateTask.execute   src/mini_spark/tasks.py:270-310   (templates/plan.zig:150-253)
+//   Col.execute_row         src/mini_spark/sql.py:262-266
+#pragma once
+#include "common.cuh"
+
+namespace mscan {
+
+constexpr int NT = 128;  // threads per CTA (4 independent warp pipelines)
+constexpr int NW = NT / 32;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_HEADER = NW * MAX_STAGES * 8;  // mbarriers: full[warp][stage]
+
+enum Mode { MODE_DENSE = 0, MODE_HASH = 1, MODE_COUNT = 2, MODE_PROJECT = 3 };
+
+struct StagedCol {
+  const unsigned char* base;
+  uint32_t width;
+  uint32_t smem_off;  // offset inside one warp stage
+  int phys;
+  int _pad;
+};
+
+struct ScanParams {
+  uint64_t nrows;
+  uint32_t ntiles;       // warp tiles of 32*R rows
+  uint32_t nstages;
+  uint32_t stage_bytes;  // one warp stage (all staged columns)
+  uint32_t warp_bytes;   // nstages * stage_bytes + temporaries of one warp
+  uint32_t nstaged;
+  uint32_t ntemps;
+  StagedCol staged[MSC_VM_MAX_STAGED];
+  const void* gather[MSC_VM_MAX_GATHER];
+  int gather_phys[MSC_VM_MAX_GATHER];
+  const void* luts[MSC_VM_MAX_LUTS];
+  uint32_t code[MSC_VM_MAX_CODE];
+  long long consts[MSC_VM_MAX_CONSTS];
+  int* err;
+  // dense aggregation: naggs includes the hidden per-group row counter (last slot)
+  int ngroups;
+  int naggs;
+  long long agg_init[MSC_VM_MAX_AGGS + 1];
+  int agg_kind[MSC_VM_MAX_AGGS + 1];
+  unsigned long long* dense_out;  // [ngroups][naggs]
+  // hash aggregation
+  unsigned long long* hkeys;
+  unsigned long long* haccs;  // [naggs][capacity]
+  uint64_t hcap;              // power of two
+  // count / project
+  uint32_t* tile_counts;
+  const uint64_t* tile_offsets;  // nullptr: no filter, output position = row
+  void* out[MSC_VM_MAX_OUT];
+  int out_phys[MSC_VM_MAX_OUT];
+};
+
+struct LaunchPlan {
+  ScanParams p;
+  int R;
+  size_t smem;
+  int grid;
+};
+
+template <int R, int MODE>
+int launch_scan(msc_ctx* ctx, LaunchPlan* lp);
+
+constexpr unsigned long long HASH_EMPTY = 0x8000000000000000ULL;
+
+#if defined(__CUDACC__) && !defined(MSCAN_DECL_ONLY)
+// ------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ double l2d(long long v) { return __longlong_as_double(v); }
+__device__ __forceinline__ long long d2l(double v) { return __double_as_longlong(v); }
+
+// ------------------------------------------------------------------------------------------------
+// scalar op semantics that follow Python (the oracle is PythonExecutionEngine, sql.py:262-266)
+// ------------------------------------------------------------------------------------------------
+static __device__ __noinline__ long long py_floordiv_i(long long a, long long b) {
+  if (b == 0) return 0;
+  long long q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+static __device__ __noinline__ long long py_mod_i(long long a, long long b) {
+  if (b == 0) return 0;
+  long long m = a % b;
+  if (m != 0 && ((m < 0) != (b < 0))) m += b;
+  return m;
+}
+// CPython float_divmod (Objects/floatobject.c): floor division and modulo of doubles
+static __device__ __noinline__ void py_divmod_f(double vx, double wx, double* fd, double* md) {
+  if (wx == 0.0) {
+    *fd = 0.0;
+    *md = 0.0;
+    return;
+  }
+  double mod = fmod(vx, wx);
+  double div = (vx - mod) / wx;
+  if (mod != 0.0) {
+    if ((wx < 0) != (mod < 0)) {
+      mod += wx;
+      div -= 1.0;
+    }
+  } else {
+    mod = copysign(0.0, wx);
+  }
+  double floordiv;
+  if (div != 0.0) {
+    floordiv = floor(div);
+    if (div - floordiv > 0.5) floordiv += 1.0;
+  } else {
+    floordiv = copysign(0.0, vx / wx);
+  }
+  *fd = floordiv;
+  *md = mod;
+}
+
+template <int R>
+__device__ __forceinline__ void flag_zero_divisor(const long long (&b)[R], bool is_float, uint32_t vmask, int* err) {
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool z = is_float ? (l2d(b[r]) == 0.0) : (b[r] == 0);
+    bad |= z && ((vmask >> r) & 1u);
+  }
+  if (bad) atomicOr(err, MSC_DEVERR_DIV_ZERO);
+}
+
+// a = a <op> b for R rows (generic path)
+template <int R>
+__device__ __forceinline__ void binop(int op, long long (&a)[R], const long long (&b)[R], uint32_t vmask, int* err) {
+  switch (op) {
+#define F_ARITH(OP, EXPR)                             \
+  case OP: {                                          \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) {   \
+      const double x = l2d(a[r]), y = l2d(b[r]);      \
+      a[r] = d2l(EXPR);                               \
+    }                                                 \
+  } break;
+#define I_ARITH(OP, EXPR)                             \
+  case OP: {                                          \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) {   \
+      const long long x = a[r], y = b[r];             \
+      a[r] = (EXPR);                                  \
+    }                                                 \
+  } break;
+    F_ARITH(MSC_OP_ADD_F, x + y)
+    F_ARITH(MSC_OP_SUB_F, x - y)
+    F_ARITH(MSC_OP_MUL_F, x * y)
+    case MSC_OP_DIV_F: {
+      flag_zero_divisor<R>(b, true, vmask, err);
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = d2l(l2d(b[r]) == 0.0 ? 0.0 : l2d(a[r]) / l2d(b[r]));
+    } break;
+    case MSC_OP_FLOORDIV_F:
+    case MSC_OP_MOD_F: {
+      flag_zero_divisor<R>(b, true, vmask, err);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double fd, md;
+        py_divmod_f(l2d(a[r]), l2d(b[r]), &fd, &md);
+        a[r] = d2l(op == MSC_OP_FLOORDIV_F ? fd : md);
+      }
+    } break;
+    I_ARITH(MSC_OP_ADD_I, x + y)
+    I_ARITH(MSC_OP_SUB_I, x - y)
+    I_ARITH(MSC_OP_MUL_I, x * y)
+    case MSC_OP_FLOORDIV_I: {
+      flag_zero_divisor<R>(b, false, vmask, err);
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = py_floordiv_i(a[r], b[r]);
+    } break;
+    case MSC_OP_MOD_I: {
+      flag_zero_divisor<R>(b, false, vmask, err);
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = py_mod_i(a[r], b[r]);
+    } break;
+    default: break;
+  }
+#undef F_ARITH
+#undef I_ARITH
+}
+
+// comparisons and boolean ops: result is i64 0/1 (generic path)
+template <int R>
+__device__ __forceinline__ void cmpop(int op, long long (&a)[R], const long long (&b)[R]) {
+  switch (op) {
+#define F_CMP(OP, REL)                                                                        \
+  case OP: {                                                                                  \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) a[r] = (l2d(a[r]) REL l2d(b[r])) ? 1 : 0;   \
+  } break;
+#define I_CMP(OP, REL)                                                              \
+  case OP: {                                                                        \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) a[r] = (a[r] REL b[r]) ? 1 : 0;   \
+  } break;
+    F_CMP(MSC_OP_LT_F, <)
+    F_CMP(MSC_OP_LE_F, <=)
+    F_CMP(MSC_OP_GT_F, >)
+    F_CMP(MSC_OP_GE_F, >=)
+    F_CMP(MSC_OP_EQ_F, ==)
+    F_CMP(MSC_OP_NE_F, !=)
+    I_CMP(MSC_OP_LT_I, <)
+    I_CMP(MSC_OP_LE_I, <=)
+    I_CMP(MSC_OP_GT_I, >)
+    I_CMP(MSC_OP_GE_I, >=)
+    I_CMP(MSC_OP_EQ_I, ==)
+    I_CMP(MSC_OP_NE_I, !=)
+    case MSC_OP_AND: {
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = a[r] & b[r];
+    } break;
+    case MSC_OP_OR: {
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = a[r] | b[r];
+    } break;
+    default: break;
+  }
+#undef F_CMP
+#undef I_CMP
+}
+
+// ------------------------------------------------------------------------------------------------
+// column loads.  A lane's R rows are consecutive, so a column segment is read with the widest
+// shared-memory vector loads.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void lds_words(const unsigned char* ptr, uint32_t (&w)[W / 4]) {
+  if constexpr (W == 4) {
+    w[0] = *reinterpret_cast<const uint32_t*>(ptr);
+  } else if constexpr (W == 8) {
+    const uint2 v = *reinterpret_cast<const uint2*>(ptr);
+    w[0] = v.x;
+    w[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < W / 16; ++i) {
+      const uint4 v = reinterpret_cast<const uint4*>(ptr)[i];
+      w[4 * i + 0] = v.x;
+      w[4 * i + 1] = v.y;
+      w[4 * i + 2] = v.z;
+      w[4 * i + 3] = v.w;
+    }
+  }
+}
+
+template <int R, int PHYS>
+__device__ __forceinline__ void load_staged(const unsigned char* col_smem, int lane, long long (&dst)[R]) {
+  constexpr int WIDTH = (PHYS == MSC_P_U8) ? 1 : (PHYS == MSC_P_U16) ? 2 : (PHYS == MSC_P_I64 || PHYS == MSC_P_F64) ? 8 : 4;
+  constexpr int W = WIDTH * R;
+  uint32_t w[W / 4];
+  lds_words<W>(col_smem + lane * W, w);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if constexpr (PHYS == MSC_P_U8) dst[r] = (w[r / 4] >> (8 * (r % 4))) & 0xffu;
+    else if constexpr (PHYS == MSC_P_U16) dst[r] = (w[r / 2] >> (16 * (r % 2))) & 0xffffu;
+    else if constexpr (PHYS == MSC_P_U32) dst[r] = static_cast<long long>(w[r]);
+    else if constexpr (PHYS == MSC_P_I32) dst[r] = static_cast<long long>(static_cast<int>(w[r]));
+    else if constexpr (PHYS == MSC_P_F32) dst[r] = d2l(static_cast<double>(__uint_as_float(w[r])));
+    else dst[r] = static_cast<long long>((static_cast<unsigned long long>(w[2 * r + 1]) << 32) | w[2 * r]);
+  }
+}
+
+// Load through an index vector (staged u32 column): dst[r] = column[index[r]].
+template <int R, int PHYS>
+__device__ __forceinline__ void load_gather(const unsigned char* idx_smem, const void* col, int lane, uint32_t vmask,
+                                            long long (&dst)[R]) {
+  uint32_t idx[R];
+  lds_words<4 * R>(idx_smem + lane * 4 * R, idx);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    long long v = 0;
+    if ((vmask >> r) & 1u) {
+      const uint32_t i = idx[r];
+      if constexpr (PHYS == MSC_P_U8) v = __ldg(reinterpret_cast<const uint8_t*>(col) + i);
+      else if constexpr (PHYS == MSC_P_U16) v = __ldg(reinterpret_cast<const uint16_t*>(col) + i);
+      else if constexpr (PHYS == MSC_P_U32) v = __ldg(reinterpret_cast<const uint32_t*>(col) + i);
+      else if constexpr (PHYS == MSC_P_I32) v = __ldg(reinterpret_cast<const int*>(col) + i);
+      else if constexpr (PHYS == MSC_P_F32) v = d2l(static_cast<double>(__ldg(reinterpret_cast<const float*>(col) + i)));
+      else v = __ldg(reinterpret_cast<const long long*>(col) + i);
+    }
+    dst[r] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregation helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long agg_combine(int kind, long long cur, long long v) {
+  switch (kind) {
+    case MSC_AGG_SUM_F: return d2l(l2d(cur) + l2d(v));
+    case MSC_AGG_SUM_I: return cur + v;
+    case MSC_AGG_MIN_F: return (l2d(v) < l2d(cur)) ? v : cur;
+    case MSC_AGG_MAX_F: return (l2d(v) > l2d(cur)) ? v : cur;
+    case MSC_AGG_MIN_I: return (v < cur) ? v : cur;
+    default: return (v > cur) ? v : cur;  // MSC_AGG_MAX_I
+  }
+}
+
+__device__ __forceinline__ void atomic_fold(int kind, unsigned long long* addr, long long v) {
+  switch (kind) {
+    case MSC_AGG_SUM_F: atomicAdd(reinterpret_cast<double*>(addr), l2d(v)); break;
+    case MSC_AGG_SUM_I: atomicAdd(addr, static_cast<unsigned long long>(v)); break;
+    case MSC_AGG_MIN_I: atomicMin(reinterpret_cast<long long*>(addr), v); break;
+    case MSC_AGG_MAX_I: atomicMax(reinterpret_cast<long long*>(addr), v); break;
+    default: {  // f64 min / max: CAS loop
+      unsigned long long old = *addr;
+      while (true) {
+        const long long merged = agg_combine(kind, static_cast<long long>(old), v);
+        if (static_cast<unsigned long long>(merged) == old) break;
+        const unsigned long long prev = atomicCAS(addr, old, static_cast<unsigned long long>(merged));
+        if (prev == old) break;
+        old = prev;
+      }
+    }
+  }
+}
+
+// hash mode: one atomic per run of equal keys among a lane's R consecutive rows (clustered tables,
+// e.g. lineitem by orderkey, fold in registers first)
+template <int R, int KIND>
+__device__ __forceinline__ void agg_hash(unsigned long long* haccs, uint64_t hcap, int a, const int (&grp)[R],
+                                         const long long (&v)[R]) {
+  unsigned long long* base = haccs + static_cast<uint64_t>(a) * hcap;
+  long long run = v[0];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int nxt = (r + 1 < R) ? r + 1 : r;
+    const bool same_next = (r + 1 < R) && grp[r] >= 0 && grp[nxt] == grp[r];
+    if (same_next) {
+      run = agg_combine(KIND, run, v[nxt]);
+    } else {
+      if (grp[r] >= 0) atomic_fold(KIND, base + grp[r], run);
+      run = v[nxt];
+    }
+  }
+}
+
+__device__ __forceinline__ int hash_find_or_insert(unsigned long long* keys, uint64_t cap, long long key, int* err) {
+  const uint64_t mask = cap - 1;
+  uint64_t pos = msc_mix64(static_cast<uint64_t>(key)) & mask;
+  const unsigned long long k = static_cast<unsigned long long>(key);
+  for (uint64_t probe = 0; probe < cap; ++probe) {
+    unsigned long long cur = keys[pos];
+    if (cur == k) return static_cast<int>(pos);
+    if (cur == HASH_EMPTY) {
+      const unsigned long long prev = atomicCAS(keys + pos, HASH_EMPTY, k);
+      if (prev == HASH_EMPTY || prev == k) return static_cast<int>(pos);
+    }
+    pos = (pos + 1) & mask;
+  }
+  atomicOr(err, MSC_DEVERR_TABLE_FULL);
+  return -1;
+}
+
+// exclusive prefix sum of one u32 per lane across the warp; total in *total
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, int lane, uint32_t* total) {
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// execution context of one warp tile
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  const ScanParams& p;
+  const unsigned char* sbase;  // this warp's current stage
+  long long* temps;            // this warp's temporaries: [(idx * R + r) * 32 + lane]
+  long long* acc;              // CTA accumulators: [(group * naggs + slot) * NT + tid]
+  int lane;
+  int tid;
+};
+
+template <int R>
+__device__ __forceinline__ void fetch_temp(const Ctx& c, int idx, long long (&v)[R]) {
+  const long long* t = c.temps + (idx * R) * 32 + c.lane;
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = t[r * 32];
+}
+template <int R>
+__device__ __forceinline__ void store_temp(const Ctx& c, int idx, const long long (&v)[R]) {
+  long long* t = c.temps + (idx * R) * 32 + c.lane;
+#pragma unroll
+  for (int r = 0; r < R; ++r) t[r * 32] = v[r];
+}
+template <int R>
+__device__ __forceinline__ void to_f64(long long (&v)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = d2l(static_cast<double>(v[r]));
+}
+
+template <int R>
+__device__ __forceinline__ void fetch_staged(const Ctx& c, int idx, long long (&v)[R]) {
+  const unsigned char* col = c.sbase + c.p.staged[idx].smem_off;
+  switch (c.p.staged[idx].phys) {
+    case MSC_P_U8: load_staged<R, MSC_P_U8>(col, c.lane, v); break;
+    case MSC_P_U16: load_staged<R, MSC_P_U16>(col, c.lane, v); break;
+    case MSC_P_U32: load_staged<R, MSC_P_U32>(col, c.lane, v); break;
+    case MSC_P_I32: load_staged<R, MSC_P_I32>(col, c.lane, v); break;
+    case MSC_P_F32: load_staged<R, MSC_P_F32>(col, c.lane, v); break;
+    default: load_staged<R, MSC_P_I64>(col, c.lane, v); break;  // I64 and F64: raw 64-bit pattern
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void fetch_gather(const Ctx& c, int idx, uint32_t vmask, long long (&v)[R]) {
+  const unsigned char* ix = c.sbase + c.p.staged[idx >> 6].smem_off;
+  const void* col = c.p.gather[idx & 63];
+  switch (c.p.gather_phys[idx & 63]) {
+    case MSC_P_U8: load_gather<R, MSC_P_U8>(ix, col, c.lane, vmask, v); break;
+    case MSC_P_U16: load_gather<R, MSC_P_U16>(ix, col, c.lane, vmask, v); break;
+    case MSC_P_U32: load_gather<R, MSC_P_U32>(ix, col, c.lane, vmask, v); break;
+    case MSC_P_I32: load_gather<R, MSC_P_I32>(ix, col, c.lane, vmask, v); break;
+    case MSC_P_F32: load_gather<R, MSC_P_F32>(ix, col, c.lane, vmask, v); break;
+    default: load_gather<R, MSC_P_I64>(ix, col, c.lane, vmask, v); break;
+  }
+}
+
+// generic operand fetch: the i2f variants are separate switch targets (a flag test would be
+// if-converted into R predicated 64-bit conversions on every fetch)
+template <int R>
+__device__ __forceinline__ void fetch(const Ctx& c, uint32_t operand, uint32_t vmask, long long (&v)[R]) {
+  const int idx = operand & 0xfff;
+  switch ((operand >> 12) & 15) {
+    case MSC_SRC_TEMP: fetch_temp<R>(c, idx, v); break;
+    case MSC_SRC_TEMP | MSC_SRC_I2F: fetch_temp<R>(c, idx, v); to_f64<R>(v); break;
+    case MSC_SRC_STAGED: fetch_staged<R>(c, idx, v); break;
+    case MSC_SRC_STAGED | MSC_SRC_I2F: fetch_staged<R>(c, idx, v); to_f64<R>(v); break;
+    case MSC_SRC_GATHER: fetch_gather<R>(c, idx, vmask, v); break;
+    case MSC_SRC_GATHER | MSC_SRC_I2F: fetch_gather<R>(c, idx, vmask, v); to_f64<R>(v); break;
+    case MSC_SRC_CONST: {
+      const long long k = c.p.consts[idx];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = k;
+    } break;
+    default: {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = 0;
+    } break;
+  }
+}
+
+template <int R, class TLut>
+__device__ __forceinline__ void op_lut(long long (&x)[R], const TLut* lut, uint32_t vmask) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) x[r] = ((vmask >> r) & 1u) ? static_cast<long long>(__ldg(lut + x[r])) : 0;
+}
+
+template <int R, int KIND>
+__device__ __forceinline__ void agg_dense_k(const Ctx& c, int slot, const int (&grp)[R], const long long (&v)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    long long* q = c.acc + (grp[r] * c.p.naggs + slot) * NT + c.tid;
+    *q = agg_combine(KIND, *q, v[r]);
+  }
+}
+
+template <int R, int MODE>
+__device__ __forceinline__ void agg_any(const Ctx& c, int slot, int kind, const int (&grp)[R], const long long (&v)[R]) {
+  switch (kind) {
+#define AGG_ANY_CASE(KIND)                                                                          \
+  case KIND:                                                                                        \
+    if constexpr (MODE == MODE_DENSE) agg_dense_k<R, KIND>(c, slot, grp, v);                        \
+    else if constexpr (MODE == MODE_HASH) agg_hash<R, KIND>(c.p.haccs, c.p.hcap, slot, grp, v);     \
+    break;
+    AGG_ANY_CASE(MSC_AGG_SUM_F)
+    AGG_ANY_CASE(MSC_AGG_SUM_I)
+    AGG_ANY_CASE(MSC_AGG_MIN_F)
+    AGG_ANY_CASE(MSC_AGG_MAX_F)
+    AGG_ANY_CASE(MSC_AGG_MIN_I)
+    default:
+      if constexpr (MODE == MODE_DENSE) agg_dense_k<R, MSC_AGG_MAX_I>(c, slot, grp, v);
+      else if constexpr (MODE == MODE_HASH) agg_hash<R, MSC_AGG_MAX_I>(c.p.haccs, c.p.hcap, slot, grp, v);
+      break;
+#undef AGG_ANY_CASE
+  }
+}
+
+template <int R, int MODE>
+__device__ __forceinline__ void set_group(const Ctx& c, const long long (&x)[R], uint32_t vmask, int (&grp)[R]) {
+  if constexpr (MODE == MODE_DENSE) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int g = c.p.ngroups;  // rows that failed the filter fold into a trash group that is never exported
+      if ((vmask >> r) & 1u) {
+        const long long code = x[r];
+        g = (code >= 0 && code < c.p.ngroups) ? static_cast<int>(code) : c.p.ngroups;
+      }
+      grp[r] = g;
+      c.acc[(g * c.p.naggs + (c.p.naggs - 1)) * NT + c.tid] += 1;  // hidden per-group row counter
+    }
+  } else if constexpr (MODE == MODE_HASH) {
+    long long prev_key = 0;
+    int prev_slot = -1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int slot = -1;
+      if ((vmask >> r) & 1u) {
+        long long key = x[r];
+        if (key == static_cast<long long>(HASH_EMPTY)) key = 0;  // -0.0 groups with +0.0, like a Python dict
+        slot = (prev_slot >= 0 && key == prev_key) ? prev_slot : hash_find_or_insert(c.p.hkeys, c.p.hcap, key, c.p.err);
+        prev_key = key;
+        prev_slot = slot;
+      }
+      grp[r] = slot;
+    }
+  }
+}
+
+template <int R, class TOut>
+__device__ __forceinline__ void store_out(const long long (&x)[R], TOut* out, uint64_t pos, uint32_t vmask) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if ((vmask >> r) & 1u) {
+      out[pos] = static_cast<TOut>(x[r]);
+      ++pos;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast shapes: handlers specialised at C++ compile time on (operand kinds, op, destination).  The
+// host picks the shape id (`fast` field of w0, include/minispark_cuda.h MSC_FAST_*) and rewrites
+// staged operand indices into (shared-memory offset / 16), so a handler needs no table lookups.
+// The ids are dense, so the switch below compiles to a single jump table.
+// ------------------------------------------------------------------------------------------------
+template <int R, int FK>
+__device__ __forceinline__ void ffetch(const Ctx& c, int idx, long long (&v)[R]) {
+  if constexpr (FK == MSC_FK_TEMP) {
+    fetch_temp<R>(c, idx, v);
+  } else if constexpr (FK == MSC_FK_CONST) {
+    const long long k = c.p.consts[idx];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = k;
+  } else {
+    const unsigned char* col = c.sbase + (idx << 4);
+    if constexpr (FK == MSC_FK_F32) load_staged<R, MSC_P_F32>(col, c.lane, v);
+    else if constexpr (FK == MSC_FK_F64 || FK == MSC_FK_I64) load_staged<R, MSC_P_I64>(col, c.lane, v);
+    else if constexpr (FK == MSC_FK_I32) load_staged<R, MSC_P_I32>(col, c.lane, v);
+    else if constexpr (FK == MSC_FK_I32F) {
+      load_staged<R, MSC_P_I32>(col, c.lane, v);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = d2l(static_cast<double>(static_cast<int>(v[r])));
+    } else if constexpr (FK == MSC_FK_U8) load_staged<R, MSC_P_U8>(col, c.lane, v);
+    else if constexpr (FK == MSC_FK_U16) load_staged<R, MSC_P_U16>(col, c.lane, v);
+    else load_staged<R, MSC_P_U32>(col, c.lane, v);
+  }
+}
+
+template <int R, int MODE, int KIND>
+__device__ __forceinline__ void fast_agg(const Ctx& c, int slot, const int (&grp)[R], const long long (&v)[R]) {
+  if constexpr (MODE == MODE_DENSE) agg_dense_k<R, KIND>(c, slot, grp, v);
+  else if constexpr (MODE == MODE_HASH) agg_hash<R, KIND>(c.p.haccs, c.p.hcap, slot, grp, v);
+}
+
+// dst <- A (+|-|*) B on f64; DK: 0 TEMP, 1 AGG(SUM_F), 2 AGG(SUM_F) + tee TEMP
+template <int R, int MODE, int OPI, int AK, int BK, int DK>
+__device__ __forceinline__ void fast_arith(const Ctx& c, uint32_t w0, uint32_t w1, const int (&grp)[R]) {
+  long long a[R], b[R];
+  ffetch<R, AK>(c, w1 & 0xfff, a);
+  ffetch<R, BK>(c, (w1 >> 16) & 0xfff, b);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double x = l2d(a[r]), y = l2d(b[r]);
+    a[r] = d2l(OPI == 0 ? x + y : (OPI == 1 ? x - y : x * y));
+  }
+  const int dst = (w0 >> 13) & 0x7f;
+  if constexpr (DK == 0) store_temp<R>(c, dst, a);
+  if constexpr (DK == 2) store_temp<R>(c, static_cast<int>((w0 >> 9) & 0xf) - 1, a);
+  if constexpr (DK >= 1) fast_agg<R, MODE, MSC_AGG_SUM_F>(c, dst, grp, a);
+}
+
+template <int R, int MODE, int KIND, int FK>
+__device__ __forceinline__ void fast_aggmov(const Ctx& c, uint32_t w0, uint32_t w1, const int (&grp)[R]) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  fast_agg<R, MODE, KIND>(c, (w0 >> 13) & 0x7f, grp, a);
+}
+
+template <int R, int CMPI, int FK>
+__device__ __forceinline__ void fast_cmp_filter(const Ctx& c, uint32_t w1, uint32_t& vmask) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  const long long k = c.p.consts[(w1 >> 16) & 0xfff];
+  constexpr bool is_f = FK == MSC_FK_F32 || FK == MSC_FK_F64 || FK == MSC_FK_I32F;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    bool t;
+    if constexpr (is_f) {
+      const double x = l2d(a[r]), y = l2d(k);
+      t = CMPI == 0 ? x < y : CMPI == 1 ? x <= y : CMPI == 2 ? x > y : CMPI == 3 ? x >= y : CMPI == 4 ? x == y : x != y;
+    } else {
+      const long long x = a[r];
+      t = CMPI == 0 ? x < k : CMPI == 1 ? x <= k : CMPI == 2 ? x > k : CMPI == 3 ? x >= k : CMPI == 4 ? x == k : x != k;
+    }
+    if (!t) vmask &= ~(1u << r);
+  }
+}
+
+template <int R, int MODE, int FK>
+__device__ __forceinline__ void fast_group(const Ctx& c, uint32_t w1, uint32_t vmask, int (&grp)[R]) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  set_group<R, MODE>(c, a, vmask, grp);
+}
+
+template <int R, int FK, int U32OUT>
+__device__ __forceinline__ void fast_out(const Ctx& c, uint32_t w0, uint32_t w1, uint64_t out_pos, uint32_t vmask) {
+  long long a[R];
+  ffetch<R, FK>(c, w1 & 0xfff, a);
+  void* out = c.p.out[(w0 >> 13) & 0x7f];
+  if constexpr (U32OUT) store_out<R, uint32_t>(a, reinterpret_cast<uint32_t*>(out), out_pos, vmask);
+  else store_out<R, long long>(a, reinterpret_cast<long long*>(out), out_pos, vmask);
+}
+
+__host__ __device__ constexpr bool fk_is_float(int fk) { return fk == MSC_FK_F32 || fk == MSC_FK_F64 || fk == MSC_FK_I32F; }
+__host__ __device__ constexpr bool fk_is_int_col(int fk) { return fk == MSC_FK_I32 || fk == MSC_FK_I64; }
+__host__ __device__ constexpr bool fk_is_code(int fk) { return fk == MSC_FK_U8 || fk == MSC_FK_U16 || fk == MSC_FK_U32; }
+__host__ __device__ constexpr bool aggmov_valid(int kind, int fk) {
+  const bool fkind = kind == MSC_AGG_SUM_F || kind == MSC_AGG_MIN_F || kind == MSC_AGG_MAX_F;
+  if (fk == MSC_FK_TEMP) return true;
+  if (fkind) return fk_is_float(fk);
+  return fk_is_int_col(fk) || (fk == MSC_FK_CONST && kind == MSC_AGG_SUM_I);
+}
+__host__ __device__ constexpr bool cmp_valid(int fk) { return fk != MSC_FK_TEMP && fk != MSC_FK_CONST; }
+__host__ __device__ constexpr bool group_valid(int fk) { return fk == MSC_FK_TEMP || fk_is_int_col(fk) || fk_is_code(fk); }
+__host__ __device__ constexpr bool out_valid(int fk, int u32) {
+  if (fk == MSC_FK_CONST) return false;
+  return u32 ? (fk_is_code(fk) || fk == MSC_FK_TEMP) : !fk_is_code(fk);
+}
+
+// returns false when the id is not a compiled shape (the caller then runs the generic path)
+template <int R, int MODE>
+__device__ __forceinline__ bool run_fast(const Ctx& c, int fast, uint32_t w0, uint32_t w1, uint32_t& vmask, int (&grp)[R],
+                                         uint64_t out_pos) {
+  constexpr bool AGG = MODE == MODE_DENSE || MODE == MODE_HASH;
+  switch (fast) {
+#define ARITH_CASE(OPI, AK, BK, DK)                                                      \
+  case MSC_FAST_ARITH + (((OPI) * 5 + (AK)) * 5 + (BK)) * 3 + (DK):                      \
+    if constexpr (AGG || DK == 0) {                                                      \
+      fast_arith<R, MODE, OPI, AK, BK, DK>(c, w0, w1, grp);                              \
+      return true;                                                                       \
+    } else {                                                                             \
+      return false;                                                                      \
+    }
+#define ARITH_DK(OPI, AK, BK) ARITH_CASE(OPI, AK, BK, 0) ARITH_CASE(OPI, AK, BK, 1) ARITH_CASE(OPI, AK, BK, 2)
+#define ARITH_BK(OPI, AK) ARITH_DK(OPI, AK, 0) ARITH_DK(OPI, AK, 1) ARITH_DK(OPI, AK, 2) ARITH_DK(OPI, AK, 3) ARITH_DK(OPI, AK, 4)
+#define ARITH_AK(OPI) ARITH_BK(OPI, 0) ARITH_BK(OPI, 1) ARITH_BK(OPI, 2) ARITH_BK(OPI, 3) ARITH_BK(OPI, 4)
+    ARITH_AK(0)
+    ARITH_AK(1)
+    ARITH_AK(2)
+#undef ARITH_AK
+#undef ARITH_BK
+#undef ARITH_DK
+#undef ARITH_CASE
+#define FK_ALL(M, X) M(X, 0) M(X, 1) M(X, 2) M(X, 3) M(X, 4) M(X, 5) M(X, 6) M(X, 7) M(X, 8) M(X, 9)
+#define AGGMOV_CASE(KIND, FK)                                     \
+  case MSC_FAST_AGGMOV + (KIND) * 10 + (FK):                      \
+    if constexpr (AGG && aggmov_valid(KIND, FK)) {                \
+      fast_aggmov<R, MODE, KIND, FK>(c, w0, w1, grp);             \
+      return true;                                                \
+    } else {                                                      \
+      return false;                                               \
+    }
+    FK_ALL(AGGMOV_CASE, 0) FK_ALL(AGGMOV_CASE, 1) FK_ALL(AGGMOV_CASE, 2) FK_ALL(AGGMOV_CASE, 3) FK_ALL(AGGMOV_CASE, 4)
+    FK_ALL(AGGMOV_CASE, 5)
+#undef AGGMOV_CASE
+#define CMP_CASE(CMPI, FK)                                        \
+  case MSC_FAST_CMP + (CMPI) * 10 + (FK):                         \
+    if constexpr (cmp_valid(FK)) {                                \
+      fast_cmp_filter<R, CMPI, FK>(c, w1, vmask);                 \
+      return true;                                                \
+    } else {                                                      \
+      return false;                                               \
+    }
+    FK_ALL(CMP_CASE, 0) FK_ALL(CMP_CASE, 1) FK_ALL(CMP_CASE, 2) FK_ALL(CMP_CASE, 3) FK_ALL(CMP_CASE, 4) FK_ALL(CMP_CASE, 5)
+#undef CMP_CASE
+#define GROUP_CASE(UNUSED, FK)                                    \
+  case MSC_FAST_GROUP + (FK):                                     \
+    if constexpr (AGG && group_valid(FK)) {                       \
+      fast_group<R, MODE, FK>(c, w1, vmask, grp);                 \
+      return true;                                                \
+    } else {                                                      \
+      return false;                                               \
+    }
+    FK_ALL(GROUP_CASE, 0)
+#undef GROUP_CASE
+#define OUT_CASE(U32OUT, FK)                                      \
+  case MSC_FAST_OUT + (FK) * 2 + (U32OUT):                        \
+    if constexpr (MODE == MODE_PROJECT && out_valid(FK, U32OUT)) {\
+      fast_out<R, FK, U32OUT>(c, w0, w1, out_pos, vmask);         \
+      return true;                                                \
+    } else {                                                      \
+      return false;                                               \
+    }
+    FK_ALL(OUT_CASE, 0) FK_ALL(OUT_CASE, 1)
+#undef OUT_CASE
+#undef FK_ALL
+    default: return false;
+  }
+}
+
+// lane 0 of a warp: start the bulk copies of warp tile `tile` into ring slot `stage`
+__device__ __forceinline__ void issue_tile(const ScanParams& p, unsigned char* stages, uint64_t* full, uint32_t stage,
+                                           uint64_t tile, uint32_t tile_rows) {
+  unsigned char* sbase = stages + static_cast<size_t>(stage) * p.stage_bytes;
+  uint32_t total = 0;
+  for (uint32_t c = 0; c < p.nstaged; ++c) total += p.staged[c].width * tile_rows;
+  mbar_expect_tx(&full[stage], total);
+  for (uint32_t c = 0; c < p.nstaged; ++c) {
+    const uint32_t bytes = p.staged[c].width * tile_rows;
+    bulk_g2s(sbase + p.staged[c].smem_off, p.staged[c].base + tile * bytes, bytes, &full[stage]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int R, int MODE>
+__global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr uint32_t WT = 32 * R;  // rows per warp tile
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem) + warp * MAX_STAGES;
+  unsigned char* stages = smem + SMEM_HEADER + static_cast<size_t>(warp) * p.warp_bytes;
+  long long* temps = reinterpret_cast<long long*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);
+  long long* acc = reinterpret_cast<long long*>(smem + SMEM_HEADER + static_cast<size_t>(NW) * p.warp_bytes);
+
+  if (lane == 0) {
+    for (uint32_t st = 0; st < p.nstages; ++st) mbar_init(&full[st], 1);
+    mbar_fence_init();
+  }
+  if constexpr (MODE == MODE_DENSE) {
+    const int cells = (p.ngroups + 1) * p.naggs;
+    for (int c = 0; c < cells; ++c) acc[c * NT + tid] = p.agg_init[c % p.naggs];
+  }
+  __syncthreads();
+
+  const uint32_t gw = blockIdx.x * NW + warp;  // global warp id
+  const uint32_t nw = gridDim.x * NW;
+  const uint32_t ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
+  if (lane == 0) {
+    const uint32_t pre = ntiles_w < p.nstages ? ntiles_w : p.nstages;
+    for (uint32_t k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + static_cast<uint64_t>(k) * nw, WT);
+  }
+
+  uint32_t stage = 0, parity = 0;
+  for (uint32_t k = 0; k < ntiles_w; ++k) {
+    const uint64_t tile = gw + static_cast<uint64_t>(k) * nw;
+    const unsigned char* sbase = stages + static_cast<size_t>(stage) * p.stage_bytes;
+    while (!mbar_try_wait(&full[stage], parity)) {
+    }
+    const uint64_t row0 = tile * WT + static_cast<uint64_t>(lane) * R;
+    uint32_t vmask = 0;
+    int grp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r < p.nrows) vmask |= 1u << r;
+      grp[r] = (MODE == MODE_DENSE) ? p.ngroups : -1;
+    }
+    uint64_t out_pos = row0;  // project: output position of this lane's first surviving row
+    const Ctx c{p, sbase, temps, acc, lane, tid};
+
+    for (int pc = 0;; pc += 2) {
+      const uint32_t w0 = p.code[pc];
+      const int op = w0 & 0x3f;
+      if (op == MSC_OP_END) break;
+      const uint32_t w1 = p.code[pc + 1];
+      const int fast = w0 >> 20;
+      if (fast != 0 && run_fast<R, MODE>(c, fast, w0, w1, vmask, grp, out_pos)) continue;
+      if (op == MSC_OP_RANK) {
+        if constexpr (MODE == MODE_COUNT) {
+          uint32_t total;
+          (void)warp_exclusive_scan(__popc(vmask), lane, &total);
+          if (lane == 0) p.tile_counts[tile] = total;
+        } else if constexpr (MODE == MODE_PROJECT) {
+          if (p.tile_offsets != nullptr) {
+            uint32_t total;
+            out_pos = p.tile_offsets[tile] + warp_exclusive_scan(__popc(vmask), lane, &total);
+          }
+        }
+        continue;
+      }
+      long long a[R];
+      fetch<R>(c, w1 & 0xffffu, vmask, a);
+      if (op >= MSC_OP_ADD_F && op <= MSC_OP_OR) {
+        long long b[R];
+        fetch<R>(c, w1 >> 16, vmask, b);
+        if (op <= MSC_OP_MOD_I) binop<R>(op, a, b, vmask, p.err);
+        else cmpop<R>(op, a, b);
+      } else if (op == MSC_OP_LUT8) {
+        op_lut<R, uint8_t>(a, reinterpret_cast<const uint8_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
+      } else if (op == MSC_OP_LUT32) {
+        op_lut<R, uint32_t>(a, reinterpret_cast<const uint32_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
+      }
+      const int tee = (w0 >> 9) & 0xf;
+      if (tee) store_temp<R>(c, tee - 1, a);
+      const int dst = (w0 >> 13) & 0x7f;
+      switch ((w0 >> 6) & 7) {
+        case MSC_DST_TEMP: store_temp<R>(c, dst, a); break;
+        case MSC_DST_FILTER: {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (a[r] == 0) vmask &= ~(1u << r);
+        } break;
+        case MSC_DST_GROUP: set_group<R, MODE>(c, a, vmask, grp); break;
+        case MSC_DST_AGG: agg_any<R, MODE>(c, dst, p.agg_kind[dst], grp, a); break;
+        case MSC_DST_OUT:
+          if constexpr (MODE == MODE_PROJECT) {
+            if (p.out_phys[dst] == MSC_P_U32) store_out<R, uint32_t>(a, reinterpret_cast<uint32_t*>(p.out[dst]), out_pos, vmask);
+            else store_out<R, long long>(a, reinterpret_cast<long long*>(p.out[dst]), out_pos, vmask);
+          }
+          break;
+        default: break;
+      }
+    }
+
+    __syncwarp();  // every lane is done reading this stage
+    if (lane == 0 && k + p.nstages < ntiles_w) issue_tile(p, stages, full, stage, gw + static_cast<uint64_t>(k + p.nstages) * nw, WT);
+    if (++stage == p.nstages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+
+  if constexpr (MODE == MODE_DENSE) {
+    __syncthreads();
+    const int cells = p.ngroups * p.naggs;  // the trash group is not exported
+    for (int cell = warp; cell < cells; cell += NW) {
+      const int kind = p.agg_kind[cell % p.naggs];
+      const long long* base = acc + cell * NT;
+      long long v = base[lane];
+#pragma unroll
+      for (int j = 1; j < NW; ++j) v = agg_combine(kind, v, base[lane + 32 * j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = agg_combine(kind, v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (lane == 0 && v != p.agg_init[cell % p.naggs]) atomic_fold(kind, p.dense_out + cell, v);
+    }
+  }
+}
+
+// host launcher, instantiated once per (R, MODE) in its own translation unit (scan_inst_*.cu)
+template <int R, int MODE>
+int launch_scan(msc_ctx* ctx, LaunchPlan* lp) {
+  auto kern = scan_kernel<R, MODE>;
+  MSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lp->smem)));
+  int occ = 0;
+  MSC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, lp->smem));
+  if (occ < 1) return ctx->fail(MSC_ERR_ARG, "scan kernel does not fit on an SM");
+  uint64_t grid = static_cast<uint64_t>(ctx->sm_count) * occ;
+  const uint64_t need = (lp->p.ntiles + NW - 1) / NW;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  lp->grid = static_cast<int>(grid);
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s0, ctx->stream));
+  kern<<<lp->grid, NT, lp->smem, ctx->stream>>>(lp->p);
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s1, ctx->stream));
+  ctx->stats.launches += 1;
+  ctx->stats.last_scan_grid = lp->grid;
+  ctx->stats.last_scan_stages = static_cast<int32_t>(lp->p.nstages);
+  ctx->stats.last_scan_smem = static_cast<int32_t>(lp->smem);
+  ctx->stats.last_scan_rows_per_thread = R;
+  MSC_CUDA(ctx, cudaGetLastError());
+  return MSC_OK;
+}
+#endif  // __CUDACC__ && !MSCAN_DECL_ONLY
+
+}  // namespace mscan
