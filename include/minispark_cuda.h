@@ -229,6 +229,9 @@ MSC_API int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, int3
 MSC_API int msc_rel_info(msc_rel* r, uint64_t* nrows, int32_t* ncols);
 MSC_API int msc_rel_col(msc_rel* r, int32_t col, void** dev_ptr, int32_t* phys);
 MSC_API void msc_rel_free(msc_rel* r);
+/* new relation of `nrows` rows with zero-initialised, tile-padded columns of the given physical types
+ * (filled by the caller, e.g. with rows received from other ranks) */
+MSC_API int msc_rel_alloc(msc_ctx* ctx, uint64_t nrows, const int32_t* phys, int32_t ncols, msc_rel** out);
 /* wrap caller-owned device memory (e.g. exchange receive buffers) as a relation; not freed */
 MSC_API int msc_rel_wrap(msc_ctx* ctx, uint64_t nrows, const msc_colbind* cols, int32_t ncols, msc_rel** out);
 

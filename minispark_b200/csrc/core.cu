@@ -173,6 +173,28 @@ extern "C" void msc_rel_free(msc_rel* r) {
   delete r;
 }
 
+extern "C" int msc_rel_alloc(msc_ctx* ctx, uint64_t nrows, const int32_t* phys, int32_t ncols, msc_rel** out) {
+  if (!ctx || !out || ncols < 0 || (ncols && !phys)) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  msc_rel* r = new msc_rel();
+  r->ctx = ctx;
+  r->nrows = nrows;
+  for (int i = 0; i < ncols; ++i) {
+    msc_col c;
+    c.phys = phys[i];
+    const size_t w = msc_phys_width(phys[i]);
+    int rc = w ? msc_alloc_rows(ctx, nrows, w, &c.data, &c.bytes) : ctx->fail(MSC_ERR_ARG, "bad physical type");
+    if (rc == MSC_OK && cudaMemsetAsync(c.data, 0, c.bytes, ctx->stream) != cudaSuccess) rc = ctx->fail(MSC_ERR_CUDA, "memset failed");
+    if (rc != MSC_OK) {
+      msc_rel_free(r);
+      return rc;
+    }
+    r->cols.push_back(c);
+  }
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = r;
+  return MSC_OK;
+}
+
 extern "C" int msc_rel_wrap(msc_ctx* ctx, uint64_t nrows, const msc_colbind* cols, int32_t ncols, msc_rel** out) {
   if (!ctx || !out || ncols < 0) return MSC_ERR_ARG;
   msc_rel* r = new msc_rel();

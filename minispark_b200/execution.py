@@ -31,6 +31,7 @@ from typing import TYPE_CHECKING, Any, Iterable, Optional
 
 from . import lowering as L
 from . import native as N
+from .distributed import Comm, unify_keys
 from .constants import ColumnType, Row, Schema
 from .io import BlockFile
 from .jobs import JobResult, OutputFile
@@ -313,6 +314,33 @@ class _ScanResolver:
         return d
 
 
+def _comm_from_torch(device: int) -> Comm:
+    """Join the process group the launcher (torchrun) set up, if any; otherwise a single-rank Comm."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return Comm()
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return Comm()
+    if not dist.is_initialized():
+        return Comm()
+    return Comm.from_env(device)
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int) -> None:
+        self.__cuda_array_interface__ = {"shape": (max(nbytes, 1),), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _torch_dtype(phys: int):  # noqa: ANN202
+    import torch  # noqa: PLC0415
+
+    return {N.P_U8: torch.uint8, N.P_U16: torch.int16, N.P_U32: torch.int32, N.P_I32: torch.int32, N.P_I64: torch.int64,
+            N.P_F32: torch.float32, N.P_F64: torch.float64}[phys]
+
+
 _LTYPE_OF = {ColumnType.INTEGER: L.INT, ColumnType.FLOAT: L.FLOAT, ColumnType.TIMESTAMP: L.TS, ColumnType.STRING: L.STR}
 _MSC_TYPE = {ColumnType.INTEGER: N.K["MSC_T_INTEGER"], ColumnType.STRING: N.K["MSC_T_STRING"],
              ColumnType.FLOAT: N.K["MSC_T_FLOAT"], ColumnType.TIMESTAMP: N.K["MSC_T_TIMESTAMP"]}
@@ -331,13 +359,17 @@ class CudaExecutionEngine(ExecutionEngine):
     """
 
     def __init__(self, device: Optional[int] = None, work_folder: Optional[Path] = None, layout: str = "native",
-                 shard: tuple[int, int] = (0, 1)) -> None:
+                 shard: Optional[tuple[int, int]] = None, comm: Optional[Comm] = None) -> None:
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.ctx = N.Context(device)  # raises when the library or the GPU is missing: no fallback
         self.device = device
         self.layout = N.K["MSC_LAYOUT_WIDE"] if layout == "wide" else N.K["MSC_LAYOUT_NATIVE"]
-        self.shard = shard
+        if comm is None:
+            comm = _comm_from_torch(device)
+        self.comm = comm
+        self.shard = shard if shard is not None else (comm.rank, comm.world)
+        self.replicate_results = True  # multi-rank: every rank ends up with the complete result
         self._own_work = work_folder is None
         self.work_folder = Path(work_folder) if work_folder is not None else Path(tempfile.mkdtemp(prefix="minispark_cuda_"))
         self.work_folder.mkdir(parents=True, exist_ok=True)
@@ -661,6 +693,8 @@ class CudaExecutionEngine(ExecutionEngine):
         # raw result: key + one column per unique accumulator slot; expose it in the aggregate's schema order
         slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog.agg_kinds]
         raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
+        if self.comm.world > 1:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
+            raw = self._merge_partials(raw, prog.agg_kinds, slot_types, group.type)
         key = raw.cols[0]
         if group.type == L.FLOAT and key.phys == N.P_I64:
             key = DeviceColumn(key.ptr, N.P_F64, L.FLOAT)  # hash mode stores the f64 bit pattern
@@ -698,3 +732,146 @@ class CudaExecutionEngine(ExecutionEngine):
             c = rrel.cols[pos]
             columns[nl + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via=1)
         return _Source(prel.nrows, columns, index_vectors=[prel.cols[0], prel.cols[1]], keep=[lrel, rrel, prel])
+
+    # ---- prepared queries ------------------------------------------------------------------------------
+    def prepare(self, full_task: Any) -> "PreparedAggregate":
+        """Compile an aggregate query once; ``run()`` then re-executes it with no Python lowering.
+
+        Supported shape: ``table -> [filter/project] -> GROUP BY -> [having / final select]`` (e.g. TPC-H Q1)."""
+        task = deepcopy(full_task)
+        task.validate_schema()
+        plan = L.lower_task(task)
+        if not (isinstance(plan, L.LSelect) and isinstance(plan.child, L.LAggregate)):
+            raise L.LoweringError("prepare() supports aggregate queries only")
+        return PreparedAggregate(self, plan)
+
+    # ---- multi-GPU exchange ---------------------------------------------------------------------------
+    def _torch_column(self, col: DeviceColumn, nrows: int):  # noqa: ANN202
+        import torch  # noqa: PLC0415
+
+        width = N.PHYS_WIDTH[col.phys]
+        raw = torch.as_tensor(_DevView(col.ptr, nrows * width), device=f"cuda:{self.device}")
+        return raw[: nrows * width].view(_torch_dtype(col.phys))
+
+    def _rel_from_torch(self, columns: list, physes: list[int], ltypes: list[str], dicts: list) -> DeviceRel:
+        """Library-owned, tile-padded relation filled from torch tensors (rows received from other ranks)."""
+        import torch  # noqa: PLC0415
+
+        nrows = int(columns[0].shape[0]) if columns else 0
+        out = C.c_void_p()
+        self.ctx.call("msc_rel_alloc", nrows, N.int32_array(physes), len(physes), C.byref(out))
+        rel = self._track(DeviceRel.from_handle(self.ctx, out.value, ltypes, dicts))
+        for col, src in zip(rel.cols, columns):
+            if nrows:
+                self._torch_column(col, nrows).copy_(src.view(_torch_dtype(col.phys)))
+        torch.cuda.synchronize(self.device)
+        return rel
+
+    def _merge_partials(self, raw: DeviceRel, agg_kinds: list[int], slot_types: list[str], group_type: str) -> DeviceRel:
+        """Combine per-rank partial aggregates: small tables are all-gathered and re-aggregated on every
+        GPU; large ones are hash-partitioned on the key (msc_partition) and exchanged with one all-to-all."""
+        import torch  # noqa: PLC0415
+
+        comm = self.comm
+        key_dict = raw.cols[0].dict
+        global_dict = None
+        if key_dict is not None:  # unify string keys through their dictionary entries
+            universe, _ = unify_keys(comm.all_gather_object(key_dict.export()))
+            global_dict = DictHandle(self.ctx)
+            self._query_dicts.append(global_dict)
+            for text in universe:
+                global_dict.literal_code(text, insert=True)
+            source = _Source(raw.nrows, dict(enumerate(raw.cols)), keep=[raw])
+            resolver = _ScanResolver(self, source, {"global": global_dict})
+            outs = [L.ECode(L.INT, L.ETranslate(L.STR, L.EInput(L.STR, 0), "global"))]
+            outs += [L.EInput(t, i + 1) for i, t in enumerate(slot_types)]
+            prog = L.compile_project(resolver, [], outs)
+            raw = self._scan_project(resolver, prog, [L.INT, *slot_types])
+        physes = [N.P_I64] + [N.P_F64 if t == L.FLOAT else N.P_I64 for t in slot_types]
+        small = comm.max_int(raw.nrows) <= int(os.environ.get("MSC_EXCHANGE_GATHER_MAX", "65536"))
+        if small:
+            cols, _ = comm.all_gather_rows([self._torch_column(c, raw.nrows) for c in raw.cols], raw.nrows)
+        else:
+            counts = (C.c_uint64 * comm.world)()
+            part = C.c_void_p()
+            self.ctx.call("msc_partition", C.c_void_p(raw.handle), 0, comm.world, counts, C.byref(part))
+            prel = self._track(DeviceRel.from_handle(self.ctx, part.value, [c.ltype for c in raw.cols], [None] * len(raw.cols)))
+            cols, _ = comm.all_to_all_rows([self._torch_column(c, prel.nrows) for c in prel.cols], [int(c) for c in counts])
+        torch.cuda.synchronize(self.device)
+        gathered = self._rel_from_torch(cols, physes, [L.INT, *slot_types], [None] * len(physes))
+        # final aggregate over the partial rows: SUM of sums / counts, MIN of mins, MAX of maxes
+        merge_kind = {N.K["MSC_AGG_SUM_F"]: "sum", N.K["MSC_AGG_SUM_I"]: "sum", N.K["MSC_AGG_MIN_F"]: "min", N.K["MSC_AGG_MIN_I"]: "min",
+                      N.K["MSC_AGG_MAX_F"]: "max", N.K["MSC_AGG_MAX_I"]: "max"}
+        source = _Source(gathered.nrows, dict(enumerate(gathered.cols)), keep=[gathered])
+        resolver = _ScanResolver(self, source)
+        prog2 = L.compile_aggregate(resolver, [], L.EInput(L.INT, 0), [(merge_kind[k], L.EInput(t, i + 1)) for i, (k, t) in enumerate(zip(agg_kinds, slot_types))])
+        desc = resolver.desc(prog2.program)
+        out = C.c_void_p()
+        self.ctx.call("msc_scan_aggregate", C.byref(desc), 0, N.int32_array(prog2.agg_kinds), len(prog2.agg_kinds), max(gathered.nrows, 1), C.byref(out))
+        self._note_kernel()
+        merged = self._track(DeviceRel.from_handle(self.ctx, out.value, [group_type, *slot_types], [global_dict] + [None] * len(slot_types)))
+        merged.cols = [merged.cols[0]] + [merged.cols[1 + s] for s in prog2.slot_of]
+        self.last_stats["exchange"] = "all_gather" if small else "all_to_all"
+        self.last_stats["result_partitioned"] = not small  # all_to_all leaves every rank with a disjoint key range
+        return merged
+
+
+class PreparedAggregate:
+    """A compiled ``scan -> filter -> GROUP BY -> final projection`` query bound to device-resident columns."""
+
+    def __init__(self, engine: CudaExecutionEngine, plan: L.LSelect) -> None:
+        self.engine = engine
+        self.plan = plan
+        agg = plan.child
+        child = agg.child
+        if isinstance(child, L.LSelect):
+            filters = list(child.filters)
+            group = L.substitute(agg.group, child.outputs)
+            aggs = [(k, L.substitute(e, child.outputs)) for k, e in agg.aggs]
+            base = child.child
+        else:
+            filters, group, aggs, base = [], agg.group, list(agg.aggs), child
+        self.source, exprs = engine._prepare(base, [*filters, group, *[e for _, e in aggs]])
+        nf = len(filters)
+        self.group_type = exprs[nf].type
+        self.resolver = _ScanResolver(engine, self.source)
+        self.prog = L.compile_aggregate(self.resolver, exprs[:nf], exprs[nf], [(k, e) for (k, _), e in zip(aggs, exprs[nf + 1:])])
+        self.desc = self.resolver.desc(self.prog.program)
+        self.kinds = N.int32_array(self.prog.agg_kinds)
+        self.slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT
+                           for k in self.prog.agg_kinds]
+        self.ngroups = 0
+        self.hint = 0
+        if self.prog.group_dict is not None:
+            size = self.prog.group_dict.size
+            if size > 0 and (size + 1) * (len(self.prog.agg_kinds) + 1) <= DENSE_MAX_CELLS:
+                self.ngroups = size
+            self.hint = max(size, 1)
+        self.bytes_per_row = sum(N.PHYS_WIDTH[c.phys] for c in self.resolver.staged)
+        self.nrows = self.source.nrows
+        self.scan_stats: dict[str, Any] = {}
+
+    def run(self) -> tuple[DeviceRel, float]:
+        """One pass of the hot path; returns (result relation, device milliseconds of this rank's launches)."""
+        e = self.engine
+        out = C.c_void_p()
+        e.ctx.call("msc_scan_aggregate", C.byref(self.desc), self.ngroups, self.kinds, len(self.prog.agg_kinds), self.hint, C.byref(out))
+        st = e.ctx.stats()
+        dev_ms = st.last_kernel_ms
+        self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
+                           "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread}
+        raw = e._track(DeviceRel.from_handle(e.ctx, out.value, [self.group_type, *self.slot_types],
+                                             [self.prog.group_dict] + [None] * len(self.slot_types)))
+        if e.comm.world > 1:
+            raw = e._merge_partials(raw, self.prog.agg_kinds, self.slot_types, self.group_type)
+            dev_ms += e.ctx.stats().last_kernel_ms
+        key = raw.cols[0]
+        if self.group_type == L.FLOAT and key.phys == N.P_I64:
+            key = DeviceColumn(key.ptr, N.P_F64, L.FLOAT)
+        cols = [key] + [raw.cols[1 + s] for s in self.prog.slot_of]
+        src2 = _Source(raw.nrows, dict(enumerate(cols)))
+        res2 = _ScanResolver(e, src2)
+        prog2 = L.compile_project(res2, self.plan.filters, self.plan.outputs)
+        final = e._scan_project(res2, prog2, [x.type for x in self.plan.outputs])
+        dev_ms += e.ctx.stats().last_kernel_ms
+        return final, dev_ms

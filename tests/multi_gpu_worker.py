@@ -1,0 +1,71 @@
+"""Worker for tests/test_gpu_multi.py: run under torchrun with one rank per GPU (NCCL)."""
+
+from __future__ import annotations
+
+import os
+import sys
+import time
+from pathlib import Path
+
+os.environ["TZ"] = "UTC"
+time.tzset()
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "tests", ROOT / "bench"):
+    sys.path.insert(0, str(p))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import cases  # noqa: E402
+import gen_tpch  # noqa: E402
+from minispark_b200 import CudaExecutionEngine  # noqa: E402
+from oracle import py_oracle as O  # noqa: E402
+
+
+def main() -> None:
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    folder = Path(sys.argv[1])
+    lineitem = folder / "lineitem.bin"
+    if rank == 0:
+        gen_tpch.write_table(lineitem, "lineitem", sf=0.004, rows_per_block=2048)  # ~24k rows in 12 blocks
+    dist.barrier()
+    ns = cases.namespace()
+
+    def high_card(engine):  # noqa: ANN001, ANN202
+        return ns.DataFrame(engine).table(str(lineitem)).group_by(ns.Col("l_orderkey")).agg(
+            ns.F.sum(ns.Col("l_quantity")).alias("q"), ns.F.avg(ns.Col("l_extendedprice")).alias("p"), ns.F.count())
+
+    with CudaExecutionEngine() as engine:
+        assert engine.shard == (rank, world)
+        # low-cardinality GROUP BY: partial tables merged with an all-gather, every rank gets the full answer
+        got = cases.q1(ns, str(lineitem), engine).collect()
+        assert engine.last_stats["exchange"] == "all_gather"
+        O.assert_rows_equal(got, O.run_task(cases.q1(ns, str(lineitem)).task, wire=True), rel=5e-7)
+        # high-cardinality GROUP BY through hash partitioning + all-to-all: ranks hold disjoint key ranges
+        os.environ["MSC_EXCHANGE_GATHER_MAX"] = "0"
+        part = high_card(engine).collect()
+        assert engine.last_stats["exchange"] == "all_to_all"
+        os.environ.pop("MSC_EXCHANGE_GATHER_MAX")
+        gathered: list = [None] * world
+        dist.all_gather_object(gathered, part)
+        merged = [row for rows in gathered for row in rows]
+        keys = [r["l_orderkey"] for r in merged]
+        assert len(keys) == len(set(keys)), "a key was aggregated on two ranks"
+        O.assert_rows_equal(merged, O.run_task(high_card(None).task, wire=True), rel=5e-7)
+        # filter / project scans stay rank-local: the union over ranks is the table
+        rows = ns.DataFrame(engine).table(str(lineitem)).filter(ns.Col("l_quantity") > 49).select(ns.Col("l_orderkey"), ns.Col("l_linenumber")).collect()
+        dist.all_gather_object(gathered, rows)
+        union = [row for rows_r in gathered for row in rows_r]
+        want = O.run_task(ns.DataFrame(None).table(str(lineitem)).filter(ns.Col("l_quantity") > 49).select(ns.Col("l_orderkey"), ns.Col("l_linenumber")).task)
+        O.assert_rows_equal(union, want)
+    dist.barrier()
+    if rank == 0:
+        print("multi-gpu ok", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
