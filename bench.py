@@ -231,7 +231,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
         return float(t.item())
 
     path, gen_s = ensure_table(args.sf, rank)
-    engine = CudaExecutionEngine(device=local_rank, layout=args.layout)
+    # every rank owns a whole table of its own (weak scaling), so the engine must not shard it again
+    engine = CudaExecutionEngine(device=local_rank, layout=args.layout, shard=(0, 1))
     ns = cases.namespace()
     try:
         # BlockFile image in pinned host memory: the "host buffers" of the e2e measurement
