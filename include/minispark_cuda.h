@@ -136,6 +136,7 @@ enum msc_opcode {
 
 #define MSC_VM_MAX_TEMPS 8
 #define MSC_VM_MAX_CODE 192  /* u32 words = 96 instructions */
+#define MSC_VM_MAX_CODE2 128 /* regvm instructions */
 #define MSC_VM_MAX_CONSTS 32
 #define MSC_VM_MAX_STAGED 12 /* directly scanned columns (incl. index vectors) */
 #define MSC_VM_MAX_GATHER 16 /* columns read through an index vector */
@@ -178,6 +179,13 @@ typedef struct msc_scan_desc {
   int32_t nluts;
   int32_t ntemps;  /* temporaries the program uses */
   const void* luts[MSC_VM_MAX_LUTS];
+  /* Optional second encoding of the SAME query for the register-resident interpreter (dense
+   * aggregate scans only; minispark_b200/csrc/gen_regvm.py, regvm_handlers.h): one u32 per
+   * instruction = handler | a1 << 8 | a2 << 20, column operands given as staged slots.  When present
+   * and valid the library runs it instead of `code`; ncode2 = 0 means "not available". */
+  int32_t ncode2;
+  int32_t _pad2;
+  uint32_t code2[MSC_VM_MAX_CODE2];
 } msc_scan_desc;
 
 typedef struct msc_stats {

@@ -15,7 +15,7 @@ LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libminispark_cuda.so"
 OBJ_DIR = PKG / "build"
 SOURCES = ["scan_inst_r4_dense.cu", "scan_inst_r8_dense.cu", "scan_inst_r4_hash.cu", "scan_inst_r8_hash.cu", "scan_inst_r4_count.cu",
-           "scan_inst_r4_project.cu", "core.cu", "scan.cu", "strings.cu", "ingest.cu", "join.cu", "result.cu"]
+           "scan_inst_r4_project.cu", "scan_regvm.cu", "core.cu", "scan.cu", "strings.cu", "ingest.cu", "join.cu", "result.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--diag-suppress", "177",
@@ -31,7 +31,7 @@ def _nvcc() -> str:
 
 def _digest(src: Path) -> str:
     h = hashlib.sha256()
-    for dep in [src, *sorted(CSRC.glob("*.cuh")), PKG.parent / "include" / "minispark_cuda.h"]:
+    for dep in [src, *sorted(CSRC.glob("*.cuh")), *sorted(CSRC.glob("*.h")), *sorted(CSRC.glob("*.inc")), PKG.parent / "include" / "minispark_cuda.h"]:
         h.update(dep.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -4,6 +4,7 @@
 // scan_inst_*.cu so the specialisations compile in parallel.
 #define MSCAN_DECL_ONLY  // the kernel is instantiated in scan_inst_*.cu
 #include "scan_kernel.cuh"
+#include "scan_regvm.h"
 
 using namespace mscan;
 
@@ -323,14 +324,15 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, const int3
 }
 
 // Build kernel params + launch geometry.  extra_smem = CTA-wide bytes after the warp regions.
-int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem, LaunchPlan* lp) {
+int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem, LaunchPlan* lp, int ntemps_override = -1) {
   ScanParams& p = lp->p;
   memset(&p, 0, sizeof(p));
   const uint32_t wt = 32 * R;  // rows per warp tile
   p.nrows = sd->nrows;
   p.ntiles = static_cast<uint32_t>((sd->nrows + wt - 1) / wt);
   p.nstaged = sd->nstaged;
-  p.ntemps = sd->ntemps;
+  const int ntemps = ntemps_override >= 0 ? ntemps_override : sd->ntemps;
+  p.ntemps = ntemps;
   uint32_t off = 0;
   for (int c = 0; c < sd->nstaged; ++c) {
     const size_t w = msc_phys_width(sd->staged[c].phys);
@@ -368,7 +370,7 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
   }
   memcpy(p.consts, sd->consts, sizeof(int64_t) * sd->nconsts);
   p.err = ctx->d_err;
-  const size_t temps_bytes = static_cast<size_t>(sd->ntemps) * wt * sizeof(long long);
+  const size_t temps_bytes = static_cast<size_t>(ntemps) * wt * sizeof(long long);
   // ring depth: aim at ~3 CTAs per SM (about 72 KB each); MSC_SCAN_STAGES overrides
   static const int forced = getenv("MSC_SCAN_STAGES") ? atoi(getenv("MSC_SCAN_STAGES")) : 0;
   const size_t budget = 72 * 1024;
@@ -384,6 +386,61 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
   if (lp->smem > 227 * 1024) return ctx->fail(MSC_ERR_ARG, "scan needs more shared memory than an SM has");
   lp->grid = 0;
   return MSC_OK;
+}
+
+// Validate the regvm encoding against the bound columns / accumulators and resolve its column
+// operands to shared-memory offsets.  Returns MSC_OK and fills `out`, or an error.
+int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, const int32_t* agg_kinds, int naggs, RegvmProgram* out) {
+  if (sd->ncode2 <= 0 || sd->ncode2 > MSC_RV_MAX_CODE) return ctx->fail(MSC_ERR_ARG, "regvm program length out of range");
+  memset(out, 0, sizeof(*out));
+  int depth = 0;
+  bool grouped = false, ended = false;
+  for (int pc = 0; pc < sd->ncode2; ++pc) {
+    const uint32_t w = sd->code2[pc];
+    const uint32_t id = w & 0xff;
+    uint32_t a[2] = {(w >> 8) & 0xfff, w >> 20};
+    if (id >= MSC_RV__COUNT) return ctx->fail(MSC_ERR_ARG, "regvm: unknown handler");
+    const msc_rv_info& info = MSC_RV_INFO[id];
+    if (id == MSC_RV_END) {
+      if (depth != 0) return ctx->fail(MSC_ERR_ARG, "regvm: unbalanced stack at END");
+      out->code[pc] = w;
+      out->n = pc + 1;
+      ended = true;
+      break;
+    }
+    if (info.depth >= 0 && depth != info.depth) return ctx->fail(MSC_ERR_ARG, "regvm: stack depth mismatch");
+    depth += info.delta;
+    if (depth < 0 || depth > MSC_RV_MAX_DEPTH) return ctx->fail(MSC_ERR_ARG, "regvm: stack depth out of range");
+    const signed char kinds[2] = {info.a1, info.a2};
+    for (int k = 0; k < 2; ++k) {
+      switch (kinds[k]) {
+        case MSC_RV_ARG_COL:
+          if (static_cast<int>(a[k]) >= sd->nstaged || sd->staged[a[k]].phys != info.phys)
+            return ctx->fail(MSC_ERR_ARG, "regvm: column operand has the wrong physical type");
+          a[k] = p.staged[a[k]].smem_off >> 4;
+          if (a[k] > 0xfff) return ctx->fail(MSC_ERR_ARG, "regvm: stage too large");
+          break;
+        case MSC_RV_ARG_CONST:
+          if (static_cast<int>(a[k]) >= sd->nconsts) return ctx->fail(MSC_ERR_ARG, "regvm: bad constant");
+          break;
+        case MSC_RV_ARG_SLOT:
+          if (static_cast<int>(a[k]) >= naggs || agg_kinds[a[k]] != info.agg) return ctx->fail(MSC_ERR_ARG, "regvm: accumulator kind mismatch");
+          if (!grouped) return ctx->fail(MSC_ERR_ARG, "regvm: aggregate before GROUP");
+          break;
+        default: a[k] = 0; break;
+      }
+    }
+    if (id == MSC_RV_GROUP_U8 || id == MSC_RV_GROUP_U16 || id == MSC_RV_GROUP_U32) grouped = true;
+    out->code[pc] = id | (a[0] << 8) | (a[1] << 20);
+  }
+  if (!ended) return ctx->fail(MSC_ERR_ARG, "regvm: program has no END");
+  if (!grouped) return ctx->fail(MSC_ERR_ARG, "regvm: program has no GROUP");
+  return MSC_OK;
+}
+
+bool regvm_enabled() {
+  static const bool on = !(getenv("MSC_SCAN_REGVM") && atoi(getenv("MSC_SCAN_REGVM")) == 0);
+  return on;
 }
 
 template <int MODE>
@@ -456,12 +513,17 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     init[naggs] = 0;
     const size_t acc_bytes = static_cast<size_t>(ngroups + 1) * ntot * NT * sizeof(long long);
     if (acc_bytes > 96 * 1024) return ctx->fail(MSC_ERR_ARG, "dense aggregate: groups x aggregates too large; use hash mode");
+    const bool use_regvm = sd->ncode2 > 0 && regvm_enabled();
+    const size_t regvm_bytes = MSC_RV_MAX_CODE * sizeof(uint32_t) + MSC_VM_MAX_CONSTS * sizeof(long long);
     LaunchPlan lp;
-    MSC_TRY(plan_launch(ctx, sd, R, acc_bytes, &lp));
+    if (use_regvm) MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, acc_bytes + regvm_bytes, &lp, 0));
+    else MSC_TRY(plan_launch(ctx, sd, R, acc_bytes, &lp));
     lp.p.ngroups = ngroups;
     lp.p.naggs = ntot;
     memcpy(lp.p.agg_init, init, sizeof(long long) * ntot);
     memcpy(lp.p.agg_kind, kinds, sizeof(int) * ntot);
+    RegvmProgram rv;
+    if (use_regvm) MSC_TRY(build_regvm(ctx, sd, lp.p, agg_kinds, naggs, &rv));
     // global table, initialised with the identities
     DevTmp table(ctx), d_init(ctx), d_n(ctx), d_ptrs(ctx);
     MSC_TRY(table.alloc(sizeof(unsigned long long) * ngroups * ntot));
@@ -471,7 +533,10 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, d_init.as<long long>());
     ctx->stats.launches += 1;
     lp.p.dense_out = table.as<unsigned long long>();
-    if (sd->nrows > 0) MSC_TRY(launch_scan_r<MODE_DENSE>(ctx, &lp));
+    if (sd->nrows > 0) {
+      if (use_regvm) MSC_TRY(launch_regvm_dense(ctx, &lp, &rv));
+      else MSC_TRY(launch_scan_r<MODE_DENSE>(ctx, &lp));
+    }
     // compact present groups into the output relation
     msc_rel* rel = new_rel(ctx, 0);
     int rc = add_col(ctx, rel, MSC_P_U32, ngroups);

@@ -309,6 +309,9 @@ class _ScanResolver:
             d.consts[i] = c
         d.nluts = len(self.luts)
         d.ntemps = program.ntemps
+        d.ncode2 = len(program.regvm)
+        for i, w in enumerate(program.regvm):
+            d.code2[i] = w
         for i, ptr in enumerate(self.luts):
             d.luts[i] = ptr
         return d

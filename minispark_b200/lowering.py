@@ -29,7 +29,7 @@ from typing import Any, Callable, Iterable, Optional, Protocol, Sequence
 
 from .constants import ColumnType, Schema
 from .io import BlockFile, datetime_to_timestamp
-from .native import K, OP, P_F32, P_F64, P_I32, P_I64, P_U8, P_U16, P_U32
+from .native import K, OP, P_F32, P_F64, P_I32, P_I64, P_U8, P_U16, P_U32, RV
 
 # value types of the IR
 INT, FLOAT, TS, STR, BOOL = "I", "F", "T", "S", "B"
@@ -535,6 +535,8 @@ class Program:
     consts: list[int] = field(default_factory=list)
     ntemps: int = 0
     text: list[str] = field(default_factory=list)    # disassembly, for explain/tests
+    regvm: list[int] = field(default_factory=list)   # same query for the register-resident interpreter (may be empty)
+    regvm_text: list[str] = field(default_factory=list)
 
     def words(self) -> list[int]:
         return list(self.code)
@@ -853,7 +855,167 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
             continue
         kinds.append(_AGG_KINDS[(kind, FLOAT if e.type == FLOAT else INT)])
         b.materialize(e, DST_AGG, slot, agg_kind=kinds[-1])
-    return AggregateProgram(b.end(), kinds, slot_of, group_dict)
+    program = b.end()
+    if REGVM_ENABLED:
+        try:
+            program.regvm, program.regvm_text = compile_regvm(b, filters, group, unique)
+        except _RegvmUnsupported:
+            program.regvm, program.regvm_text = [], []
+    return AggregateProgram(program, kinds, slot_of, group_dict)
+
+
+# ------------------------------------------------------------------------------------------------
+# second encoding for the register-resident interpreter (csrc/gen_regvm.py, scan_regvm.cu)
+# ------------------------------------------------------------------------------------------------
+REGVM_ENABLED = os.environ.get("MSC_SCAN_REGVM", "1") != "0"
+RV_MAX_DEPTH = RV["MAX_DEPTH"]
+RV_MAX_TEMPS = RV["MAX_TEMPS"]
+
+
+class _RegvmUnsupported(Exception):
+    """The query uses something outside the regvm op set; the C++ interpreter runs it instead."""
+
+
+def _float_const(e: Expr) -> Optional[float]:
+    if isinstance(e, EConst) and e.type == FLOAT:
+        return float(e.value)
+    if isinstance(e, ECast) and isinstance(e.child, EConst) and e.child.type in (INT, BOOL):
+        return float(e.child.value)
+    return None
+
+
+def compile_regvm(b: "ProgramBuilder", filters: Sequence[Expr], group: Expr, unique: dict) -> tuple[list[int], list[str]]:
+    """Postfix stack code (one u32 per instruction) for a dense aggregate scan, or raise _RegvmUnsupported.
+
+    Column operands are emitted as staged slots (the library resolves them to shared-memory offsets and
+    checks their physical types against the handler); constants share the main program's pool."""
+    words: list[int] = []
+    text: list[str] = []
+
+    def emit(name: str, a1: int = 0, a2: int = 0) -> None:
+        if name not in RV:
+            raise _RegvmUnsupported(name)
+        if not (0 <= a1 < 4096 and 0 <= a2 < 4096):
+            raise _RegvmUnsupported("operand out of range")
+        words.append(RV[name] | (a1 << 8) | (a2 << 20))
+        text.append(f"{name} {a1} {a2}")
+
+    def column(e: Expr) -> Binding:
+        if not isinstance(e, EInput):
+            raise _RegvmUnsupported("not a column")
+        bd = b.r.binding(e.index)
+        if bd.staged is None:
+            raise _RegvmUnsupported("gathered column")
+        return bd
+
+    flip = {"lt": "gt", "le": "ge", "gt": "lt", "ge": "le", "eq": "eq", "ne": "ne"}
+    for f in filters:
+        if not (isinstance(f, EBin) and f.op in _CMP):
+            raise _RegvmUnsupported("filter shape")
+        left, right, op = f.left, f.right, f.op
+        if isinstance(left, EConst) and not isinstance(right, EConst):
+            left, right, op = right, left, flip[op]
+        if not isinstance(right, EConst) or right.type == STR or left.type == STR:
+            raise _RegvmUnsupported("filter operand")
+        bd = column(left)
+        ty = {P_I64: "I64", P_I32: "I32", P_F32: "F32", P_F64: "F64"}.get(bd.phys)
+        if ty is None or (ty[0] == "F") != (left.type == FLOAT) or (left.type == FLOAT) != (right.type == FLOAT):
+            raise _RegvmUnsupported("filter type")
+        bits = f64_bits(right.value) if ty[0] == "F" else int(right.value)
+        emit(f"CMPCOL_{op.upper()}_{ty}", bd.staged, b.const(bits))
+
+    if not (isinstance(group, EInput) and group.type == STR):
+        raise _RegvmUnsupported("group key")
+    gb = column(group)
+    emit({P_U8: "GROUP_U8", P_U16: "GROUP_U16", P_U32: "GROUP_U32"}.get(gb.phys, "?"), gb.staged)
+
+    counts: dict[Expr, int] = {}
+
+    def walk(e: Expr) -> None:
+        if isinstance(e, (EInput, EConst)) or _float_const(e) is not None or (isinstance(e, ECast) and isinstance(e.child, EInput)):
+            return
+        counts[e] = counts.get(e, 0) + 1
+        if counts[e] == 1:
+            for c in expr_children(e):
+                walk(c)
+
+    for (kind, e) in unique:
+        if kind != "count":
+            walk(e)
+    temps: dict[Expr, int] = {}
+
+    def load(e: Expr, d: int) -> bool:
+        """Push a column leaf at depth d; False when e is not a loadable leaf."""
+        if isinstance(e, EInput) and e.type == FLOAT:
+            bd = column(e)
+            name = {P_F32: "LD_F32", P_F64: "LD_F64"}.get(bd.phys)
+        elif isinstance(e, ECast) and isinstance(e.child, EInput) and e.child.type in (INT, BOOL):
+            bd = column(e.child)
+            name = {P_I32: "LD_I32F"}.get(bd.phys)
+        elif isinstance(e, EInput) and e.type in (INT, TS):
+            bd = column(e)
+            name = {P_I32: "LD_I32", P_I64: "LD_I64"}.get(bd.phys)
+        else:
+            return False
+        if name is None:
+            raise _RegvmUnsupported("column type")
+        emit(f"{name}_D{d}", bd.staged)
+        return True
+
+    def gen(e: Expr, d: int) -> None:
+        """Evaluate e into stack slot d (depth d -> d + 1)."""
+        if d >= RV_MAX_DEPTH:
+            raise _RegvmUnsupported("expression too deep")
+        if e in temps:
+            emit(f"GET{temps[e]}_D{d}")
+            return
+        if load(e, d):
+            return
+        c = _float_const(e)
+        if c is not None:
+            emit(f"CONST_D{d}", b.const(f64_bits(c)))
+            return
+        if not (isinstance(e, EBin) and e.type == FLOAT and e.op in ("add", "sub", "mul")):
+            raise _RegvmUnsupported(f"operator {getattr(e, 'op', type(e).__name__)}")
+        cl, cr = _float_const(e.left), _float_const(e.right)
+        if cr is not None and cl is None:      # x op c
+            gen(e.left, d)
+            emit({"add": "ADDC", "sub": "ADDC", "mul": "MULC"}[e.op] + f"_D{d + 1}", b.const(f64_bits(-cr if e.op == "sub" else cr)))
+        elif cl is not None and cr is None:    # c op x
+            gen(e.right, d)
+            emit({"add": "ADDC", "sub": "RSUBC", "mul": "MULC"}[e.op] + f"_D{d + 1}", b.const(f64_bits(cl)))
+        else:
+            gen(e.left, d)
+            gen(e.right, d + 1)
+            emit({"add": "ADDF", "sub": "SUBF", "mul": "MULF"}[e.op] + f"_D{d + 2}")
+        if counts.get(e, 0) > 1 and len(temps) < RV_MAX_TEMPS:
+            temps[e] = len(temps)
+            emit(f"TEE{temps[e]}_D{d + 1}")
+
+    for (kind, e), slot in unique.items():
+        if kind == "count":
+            emit("COUNT", slot)
+            continue
+        is_float = e.type == FLOAT
+        if kind == "sum" and is_float and e not in temps:
+            if isinstance(e, EInput):
+                bd = column(e)
+                fused = {P_F32: "AGGCOL_F32", P_F64: "AGGCOL_F64"}.get(bd.phys)
+                if fused:
+                    emit(fused, bd.staged, slot)
+                    continue
+            if isinstance(e, ECast) and isinstance(e.child, EInput) and column(e.child).phys == P_I32:
+                emit("AGGCOL_I32F", column(e.child).staged, slot)
+                continue
+        if is_float:
+            gen(e, 0)
+        elif not load(e, 0):
+            raise _RegvmUnsupported("integer expression")
+        emit(f"AGG_{kind.upper()}{'F' if is_float else 'I'}_D1", slot)
+    emit("END")
+    if len(words) > K["MSC_VM_MAX_CODE2"]:
+        raise _RegvmUnsupported("program too long")
+    return words, text
 
 
 @dataclass

@@ -32,7 +32,14 @@ def _parse_header() -> dict[str, int]:
     return consts
 
 
+def _parse_regvm() -> dict[str, int]:
+    """Handler ids of the register-resident interpreter (generated header next to the CUDA sources)."""
+    text = (PKG / "csrc" / "regvm_handlers.h").read_text()
+    return {name: int(value) for name, value in re.findall(r"#define\s+MSC_RV_([A-Z0-9_]+)\s+(\d+)", text)}
+
+
 K = _parse_header()
+RV = _parse_regvm()
 OP = {name[len("MSC_OP_"):]: value for name, value in K.items() if name.startswith("MSC_OP_")}
 P_U8, P_U16, P_U32, P_I32, P_I64, P_F32, P_F64 = (K[f"MSC_P_{n}"] for n in ("U8", "U16", "U32", "I32", "I64", "F32", "F64"))
 PHYS_WIDTH = {P_U8: 1, P_U16: 2, P_U32: 4, P_I32: 4, P_I64: 8, P_F32: 4, P_F64: 8}
@@ -58,6 +65,9 @@ class ScanDesc(C.Structure):
         ("nluts", C.c_int32),
         ("ntemps", C.c_int32),
         ("luts", C.c_void_p * K["MSC_VM_MAX_LUTS"]),
+        ("ncode2", C.c_int32),
+        ("_pad2", C.c_int32),
+        ("code2", C.c_uint32 * K["MSC_VM_MAX_CODE2"]),
     ]
 
 
