@@ -184,7 +184,7 @@ typedef struct msc_scan_desc {
    * instruction = handler | a1 << 8 | a2 << 20, column operands given as staged slots.  When present
    * and valid the library runs it instead of `code`; ncode2 = 0 means "not available". */
   int32_t ncode2;
-  int32_t _pad2;
+  int32_t count_slot2; /* accumulator that code2 increments once per surviving row (its COUNT), or -1 */
   uint32_t code2[MSC_VM_MAX_CODE2];
 } msc_scan_desc;
 

@@ -80,10 +80,8 @@ def group_body(codes: list[str]) -> list[str]:
     body = []
     for r in range(R):
         body += codes[r] if isinstance(codes[r], list) else [codes[r]]
-        body += [f"setp.lt.u32 q, c{r}, ng;", f"and.pred q, q, pv{r};", f"selp.b32 c{r}, c{r}, ng, q;",
-                 f"mul.lo.u32 go{r}, c{r}, gstride;",
-                 f"add.u32 ad2, accb, go{r};", "add.u32 ad2, ad2, cntoff;",
-                 "ld.shared.u64 xi, [ad2];", "add.u64 xi, xi, 1;", "st.shared.u64 [ad2], xi;"]
+        # a code outside [0, ngroups) cannot be aggregated: the row is dropped like a filtered one
+        body += [f"setp.lt.u32 q, c{r}, ng;", f"and.pred pv{r}, pv{r}, q;", f"mul.lo.u32 go{r}, c{r}, gstride;"]
     return body
 
 
@@ -122,16 +120,19 @@ def agg_rmw(kind: str, val: str) -> list[str]:
     for r in range(R):
         v = val.format(r=r)
         body.append(f"add.u32 ad2, base, go{r};")
+        pr = f"@pv{r} "  # rows that failed a filter (or lie past the end of the relation) touch nothing
         if kind == "SUMF":
-            body += ["ld.shared.f64 xf, [ad2];", f"add.f64 xf, xf, {v};", "st.shared.f64 [ad2], xf;"]
+            body += [pr + "ld.shared.f64 xf, [ad2];", pr + f"add.f64 xf, xf, {v};", pr + "st.shared.f64 [ad2], xf;"]
         elif kind == "SUMI":
-            body += ["ld.shared.u64 xi, [ad2];", f"add.s64 xi, xi, {v};", "st.shared.u64 [ad2], xi;"]
+            body += [pr + "ld.shared.u64 xi, [ad2];", pr + f"add.s64 xi, xi, {v};", pr + "st.shared.u64 [ad2], xi;"]
         elif kind in ("MINF", "MAXF"):
             cmp_ = "lt" if kind == "MINF" else "gt"
-            body += ["ld.shared.f64 xf, [ad2];", f"setp.{cmp_}.f64 q, {v}, xf;", f"selp.f64 xf, {v}, xf, q;", "st.shared.f64 [ad2], xf;"]
+            body += [pr + "ld.shared.f64 xf, [ad2];", pr + f"setp.{cmp_}.f64 q, {v}, xf;", pr + f"selp.f64 xf, {v}, xf, q;",
+                     pr + "st.shared.f64 [ad2], xf;"]
         else:
             cmp_ = "lt" if kind == "MINI" else "gt"
-            body += ["ld.shared.u64 xi, [ad2];", f"setp.{cmp_}.s64 q, {v}, xi;", f"selp.b64 xi, {v}, xi, q;", "st.shared.u64 [ad2], xi;"]
+            body += [pr + "ld.shared.u64 xi, [ad2];", pr + f"setp.{cmp_}.s64 q, {v}, xi;", pr + f"selp.b64 xi, {v}, xi, q;",
+                     pr + "st.shared.u64 [ad2], xi;"]
     return body
 
 
@@ -143,13 +144,13 @@ for d in range(1, DEPTH + 1):
 
 count_body = [f"mad.lo.u32 base, a1, {SLOT_STRIDE}, accb;"]
 for r in range(R):
-    count_body += [f"add.u32 ad2, base, go{r};", "ld.shared.u64 xi, [ad2];", "add.u64 xi, xi, 1;", "st.shared.u64 [ad2], xi;"]
+    count_body += [f"add.u32 ad2, base, go{r};", f"@pv{r} ld.shared.u64 xi, [ad2];", f"@pv{r} add.u64 xi, xi, 1;", f"@pv{r} st.shared.u64 [ad2], xi;"]
 add("COUNT", count_body, A_SLOT, agg=AGG_KIND["SUMI"])
 
 for kind, phys in (("F32", "F32"), ("F64", "F64"), ("I32F", "I32")):  # fused load + SUM: a1 = column, a2 = slot
     body = load_rows(kind, "x") + [f"mad.lo.u32 base, a2, {SLOT_STRIDE}, accb;"]
     for r in range(R):
-        body += [f"add.u32 ad2, base, go{r};", "ld.shared.f64 xf, [ad2];", f"add.f64 xf, xf, x_{r};", "st.shared.f64 [ad2], xf;"]
+        body += [f"add.u32 ad2, base, go{r};", f"@pv{r} ld.shared.f64 xf, [ad2];", f"@pv{r} add.f64 xf, xf, x_{r};", f"@pv{r} st.shared.f64 [ad2], xf;"]
     add(f"AGGCOL_{kind}", body, A_COL, A_SLOT, PHYS[phys], agg=AGG_KIND["SUMF"])
 
 
@@ -164,21 +165,22 @@ def ptx() -> str:
         ".reg .f64 xf;",
         ".reg .f32 f0, f1, f2, f3;",
         ".reg .b32 i0, i1, i2, i3, c0, c1, c2, c3, go0, go1, go2, go3, w8, w9;",
-        ".reg .b32 sb, accb, pc, cstb, lane, ng, gstride, cntoff, vm, w, h, a1, a2, ad, ad2, base, tb;",
+        ".reg .b32 sb, accb, pc, cstb, lane, ng, gstride, vm, w, wn, h, a1, a2, ad, ad2, base, tb;",
         ".reg .pred pv0, pv1, pv2, pv3, q;",
     ]
     lines = ["{"] + regs
     lines += ["mov.u32 sb, %0;", "mov.u32 accb, %1;", "mov.u32 pc, %2;", "mov.u32 cstb, %3;", "mov.u32 lane, %4;",
-              "mov.u32 ng, %5;", "mov.u32 gstride, %6;", "mov.u32 vm, %7;", "mov.u32 cntoff, %8;"]
+              "mov.u32 ng, %5;", "mov.u32 gstride, %6;", "mov.u32 vm, %7;", "ld.shared.u32 wn, [pc];"]
     for r in range(R):
-        lines += [f"and.b32 tb, vm, {1 << r};", f"setp.ne.u32 pv{r}, tb, 0;", f"mul.lo.u32 go{r}, ng, gstride;"]
+        lines += [f"and.b32 tb, vm, {1 << r};", f"setp.ne.u32 pv{r}, tb, 0;", f"mov.u32 go{r}, 0;"]
     for d in range(DEPTH):  # defined values everywhere (ptxas would otherwise warn about use-before-def paths)
         lines += [f"mov.b64 s{d}_{r}, 0;" for r in range(R)]
     for k in range(NTEMPS):
         lines += [f"mov.b64 t{k}_{r}, 0;" for r in range(R)]
     lines.append("RV_TABLE: .branchtargets " + ", ".join(f"RV_H{i}" for i in range(len(handlers))) + ";")
-    lines += ["RV_NEXT:", "ld.shared.u32 w, [pc];", "add.u32 pc, pc, 4;", "and.b32 h, w, 255;", "bfe.u32 a1, w, 8, 12;",
-              "shr.u32 a2, w, 20;", "brx.idx h, RV_TABLE;"]
+    # dispatch: the next instruction word is fetched one instruction ahead so its shared-memory latency overlaps the handler
+    lines += ["RV_NEXT:", "mov.b32 w, wn;", "ld.shared.u32 wn, [pc+4];", "add.u32 pc, pc, 4;", "and.b32 h, w, 255;",
+              "bfe.u32 a1, w, 8, 12;", "shr.u32 a2, w, 20;", "brx.idx h, RV_TABLE;"]
     for i, hnd in enumerate(handlers):
         lines.append(f"RV_H{i}:  // {hnd['name']}")
         lines += [ln for ln in hnd["body"] if ln]

@@ -25,14 +25,16 @@ __global__ void dense_init_kernel(unsigned long long* out, int ngroups, int nagg
 }
 
 // compact the dense table: one output row per group whose hidden row counter is > 0
-__global__ void dense_finalize_kernel(const unsigned long long* table, int ngroups, int naggs_total, uint32_t* out_key,
-                                      unsigned long long* const* out_acc, unsigned long long* out_n) {
+// table[g][stride]: export the first `nexport` accumulators of every group whose row counter (slot
+// `count_slot`) is non-zero
+__global__ void dense_finalize_kernel(const unsigned long long* table, int ngroups, int stride, int nexport, int count_slot,
+                                      uint32_t* out_key, unsigned long long* const* out_acc, unsigned long long* out_n) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   unsigned long long n = 0;
   for (int g = 0; g < ngroups; ++g) {
-    if (table[g * naggs_total + naggs_total - 1] == 0) continue;
+    if (table[g * stride + count_slot] == 0) continue;
     out_key[n] = g;
-    for (int a = 0; a < naggs_total - 1; ++a) out_acc[a][n] = table[g * naggs_total + a];
+    for (int a = 0; a < nexport; ++a) out_acc[a][n] = table[g * stride + a];
     ++n;
   }
   *out_n = n;
@@ -378,6 +380,7 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
   uint32_t ns = budget > fixed ? static_cast<uint32_t>((budget - fixed) / (static_cast<size_t>(NW) * p.stage_bytes)) : 0;
   if (ns > 4) ns = 4;
   if (ns < 2) ns = 2;
+  if (ntemps_override == 0 && ns > 2) ns = 2;  // regvm: latency bound per warp, so spend shared memory on resident warps
   if (forced >= 1 && forced <= MAX_STAGES) ns = static_cast<uint32_t>(forced);
   p.nstages = ns;
   p.warp_bytes = static_cast<uint32_t>(ns * p.stage_bytes + temps_bytes);
@@ -508,13 +511,17 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
 
   if (dense) {
-    const int ntot = naggs + 1;  // + hidden row counter
+    // The C++ kernel keeps a hidden per-group row counter and a trash group for filtered rows; the regvm
+    // kernel predicates its updates instead and uses the query's own COUNT accumulator (count_slot2).
+    const bool use_regvm = sd->ncode2 > 0 && regvm_enabled() && sd->count_slot2 >= 0 && sd->count_slot2 < naggs &&
+                           agg_kinds[sd->count_slot2] == MSC_AGG_SUM_I;
+    const int ntot = use_regvm ? naggs : naggs + 1;
+    const int count_slot = use_regvm ? sd->count_slot2 : naggs;
     kinds[naggs] = MSC_AGG_SUM_I;
     init[naggs] = 0;
-    const size_t acc_bytes = static_cast<size_t>(ngroups + 1) * ntot * NT * sizeof(long long);
+    const size_t acc_bytes = static_cast<size_t>(use_regvm ? ngroups : ngroups + 1) * ntot * NT * sizeof(long long);
     if (acc_bytes > 96 * 1024) return ctx->fail(MSC_ERR_ARG, "dense aggregate: groups x aggregates too large; use hash mode");
-    const bool use_regvm = sd->ncode2 > 0 && regvm_enabled();
-    const size_t regvm_bytes = MSC_RV_MAX_CODE * sizeof(uint32_t) + MSC_VM_MAX_CONSTS * sizeof(long long);
+    const size_t regvm_bytes = (MSC_RV_MAX_CODE + 2) * sizeof(uint32_t) + MSC_VM_MAX_CONSTS * sizeof(long long);
     LaunchPlan lp;
     if (use_regvm) MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, acc_bytes + regvm_bytes, &lp, 0));
     else MSC_TRY(plan_launch(ctx, sd, R, acc_bytes, &lp));
@@ -550,7 +557,7 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     for (int a = 0; a < naggs; ++a) ptrs.push_back(static_cast<unsigned long long*>(rel->cols[1 + a].data));
     MSC_TRY(d_ptrs.alloc(sizeof(void*) * (naggs + 1)));
     if (naggs) MSC_CUDA(ctx, cudaMemcpyAsync(d_ptrs.p, ptrs.data(), sizeof(void*) * naggs, cudaMemcpyHostToDevice, ctx->stream));
-    dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot,
+    dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, naggs, count_slot,
                                                     static_cast<uint32_t*>(rel->cols[0].data),
                                                     d_ptrs.as<unsigned long long*>(), d_n.as<unsigned long long>());
     ctx->stats.launches += 1;

@@ -310,6 +310,7 @@ class _ScanResolver:
         d.nluts = len(self.luts)
         d.ntemps = program.ntemps
         d.ncode2 = len(program.regvm)
+        d.count_slot2 = program.regvm_count_slot
         for i, w in enumerate(program.regvm):
             d.code2[i] = w
         for i, ptr in enumerate(self.luts):

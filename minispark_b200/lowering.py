@@ -536,6 +536,7 @@ class Program:
     ntemps: int = 0
     text: list[str] = field(default_factory=list)    # disassembly, for explain/tests
     regvm: list[int] = field(default_factory=list)   # same query for the register-resident interpreter (may be empty)
+    regvm_count_slot: int = -1                       # accumulator slot of COUNT (the regvm kernel's group-presence counter)
     regvm_text: list[str] = field(default_factory=list)
 
     def words(self) -> list[int]:
@@ -842,6 +843,9 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
                 raise LoweringError("too many aggregates in one GROUP BY")
             unique[key] = len(unique)
         slot_of.append(unique[key])
+    count_key = ("count", EConst(INT, 1))
+    if REGVM_ENABLED and count_key not in unique and len(unique) < K["MSC_VM_MAX_AGGS"]:
+        unique[count_key] = len(unique)  # the regvm kernel tells present groups by their row count
     filters = split_conjunctions(filters)
     b.plan_cse([*filters, group, *[e for (k, e) in unique if k != "count"]])
     for f in filters:
@@ -859,6 +863,7 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
     if REGVM_ENABLED:
         try:
             program.regvm, program.regvm_text = compile_regvm(b, filters, group, unique)
+            program.regvm_count_slot = unique.get(count_key, -1)
         except _RegvmUnsupported:
             program.regvm, program.regvm_text = [], []
     return AggregateProgram(program, kinds, slot_of, group_dict)

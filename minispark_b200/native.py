@@ -66,7 +66,7 @@ class ScanDesc(C.Structure):
         ("ntemps", C.c_int32),
         ("luts", C.c_void_p * K["MSC_VM_MAX_LUTS"]),
         ("ncode2", C.c_int32),
-        ("_pad2", C.c_int32),
+        ("count_slot2", C.c_int32),
         ("code2", C.c_uint32 * K["MSC_VM_MAX_CODE2"]),
     ]
 
