@@ -81,7 +81,7 @@ def group_body(codes: list[str]) -> list[str]:
     for r in range(R):
         body += codes[r] if isinstance(codes[r], list) else [codes[r]]
         # a code outside [0, ngroups) cannot be aggregated: the row is dropped like a filtered one
-        body += [f"setp.lt.u32 q, c{r}, ng;", f"and.pred pv{r}, pv{r}, q;", f"mul.lo.u32 go{r}, c{r}, gstride;"]
+        body += [f"setp.lt.u32 q, c{r}, ng;", f"and.pred pv{r}, pv{r}, q;", f"selp.b32 c{r}, c{r}, 0, q;", f"mul.lo.u32 go{r}, c{r}, gstride;"]
     return body
 
 
@@ -121,18 +121,16 @@ def agg_rmw(kind: str, val: str) -> list[str]:
         v = val.format(r=r)
         body.append(f"add.u32 ad2, base, go{r};")
         pr = f"@pv{r} "  # rows that failed a filter (or lie past the end of the relation) touch nothing
-        if kind == "SUMF":
-            body += [pr + "ld.shared.f64 xf, [ad2];", pr + f"add.f64 xf, xf, {v};", pr + "st.shared.f64 [ad2], xf;"]
+        if kind == "SUMF":   # only the store is predicated: a predicated load + add would be if-converted into selects
+            body += ["ld.shared.f64 xf, [ad2];", f"add.f64 xf, xf, {v};", pr + "st.shared.f64 [ad2], xf;"]
         elif kind == "SUMI":
-            body += [pr + "ld.shared.u64 xi, [ad2];", pr + f"add.s64 xi, xi, {v};", pr + "st.shared.u64 [ad2], xi;"]
+            body += ["ld.shared.u64 xi, [ad2];", f"add.s64 xi, xi, {v};", pr + "st.shared.u64 [ad2], xi;"]
         elif kind in ("MINF", "MAXF"):
             cmp_ = "lt" if kind == "MINF" else "gt"
-            body += [pr + "ld.shared.f64 xf, [ad2];", pr + f"setp.{cmp_}.f64 q, {v}, xf;", pr + f"selp.f64 xf, {v}, xf, q;",
-                     pr + "st.shared.f64 [ad2], xf;"]
+            body += ["ld.shared.f64 xf, [ad2];", f"setp.{cmp_}.f64 q, {v}, xf;", f"selp.f64 xf, {v}, xf, q;", pr + "st.shared.f64 [ad2], xf;"]
         else:
             cmp_ = "lt" if kind == "MINI" else "gt"
-            body += [pr + "ld.shared.u64 xi, [ad2];", pr + f"setp.{cmp_}.s64 q, {v}, xi;", pr + f"selp.b64 xi, {v}, xi, q;",
-                     pr + "st.shared.u64 [ad2], xi;"]
+            body += ["ld.shared.u64 xi, [ad2];", f"setp.{cmp_}.s64 q, {v}, xi;", f"selp.b64 xi, {v}, xi, q;", pr + "st.shared.u64 [ad2], xi;"]
     return body
 
 
@@ -142,15 +140,38 @@ for d in range(1, DEPTH + 1):
         add(f"AGG_{kind}_D{d}", agg_rmw(kind, f"s{top}_{{r}}"), A_SLOT, A_NONE, -1, -1, d, AGG_KIND[kind])
     add(f"AGGK_SUMF_D{d}", agg_rmw("SUMF", f"s{top}_{{r}}"), A_SLOT, A_NONE, -1, 0, d, AGG_KIND["SUMF"])  # keep the value on the stack
 
+# ---- fused forms (fewer dispatches for the common f64 expression shapes) --------------------------------
+FLOAT_COLS = (("F32", "F32"), ("F64", "F64"), ("I32F", "I32"))
+for d in range(DEPTH):  # push op(column, const): a1 = column, a2 = constant
+    for kind, phys in FLOAT_COLS:
+        for name, expr in (("LDADDC", "add.f64 s{d}_{r}, x_{r}, c64;"), ("LDRSUBC", "sub.f64 s{d}_{r}, c64, x_{r};"),
+                           ("LDMULC", "mul.f64 s{d}_{r}, x_{r}, c64;")):
+            add(f"{name}_{kind}_D{d}", load_rows(kind, "x") + const_load("c64", "a2") + [expr.format(d=d, r=r) for r in range(R)],
+                A_COL, A_CONST, PHYS[phys], +1, d)
+for d in range(1, DEPTH + 1):  # top = top op column / top = top op temporary
+    top = d - 1
+    forms = (("ADD", "add.f64 s{t}_{r}, s{t}_{r}, {v};"), ("SUB", "sub.f64 s{t}_{r}, s{t}_{r}, {v};"),
+             ("RSUB", "sub.f64 s{t}_{r}, {v}, s{t}_{r};"), ("MUL", "mul.f64 s{t}_{r}, s{t}_{r}, {v};"))
+    for kind, phys in FLOAT_COLS:
+        for name, expr in forms:
+            add(f"{name}COL_{kind}_D{d}", load_rows(kind, "x") + [expr.format(t=top, r=r, v=f"x_{r}") for r in range(R)],
+                A_COL, A_NONE, PHYS[phys], 0, d)
+    for k in range(NTEMPS):
+        for name, expr in forms:
+            add(f"{name}T{k}_D{d}", [expr.format(t=top, r=r, v=f"t{k}_{r}") for r in range(R)], A_NONE, A_NONE, -1, 0, d)
+        # SUM the top of stack into slot a1, keep a copy in temporary k, pop
+        add(f"AGGT{k}_SUMF_D{d}", [f"mov.b64 t{k}_{r}, s{top}_{r};" for r in range(R)] + agg_rmw("SUMF", f"s{top}_{{r}}"),
+            A_SLOT, A_NONE, -1, -1, d, AGG_KIND["SUMF"])
+
 count_body = [f"mad.lo.u32 base, a1, {SLOT_STRIDE}, accb;"]
 for r in range(R):
-    count_body += [f"add.u32 ad2, base, go{r};", f"@pv{r} ld.shared.u64 xi, [ad2];", f"@pv{r} add.u64 xi, xi, 1;", f"@pv{r} st.shared.u64 [ad2], xi;"]
+    count_body += [f"add.u32 ad2, base, go{r};", "ld.shared.u64 xi, [ad2];", "add.u64 xi, xi, 1;", f"@pv{r} st.shared.u64 [ad2], xi;"]
 add("COUNT", count_body, A_SLOT, agg=AGG_KIND["SUMI"])
 
 for kind, phys in (("F32", "F32"), ("F64", "F64"), ("I32F", "I32")):  # fused load + SUM: a1 = column, a2 = slot
     body = load_rows(kind, "x") + [f"mad.lo.u32 base, a2, {SLOT_STRIDE}, accb;"]
     for r in range(R):
-        body += [f"add.u32 ad2, base, go{r};", f"@pv{r} ld.shared.f64 xf, [ad2];", f"@pv{r} add.f64 xf, xf, x_{r};", f"@pv{r} st.shared.f64 [ad2], xf;"]
+        body += [f"add.u32 ad2, base, go{r};", "ld.shared.f64 xf, [ad2];", f"add.f64 xf, xf, x_{r};", f"@pv{r} st.shared.f64 [ad2], xf;"]
     add(f"AGGCOL_{kind}", body, A_COL, A_SLOT, PHYS[phys], agg=AGG_KIND["SUMF"])
 
 
@@ -173,10 +194,7 @@ def ptx() -> str:
               "mov.u32 ng, %5;", "mov.u32 gstride, %6;", "mov.u32 vm, %7;", "ld.shared.u32 wn, [pc];"]
     for r in range(R):
         lines += [f"and.b32 tb, vm, {1 << r};", f"setp.ne.u32 pv{r}, tb, 0;", f"mov.u32 go{r}, 0;"]
-    for d in range(DEPTH):  # defined values everywhere (ptxas would otherwise warn about use-before-def paths)
-        lines += [f"mov.b64 s{d}_{r}, 0;" for r in range(R)]
-    for k in range(NTEMPS):
-        lines += [f"mov.b64 t{k}_{r}, 0;" for r in range(R)]
+    # stack slots / temporaries are written before they are read (the host validates the depth of every instruction)
     lines.append("RV_TABLE: .branchtargets " + ", ".join(f"RV_H{i}" for i in range(len(handlers))) + ";")
     # dispatch: the next instruction word is fetched one instruction ahead so its shared-memory latency overlaps the handler
     lines += ["RV_NEXT:", "mov.b32 w, wn;", "ld.shared.u32 wn, [pc+4];", "add.u32 pc, pc, 4;", "and.b32 h, w, 255;",

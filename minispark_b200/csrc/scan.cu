@@ -344,6 +344,8 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
     p.staged[c].width = static_cast<uint32_t>(w);
     p.staged[c].smem_off = off;
     p.staged[c].phys = sd->staged[c].phys;
+    p.staged[c].tile_bytes = static_cast<uint32_t>(w * wt);
+    p.tile_tx_bytes += static_cast<uint32_t>(w * wt);
     off += static_cast<uint32_t>(msc_round_up(w * wt, 128));
   }
   p.stage_bytes = off ? off : 128;

@@ -29,9 +29,9 @@ enum Mode { MODE_DENSE = 0, MODE_HASH = 1, MODE_COUNT = 2, MODE_PROJECT = 3 };
 struct StagedCol {
   const unsigned char* base;
   uint32_t width;
-  uint32_t smem_off;  // offset inside one warp stage
+  uint32_t smem_off;    // offset inside one warp stage
   int phys;
-  int _pad;
+  uint32_t tile_bytes;  // width * rows per warp tile: bytes of one bulk copy
 };
 
 struct ScanParams {
@@ -42,6 +42,8 @@ struct ScanParams {
   uint32_t warp_bytes;   // nstages * stage_bytes + temporaries of one warp
   uint32_t nstaged;
   uint32_t ntemps;
+  uint32_t tile_tx_bytes;  // sum of tile_bytes: what one warp tile's mbarrier expects
+  uint32_t _pad0;
   StagedCol staged[MSC_VM_MAX_STAGED];
   const void* gather[MSC_VM_MAX_GATHER];
   int gather_phys[MSC_VM_MAX_GATHER];
@@ -743,17 +745,27 @@ __device__ __forceinline__ bool run_fast(const Ctx& c, int fast, uint32_t w0, ui
   }
 }
 
-// lane 0 of a warp: start the bulk copies of warp tile `tile` into ring slot `stage`
+// Start the bulk copies of warp tile `tile` into ring slot `stage`: lane 0 arms the mbarrier with the
+// tile's byte count, then lane c starts column c's copy (one cp.async.bulk per referenced column).
 __device__ __forceinline__ void issue_tile(const ScanParams& p, unsigned char* stages, uint64_t* full, uint32_t stage,
-                                           uint64_t tile, uint32_t tile_rows) {
-  unsigned char* sbase = stages + static_cast<size_t>(stage) * p.stage_bytes;
-  uint32_t total = 0;
-  for (uint32_t c = 0; c < p.nstaged; ++c) total += p.staged[c].width * tile_rows;
-  mbar_expect_tx(&full[stage], total);
-  for (uint32_t c = 0; c < p.nstaged; ++c) {
-    const uint32_t bytes = p.staged[c].width * tile_rows;
-    bulk_g2s(sbase + p.staged[c].smem_off, p.staged[c].base + tile * bytes, bytes, &full[stage]);
+                                           uint64_t tile, int lane) {
+  if (lane == 0) mbar_expect_tx(&full[stage], p.tile_tx_bytes);
+  __syncwarp();
+  if (lane < static_cast<int>(p.nstaged)) {
+    const StagedCol& c = p.staged[lane];
+    bulk_g2s(stages + stage * p.stage_bytes + c.smem_off, c.base + tile * c.tile_bytes, c.tile_bytes, &full[stage]);
   }
+}
+
+// validity bits of a lane's R consecutive rows starting at row0
+template <int R>
+__device__ __forceinline__ uint32_t row_mask(uint64_t row0, uint64_t nrows) {
+  if (row0 + R <= nrows) return (1u << R) - 1u;
+  uint32_t m = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (row0 + r < nrows) m |= 1u << r;
+  return m;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -783,9 +795,9 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
   const uint32_t gw = blockIdx.x * NW + warp;  // global warp id
   const uint32_t nw = gridDim.x * NW;
   const uint32_t ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
-  if (lane == 0) {
+  {
     const uint32_t pre = ntiles_w < p.nstages ? ntiles_w : p.nstages;
-    for (uint32_t k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + static_cast<uint64_t>(k) * nw, WT);
+    for (uint32_t k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + static_cast<uint64_t>(k) * nw, lane);
   }
 
   uint32_t stage = 0, parity = 0;
@@ -795,13 +807,10 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     while (!mbar_try_wait(&full[stage], parity)) {
     }
     const uint64_t row0 = tile * WT + static_cast<uint64_t>(lane) * R;
-    uint32_t vmask = 0;
+    uint32_t vmask = row_mask<R>(row0, p.nrows);
     int grp[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (row0 + r < p.nrows) vmask |= 1u << r;
-      grp[r] = (MODE == MODE_DENSE) ? p.ngroups : -1;
-    }
+    for (int r = 0; r < R; ++r) grp[r] = (MODE == MODE_DENSE) ? p.ngroups : -1;
     uint64_t out_pos = row0;  // project: output position of this lane's first surviving row
     const Ctx c{p, sbase, temps, acc, lane, tid};
 
@@ -860,7 +869,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     }
 
     __syncwarp();  // every lane is done reading this stage
-    if (lane == 0 && k + p.nstages < ntiles_w) issue_tile(p, stages, full, stage, gw + static_cast<uint64_t>(k + p.nstages) * nw, WT);
+    if (k + p.nstages < ntiles_w) issue_tile(p, stages, full, stage, gw + static_cast<uint64_t>(k + p.nstages) * nw, lane);
     if (++stage == p.nstages) {
       stage = 0;
       parity ^= 1u;

@@ -949,26 +949,37 @@ def compile_regvm(b: "ProgramBuilder", filters: Sequence[Expr], group: Expr, uni
             walk(e)
     temps: dict[Expr, int] = {}
 
-    def load(e: Expr, d: int) -> bool:
-        """Push a column leaf at depth d; False when e is not a loadable leaf."""
+    def float_leaf(e: Expr) -> Optional[tuple[str, int]]:
+        """(column kind, staged slot) of a FLOAT-valued column leaf: f32 / f64 column or an i32 column cast to float."""
         if isinstance(e, EInput) and e.type == FLOAT:
             bd = column(e)
-            name = {P_F32: "LD_F32", P_F64: "LD_F64"}.get(bd.phys)
+            kind = {P_F32: "F32", P_F64: "F64"}.get(bd.phys)
         elif isinstance(e, ECast) and isinstance(e.child, EInput) and e.child.type in (INT, BOOL):
             bd = column(e.child)
-            name = {P_I32: "LD_I32F"}.get(bd.phys)
-        elif isinstance(e, EInput) and e.type in (INT, TS):
+            kind = {P_I32: "I32F"}.get(bd.phys)
+        else:
+            return None
+        if kind is None:
+            raise _RegvmUnsupported("column type")
+        return kind, bd.staged
+
+    def load(e: Expr, d: int) -> bool:
+        """Push a column leaf at depth d; False when e is not a loadable leaf."""
+        leaf = float_leaf(e)
+        if leaf is not None:
+            emit(f"LD_{leaf[0]}_D{d}", leaf[1])
+            return True
+        if isinstance(e, EInput) and e.type in (INT, TS):
             bd = column(e)
             name = {P_I32: "LD_I32", P_I64: "LD_I64"}.get(bd.phys)
-        else:
-            return False
-        if name is None:
-            raise _RegvmUnsupported("column type")
-        emit(f"{name}_D{d}", bd.staged)
-        return True
+            if name is None:
+                raise _RegvmUnsupported("column type")
+            emit(f"{name}_D{d}", bd.staged)
+            return True
+        return False
 
-    def gen(e: Expr, d: int) -> None:
-        """Evaluate e into stack slot d (depth d -> d + 1)."""
+    def gen(e: Expr, d: int, tee: bool = True) -> None:
+        """Evaluate e into stack slot d (depth d -> d + 1), preferring the fused instruction forms."""
         if d >= RV_MAX_DEPTH:
             raise _RegvmUnsupported("expression too deep")
         if e in temps:
@@ -982,18 +993,39 @@ def compile_regvm(b: "ProgramBuilder", filters: Sequence[Expr], group: Expr, uni
             return
         if not (isinstance(e, EBin) and e.type == FLOAT and e.op in ("add", "sub", "mul")):
             raise _RegvmUnsupported(f"operator {getattr(e, 'op', type(e).__name__)}")
-        cl, cr = _float_const(e.left), _float_const(e.right)
-        if cr is not None and cl is None:      # x op c
-            gen(e.left, d)
-            emit({"add": "ADDC", "sub": "ADDC", "mul": "MULC"}[e.op] + f"_D{d + 1}", b.const(f64_bits(-cr if e.op == "sub" else cr)))
-        elif cl is not None and cr is None:    # c op x
-            gen(e.right, d)
-            emit({"add": "ADDC", "sub": "RSUBC", "mul": "MULC"}[e.op] + f"_D{d + 1}", b.const(f64_bits(cl)))
+        left, right, op = e.left, e.right, e.op
+        cl, cr = _float_const(left), _float_const(right)
+        if (cl is None) != (cr is None):  # one side is a constant
+            other, cval = (left, cr) if cr is not None else (right, cl)
+            if cr is not None:   # x op c
+                name, cval = {"add": ("ADDC", cval), "sub": ("ADDC", -cval), "mul": ("MULC", cval)}[op]
+            else:                # c op x
+                name = {"add": "ADDC", "sub": "RSUBC", "mul": "MULC"}[op]
+            leaf = float_leaf(other) if other not in temps else None
+            if leaf is not None:
+                emit(f"LD{name}_{leaf[0]}_D{d}", leaf[1], b.const(f64_bits(cval)))
+            else:
+                gen(other, d)
+                emit(f"{name}_D{d + 1}", b.const(f64_bits(cval)))
         else:
-            gen(e.left, d)
-            gen(e.right, d + 1)
-            emit({"add": "ADDF", "sub": "SUBF", "mul": "MULF"}[e.op] + f"_D{d + 2}")
-        if counts.get(e, 0) > 1 and len(temps) < RV_MAX_TEMPS:
+            def operand_form(x: Expr) -> Optional[tuple[str, int]]:
+                if x in temps:
+                    return f"T{temps[x]}", 0
+                leaf = float_leaf(x)
+                return (f"COL_{leaf[0]}", leaf[1]) if leaf is not None else None
+
+            rform, lform = operand_form(right), operand_form(left)
+            if rform is not None:      # top = left op right-operand
+                gen(left, d)
+                emit({"add": "ADD", "sub": "SUB", "mul": "MUL"}[op] + f"{rform[0]}_D{d + 1}", rform[1])
+            elif lform is not None:    # top = left-operand op right  (reversed subtraction)
+                gen(right, d)
+                emit({"add": "ADD", "sub": "RSUB", "mul": "MUL"}[op] + f"{lform[0]}_D{d + 1}", lform[1])
+            else:
+                gen(left, d)
+                gen(right, d + 1)
+                emit({"add": "ADDF", "sub": "SUBF", "mul": "MULF"}[op] + f"_D{d + 2}")
+        if tee and counts.get(e, 0) > 1 and len(temps) < RV_MAX_TEMPS:
             temps[e] = len(temps)
             emit(f"TEE{temps[e]}_D{d + 1}")
 
@@ -1013,7 +1045,12 @@ def compile_regvm(b: "ProgramBuilder", filters: Sequence[Expr], group: Expr, uni
                 emit("AGGCOL_I32F", column(e.child).staged, slot)
                 continue
         if is_float:
-            gen(e, 0)
+            shared = kind == "sum" and e not in temps and counts.get(e, 0) > 1 and len(temps) < RV_MAX_TEMPS
+            gen(e, 0, tee=not shared)
+            if shared:  # aggregate and keep the value for a later expression in one instruction
+                temps[e] = len(temps)
+                emit(f"AGGT{temps[e]}_SUMF_D1", slot)
+                continue
         elif not load(e, 0):
             raise _RegvmUnsupported("integer expression")
         emit(f"AGG_{kind.upper()}{'F' if is_float else 'I'}_D1", slot)

@@ -223,6 +223,18 @@ DF_CASES: dict[str, tuple[Callable[[Any, dict, Any], Any], Any, bool]] = {
         ns.DataFrame().table(t["orders"]).alias("o"), on=ns.Col("u.user_id") == ns.Col("o.user_id"), how="inner")
         .filter(ns.Col("o.quantity") >= 1).group_by(ns.Col("u.country")).agg(
             ns.F.sum(ns.Col("o.price")).alias("sales"), ns.F.avg(ns.Col("u.age")).alias("avg_age"), ns.F.count()), None, False),
+    # arithmetic shapes of the register-resident interpreter (operand order of -, fused column / constant forms, CSE)
+    "agg_arith_shapes": (lambda ns, t, e: _df(ns, e, t["orders"]).filter(ns.Col("quantity") >= 1).group_by(ns.Col("product")).agg(
+        ns.F.sum(ns.Col("price") - ns.Col("quantity")).alias("a"), ns.F.sum(ns.Col("quantity") - ns.Col("price")).alias("b"),
+        ns.F.sum(ns.Lit(100) - ns.Col("price")).alias("c"), ns.F.sum(ns.Col("price") - 100).alias("d"),
+        ns.F.sum((ns.Col("price") + ns.Col("quantity")) * (ns.Col("price") - ns.Col("quantity"))).alias("e"),
+        ns.F.sum(ns.Col("price") * ns.Col("price") * ns.Col("quantity")).alias("f"),
+        ns.F.min(ns.Col("price") - 1).alias("g"), ns.F.max(ns.Lit(2) * ns.Col("price")).alias("h"),
+        ns.F.sum((ns.Col("price") + ns.Col("quantity")) * (ns.Col("price") - ns.Col("quantity")) * ns.Col("price")).alias("i"),
+        ns.F.avg(ns.Col("price") * (ns.Lit(1) - ns.Col("quantity")) * (ns.Lit(1) + ns.Col("price"))).alias("j"),
+        ns.F.sum(ns.Col("quantity")).alias("k"), ns.F.max(ns.Col("quantity")).alias("l"), ns.F.count()), None, False),
+    "agg_float_filter": (lambda ns, t, e: _df(ns, e, t["orders"]).filter(ns.Col("price") <= 300.0).filter(ns.Col("order_date") > "2025-01-01")
+        .group_by(ns.Col("product")).agg(ns.F.sum(ns.Col("price")).alias("s"), ns.F.min(ns.Col("price")).alias("lo")), None, False),
     "empty_result": (lambda ns, t, e: _df(ns, e, t["orders"]).filter(ns.Col("price") > 1e9), [], True),
     "concat_filter": (lambda ns, t, e: _df(ns, e, t["users"]).filter(ns.Col("age") < 30).select(
         (ns.Col("first_name") + "-" + ns.Col("country")).alias("tag"), ns.Col("age")), None, True),
