@@ -138,11 +138,11 @@ enum msc_opcode {
 #define MSC_VM_MAX_CODE 192  /* u32 words = 96 instructions */
 #define MSC_VM_MAX_CODE2 128 /* regvm instructions */
 #define MSC_VM_MAX_CONSTS 32
-#define MSC_VM_MAX_STAGED 12 /* directly scanned columns (incl. index vectors) */
+#define MSC_VM_MAX_STAGED 24 /* directly scanned columns (incl. index vectors); <= 32: one lane issues one column's copy */
 #define MSC_VM_MAX_GATHER 16 /* columns read through an index vector */
 #define MSC_VM_MAX_LUTS 8
 #define MSC_VM_MAX_AGGS 16
-#define MSC_VM_MAX_OUT 16
+#define MSC_VM_MAX_OUT 24
 
 /* aggregate kinds for msc_scan_aggregate */
 #define MSC_AGG_SUM_F 0
