@@ -46,7 +46,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--sf", type=float, default=15.0, help="lineitem scale factor PER GPU (sf15 ~ 90M rows)")
     ap.add_argument("--layout", choices=["native", "wide"], default="native")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=7)
     ap.add_argument("--keep", action="store_true", help="keep the generated table")
     return ap.parse_args()
 
@@ -326,7 +326,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
             engine.release_query()
             if i > 0:  # first pass warms allocator pools
                 e2e_times.append(dt)
-        e2e_s = max_over_ranks(statistics.mean(e2e_times))
+        # median: the host link is shared with other tenants of the box, single passes are occasionally several times slower
+        e2e_s = max_over_ranks(statistics.median(e2e_times))
         e2e_value = total_rows / e2e_s
 
         if rank == 0:
@@ -358,7 +359,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
                              "north_star_layout_equiv_gbs": nrows_table * Q1_WIDE_BYTES_PER_ROW / (scan_ms * 1e-3) / 1e9 if args.layout == "native" else None},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                        "ms_per_step": 1e3 * e2e_s, "h2d_gbs": h2d_bytes / e2e_s / 1e9},
+                        "ms_per_step": 1e3 * e2e_s, "h2d_gbs": h2d_bytes / e2e_s / 1e9,
+                        "passes_ms": [round(1e3 * t, 2) for t in e2e_times], "statistic": "median of the passes (wall clock, rank-local)"},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "clocks": clocks.summary(),
                 "setup": {"generate_s": gen_s},

@@ -7,7 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/minispark_cuda.h"
@@ -32,6 +34,16 @@ struct msc_ctx {
   void* ring[kRing] = {nullptr, nullptr, nullptr, nullptr};
   size_t ring_bytes = 0;
   cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+
+  // Large-block cache in front of the driver's pool: a query (and every re-ingest of a table) asks for
+  // the same multi-hundred-MB column sizes again and again, and growing the driver pool by gigabytes
+  // costs 50 ms to > 1 s.  Freed blocks >= kBigBlock wait here, keyed by size; everything is ordered
+  // on `stream`, so a cached block may be handed out again immediately.
+  static constexpr size_t kBigBlock = 1 << 20;
+  std::multimap<size_t, void*> big_free;
+  std::unordered_map<void*, size_t> big_live;
+  size_t big_free_bytes = 0;
+  size_t big_free_cap = 0;  // set from the device's memory size in msc_create
 
   int fail(int code, const std::string& msg) {
     err = msg;

@@ -1,9 +1,37 @@
 // core.cu -- context lifetime, stream-ordered device memory, error word, relation handles.
 #include "common.cuh"
 
+static void release_cached_blocks(msc_ctx* ctx, size_t keep_bytes) {
+  while (ctx->big_free_bytes > keep_bytes && !ctx->big_free.empty()) {
+    auto it = std::prev(ctx->big_free.end());  // largest first
+    cudaFreeAsync(it->second, ctx->stream);
+    ctx->big_free_bytes -= it->first;
+    ctx->big_free.erase(it);
+  }
+}
+
 int msc_alloc(msc_ctx* ctx, size_t nbytes, void** out) {
   if (nbytes == 0) nbytes = 16;
-  MSC_CUDA(ctx, cudaMallocAsync(out, nbytes, ctx->stream));
+  if (nbytes >= msc_ctx::kBigBlock) {
+    auto it = ctx->big_free.lower_bound(nbytes);
+    if (it != ctx->big_free.end() && it->first <= nbytes + nbytes / 8) {
+      *out = it->second;
+      ctx->big_live[it->second] = it->first;
+      ctx->big_free_bytes -= it->first;
+      ctx->big_free.erase(it);
+      ctx->stats.device_bytes += nbytes;
+      return MSC_OK;
+    }
+  }
+  cudaError_t e = cudaMallocAsync(out, nbytes, ctx->stream);
+  if (e == cudaErrorMemoryAllocation && !ctx->big_free.empty()) {  // give the cache back and try once more
+    cudaGetLastError();
+    release_cached_blocks(ctx, 0);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaMallocAsync(out, nbytes, ctx->stream);
+  }
+  MSC_CUDA(ctx, e);
+  if (nbytes >= msc_ctx::kBigBlock) ctx->big_live[*out] = nbytes;
   ctx->stats.device_bytes += nbytes;
   return MSC_OK;
 }
@@ -12,6 +40,15 @@ int msc_free(msc_ctx* ctx, void* p, size_t nbytes) {
   if (!p) return MSC_OK;
   if (nbytes == 0) nbytes = 16;
   ctx->stats.device_bytes -= nbytes;
+  auto live = ctx->big_live.find(p);
+  if (live != ctx->big_live.end()) {
+    const size_t real = live->second;
+    ctx->big_live.erase(live);
+    ctx->big_free.emplace(real, p);
+    ctx->big_free_bytes += real;
+    if (ctx->big_free_bytes > ctx->big_free_cap) release_cached_blocks(ctx, ctx->big_free_cap / 2);
+    return MSC_OK;
+  }
   MSC_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
   return MSC_OK;
 }
@@ -62,6 +99,7 @@ extern "C" int msc_create(int device, msc_ctx** out) {
     return MSC_ERR_CUDA;
   }
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->big_free_cap = prop.totalGlobalMem / 2;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
   for (auto& s : ctx->copy)
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
@@ -85,6 +123,7 @@ extern "C" int msc_create(int device, msc_ctx** out) {
 extern "C" void msc_destroy(msc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  release_cached_blocks(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->ring)
     if (r) cudaFreeHost(r);
@@ -133,8 +172,7 @@ extern "C" int msc_dev_alloc(msc_ctx* ctx, size_t nbytes, void** out) {
 
 extern "C" int msc_dev_free(msc_ctx* ctx, void* p) {
   if (!p) return MSC_OK;
-  MSC_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
-  return MSC_OK;
+  return msc_free(ctx, p, 0);
 }
 
 extern "C" int msc_memcpy_d2h(msc_ctx* ctx, void* host_dst, const void* dev_src, size_t nbytes) {

@@ -238,6 +238,11 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
   if (!ctx || !t || !out || ncols < 0 || nblocks < 0 || (ncols && !cols) || (nblocks && !blocks))
     return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   const auto t0 = std::chrono::steady_clock::now();
+  static const bool trace = getenv("MSC_TRACE") != nullptr;  // phase timings of the load on stderr
+  auto mark = [&](const char* what) {
+    if (trace) fprintf(stderr, "[msc_table_load] %-28s +%.2f ms\n", what,
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
   uint64_t total = 0, max_rows = 0, max_str_bytes = 0;
   for (int b = 0; b < nblocks; ++b) {
     if (blocks[b] < 0 || blocks[b] >= static_cast<int32_t>(t->blocks.size())) return ctx->fail(MSC_ERR_ARG, "bad block id");
@@ -299,6 +304,7 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
   // all allocations above are stream-ordered on ctx->stream: make them visible to the copy streams
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(ctx->fail(MSC_ERR_CUDA, "sync failed"));
 
+  mark("allocated + synced");
   Loader ld{ctx, t};
   int flip = 0;
   uint64_t row_off = 0;
@@ -343,6 +349,7 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
     }
     row_off += bi.rows;
   }
+  mark("block loop issued");
   // join the copy streams into the compute stream
   for (int i = 0; i < 2; ++i) {
     if (cudaStreamSynchronize(ctx->copy[i]) != cudaSuccess && rc == MSC_OK) rc = ctx->fail(MSC_ERR_CUDA, "copy stream failed");
@@ -353,6 +360,7 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
     if (ev_done[i]) cudaEventDestroy(ev_done[i]);
   }
   if (rc != MSC_OK) return fail(rc);
+  mark("copies + decode complete");
 
   // narrow dictionary codes (native layout): u8 for <=256 entries, u16 for <=65536
   if (!wide) {
@@ -376,6 +384,7 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(ctx->fail(MSC_ERR_CUDA, "narrow failed"));
   }
+  mark("codes narrowed");
   const auto t1 = std::chrono::steady_clock::now();
   ctx->stats.last_ingest_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
   ctx->stats.last_ingest_bytes = ld.bytes;

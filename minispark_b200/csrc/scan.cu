@@ -3,6 +3,8 @@
 // The scan kernel itself lives in scan_kernel.cuh and is instantiated per (rows per lane, mode) in
 // scan_inst_*.cu so the specialisations compile in parallel.
 #define MSCAN_DECL_ONLY  // the kernel is instantiated in scan_inst_*.cu
+#include <algorithm>
+
 #include "scan_kernel.cuh"
 #include "scan_regvm.h"
 
@@ -28,16 +30,20 @@ __global__ void dense_init_kernel(unsigned long long* out, int ngroups, int nagg
 // table[g][stride]: export the first `nexport` accumulators of every group whose row counter (slot
 // `count_slot`) is non-zero
 __global__ void dense_finalize_kernel(const unsigned long long* table, int ngroups, int stride, int nexport, int count_slot,
-                                      uint32_t* out_key, unsigned long long* const* out_acc, unsigned long long* out_n) {
+                                      const int* kinds, uint32_t* out_key, unsigned long long* const* out_acc,
+                                      unsigned long long* out_n) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  unsigned long long n = 0;
+  unsigned long long n = 0, nonfinite = 0;
   for (int g = 0; g < ngroups; ++g) {
+    for (int a = 0; a < nexport; ++a)
+      if (kinds[a] == MSC_AGG_SUM_F && !isfinite(__longlong_as_double(static_cast<long long>(table[g * stride + a])))) nonfinite = 1;
     if (table[g * stride + count_slot] == 0) continue;
     out_key[n] = g;
     for (int a = 0; a < nexport; ++a) out_acc[a][n] = table[g * stride + a];
     ++n;
   }
-  *out_n = n;
+  out_n[0] = n;
+  out_n[1] = nonfinite;  // a masked regvm variant must not be trusted then (v * 0.0 = NaN leaks across groups)
 }
 
 constexpr int HTILE = 1024;  // slots per block in the hash-table compaction
@@ -326,7 +332,8 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, const int3
 }
 
 // Build kernel params + launch geometry.  extra_smem = CTA-wide bytes after the warp regions.
-int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem, LaunchPlan* lp, int ntemps_override = -1) {
+int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem, LaunchPlan* lp, int ntemps_override = -1,
+                int max_ctas = 4) {
   ScanParams& p = lp->p;
   memset(&p, 0, sizeof(p));
   const uint32_t wt = 32 * R;  // rows per warp tile
@@ -382,7 +389,16 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
   uint32_t ns = budget > fixed ? static_cast<uint32_t>((budget - fixed) / (static_cast<size_t>(NW) * p.stage_bytes)) : 0;
   if (ns > 4) ns = 4;
   if (ns < 2) ns = 2;
-  if (ntemps_override == 0 && ns > 2) ns = 2;  // regvm: latency bound per warp, so spend shared memory on resident warps
+  if (ntemps_override == 0) {
+    // regvm: registers allow `max_ctas` CTAs per SM (128 registers -> 4, the 168 of the 3- and 4-group masked
+    // variants -> 3).  A second ring slot hides the HBM latency of a warp's next tile (prof_r1h: 18 % of the stall
+    // samples were the wait for a single-slot ring), but resident warps matter more: take it only when it is free.
+    auto ctas = [&](uint32_t n) {
+      const size_t per_cta = fixed + static_cast<size_t>(NW) * n * p.stage_bytes + 1024;
+      return std::min<size_t>(static_cast<size_t>(max_ctas), (227 * 1024) / per_cta);
+    };
+    ns = ctas(2) >= ctas(1) ? 2 : 1;
+  }
   if (forced >= 1 && forced <= MAX_STAGES) ns = static_cast<uint32_t>(forced);
   p.nstages = ns;
   p.warp_bytes = static_cast<uint32_t>(ns * p.stage_bytes + temps_bytes);
@@ -395,7 +411,9 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
 
 // Validate the regvm encoding against the bound columns / accumulators and resolve its column
 // operands to shared-memory offsets.  Returns MSC_OK and fills `out`, or an error.
-int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, const int32_t* agg_kinds, int naggs, RegvmProgram* out) {
+int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, const int32_t* agg_kinds, int naggs, RegvmProgram* out,
+                bool* generic_only) {
+  *generic_only = false;
   if (sd->ncode2 <= 0 || sd->ncode2 > MSC_RV_MAX_CODE) return ctx->fail(MSC_ERR_ARG, "regvm program length out of range");
   memset(out, 0, sizeof(*out));
   int depth = 0;
@@ -403,8 +421,8 @@ int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, cons
   for (int pc = 0; pc < sd->ncode2; ++pc) {
     const uint32_t w = sd->code2[pc];
     const uint32_t id = w & 0xff;
-    uint32_t a[2] = {(w >> 8) & 0xfff, w >> 20};
-    if (id >= MSC_RV__COUNT) return ctx->fail(MSC_ERR_ARG, "regvm: unknown handler");
+    uint32_t a[2] = {(w >> 8) & 0xff, (w >> 16) & 0xff};
+    if (id >= MSC_RV__COUNT || (w >> 24) != 0) return ctx->fail(MSC_ERR_ARG, "regvm: unknown handler");
     const msc_rv_info& info = MSC_RV_INFO[id];
     if (id == MSC_RV_END) {
       if (depth != 0) return ctx->fail(MSC_ERR_ARG, "regvm: unbalanced stack at END");
@@ -416,14 +434,18 @@ int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, cons
     if (info.depth >= 0 && depth != info.depth) return ctx->fail(MSC_ERR_ARG, "regvm: stack depth mismatch");
     depth += info.delta;
     if (depth < 0 || depth > MSC_RV_MAX_DEPTH) return ctx->fail(MSC_ERR_ARG, "regvm: stack depth out of range");
+    // GROUP freezes the rows' groups (masked-out rows go to the trash group), so filters must come first
+    if ((info.flags & MSC_RV_F_FILTER) && grouped) return ctx->fail(MSC_ERR_ARG, "regvm: filter after GROUP");
+    if ((info.flags & MSC_RV_F_GROUP) && grouped) return ctx->fail(MSC_ERR_ARG, "regvm: more than one GROUP");
+    if (info.flags & MSC_RV_F_GENERIC_ONLY) *generic_only = true;
     const signed char kinds[2] = {info.a1, info.a2};
     for (int k = 0; k < 2; ++k) {
       switch (kinds[k]) {
         case MSC_RV_ARG_COL:
           if (static_cast<int>(a[k]) >= sd->nstaged || sd->staged[a[k]].phys != info.phys)
             return ctx->fail(MSC_ERR_ARG, "regvm: column operand has the wrong physical type");
-          a[k] = p.staged[a[k]].smem_off >> 4;
-          if (a[k] > 0xfff) return ctx->fail(MSC_ERR_ARG, "regvm: stage too large");
+          a[k] = p.staged[a[k]].smem_off / MSC_RV_COL_UNIT;
+          if (a[k] > 0xff) return ctx->fail(MSC_ERR_ARG, "regvm: stage too large");
           break;
         case MSC_RV_ARG_CONST:
           if (static_cast<int>(a[k]) >= sd->nconsts) return ctx->fail(MSC_ERR_ARG, "regvm: bad constant");
@@ -435,8 +457,8 @@ int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, cons
         default: a[k] = 0; break;
       }
     }
-    if (id == MSC_RV_GROUP_U8 || id == MSC_RV_GROUP_U16 || id == MSC_RV_GROUP_U32) grouped = true;
-    out->code[pc] = id | (a[0] << 8) | (a[1] << 20);
+    if (info.flags & MSC_RV_F_GROUP) grouped = true;
+    out->code[pc] = id | (a[0] << 8) | (a[1] << 16);
   }
   if (!ended) return ctx->fail(MSC_ERR_ARG, "regvm: program has no END");
   if (!grouped) return ctx->fail(MSC_ERR_ARG, "regvm: program has no GROUP");
@@ -513,72 +535,108 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
 
   if (dense) {
-    // The C++ kernel keeps a hidden per-group row counter and a trash group for filtered rows; the regvm
-    // kernel predicates its updates instead and uses the query's own COUNT accumulator (count_slot2).
+    // All dense kernels but the masked regvm variants fold filtered rows into a trash group.  The C++ kernel keeps
+    // a hidden per-group row counter to tell which groups received rows; the regvm kernels use the query's own
+    // COUNT accumulator (count_slot2) for that.
     const bool use_regvm = sd->ncode2 > 0 && regvm_enabled() && sd->count_slot2 >= 0 && sd->count_slot2 < naggs &&
                            agg_kinds[sd->count_slot2] == MSC_AGG_SUM_I;
     const int ntot = use_regvm ? naggs : naggs + 1;
     const int count_slot = use_regvm ? sd->count_slot2 : naggs;
     kinds[naggs] = MSC_AGG_SUM_I;
     init[naggs] = 0;
-    const size_t acc_bytes = static_cast<size_t>(use_regvm ? ngroups : ngroups + 1) * ntot * NT * sizeof(long long);
-    if (acc_bytes > 96 * 1024) return ctx->fail(MSC_ERR_ARG, "dense aggregate: groups x aggregates too large; use hash mode");
-    const size_t regvm_bytes = (MSC_RV_MAX_CODE + 2) * sizeof(uint32_t) + MSC_VM_MAX_CONSTS * sizeof(long long);
-    LaunchPlan lp;
-    if (use_regvm) MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, acc_bytes + regvm_bytes, &lp, 0));
-    else MSC_TRY(plan_launch(ctx, sd, R, acc_bytes, &lp));
-    lp.p.ngroups = ngroups;
-    lp.p.naggs = ntot;
-    memcpy(lp.p.agg_init, init, sizeof(long long) * ntot);
-    memcpy(lp.p.agg_kind, kinds, sizeof(int) * ntot);
-    RegvmProgram rv;
-    if (use_regvm) MSC_TRY(build_regvm(ctx, sd, lp.p, agg_kinds, naggs, &rv));
-    // global table, initialised with the identities
-    DevTmp table(ctx), d_init(ctx), d_n(ctx), d_ptrs(ctx);
-    MSC_TRY(table.alloc(sizeof(unsigned long long) * ngroups * ntot));
-    MSC_TRY(d_init.alloc(sizeof(long long) * ntot));
-    MSC_TRY(d_n.alloc(sizeof(unsigned long long)));
-    MSC_CUDA(ctx, cudaMemcpyAsync(d_init.p, init, sizeof(long long) * ntot, cudaMemcpyHostToDevice, ctx->stream));
-    dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, d_init.as<long long>());
-    ctx->stats.launches += 1;
-    lp.p.dense_out = table.as<unsigned long long>();
-    if (sd->nrows > 0) {
-      if (use_regvm) MSC_TRY(launch_regvm_dense(ctx, &lp, &rv));
-      else MSC_TRY(launch_scan_r<MODE_DENSE>(ctx, &lp));
+    static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
+    // attempt 0 may use a masked regvm variant (exactly `ngroups` groups, per-group reduction in registers); if a SUM
+    // comes back non-finite that variant cannot be trusted (gen_regvm.py) and attempt 1 reruns on the generic kernel
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      LaunchPlan lp;
+      RegvmProgram rv;
+      int variant = 0;
+      if (use_regvm) {
+        // validate against a provisional plan first: whether the masked variants apply depends on the program
+        bool generic_only = false;
+        MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, 0, &lp, 0));
+        MSC_TRY(build_regvm(ctx, sd, lp.p, agg_kinds, naggs, &rv, &generic_only));
+        if (attempt == 0 && masked_enabled && !generic_only && ngroups <= MSC_RV_MAX_NG) variant = ngroups;
+      }
+      const int smem_groups = variant > 0 ? ngroups : ngroups + 1;  // + the trash group
+      const size_t acc_bytes = static_cast<size_t>(smem_groups) * ntot * NT * sizeof(long long);
+      if (acc_bytes > 96 * 1024) return ctx->fail(MSC_ERR_ARG, "dense aggregate: groups x aggregates too large; use hash mode");
+      const size_t regvm_bytes = (MSC_RV_MAX_CODE + 2) * sizeof(uint32_t) + MSC_VM_MAX_CONSTS * sizeof(long long);
+      if (use_regvm) MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, acc_bytes + regvm_bytes, &lp, 0, variant >= 3 ? 3 : 4));
+      else MSC_TRY(plan_launch(ctx, sd, R, acc_bytes, &lp));
+      lp.p.ngroups = ngroups;
+      lp.p.naggs = ntot;
+      memcpy(lp.p.agg_init, init, sizeof(long long) * ntot);
+      memcpy(lp.p.agg_kind, kinds, sizeof(int) * ntot);
+      // global table, initialised with the identities
+      DevTmp table(ctx), d_init(ctx), d_kinds(ctx), d_n(ctx), d_ptrs(ctx);
+      MSC_TRY(table.alloc(sizeof(unsigned long long) * ngroups * ntot));
+      MSC_TRY(d_init.alloc(sizeof(long long) * ntot));
+      MSC_TRY(d_kinds.alloc(sizeof(int) * ntot));
+      MSC_TRY(d_n.alloc(2 * sizeof(unsigned long long)));
+      MSC_CUDA(ctx, cudaMemcpyAsync(d_init.p, init, sizeof(long long) * ntot, cudaMemcpyHostToDevice, ctx->stream));
+      MSC_CUDA(ctx, cudaMemcpyAsync(d_kinds.p, kinds, sizeof(int) * ntot, cudaMemcpyHostToDevice, ctx->stream));
+      dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, d_init.as<long long>());
+      ctx->stats.launches += 1;
+      lp.p.dense_out = table.as<unsigned long long>();
+      if (sd->nrows > 0) {
+        if (!use_regvm) MSC_TRY(launch_scan_r<MODE_DENSE>(ctx, &lp));
+        else switch (variant) {
+          case 1: MSC_TRY(launch_regvm_dense_ng1(ctx, &lp, &rv)); break;
+          case 2: MSC_TRY(launch_regvm_dense_ng2(ctx, &lp, &rv)); break;
+          case 3: MSC_TRY(launch_regvm_dense_ng3(ctx, &lp, &rv)); break;
+          case 4: MSC_TRY(launch_regvm_dense_ng4(ctx, &lp, &rv)); break;
+          default: MSC_TRY(launch_regvm_dense_ng0(ctx, &lp, &rv)); break;
+        }
+      }
+      // compact present groups into the output relation
+      msc_rel* rel = new_rel(ctx, 0);
+      int rc = add_col(ctx, rel, MSC_P_U32, ngroups);
+      for (int a = 0; rc == MSC_OK && a < naggs; ++a)
+        rc = add_col(ctx, rel, (kinds[a] == MSC_AGG_SUM_F || kinds[a] == MSC_AGG_MIN_F || kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64, ngroups);
+      if (rc != MSC_OK) {
+        msc_rel_free(rel);
+        return rc;
+      }
+      std::vector<unsigned long long*> ptrs;
+      for (int a = 0; a < naggs; ++a) ptrs.push_back(static_cast<unsigned long long*>(rel->cols[1 + a].data));
+      rc = d_ptrs.alloc(sizeof(void*) * (naggs + 1));
+      if (rc == MSC_OK && naggs &&
+          cudaMemcpyAsync(d_ptrs.p, ptrs.data(), sizeof(void*) * naggs, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        rc = ctx->fail(MSC_ERR_CUDA, "cudaMemcpyAsync failed");
+      if (rc != MSC_OK) {
+        msc_rel_free(rel);
+        return rc;
+      }
+      dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, naggs, count_slot, d_kinds.as<int>(),
+                                                      static_cast<uint32_t*>(rel->cols[0].data), d_ptrs.as<unsigned long long*>(),
+                                                      d_n.as<unsigned long long>());
+      ctx->stats.launches += 1;
+      cudaEventRecord(ctx->ev_b, ctx->stream);
+      unsigned long long n[2] = {0, 0};
+      if (cudaMemcpyAsync(n, d_n.p, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        msc_rel_free(rel);
+        return ctx->fail(MSC_ERR_CUDA, "dense aggregate failed");
+      }
+      if (variant > 0 && n[1] != 0) {  // non-finite SUM out of a masked variant: redo it the exact way
+        msc_rel_free(rel);
+        continue;
+      }
+      rel->nrows = n[0];
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+      ctx->stats.last_kernel_ms = ms;
+      if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
+      int drc = msc_check_device_error(ctx);
+      if (drc != MSC_OK) {
+        msc_rel_free(rel);
+        return drc;
+      }
+      *out = rel;
+      return MSC_OK;
     }
-    // compact present groups into the output relation
-    msc_rel* rel = new_rel(ctx, 0);
-    int rc = add_col(ctx, rel, MSC_P_U32, ngroups);
-    for (int a = 0; rc == MSC_OK && a < naggs; ++a)
-      rc = add_col(ctx, rel, (kinds[a] == MSC_AGG_SUM_F || kinds[a] == MSC_AGG_MIN_F || kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64, ngroups);
-    if (rc != MSC_OK) {
-      msc_rel_free(rel);
-      return rc;
-    }
-    std::vector<unsigned long long*> ptrs;
-    for (int a = 0; a < naggs; ++a) ptrs.push_back(static_cast<unsigned long long*>(rel->cols[1 + a].data));
-    MSC_TRY(d_ptrs.alloc(sizeof(void*) * (naggs + 1)));
-    if (naggs) MSC_CUDA(ctx, cudaMemcpyAsync(d_ptrs.p, ptrs.data(), sizeof(void*) * naggs, cudaMemcpyHostToDevice, ctx->stream));
-    dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, naggs, count_slot,
-                                                    static_cast<uint32_t*>(rel->cols[0].data),
-                                                    d_ptrs.as<unsigned long long*>(), d_n.as<unsigned long long>());
-    ctx->stats.launches += 1;
-    MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
-    unsigned long long n = 0;
-    MSC_CUDA(ctx, cudaMemcpyAsync(&n, d_n.p, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
-    MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    rel->nrows = n;
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
-    ctx->stats.last_kernel_ms = ms;
-  if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
-    int drc = msc_check_device_error(ctx);
-    if (drc != MSC_OK) {
-      msc_rel_free(rel);
-      return drc;
-    }
-    *out = rel;
-    return MSC_OK;
+    return ctx->fail(MSC_ERR_ARG, "dense aggregate: unreachable");
   }
 
   // ---- hash mode ----

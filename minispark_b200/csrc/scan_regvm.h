@@ -1,4 +1,4 @@
-// scan_regvm.h -- host-visible declarations of the regvm dense aggregate kernel (scan_regvm.cu).
+// scan_regvm.h -- host-visible declarations of the regvm dense aggregate kernels (scan_regvm_ng<N>.cu).
 #pragma once
 #include "regvm_handlers.h"
 #include "scan_kernel.cuh"
@@ -12,6 +12,11 @@ struct RegvmProgram {
   uint32_t code[MSC_RV_MAX_CODE];
 };
 
-int launch_regvm_dense(msc_ctx* ctx, LaunchPlan* lp, const RegvmProgram* prog);
+// variant 0: any number of groups; variants 1..MSC_RV_MAX_NG: exactly that many groups, SUM_F / COUNT only
+int launch_regvm_dense_ng0(msc_ctx* ctx, LaunchPlan* lp, const RegvmProgram* prog);
+int launch_regvm_dense_ng1(msc_ctx* ctx, LaunchPlan* lp, const RegvmProgram* prog);
+int launch_regvm_dense_ng2(msc_ctx* ctx, LaunchPlan* lp, const RegvmProgram* prog);
+int launch_regvm_dense_ng3(msc_ctx* ctx, LaunchPlan* lp, const RegvmProgram* prog);
+int launch_regvm_dense_ng4(msc_ctx* ctx, LaunchPlan* lp, const RegvmProgram* prog);
 
 }  // namespace mscan

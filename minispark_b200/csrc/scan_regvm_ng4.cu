@@ -1,0 +1,5 @@
+// scan_regvm_ng4.cu -- regvm dense aggregate kernel, variant NG = 4 (see scan_regvm_impl.cuh, gen_regvm.py).
+#define MSC_RV_NG 4
+#define MSC_RV_MIN_CTAS 3
+#define MSC_RV_PTX_INC "regvm_ptx_ng4.inc"
+#include "scan_regvm_impl.cuh"

@@ -900,9 +900,9 @@ def compile_regvm(b: "ProgramBuilder", filters: Sequence[Expr], group: Expr, uni
     def emit(name: str, a1: int = 0, a2: int = 0) -> None:
         if name not in RV:
             raise _RegvmUnsupported(name)
-        if not (0 <= a1 < 4096 and 0 <= a2 < 4096):
+        if not (0 <= a1 < 256 and 0 <= a2 < 256):
             raise _RegvmUnsupported("operand out of range")
-        words.append(RV[name] | (a1 << 8) | (a2 << 20))
+        words.append(RV[name] | (a1 << 8) | (a2 << 16))
         text.append(f"{name} {a1} {a2}")
 
     def column(e: Expr) -> Binding:
