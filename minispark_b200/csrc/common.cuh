@@ -27,6 +27,7 @@ struct msc_ctx {
   cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // bracket the fused scan kernel alone
   int* d_err = nullptr;               // device error word (bit flags written by kernels)
   int* h_err = nullptr;               // pinned mirror
+  unsigned long long* h_scratch = nullptr;  // pinned, 16 words: small result read-backs
   std::string err;
   msc_stats stats{};
   // pinned staging ring for file ingest
@@ -87,6 +88,8 @@ int msc_free(msc_ctx* ctx, void* p, size_t nbytes);
 int msc_alloc_rows(msc_ctx* ctx, uint64_t nrows, size_t width, void** out, size_t* bytes_out);
 // Read + clear the device error word; returns an MSC_ERR_* or MSC_OK.
 int msc_check_device_error(msc_ctx* ctx);
+// MSC_ERR_* (with the message set) for a device error word a kernel already fetched and cleared.
+int msc_device_error_rc(msc_ctx* ctx, int e);
 
 struct msc_col {
   void* data = nullptr;

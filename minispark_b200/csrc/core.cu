@@ -63,17 +63,22 @@ int msc_alloc_rows(msc_ctx* ctx, uint64_t nrows, size_t width, void** out, size_
   return MSC_OK;
 }
 
+int msc_device_error_rc(msc_ctx* ctx, int e) {
+  if (e == 0) return MSC_OK;
+  if (e & MSC_DEVERR_DIV_ZERO) return ctx->fail(MSC_ERR_DIV_ZERO, "division by zero");
+  if (e & MSC_DEVERR_OVERFLOW) return ctx->fail(MSC_ERR_OVERFLOW, "int too big to convert");
+  if (e & MSC_DEVERR_COLLISION) return ctx->fail(MSC_ERR_COLLISION, "string hash collision in dictionary");
+  if (e & MSC_DEVERR_STRLEN) return ctx->fail(MSC_ERR_STRLEN, "string longer than 255 bytes");
+  return ctx->fail(MSC_ERR_ARG, "hash table full");
+}
+
 int msc_check_device_error(msc_ctx* ctx) {
   MSC_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const int e = *ctx->h_err;
   if (e == 0) return MSC_OK;
   MSC_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-  if (e & MSC_DEVERR_DIV_ZERO) return ctx->fail(MSC_ERR_DIV_ZERO, "division by zero");
-  if (e & MSC_DEVERR_OVERFLOW) return ctx->fail(MSC_ERR_OVERFLOW, "int too big to convert");
-  if (e & MSC_DEVERR_COLLISION) return ctx->fail(MSC_ERR_COLLISION, "string hash collision in dictionary");
-  if (e & MSC_DEVERR_STRLEN) return ctx->fail(MSC_ERR_STRLEN, "string longer than 255 bytes");
-  return ctx->fail(MSC_ERR_ARG, "hash table full");
+  return msc_device_error_rc(ctx, e);
 }
 
 extern "C" int msc_abi_version(void) { return MSC_ABI_VERSION; }
@@ -116,6 +121,8 @@ extern "C" int msc_create(int device, msc_ctx** out) {
   if (cudaMalloc(&ctx->d_err, sizeof(int)) != cudaSuccess) return bail("cudaMalloc");
   if (cudaMemset(ctx->d_err, 0, sizeof(int)) != cudaSuccess) return bail("cudaMemset");
   if (cudaHostAlloc(&ctx->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
+  if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_scratch), 16 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
+    return bail("cudaHostAlloc");
   *out = ctx;
   return MSC_OK;
 }
@@ -131,6 +138,7 @@ extern "C" void msc_destroy(msc_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->d_err) cudaFree(ctx->d_err);
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
+  if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_s0) cudaEventDestroy(ctx->ev_s0);

@@ -27,8 +27,9 @@ Variants (one PTX file each, same handler ids):
   NG 1..4  exactly NG groups.  prof_r1g showed the generic form bound by those updates (65 % of the
            shared-memory pipe, short-scoreboard stalls on the serial ld -> add -> st chains), so here GROUP
            builds one-hot f64 masks m<r>_<g> (1.0 when row r is valid and in group g) and the SUM / COUNT
-           handlers first reduce the lane's 8 rows per group in registers -- fma(v, 1.0, s) == s + v and
-           fma(v, 0.0, s) == s exactly for finite v -- then update each group's accumulator once: NG
+           handlers first reduce the lane's 8 rows per group in registers (two fma chains of 4 rows each per
+           group) -- fma(v, 1.0, s) == s + v and fma(v, 0.0, s) == s exactly for finite v -- then update each
+           group's accumulator once: NG
            independent updates instead of 8 dependent ones, and no trash group.  A non-finite input would
            leak into the other groups through v * 0.0 = NaN; it always leaves a non-finite SUM behind, so
            the host detects it and reruns the scan on the generic kernel (scan.cu).  MIN / MAX / integer
@@ -182,12 +183,16 @@ def build(NG: int) -> list[dict]:
         """Masked variant: per-group sums of the lane's 8 rows in registers (row order, one chain per group), then one
         update per group; the NG accumulator addresses are distinct, so loads, adds and stores are batched."""
         body = []
-        if kind == "SUMF":
-            for g in range(NG):
-                body.append(f"mul.f64 p{g}, {val.format(r=0)}, m0_{g};")
-            for r in range(1, R):
+        if kind == "SUMF":  # two chains per group (rows 0-3, rows 4-7): 2 * NG independent fma chains of depth 4
+            for r0, acc in ((0, "p"), (HALF, "ph")):
                 for g in range(NG):
-                    body.append(f"fma.rn.f64 p{g}, {val.format(r=r)}, m{r}_{g}, p{g};")
+                    body.append(f"mul.f64 {acc}{g}, {val.format(r=r0)}, m{r0}_{g};")
+            for j in range(1, HALF):
+                for r0, acc in ((0, "p"), (HALF, "ph")):
+                    for g in range(NG):
+                        body.append(f"fma.rn.f64 {acc}{g}, {val.format(r=r0 + j)}, m{r0 + j}_{g}, {acc}{g};")
+            for g in range(NG):
+                body.append(f"add.f64 p{g}, p{g}, ph{g};")
         else:  # COUNT: the masks themselves, summed (exact: at most 8)
             for g in range(NG):
                 body.append(f"add.f64 p{g}, m0_{g}, m1_{g};")
@@ -269,7 +274,7 @@ def ptx(NG: int) -> str:
     if NG > 0:
         for r in ROWS:
             regs.append(".reg .f64 " + ", ".join(f"m{r}_{g}" for g in range(NG)) + ";")
-        regs += [".reg .f64 " + ", ".join(f"p{g}, q{g}f" for g in range(NG)) + ";",
+        regs += [".reg .f64 " + ", ".join(f"p{g}, ph{g}, q{g}f" for g in range(NG)) + ";",
                  ".reg .b64 " + ", ".join(f"n{g}, q{g}i" for g in range(NG)) + ";",
                  ".reg .b32 " + ", ".join(f"ag{g}" for g in range(NG)) + ";"]
     else:

@@ -342,8 +342,8 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
         const uint8_t* body = lens + bi.rows;
         rc = msc_exclusive_scan_u8_u64(ctx, lens, offs[sset].as<uint64_t>(), bi.rows);
         if (rc == MSC_OK)
-          rc = msc_dict_encode_u8(ctx, dicts[c], offs[sset].as<uint64_t>(), lens, body, bi.rows, bi.col_bytes[fc] - bi.rows, 1,
-                                  static_cast<uint32_t*>(col.data) + row_off);
+          rc = msc_dict_encode_u8_async(ctx, dicts[c], offs[sset].as<uint64_t>(), lens, body, bi.rows, bi.col_bytes[fc] - bi.rows,
+                                        static_cast<uint32_t*>(col.data) + row_off);
       }
       cudaEventRecord(ev_done[sset], ctx->stream);
     }
@@ -359,6 +359,8 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
     if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
     if (ev_done[i]) cudaEventDestroy(ev_done[i]);
   }
+  for (int c = 0; c < ncols && rc == MSC_OK; ++c)
+    if (t->types[cols[c]] == MSC_T_STRING) rc = msc_dict_settle(ctx, dicts[c]);  // host mirrors + the device error word
   if (rc != MSC_OK) return fail(rc);
   mark("copies + decode complete");
 

@@ -21,29 +21,37 @@ __global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, uin
     p[i] = v;
 }
 
-__global__ void dense_init_kernel(unsigned long long* out, int ngroups, int naggs, const long long* init) {
+// identities, kinds and output columns of a dense aggregate travel as kernel parameters (no staging copies)
+struct DenseMeta {
+  long long init[MSC_VM_MAX_AGGS + 1];
+  int kinds[MSC_VM_MAX_AGGS + 1];
+  unsigned long long* out_acc[MSC_VM_MAX_AGGS];
+};
+
+__global__ void dense_init_kernel(unsigned long long* out, int ngroups, int naggs, const __grid_constant__ DenseMeta m) {
   const int n = ngroups * naggs;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = static_cast<unsigned long long>(init[i % naggs]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = static_cast<unsigned long long>(m.init[i % naggs]);
 }
 
-// compact the dense table: one output row per group whose hidden row counter is > 0
-// table[g][stride]: export the first `nexport` accumulators of every group whose row counter (slot
-// `count_slot`) is non-zero
+// compact the dense table: one output row per group whose row counter (slot `count_slot`) is non-zero, carrying
+// the first `nexport` accumulators; out_n[0] = groups, out_n[1] = 1 when a SUM_F came out non-finite, out_n[2] =
+// the device error word (fetched and cleared)
 __global__ void dense_finalize_kernel(const unsigned long long* table, int ngroups, int stride, int nexport, int count_slot,
-                                      const int* kinds, uint32_t* out_key, unsigned long long* const* out_acc,
-                                      unsigned long long* out_n) {
+                                      const __grid_constant__ DenseMeta m, uint32_t* out_key, unsigned long long* out_n, int* err) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   unsigned long long n = 0, nonfinite = 0;
   for (int g = 0; g < ngroups; ++g) {
     for (int a = 0; a < nexport; ++a)
-      if (kinds[a] == MSC_AGG_SUM_F && !isfinite(__longlong_as_double(static_cast<long long>(table[g * stride + a])))) nonfinite = 1;
+      if (m.kinds[a] == MSC_AGG_SUM_F && !isfinite(__longlong_as_double(static_cast<long long>(table[g * stride + a])))) nonfinite = 1;
     if (table[g * stride + count_slot] == 0) continue;
     out_key[n] = g;
-    for (int a = 0; a < nexport; ++a) out_acc[a][n] = table[g * stride + a];
+    for (int a = 0; a < nexport; ++a) m.out_acc[a][n] = table[g * stride + a];
     ++n;
   }
   out_n[0] = n;
   out_n[1] = nonfinite;  // a masked regvm variant must not be trusted then (v * 0.0 = NaN leaks across groups)
+  out_n[2] = static_cast<unsigned long long>(*err);  // the device error word rides along with the group count
+  *err = 0;
 }
 
 constexpr int HTILE = 1024;  // slots per block in the hash-table compaction
@@ -501,6 +509,35 @@ int add_col(msc_ctx* ctx, msc_rel* rel, int phys, uint64_t nrows) {
   return MSC_OK;
 }
 
+// All columns of a result relation.  Small results (a GROUP BY's handful of rows) share one allocation and one
+// memset: per-column calls cost a few microseconds each on the stream, which adds up to more than the scan of a
+// small table.  The first column owns the block.
+int add_cols(msc_ctx* ctx, msc_rel* rel, const int* phys, int ncols, uint64_t nrows) {
+  const uint64_t padded = msc_round_up(nrows ? nrows : 1, MSC_ROW_PAD);
+  if (padded > MSC_ROW_PAD || ncols == 0) {
+    for (int i = 0; i < ncols; ++i) MSC_TRY(add_col(ctx, rel, phys[i], nrows));
+    return MSC_OK;
+  }
+  size_t total = 0;
+  std::vector<size_t> off(ncols);
+  for (int i = 0; i < ncols; ++i) {
+    off[i] = total;
+    total += msc_round_up(padded * msc_phys_width(phys[i]) + 256, 256);
+  }
+  void* base = nullptr;
+  MSC_TRY(msc_alloc(ctx, total, &base));
+  MSC_CUDA(ctx, cudaMemsetAsync(base, 0, total, ctx->stream));
+  for (int i = 0; i < ncols; ++i) {
+    msc_col c;
+    c.phys = phys[i];
+    c.data = static_cast<char*>(base) + off[i];
+    c.bytes = i == 0 ? total : 0;
+    c.owned = i == 0;
+    rel->cols.push_back(c);
+  }
+  return MSC_OK;
+}
+
 }  // namespace
 
 int msc_exclusive_scan_u8_u64(msc_ctx* ctx, const uint8_t* in, uint64_t* out, uint64_t n) {
@@ -569,14 +606,14 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
       memcpy(lp.p.agg_init, init, sizeof(long long) * ntot);
       memcpy(lp.p.agg_kind, kinds, sizeof(int) * ntot);
       // global table, initialised with the identities
-      DevTmp table(ctx), d_init(ctx), d_kinds(ctx), d_n(ctx), d_ptrs(ctx);
+      DevTmp table(ctx), d_n(ctx);
       MSC_TRY(table.alloc(sizeof(unsigned long long) * ngroups * ntot));
-      MSC_TRY(d_init.alloc(sizeof(long long) * ntot));
-      MSC_TRY(d_kinds.alloc(sizeof(int) * ntot));
-      MSC_TRY(d_n.alloc(2 * sizeof(unsigned long long)));
-      MSC_CUDA(ctx, cudaMemcpyAsync(d_init.p, init, sizeof(long long) * ntot, cudaMemcpyHostToDevice, ctx->stream));
-      MSC_CUDA(ctx, cudaMemcpyAsync(d_kinds.p, kinds, sizeof(int) * ntot, cudaMemcpyHostToDevice, ctx->stream));
-      dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, d_init.as<long long>());
+      MSC_TRY(d_n.alloc(3 * sizeof(unsigned long long)));
+      DenseMeta meta;
+      memset(&meta, 0, sizeof(meta));
+      memcpy(meta.init, init, sizeof(long long) * ntot);
+      memcpy(meta.kinds, kinds, sizeof(int) * ntot);
+      dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, meta);
       ctx->stats.launches += 1;
       lp.p.dense_out = table.as<unsigned long long>();
       if (sd->nrows > 0) {
@@ -591,33 +628,30 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
       }
       // compact present groups into the output relation
       msc_rel* rel = new_rel(ctx, 0);
-      int rc = add_col(ctx, rel, MSC_P_U32, ngroups);
-      for (int a = 0; rc == MSC_OK && a < naggs; ++a)
-        rc = add_col(ctx, rel, (kinds[a] == MSC_AGG_SUM_F || kinds[a] == MSC_AGG_MIN_F || kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64, ngroups);
+      int physes[MSC_VM_MAX_AGGS + 1];
+      physes[0] = MSC_P_U32;
+      for (int a = 0; a < naggs; ++a)
+        physes[1 + a] = (kinds[a] == MSC_AGG_SUM_F || kinds[a] == MSC_AGG_MIN_F || kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64;
+      int rc = add_cols(ctx, rel, physes, 1 + naggs, ngroups);
       if (rc != MSC_OK) {
         msc_rel_free(rel);
         return rc;
       }
-      std::vector<unsigned long long*> ptrs;
-      for (int a = 0; a < naggs; ++a) ptrs.push_back(static_cast<unsigned long long*>(rel->cols[1 + a].data));
-      rc = d_ptrs.alloc(sizeof(void*) * (naggs + 1));
-      if (rc == MSC_OK && naggs &&
-          cudaMemcpyAsync(d_ptrs.p, ptrs.data(), sizeof(void*) * naggs, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
-        rc = ctx->fail(MSC_ERR_CUDA, "cudaMemcpyAsync failed");
-      if (rc != MSC_OK) {
-        msc_rel_free(rel);
-        return rc;
-      }
-      dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, naggs, count_slot, d_kinds.as<int>(),
-                                                      static_cast<uint32_t*>(rel->cols[0].data), d_ptrs.as<unsigned long long*>(),
-                                                      d_n.as<unsigned long long>());
+      for (int a = 0; a < naggs; ++a) meta.out_acc[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
+      dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, naggs, count_slot, meta,
+                                                      static_cast<uint32_t*>(rel->cols[0].data), d_n.as<unsigned long long>(), ctx->d_err);
       ctx->stats.launches += 1;
       cudaEventRecord(ctx->ev_b, ctx->stream);
-      unsigned long long n[2] = {0, 0};
-      if (cudaMemcpyAsync(n, d_n.p, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      unsigned long long* n = ctx->h_scratch;  // pinned: a plain stack buffer would make the copy synchronous twice over
+      if (cudaMemcpyAsync(n, d_n.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
           cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         msc_rel_free(rel);
         return ctx->fail(MSC_ERR_CUDA, "dense aggregate failed");
+      }
+      const int drc = msc_device_error_rc(ctx, static_cast<int>(n[2]));
+      if (drc != MSC_OK) {
+        msc_rel_free(rel);
+        return drc;
       }
       if (variant > 0 && n[1] != 0) {  // non-finite SUM out of a masked variant: redo it the exact way
         msc_rel_free(rel);
@@ -628,11 +662,6 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
       cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
       ctx->stats.last_kernel_ms = ms;
       if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
-      int drc = msc_check_device_error(ctx);
-      if (drc != MSC_OK) {
-        msc_rel_free(rel);
-        return drc;
-      }
       *out = rel;
       return MSC_OK;
     }
@@ -737,12 +766,14 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
     lp.p.tile_offsets = offsets.as<uint64_t>();
   }
   msc_rel* rel = new_rel(ctx, nout_rows);
-  for (int i = 0; i < nout; ++i) {
-    int rc = add_col(ctx, rel, out_phys[i], nout_rows);
+  {
+    const int rc = add_cols(ctx, rel, out_phys, nout, nout_rows);
     if (rc != MSC_OK) {
       msc_rel_free(rel);
       return rc;
     }
+  }
+  for (int i = 0; i < nout; ++i) {
     lp.p.out[i] = rel->cols[i].data;
     lp.p.out_phys[i] = out_phys[i];
   }

@@ -52,7 +52,12 @@ __global__ void dict_probe_kernel(const uint64_t* starts, const TLen* lens, cons
     pos = (pos + 1) & mask;
   }
   if (insert && slot == NO_CODE) atomicOr(err, MSC_DEVERR_TABLE_FULL);
-  if (insert && slot != NO_CODE && hcode[slot] < 0) atomicMin(hrep + slot, static_cast<uint32_t>(i));
+  if (insert && slot != NO_CODE && hcode[slot] < 0) {
+    // one atomic per distinct slot and warp (the lowest lane holds the smallest row): a low-cardinality column
+    // would otherwise serialise millions of atomics on a handful of addresses in its first batch
+    const unsigned peers = __match_any_sync(__activemask(), slot);
+    if ((__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31)) atomicMin(hrep + slot, static_cast<uint32_t>(i));
+  }
   slot_out[i] = slot;
 }
 
@@ -216,16 +221,14 @@ __global__ void pack_entries_kernel(const uint64_t* ent_start, const uint32_t* e
 
 inline unsigned grid_for(uint64_t n, int block) { return static_cast<unsigned>((n + block - 1) / block); }
 
-// grow entry arrays / heap / hash table so that `add_entries` new strings totalling `add_bytes` fit
-int dict_reserve(msc_ctx* ctx, msc_dict* d, uint64_t add_entries, uint64_t add_bytes) {
-  const uint64_t need_ent = d->n + add_entries;
-  if (need_ent > d->ent_cap) {
-    uint64_t cap = d->ent_cap ? d->ent_cap : 1024;
-    while (cap < need_ent) cap *= 2;
+// Re-home the dictionary into arrays of the given capacities (entries / heap bytes / hash slots, the last a power
+// of two); unchanged capacities keep their arrays.  Needs exact host mirrors (no batches in flight).
+int dict_resize(msc_ctx* ctx, msc_dict* d, uint64_t ent_cap, uint64_t heap_cap, uint64_t hcap) {
+  if (ent_cap != d->ent_cap) {
     uint64_t* ns = nullptr;
     uint32_t* nl = nullptr;
-    MSC_TRY(msc_alloc(ctx, cap * sizeof(uint64_t), reinterpret_cast<void**>(&ns)));
-    MSC_TRY(msc_alloc(ctx, cap * sizeof(uint32_t), reinterpret_cast<void**>(&nl)));
+    MSC_TRY(msc_alloc(ctx, ent_cap * sizeof(uint64_t), reinterpret_cast<void**>(&ns)));
+    MSC_TRY(msc_alloc(ctx, ent_cap * sizeof(uint32_t), reinterpret_cast<void**>(&nl)));
     if (d->n) {
       MSC_CUDA(ctx, cudaMemcpyAsync(ns, d->ent_start, d->n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
       MSC_CUDA(ctx, cudaMemcpyAsync(nl, d->ent_len, d->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -234,37 +237,32 @@ int dict_reserve(msc_ctx* ctx, msc_dict* d, uint64_t add_entries, uint64_t add_b
     msc_free(ctx, d->ent_len, d->ent_cap * sizeof(uint32_t));
     d->ent_start = ns;
     d->ent_len = nl;
-    d->ent_cap = cap;
+    d->ent_cap = ent_cap;
   }
-  const uint64_t need_bytes = d->nbytes + add_bytes;
-  if (need_bytes > d->heap_cap) {
-    uint64_t cap = d->heap_cap ? d->heap_cap : 4096;
-    while (cap < need_bytes) cap *= 2;
+  if (heap_cap != d->heap_cap) {
     uint8_t* nh = nullptr;
-    MSC_TRY(msc_alloc(ctx, cap, reinterpret_cast<void**>(&nh)));
+    MSC_TRY(msc_alloc(ctx, heap_cap, reinterpret_cast<void**>(&nh)));
     if (d->nbytes) MSC_CUDA(ctx, cudaMemcpyAsync(nh, d->heap, d->nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
     msc_free(ctx, d->heap, d->heap_cap);
     d->heap = nh;
-    d->heap_cap = cap;
+    d->heap_cap = heap_cap;
   }
-  if (need_ent * 2 > d->hcap) {
-    uint64_t cap = d->hcap ? d->hcap : 1024;
-    while (cap < need_ent * 2) cap *= 2;
-    if (cap > (1ULL << 31)) return ctx->fail(MSC_ERR_ARG, "dictionary too large");
+  if (hcap != d->hcap) {
+    if (hcap > (1ULL << 31)) return ctx->fail(MSC_ERR_ARG, "dictionary too large");
     msc_free(ctx, d->hkeys, d->hcap * sizeof(uint64_t));
     msc_free(ctx, d->hcode, d->hcap * sizeof(int32_t));
     msc_free(ctx, d->hrep, d->hcap * sizeof(uint32_t));
-    MSC_TRY(msc_alloc(ctx, cap * sizeof(uint64_t), reinterpret_cast<void**>(&d->hkeys)));
-    MSC_TRY(msc_alloc(ctx, cap * sizeof(int32_t), reinterpret_cast<void**>(&d->hcode)));
-    MSC_TRY(msc_alloc(ctx, cap * sizeof(uint32_t), reinterpret_cast<void**>(&d->hrep)));
-    d->hcap = cap;
-    MSC_CUDA(ctx, cudaMemsetAsync(d->hkeys, 0, cap * sizeof(uint64_t), ctx->stream));
-    MSC_CUDA(ctx, cudaMemsetAsync(d->hrep, 0xFF, cap * sizeof(uint32_t), ctx->stream));
-    fill_i32_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d->hcode, -1, cap);
+    MSC_TRY(msc_alloc(ctx, hcap * sizeof(uint64_t), reinterpret_cast<void**>(&d->hkeys)));
+    MSC_TRY(msc_alloc(ctx, hcap * sizeof(int32_t), reinterpret_cast<void**>(&d->hcode)));
+    MSC_TRY(msc_alloc(ctx, hcap * sizeof(uint32_t), reinterpret_cast<void**>(&d->hrep)));
+    d->hcap = hcap;
+    MSC_CUDA(ctx, cudaMemsetAsync(d->hkeys, 0, hcap * sizeof(uint64_t), ctx->stream));
+    MSC_CUDA(ctx, cudaMemsetAsync(d->hrep, 0xFF, hcap * sizeof(uint32_t), ctx->stream));
+    fill_i32_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d->hcode, -1, hcap);
     ctx->stats.launches += 1;
     if (d->n) {
       dict_rehash_kernel<<<grid_for(d->n, 256), 256, 0, ctx->stream>>>(
-          d->ent_start, d->ent_len, d->heap, d->n, reinterpret_cast<unsigned long long*>(d->hkeys), d->hcode, cap, d->seed);
+          d->ent_start, d->ent_len, d->heap, d->n, reinterpret_cast<unsigned long long*>(d->hkeys), d->hcode, hcap, d->seed);
       ctx->stats.launches += 1;
     }
     MSC_CUDA(ctx, cudaGetLastError());
@@ -272,16 +270,63 @@ int dict_reserve(msc_ctx* ctx, msc_dict* d, uint64_t add_entries, uint64_t add_b
   return MSC_OK;
 }
 
+uint64_t pow2_at_least(uint64_t v, uint64_t floor_) {
+  uint64_t c = floor_;
+  while (c < v) c *= 2;
+  return c;
+}
+
+// grow entry arrays / heap / hash table so that `add_entries` new strings totalling `add_bytes` fit
+int dict_reserve(msc_ctx* ctx, msc_dict* d, uint64_t add_entries, uint64_t add_bytes) {
+  const uint64_t need_ent = d->n + add_entries, need_bytes = d->nbytes + add_bytes;
+  const uint64_t ent_cap = need_ent > d->ent_cap ? pow2_at_least(need_ent, d->ent_cap ? d->ent_cap : 1024) : d->ent_cap;
+  const uint64_t heap_cap = need_bytes > d->heap_cap ? pow2_at_least(need_bytes, d->heap_cap ? d->heap_cap : 4096) : d->heap_cap;
+  const uint64_t hcap = need_ent * 2 > d->hcap ? pow2_at_least(need_ent * 2, d->hcap ? d->hcap : 1024) : d->hcap;
+  return dict_resize(ctx, d, ent_cap, heap_cap, hcap);
+}
+
+// fold completed counter snapshots into the host mirrors; returns the rows / bytes still unaccounted for
+void dict_poll(msc_dict* d, bool wait, uint64_t* pend_rows, uint64_t* pend_bytes) {
+  while (d->ring_count > 0) {
+    msc_dict::Pending& e = d->ring[d->ring_head];
+    if (wait) cudaEventSynchronize(e.ev);
+    else if (cudaEventQuery(e.ev) != cudaSuccess) break;
+    d->n = static_cast<uint32_t>(e.host[0]);
+    d->nbytes = e.host[1];
+    d->ring_head = (d->ring_head + 1) % msc_dict::kPending;
+    --d->ring_count;
+  }
+  uint64_t r = 0, b = 0;
+  for (int i = 0; i < d->ring_count; ++i) {
+    const msc_dict::Pending& e = d->ring[(d->ring_head + i) % msc_dict::kPending];
+    r += e.rows;
+    b += e.bytes;
+  }
+  *pend_rows = r;
+  *pend_bytes = b;
+}
+
 template <class TLen>
 int dict_encode_impl(msc_ctx* ctx, msc_dict* d, const uint64_t* starts, const TLen* lens, const uint8_t* bytes, uint64_t n,
-                     uint64_t batch_bytes, int insert, uint32_t* codes_out) {
+                     uint64_t batch_bytes, int insert, uint32_t* codes_out, bool async) {
   if (n == 0) return MSC_OK;
   if (n > 0xFFFFFFF0ULL) return ctx->fail(MSC_ERR_ARG, "dictionary batch too large");
-  if (!insert && d->n == 0) {  // nothing can match an empty dictionary
+  uint64_t pend_rows = 0, pend_bytes = 0;
+  dict_poll(d, !async, &pend_rows, &pend_bytes);
+  if (!insert && d->n == 0 && pend_rows == 0) {  // nothing can match an empty dictionary
     MSC_CUDA(ctx, cudaMemsetAsync(codes_out, 0xFF, n * sizeof(uint32_t), ctx->stream));
     return MSC_OK;
   }
-  MSC_TRY(dict_reserve(ctx, d, insert ? n : 0, insert ? batch_bytes : 0));
+  if (insert) {
+    // capacity must cover what the in-flight batches may still add; growing needs exact mirrors, so settle first
+    const bool fits = d->n + pend_rows + n <= d->ent_cap && d->nbytes + pend_bytes + batch_bytes <= d->heap_cap &&
+                      (d->n + pend_rows + n) * 2 <= d->hcap;
+    if (!fits) {
+      dict_poll(d, true, &pend_rows, &pend_bytes);
+      // pipelined loads reserve for two further batches so that steady state never has to settle
+      MSC_TRY(dict_reserve(ctx, d, async ? 3 * n : n, async ? 3 * batch_bytes : batch_bytes));
+    }
+  }
   DevTmp slots(ctx);
   MSC_TRY(slots.alloc(n * sizeof(uint32_t)));
   const unsigned grid = grid_for(n, 256);
@@ -296,12 +341,20 @@ int dict_encode_impl(msc_ctx* ctx, msc_dict* d, const uint64_t* starts, const TL
   ctx->stats.launches += insert ? 3 : 2;
   MSC_CUDA(ctx, cudaGetLastError());
   if (insert) {
-    unsigned long long counters[2];
-    MSC_CUDA(ctx, cudaMemcpyAsync(counters, d->d_counters, sizeof(counters), cudaMemcpyDeviceToHost, ctx->stream));
-    MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    d->n = static_cast<uint32_t>(counters[0]);
-    d->nbytes = counters[1];
+    if (d->ring_count == msc_dict::kPending) dict_poll(d, true, &pend_rows, &pend_bytes);
+    msc_dict::Pending& e = d->ring[(d->ring_head + d->ring_count) % msc_dict::kPending];
+    if (!e.ev) {
+      MSC_CUDA(ctx, cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming));
+      MSC_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&e.host), 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    }
+    e.rows = n;
+    e.bytes = batch_bytes;
+    MSC_CUDA(ctx, cudaMemcpyAsync(e.host, d->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    MSC_CUDA(ctx, cudaEventRecord(e.ev, ctx->stream));
+    ++d->ring_count;
   }
+  if (async) return MSC_OK;
+  dict_poll(d, true, &pend_rows, &pend_bytes);
   return msc_check_device_error(ctx);
 }
 
@@ -309,11 +362,25 @@ int dict_encode_impl(msc_ctx* ctx, msc_dict* d, const uint64_t* starts, const TL
 
 int msc_dict_encode_u8(msc_ctx* ctx, msc_dict* d, const uint64_t* starts, const uint8_t* lens, const uint8_t* bytes, uint64_t n,
                        uint64_t batch_bytes, int insert, uint32_t* codes_out) {
-  return dict_encode_impl<uint8_t>(ctx, d, starts, lens, bytes, n, batch_bytes, insert, codes_out);
+  return dict_encode_impl<uint8_t>(ctx, d, starts, lens, bytes, n, batch_bytes, insert, codes_out, false);
+}
+int msc_dict_encode_u8_async(msc_ctx* ctx, msc_dict* d, const uint64_t* starts, const uint8_t* lens, const uint8_t* bytes, uint64_t n,
+                             uint64_t batch_bytes, uint32_t* codes_out) {
+  return dict_encode_impl<uint8_t>(ctx, d, starts, lens, bytes, n, batch_bytes, 1, codes_out, true);
+}
+int msc_dict_settle(msc_ctx* ctx, msc_dict* d) {
+  uint64_t r = 0, b = 0;
+  dict_poll(d, true, &r, &b);
+  MSC_TRY(msc_check_device_error(ctx));
+  // pipelined loads reserve for whole batches of distinct strings; give back what a low-cardinality column never used
+  const uint64_t ent_cap = pow2_at_least(d->n, 1024), heap_cap = pow2_at_least(d->nbytes, 4096);
+  const uint64_t hcap = pow2_at_least(static_cast<uint64_t>(d->n) * 2, 1024);
+  if (d->ent_cap > 4 * ent_cap || d->hcap > 4 * hcap || d->heap_cap > 4 * heap_cap) MSC_TRY(dict_resize(ctx, d, ent_cap, heap_cap, hcap));
+  return MSC_OK;
 }
 int msc_dict_encode_u32(msc_ctx* ctx, msc_dict* d, const uint64_t* starts, const uint32_t* lens, const uint8_t* bytes, uint64_t n,
                         uint64_t batch_bytes, int insert, uint32_t* codes_out) {
-  return dict_encode_impl<uint32_t>(ctx, d, starts, lens, bytes, n, batch_bytes, insert, codes_out);
+  return dict_encode_impl<uint32_t>(ctx, d, starts, lens, bytes, n, batch_bytes, insert, codes_out, false);
 }
 
 extern "C" int msc_dict_create(msc_ctx* ctx, msc_dict** out) {
@@ -340,6 +407,13 @@ extern "C" void msc_dict_free(msc_dict* d) {
   msc_free(ctx, d->hcode, d->hcap * sizeof(int32_t));
   msc_free(ctx, d->hrep, d->hcap * sizeof(uint32_t));
   msc_free(ctx, d->d_counters, 2 * sizeof(unsigned long long));
+  for (auto& e : d->ring) {
+    if (e.ev) {
+      cudaEventSynchronize(e.ev);
+      cudaEventDestroy(e.ev);
+    }
+    if (e.host) cudaFreeHost(e.host);
+  }
   delete d;
 }
 
