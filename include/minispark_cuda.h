@@ -272,6 +272,11 @@ MSC_API int msc_dict_like(msc_ctx* ctx, msc_dict* d, const char* pattern, size_t
 MSC_API int msc_dict_translate(msc_ctx* ctx, msc_dict* from, msc_dict* to, int32_t insert, void** lut_dev);
 /* copy the dictionary to the host: lens[nentries] (u32) and concatenated bytes */
 MSC_API int msc_dict_export(msc_ctx* ctx, msc_dict* d, uint32_t* lens, uint8_t* bytes);
+/* fill an EMPTY dictionary from the host in one go: entry i (code i) is the next lens[i] bytes of `bytes`; the
+ * entries must be distinct.  Codes follow the given order, so ranks that load the same list agree on every code
+ * (multi-GPU joins and merges unify string columns this way; the reference compares the strings themselves,
+ * tasks.py:201-240). */
+MSC_API int msc_dict_load(msc_ctx* ctx, msc_dict* d, const uint32_t* lens, const uint8_t* bytes, uint32_t nentries);
 /* STRING '+' STRING (sql.py:331-333, zig concatStrings utils.zig:118-131): per-row concatenation
  * of `nparts` parts; part i is a code column (codes[i] != NULL, with its dictionary) or a literal.
  * Result: new U32 code column (1-column relation) over dictionary `out_dict`. */

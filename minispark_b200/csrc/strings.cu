@@ -494,6 +494,43 @@ extern "C" int msc_dict_translate(msc_ctx* ctx, msc_dict* from, msc_dict* to, in
   return MSC_OK;
 }
 
+extern "C" int msc_dict_load(msc_ctx* ctx, msc_dict* d, const uint32_t* lens, const uint8_t* bytes, uint32_t nentries) {
+  if (!ctx || !d || (nentries && (!lens || !bytes))) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  MSC_TRY(msc_dict_settle(ctx, d));
+  if (d->n != 0) return ctx->fail(MSC_ERR_ARG, "msc_dict_load needs an empty dictionary");
+  if (nentries == 0) return MSC_OK;
+  std::vector<uint64_t> starts(nentries);
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < nentries; ++i) {
+    if (lens[i] > 255) return ctx->fail(MSC_ERR_STRLEN, "string longer than 255 bytes");
+    starts[i] = total;
+    total += lens[i];
+  }
+  // arrays first (n == 0: nothing to carry over or rehash), then the entries, then one rehash that assigns code i to entry i
+  MSC_TRY(dict_resize(ctx, d, pow2_at_least(nentries, 1024), pow2_at_least(total, 4096), d->hcap));
+  MSC_CUDA(ctx, cudaMemcpyAsync(d->ent_start, starts.data(), nentries * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  MSC_CUDA(ctx, cudaMemcpyAsync(d->ent_len, lens, nentries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (total) MSC_CUDA(ctx, cudaMemcpyAsync(d->heap, bytes, total, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned long long counters[2] = {nentries, total};
+  MSC_CUDA(ctx, cudaMemcpyAsync(d->d_counters, counters, sizeof(counters), cudaMemcpyHostToDevice, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffers above may go away after return
+  d->n = nentries;
+  d->nbytes = total;
+  const uint64_t hcap = pow2_at_least(static_cast<uint64_t>(nentries) * 2, 1024);
+  if (hcap == d->hcap) {  // force the rebuild: dict_resize only rehashes when the slot count changes
+    msc_free(ctx, d->hkeys, d->hcap * sizeof(uint64_t));
+    msc_free(ctx, d->hcode, d->hcap * sizeof(int32_t));
+    msc_free(ctx, d->hrep, d->hcap * sizeof(uint32_t));
+    d->hkeys = nullptr;
+    d->hcode = nullptr;
+    d->hrep = nullptr;
+    d->hcap = 0;
+  }
+  MSC_TRY(dict_resize(ctx, d, d->ent_cap, d->heap_cap, hcap));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MSC_OK;
+}
+
 extern "C" int msc_dict_export(msc_ctx* ctx, msc_dict* d, uint32_t* lens, uint8_t* bytes) {
   if (!ctx || !d) return MSC_ERR_ARG;
   if (d->n == 0) return MSC_OK;

@@ -141,6 +141,16 @@ class DictHandle:
             pos += ln
         return out
 
+    def load(self, entries: list[str]) -> "DictHandle":
+        """Fill this (empty) dictionary with ``entries``; entry i gets code i on every rank that loads the same list."""
+        import numpy as np  # noqa: PLC0415
+
+        raws = [t.encode("utf-8") for t in entries]
+        lens = np.asarray([len(r) for r in raws], dtype=np.uint32)
+        blob = np.frombuffer(b"".join(raws) or b"\0", dtype=np.uint8)
+        self.ctx.call("msc_dict_load", C.c_void_p(self.handle), lens.ctypes.data_as(C.c_void_p), blob.ctypes.data_as(C.c_void_p), len(raws))
+        return self
+
     def free(self) -> None:
         if self.handle:
             for ptr in self._luts.values():
@@ -717,13 +727,24 @@ class CudaExecutionEngine(ExecutionEngine):
             sel = L.fuse_selects(L.LSelect(schema, node, [], [*outs, key_out]))
             return self._run_select(sel, targets)
 
+        # A STR key is joined on its dictionary code (key_out above), so both sides must be coded in ONE dictionary:
+        # the left key column's -- unified over all ranks first when the tables are sharded.
         lrel = side(join.left, left_needed, join.left_key, None)
+        key_dict = lrel.cols[-1].dict if join.left_key.type == L.STR else None
+        if key_dict is not None and self.comm.world > 1:
+            key_dict = self._unified_dictionary(key_dict)
+            lrel = side(join.left, left_needed, L.ETranslate(L.STR, join.left_key, "join"), {"join": key_dict})
         targets = None
         rkey = join.right_key
-        if rkey.type == L.STR:  # both sides must be coded in one dictionary: recode the right key into the left's
-            targets = {"join": lrel.cols[-1].dict}
+        if rkey.type == L.STR:
+            targets = {"join": key_dict}
             rkey = L.ETranslate(L.STR, rkey, "join")
         rrel = side(join.right, right_needed, rkey, targets)
+        if self.comm.world > 1:  # the reference shuffles both sides on the key (plan.py:186-189): same here, over NVLink
+            lrel = self._exchange_on_key(lrel)
+            rrel = self._exchange_on_key(rrel)
+            self.last_stats["exchange"] = "all_to_all"
+            self.last_stats["result_partitioned"] = True
         pairs = C.c_void_p()
         self.ctx.call("msc_hash_join", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.c_void_p(rrel.cols[-1].ptr), rrel.nrows, C.byref(pairs))
         self._note_kernel()
@@ -736,6 +757,42 @@ class CudaExecutionEngine(ExecutionEngine):
             c = rrel.cols[pos]
             columns[nl + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via=1)
         return _Source(prel.nrows, columns, index_vectors=[prel.cols[0], prel.cols[1]], keep=[lrel, rrel, prel])
+
+    def _unified_dictionary(self, local: DictHandle) -> DictHandle:
+        """The same dictionary on every rank: the sorted union of all ranks' entries (code = position)."""
+        universe, _ = unify_keys(self.comm.all_gather_object(local.export()))
+        unified = DictHandle(self.ctx).load(universe)
+        self._query_dicts.append(unified)
+        return unified
+
+    def _exchange_on_key(self, rel: DeviceRel) -> DeviceRel:
+        """Multi-rank join: send every row to rank hash(key) % world (key = last column, an integer), so that equal
+        keys of both sides meet on one GPU.  STR columns are re-coded into rank-independent dictionaries first."""
+        import torch  # noqa: PLC0415
+
+        comm = self.comm
+        ltypes = [c.ltype for c in rel.cols]
+        # (the key column is an integer already: a STR key was coded in the unified key dictionary by the caller)
+        recode = [c.dict is not None and c.ltype == L.STR for c in rel.cols]
+        if any(recode):
+            targets: dict[str, DictHandle] = {}
+            outs: list[L.Expr] = []
+            for i, c in enumerate(rel.cols):
+                if not recode[i]:
+                    outs.append(L.EInput(c.ltype, i))
+                    continue
+                targets[f"x{i}"] = self._unified_dictionary(c.dict)
+                outs.append(L.ETranslate(L.STR, L.EInput(L.STR, i), f"x{i}"))
+            source = _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel])
+            resolver = _ScanResolver(self, source, targets)
+            rel = self._scan_project(resolver, L.compile_project(resolver, [], outs), ltypes)
+        counts = (C.c_uint64 * comm.world)()
+        part = C.c_void_p()
+        self.ctx.call("msc_partition", C.c_void_p(rel.handle), len(rel.cols) - 1, comm.world, counts, C.byref(part))
+        prel = self._track(DeviceRel.from_handle(self.ctx, part.value, ltypes, [c.dict for c in rel.cols]))
+        cols, _ = comm.all_to_all_rows([self._torch_column(c, prel.nrows) for c in prel.cols], [int(c) for c in counts])
+        torch.cuda.synchronize(self.device)
+        return self._rel_from_torch(cols, [c.phys for c in prel.cols], ltypes, [c.dict for c in prel.cols])
 
     # ---- prepared queries ------------------------------------------------------------------------------
     def prepare(self, full_task: Any) -> "PreparedAggregate":
@@ -781,10 +838,8 @@ class CudaExecutionEngine(ExecutionEngine):
         global_dict = None
         if key_dict is not None:  # unify string keys through their dictionary entries
             universe, _ = unify_keys(comm.all_gather_object(key_dict.export()))
-            global_dict = DictHandle(self.ctx)
+            global_dict = DictHandle(self.ctx).load(universe)
             self._query_dicts.append(global_dict)
-            for text in universe:
-                global_dict.literal_code(text, insert=True)
             source = _Source(raw.nrows, dict(enumerate(raw.cols)), keep=[raw])
             resolver = _ScanResolver(self, source, {"global": global_dict})
             outs = [L.ECode(L.INT, L.ETranslate(L.STR, L.EInput(L.STR, 0), "global"))]
@@ -813,7 +868,10 @@ class CudaExecutionEngine(ExecutionEngine):
         out = C.c_void_p()
         self.ctx.call("msc_scan_aggregate", C.byref(desc), 0, N.int32_array(prog2.agg_kinds), len(prog2.agg_kinds), max(gathered.nrows, 1), C.byref(out))
         self._note_kernel()
-        merged = self._track(DeviceRel.from_handle(self.ctx, out.value, [group_type, *slot_types], [global_dict] + [None] * len(slot_types)))
+        # prog2 may carry one accumulator more than asked for (the hidden COUNT of the regvm encoding): type every
+        # column the library returns, then keep the requested ones in order
+        types2 = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog2.agg_kinds]
+        merged = self._track(DeviceRel.from_handle(self.ctx, out.value, [group_type, *types2], [global_dict] + [None] * len(types2)))
         merged.cols = [merged.cols[0]] + [merged.cols[1 + s] for s in prog2.slot_of]
         self.last_stats["exchange"] = "all_gather" if small else "all_to_all"
         self.last_stats["result_partitioned"] = not small  # all_to_all leaves every rank with a disjoint key range

@@ -61,6 +61,50 @@ def main() -> None:
         union = [row for rows_r in gathered for row in rows_r]
         want = O.run_task(ns.DataFrame(None).table(str(lineitem)).filter(ns.Col("l_quantity") > 49).select(ns.Col("l_orderkey"), ns.Col("l_linenumber")).task)
         O.assert_rows_equal(union, want)
+        # JOIN: both sides are co-partitioned on the key (msc_partition + all-to-all), joined locally, and the
+        # aggregate above merges the per-rank partials; string columns travel as codes of rank-independent dictionaries
+        orders = folder / "orders.bin"
+        if rank == 0:
+            gen_tpch.write_table(orders, "orders", sf=0.004, rows_per_block=1024)
+        dist.barrier()
+
+        def join_agg(e):  # noqa: ANN001, ANN202
+            o = ns.DataFrame(e).table(str(orders)).alias("o")
+            l = ns.DataFrame().table(str(lineitem)).alias("l")
+            return (o.join(l, on=ns.Col("o.o_orderkey") == ns.Col("l.l_orderkey"), how="inner")
+                    .filter(ns.Col("o.o_orderdate").between("1994-01-01", "1995-12-31"))
+                    .filter(ns.Col("l.l_shipmode").like("%AIR%"))
+                    .group_by(ns.Col("o.o_orderpriority")).agg(ns.F.count(), ns.F.sum(ns.Col("l.l_extendedprice")).alias("rev")))
+
+        got = join_agg(engine).collect()
+        want = O.run_task(join_agg(None).task, wire=True)
+        assert len(want) > 0
+        O.assert_rows_equal(got, want, rel=5e-7)
+
+        def join_rows(e):  # noqa: ANN001, ANN202
+            o = ns.DataFrame(e).table(str(orders)).alias("o")
+            l = ns.DataFrame().table(str(lineitem)).alias("l")
+            return (o.join(l, on=ns.Col("o.o_orderkey") == ns.Col("l.l_orderkey"), how="inner")
+                    .filter(ns.Col("l.l_quantity") > 48)
+                    .select(ns.Col("o.o_orderkey"), ns.Col("o.o_orderstatus"), ns.Col("l.l_linenumber"), ns.Col("l.l_shipmode")))
+
+        rows = join_rows(engine).collect()
+        dist.all_gather_object(gathered, rows)
+        union = [row for rows_r in gathered for row in rows_r]
+        O.assert_rows_equal(union, O.run_task(join_rows(None).task, wire=True))
+
+        def join_str_key(e):  # noqa: ANN001, ANN202  -- string join key: lineitem's ship modes against a 3-row lookup table
+            m = ns.DataFrame(e).table(str(folder / "modes.bin")).alias("m")
+            l = ns.DataFrame().table(str(lineitem)).alias("l")
+            return (m.join(l, on=ns.Col("m.mode") == ns.Col("l.l_shipmode"), how="inner")
+                    .group_by(ns.Col("m.label")).agg(ns.F.count(), ns.F.sum(ns.Col("l.l_quantity")).alias("q")))
+
+        if rank == 0:
+            ns.BlockFile(folder / "modes.bin").write_rows([{"mode": "AIR", "label": "sky"}, {"mode": "REG AIR", "label": "sky"},
+                                                           {"mode": "SHIP", "label": "sea"}, {"mode": "NOPE", "label": "none"}])
+        dist.barrier()
+        got = join_str_key(engine).collect()
+        O.assert_rows_equal(got, O.run_task(join_str_key(None).task, wire=True), rel=5e-7)
     dist.barrier()
     if rank == 0:
         print("multi-gpu ok", world)
