@@ -208,6 +208,10 @@ MSC_API void msc_destroy(msc_ctx* ctx);
 MSC_API const char* msc_last_error(msc_ctx* ctx);
 MSC_API int msc_sync(msc_ctx* ctx);
 MSC_API int msc_get_stats(msc_ctx* ctx, msc_stats* out);
+/* device time of a region of library calls: start records an event on the compute stream, stop records another,
+ * waits for it and returns the milliseconds in between (what bench.py brackets its K steps with) */
+MSC_API int msc_timer_start(msc_ctx* ctx);
+MSC_API int msc_timer_stop(msc_ctx* ctx, double* ms);
 /* pinned host memory for callers that stage BlockFile images themselves */
 MSC_API int msc_host_alloc(msc_ctx* ctx, size_t nbytes, void** out);
 MSC_API int msc_host_free(msc_ctx* ctx, void* p);
@@ -237,6 +241,8 @@ MSC_API int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, int3
 MSC_API int msc_rel_info(msc_rel* r, uint64_t* nrows, int32_t* ncols);
 MSC_API int msc_rel_col(msc_rel* r, int32_t col, void** dev_ptr, int32_t* phys);
 MSC_API void msc_rel_free(msc_rel* r);
+/* pointers and physical types of all columns in one call (cols[ncols], caller-owned) */
+MSC_API int msc_rel_cols(msc_rel* r, msc_colbind* cols, int32_t ncols);
 /* new relation of `nrows` rows with zero-initialised, tile-padded columns of the given physical types
  * (filled by the caller, e.g. with rows received from other ranks) */
 MSC_API int msc_rel_alloc(msc_ctx* ctx, uint64_t nrows, const int32_t* phys, int32_t ncols, msc_rel** out);
@@ -253,6 +259,23 @@ MSC_API int msc_rel_wrap(msc_ctx* ctx, uint64_t nrows, const msc_colbind* cols, 
 MSC_API int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups,
                        const int32_t* agg_kinds, int32_t naggs, uint64_t hash_capacity_hint,
                        msc_rel** out);
+/* The dense mode in pieces, for callers that put an exchange between the scan and the result (multi-GPU: every
+ * rank scans its row-blocks into a table, the tables are all-gathered over NVLink, merged, compacted -- the
+ * reference's pre-aggregate -> shuffle -> final aggregate, plan.py:190-199).  A table is [ngroups][stride] 64-bit
+ * cells (I64, or F64 bit patterns); msc_dense_layout gives `stride` (naggs, or naggs + 1 when the library keeps
+ * its own row counter) and the slot that tells whether a group received rows. */
+MSC_API int msc_dense_layout(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* agg_kinds, int32_t naggs,
+                     int32_t* stride, int32_t* count_slot);
+/* identities + fused scan into `table` (device, ngroups * stride cells) */
+MSC_API int msc_scan_dense_table(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds,
+                         int32_t naggs, void* table);
+/* fold `world` tables of [gmax][stride] cells (device, rank-major) into out_table[ngroups_out][stride];
+ * perm[r * gmax + g] (host) = output group of rank r's group g, or < 0.  Folds in rank order. */
+MSC_API int msc_dense_merge(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride,
+                    const int32_t* agg_kinds, int32_t naggs, const int32_t* perm, int32_t ngroups_out, void* out_table);
+/* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
+MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
+                      int32_t naggs, int32_t count_slot, msc_rel** out);
 /* Filter + project with stable compaction (output keeps input order, tasks.py:177).  Output
  * column i is written by the instructions whose destination is MSC_DST_OUT i; out_phys[i] in {I64,F64,U32}. */
 MSC_API int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* out_phys,

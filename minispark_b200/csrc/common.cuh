@@ -25,6 +25,7 @@ struct msc_ctx {
   cudaStream_t copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // bracket the fused scan kernel alone
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // msc_timer_start / msc_timer_stop
   int* d_err = nullptr;               // device error word (bit flags written by kernels)
   int* h_err = nullptr;               // pinned mirror
   unsigned long long* h_scratch = nullptr;  // pinned, 16 words: small result read-backs

@@ -110,6 +110,7 @@ extern "C" int msc_create(int device, msc_ctx** out) {
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
   if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) return bail("cudaEventCreate");
   if (cudaEventCreate(&ctx->ev_s0) != cudaSuccess || cudaEventCreate(&ctx->ev_s1) != cudaSuccess) return bail("cudaEventCreate");
+  if (cudaEventCreate(&ctx->ev_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_t1) != cudaSuccess) return bail("cudaEventCreate");
   for (auto& e : ctx->ring_ev)
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail("cudaEventCreate");
   // keep freed blocks in the pool: relations are created and dropped on every query
@@ -143,6 +144,8 @@ extern "C" void msc_destroy(msc_ctx* ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_s0) cudaEventDestroy(ctx->ev_s0);
   if (ctx->ev_s1) cudaEventDestroy(ctx->ev_s1);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   for (auto& s : ctx->copy)
     if (s) cudaStreamDestroy(s);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -153,6 +156,22 @@ extern "C" const char* msc_last_error(msc_ctx* ctx) { return ctx ? ctx->err.c_st
 
 extern "C" int msc_sync(msc_ctx* ctx) {
   MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MSC_OK;
+}
+
+extern "C" int msc_timer_start(msc_ctx* ctx) {
+  if (!ctx) return MSC_ERR_ARG;
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+  return MSC_OK;
+}
+
+extern "C" int msc_timer_stop(msc_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+  MSC_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+  float f = 0;
+  MSC_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+  *ms = f;
   return MSC_OK;
 }
 
@@ -209,6 +228,15 @@ extern "C" int msc_rel_col(msc_rel* r, int32_t col, void** dev_ptr, int32_t* phy
   if (!r || col < 0 || col >= static_cast<int32_t>(r->cols.size())) return MSC_ERR_ARG;
   if (dev_ptr) *dev_ptr = r->cols[col].data;
   if (phys) *phys = r->cols[col].phys;
+  return MSC_OK;
+}
+
+extern "C" int msc_rel_cols(msc_rel* r, msc_colbind* cols, int32_t ncols) {
+  if (!r || !cols || ncols != static_cast<int32_t>(r->cols.size())) return MSC_ERR_ARG;
+  for (int32_t i = 0; i < ncols; ++i) {
+    cols[i].data = r->cols[i].data;
+    cols[i].phys = r->cols[i].phys;
+  }
   return MSC_OK;
 }
 

@@ -54,6 +54,20 @@ __global__ void dense_finalize_kernel(const unsigned long long* table, int ngrou
   *err = 0;
 }
 
+// the part of dense_finalize_kernel a caller needs when the table goes on to a cross-rank merge instead
+__global__ void dense_check_kernel(const unsigned long long* table, int ngroups, int stride, const __grid_constant__ DenseMeta m,
+                                   unsigned long long* out_n, int* err) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long nonfinite = 0;
+  for (int g = 0; g < ngroups; ++g)
+    for (int a = 0; a < stride; ++a)
+      if (m.kinds[a] == MSC_AGG_SUM_F && !isfinite(__longlong_as_double(static_cast<long long>(table[g * stride + a])))) nonfinite = 1;
+  out_n[0] = 0;
+  out_n[1] = nonfinite;
+  out_n[2] = static_cast<unsigned long long>(*err);
+  *err = 0;
+}
+
 constexpr int HTILE = 1024;  // slots per block in the hash-table compaction
 __global__ void hash_count_kernel(const unsigned long long* keys, uint64_t cap, uint32_t* tile_counts) {
   __shared__ uint32_t wsum[8];
@@ -548,125 +562,298 @@ int msc_exclusive_scan_u32_u64(msc_ctx* ctx, const uint32_t* in, uint64_t* out, 
 }
 
 // =================================================================================================
+// dense aggregation, in pieces: identities / layout, init + scan into a [ngroups][stride] table, merge of several
+// ranks' tables, compaction into a relation.  msc_scan_aggregate chains scan + compaction; the multi-GPU path
+// (execution.py) puts an all-gather and a merge between them.
+namespace {
+
+struct DensePlan {
+  long long init[MSC_VM_MAX_AGGS + 1];
+  int kinds[MSC_VM_MAX_AGGS + 1];
+  bool use_regvm;
+  int stride;      // accumulators per group in the table: naggs, or naggs + 1 with the hidden row counter
+  int count_slot;  // slot whose value tells whether the group received rows
+};
+
+int agg_identity(msc_ctx* ctx, int kind, long long* out) {
+  switch (kind) {
+    case MSC_AGG_SUM_F: *out = __builtin_bit_cast(long long, 0.0); return MSC_OK;
+    case MSC_AGG_SUM_I: *out = 0; return MSC_OK;
+    // MIN/MAX are seeded with the reference's MAX_INT / MIN_INT sentinels (tasks.py:303-310, constants.py:14-15)
+    case MSC_AGG_MIN_F: *out = __builtin_bit_cast(long long, 2147483647.0); return MSC_OK;
+    case MSC_AGG_MAX_F: *out = __builtin_bit_cast(long long, -2147483648.0); return MSC_OK;
+    case MSC_AGG_MIN_I: *out = 2147483647LL; return MSC_OK;
+    case MSC_AGG_MAX_I: *out = -2147483648LL; return MSC_OK;
+    default: return ctx->fail(MSC_ERR_ARG, "bad aggregate kind");
+  }
+}
+
+// All dense kernels but the masked regvm variants fold filtered rows into a trash group.  The C++ kernel keeps a
+// hidden per-group row counter to tell which groups received rows; the regvm kernels use the query's own COUNT
+// accumulator (count_slot2) for that.
+int dense_plan(msc_ctx* ctx, const msc_scan_desc* sd, const int32_t* agg_kinds, int naggs, DensePlan* dp) {
+  if (naggs < 0 || naggs > MSC_VM_MAX_AGGS) return ctx->fail(MSC_ERR_ARG, "bad arguments");
+  for (int a = 0; a < naggs; ++a) {
+    dp->kinds[a] = agg_kinds[a];
+    MSC_TRY(agg_identity(ctx, agg_kinds[a], &dp->init[a]));
+  }
+  dp->kinds[naggs] = MSC_AGG_SUM_I;
+  dp->init[naggs] = 0;
+  dp->use_regvm = sd->ncode2 > 0 && regvm_enabled() && sd->count_slot2 >= 0 && sd->count_slot2 < naggs &&
+                  agg_kinds[sd->count_slot2] == MSC_AGG_SUM_I;
+  dp->stride = dp->use_regvm ? naggs : naggs + 1;
+  dp->count_slot = dp->use_regvm ? sd->count_slot2 : naggs;
+  return MSC_OK;
+}
+
+DenseMeta dense_meta(const DensePlan& dp) {
+  DenseMeta meta;
+  memset(&meta, 0, sizeof(meta));
+  memcpy(meta.init, dp.init, sizeof(long long) * dp.stride);
+  memcpy(meta.kinds, dp.kinds, sizeof(int) * dp.stride);
+  return meta;
+}
+
+// init + scan into `table` ([ngroups][stride], device).  allow_masked: a masked regvm variant may run (the caller
+// must then look at the sums: non-finite ones mean "run again with allow_masked = false", gen_regvm.py).
+int dense_scan_into(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, const int32_t* agg_kinds, int naggs, const DensePlan& dp,
+                    bool allow_masked, unsigned long long* table, bool* was_masked) {
+  static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
+  const int ntot = dp.stride;
+  LaunchPlan lp;
+  RegvmProgram rv;
+  int variant = 0;
+  if (dp.use_regvm) {
+    // validate against a provisional plan first: whether the masked variants apply depends on the program
+    bool generic_only = false;
+    MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, 0, &lp, 0));
+    MSC_TRY(build_regvm(ctx, sd, lp.p, agg_kinds, naggs, &rv, &generic_only));
+    if (allow_masked && masked_enabled && !generic_only && ngroups <= MSC_RV_MAX_NG) variant = ngroups;
+  }
+  *was_masked = variant > 0;
+  const int smem_groups = variant > 0 ? ngroups : ngroups + 1;  // + the trash group
+  const size_t acc_bytes = static_cast<size_t>(smem_groups) * ntot * NT * sizeof(long long);
+  if (acc_bytes > 96 * 1024) return ctx->fail(MSC_ERR_ARG, "dense aggregate: groups x aggregates too large; use hash mode");
+  const size_t regvm_bytes = (MSC_RV_MAX_CODE + 2) * sizeof(uint32_t) + MSC_VM_MAX_CONSTS * sizeof(long long);
+  if (dp.use_regvm) MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, acc_bytes + regvm_bytes, &lp, 0, variant >= 3 ? 3 : 4));
+  else MSC_TRY(plan_launch(ctx, sd, pick_rows_per_thread(sd->nrows), acc_bytes, &lp));
+  lp.p.ngroups = ngroups;
+  lp.p.naggs = ntot;
+  memcpy(lp.p.agg_init, dp.init, sizeof(long long) * ntot);
+  memcpy(lp.p.agg_kind, dp.kinds, sizeof(int) * ntot);
+  dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table, ngroups, ntot, dense_meta(dp));
+  ctx->stats.launches += 1;
+  lp.p.dense_out = table;
+  if (sd->nrows == 0) return MSC_OK;
+  if (!dp.use_regvm) return launch_scan_r<MODE_DENSE>(ctx, &lp);
+  switch (variant) {
+    case 1: return launch_regvm_dense_ng1(ctx, &lp, &rv);
+    case 2: return launch_regvm_dense_ng2(ctx, &lp, &rv);
+    case 3: return launch_regvm_dense_ng3(ctx, &lp, &rv);
+    case 4: return launch_regvm_dense_ng4(ctx, &lp, &rv);
+    default: return launch_regvm_dense_ng0(ctx, &lp, &rv);
+  }
+}
+
+// compact `table` into a relation: group id (U32) + the first naggs accumulators of every group that received rows.
+// One host synchronisation; reports a non-finite SUM_F and the device error word along with the group count.
+int dense_compact(msc_ctx* ctx, const unsigned long long* table, int ngroups, int naggs, const DensePlan& dp, msc_rel** out,
+                  bool* nonfinite) {
+  DevTmp d_n(ctx);
+  MSC_TRY(d_n.alloc(3 * sizeof(unsigned long long)));
+  msc_rel* rel = new_rel(ctx, 0);
+  int physes[MSC_VM_MAX_AGGS + 1];
+  physes[0] = MSC_P_U32;
+  for (int a = 0; a < naggs; ++a)
+    physes[1 + a] = (dp.kinds[a] == MSC_AGG_SUM_F || dp.kinds[a] == MSC_AGG_MIN_F || dp.kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64;
+  const int rc = add_cols(ctx, rel, physes, 1 + naggs, ngroups);
+  if (rc != MSC_OK) {
+    msc_rel_free(rel);
+    return rc;
+  }
+  DenseMeta meta = dense_meta(dp);
+  for (int a = 0; a < naggs; ++a) meta.out_acc[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
+  dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table, ngroups, dp.stride, naggs, dp.count_slot, meta,
+                                                  static_cast<uint32_t*>(rel->cols[0].data), d_n.as<unsigned long long>(), ctx->d_err);
+  ctx->stats.launches += 1;
+  cudaEventRecord(ctx->ev_b, ctx->stream);
+  unsigned long long* n = ctx->h_scratch;  // pinned: a plain stack buffer would make the copy synchronous twice over
+  if (cudaMemcpyAsync(n, d_n.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    msc_rel_free(rel);
+    return ctx->fail(MSC_ERR_CUDA, "dense aggregate failed");
+  }
+  const int drc = msc_device_error_rc(ctx, static_cast<int>(n[2]));
+  if (drc != MSC_OK) {
+    msc_rel_free(rel);
+    return drc;
+  }
+  rel->nrows = n[0];
+  *nonfinite = n[1] != 0;
+  *out = rel;
+  return MSC_OK;
+}
+
+void note_times(msc_ctx* ctx, bool scanned) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+  if (scanned && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
+}
+
+__device__ __forceinline__ long long agg_combine_dev(int kind, long long cur, long long v) {  // = mscan::agg_combine
+  switch (kind) {
+    case MSC_AGG_SUM_F: return __double_as_longlong(__longlong_as_double(cur) + __longlong_as_double(v));
+    case MSC_AGG_SUM_I: return cur + v;
+    case MSC_AGG_MIN_F: return (__longlong_as_double(v) < __longlong_as_double(cur)) ? v : cur;
+    case MSC_AGG_MAX_F: return (__longlong_as_double(v) > __longlong_as_double(cur)) ? v : cur;
+    case MSC_AGG_MIN_I: return (v < cur) ? v : cur;
+    default: return (v > cur) ? v : cur;  // MSC_AGG_MAX_I
+  }
+}
+
+// fold `world` tables ([gmax][stride] each, rank-major) into out[ngroups_out][stride]; perm[r * gmax + g] is the
+// output group of rank r's group g (< 0: rank r has no such group).  Rank order, so every rank computes the same bits.
+__global__ void dense_merge_kernel(const unsigned long long* tables, int world, int gmax, int stride, const int* perm, int ngroups_out,
+                                   const __grid_constant__ DenseMeta m, unsigned long long* out) {
+  const int cells = ngroups_out * stride;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) out[i] = static_cast<unsigned long long>(m.init[i % stride]);
+  __syncthreads();
+  for (int a = threadIdx.x; a < stride; a += blockDim.x) {  // one thread per accumulator column: no races between ranks
+    for (int r = 0; r < world; ++r)
+      for (int g = 0; g < gmax; ++g) {
+        const int dst = perm[r * gmax + g];
+        if (dst < 0 || dst >= ngroups_out) continue;
+        unsigned long long* cell = out + dst * stride + a;
+        *cell = static_cast<unsigned long long>(
+            agg_combine_dev(m.kinds[a], static_cast<long long>(*cell), static_cast<long long>(tables[(static_cast<size_t>(r) * gmax + g) * stride + a])));
+      }
+  }
+}
+
+}  // namespace
+
+extern "C" int msc_dense_layout(msc_ctx* ctx, const msc_scan_desc* sd, const int32_t* agg_kinds, int32_t naggs, int32_t* stride,
+                                int32_t* count_slot) {
+  if (!ctx || !sd || !stride || !count_slot) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  DensePlan dp;
+  MSC_TRY(dense_plan(ctx, sd, agg_kinds, naggs, &dp));
+  *stride = dp.stride;
+  *count_slot = dp.count_slot;
+  return MSC_OK;
+}
+
+extern "C" int msc_scan_dense_table(msc_ctx* ctx, const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs,
+                                    void* table) {
+  if (!ctx || !sd || !table || ngroups <= 0) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  MSC_TRY(validate_program(ctx, sd, MODE_DENSE, agg_kinds, naggs, nullptr, 0));
+  DensePlan dp;
+  MSC_TRY(dense_plan(ctx, sd, agg_kinds, naggs, &dp));
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  DevTmp d_n(ctx);
+  MSC_TRY(d_n.alloc(3 * sizeof(unsigned long long)));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    bool masked = false;
+    MSC_TRY(dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, attempt == 0, static_cast<unsigned long long*>(table), &masked));
+    dense_check_kernel<<<1, 32, 0, ctx->stream>>>(static_cast<const unsigned long long*>(table), ngroups, dp.stride, dense_meta(dp),
+                                                 d_n.as<unsigned long long>(), ctx->d_err);
+    ctx->stats.launches += 1;
+    MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    unsigned long long* n = ctx->h_scratch;
+    MSC_CUDA(ctx, cudaMemcpyAsync(n, d_n.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MSC_TRY(msc_device_error_rc(ctx, static_cast<int>(n[2])));
+    if (masked && n[1] != 0) continue;  // non-finite SUM out of a masked variant: redo it the exact way
+    note_times(ctx, sd->nrows > 0);
+    return MSC_OK;
+  }
+  return ctx->fail(MSC_ERR_ARG, "dense aggregate: unreachable");
+}
+
+extern "C" int msc_dense_merge(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride, const int32_t* agg_kinds,
+                               int32_t naggs, const int32_t* perm, int32_t ngroups_out, void* out_table) {
+  if (!ctx || !tables || !perm || !out_table || world <= 0 || gmax <= 0 || ngroups_out <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS ||
+      (stride != naggs && stride != naggs + 1))
+    return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  DensePlan dp;
+  for (int a = 0; a < naggs; ++a) {
+    dp.kinds[a] = agg_kinds[a];
+    MSC_TRY(agg_identity(ctx, agg_kinds[a], &dp.init[a]));
+  }
+  dp.kinds[naggs] = MSC_AGG_SUM_I;
+  dp.init[naggs] = 0;
+  dp.stride = stride;
+  DevTmp d_perm(ctx);
+  MSC_TRY(d_perm.alloc(sizeof(int32_t) * world * gmax));
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  MSC_CUDA(ctx, cudaMemcpyAsync(d_perm.p, perm, sizeof(int32_t) * world * gmax, cudaMemcpyHostToDevice, ctx->stream));
+  dense_merge_kernel<<<1, 64, 0, ctx->stream>>>(static_cast<const unsigned long long*>(tables), world, gmax, stride, d_perm.as<int>(),
+                                               ngroups_out, dense_meta(dp), static_cast<unsigned long long*>(out_table));
+  ctx->stats.launches += 1;
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  MSC_CUDA(ctx, cudaGetLastError());
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `perm` is the caller's
+  note_times(ctx, false);
+  return MSC_OK;
+}
+
+extern "C" int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
+                                 int32_t naggs, int32_t count_slot, msc_rel** out) {
+  if (!ctx || !table || !out || ngroups <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS || (stride != naggs && stride != naggs + 1) ||
+      count_slot < 0 || count_slot >= stride)
+    return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  DensePlan dp;
+  for (int a = 0; a < naggs; ++a) {
+    dp.kinds[a] = agg_kinds[a];
+    MSC_TRY(agg_identity(ctx, agg_kinds[a], &dp.init[a]));
+  }
+  dp.kinds[naggs] = MSC_AGG_SUM_I;
+  dp.init[naggs] = 0;
+  dp.stride = stride;
+  dp.count_slot = count_slot;
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  bool nonfinite = false;
+  MSC_TRY(dense_compact(ctx, static_cast<const unsigned long long*>(table), ngroups, naggs, dp, out, &nonfinite));
+  note_times(ctx, false);
+  return MSC_OK;
+}
+
 extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds,
                                   int32_t naggs, uint64_t hash_capacity_hint, msc_rel** out) {
   if (!ctx || !sd || !out || naggs < 0 || naggs > MSC_VM_MAX_AGGS) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   const bool dense = ngroups > 0;
   MSC_TRY(validate_program(ctx, sd, dense ? MODE_DENSE : MODE_HASH, agg_kinds, naggs, nullptr, 0));
-  long long init[MSC_VM_MAX_AGGS + 1];
-  int kinds[MSC_VM_MAX_AGGS + 1];
-  for (int a = 0; a < naggs; ++a) {
-    kinds[a] = agg_kinds[a];
-    switch (agg_kinds[a]) {
-      case MSC_AGG_SUM_F: init[a] = __builtin_bit_cast(long long, 0.0); break;
-      case MSC_AGG_SUM_I: init[a] = 0; break;
-      // MIN/MAX are seeded with the reference's MAX_INT / MIN_INT sentinels (tasks.py:303-310, constants.py:14-15)
-      case MSC_AGG_MIN_F: init[a] = __builtin_bit_cast(long long, 2147483647.0); break;
-      case MSC_AGG_MAX_F: init[a] = __builtin_bit_cast(long long, -2147483648.0); break;
-      case MSC_AGG_MIN_I: init[a] = 2147483647LL; break;
-      case MSC_AGG_MAX_I: init[a] = -2147483648LL; break;
-      default: return ctx->fail(MSC_ERR_ARG, "bad aggregate kind");
-    }
-  }
-  const int R = pick_rows_per_thread(sd->nrows);
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
 
   if (dense) {
-    // All dense kernels but the masked regvm variants fold filtered rows into a trash group.  The C++ kernel keeps
-    // a hidden per-group row counter to tell which groups received rows; the regvm kernels use the query's own
-    // COUNT accumulator (count_slot2) for that.
-    const bool use_regvm = sd->ncode2 > 0 && regvm_enabled() && sd->count_slot2 >= 0 && sd->count_slot2 < naggs &&
-                           agg_kinds[sd->count_slot2] == MSC_AGG_SUM_I;
-    const int ntot = use_regvm ? naggs : naggs + 1;
-    const int count_slot = use_regvm ? sd->count_slot2 : naggs;
-    kinds[naggs] = MSC_AGG_SUM_I;
-    init[naggs] = 0;
-    static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
+    DensePlan dp;
+    MSC_TRY(dense_plan(ctx, sd, agg_kinds, naggs, &dp));
+    DevTmp table(ctx);
+    MSC_TRY(table.alloc(sizeof(unsigned long long) * ngroups * dp.stride));
     // attempt 0 may use a masked regvm variant (exactly `ngroups` groups, per-group reduction in registers); if a SUM
     // comes back non-finite that variant cannot be trusted (gen_regvm.py) and attempt 1 reruns on the generic kernel
     for (int attempt = 0; attempt < 2; ++attempt) {
-      LaunchPlan lp;
-      RegvmProgram rv;
-      int variant = 0;
-      if (use_regvm) {
-        // validate against a provisional plan first: whether the masked variants apply depends on the program
-        bool generic_only = false;
-        MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, 0, &lp, 0));
-        MSC_TRY(build_regvm(ctx, sd, lp.p, agg_kinds, naggs, &rv, &generic_only));
-        if (attempt == 0 && masked_enabled && !generic_only && ngroups <= MSC_RV_MAX_NG) variant = ngroups;
-      }
-      const int smem_groups = variant > 0 ? ngroups : ngroups + 1;  // + the trash group
-      const size_t acc_bytes = static_cast<size_t>(smem_groups) * ntot * NT * sizeof(long long);
-      if (acc_bytes > 96 * 1024) return ctx->fail(MSC_ERR_ARG, "dense aggregate: groups x aggregates too large; use hash mode");
-      const size_t regvm_bytes = (MSC_RV_MAX_CODE + 2) * sizeof(uint32_t) + MSC_VM_MAX_CONSTS * sizeof(long long);
-      if (use_regvm) MSC_TRY(plan_launch(ctx, sd, MSC_RV_ROWS, acc_bytes + regvm_bytes, &lp, 0, variant >= 3 ? 3 : 4));
-      else MSC_TRY(plan_launch(ctx, sd, R, acc_bytes, &lp));
-      lp.p.ngroups = ngroups;
-      lp.p.naggs = ntot;
-      memcpy(lp.p.agg_init, init, sizeof(long long) * ntot);
-      memcpy(lp.p.agg_kind, kinds, sizeof(int) * ntot);
-      // global table, initialised with the identities
-      DevTmp table(ctx), d_n(ctx);
-      MSC_TRY(table.alloc(sizeof(unsigned long long) * ngroups * ntot));
-      MSC_TRY(d_n.alloc(3 * sizeof(unsigned long long)));
-      DenseMeta meta;
-      memset(&meta, 0, sizeof(meta));
-      memcpy(meta.init, init, sizeof(long long) * ntot);
-      memcpy(meta.kinds, kinds, sizeof(int) * ntot);
-      dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, meta);
-      ctx->stats.launches += 1;
-      lp.p.dense_out = table.as<unsigned long long>();
-      if (sd->nrows > 0) {
-        if (!use_regvm) MSC_TRY(launch_scan_r<MODE_DENSE>(ctx, &lp));
-        else switch (variant) {
-          case 1: MSC_TRY(launch_regvm_dense_ng1(ctx, &lp, &rv)); break;
-          case 2: MSC_TRY(launch_regvm_dense_ng2(ctx, &lp, &rv)); break;
-          case 3: MSC_TRY(launch_regvm_dense_ng3(ctx, &lp, &rv)); break;
-          case 4: MSC_TRY(launch_regvm_dense_ng4(ctx, &lp, &rv)); break;
-          default: MSC_TRY(launch_regvm_dense_ng0(ctx, &lp, &rv)); break;
-        }
-      }
-      // compact present groups into the output relation
-      msc_rel* rel = new_rel(ctx, 0);
-      int physes[MSC_VM_MAX_AGGS + 1];
-      physes[0] = MSC_P_U32;
-      for (int a = 0; a < naggs; ++a)
-        physes[1 + a] = (kinds[a] == MSC_AGG_SUM_F || kinds[a] == MSC_AGG_MIN_F || kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64;
-      int rc = add_cols(ctx, rel, physes, 1 + naggs, ngroups);
-      if (rc != MSC_OK) {
-        msc_rel_free(rel);
-        return rc;
-      }
-      for (int a = 0; a < naggs; ++a) meta.out_acc[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
-      dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table.as<unsigned long long>(), ngroups, ntot, naggs, count_slot, meta,
-                                                      static_cast<uint32_t*>(rel->cols[0].data), d_n.as<unsigned long long>(), ctx->d_err);
-      ctx->stats.launches += 1;
-      cudaEventRecord(ctx->ev_b, ctx->stream);
-      unsigned long long* n = ctx->h_scratch;  // pinned: a plain stack buffer would make the copy synchronous twice over
-      if (cudaMemcpyAsync(n, d_n.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-          cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-        msc_rel_free(rel);
-        return ctx->fail(MSC_ERR_CUDA, "dense aggregate failed");
-      }
-      const int drc = msc_device_error_rc(ctx, static_cast<int>(n[2]));
-      if (drc != MSC_OK) {
-        msc_rel_free(rel);
-        return drc;
-      }
-      if (variant > 0 && n[1] != 0) {  // non-finite SUM out of a masked variant: redo it the exact way
+      bool masked = false, nonfinite = false;
+      MSC_TRY(dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, attempt == 0, table.as<unsigned long long>(), &masked));
+      msc_rel* rel = nullptr;
+      MSC_TRY(dense_compact(ctx, table.as<unsigned long long>(), ngroups, naggs, dp, &rel, &nonfinite));
+      if (masked && nonfinite) {
         msc_rel_free(rel);
         continue;
       }
-      rel->nrows = n[0];
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
-      ctx->stats.last_kernel_ms = ms;
-      if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
+      note_times(ctx, sd->nrows > 0);
       *out = rel;
       return MSC_OK;
     }
     return ctx->fail(MSC_ERR_ARG, "dense aggregate: unreachable");
   }
+
+  long long init[MSC_VM_MAX_AGGS + 1];
+  int kinds[MSC_VM_MAX_AGGS + 1];
+  for (int a = 0; a < naggs; ++a) {
+    kinds[a] = agg_kinds[a];
+    MSC_TRY(agg_identity(ctx, agg_kinds[a], &init[a]));
+  }
+  const int R = pick_rows_per_thread(sd->nrows);
 
   // ---- hash mode ----
   uint64_t want = hash_capacity_hint ? hash_capacity_hint : sd->nrows;
@@ -785,16 +972,12 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
     }
   }
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
-  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
-  ctx->stats.last_kernel_ms = ms;
-  if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
-  int drc = msc_check_device_error(ctx);
+  const int drc = msc_check_device_error(ctx);  // synchronises the stream
   if (drc != MSC_OK) {
     msc_rel_free(rel);
     return drc;
   }
+  note_times(ctx, sd->nrows > 0);
   *out = rel;
   return MSC_OK;
 }

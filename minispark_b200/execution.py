@@ -185,12 +185,9 @@ class DeviceRel:
         nrows = C.c_uint64()
         ncols = C.c_int32()
         ctx.check(ctx.lib.msc_rel_info(C.c_void_p(handle), C.byref(nrows), C.byref(ncols)))
-        cols = []
-        for i in range(ncols.value):
-            ptr = C.c_void_p()
-            phys = C.c_int32()
-            ctx.check(ctx.lib.msc_rel_col(C.c_void_p(handle), i, C.byref(ptr), C.byref(phys)))
-            cols.append(DeviceColumn(ptr.value or 0, phys.value, ltypes[i], dicts[i]))
+        binds = (N.ColBind * max(ncols.value, 1))()
+        ctx.check(ctx.lib.msc_rel_cols(C.c_void_p(handle), binds, ncols.value))
+        cols = [DeviceColumn(binds[i].data or 0, binds[i].phys, ltypes[i], dicts[i]) for i in range(ncols.value)]
         return cls(ctx, handle, nrows.value, cols)
 
     def free(self) -> None:
@@ -691,29 +688,45 @@ class CudaExecutionEngine(ExecutionEngine):
         aggs = [(k, e) for (k, _), e in zip(aggs, exprs[nf + 1:])]
         resolver = _ScanResolver(self, source)
         prog = L.compile_aggregate(resolver, filters, group, aggs)
-        ngroups = 0
-        hint = 0
-        if prog.group_dict is not None:
-            size = prog.group_dict.size
-            if size > 0 and (size + 1) * (len(prog.agg_kinds) + 1) <= DENSE_MAX_CELLS:
-                ngroups = size
-            hint = max(size, 1)
+        ngroups, hint = self._dense_groups(prog)
         desc = resolver.desc(prog.program)
         kinds = N.int32_array(prog.agg_kinds)
-        out = C.c_void_p()
-        self.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), hint, C.byref(out))
-        self._note_kernel()
-        self.last_stats["agg_mode"] = "dense" if ngroups else "hash"
         # raw result: key + one column per unique accumulator slot; expose it in the aggregate's schema order
         slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog.agg_kinds]
-        raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
-        if self.comm.world > 1:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
-            raw = self._merge_partials(raw, prog.agg_kinds, slot_types, group.type)
+        self.last_stats["agg_mode"] = "dense" if ngroups else "hash"
+        if ngroups and self.comm.world > 1:  # dense tables merge across ranks without moving rows (_DenseMerge)
+            merge = _DenseMerge(self, prog.group_dict, desc, kinds, len(prog.agg_kinds))
+            handle, _ = merge.run(desc)
+            self._note_kernel()
+            self.last_stats["exchange"] = "all_gather"
+            self.last_stats["result_partitioned"] = False
+            raw = self._track(DeviceRel.from_handle(self.ctx, handle, [group.type, *slot_types], [merge.global_dict] + [None] * len(slot_types)))
+        else:
+            out = C.c_void_p()
+            self.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), hint, C.byref(out))
+            self._note_kernel()
+            raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
+            if self.comm.world > 1:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
+                raw = self._merge_partials(raw, prog.agg_kinds, slot_types, group.type)
         key = raw.cols[0]
         if group.type == L.FLOAT and key.phys == N.P_I64:
             key = DeviceColumn(key.ptr, N.P_F64, L.FLOAT)  # hash mode stores the f64 bit pattern
         cols = [key] + [raw.cols[1 + s] for s in prog.slot_of]
         return DeviceRel(self.ctx, None, raw.nrows, cols, keep=[raw, *source.keep])
+
+    def _dense_groups(self, prog: L.AggregateProgram) -> tuple[int, int]:
+        """(groups of the dense table or 0 for hash mode, capacity hint).  Dense mode needs a dictionary-coded key and a
+        table that fits shared memory; with several ranks all of them must take the same decision."""
+        if prog.group_dict is None:
+            return 0, 0
+        size = prog.group_dict.size
+        limit = size
+        if self.comm.world > 1:
+            limit = max(self.comm.all_gather_object(size))
+        dense = limit > 0 and (limit + 1) * (len(prog.agg_kinds) + 1) <= DENSE_MAX_CELLS
+        if self.comm.world == 1:
+            dense = dense and size > 0
+        return (max(size, 1) if dense else 0), max(size, 1)
 
     def _join_source(self, join: L.LJoin, needed: set[int]) -> _Source:
         nl = len(join.left.schema)
@@ -878,6 +891,71 @@ class CudaExecutionEngine(ExecutionEngine):
         return merged
 
 
+class _DenseMerge:
+    """Cross-rank merge of a low-cardinality (dense) GROUP BY, set up once per query.
+
+    Every rank scans its row-blocks into a [groups][stride] table of its own dictionary codes; the tables are
+    all-gathered (NCCL over NVLink: a few hundred bytes per rank), folded in rank order by ``msc_dense_merge`` through
+    per-rank code permutations into the unified dictionary, and compacted.  Every rank ends up with the complete,
+    bit-identical result.  This is the reference's pre-aggregate -> shuffle -> final aggregate (plan.py:190-199)
+    without a row ever leaving its GPU."""
+
+    def __init__(self, engine: "CudaExecutionEngine", group_dict: DictHandle, desc: N.ScanDesc, kinds, naggs: int,  # noqa: ANN001
+                 persistent: bool = False) -> None:
+        import torch  # noqa: PLC0415
+
+        self.engine = engine
+        self.kinds, self.naggs = kinds, naggs
+        comm = engine.comm
+        stride, count_slot = C.c_int32(), C.c_int32()
+        engine.ctx.call("msc_dense_layout", C.byref(desc), kinds, naggs, C.byref(stride), C.byref(count_slot))
+        self.stride, self.count_slot = stride.value, count_slot.value
+        layouts = comm.all_gather_object((self.stride, self.count_slot))
+        if len(set(layouts)) != 1:
+            raise ExecutionError("ranks disagree on the aggregate table layout")
+        per_rank = comm.all_gather_object(group_dict.export())
+        universe, maps = unify_keys(per_rank)
+        self.nlocal = len(per_rank[comm.rank])
+        self.gmax = max(max(len(e) for e in per_rank), 1)
+        self.nglobal = len(universe)
+        flat = []
+        for m in maps:
+            flat.extend(list(m) + [-1] * (self.gmax - len(m)))
+        self.perm = N.int32_array(flat)
+        self.global_dict = DictHandle(engine.ctx).load(universe)
+        # a prepared query outlives release_query(): its dictionary is freed with the engine instead
+        (engine._table_dicts if persistent else engine._query_dicts).append(self.global_dict)
+        dev = torch.device("cuda", engine.device)
+        cells = self.gmax * self.stride
+        self.local = torch.zeros(cells, dtype=torch.int64, device=dev)
+        self.gathered = torch.zeros(comm.world * cells, dtype=torch.int64, device=dev)
+        self.merged = torch.zeros(max(self.nglobal, 1) * self.stride, dtype=torch.int64, device=dev)
+
+    def run(self, desc: N.ScanDesc) -> tuple[Optional[int], float]:
+        """One pass; returns (handle of the merged result relation or None when there are no groups, device ms)."""
+        import torch  # noqa: PLC0415
+        import torch.distributed as dist  # noqa: PLC0415
+
+        e = self.engine
+        ms = 0.0
+        if self.nlocal > 0:
+            e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()))
+            ms += e.ctx.stats().last_kernel_ms
+        if self.nglobal == 0:
+            return None, ms
+        # the library call above ended with a stream synchronisation, so NCCL may read `local` right away
+        dist.all_gather_into_tensor(self.gathered, self.local)
+        torch.cuda.current_stream(e.device).synchronize()
+        e.ctx.call("msc_dense_merge", C.c_void_p(self.gathered.data_ptr()), e.comm.world, self.gmax, self.stride, self.kinds, self.naggs,
+                   self.perm, self.nglobal, C.c_void_p(self.merged.data_ptr()))
+        ms += e.ctx.stats().last_kernel_ms
+        out = C.c_void_p()
+        e.ctx.call("msc_dense_compact", C.c_void_p(self.merged.data_ptr()), self.nglobal, self.stride, self.kinds, self.naggs, self.count_slot,
+                   C.byref(out))
+        ms += e.ctx.stats().last_kernel_ms
+        return out.value, ms
+
+
 class PreparedAggregate:
     """A compiled ``scan -> filter -> GROUP BY -> final projection`` query bound to device-resident columns."""
 
@@ -902,38 +980,54 @@ class PreparedAggregate:
         self.kinds = N.int32_array(self.prog.agg_kinds)
         self.slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT
                            for k in self.prog.agg_kinds]
-        self.ngroups = 0
-        self.hint = 0
-        if self.prog.group_dict is not None:
-            size = self.prog.group_dict.size
-            if size > 0 and (size + 1) * (len(self.prog.agg_kinds) + 1) <= DENSE_MAX_CELLS:
-                self.ngroups = size
-            self.hint = max(size, 1)
+        self.ngroups, self.hint = engine._dense_groups(self.prog)
+        self.merge = None
+        if self.ngroups and engine.comm.world > 1:
+            self.merge = _DenseMerge(engine, self.prog.group_dict, self.desc, self.kinds, len(self.prog.agg_kinds), persistent=True)
         self.bytes_per_row = sum(N.PHYS_WIDTH[c.phys] for c in self.resolver.staged)
         self.nrows = self.source.nrows
         self.scan_stats: dict[str, Any] = {}
+        self._final: Optional[tuple] = None  # compiled final projection, re-bound to every pass's aggregate result
 
     def run(self) -> tuple[DeviceRel, float]:
         """One pass of the hot path; returns (result relation, device milliseconds of this rank's launches)."""
         e = self.engine
-        out = C.c_void_p()
-        e.ctx.call("msc_scan_aggregate", C.byref(self.desc), self.ngroups, self.kinds, len(self.prog.agg_kinds), self.hint, C.byref(out))
+        naggs = len(self.prog.agg_kinds)
+        key_dict = self.prog.group_dict
+        if self.merge is not None:
+            handle, dev_ms = self.merge.run(self.desc)
+            key_dict = self.merge.global_dict
+        else:
+            out = C.c_void_p()
+            e.ctx.call("msc_scan_aggregate", C.byref(self.desc), self.ngroups, self.kinds, naggs, self.hint, C.byref(out))
+            handle, dev_ms = out.value, e.ctx.stats().last_kernel_ms
         st = e.ctx.stats()
-        dev_ms = st.last_kernel_ms
         self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
                            "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread}
-        raw = e._track(DeviceRel.from_handle(e.ctx, out.value, [self.group_type, *self.slot_types],
-                                             [self.prog.group_dict] + [None] * len(self.slot_types)))
-        if e.comm.world > 1:
+        raw = e._track(DeviceRel.from_handle(e.ctx, handle, [self.group_type, *self.slot_types], [key_dict] + [None] * len(self.slot_types)))
+        if self.merge is None and e.comm.world > 1:  # hash mode: partition + all-to-all (or all-gather when small)
             raw = e._merge_partials(raw, self.prog.agg_kinds, self.slot_types, self.group_type)
             dev_ms += e.ctx.stats().last_kernel_ms
         key = raw.cols[0]
         if self.group_type == L.FLOAT and key.phys == N.P_I64:
             key = DeviceColumn(key.ptr, N.P_F64, L.FLOAT)
         cols = [key] + [raw.cols[1 + s] for s in self.prog.slot_of]
-        src2 = _Source(raw.nrows, dict(enumerate(cols)))
-        res2 = _ScanResolver(e, src2)
-        prog2 = L.compile_project(res2, self.plan.filters, self.plan.outputs)
-        final = e._scan_project(res2, prog2, [x.type for x in self.plan.outputs])
+        if self._final is None or self._final[3] != [(c.phys, id(c.dict)) for c in cols]:
+            # compile the final projection (AVG = SUM / COUNT, HAVING, output order) once; later passes only re-bind it
+            src2 = _Source(raw.nrows, dict(enumerate(cols)))
+            res2 = _ScanResolver(e, src2)
+            prog2 = L.compile_project(res2, self.plan.filters, self.plan.outputs)
+            index_of = {c.ptr: i for i, c in enumerate(cols)}
+            self._final = (res2.desc(prog2.program), prog2, [index_of[c.ptr] for c in res2.staged], [(c.phys, id(c.dict)) for c in cols],
+                           bool(res2.gather))
+        desc2, prog2, staged_cols, _, gathers = self._final
+        if gathers:
+            raise L.LoweringError("prepared final projection must not gather")
+        desc2.nrows = raw.nrows
+        for slot, ci in enumerate(staged_cols):
+            desc2.staged[slot].data = cols[ci].ptr
+        out2 = C.c_void_p()
+        e.ctx.call("msc_scan_project", C.byref(desc2), N.int32_array(prog2.out_phys), len(prog2.out_phys), C.byref(out2))
         dev_ms += e.ctx.stats().last_kernel_ms
+        final = e._track(DeviceRel.from_handle(e.ctx, out2.value, [x.type for x in self.plan.outputs], prog2.out_dicts))
         return final, dev_ms

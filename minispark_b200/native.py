@@ -118,6 +118,16 @@ _SIGNATURES = {
     "msc_rel_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "msc_rel_col": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "msc_rel_free": (None, [C.c_void_p]),
+    "msc_rel_cols": (C.c_int, [C.c_void_p, C.POINTER(ColBind), C.c_int32]),
+    "msc_timer_start": (C.c_int, [C.c_void_p]),
+    "msc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "msc_dense_layout": (C.c_int, [C.c_void_p, C.POINTER(ScanDesc), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32)]),
+    "msc_scan_dense_table": (C.c_int, [C.c_void_p, C.POINTER(ScanDesc), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
+    "msc_dense_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                  C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
+    "msc_dense_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_void_p)]),
     "msc_rel_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
     "msc_rel_wrap": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(ColBind), C.c_int32, C.POINTER(C.c_void_p)]),
     "msc_scan_aggregate": (C.c_int, [C.c_void_p, C.POINTER(ScanDesc), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_uint64,
