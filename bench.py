@@ -113,6 +113,26 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def captured_traffic(sf: float, layout: str, rows: int, bytes_per_row: int) -> tuple[float | None, str | None]:
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very workload (profiles/)."""
+    path = ROOT / "profiles" / "r01_traffic.json"
+    if not path.exists():
+        return None, None
+    for cap in json.loads(path.read_text()).get("captures", []):
+        w = cap["workload"]
+        if (w["sf_per_gpu"], w["layout"], w["rows_per_gpu"], w["bytes_per_row_scanned"]) == (sf, layout, rows, bytes_per_row):
+            return float(cap["traffic_bytes"]), f"profiles/r01_traffic.json ({cap['capture']})"
+    return None, None
+
+
+def kernel_name(rows_per_thread: int) -> str:
+    """msc_stats.last_scan_rows_per_thread: R of scan_kernel<R, MODE_DENSE>, or -(8 + 100 * NG) for the regvm variants."""
+    if rows_per_thread >= 0:
+        return f"scan_kernel<R={rows_per_thread}, MODE_DENSE>"
+    ng, rows = divmod(-rows_per_thread, 100)
+    return f"regvm_dense_kernel_ng{ng} ({rows} rows per lane)"
+
+
 def table_path(sf: float, rank: int) -> Path:
     base = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
     folder = base / f"minispark_b200_bench_{os.getuid()}"
@@ -319,6 +339,7 @@ def cuda_arm(args: argparse.Namespace) -> None:
         scan_ms = statistics.mean(scan_ms_all)
         achieved = nrows_table * bytes_per_row / (scan_ms * 1e-3) / 1e9
         peak, peak_src = peaks()
+        traffic, traffic_src = captured_traffic(args.sf, args.layout, nrows_table, bytes_per_row)
 
         # ---- e2e: pinned host image -> H2D -> decode -> scan -> result back on the host -----------------
         e2e_times, h2d_bytes, d2h_bytes = [], 0, 0
@@ -360,8 +381,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
                     "timing": "two CUDA events on the library's stream bracketing all timed steps (host gaps and the NCCL merge included), max over ranks",
                     "wall_ms_per_step": 1e3 * wall_max / args.steps, "parity_check": check,
                 },
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "kernel": "scan_kernel<R=%d, MODE_DENSE>" % agg_launch["rows_per_thread"], "launch": agg_launch,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "kernel": kernel_name(agg_launch["rows_per_thread"]), "launch": agg_launch,
                              "program": prepared.prog.program.text,
                              "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": nrows_table * bytes_per_row, "peak_source": peak_src,
                              "north_star_layout_equiv_gbs": nrows_table * Q1_WIDE_BYTES_PER_ROW / (scan_ms * 1e-3) / 1e9 if args.layout == "native" else None},

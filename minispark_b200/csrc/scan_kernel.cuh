@@ -896,9 +896,16 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
 template <int R, int MODE>
 int launch_scan(msc_ctx* ctx, LaunchPlan* lp) {
   auto kern = scan_kernel<R, MODE>;
-  MSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lp->smem)));
-  int occ = 0;
-  MSC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, lp->smem));
+  // attribute + occupancy query cost ~10 us per launch, which shows on sub-millisecond scans: remember the last answer
+  static size_t cached_smem = ~static_cast<size_t>(0);
+  static int cached_occ = 0, cached_dev = -1;
+  if (cached_smem != lp->smem || cached_dev != ctx->device) {
+    MSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lp->smem)));
+    MSC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_occ, kern, NT, lp->smem));
+    cached_smem = lp->smem;
+    cached_dev = ctx->device;
+  }
+  const int occ = cached_occ;
   if (occ < 1) return ctx->fail(MSC_ERR_ARG, "scan kernel does not fit on an SM");
   uint64_t grid = static_cast<uint64_t>(ctx->sm_count) * occ;
   const uint64_t need = (lp->p.ntiles + NW - 1) / NW;
