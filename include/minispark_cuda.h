@@ -208,6 +208,9 @@ MSC_API void msc_destroy(msc_ctx* ctx);
 MSC_API const char* msc_last_error(msc_ctx* ctx);
 MSC_API int msc_sync(msc_ctx* ctx);
 MSC_API int msc_get_stats(msc_ctx* ctx, msc_stats* out);
+/* the compute stream (a cudaStream_t) every call of this context is ordered on: lets the host language order its own
+ * work -- e.g. the NCCL collective between msc_scan_dense_table(ASYNC) and msc_dense_merge_compact -- without host waits */
+MSC_API int msc_stream_handle(msc_ctx* ctx, void** stream);
 /* device time of a region of library calls: start records an event on the compute stream, stop records another,
  * waits for it and returns the milliseconds in between (what bench.py brackets its K steps with) */
 MSC_API int msc_timer_start(msc_ctx* ctx);
@@ -266,13 +269,23 @@ MSC_API int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* scan, int32_t 
  * its own row counter) and the slot that tells whether a group received rows. */
 MSC_API int msc_dense_layout(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* agg_kinds, int32_t naggs,
                      int32_t* stride, int32_t* count_slot);
-/* identities + fused scan into `table` (device, ngroups * stride cells) */
+/* identities + fused scan into `table` (device, ngroups * stride cells).  flags: MSC_DENSE_EXACT = never use the
+ * register-reduction kernels (which cannot be trusted when a SUM comes out non-finite; without this flag the call
+ * checks and reruns by itself), MSC_DENSE_ASYNC = only enqueue on the compute stream: no check, no host wait --
+ * the caller looks at `nonfinite` of msc_dense_merge_compact and repeats the pass with MSC_DENSE_EXACT if set. */
+#define MSC_DENSE_EXACT 1
+#define MSC_DENSE_ASYNC 2
 MSC_API int msc_scan_dense_table(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds,
-                         int32_t naggs, void* table);
+                         int32_t naggs, void* table, int32_t flags);
 /* fold `world` tables of [gmax][stride] cells (device, rank-major) into out_table[ngroups_out][stride];
  * perm[r * gmax + g] (host) = output group of rank r's group g, or < 0.  Folds in rank order. */
 MSC_API int msc_dense_merge(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride,
                     const int32_t* agg_kinds, int32_t naggs, const int32_t* perm, int32_t ngroups_out, void* out_table);
+/* merge (perm_dev: the permutation already on the device) + compaction in one stream-ordered sequence with a single
+ * host wait at the end; scratch_table: ngroups_out * stride cells of device memory */
+MSC_API int msc_dense_merge_compact(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride,
+                            const int32_t* agg_kinds, int32_t naggs, const int32_t* perm_dev, int32_t ngroups_out,
+                            int32_t count_slot, void* scratch_table, msc_rel** out, int32_t* nonfinite);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                       int32_t naggs, int32_t count_slot, msc_rel** out);

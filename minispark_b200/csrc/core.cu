@@ -159,6 +159,12 @@ extern "C" int msc_sync(msc_ctx* ctx) {
   return MSC_OK;
 }
 
+extern "C" int msc_stream_handle(msc_ctx* ctx, void** stream) {
+  if (!ctx || !stream) return MSC_ERR_ARG;
+  *stream = ctx->stream;
+  return MSC_OK;
+}
+
 extern "C" int msc_timer_start(msc_ctx* ctx) {
   if (!ctx) return MSC_ERR_ARG;
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));

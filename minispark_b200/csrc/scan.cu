@@ -743,15 +743,20 @@ extern "C" int msc_dense_layout(msc_ctx* ctx, const msc_scan_desc* sd, const int
 }
 
 extern "C" int msc_scan_dense_table(msc_ctx* ctx, const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs,
-                                    void* table) {
+                                    void* table, int32_t flags) {
   if (!ctx || !sd || !table || ngroups <= 0) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   MSC_TRY(validate_program(ctx, sd, MODE_DENSE, agg_kinds, naggs, nullptr, 0));
   DensePlan dp;
   MSC_TRY(dense_plan(ctx, sd, agg_kinds, naggs, &dp));
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  const bool exact_only = (flags & MSC_DENSE_EXACT) != 0;
+  if (flags & MSC_DENSE_ASYNC) {  // enqueue only: the caller checks the sums after its merge (msc_dense_merge_compact)
+    bool masked = false;
+    return dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, !exact_only, static_cast<unsigned long long*>(table), &masked);
+  }
   DevTmp d_n(ctx);
   MSC_TRY(d_n.alloc(3 * sizeof(unsigned long long)));
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = exact_only ? 1 : 0; attempt < 2; ++attempt) {
     bool masked = false;
     MSC_TRY(dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, attempt == 0, static_cast<unsigned long long*>(table), &masked));
     dense_check_kernel<<<1, 32, 0, ctx->stream>>>(static_cast<const unsigned long long*>(table), ngroups, dp.stride, dense_meta(dp),
@@ -769,19 +774,29 @@ extern "C" int msc_scan_dense_table(msc_ctx* ctx, const msc_scan_desc* sd, int32
   return ctx->fail(MSC_ERR_ARG, "dense aggregate: unreachable");
 }
 
+namespace {
+int plan_for_table(msc_ctx* ctx, const int32_t* agg_kinds, int naggs, int stride, int count_slot, DensePlan* dp) {
+  if (naggs < 0 || naggs > MSC_VM_MAX_AGGS || (stride != naggs && stride != naggs + 1) || count_slot < 0 || count_slot >= stride)
+    return ctx->fail(MSC_ERR_ARG, "bad dense table layout");
+  for (int a = 0; a < naggs; ++a) {
+    dp->kinds[a] = agg_kinds[a];
+    MSC_TRY(agg_identity(ctx, agg_kinds[a], &dp->init[a]));
+  }
+  dp->kinds[naggs] = MSC_AGG_SUM_I;
+  dp->init[naggs] = 0;
+  dp->stride = stride;
+  dp->count_slot = count_slot;
+  dp->use_regvm = false;
+  return MSC_OK;
+}
+}  // namespace
+
 extern "C" int msc_dense_merge(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride, const int32_t* agg_kinds,
                                int32_t naggs, const int32_t* perm, int32_t ngroups_out, void* out_table) {
-  if (!ctx || !tables || !perm || !out_table || world <= 0 || gmax <= 0 || ngroups_out <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS ||
-      (stride != naggs && stride != naggs + 1))
+  if (!ctx || !tables || !perm || !out_table || world <= 0 || gmax <= 0 || ngroups_out <= 0)
     return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   DensePlan dp;
-  for (int a = 0; a < naggs; ++a) {
-    dp.kinds[a] = agg_kinds[a];
-    MSC_TRY(agg_identity(ctx, agg_kinds[a], &dp.init[a]));
-  }
-  dp.kinds[naggs] = MSC_AGG_SUM_I;
-  dp.init[naggs] = 0;
-  dp.stride = stride;
+  MSC_TRY(plan_for_table(ctx, agg_kinds, naggs, stride, 0, &dp));
   DevTmp d_perm(ctx);
   MSC_TRY(d_perm.alloc(sizeof(int32_t) * world * gmax));
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
@@ -796,20 +811,30 @@ extern "C" int msc_dense_merge(msc_ctx* ctx, const void* tables, int32_t world, 
   return MSC_OK;
 }
 
-extern "C" int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
-                                 int32_t naggs, int32_t count_slot, msc_rel** out) {
-  if (!ctx || !table || !out || ngroups <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS || (stride != naggs && stride != naggs + 1) ||
-      count_slot < 0 || count_slot >= stride)
+extern "C" int msc_dense_merge_compact(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride,
+                                       const int32_t* agg_kinds, int32_t naggs, const int32_t* perm_dev, int32_t ngroups_out,
+                                       int32_t count_slot, void* scratch_table, msc_rel** out, int32_t* nonfinite) {
+  if (!ctx || !tables || !perm_dev || !scratch_table || !out || !nonfinite || world <= 0 || gmax <= 0 || ngroups_out <= 0)
     return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   DensePlan dp;
-  for (int a = 0; a < naggs; ++a) {
-    dp.kinds[a] = agg_kinds[a];
-    MSC_TRY(agg_identity(ctx, agg_kinds[a], &dp.init[a]));
-  }
-  dp.kinds[naggs] = MSC_AGG_SUM_I;
-  dp.init[naggs] = 0;
-  dp.stride = stride;
-  dp.count_slot = count_slot;
+  MSC_TRY(plan_for_table(ctx, agg_kinds, naggs, stride, count_slot, &dp));
+  // no event here: ev_a still marks the start of the msc_scan_dense_table(ASYNC) this call completes
+  dense_merge_kernel<<<1, 64, 0, ctx->stream>>>(static_cast<const unsigned long long*>(tables), world, gmax, stride, perm_dev, ngroups_out,
+                                               dense_meta(dp), static_cast<unsigned long long*>(scratch_table));
+  ctx->stats.launches += 1;
+  MSC_CUDA(ctx, cudaGetLastError());
+  bool nf = false;
+  MSC_TRY(dense_compact(ctx, static_cast<const unsigned long long*>(scratch_table), ngroups_out, naggs, dp, out, &nf));
+  *nonfinite = nf ? 1 : 0;
+  note_times(ctx, true);
+  return MSC_OK;
+}
+
+extern "C" int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
+                                 int32_t naggs, int32_t count_slot, msc_rel** out) {
+  if (!ctx || !table || !out || ngroups <= 0) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  DensePlan dp;
+  MSC_TRY(plan_for_table(ctx, agg_kinds, naggs, stride, count_slot, &dp));
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
   bool nonfinite = false;
   MSC_TRY(dense_compact(ctx, static_cast<const unsigned long long*>(table), ngroups, naggs, dp, out, &nonfinite));

@@ -930,30 +930,38 @@ class _DenseMerge:
         self.local = torch.zeros(cells, dtype=torch.int64, device=dev)
         self.gathered = torch.zeros(comm.world * cells, dtype=torch.int64, device=dev)
         self.merged = torch.zeros(max(self.nglobal, 1) * self.stride, dtype=torch.int64, device=dev)
+        self.perm_dev = torch.tensor(flat, dtype=torch.int32, device=dev)
+        # the collective runs stream-ordered between the library's launches: torch sees the library's compute stream
+        stream = C.c_void_p()
+        engine.ctx.call("msc_stream_handle", C.byref(stream))
+        self.stream = torch.cuda.ExternalStream(stream.value, device=dev)
+        torch.cuda.synchronize(dev)
 
     def run(self, desc: N.ScanDesc) -> tuple[Optional[int], float]:
-        """One pass; returns (handle of the merged result relation or None when there are no groups, device ms)."""
+        """One pass; returns (handle of the merged result relation, device ms from the scan's first launch to the result).
+
+        scan (enqueued) -> all-gather of the tables -> merge + compaction, all ordered on one stream with a single host
+        wait at the end.  A non-finite SUM in the merged table -- identical on every rank, so all ranks agree -- means the
+        register-reduction kernel must not be trusted (gen_regvm.py): the pass is repeated with the exact kernel."""
         import torch  # noqa: PLC0415
         import torch.distributed as dist  # noqa: PLC0415
 
         e = self.engine
-        ms = 0.0
-        if self.nlocal > 0:
-            e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()))
-            ms += e.ctx.stats().last_kernel_ms
-        if self.nglobal == 0:
-            return None, ms
-        # the library call above ended with a stream synchronisation, so NCCL may read `local` right away
-        dist.all_gather_into_tensor(self.gathered, self.local)
-        torch.cuda.current_stream(e.device).synchronize()
-        e.ctx.call("msc_dense_merge", C.c_void_p(self.gathered.data_ptr()), e.comm.world, self.gmax, self.stride, self.kinds, self.naggs,
-                   self.perm, self.nglobal, C.c_void_p(self.merged.data_ptr()))
-        ms += e.ctx.stats().last_kernel_ms
-        out = C.c_void_p()
-        e.ctx.call("msc_dense_compact", C.c_void_p(self.merged.data_ptr()), self.nglobal, self.stride, self.kinds, self.naggs, self.count_slot,
-                   C.byref(out))
-        ms += e.ctx.stats().last_kernel_ms
-        return out.value, ms
+        flags = N.K["MSC_DENSE_ASYNC"]
+        for _attempt in range(2):
+            if self.nlocal > 0:
+                e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()), flags)
+            with torch.cuda.stream(self.stream):
+                dist.all_gather_into_tensor(self.gathered, self.local)
+            out, nonfinite = C.c_void_p(), C.c_int32()
+            e.ctx.call("msc_dense_merge_compact", C.c_void_p(self.gathered.data_ptr()), e.comm.world, self.gmax, self.stride, self.kinds,
+                       self.naggs, C.c_void_p(self.perm_dev.data_ptr()), self.nglobal, self.count_slot, C.c_void_p(self.merged.data_ptr()),
+                       C.byref(out), C.byref(nonfinite))
+            if not nonfinite.value or flags & N.K["MSC_DENSE_EXACT"]:
+                break
+            e.ctx.lib.msc_rel_free(out)
+            flags |= N.K["MSC_DENSE_EXACT"]
+        return out.value, e.ctx.stats().last_kernel_ms
 
 
 class PreparedAggregate:

@@ -123,7 +123,10 @@ _SIGNATURES = {
     "msc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "msc_dense_layout": (C.c_int, [C.c_void_p, C.POINTER(ScanDesc), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32)]),
-    "msc_scan_dense_table": (C.c_int, [C.c_void_p, C.POINTER(ScanDesc), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
+    "msc_scan_dense_table": (C.c_int, [C.c_void_p, C.POINTER(ScanDesc), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32]),
+    "msc_dense_merge_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                          C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "msc_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_dense_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                   C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
     "msc_dense_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
