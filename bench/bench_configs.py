@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Timings of BASELINE.json configs 4 and 5 on one B200 (they are parity cases for bench.py; this prints numbers).
+
+    python bench/bench_configs.py --sf 2 [--reps 5]
+
+config 4: SELECT l_orderkey, SUM(l_quantity), AVG(l_extendedprice) FROM lineitem GROUP BY l_orderkey   (hash aggregate)
+config 5: orders JOIN lineitem ON o_orderkey = l_orderkey WHERE o_orderdate BETWEEN .. AND l_shipmode LIKE '%AIR%'
+          GROUP BY o_orderpriority  (hash join with late materialisation, then a dense aggregate)
+Tables are device resident when the clock starts (first execution ingests them); one JSON line per config.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "tests", ROOT / "bench"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+os.environ["TZ"] = "UTC"
+time.tzset()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sf", type=float, default=2.0)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    import cases
+    import gen_tpch
+    from minispark_b200 import CudaExecutionEngine
+
+    base = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
+    folder = base / f"minispark_b200_cfg_{os.getuid()}"
+    folder.mkdir(parents=True, exist_ok=True)
+    lineitem, orders = folder / f"lineitem_sf{args.sf:g}.bin", folder / f"orders_sf{args.sf:g}.bin"
+    if not lineitem.exists():
+        gen_tpch.write_table(lineitem, "lineitem", sf=args.sf, columns=["l_orderkey", "l_quantity", "l_extendedprice", "l_shipmode"])
+    if not orders.exists():
+        gen_tpch.write_table(orders, "orders", sf=args.sf, columns=["o_orderkey", "o_orderdate", "o_orderpriority"])
+    ns = cases.namespace()
+
+    def config4(e):  # noqa: ANN001, ANN202
+        return ns.DataFrame(e).table(str(lineitem)).group_by(ns.Col("l_orderkey")).agg(
+            ns.F.sum(ns.Col("l_quantity")).alias("q"), ns.F.avg(ns.Col("l_extendedprice")).alias("p"))
+
+    def config5(e):  # noqa: ANN001, ANN202
+        o = ns.DataFrame(e).table(str(orders)).alias("o")
+        l = ns.DataFrame().table(str(lineitem)).alias("l")
+        return (o.join(l, on=ns.Col("o.o_orderkey") == ns.Col("l.l_orderkey"), how="inner")
+                .filter(ns.Col("o.o_orderdate").between("1994-01-01", "1994-12-31"))
+                .filter(ns.Col("l.l_shipmode").like("%AIR%"))
+                .group_by(ns.Col("o.o_orderpriority")).agg(ns.F.count(), ns.F.sum(ns.Col("l.l_extendedprice")).alias("rev")))
+
+    with CudaExecutionEngine(device=0, shard=(0, 1)) as e:
+        for name, build in (("config4_high_cardinality_group_by", config4), ("config5_join_filter_like_group_by", config5)):
+            task = build(e).task
+            times, rows_out = [], 0
+            for i in range(args.reps + 1):
+                t0 = time.perf_counter()
+                rel, _ = e.execute_to_device(task)
+                e.ctx.call("msc_sync")
+                dt = time.perf_counter() - t0
+                rows_out = rel.nrows
+                stats = dict(e.last_stats)
+                e.release_query()
+                if i:
+                    times.append(dt)
+            nl = e._tables[str(lineitem)].nrows
+            med = statistics.median(times)
+            print(json.dumps({"config": name, "sf": args.sf, "lineitem_rows": nl, "result_rows": rows_out, "ms": round(1e3 * med, 3),
+                              "lineitem_rows_per_s": nl / med, "passes_ms": [round(1e3 * t, 2) for t in times],
+                              "last_kernel_ms": stats.get("kernel_ms"), "agg_mode": stats.get("agg_mode")}), flush=True)
+    if os.environ.get("MSC_BENCH_KEEP") is None:
+        lineitem.unlink(missing_ok=True)
+        orders.unlink(missing_ok=True)
+
+
+if __name__ == "__main__":
+    main()
