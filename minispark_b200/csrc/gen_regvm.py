@@ -64,22 +64,26 @@ def col_addr(lane_bytes: int, arg: str = "a1") -> list[str]:
     return [f"mad.lo.u32 ad, {arg}, {COL_UNIT}, sbl{lane_bytes};"]
 
 
-def load_rows(kind: str, dst: str, arg: str = "a1") -> list[str]:
-    """Load this lane's 8 rows of a staged column into registers <dst>_0..7 as 64-bit values."""
+def load_rows(kind: str, dst: str, arg: str = "a1", off: int = 0) -> list[str]:
+    """Load this lane's 8 rows of a staged column (`off` bytes past the operand's column) into registers <dst>_0..7 as
+    64-bit values."""
     if kind in ("F32", "I32F", "I32"):
         half = 128 * 4
         if kind == "F32":
-            out = col_addr(16, arg) + ["ld.shared.v4.f32 {f0, f1, f2, f3}, [ad];", f"ld.shared.v4.f32 {{f4, f5, f6, f7}}, [ad+{half}];"]
+            out = col_addr(16, arg) + [f"ld.shared.v4.f32 {{f0, f1, f2, f3}}, [ad+{off}];", f"ld.shared.v4.f32 {{f4, f5, f6, f7}}, [ad+{off + half}];"]
             return out + [f"cvt.f64.f32 {dst}_{r}, f{r};" for r in ROWS]
-        out = col_addr(16, arg) + ["ld.shared.v4.s32 {i0, i1, i2, i3}, [ad];", f"ld.shared.v4.s32 {{i4, i5, i6, i7}}, [ad+{half}];"]
+        out = col_addr(16, arg) + [f"ld.shared.v4.s32 {{i0, i1, i2, i3}}, [ad+{off}];", f"ld.shared.v4.s32 {{i4, i5, i6, i7}}, [ad+{off + half}];"]
         cvt = "cvt.rn.f64.s32" if kind == "I32F" else "cvt.s64.s32"
         return out + [f"{cvt} {dst}_{r}, i{r};" for r in ROWS]
     if kind in ("F64", "I64"):
         half = 128 * 8
-        return col_addr(32, arg) + [f"ld.shared.v2.b64 {{{dst}_0, {dst}_1}}, [ad];", f"ld.shared.v2.b64 {{{dst}_2, {dst}_3}}, [ad+16];",
-                                    f"ld.shared.v2.b64 {{{dst}_4, {dst}_5}}, [ad+{half}];",
-                                    f"ld.shared.v2.b64 {{{dst}_6, {dst}_7}}, [ad+{half + 16}];"]
+        return col_addr(32, arg) + [f"ld.shared.v2.b64 {{{dst}_0, {dst}_1}}, [ad+{off}];", f"ld.shared.v2.b64 {{{dst}_2, {dst}_3}}, [ad+{off + 16}];",
+                                    f"ld.shared.v2.b64 {{{dst}_4, {dst}_5}}, [ad+{off + half}];",
+                                    f"ld.shared.v2.b64 {{{dst}_6, {dst}_7}}, [ad+{off + half + 16}];"]
     raise ValueError(kind)
+
+
+TILE_BYTES = {"F32": 256 * 4, "I32F": 256 * 4, "F64": 256 * 8}  # one column's bytes in a warp tile
 
 
 def const_load(reg: str, arg: str) -> list[str]:
@@ -92,11 +96,12 @@ def build(NG: int) -> list[dict]:
     masked = NG > 0
 
     def add(name: str, body: list[str], a1: int = A_NONE, a2: int = A_NONE, phys: int = -1, delta: int = 0, depth: int = -1,
-            agg: int = -1, flags: int = 0) -> None:
-        """depth: stack depth required before the instruction (-1: any); agg: accumulator kind the slot operand must have."""
+            agg: int = -1, flags: int = 0, span: int = 1) -> None:
+        """depth: stack depth required before the instruction (-1: any); agg: accumulator kind the slot operand must have;
+        span: the column / slot operands each name `span` consecutive columns / slots."""
         if masked and (flags & F_GENERIC_ONLY):
             body = ["trap;"]  # the host never sends such a program to a masked variant
-        handlers.append(dict(name=name, body=body, a1=a1, a2=a2, phys=phys, delta=delta, depth=depth, agg=agg, flags=flags))
+        handlers.append(dict(name=name, body=body, a1=a1, a2=a2, phys=phys, delta=delta, depth=depth, agg=agg, flags=flags, span=span))
 
     # ---- END -------------------------------------------------------------------------------------
     add("END", ["bra.uni RV_DONE;"])
@@ -158,10 +163,10 @@ def build(NG: int) -> list[dict]:
             add(f"{name}_D{d}", [f"{op}.f64 s{a}_{r}, s{a}_{r}, s{b}_{r};" for r in ROWS], A_NONE, A_NONE, -1, -1, d)
 
     # ---- aggregation -------------------------------------------------------------------------------
-    def agg_rmw(kind: str, val: str, slot_arg: str = "a1") -> list[str]:
+    def agg_rmw(kind: str, val: str, slot_arg: str = "a1", slot_off: int = 0) -> list[str]:
         """Generic variant: read-modify-write of the lane's private accumulator (slot, group of row r) for the 8 rows,
         in row order -- two rows of one lane may share a group, so the updates must not be reordered."""
-        body = [f"mad.lo.u32 base, {slot_arg}, {SLOT_STRIDE}, accb;"]
+        body = [f"mad.lo.u32 base, {slot_arg}, {SLOT_STRIDE}, accb;"] + ([f"add.u32 base, base, {slot_off};"] if slot_off else [])
         for r in ROWS:
             v = val.format(r=r)
             body.append(f"add.u32 ad2, base, go{r};")
@@ -179,7 +184,7 @@ def build(NG: int) -> list[dict]:
                 body += ["ld.shared.u64 xi, [ad2];", f"setp.{cmp_}.s64 q, {v}, xi;", f"@q st.shared.u64 [ad2], {v};"]
         return body
 
-    def agg_masked(kind: str, val: str, slot_arg: str = "a1") -> list[str]:
+    def agg_masked(kind: str, val: str, slot_arg: str = "a1", slot_off: int = 0) -> list[str]:
         """Masked variant: per-group sums of the lane's 8 rows in registers (row order, one chain per group), then one
         update per group; the NG accumulator addresses are distinct, so loads, adds and stores are batched."""
         body = []
@@ -202,6 +207,8 @@ def build(NG: int) -> list[dict]:
             for g in range(NG):
                 body.append(f"cvt.rzi.s64.f64 n{g}, p{g};")
         body.append(f"mad.lo.u32 base, {slot_arg}, {SLOT_STRIDE}, accb;")
+        if slot_off:
+            body.append(f"add.u32 base, base, {slot_off};")
         for g in range(NG):
             body.append(f"mad.lo.u32 ag{g}, gstride, {g}, base;")
         if kind == "SUMF":
@@ -214,8 +221,8 @@ def build(NG: int) -> list[dict]:
             body += [f"st.shared.u64 [ag{g}], q{g}i;" for g in range(NG)]
         return body
 
-    def agg(kind: str, val: str, slot_arg: str = "a1") -> list[str]:
-        return agg_masked(kind, val, slot_arg) if masked and kind in ("SUMF", "COUNT") else agg_rmw(kind, val, slot_arg)
+    def agg(kind: str, val: str, slot_arg: str = "a1", slot_off: int = 0) -> list[str]:
+        return agg_masked(kind, val, slot_arg, slot_off) if masked and kind in ("SUMF", "COUNT") else agg_rmw(kind, val, slot_arg, slot_off)
 
     for d in range(1, DEPTH + 1):
         top = d - 1
@@ -251,6 +258,14 @@ def build(NG: int) -> list[dict]:
 
     for kind, phys in float_cols:  # fused load + SUM: a1 = column, a2 = slot
         add(f"AGGCOL_{kind}", load_rows(kind, "x") + agg("SUMF", "x_{r}", "a2"), A_COL, A_SLOT, PHYS[phys], agg=AGG_KIND["SUMF"])
+    # SUM of 2..4 adjacent columns into adjacent slots in one dispatch (SUM(a), SUM(b), SUM(c) of one query): fewer
+    # dispatches, and independent load / convert / reduce sequences for the scheduler to overlap
+    for n in (2, 3, 4):
+        for kind, phys in float_cols:
+            body = []
+            for j in range(n):
+                body += load_rows(kind, "x", off=j * TILE_BYTES[kind]) + agg("SUMF", "x_{r}", "a2", j * SLOT_STRIDE)
+            add(f"AGGCOL{n}_{kind}", body, A_COL, A_SLOT, PHYS[phys], agg=AGG_KIND["SUMF"], span=n)
     return handlers
 
 
@@ -268,7 +283,7 @@ def ptx(NG: int) -> str:
         ".reg .b32 " + ", ".join(f"i{r}" for r in ROWS) + ";",
         ".reg .b32 " + ", ".join(f"c{r}" for r in ROWS) + ";",
         ".reg .b32 w8, w9, w10, w11;",
-        ".reg .b32 sb, sbl4, sbl8, sbl16, sbl32, accb, pc, cstb, lane, ng, gstride, trash, vm, w, wn, wnn, h, a1, a2, ad, ad2, base, tb;",
+        ".reg .b32 sb, sbl4, sbl8, sbl16, sbl32, accb, pc, cstb, lane, ng, gstride, trash, vm, wn, h, a1, a2, ad, ad2, base, tb;",
         ".reg .pred q, qv;",
     ]
     if NG > 0:
@@ -281,16 +296,17 @@ def ptx(NG: int) -> str:
         regs.append(".reg .b32 " + ", ".join(f"go{r}" for r in ROWS) + ";")
     lines = ["{"] + regs
     lines += ["mov.u32 sb, %0;", "mov.u32 accb, %1;", "mov.u32 pc, %2;", "mov.u32 cstb, %3;", "mov.u32 lane, %4;",
-              "mov.u32 ng, %5;", "mov.u32 gstride, %6;", "mov.u32 vm, %7;", "ld.shared.u32 wn, [pc];", "ld.shared.u32 wnn, [pc+4];"]
+              "mov.u32 ng, %5;", "mov.u32 gstride, %6;", "mov.u32 vm, %7;", "ld.shared.u32 wn, [pc];"]
     lines += [f"mad.lo.u32 sbl{k}, lane, {k}, sb;" for k in (4, 8, 16, 32)]
     if NG == 0:
         lines += ["mul.lo.u32 trash, ng, gstride;"] + [f"mov.u32 go{r}, trash;" for r in ROWS]
     # stack slots / temporaries / masks are written before they are read (the host validates depths and GROUP-before-aggregate)
     lines.append("RV_TABLE: .branchtargets " + ", ".join(f"RV_H{i}" for i in range(len(handlers))) + ";")
-    # dispatch: instruction words are fetched two instructions ahead, so the shared-memory latency is covered even by
-    # the shortest handlers (prof_r1h: 4 % of all stall samples sat on the one-ahead word)
-    lines += ["RV_NEXT:", "mov.b32 w, wn;", "mov.b32 wn, wnn;", "ld.shared.u32 wnn, [pc+8];", "add.u32 pc, pc, 4;", "and.b32 h, w, 255;",
-              "bfe.u32 a1, w, 8, 8;", "bfe.u32 a2, w, 16, 8;", "brx.idx h, RV_TABLE;"]
+    # dispatch: the word of the NEXT instruction is already in wn (its shared-memory latency overlapped the previous
+    # handler); its fields are extracted, then wn is reloaded in place -- no register moves (prof_r1j: the moves of a
+    # two-deep prefetch cost 26 of 794 instructions per tile and did not remove the wait, which only moved onto them)
+    lines += ["RV_NEXT:", "and.b32 h, wn, 255;", "bfe.u32 a1, wn, 8, 8;", "bfe.u32 a2, wn, 16, 8;", "ld.shared.u32 wn, [pc+4];",
+              "add.u32 pc, pc, 4;", "brx.idx h, RV_TABLE;"]
     for i, hnd in enumerate(handlers):
         lines.append(f"RV_H{i}:  // {hnd['name']}")
         lines += [ln for ln in hnd["body"] if ln]
@@ -308,8 +324,8 @@ def header() -> str:
     handlers = build(0)
     assert len(handlers) <= 256
     for ng in range(1, MAX_NG + 1):
-        assert [(h["name"], h["a1"], h["a2"], h["phys"], h["delta"], h["depth"], h["agg"], h["flags"]) for h in build(ng)] == \
-               [(h["name"], h["a1"], h["a2"], h["phys"], h["delta"], h["depth"], h["agg"], h["flags"]) for h in handlers]
+        meta = lambda hs: [tuple(h[k] for k in ("name", "a1", "a2", "phys", "delta", "depth", "agg", "flags", "span")) for h in hs]  # noqa: E731
+        assert meta(build(ng)) == meta(handlers)
     lines = ["// GENERATED by gen_regvm.py -- do not edit.  Handler ids and operand metadata of the regvm interpreter.",
              "#pragma once", f"#define MSC_RV_ROWS {R}", f"#define MSC_RV_MAX_DEPTH {DEPTH}", f"#define MSC_RV_MAX_TEMPS {NTEMPS}",
              f"#define MSC_RV_COL_UNIT {COL_UNIT}", f"#define MSC_RV_MAX_NG {MAX_NG}", f"#define MSC_RV__COUNT {len(handlers)}"]
@@ -317,10 +333,10 @@ def header() -> str:
         lines.append(f"#define MSC_RV_{hnd['name']} {i}")
     lines += ["#define MSC_RV_ARG_NONE 0", "#define MSC_RV_ARG_COL 1", "#define MSC_RV_ARG_CONST 2", "#define MSC_RV_ARG_SLOT 3",
               f"#define MSC_RV_F_FILTER {F_FILTER}", f"#define MSC_RV_F_GROUP {F_GROUP}", f"#define MSC_RV_F_GENERIC_ONLY {F_GENERIC_ONLY}",
-              "struct msc_rv_info { const char* name; signed char a1, a2, phys, delta, depth, agg, flags; };",
+              "struct msc_rv_info { const char* name; signed char a1, a2, phys, delta, depth, agg, flags, span; };",
               "static const msc_rv_info MSC_RV_INFO[MSC_RV__COUNT] = {"]
     for hnd in handlers:
-        lines.append(f'  {{"{hnd["name"]}", {hnd["a1"]}, {hnd["a2"]}, {hnd["phys"]}, {hnd["delta"]}, {hnd["depth"]}, {hnd["agg"]}, {hnd["flags"]}}},')
+        lines.append(f'  {{"{hnd["name"]}", {hnd["a1"]}, {hnd["a2"]}, {hnd["phys"]}, {hnd["delta"]}, {hnd["depth"]}, {hnd["agg"]}, {hnd["flags"]}, {hnd["span"]}}},')
     lines.append("};")
     return "\n".join(lines) + "\n"
 

@@ -464,8 +464,14 @@ int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, cons
     for (int k = 0; k < 2; ++k) {
       switch (kinds[k]) {
         case MSC_RV_ARG_COL:
-          if (static_cast<int>(a[k]) >= sd->nstaged || sd->staged[a[k]].phys != info.phys)
-            return ctx->fail(MSC_ERR_ARG, "regvm: column operand has the wrong physical type");
+          // a spanning handler reads `span` columns at fixed strides: they must be staged back to back
+          for (int j = 0; j < info.span; ++j) {
+            const int c = static_cast<int>(a[k]) + j;
+            if (c >= sd->nstaged || sd->staged[c].phys != info.phys)
+              return ctx->fail(MSC_ERR_ARG, "regvm: column operand has the wrong physical type");
+            if (p.staged[c].smem_off != p.staged[a[k]].smem_off + j * p.staged[a[k]].tile_bytes)
+              return ctx->fail(MSC_ERR_ARG, "regvm: spanned columns are not adjacent in the stage");
+          }
           a[k] = p.staged[a[k]].smem_off / MSC_RV_COL_UNIT;
           if (a[k] > 0xff) return ctx->fail(MSC_ERR_ARG, "regvm: stage too large");
           break;
@@ -473,7 +479,9 @@ int build_regvm(msc_ctx* ctx, const msc_scan_desc* sd, const ScanParams& p, cons
           if (static_cast<int>(a[k]) >= sd->nconsts) return ctx->fail(MSC_ERR_ARG, "regvm: bad constant");
           break;
         case MSC_RV_ARG_SLOT:
-          if (static_cast<int>(a[k]) >= naggs || agg_kinds[a[k]] != info.agg) return ctx->fail(MSC_ERR_ARG, "regvm: accumulator kind mismatch");
+          for (int j = 0; j < info.span; ++j)
+            if (static_cast<int>(a[k]) + j >= naggs || agg_kinds[a[k] + j] != info.agg)
+              return ctx->fail(MSC_ERR_ARG, "regvm: accumulator kind mismatch");
           if (!grouped) return ctx->fail(MSC_ERR_ARG, "regvm: aggregate before GROUP");
           break;
         default: a[k] = 0; break;

@@ -835,14 +835,18 @@ class AggregateProgram:
 def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, aggs: Sequence[tuple[str, Expr]]) -> AggregateProgram:
     b = ProgramBuilder(resolver)
     norm = [(k, EConst(INT, 1) if k == "count" else (EBin(INT, "add", e, EConst(INT, 0)) if e.type == BOOL else e)) for k, e in aggs]
+    # accumulator slots: plain SUM(column) aggregates first and next to each other, so that the register interpreter
+    # can take runs of them in one instruction (AGGCOL<n>, gen_regvm.py); the slot order is internal (slot_of maps back)
+    def plain_sum(key: tuple[str, Expr]) -> bool:
+        kind, e = key
+        return kind == "sum" and e.type == FLOAT and (isinstance(e, EInput) or (isinstance(e, ECast) and isinstance(e.child, EInput)))
+
     unique: dict[tuple[str, Expr], int] = {}
-    slot_of: list[int] = []
-    for key in norm:
-        if key not in unique:
-            if len(unique) >= K["MSC_VM_MAX_AGGS"]:
-                raise LoweringError("too many aggregates in one GROUP BY")
-            unique[key] = len(unique)
-        slot_of.append(unique[key])
+    for key in sorted(dict.fromkeys(norm), key=lambda k: 0 if plain_sum(k) else 1):
+        if len(unique) >= K["MSC_VM_MAX_AGGS"]:
+            raise LoweringError("too many aggregates in one GROUP BY")
+        unique[key] = len(unique)
+    slot_of = [unique[key] for key in norm]
     count_key = ("count", EConst(INT, 1))
     if REGVM_ENABLED and count_key not in unique and len(unique) < K["MSC_VM_MAX_AGGS"]:
         unique[count_key] = len(unique)  # the regvm kernel tells present groups by their row count
@@ -851,6 +855,10 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
     for f in filters:
         b.materialize(f, DST_FILTER)
     group_dict = b.materialize(group, DST_GROUP)
+    for (kind, e) in unique:  # stage the plain-SUM columns back to back (a run needs adjacent stage slots)
+        if plain_sum((kind, e)):
+            leaf = e if isinstance(e, EInput) else e.child
+            b.r.binding(leaf.index)
     kinds: list[int] = []
     for (kind, e), slot in unique.items():
         if kind == "count":
@@ -1029,11 +1037,36 @@ def compile_regvm(b: "ProgramBuilder", filters: Sequence[Expr], group: Expr, uni
             temps[e] = len(temps)
             emit(f"TEE{temps[e]}_D{d + 1}")
 
-    for (kind, e), slot in unique.items():
+    def plain_sum_leaf(kind: str, e: Expr) -> Optional[tuple[str, int]]:
+        if kind != "sum" or e.type != FLOAT or e in temps:
+            return None
+        if isinstance(e, EInput) or (isinstance(e, ECast) and isinstance(e.child, EInput)):
+            return float_leaf(e)
+        return None
+
+    items = list(unique.items())
+    skip = 0
+    for pos, ((kind, e), slot) in enumerate(items):
+        if skip:
+            skip -= 1
+            continue
         if kind == "count":
             emit("COUNT", slot)
             continue
         is_float = e.type == FLOAT
+        first = plain_sum_leaf(kind, e)
+        if first is not None:  # a run of SUM(column) over adjacent stage slots into adjacent accumulators: one instruction
+            run = 1
+            while run < 4 and pos + run < len(items):
+                (k2, e2), s2 = items[pos + run]
+                nxt = plain_sum_leaf(k2, e2)
+                if nxt is None or nxt[0] != first[0] or nxt[1] != first[1] + run or s2 != slot + run:
+                    break
+                run += 1
+            if run > 1 and f"AGGCOL{run}_{first[0]}" in RV:
+                emit(f"AGGCOL{run}_{first[0]}", first[1], slot)
+                skip = run - 1
+                continue
         if kind == "sum" and is_float and e not in temps:
             if isinstance(e, EInput):
                 bd = column(e)
