@@ -49,6 +49,7 @@ NTEMPS = 2
 MAX_NG = 4             # masked variants exist for 1..MAX_NG groups
 SLOT_STRIDE = 128 * 8  # bytes between accumulator slots: NT lanes x 8 B
 COL_UNIT = 128         # column operands address the warp stage in units of 128 bytes
+TAIL_DISPATCH = False  # True: replicate the dispatch at the end of every handler (threaded code); measured no gain (0.502 vs 0.495 ms), 4x the code
 
 # operand kinds for the host-side validator
 A_NONE, A_COL, A_CONST, A_SLOT = 0, 1, 2, 3
@@ -305,13 +306,16 @@ def ptx(NG: int) -> str:
     # dispatch: the word of the NEXT instruction is already in wn (its shared-memory latency overlapped the previous
     # handler); its fields are extracted, then wn is reloaded in place -- no register moves (prof_r1j: the moves of a
     # two-deep prefetch cost 26 of 794 instructions per tile and did not remove the wait, which only moved onto them)
-    lines += ["RV_NEXT:", "and.b32 h, wn, 255;", "bfe.u32 a1, wn, 8, 8;", "bfe.u32 a2, wn, 16, 8;", "ld.shared.u32 wn, [pc+4];",
-              "add.u32 pc, pc, 4;", "brx.idx h, RV_TABLE;"]
+    dispatch = ["and.b32 h, wn, 255;", "bfe.u32 a1, wn, 8, 8;", "bfe.u32 a2, wn, 16, 8;", "ld.shared.u32 wn, [pc+4];",
+                "add.u32 pc, pc, 4;", "brx.idx h, RV_TABLE;"]
+    lines += dispatch
     for i, hnd in enumerate(handlers):
         lines.append(f"RV_H{i}:  // {hnd['name']}")
         lines += [ln for ln in hnd["body"] if ln]
         if hnd["name"] != "END":
-            lines.append("bra.uni RV_NEXT;")
+            # threaded code: every handler ends with its own copy of the dispatch, so the scheduler can start the
+            # next instruction's decode and jump-table load while this handler's arithmetic is still in flight
+            lines += dispatch if TAIL_DISPATCH else ["bra.uni RV_NEXT;"]
     lines += ["RV_DONE:", "}"]
     out = []
     for ln in lines:
