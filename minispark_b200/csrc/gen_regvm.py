@@ -308,7 +308,7 @@ def ptx(NG: int) -> str:
     # two-deep prefetch cost 26 of 794 instructions per tile and did not remove the wait, which only moved onto them)
     dispatch = ["and.b32 h, wn, 255;", "bfe.u32 a1, wn, 8, 8;", "bfe.u32 a2, wn, 16, 8;", "ld.shared.u32 wn, [pc+4];",
                 "add.u32 pc, pc, 4;", "brx.idx h, RV_TABLE;"]
-    lines += dispatch
+    lines += ["RV_NEXT:"] + dispatch
     for i, hnd in enumerate(handlers):
         lines.append(f"RV_H{i}:  // {hnd['name']}")
         lines += [ln for ln in hnd["body"] if ln]
