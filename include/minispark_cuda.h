@@ -181,11 +181,15 @@ typedef struct msc_scan_desc {
   const void* luts[MSC_VM_MAX_LUTS];
   /* Optional second encoding of the SAME query for the register-resident interpreter (dense
    * aggregate scans only; minispark_b200/csrc/gen_regvm.py, regvm_handlers.h): one u32 per
-   * instruction = handler | a1 << 8 | a2 << 20, column operands given as staged slots.  When present
+   * instruction = handler | a1 << 8 | a2 << 16, column operands given as staged slots.  When present
    * and valid the library runs it instead of `code`; ncode2 = 0 means "not available". */
   int32_t ncode2;
   int32_t count_slot2; /* accumulator that code2 increments once per surviving row (its COUNT), or -1 */
   uint32_t code2[MSC_VM_MAX_CODE2];
+  /* Optional: the row count lives on the device (a relation still pending, see msc_rel_settle).  `nrows` is then
+   * an upper bound used for launch geometry and allocation; msc_scan_project returns a pending relation without
+   * waiting for the device. */
+  const uint64_t* nrows_dev;
 } msc_scan_desc;
 
 typedef struct msc_stats {
@@ -244,6 +248,13 @@ MSC_API int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, int3
 MSC_API int msc_rel_info(msc_rel* r, uint64_t* nrows, int32_t* ncols);
 MSC_API int msc_rel_col(msc_rel* r, int32_t col, void** dev_ptr, int32_t* phys);
 MSC_API void msc_rel_free(msc_rel* r);
+/* Pending relations.  The *_async entry points and msc_scan_project with scan->nrows_dev enqueue their work and
+ * return a relation whose row count is still on the device (msc_rel_info reports the upper bound it was allocated
+ * for).  msc_rel_nrows_dev gives that device word for the next scan's nrows_dev; msc_rel_settle waits ONCE for all
+ * listed relations, fixes their row counts, reports the device error word and whether an aggregate among them
+ * produced a non-finite SUM.  A chain scan-aggregate -> final projection thus costs one host wait, not three. */
+MSC_API int msc_rel_nrows_dev(msc_rel* r, const uint64_t** nrows_dev);
+MSC_API int msc_rel_settle(msc_ctx* ctx, msc_rel* const* rels, int32_t nrels, int32_t* nonfinite);
 /* pointers and physical types of all columns in one call (cols[ncols], caller-owned) */
 MSC_API int msc_rel_cols(msc_rel* r, msc_colbind* cols, int32_t ncols);
 /* new relation of `nrows` rows with zero-initialised, tile-padded columns of the given physical types
@@ -286,6 +297,12 @@ MSC_API int msc_dense_merge(msc_ctx* ctx, const void* tables, int32_t world, int
 MSC_API int msc_dense_merge_compact(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride,
                             const int32_t* agg_kinds, int32_t naggs, const int32_t* perm_dev, int32_t ngroups_out,
                             int32_t count_slot, void* scratch_table, msc_rel** out, int32_t* nonfinite);
+/* the same without the host wait: returns a pending relation (msc_rel_settle) */
+MSC_API int msc_dense_merge_compact_async(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride,
+                                  const int32_t* agg_kinds, int32_t naggs, const int32_t* perm_dev, int32_t ngroups_out,
+                                  int32_t count_slot, void* scratch_table, msc_rel** out);
+MSC_API int msc_dense_compact_async(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
+                            int32_t naggs, int32_t count_slot, msc_rel** out);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                       int32_t naggs, int32_t count_slot, msc_rel** out);

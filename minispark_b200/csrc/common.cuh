@@ -101,8 +101,11 @@ struct msc_col {
 
 struct msc_rel {
   msc_ctx* ctx = nullptr;
-  uint64_t nrows = 0;
+  uint64_t nrows = 0;  // while `pending`: the upper bound the columns were allocated for
   std::vector<msc_col> cols;
+  // pending relation: d_meta (device, owned) = {row count, 1 if a SUM_F came out non-finite, device error word}
+  unsigned long long* d_meta = nullptr;
+  bool pending = false;
 };
 
 // RAII temporary device buffer (freed stream-ordered on scope exit).

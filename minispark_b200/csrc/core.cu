@@ -250,7 +250,37 @@ extern "C" void msc_rel_free(msc_rel* r) {
   if (!r) return;
   for (auto& c : r->cols)
     if (c.owned && c.data) msc_free(r->ctx, c.data, c.bytes);
+  if (r->d_meta) msc_free(r->ctx, r->d_meta, 3 * sizeof(unsigned long long));
   delete r;
+}
+
+extern "C" int msc_rel_nrows_dev(msc_rel* r, const uint64_t** nrows_dev) {
+  if (!r || !nrows_dev || !r->d_meta) return MSC_ERR_ARG;
+  *nrows_dev = reinterpret_cast<const uint64_t*>(r->d_meta);
+  return MSC_OK;
+}
+
+extern "C" int msc_rel_settle(msc_ctx* ctx, msc_rel* const* rels, int32_t nrels, int32_t* nonfinite) {
+  if (!ctx || (nrels && !rels) || nrels < 0 || nrels > 5) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  unsigned long long* h = ctx->h_scratch;  // 16 pinned words: 3 per relation
+  for (int i = 0; i < nrels; ++i)
+    if (rels[i] && rels[i]->pending)
+      MSC_CUDA(ctx, cudaMemcpyAsync(h + 3 * i, rels[i]->d_meta, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int err = 0, nf = 0;
+  for (int i = 0; i < nrels; ++i) {
+    if (!rels[i] || !rels[i]->pending) continue;
+    rels[i]->nrows = h[3 * i];
+    nf |= h[3 * i + 1] != 0;
+    err |= static_cast<int>(h[3 * i + 2]);
+    rels[i]->pending = false;
+  }
+  if (nonfinite) *nonfinite = nf;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
+  return msc_device_error_rc(ctx, err);
 }
 
 extern "C" int msc_rel_alloc(msc_ctx* ctx, uint64_t nrows, const int32_t* phys, int32_t ncols, msc_rel** out) {

@@ -4,6 +4,7 @@
 // scan_inst_*.cu so the specialisations compile in parallel.
 #define MSCAN_DECL_ONLY  // the kernel is instantiated in scan_inst_*.cu
 #include <algorithm>
+#include <chrono>
 
 #include "scan_kernel.cuh"
 #include "scan_regvm.h"
@@ -51,6 +52,15 @@ __global__ void dense_finalize_kernel(const unsigned long long* table, int ngrou
   out_n[0] = n;
   out_n[1] = nonfinite;  // a masked regvm variant must not be trusted then (v * 0.0 = NaN leaks across groups)
   out_n[2] = static_cast<unsigned long long>(*err);  // the device error word rides along with the group count
+  *err = 0;
+}
+
+// {row count, 0, device error word (fetched and cleared)} of a pending relation
+__global__ void pending_meta_kernel(const unsigned long long* count, unsigned long long* meta, int* err) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  meta[0] = *count;
+  meta[1] = 0;
+  meta[2] = static_cast<unsigned long long>(*err);
   *err = 0;
 }
 
@@ -664,17 +674,17 @@ int dense_scan_into(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, const in
 }
 
 // compact `table` into a relation: group id (U32) + the first naggs accumulators of every group that received rows.
-// One host synchronisation; reports a non-finite SUM_F and the device error word along with the group count.
+// Synchronous form: one host wait; reports a non-finite SUM_F and the device error word along with the group count.
+// async: nothing is waited for -- the relation comes back pending (its counts stay in rel->d_meta, msc_rel_settle).
 int dense_compact(msc_ctx* ctx, const unsigned long long* table, int ngroups, int naggs, const DensePlan& dp, msc_rel** out,
-                  bool* nonfinite) {
-  DevTmp d_n(ctx);
-  MSC_TRY(d_n.alloc(3 * sizeof(unsigned long long)));
-  msc_rel* rel = new_rel(ctx, 0);
+                  bool* nonfinite, bool async = false) {
+  msc_rel* rel = new_rel(ctx, async ? ngroups : 0);
   int physes[MSC_VM_MAX_AGGS + 1];
   physes[0] = MSC_P_U32;
   for (int a = 0; a < naggs; ++a)
     physes[1 + a] = (dp.kinds[a] == MSC_AGG_SUM_F || dp.kinds[a] == MSC_AGG_MIN_F || dp.kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64;
-  const int rc = add_cols(ctx, rel, physes, 1 + naggs, ngroups);
+  int rc = add_cols(ctx, rel, physes, 1 + naggs, ngroups);
+  if (rc == MSC_OK) rc = msc_alloc(ctx, 3 * sizeof(unsigned long long), reinterpret_cast<void**>(&rel->d_meta));
   if (rc != MSC_OK) {
     msc_rel_free(rel);
     return rc;
@@ -682,11 +692,16 @@ int dense_compact(msc_ctx* ctx, const unsigned long long* table, int ngroups, in
   DenseMeta meta = dense_meta(dp);
   for (int a = 0; a < naggs; ++a) meta.out_acc[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
   dense_finalize_kernel<<<1, 32, 0, ctx->stream>>>(table, ngroups, dp.stride, naggs, dp.count_slot, meta,
-                                                  static_cast<uint32_t*>(rel->cols[0].data), d_n.as<unsigned long long>(), ctx->d_err);
+                                                  static_cast<uint32_t*>(rel->cols[0].data), rel->d_meta, ctx->d_err);
   ctx->stats.launches += 1;
+  if (async) {
+    rel->pending = true;
+    *out = rel;
+    return MSC_OK;
+  }
   cudaEventRecord(ctx->ev_b, ctx->stream);
   unsigned long long* n = ctx->h_scratch;  // pinned: a plain stack buffer would make the copy synchronous twice over
-  if (cudaMemcpyAsync(n, d_n.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+  if (cudaMemcpyAsync(n, rel->d_meta, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
       cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     msc_rel_free(rel);
     return ctx->fail(MSC_ERR_CUDA, "dense aggregate failed");
@@ -838,6 +853,30 @@ extern "C" int msc_dense_merge_compact(msc_ctx* ctx, const void* tables, int32_t
   return MSC_OK;
 }
 
+extern "C" int msc_dense_merge_compact_async(msc_ctx* ctx, const void* tables, int32_t world, int32_t gmax, int32_t stride,
+                                             const int32_t* agg_kinds, int32_t naggs, const int32_t* perm_dev, int32_t ngroups_out,
+                                             int32_t count_slot, void* scratch_table, msc_rel** out) {
+  if (!ctx || !tables || !perm_dev || !scratch_table || !out || world <= 0 || gmax <= 0 || ngroups_out <= 0)
+    return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  DensePlan dp;
+  MSC_TRY(plan_for_table(ctx, agg_kinds, naggs, stride, count_slot, &dp));
+  dense_merge_kernel<<<1, 64, 0, ctx->stream>>>(static_cast<const unsigned long long*>(tables), world, gmax, stride, perm_dev, ngroups_out,
+                                               dense_meta(dp), static_cast<unsigned long long*>(scratch_table));
+  ctx->stats.launches += 1;
+  MSC_CUDA(ctx, cudaGetLastError());
+  bool nf = false;
+  return dense_compact(ctx, static_cast<const unsigned long long*>(scratch_table), ngroups_out, naggs, dp, out, &nf, true);
+}
+
+extern "C" int msc_dense_compact_async(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
+                                       int32_t naggs, int32_t count_slot, msc_rel** out) {
+  if (!ctx || !table || !out || ngroups <= 0) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  DensePlan dp;
+  MSC_TRY(plan_for_table(ctx, agg_kinds, naggs, stride, count_slot, &dp));
+  bool nf = false;
+  return dense_compact(ctx, static_cast<const unsigned long long*>(table), ngroups, naggs, dp, out, &nf, true);
+}
+
 extern "C" int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                                  int32_t naggs, int32_t count_slot, msc_rel** out) {
   if (!ctx || !table || !out || ngroups <= 0) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
@@ -965,9 +1004,20 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
     if (op == MSC_OP_RANK) rank_pc = pc;
   }
   if (has_filter && rank_pc < 0) return ctx->fail(MSC_ERR_ARG, "filtered projection needs a RANK instruction");
-  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  // pending mode (sd->nrows_dev): the input's row count is still on the device; sd->nrows bounds it.  Nothing is waited
+  // for: outputs are sized for the bound, the kernels mask by the device's count, and the result comes back pending.
+  const bool pending = sd->nrows_dev != nullptr;
+  static const bool trace = getenv("MSC_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (trace) fprintf(stderr, "[msc_scan_project pending=%d] %-20s +%.1f us\n", pending ? 1 : 0, what,
+                       std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  };
+  if (!pending) MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));  // a pending chain keeps the first call's start mark
   LaunchPlan lp;
   MSC_TRY(plan_launch(ctx, sd, R, 0, &lp));
+  lp.p.nrows_dev = reinterpret_cast<const unsigned long long*>(sd->nrows_dev);
+  lp.timed = !pending;  // a pending chain reports the scan it started with (the aggregate), not this follow-up
   uint64_t nout_rows = sd->nrows;
   DevTmp counts(ctx), offsets(ctx);
   if (has_filter && sd->nrows > 0) {
@@ -979,20 +1029,24 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
     cp.p.tile_counts = counts.as<uint32_t>();
     MSC_TRY(launch_scan_r<MODE_COUNT>(ctx, &cp));
     MSC_TRY(msc_exclusive_scan_u32_u64(ctx, counts.as<uint32_t>(), offsets.as<uint64_t>(), cp.p.ntiles));
-    MSC_CUDA(ctx, cudaMemcpyAsync(&nout_rows, offsets.as<uint64_t>() + cp.p.ntiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    int drc = msc_check_device_error(ctx);
-    if (drc != MSC_OK) return drc;
+    if (!pending) {
+      MSC_CUDA(ctx, cudaMemcpyAsync(&nout_rows, offsets.as<uint64_t>() + cp.p.ntiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      int drc = msc_check_device_error(ctx);  // synchronises the stream
+      if (drc != MSC_OK) return drc;
+    }
     lp.p.tile_offsets = offsets.as<uint64_t>();
   }
+  mark("planned");
   msc_rel* rel = new_rel(ctx, nout_rows);
   {
-    const int rc = add_cols(ctx, rel, out_phys, nout, nout_rows);
+    int rc = add_cols(ctx, rel, out_phys, nout, nout_rows);
+    if (rc == MSC_OK && pending) rc = msc_alloc(ctx, 3 * sizeof(unsigned long long), reinterpret_cast<void**>(&rel->d_meta));
     if (rc != MSC_OK) {
       msc_rel_free(rel);
       return rc;
     }
   }
+  mark("allocated");
   for (int i = 0; i < nout; ++i) {
     lp.p.out[i] = rel->cols[i].data;
     lp.p.out_phys[i] = out_phys[i];
@@ -1003,6 +1057,17 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
       msc_rel_free(rel);
       return rc;
     }
+  }
+  mark("launched");
+  if (pending) {
+    const unsigned long long* count = (has_filter && sd->nrows > 0) ? offsets.as<unsigned long long>() + lp.p.ntiles
+                                                                   : reinterpret_cast<const unsigned long long*>(sd->nrows_dev);
+    pending_meta_kernel<<<1, 32, 0, ctx->stream>>>(count, rel->d_meta, ctx->d_err);
+    ctx->stats.launches += 1;
+    MSC_CUDA(ctx, cudaGetLastError());
+    rel->pending = true;
+    *out = rel;
+    return MSC_OK;
   }
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
   const int drc = msc_check_device_error(ctx);  // synchronises the stream

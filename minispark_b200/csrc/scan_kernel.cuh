@@ -66,6 +66,7 @@ struct ScanParams {
   const uint64_t* tile_offsets;  // nullptr: no filter, output position = row
   void* out[MSC_VM_MAX_OUT];
   int out_phys[MSC_VM_MAX_OUT];
+  const unsigned long long* nrows_dev;  // when set: the row count is the device's (nrows is an upper bound)
 };
 
 struct LaunchPlan {
@@ -73,6 +74,7 @@ struct LaunchPlan {
   int R;
   size_t smem;
   int grid;
+  bool timed = true;  // record ev_s0 / ev_s1 around the launch (off for the follow-up scans of a pending chain)
 };
 
 template <int R, int MODE>
@@ -799,6 +801,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     const uint32_t pre = ntiles_w < p.nstages ? ntiles_w : p.nstages;
     for (uint32_t k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + static_cast<uint64_t>(k) * nw, lane);
   }
+  const uint64_t nrows = p.nrows_dev ? *p.nrows_dev : p.nrows;  // tiles past the device's count are fully masked
 
   uint32_t stage = 0, parity = 0;
   for (uint32_t k = 0; k < ntiles_w; ++k) {
@@ -807,7 +810,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     while (!mbar_try_wait(&full[stage], parity)) {
     }
     const uint64_t row0 = tile * WT + static_cast<uint64_t>(lane) * R;
-    uint32_t vmask = row_mask<R>(row0, p.nrows);
+    uint32_t vmask = row_mask<R>(row0, nrows);
     int grp[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) grp[r] = (MODE == MODE_DENSE) ? p.ngroups : -1;
@@ -912,14 +915,16 @@ int launch_scan(msc_ctx* ctx, LaunchPlan* lp) {
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   lp->grid = static_cast<int>(grid);
-  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s0, ctx->stream));
+  if (lp->timed) MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s0, ctx->stream));
   kern<<<lp->grid, NT, lp->smem, ctx->stream>>>(lp->p);
-  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s1, ctx->stream));
   ctx->stats.launches += 1;
-  ctx->stats.last_scan_grid = lp->grid;
-  ctx->stats.last_scan_stages = static_cast<int32_t>(lp->p.nstages);
-  ctx->stats.last_scan_smem = static_cast<int32_t>(lp->smem);
-  ctx->stats.last_scan_rows_per_thread = R;
+  if (lp->timed) {
+    MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s1, ctx->stream));
+    ctx->stats.last_scan_grid = lp->grid;
+    ctx->stats.last_scan_stages = static_cast<int32_t>(lp->p.nstages);
+    ctx->stats.last_scan_smem = static_cast<int32_t>(lp->smem);
+    ctx->stats.last_scan_rows_per_thread = R;
+  }
   MSC_CUDA(ctx, cudaGetLastError());
   return MSC_OK;
 }

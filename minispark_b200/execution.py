@@ -937,31 +937,39 @@ class _DenseMerge:
         self.stream = torch.cuda.ExternalStream(stream.value, device=dev)
         torch.cuda.synchronize(dev)
 
-    def run(self, desc: N.ScanDesc) -> tuple[Optional[int], float]:
-        """One pass; returns (handle of the merged result relation, device ms from the scan's first launch to the result).
-
-        scan (enqueued) -> all-gather of the tables -> merge + compaction, all ordered on one stream with a single host
-        wait at the end.  A non-finite SUM in the merged table -- identical on every rank, so all ranks agree -- means the
-        register-reduction kernel must not be trusted (gen_regvm.py): the pass is repeated with the exact kernel."""
+    def enqueue(self, desc: N.ScanDesc, exact: bool = False) -> int:
+        """scan (enqueued) -> all-gather of the tables -> merge + compaction, all ordered on one stream and none waited
+        for: returns the handle of a PENDING relation (msc_rel_settle)."""
         import torch  # noqa: PLC0415
         import torch.distributed as dist  # noqa: PLC0415
 
         e = self.engine
-        flags = N.K["MSC_DENSE_ASYNC"]
-        for _attempt in range(2):
-            if self.nlocal > 0:
-                e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()), flags)
-            with torch.cuda.stream(self.stream):
-                dist.all_gather_into_tensor(self.gathered, self.local)
-            out, nonfinite = C.c_void_p(), C.c_int32()
-            e.ctx.call("msc_dense_merge_compact", C.c_void_p(self.gathered.data_ptr()), e.comm.world, self.gmax, self.stride, self.kinds,
-                       self.naggs, C.c_void_p(self.perm_dev.data_ptr()), self.nglobal, self.count_slot, C.c_void_p(self.merged.data_ptr()),
-                       C.byref(out), C.byref(nonfinite))
-            if not nonfinite.value or flags & N.K["MSC_DENSE_EXACT"]:
+        flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
+        if self.nlocal > 0:
+            e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()), flags)
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.gathered, self.local)
+        out = C.c_void_p()
+        e.ctx.call("msc_dense_merge_compact_async", C.c_void_p(self.gathered.data_ptr()), e.comm.world, self.gmax, self.stride, self.kinds,
+                   self.naggs, C.c_void_p(self.perm_dev.data_ptr()), self.nglobal, self.count_slot, C.c_void_p(self.merged.data_ptr()),
+                   C.byref(out))
+        return out.value
+
+    def run(self, desc: N.ScanDesc) -> tuple[Optional[int], float]:
+        """One pass with a single host wait; returns (handle of the merged result relation, device ms from the scan's
+        first launch to the result).  A non-finite SUM in the merged table -- identical on every rank, so all ranks
+        agree -- means the register-reduction kernel must not be trusted (gen_regvm.py): the pass is repeated with the
+        exact kernel."""
+        e = self.engine
+        for exact in (False, True):
+            handle = self.enqueue(desc, exact)
+            rels = (C.c_void_p * 1)(handle)
+            nonfinite = C.c_int32()
+            e.ctx.call("msc_rel_settle", rels, 1, C.byref(nonfinite))
+            if not nonfinite.value or exact:
                 break
-            e.ctx.lib.msc_rel_free(out)
-            flags |= N.K["MSC_DENSE_EXACT"]
-        return out.value, e.ctx.stats().last_kernel_ms
+            e.ctx.lib.msc_rel_free(C.c_void_p(handle))
+        return handle, e.ctx.stats().last_kernel_ms
 
 
 class PreparedAggregate:
@@ -990,6 +998,14 @@ class PreparedAggregate:
                            for k in self.prog.agg_kinds]
         self.ngroups, self.hint = engine._dense_groups(self.prog)
         self.merge = None
+        self._table = None
+        if self.ngroups and engine.comm.world == 1:  # the dense accumulator table of every pass (identities + scan + compaction)
+            stride, count_slot = C.c_int32(), C.c_int32()
+            engine.ctx.call("msc_dense_layout", C.byref(self.desc), self.kinds, len(self.prog.agg_kinds), C.byref(stride), C.byref(count_slot))
+            self._stride, self._count_slot = stride.value, count_slot.value
+            table = C.c_void_p()
+            engine.ctx.call("msc_dev_alloc", self.ngroups * self._stride * 8, C.byref(table))
+            self._table = table.value
         if self.ngroups and engine.comm.world > 1:
             self.merge = _DenseMerge(engine, self.prog.group_dict, self.desc, self.kinds, len(self.prog.agg_kinds), persistent=True)
         self.bytes_per_row = sum(N.PHYS_WIDTH[c.phys] for c in self.resolver.staged)
@@ -998,40 +1014,87 @@ class PreparedAggregate:
         self._final: Optional[tuple] = None  # compiled final projection, re-bound to every pass's aggregate result
 
     def run(self) -> tuple[DeviceRel, float]:
-        """One pass of the hot path; returns (result relation, device milliseconds of this rank's launches)."""
+        """One pass of the hot path; returns (result relation, device milliseconds from the first launch to the result).
+
+        Dense mode chains scan-aggregate (-> cross-rank merge) -> compaction -> final projection on the stream as PENDING
+        relations and waits for the device once (msc_rel_settle); hash mode runs call by call."""
         e = self.engine
         naggs = len(self.prog.agg_kinds)
-        key_dict = self.prog.group_dict
-        if self.merge is not None:
-            handle, dev_ms = self.merge.run(self.desc)
-            key_dict = self.merge.global_dict
-        else:
-            out = C.c_void_p()
-            e.ctx.call("msc_scan_aggregate", C.byref(self.desc), self.ngroups, self.kinds, naggs, self.hint, C.byref(out))
-            handle, dev_ms = out.value, e.ctx.stats().last_kernel_ms
+        if not self.ngroups:
+            return self._run_stepwise()
+        key_dict = self.merge.global_dict if self.merge is not None else self.prog.group_dict
+        upper = self.merge.nglobal if self.merge is not None else self.ngroups
+        for exact in (False, True):
+            if self.merge is not None:
+                raw_h = self.merge.enqueue(self.desc, exact)
+            else:
+                flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
+                e.ctx.call("msc_scan_dense_table", C.byref(self.desc), self.ngroups, self.kinds, naggs, C.c_void_p(self._table), flags)
+                out = C.c_void_p()
+                e.ctx.call("msc_dense_compact_async", C.c_void_p(self._table), self.ngroups, self._stride, self.kinds, naggs, self._count_slot,
+                           C.byref(out))
+                raw_h = out.value
+            binds = (N.ColBind * (1 + naggs))()
+            e.ctx.check(e.ctx.lib.msc_rel_cols(C.c_void_p(raw_h), binds, 1 + naggs))
+            cols = [DeviceColumn(binds[0].data, binds[0].phys, self.group_type, key_dict)]
+            cols += [DeviceColumn(binds[1 + s].data, binds[1 + s].phys, self.slot_types[s]) for s in self.prog.slot_of]
+            desc2, prog2, staged_cols = self._final_projection(cols, upper)
+            nrows_dev = C.c_void_p()
+            e.ctx.check(e.ctx.lib.msc_rel_nrows_dev(C.c_void_p(raw_h), C.byref(nrows_dev)))  # (no ctx argument)
+            desc2.nrows = upper
+            desc2.nrows_dev = nrows_dev.value
+            for slot, ci in enumerate(staged_cols):
+                desc2.staged[slot].data = cols[ci].ptr
+            out2 = C.c_void_p()
+            e.ctx.call("msc_scan_project", C.byref(desc2), N.int32_array(prog2.out_phys), len(prog2.out_phys), C.byref(out2))
+            rels = (C.c_void_p * 2)(raw_h, out2.value)
+            nonfinite = C.c_int32()
+            e.ctx.call("msc_rel_settle", rels, 2, C.byref(nonfinite))
+            if not nonfinite.value or exact:
+                break
+            e.ctx.lib.msc_rel_free(C.c_void_p(raw_h))  # non-finite SUM out of a masked variant: redo the pass the exact way
+            e.ctx.lib.msc_rel_free(C.c_void_p(out2.value))
         st = e.ctx.stats()
         self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
                            "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread}
-        raw = e._track(DeviceRel.from_handle(e.ctx, handle, [self.group_type, *self.slot_types], [key_dict] + [None] * len(self.slot_types)))
-        if self.merge is None and e.comm.world > 1:  # hash mode: partition + all-to-all (or all-gather when small)
+        e._track(DeviceRel(e.ctx, raw_h, 0, []))
+        final = e._track(DeviceRel.from_handle(e.ctx, out2.value, [x.type for x in self.plan.outputs], prog2.out_dicts))
+        return final, st.last_kernel_ms
+
+    def _final_projection(self, cols: list[DeviceColumn], nrows: int) -> tuple:
+        """The final projection (AVG = SUM / COUNT, HAVING, output order), compiled once; later passes only re-bind it."""
+        e = self.engine
+        sig = [(c.phys, id(c.dict)) for c in cols]
+        if self._final is None or self._final[3] != sig:
+            src2 = _Source(nrows, dict(enumerate(cols)))
+            res2 = _ScanResolver(e, src2)
+            prog2 = L.compile_project(res2, self.plan.filters, self.plan.outputs)
+            if res2.gather:
+                raise L.LoweringError("prepared final projection must not gather")
+            index_of = {c.ptr: i for i, c in enumerate(cols)}
+            self._final = (res2.desc(prog2.program), prog2, [index_of[c.ptr] for c in res2.staged], sig)
+        return self._final[0], self._final[1], self._final[2]
+
+    def _run_stepwise(self) -> tuple[DeviceRel, float]:
+        e = self.engine
+        naggs = len(self.prog.agg_kinds)
+        out = C.c_void_p()
+        e.ctx.call("msc_scan_aggregate", C.byref(self.desc), self.ngroups, self.kinds, naggs, self.hint, C.byref(out))
+        st = e.ctx.stats()
+        dev_ms = st.last_kernel_ms
+        self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
+                           "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread}
+        raw = e._track(DeviceRel.from_handle(e.ctx, out.value, [self.group_type, *self.slot_types], [self.prog.group_dict] + [None] * len(self.slot_types)))
+        if e.comm.world > 1:  # hash mode: partition + all-to-all (or all-gather when small)
             raw = e._merge_partials(raw, self.prog.agg_kinds, self.slot_types, self.group_type)
             dev_ms += e.ctx.stats().last_kernel_ms
         key = raw.cols[0]
         if self.group_type == L.FLOAT and key.phys == N.P_I64:
             key = DeviceColumn(key.ptr, N.P_F64, L.FLOAT)
         cols = [key] + [raw.cols[1 + s] for s in self.prog.slot_of]
-        if self._final is None or self._final[3] != [(c.phys, id(c.dict)) for c in cols]:
-            # compile the final projection (AVG = SUM / COUNT, HAVING, output order) once; later passes only re-bind it
-            src2 = _Source(raw.nrows, dict(enumerate(cols)))
-            res2 = _ScanResolver(e, src2)
-            prog2 = L.compile_project(res2, self.plan.filters, self.plan.outputs)
-            index_of = {c.ptr: i for i, c in enumerate(cols)}
-            self._final = (res2.desc(prog2.program), prog2, [index_of[c.ptr] for c in res2.staged], [(c.phys, id(c.dict)) for c in cols],
-                           bool(res2.gather))
-        desc2, prog2, staged_cols, _, gathers = self._final
-        if gathers:
-            raise L.LoweringError("prepared final projection must not gather")
+        desc2, prog2, staged_cols = self._final_projection(cols, raw.nrows)
         desc2.nrows = raw.nrows
+        desc2.nrows_dev = None
         for slot, ci in enumerate(staged_cols):
             desc2.staged[slot].data = cols[ci].ptr
         out2 = C.c_void_p()

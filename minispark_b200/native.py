@@ -68,6 +68,7 @@ class ScanDesc(C.Structure):
         ("ncode2", C.c_int32),
         ("count_slot2", C.c_int32),
         ("code2", C.c_uint32 * K["MSC_VM_MAX_CODE2"]),
+        ("nrows_dev", C.c_void_p),
     ]
 
 
@@ -127,6 +128,12 @@ _SIGNATURES = {
     "msc_dense_merge_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
                                           C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "msc_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "msc_rel_nrows_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "msc_rel_settle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int32)]),
+    "msc_dense_merge_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                                C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "msc_dense_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                          C.POINTER(C.c_void_p)]),
     "msc_dense_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                   C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
     "msc_dense_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
@@ -199,7 +206,11 @@ class Context:
             raise NativeError(rc, (self.lib.msc_last_error(self.handle) or b"").decode("utf-8", "replace"))
 
     def call(self, name: str, *args):  # noqa: ANN002, ANN201
-        self.check(getattr(self.lib, name)(self.handle, *args))
+        """``name(ctx, *args)`` for the entry points that take the context first; raises on a non-zero return."""
+        fn = getattr(self.lib, name)
+        if len(fn.argtypes) != len(args) + 1:  # ctypes itself lets extra arguments through
+            raise TypeError(f"{name} takes {len(fn.argtypes)} arguments, {len(args) + 1} given (does it take the context?)")
+        self.check(fn(self.handle, *args))
 
     def stats(self) -> Stats:
         st = Stats()
