@@ -125,8 +125,11 @@ def captured_traffic(sf: float, layout: str, rows: int, bytes_per_row: int) -> t
     return None, None
 
 
-def kernel_name(rows_per_thread: int) -> str:
-    """msc_stats.last_scan_rows_per_thread: R of scan_kernel<R, MODE_DENSE>, or -(8 + 100 * NG) for the regvm variants."""
+def kernel_name(rows_per_thread: int, kind: int = 0, regs: int = 0) -> str:
+    """msc_stats.last_scan_kind 2 = query-specialised kernel (csrc/jit.cu); otherwise last_scan_rows_per_thread is R of
+    scan_kernel<R, MODE_DENSE>, or -(8 + 100 * NG) for the regvm variants."""
+    if kind == 2:
+        return f"msc_jit_dense (specialised for this query by NVRTC, {rows_per_thread} rows per lane, {regs} registers)"
     if rows_per_thread >= 0:
         return f"scan_kernel<R={rows_per_thread}, MODE_DENSE>"
     ng, rows = divmod(-rows_per_thread, 100)
@@ -382,7 +385,7 @@ def cuda_arm(args: argparse.Namespace) -> None:
                     "wall_ms_per_step": 1e3 * wall_max / args.steps, "parity_check": check,
                 },
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                             "kernel": kernel_name(agg_launch["rows_per_thread"]), "launch": agg_launch,
+                             "kernel": kernel_name(agg_launch["rows_per_thread"], agg_launch.get("kind", 0), agg_launch.get("regs", 0)), "launch": agg_launch,
                              "program": prepared.prog.program.text,
                              "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": nrows_table * bytes_per_row, "peak_source": peak_src,
                              "north_star_layout_equiv_gbs": nrows_table * Q1_WIDE_BYTES_PER_ROW / (scan_ms * 1e-3) / 1e9 if args.layout == "native" else None},

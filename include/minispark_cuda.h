@@ -203,7 +203,14 @@ typedef struct msc_stats {
   int32_t last_scan_stages; /* shared-memory ring depth */
   int32_t last_scan_smem;   /* dynamic shared memory bytes per CTA */
   int32_t last_scan_rows_per_thread;
+  int32_t last_scan_kind;   /* which kernel ran the last fused scan: MSC_SCAN_KIND_* */
+  int32_t last_scan_regs;   /* registers per thread of a specialised kernel (0 otherwise) */
+  uint64_t jit_compiles;    /* specialised kernels compiled by this ctx since creation */
+  double last_jit_compile_ms; /* host time of the last NVRTC compilation (or on-disk cache hit) */
 } msc_stats;
+#define MSC_SCAN_KIND_VM 0    /* C++ three-address interpreter (scan_kernel.cuh) */
+#define MSC_SCAN_KIND_REGVM 1 /* register-resident PTX interpreter (scan_regvm_impl.cuh) */
+#define MSC_SCAN_KIND_JIT 2   /* query-specialised kernel compiled at run time (jit.cu) */
 
 /* ---- context ---------------------------------------------------------------------------- */
 MSC_API int msc_abi_version(void);
@@ -286,6 +293,13 @@ MSC_API int msc_dense_layout(msc_ctx* ctx, const msc_scan_desc* scan, const int3
  * the caller looks at `nonfinite` of msc_dense_merge_compact and repeats the pass with MSC_DENSE_EXACT if set. */
 #define MSC_DENSE_EXACT 1
 #define MSC_DENSE_ASYNC 2
+/* MSC_DENSE_JIT = run the scan on a kernel specialised for this query (jit.cu): the three-address program is turned
+ * into straight-line CUDA C++ and compiled for sm_100a with NVRTC on first use (0.1-0.3 s; cached in the process and,
+ * with MSC_JIT_CACHE=<dir>, on disk), the way the reference's ThreadEngine compiles one Zig program per query
+ * (execution.py:139-160).  Without the flag a scan uses an already compiled kernel when there is one and the
+ * interpreters otherwise.  Exact arithmetic (no masked reduction), so MSC_DENSE_EXACT is implied.  Scans the generator
+ * cannot express (groups x accumulators > 32) ignore the flag. */
+#define MSC_DENSE_JIT 4
 MSC_API int msc_scan_dense_table(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds,
                          int32_t naggs, void* table, int32_t flags);
 /* fold `world` tables of [gmax][stride] cells (device, rank-major) into out_table[ngroups_out][stride];
@@ -303,6 +317,15 @@ MSC_API int msc_dense_merge_compact_async(msc_ctx* ctx, const void* tables, int3
                                   int32_t count_slot, void* scratch_table, msc_rel** out);
 MSC_API int msc_dense_compact_async(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                             int32_t naggs, int32_t count_slot, msc_rel** out);
+/* The specialised kernel's CUDA C++ source for a dense aggregate scan (column pointers are not looked at) and its
+ * compilation, as two device-free steps: lets a host inspect / test / pre-compile what MSC_DENSE_JIT would run.
+ * msc_jit_dense_source writes at most `cap` bytes (NUL-terminated) and the full length to *len; msc_jit_compile returns
+ * the sm_100a cubin the same way and NVRTC's log (or the reason no compiler is available) in `log`.  masked != 0 asks
+ * for the variant MSC_DENSE_JIT runs first (SUM / COUNT through one-hot f64 masks, one fma per group and aggregate;
+ * the exact variant is what MSC_DENSE_EXACT, or a non-finite sum, falls back to). */
+MSC_API int msc_jit_dense_source(const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked, char* buf,
+                         size_t cap, size_t* len);
+MSC_API int msc_jit_compile(const char* source, void* cubin, size_t cap, size_t* len, char* log, size_t log_cap);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                       int32_t naggs, int32_t count_slot, msc_rel** out);

@@ -1,0 +1,663 @@
+// jit.cu -- query-specialised dense aggregate scan: source generation, NVRTC compilation, kernel cache, launch.
+//
+// The reference's native engine renders one program per query from templates/plan.zig (src/mini_spark/codegen.py),
+// compiles it and caches the executable (execution.py:139-160).  This is the same idea on the GPU: the query's
+// three-address expression program (include/minispark_cuda.h) is translated into straight-line CUDA C++ for a
+// lane's 8 rows, appended to the hand-written kernel frame of jit_prelude.inc (persistent grid, warp-private
+// cp.async.bulk rings), compiled for sm_100a with NVRTC and kept in a per-process cache keyed by the source text
+// (plus an optional on-disk cubin cache).  Group accumulators live in REGISTERS for the whole kernel -- one
+// predicated add per (group, aggregate) and row -- so there is no dispatch, no mask arithmetic and no shared-memory
+// accumulator traffic; the interpreters (scan_regvm_impl.cuh, scan_kernel.cuh) remain for one-shot queries, whose
+// scan is shorter than a compile, and for shapes outside this generator (many groups).
+//
+// libnvrtc and libcuda are dlopen()ed on first use: the library still loads (and every other entry point works)
+// where they are absent, and msc_jit_* then fail with a message.
+#include <dlfcn.h>
+#include <sys/stat.h>
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <fstream>
+#include <memory>
+#include <sstream>
+
+#include "jit.h"
+
+namespace mscan {
+namespace {
+
+const char* const kPrelude =
+#include "jit_prelude.inc"
+    ;
+
+struct JitParams {  // must match struct JitParams in jit_prelude.inc
+  unsigned long long nrows;
+  const unsigned long long* nrows_dev;
+  uint32_t ntiles;
+  uint32_t _pad;
+  const unsigned char* col[24];
+  const void* gather[16];
+  const void* luts[8];
+  long long consts[32];
+  unsigned long long* dense_out;
+  int* err;
+};
+static_assert(MSC_VM_MAX_STAGED == 24 && MSC_VM_MAX_GATHER == 16 && MSC_VM_MAX_LUTS == 8 && MSC_VM_MAX_CONSTS == 32, "JitParams layout");
+
+// ---- NVRTC + driver API through dlopen ------------------------------------------------------------------------
+typedef struct _nvrtcProgram* nvrtcProgram;
+typedef struct CUmod_st* CUmodule;
+typedef struct CUfunc_st* CUfunction;
+typedef struct CUstream_st* CUstream;
+
+struct Api {
+  bool tried = false;
+  std::string why;
+  void *nvrtc = nullptr, *cuda = nullptr;
+  int (*nvrtcCreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*nvrtcCompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*nvrtcGetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*nvrtcGetProgramLog)(nvrtcProgram, char*) = nullptr;
+  int (*nvrtcGetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*nvrtcGetCUBIN)(nvrtcProgram, char*) = nullptr;
+  int (*nvrtcDestroyProgram)(nvrtcProgram*) = nullptr;
+  int (*nvrtcVersion)(int*, int*) = nullptr;
+  int (*cuModuleLoadData)(CUmodule*, const void*) = nullptr;
+  int (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  int (*cuFuncSetAttribute)(CUfunction, int, int) = nullptr;
+  int (*cuFuncGetAttribute)(int*, int, CUfunction) = nullptr;
+  int (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  int (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  int (*cuGetErrorString)(int, const char**) = nullptr;
+};
+
+Api& api() {
+  static Api a;
+  return a;
+}
+
+template <class F>
+bool sym(void* lib, const char* name, F* out, std::string* why) {
+  *out = reinterpret_cast<F>(dlsym(lib, name));
+  if (!*out) *why = std::string("missing symbol ") + name;
+  return *out != nullptr;
+}
+
+bool load_nvrtc(std::string* why) {
+  Api& a = api();
+  if (a.nvrtc) return true;
+  const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"};
+  for (const char* n : names)
+    if ((a.nvrtc = dlopen(n, RTLD_NOW | RTLD_LOCAL)) != nullptr) break;
+  if (!a.nvrtc) {
+    *why = "libnvrtc.so.12 not found (needed to specialise scan kernels)";
+    return false;
+  }
+  return sym(a.nvrtc, "nvrtcCreateProgram", &a.nvrtcCreateProgram, why) && sym(a.nvrtc, "nvrtcCompileProgram", &a.nvrtcCompileProgram, why) &&
+         sym(a.nvrtc, "nvrtcGetProgramLogSize", &a.nvrtcGetProgramLogSize, why) && sym(a.nvrtc, "nvrtcGetProgramLog", &a.nvrtcGetProgramLog, why) &&
+         sym(a.nvrtc, "nvrtcGetCUBINSize", &a.nvrtcGetCUBINSize, why) && sym(a.nvrtc, "nvrtcGetCUBIN", &a.nvrtcGetCUBIN, why) &&
+         sym(a.nvrtc, "nvrtcDestroyProgram", &a.nvrtcDestroyProgram, why) && sym(a.nvrtc, "nvrtcVersion", &a.nvrtcVersion, why);
+}
+
+bool load_driver(std::string* why) {
+  Api& a = api();
+  if (a.cuda) return true;
+  a.cuda = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+  if (!a.cuda) {
+    *why = "libcuda.so.1 not found";
+    return false;
+  }
+  return sym(a.cuda, "cuModuleLoadData", &a.cuModuleLoadData, why) && sym(a.cuda, "cuModuleGetFunction", &a.cuModuleGetFunction, why) &&
+         sym(a.cuda, "cuFuncSetAttribute", &a.cuFuncSetAttribute, why) && sym(a.cuda, "cuFuncGetAttribute", &a.cuFuncGetAttribute, why) &&
+         sym(a.cuda, "cuOccupancyMaxActiveBlocksPerMultiprocessor", &a.cuOccupancyMaxActiveBlocksPerMultiprocessor, why) &&
+         sym(a.cuda, "cuLaunchKernel", &a.cuLaunchKernel, why) && sym(a.cuda, "cuGetErrorString", &a.cuGetErrorString, why);
+}
+
+constexpr int CU_FUNC_ATTRIBUTE_NUM_REGS = 4;
+constexpr int CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8;
+
+// ---- source generation ----------------------------------------------------------------------------------------
+struct Layout {  // of one warp stage, as plan_launch lays it out
+  uint32_t off[MSC_VM_MAX_STAGED];
+  uint32_t tile_bytes[MSC_VM_MAX_STAGED];
+  uint32_t stage_bytes = 0, tx_bytes = 0;
+};
+
+Layout stage_layout(const msc_scan_desc* sd) {
+  Layout l;
+  uint32_t off = 0;
+  for (int c = 0; c < sd->nstaged; ++c) {
+    const uint32_t w = static_cast<uint32_t>(msc_phys_width(sd->staged[c].phys));
+    l.off[c] = off;
+    l.tile_bytes[c] = w * 256;
+    l.tx_bytes += w * 256;
+    off += static_cast<uint32_t>(msc_round_up(w * 256, 128));
+  }
+  l.stage_bytes = off ? off : 128;
+  return l;
+}
+
+const char* ld_fn(int phys) {
+  switch (phys) {
+    case MSC_P_U8: return "ld_u8";
+    case MSC_P_U16: return "ld_u16";
+    case MSC_P_U32: return "ld_u32";
+    case MSC_P_I32: return "ld_i32";
+    case MSC_P_F32: return "ld_f32";
+    default: return "ld_64";
+  }
+}
+
+bool is_float_kind(int k) { return k == MSC_AGG_SUM_F || k == MSC_AGG_MIN_F || k == MSC_AGG_MAX_F; }
+
+struct Gen {
+  const msc_scan_desc* sd;
+  int ngroups, naggs, stride;  // stride = naggs, or naggs + 1 with the hidden per-group row counter in slot naggs
+  const int* kinds;            // [stride]
+  const long long* init;       // [stride]
+  int nstages;
+  bool masked;  // SUM_F / COUNT as acc = fma(v, m, acc) with one-hot f64 masks m read from a shared-memory table
+  std::ostringstream o;
+  std::string why;
+  bool counted[MSC_VM_MAX_AGGS + 1] = {};  // slot is "SUM_I of a constant": counted in a u32 per tile, folded at the tile's end
+  long long count_mul[MSC_VM_MAX_AGGS + 1] = {};
+
+  std::string operand(uint32_t opnd, bool* ok) {
+    const int kind = (opnd >> 12) & 7, idx = opnd & 0xfff;
+    const bool i2f = ((opnd >> 12) & MSC_SRC_I2F) != 0;
+    std::string s;
+    switch (kind) {
+      case MSC_SRC_TEMP: s = "t" + std::to_string(idx); break;
+      case MSC_SRC_STAGED: s = "c" + std::to_string(idx) + "[r]"; break;
+      case MSC_SRC_CONST: s = "p.consts[" + std::to_string(idx) + "]"; break;
+      case MSC_SRC_GATHER:
+        s = "gather_at<" + std::to_string(sd->gather[idx & 63].phys) + ">(p.gather[" + std::to_string(idx & 63) + "], c" +
+            std::to_string(idx >> 6) + "[r], valid)";
+        break;
+      case MSC_SRC_NONE: s = "0ll"; break;
+      default: *ok = false; return "0ll";
+    }
+    if (i2f) s = "d2l((double)(" + s + "))";
+    return s;
+  }
+
+  // the value of one instruction as an i64 expression of a and b (raw 64-bit operands)
+  std::string compute(int op, const std::string& a, const std::string& b, uint32_t opnd_b, bool* ok) {
+    auto f2 = [&](const char* sym) { return "d2l(l2d(" + a + ") " + sym + " l2d(" + b + "))"; };
+    auto i2 = [&](const char* sym) { return "((" + a + ") " + sym + " (" + b + "))"; };
+    auto cf = [&](const char* sym) { return "((l2d(" + a + ") " + sym + " l2d(" + b + ")) ? 1ll : 0ll)"; };
+    auto ci = [&](const char* sym) { return "(((" + a + ") " + sym + " (" + b + ")) ? 1ll : 0ll)"; };
+    switch (op) {
+      case MSC_OP_MOV: return a;
+      case MSC_OP_ADD_F: return f2("+");
+      case MSC_OP_SUB_F: return f2("-");
+      case MSC_OP_MUL_F: return f2("*");
+      case MSC_OP_DIV_F: return "(l2d(" + b + ") == 0.0 ? d2l(0.0) : d2l(l2d(" + a + ") / l2d(" + b + ")))";
+      case MSC_OP_FLOORDIV_F: return "py_floordiv_f(" + a + ", " + b + ")";
+      case MSC_OP_MOD_F: return "py_mod_f(" + a + ", " + b + ")";
+      case MSC_OP_ADD_I: return i2("+");
+      case MSC_OP_SUB_I: return i2("-");
+      case MSC_OP_MUL_I: return i2("*");
+      case MSC_OP_FLOORDIV_I: return "py_floordiv_i(" + a + ", " + b + ")";
+      case MSC_OP_MOD_I: return "py_mod_i(" + a + ", " + b + ")";
+      case MSC_OP_LT_F: return cf("<");
+      case MSC_OP_LE_F: return cf("<=");
+      case MSC_OP_GT_F: return cf(">");
+      case MSC_OP_GE_F: return cf(">=");
+      case MSC_OP_EQ_F: return cf("==");
+      case MSC_OP_NE_F: return cf("!=");
+      case MSC_OP_LT_I: return ci("<");
+      case MSC_OP_LE_I: return ci("<=");
+      case MSC_OP_GT_I: return ci(">");
+      case MSC_OP_GE_I: return ci(">=");
+      case MSC_OP_EQ_I: return ci("==");
+      case MSC_OP_NE_I: return ci("!=");
+      case MSC_OP_AND: return i2("&");
+      case MSC_OP_OR: return i2("|");
+      case MSC_OP_LUT8:
+        return "(valid ? (i64)__ldg(reinterpret_cast<const unsigned char*>(p.luts[" + std::to_string(opnd_b & 0xfff) + "]) + (" + a + ")) : 0ll)";
+      case MSC_OP_LUT32:
+        return "(valid ? (i64)__ldg(reinterpret_cast<const u32*>(p.luts[" + std::to_string(opnd_b & 0xfff) + "]) + (" + a + ")) : 0ll)";
+      default: *ok = false; return "0ll";
+    }
+  }
+
+  std::string acc(int g, int s) { return "a" + std::to_string(g) + "_" + std::to_string(s); }
+  std::string cnt(int g, int s) { return "n" + std::to_string(g) + "_" + std::to_string(s); }
+
+  // accumulators are typed: double for the float kinds, i64 otherwise
+  void emit_agg(int slot, const std::string& x) {
+    o << "        { const int gsel = valid ? grp : -1;\n";
+    for (int g = 0; g < ngroups; ++g) {
+      o << "          ";
+      const std::string a = acc(g, slot), gs = std::to_string(g);
+      if (counted[slot] && masked) o << cnt(g, slot) << " += m" << gs << ";\n";
+      else if (counted[slot]) o << "inc_if<" << gs << ">(" << cnt(g, slot) << ", gsel);\n";
+      else if (kinds[slot] == MSC_AGG_SUM_F && masked) o << a << " = fma(l2d(" << x << "), m" << gs << ", " << a << ");\n";
+      else if (kinds[slot] == MSC_AGG_SUM_F) o << "addf_if<" << gs << ">(" << a << ", l2d(" << x << "), gsel);\n";
+      else if (kinds[slot] == MSC_AGG_SUM_I) o << "addi_if<" << gs << ">(" << a << ", " << x << ", gsel);\n";
+      else if (is_float_kind(kinds[slot])) o << "if (gsel == " << gs << ") " << a << " = l2d(agg_combine<" << kinds[slot] << ">(d2l(" << a << "), " << x << "));\n";
+      else o << "if (gsel == " << gs << ") " << a << " = agg_combine<" << kinds[slot] << ">(" << a << ", " << x << ");\n";
+    }
+    o << "        }\n";
+  }
+
+  bool generate() {
+    const Layout lay = stage_layout(sd);
+    // which accumulators are SUM_I of a constant (COUNT, plan.py:190-204 / sql.py:463-464)?
+    int ninstr = 0;
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2, ++ninstr) {
+      const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
+      const int op = w0 & 0x3f;
+      if (op == MSC_OP_END) break;
+      const int dkind = (w0 >> 6) & 7, dst = (w0 >> 13) & 0x7f, tee = (w0 >> 9) & 0xf;
+      const uint32_t a = w1 & 0xffffu;
+      if (dkind == MSC_DST_AGG && op == MSC_OP_MOV && tee == 0 && ((a >> 12) & 15) == MSC_SRC_CONST && kinds[dst] == MSC_AGG_SUM_I) {
+        counted[dst] = true;
+        count_mul[dst] = sd->consts[a & 0xfff];
+      }
+    }
+    for (int pc = 0, seen[MSC_VM_MAX_AGGS + 1] = {}; pc + 1 < sd->ncode; pc += 2) {  // a slot written twice is not a plain count
+      const uint32_t w0 = sd->code[pc];
+      if ((w0 & 0x3f) == MSC_OP_END) break;
+      if (((w0 >> 6) & 7) == MSC_DST_AGG && ++seen[(w0 >> 13) & 0x7f] > 1) counted[(w0 >> 13) & 0x7f] = false;
+    }
+    if (stride > naggs) {  // hidden per-group row counter
+      counted[naggs] = true;
+      count_mul[naggs] = 1;
+    }
+
+    o << kPrelude;
+    if (masked) {  // the masks are fixed at GROUP: a later filter would not reach them
+      bool grouped_seen = false;
+      for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+        const uint32_t w0 = sd->code[pc];
+        if ((w0 & 0x3f) == MSC_OP_END) break;
+        const int dk = (w0 >> 6) & 7;
+        if (dk == MSC_DST_GROUP) grouped_seen = true;
+        if (dk == MSC_DST_FILTER && grouped_seen) {
+          why = "filter after GROUP (masked variant)";
+          return false;
+        }
+      }
+    }
+    o << "constexpr int NG = " << ngroups << ", NGP = " << (ngroups + 1) / 2 * 2 << ", STRIDE = " << stride << ", NSTAGES = " << nstages << ";\n";
+    o << "constexpr u32 STAGE_BYTES = " << lay.stage_bytes << ", TX_BYTES = " << lay.tx_bytes << ", NSTAGED = " << sd->nstaged << ";\n";
+    o << "__device__ const u32 COL_OFF[" << std::max(1, sd->nstaged) << "] = {";
+    for (int c = 0; c < sd->nstaged; ++c) o << (c ? ", " : "") << lay.off[c];
+    if (!sd->nstaged) o << "0";
+    o << "};\n__device__ const u32 COL_BYTES[" << std::max(1, sd->nstaged) << "] = {";
+    for (int c = 0; c < sd->nstaged; ++c) o << (c ? ", " : "") << lay.tile_bytes[c];
+    if (!sd->nstaged) o << "0";
+    o << "};\n__device__ const int KIND[STRIDE] = {";
+    for (int s = 0; s < stride; ++s) o << (s ? ", " : "") << kinds[s];
+    o << "};\n__device__ const i64 INIT[STRIDE] = {";
+    for (int s = 0; s < stride; ++s) o << (s ? ", " : "") << init[s] << "ll";
+    o << "};\n\n";
+    o << R"(__device__ __forceinline__ void issue_tile(const JitParams& p, unsigned char* stages, u64* full, u32 stage, u64 tile, int lane) {
+  if (lane == 0) mbar_expect_tx(&full[stage], TX_BYTES);
+  __syncwarp();
+  if (lane < (int)NSTAGED) bulk_g2s(stages + stage * STAGE_BYTES + COL_OFF[lane], p.col[lane] + tile * COL_BYTES[lane], COL_BYTES[lane], &full[stage]);
+}
+
+extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __grid_constant__ JitParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64* full = reinterpret_cast<u64*>(smem) + warp * 8;
+  unsigned char* stages = smem + SMEM_HEADER + warp * (NSTAGES * STAGE_BYTES);
+  i64* red = reinterpret_cast<i64*>(smem + SMEM_HEADER + NW * (NSTAGES * STAGE_BYTES));  // [NW][NG * STRIDE]
+  // one-hot f64 masks: row e = 0 is "no group" (filtered out / past the end / code out of range), row g + 1 selects group g
+  double* mlut = reinterpret_cast<double*>(red + NW * NG * STRIDE);  // [NG + 1][NGP]
+  if (lane == 0) {
+    for (u32 st = 0; st < NSTAGES; ++st) mbar_init(&full[st], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < (NG + 1) * NGP; i += NT) mlut[i] = (i / NGP >= 1 && i % NGP == i / NGP - 1) ? 1.0 : 0.0;
+  __syncthreads();
+  const u32 gw = blockIdx.x * NW + warp, nw = gridDim.x * NW;
+  const u32 ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
+  {
+    const u32 pre = ntiles_w < NSTAGES ? ntiles_w : NSTAGES;
+    for (u32 k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + (u64)k * nw, lane);
+  }
+  const u64 nrows = p.nrows_dev ? *p.nrows_dev : p.nrows;
+  bool bad = false;
+)";
+    for (int g = 0; g < ngroups; ++g)
+      for (int s = 0; s < stride; ++s) {
+        if (is_float_kind(kinds[s])) o << "  double " << acc(g, s) << " = l2d(INIT[" << s << "]);";
+        else o << "  i64 " << acc(g, s) << " = INIT[" << s << "];";
+        if (counted[s]) o << (masked ? " double " : " u32 ") << cnt(g, s) << " = 0;";
+        o << "\n";
+      }
+    o << R"(  u32 stage = 0, parity = 0;
+  for (u32 k = 0; k < ntiles_w; ++k) {
+    const u64 tile = gw + (u64)k * nw;
+    const unsigned char* sb = stages + stage * STAGE_BYTES;
+    while (!mbar_try_wait(&full[stage], parity)) {
+    }
+    u32 vmask = 0xffu;
+    const u64 tile_row0 = tile * WT;
+    if (tile_row0 + WT > nrows) {
+      vmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (tile_row0 + (r / 4) * 128 + 4 * lane + (r % 4) < nrows) vmask |= 1u << r;
+    }
+)";
+    // Rows past the end of the relation exist only in the last tile.  When the group key is a staged column read as it
+    // is, that tile overwrites the key of its invalid rows with -1 ("no group") and the row loop needs no validity
+    // bits at all; programs that dereference row values (gathers, lookup tables) keep the per-row bit.
+    int key_col = -1;
+    bool derefs = false;
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+      const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
+      const int op = w0 & 0x3f;
+      if (op == MSC_OP_END) break;
+      const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
+      if (op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || ((oa >> 12) & 7) == MSC_SRC_GATHER || ((ob >> 12) & 7) == MSC_SRC_GATHER) derefs = true;
+      if (((w0 >> 6) & 7) == MSC_DST_GROUP && op == MSC_OP_MOV && ((oa >> 12) & 15) == MSC_SRC_STAGED) key_col = oa & 0xfff;
+    }
+    const bool valid_bits = derefs || key_col < 0;
+    for (int c = 0; c < sd->nstaged; ++c)
+      o << "    i64 c" << c << "[R]; " << ld_fn(sd->staged[c].phys) << "(sb + " << lay.off[c] << ", lane, c" << c << ");\n";
+    if (!valid_bits) {
+      o << "    if (vmask != 0xffu) {\n#pragma unroll\n      for (int r = 0; r < R; ++r)\n        if (!((vmask >> r) & 1u)) c" << key_col
+        << "[r] = -1;\n    }\n";
+    }
+    o << "#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = " << (valid_bits ? "(vmask >> r) & 1u" : "true") << ";\n      int grp = -1;\n";
+    if (masked) {
+      o << "      double";
+      for (int g = 0; g < (ngroups + 1) / 2 * 2; ++g) o << (g ? ", m" : " m") << g << " = 0.0";
+      o << ";\n";
+    }
+    for (int t = 0; t < sd->ntemps; ++t) o << "      i64 t" << t << " = 0;\n";
+    bool ok = true, grouped = false;
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+      const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
+      const int op = w0 & 0x3f;
+      if (op == MSC_OP_END) break;
+      if (op == MSC_OP_RANK) {
+        why = "RANK in an aggregate scan";
+        return false;
+      }
+      const int dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
+      const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
+      const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+      const std::string a = operand(oa, &ok), b = lut ? std::string("0ll") : operand(ob, &ok);
+      o << "      {  // instruction " << pc / 2 << "\n";
+      if (op == MSC_OP_DIV_F || op == MSC_OP_FLOORDIV_F || op == MSC_OP_MOD_F)
+        o << "        bad |= valid && (l2d(" << b << ") == 0.0);\n";
+      if (op == MSC_OP_FLOORDIV_I || op == MSC_OP_MOD_I) o << "        bad |= valid && ((" << b << ") == 0);\n";
+      const bool plain_count = dkind == MSC_DST_AGG && counted[dst];
+      if (!plain_count) o << "        const i64 x = " << compute(op, a, b, ob, &ok) << ";\n";
+      if (tee) o << "        t" << tee - 1 << " = x;\n";
+      switch (dkind) {
+        case MSC_DST_TEMP: o << "        t" << dst << " = x;\n"; break;
+        case MSC_DST_FILTER: o << "        valid = valid && (x != 0);\n"; break;
+        case MSC_DST_GROUP:
+          o << "        grp = (x >= 0 && x < NG) ? (int)x : -1;\n";
+          if (masked) {
+            o << "        { const double2* mrow = reinterpret_cast<const double2*>(mlut + (valid ? grp + 1 : 0) * NGP);\n";
+            for (int g = 0; g < (ngroups + 1) / 2 * 2; g += 2)
+              o << "          { const double2 mm = mrow[" << g / 2 << "]; m" << g << " = mm.x; m" << g + 1 << " = mm.y; }\n";
+            o << "        }\n";
+          }
+          if (stride > naggs) emit_agg(naggs, "");
+          grouped = true;
+          break;
+        case MSC_DST_AGG:
+          if (!grouped) {
+            why = "aggregate before GROUP";
+            return false;
+          }
+          emit_agg(dst, "x");
+          break;
+        case MSC_DST_NONE: break;
+        default: why = "destination kind outside an aggregate scan"; return false;
+      }
+      o << "      }\n";
+    }
+    if (!ok) {
+      why = "operand or opcode outside the generator";
+      return false;
+    }
+    if (!grouped) {
+      why = "program has no GROUP";
+      return false;
+    }
+    o << "    }\n";
+    // fold the tile's u32 row counts into their i64 accumulators (8 rows per lane and tile: no overflow)
+    for (int g = 0; g < ngroups; ++g)
+      for (int s = 0; s < stride; ++s)
+        if (counted[s] && !masked) o << "    " << acc(g, s) << " += (i64)" << cnt(g, s) << " * " << count_mul[s] << "ll; " << cnt(g, s) << " = 0;\n";
+    o << R"(    __syncwarp();
+    if (k + NSTAGES < ntiles_w) issue_tile(p, stages, full, stage, gw + (u64)(k + NSTAGES) * nw, lane);
+    if (++stage == NSTAGES) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (bad) atomicOr(p.err, 1);  // MSC_DEVERR_DIV_ZERO
+)";
+    if (masked)  // row counts were summed as f64 (exact below 2^53)
+      for (int g = 0; g < ngroups; ++g)
+        for (int s = 0; s < stride; ++s)
+          if (counted[s]) o << "  " << acc(g, s) << " += (i64)" << cnt(g, s) << " * " << count_mul[s] << "ll;\n";
+    for (int g = 0; g < ngroups; ++g)
+      for (int s = 0; s < stride; ++s) {
+        const std::string raw = is_float_kind(kinds[s]) ? "d2l(" + acc(g, s) + ")" : acc(g, s);
+        o << "  { const i64 v = warp_fold<" << kinds[s] << ">(" << raw << "); if (lane == 0) red[warp * (NG * STRIDE) + " << g * stride + s << "] = v; }\n";
+      }
+    o << R"(  __syncthreads();
+  for (int cell = tid; cell < NG * STRIDE; cell += NT) {
+    const int kind = KIND[cell % STRIDE];
+    i64 v = red[cell];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) v = agg_combine_k(kind, v, red[w * (NG * STRIDE) + cell]);
+    if (v != INIT[cell % STRIDE]) atomic_fold(kind, p.dense_out + cell, v);
+  }
+}
+)";
+    return true;
+  }
+};
+
+// ---- kernel cache ------------------------------------------------------------------------------------------------
+struct Kernel {
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  std::vector<char> cubin;
+  int regs = 0, occ = 0, nstages = 0;
+  size_t smem = 0;
+};
+
+std::unordered_map<std::string, std::unique_ptr<Kernel>>& cache() {
+  static std::unordered_map<std::string, std::unique_ptr<Kernel>> c;
+  return c;
+}
+
+uint64_t fnv1a(const std::string& s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char ch : s) {
+    h ^= ch;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+std::string disk_cache_path(const std::string& source) {
+  const char* dir = getenv("MSC_JIT_CACHE");
+  if (!dir || !*dir) return "";
+  int major = 0, minor = 0;
+  api().nvrtcVersion(&major, &minor);
+  char name[96];
+  snprintf(name, sizeof(name), "/msc_jit_%016llx_%zu_nvrtc%d.%d_sm100a.cubin", static_cast<unsigned long long>(fnv1a(source)), source.size(), major, minor);
+  return std::string(dir) + name;
+}
+
+int compile(const std::string& source, int minctas, std::vector<char>* cubin, std::string* err) {
+  if (!load_nvrtc(err)) return MSC_ERR_ARG;
+  const std::string path = disk_cache_path(source + "#" + std::to_string(minctas));
+  if (!path.empty()) {
+    std::ifstream f(path, std::ios::binary);
+    if (f) {
+      cubin->assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+      if (!cubin->empty()) return MSC_OK;
+    }
+  }
+  Api& a = api();
+  nvrtcProgram prog = nullptr;
+  if (a.nvrtcCreateProgram(&prog, source.c_str(), "msc_jit_dense.cu", 0, nullptr, nullptr) != 0) {
+    *err = "nvrtcCreateProgram failed";
+    return MSC_ERR_ARG;
+  }
+  const std::string minb = "-DMINCTAS=" + std::to_string(minctas);
+  // --fmad=false: Python rounds every operation (sql.py:262-266); a contracted a * b + c would not
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "--fmad=false", minb.c_str()};
+  const int rc = a.nvrtcCompileProgram(prog, 6, opts);
+  if (rc != 0) {
+    size_t n = 0;
+    a.nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) a.nvrtcGetProgramLog(prog, &log[0]);
+    a.nvrtcDestroyProgram(&prog);
+    if (getenv("MSC_JIT_DUMP")) fprintf(stderr, "%s\n", source.c_str());
+    *err = "compilation failed: " + log.substr(0, 1500);
+    return MSC_ERR_ARG;
+  }
+  size_t n = 0;
+  a.nvrtcGetCUBINSize(prog, &n);
+  cubin->resize(n);
+  a.nvrtcGetCUBIN(prog, cubin->data());
+  a.nvrtcDestroyProgram(&prog);
+  if (!path.empty()) {
+    mkdir(getenv("MSC_JIT_CACHE"), 0755);
+    const std::string tmp = path + ".tmp" + std::to_string(getpid());
+    std::ofstream f(tmp, std::ios::binary);
+    f.write(cubin->data(), static_cast<std::streamsize>(cubin->size()));
+    f.close();
+    rename(tmp.c_str(), path.c_str());
+  }
+  return MSC_OK;
+}
+
+int cu_fail(msc_ctx* ctx, const char* what, int rc) {
+  const char* s = nullptr;
+  if (api().cuGetErrorString) api().cuGetErrorString(rc, &s);
+  return ctx->fail(MSC_ERR_CUDA, std::string("jit: ") + what + " -> " + (s ? s : "error"));
+}
+
+// generated source for this query, or "" with ctx->err set
+int generate(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, int nstages, bool masked,
+             std::string* source, std::string* err) {
+  Gen g{sd, ngroups, naggs, stride, kinds, init, nstages, masked};
+  if (!g.generate()) {
+    *err = g.why;
+    return MSC_ERR_ARG;
+  }
+  *source = g.o.str();
+  return MSC_OK;
+}
+
+}  // namespace
+
+bool jit_dense_supported(const msc_scan_desc* sd, int ngroups, int stride) {
+  // register accumulators: groups x accumulators x 2 registers must leave room for the rows in flight
+  return ngroups >= 1 && ngroups * stride <= JIT_MAX_REG_CELLS && sd->nstaged >= 1 && sd->nstaged <= 24;
+}
+
+// masked: try the mask-table variant first, fall back to the exact one when the program does not allow it
+int generate_either(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, bool* masked,
+                    std::string* source, std::string* err) {
+  if (*masked && generate(sd, ngroups, naggs, stride, kinds, init, 2, true, source, err) == MSC_OK) return MSC_OK;
+  *masked = false;
+  return generate(sd, ngroups, naggs, stride, kinds, init, 2, false, source, err);
+}
+
+int jit_dense_source(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, bool masked,
+                     std::string* source, std::string* err) {
+  return generate_either(sd, ngroups, naggs, stride, kinds, init, &masked, source, err);
+}
+
+int jit_compile_source(const std::string& source, std::vector<char>* cubin, std::string* err) { return compile(source, JIT_MIN_CTAS, cubin, err); }
+
+bool jit_dense_cached(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
+                      bool masked) {
+  std::string source, err;
+  if (generate_either(sd, ngroups, naggs, stride, kinds, init, &masked, &source, &err) != MSC_OK) return false;
+  return cache().count(std::to_string(ctx->device) + "#" + source) != 0;
+}
+
+int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
+                     unsigned long long* table, bool timed, bool* masked) {
+  std::string source, why;
+  if (generate_either(sd, ngroups, naggs, stride, kinds, init, masked, &source, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
+  const std::string key = std::to_string(ctx->device) + "#" + source;
+  auto it = cache().find(key);
+  if (it == cache().end()) {
+    if (!load_driver(&why)) return ctx->fail(MSC_ERR_CUDA, "jit: " + why);
+    auto k = std::make_unique<Kernel>();
+    const auto t0 = std::chrono::steady_clock::now();
+    if (compile(source, JIT_MIN_CTAS, &k->cubin, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
+    ctx->stats.last_jit_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    Api& a = api();
+    int rc = a.cuModuleLoadData(&k->mod, k->cubin.data());
+    if (rc != 0) return cu_fail(ctx, "cuModuleLoadData", rc);
+    rc = a.cuModuleGetFunction(&k->fn, k->mod, "msc_jit_dense");
+    if (rc != 0) return cu_fail(ctx, "cuModuleGetFunction", rc);
+    const Layout lay = stage_layout(sd);
+    k->nstages = 2;
+    k->smem = 4 * 8 * 8 + static_cast<size_t>(NW) * k->nstages * lay.stage_bytes + static_cast<size_t>(NW) * ngroups * stride * 8 +
+              static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8;
+    if (k->smem > 227 * 1024) return ctx->fail(MSC_ERR_ARG, "jit: scan needs more shared memory than an SM has");
+    rc = a.cuFuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, static_cast<int>(k->smem));
+    if (rc != 0) return cu_fail(ctx, "cuFuncSetAttribute", rc);
+    a.cuFuncGetAttribute(&k->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, k->fn);
+    rc = a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&k->occ, k->fn, NT, k->smem);
+    if (rc != 0 || k->occ < 1) return cu_fail(ctx, "cuOccupancyMaxActiveBlocksPerMultiprocessor", rc);
+    it = cache().emplace(key, std::move(k)).first;
+    ctx->stats.jit_compiles += 1;
+  }
+  Kernel& k = *it->second;
+  if (sd->nrows == 0) return MSC_OK;
+  JitParams p;
+  memset(&p, 0, sizeof(p));
+  p.nrows = sd->nrows;
+  p.nrows_dev = reinterpret_cast<const unsigned long long*>(sd->nrows_dev);
+  p.ntiles = static_cast<uint32_t>((sd->nrows + 255) / 256);
+  for (int c = 0; c < sd->nstaged; ++c) {
+    if (!sd->staged[c].data || (reinterpret_cast<uintptr_t>(sd->staged[c].data) & 15) != 0) return ctx->fail(MSC_ERR_ARG, "staged column not 16B aligned");
+    p.col[c] = static_cast<const unsigned char*>(sd->staged[c].data);
+  }
+  for (int c = 0; c < sd->ngather; ++c) p.gather[c] = sd->gather[c].data;
+  for (int c = 0; c < sd->nluts; ++c) p.luts[c] = sd->luts[c];
+  memcpy(p.consts, sd->consts, sizeof(int64_t) * sd->nconsts);
+  p.dense_out = table;
+  p.err = ctx->d_err;
+  uint64_t grid = static_cast<uint64_t>(ctx->sm_count) * k.occ;
+  const uint64_t need = (p.ntiles + NW - 1) / NW;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  void* args[] = {&p};
+  if (timed) MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s0, ctx->stream));
+  const int rc = api().cuLaunchKernel(k.fn, static_cast<unsigned>(grid), 1, 1, NT, 1, 1, static_cast<unsigned>(k.smem),
+                                      reinterpret_cast<CUstream>(ctx->stream), args, nullptr);
+  if (rc != 0) return cu_fail(ctx, "cuLaunchKernel", rc);
+  ctx->stats.launches += 1;
+  if (timed) {
+    MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s1, ctx->stream));
+    ctx->stats.last_scan_grid = static_cast<int32_t>(grid);
+    ctx->stats.last_scan_stages = k.nstages;
+    ctx->stats.last_scan_smem = static_cast<int32_t>(k.smem);
+    ctx->stats.last_scan_rows_per_thread = 8;
+    ctx->stats.last_scan_kind = MSC_SCAN_KIND_JIT;
+    ctx->stats.last_scan_regs = k.regs;
+  }
+  return MSC_OK;
+}
+
+}  // namespace mscan

@@ -1,0 +1,30 @@
+// jit.h -- query-specialised dense aggregate scan (jit.cu): declarations for scan.cu / core.cu.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "scan_kernel.cuh"
+
+namespace mscan {
+
+constexpr int JIT_MAX_REG_CELLS = 32;  // groups x accumulators kept in registers by the specialised kernel
+constexpr int JIT_MIN_CTAS = 4;        // __launch_bounds__(128, 4): at most 128 registers per thread
+
+// can this scan run on a specialised kernel at all (cheap checks; the generator may still refuse a program)?
+bool jit_dense_supported(const msc_scan_desc* sd, int ngroups, int stride);
+// CUDA C++ source of the specialised kernel (no device needed)
+// masked: SUM_F / COUNT by fma with one-hot f64 masks (1 instruction per group and aggregate instead of 3; a non-finite
+// input leaks into the other groups as NaN, so the caller must check the sums and rerun unmasked -- as for the masked
+// regvm variants, gen_regvm.py); programs that do not allow it get the exact form anyway
+int jit_dense_source(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, bool masked,
+                     std::string* source, std::string* err);
+// NVRTC: source -> sm_100a cubin (no device needed)
+int jit_compile_source(const std::string& source, std::vector<char>* cubin, std::string* err);
+// is the kernel for this scan already compiled and loaded in this process?
+bool jit_dense_cached(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
+                      bool masked);
+// compile (or take from the cache) and launch into `table` ([ngroups][stride], already holding the identities)
+int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
+                     unsigned long long* table, bool timed, bool* masked);  // *masked in: allowed, out: used
+
+}  // namespace mscan

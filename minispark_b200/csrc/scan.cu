@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 
+#include "jit.h"
 #include "scan_kernel.cuh"
 #include "scan_regvm.h"
 
@@ -635,9 +636,18 @@ DenseMeta dense_meta(const DensePlan& dp) {
 // init + scan into `table` ([ngroups][stride], device).  allow_masked: a masked regvm variant may run (the caller
 // must then look at the sums: non-finite ones mean "run again with allow_masked = false", gen_regvm.py).
 int dense_scan_into(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, const int32_t* agg_kinds, int naggs, const DensePlan& dp,
-                    bool allow_masked, unsigned long long* table, bool* was_masked) {
+                    bool allow_masked, unsigned long long* table, bool* was_masked, bool want_jit = false) {
   static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
+  // MSC_SCAN_JIT: 0 = never specialise, 1 (default) = when asked (MSC_DENSE_JIT) or already compiled, 2 = always
+  static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
   const int ntot = dp.stride;
+  if (jit_mode > 0 && jit_dense_supported(sd, ngroups, ntot) &&
+      (want_jit || jit_mode > 1 || jit_dense_cached(ctx, sd, ngroups, naggs, ntot, dp.kinds, dp.init, allow_masked && masked_enabled))) {
+    *was_masked = allow_masked && masked_enabled;
+    dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table, ngroups, ntot, dense_meta(dp));
+    ctx->stats.launches += 1;
+    return jit_dense_launch(ctx, sd, ngroups, naggs, ntot, dp.kinds, dp.init, table, true, was_masked);
+  }
   LaunchPlan lp;
   RegvmProgram rv;
   int variant = 0;
@@ -772,16 +782,16 @@ extern "C" int msc_scan_dense_table(msc_ctx* ctx, const msc_scan_desc* sd, int32
   DensePlan dp;
   MSC_TRY(dense_plan(ctx, sd, agg_kinds, naggs, &dp));
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
-  const bool exact_only = (flags & MSC_DENSE_EXACT) != 0;
+  const bool exact_only = (flags & MSC_DENSE_EXACT) != 0, want_jit = (flags & MSC_DENSE_JIT) != 0;
   if (flags & MSC_DENSE_ASYNC) {  // enqueue only: the caller checks the sums after its merge (msc_dense_merge_compact)
     bool masked = false;
-    return dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, !exact_only, static_cast<unsigned long long*>(table), &masked);
+    return dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, !exact_only, static_cast<unsigned long long*>(table), &masked, want_jit);
   }
   DevTmp d_n(ctx);
   MSC_TRY(d_n.alloc(3 * sizeof(unsigned long long)));
   for (int attempt = exact_only ? 1 : 0; attempt < 2; ++attempt) {
     bool masked = false;
-    MSC_TRY(dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, attempt == 0, static_cast<unsigned long long*>(table), &masked));
+    MSC_TRY(dense_scan_into(ctx, sd, ngroups, agg_kinds, naggs, dp, attempt == 0, static_cast<unsigned long long*>(table), &masked, want_jit));
     dense_check_kernel<<<1, 32, 0, ctx->stream>>>(static_cast<const unsigned long long*>(table), ngroups, dp.stride, dense_meta(dp),
                                                  d_n.as<unsigned long long>(), ctx->d_err);
     ctx->stats.launches += 1;
@@ -875,6 +885,36 @@ extern "C" int msc_dense_compact_async(msc_ctx* ctx, const void* table, int32_t 
   MSC_TRY(plan_for_table(ctx, agg_kinds, naggs, stride, count_slot, &dp));
   bool nf = false;
   return dense_compact(ctx, static_cast<const unsigned long long*>(table), ngroups, naggs, dp, out, &nf, true);
+}
+
+extern "C" int msc_jit_dense_source(const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked, char* buf,
+                                    size_t cap, size_t* len) {
+  if (!sd || !agg_kinds || !len || ngroups <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS) return MSC_ERR_ARG;
+  msc_ctx scratch;  // only carries the error text of dense_plan
+  DensePlan dp;
+  if (dense_plan(&scratch, sd, agg_kinds, naggs, &dp) != MSC_OK) return MSC_ERR_ARG;
+  std::string source, err;
+  if (!jit_dense_supported(sd, ngroups, dp.stride)) err = "groups x accumulators exceed the register budget of a specialised kernel";
+  else jit_dense_source(sd, ngroups, naggs, dp.stride, dp.kinds, dp.init, masked != 0, &source, &err);
+  const std::string& text = source.empty() ? err : source;
+  *len = text.size();
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, text.size());
+    memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return source.empty() ? MSC_ERR_ARG : MSC_OK;
+}
+
+extern "C" int msc_jit_compile(const char* source, void* cubin, size_t cap, size_t* len, char* log, size_t log_cap) {
+  if (!source || !len) return MSC_ERR_ARG;
+  std::vector<char> bin;
+  std::string err;
+  const int rc = jit_compile_source(source, &bin, &err);
+  if (log && log_cap) snprintf(log, log_cap, "%s", err.c_str());
+  *len = bin.size();
+  if (rc == MSC_OK && cubin && cap >= bin.size()) memcpy(cubin, bin.data(), bin.size());
+  return rc;
 }
 
 extern "C" int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,

@@ -924,6 +924,8 @@ int launch_scan(msc_ctx* ctx, LaunchPlan* lp) {
     ctx->stats.last_scan_stages = static_cast<int32_t>(lp->p.nstages);
     ctx->stats.last_scan_smem = static_cast<int32_t>(lp->smem);
     ctx->stats.last_scan_rows_per_thread = R;
+    ctx->stats.last_scan_kind = MSC_SCAN_KIND_VM;
+    ctx->stats.last_scan_regs = 0;
   }
   MSC_CUDA(ctx, cudaGetLastError());
   return MSC_OK;

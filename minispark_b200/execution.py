@@ -906,6 +906,7 @@ class _DenseMerge:
 
         self.engine = engine
         self.kinds, self.naggs = kinds, naggs
+        self.persistent = persistent
         comm = engine.comm
         stride, count_slot = C.c_int32(), C.c_int32()
         engine.ctx.call("msc_dense_layout", C.byref(desc), kinds, naggs, C.byref(stride), C.byref(count_slot))
@@ -944,7 +945,7 @@ class _DenseMerge:
         import torch.distributed as dist  # noqa: PLC0415
 
         e = self.engine
-        flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
+        flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0) | (N.K["MSC_DENSE_JIT"] if self.persistent else 0)
         if self.nlocal > 0:
             e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()), flags)
         with torch.cuda.stream(self.stream):
@@ -1028,7 +1029,8 @@ class PreparedAggregate:
             if self.merge is not None:
                 raw_h = self.merge.enqueue(self.desc, exact)
             else:
-                flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
+                # a prepared query runs many times: worth a kernel compiled for exactly this program (csrc/jit.cu)
+                flags = N.K["MSC_DENSE_ASYNC"] | N.K["MSC_DENSE_JIT"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
                 e.ctx.call("msc_scan_dense_table", C.byref(self.desc), self.ngroups, self.kinds, naggs, C.c_void_p(self._table), flags)
                 out = C.c_void_p()
                 e.ctx.call("msc_dense_compact_async", C.c_void_p(self._table), self.ngroups, self._stride, self.kinds, naggs, self._count_slot,
@@ -1056,7 +1058,8 @@ class PreparedAggregate:
             e.ctx.lib.msc_rel_free(C.c_void_p(out2.value))
         st = e.ctx.stats()
         self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
-                           "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread}
+                           "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread, "kind": st.last_scan_kind,
+                           "regs": st.last_scan_regs}
         e._track(DeviceRel(e.ctx, raw_h, 0, []))
         final = e._track(DeviceRel.from_handle(e.ctx, out2.value, [x.type for x in self.plan.outputs], prog2.out_dicts))
         return final, st.last_kernel_ms
@@ -1083,7 +1086,8 @@ class PreparedAggregate:
         st = e.ctx.stats()
         dev_ms = st.last_kernel_ms
         self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
-                           "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread}
+                           "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread, "kind": st.last_scan_kind,
+                           "regs": st.last_scan_regs}
         raw = e._track(DeviceRel.from_handle(e.ctx, out.value, [self.group_type, *self.slot_types], [self.prog.group_dict] + [None] * len(self.slot_types)))
         if e.comm.world > 1:  # hash mode: partition + all-to-all (or all-gather when small)
             raw = e._merge_partials(raw, self.prog.agg_kinds, self.slot_types, self.group_type)

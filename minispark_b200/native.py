@@ -84,6 +84,10 @@ class Stats(C.Structure):
         ("last_scan_stages", C.c_int32),
         ("last_scan_smem", C.c_int32),
         ("last_scan_rows_per_thread", C.c_int32),
+        ("last_scan_kind", C.c_int32),
+        ("last_scan_regs", C.c_int32),
+        ("jit_compiles", C.c_uint64),
+        ("last_jit_compile_ms", C.c_double),
     ]
 
 
@@ -128,6 +132,9 @@ _SIGNATURES = {
     "msc_dense_merge_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
                                           C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "msc_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "msc_jit_dense_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t,
+                             C.POINTER(C.c_size_t)]),
+    "msc_jit_compile": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "msc_rel_nrows_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_rel_settle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int32)]),
     "msc_dense_merge_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,

@@ -1,0 +1,120 @@
+"""Query-specialised dense aggregate kernels (csrc/jit.cu) on the GPU: same answers as the interpreters and the oracle.
+
+A prepared query (engine.prepare) asks for the specialised kernel; MSC_SCAN_JIT=2 (used by the whole-suite rerun in
+DESIGN.md) makes every dense aggregate take it."""
+
+from __future__ import annotations
+
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "bench"))
+
+
+def _table(tmp_path, sf=0.01, rows_per_block=1 << 15):
+    import gen_tpch
+
+    path = tmp_path / "lineitem.bin"
+    gen_tpch.write_table(path, "lineitem", sf=sf, columns=gen_tpch.Q1_COLUMNS, rows_per_block=rows_per_block)
+    return path
+
+
+def _rows(engine, rel, schema):
+    names = [n for n, _ in schema]
+    keys = rel.cols[0].dict.export()
+    cols = [rel.column_numpy(i) for i in range(len(names))]
+    return {keys[int(cols[0][r])]: {n: cols[i][r].item() for i, n in enumerate(names) if i} for r in range(rel.nrows)}
+
+
+def _close(a, b, rel=1e-9):
+    return a == b if isinstance(a, int) and isinstance(b, int) else abs(a - b) <= rel * max(abs(a), abs(b), 1e-300)
+
+
+def test_prepared_q1_runs_the_specialised_kernel_and_matches_the_interpreter(tmp_path):
+    from minispark_b200.execution import CudaExecutionEngine
+
+    path = _table(tmp_path)
+    with CudaExecutionEngine() as engine:
+        task = engine.sql(cases.Q1_SQL.format(table=str(path))).task
+        rel, schema = engine.execute_to_device(task)     # one-shot: interpreter
+        assert engine.ctx.stats().last_scan_kind != 2
+        want = _rows(engine, rel, schema)
+        engine.release_query()
+        prepared = engine.prepare(task)
+        schema = prepared.plan.schema
+        for _ in range(3):
+            final, _ms = prepared.run()
+            assert prepared.scan_stats["kind"] == 2 and prepared.scan_stats["regs"] > 0
+            got = _rows(engine, final, schema)
+            engine.release_query()
+            assert got.keys() == want.keys()
+            for k in want:
+                for name, v in want[k].items():
+                    assert _close(got[k][name], v), (k, name, got[k][name], v)
+        assert engine.ctx.stats().jit_compiles == 1      # compiled once, then taken from the cache
+        # once compiled, the one-shot path takes the kernel too
+        rel, schema = engine.execute_to_device(task)
+        assert engine.ctx.stats().last_scan_kind == 2
+        again = _rows(engine, rel, schema)
+        for k in want:
+            for name, v in want[k].items():
+                assert _close(again[k][name], v)
+
+
+def test_prepared_q1_matches_the_c_oracle(tmp_path):
+    from bench import run_q1_port  # noqa: PLC0415  (repo root is on sys.path via conftest)
+    from minispark_b200.execution import CudaExecutionEngine
+
+    path = _table(tmp_path, sf=0.02)
+    oracle = run_q1_port(path, 2, 0, 0)
+    with CudaExecutionEngine() as engine:
+        task = engine.sql(cases.Q1_SQL.format(table=str(path))).task
+        prepared = engine.prepare(task)
+        final, _ = prepared.run()
+        schema = prepared.plan.schema
+        got = _rows(engine, final, schema)
+        assert prepared.scan_stats["kind"] == 2
+    assert len(oracle["groups"]) == len(got)
+    for g in oracle["groups"]:
+        mine = got[g["key"]]
+        assert mine["count_order"] == g["count"]
+        for name in ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge"):
+            assert abs(mine[name] - g[name]) <= 1e-9 * abs(g[name]), (g["key"], name)
+        assert abs(mine["avg_disc"] - g["sum_disc"] / g["count"]) <= 1e-9 * abs(g["sum_disc"] / g["count"])
+
+
+def test_non_finite_inputs_rerun_on_the_exact_variant(tmp_path):
+    """A masked fma turns inf * 0.0 into NaN in the other groups; the pass must notice and repeat unmasked."""
+    from minispark_b200 import BlockFile
+    from minispark_b200.constants import ColumnType
+    from minispark_b200.execution import CudaExecutionEngine
+
+    path = tmp_path / "t.bin"
+    n = 5000
+    rng = np.random.default_rng(7)
+    vals = rng.uniform(1, 10, n).astype(np.float32).astype(float).tolist()
+    vals[17] = float("inf")
+    keys = ["a" if i % 3 == 0 else "b" if i % 3 == 1 else "c" for i in range(n)]
+    BlockFile(path, [("k", ColumnType.STRING), ("v", ColumnType.FLOAT)]).write_rows([{"k": k, "v": v} for k, v in zip(keys, vals)])
+    with CudaExecutionEngine() as engine:
+        task = engine.sql(f"SELECT k, SUM(v) AS s, COUNT() AS c FROM '{path}' GROUP BY k").task
+        prepared = engine.prepare(task)
+        final, _ = prepared.run()
+        schema = prepared.plan.schema
+        got = _rows(engine, final, schema)
+        assert prepared.scan_stats["kind"] == 2
+    for k in "abc":
+        mine = [v for kk, v in zip(keys, vals) if kk == k]
+        assert got[k]["c"] == len(mine)
+        if any(math.isinf(v) for v in mine):
+            assert math.isinf(got[k]["s"])
+        else:
+            assert math.isfinite(got[k]["s"]) and abs(got[k]["s"] - math.fsum(mine)) <= 1e-9 * math.fsum(mine)
