@@ -113,14 +113,15 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def captured_traffic(sf: float, layout: str, rows: int, bytes_per_row: int) -> tuple[float | None, str | None]:
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very workload (profiles/)."""
+def captured_traffic(sf: float, layout: str, rows: int, bytes_per_row: int, kernel: str) -> tuple[float | None, str | None]:
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very workload and kernel (profiles/)."""
     path = ROOT / "profiles" / "r01_traffic.json"
     if not path.exists():
         return None, None
     for cap in json.loads(path.read_text()).get("captures", []):
         w = cap["workload"]
-        if (w["sf_per_gpu"], w["layout"], w["rows_per_gpu"], w["bytes_per_row_scanned"]) == (sf, layout, rows, bytes_per_row):
+        same_kernel = kernel.startswith(cap["kernel"].split("::")[-1])
+        if same_kernel and (w["sf_per_gpu"], w["layout"], w["rows_per_gpu"], w["bytes_per_row_scanned"]) == (sf, layout, rows, bytes_per_row):
             return float(cap["traffic_bytes"]), f"profiles/r01_traffic.json ({cap['capture']})"
     return None, None
 
@@ -342,7 +343,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
         scan_ms = statistics.mean(scan_ms_all)
         achieved = nrows_table * bytes_per_row / (scan_ms * 1e-3) / 1e9
         peak, peak_src = peaks()
-        traffic, traffic_src = captured_traffic(args.sf, args.layout, nrows_table, bytes_per_row)
+        kernel = kernel_name(agg_launch["rows_per_thread"], agg_launch.get("kind", 0), agg_launch.get("regs", 0))
+        traffic, traffic_src = captured_traffic(args.sf, args.layout, nrows_table, bytes_per_row, kernel)
 
         # ---- e2e: pinned host image -> H2D -> decode -> scan -> result back on the host -----------------
         e2e_times, h2d_bytes, d2h_bytes = [], 0, 0
@@ -385,7 +387,7 @@ def cuda_arm(args: argparse.Namespace) -> None:
                     "wall_ms_per_step": 1e3 * wall_max / args.steps, "parity_check": check,
                 },
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                             "kernel": kernel_name(agg_launch["rows_per_thread"], agg_launch.get("kind", 0), agg_launch.get("regs", 0)), "launch": agg_launch,
+                             "kernel": kernel, "launch": agg_launch,
                              "program": prepared.prog.program.text,
                              "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": nrows_table * bytes_per_row, "peak_source": peak_src,
                              "north_star_layout_equiv_gbs": nrows_table * Q1_WIDE_BYTES_PER_ROW / (scan_ms * 1e-3) / 1e9 if args.layout == "native" else None},

@@ -511,7 +511,18 @@ int compile(const std::string& source, int minctas, std::vector<char>* cubin, st
   }
   Api& a = api();
   nvrtcProgram prog = nullptr;
-  if (a.nvrtcCreateProgram(&prog, source.c_str(), "msc_jit_dense.cu", 0, nullptr, nullptr) != 0) {
+  // MSC_JIT_DUMP_DIR=<dir>: keep the generated source as a file and compile it under that name, so that profilers
+  // (ncu --import-source) and cuobjdump -lineinfo can show it
+  std::string name = "msc_jit_dense.cu";
+  if (const char* dump = getenv("MSC_JIT_DUMP_DIR")) {
+    mkdir(dump, 0755);
+    char file[64];
+    snprintf(file, sizeof(file), "/msc_jit_%016llx.cu", static_cast<unsigned long long>(fnv1a(source)));
+    name = std::string(dump) + file;
+    std::ofstream f(name);
+    f << source;
+  }
+  if (a.nvrtcCreateProgram(&prog, source.c_str(), name.c_str(), 0, nullptr, nullptr) != 0) {
     *err = "nvrtcCreateProgram failed";
     return MSC_ERR_ARG;
   }

@@ -660,6 +660,7 @@ class CudaExecutionEngine(ExecutionEngine):
         self.last_stats["scan_grid"] = st.last_scan_grid
         self.last_stats["scan_stages"] = st.last_scan_stages
         self.last_stats["scan_smem"] = st.last_scan_smem
+        self.last_stats["scan_kind"] = st.last_scan_kind  # N.K["MSC_SCAN_KIND_*"]: which kernel ran this (aggregate) scan
         self.last_stats["launches"] = st.launches
 
     def _run_select(self, sel: L.LSelect, translate_targets: Optional[dict[str, DictHandle]] = None) -> DeviceRel:
@@ -705,6 +706,7 @@ class CudaExecutionEngine(ExecutionEngine):
             out = C.c_void_p()
             self.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), hint, C.byref(out))
             self._note_kernel()
+            self.last_stats["agg_scan_kind"] = self.last_stats["scan_kind"]  # later scans (final projection) overwrite scan_kind
             raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
             if self.comm.world > 1:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
                 raw = self._merge_partials(raw, prog.agg_kinds, slot_types, group.type)
