@@ -32,6 +32,8 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--sf", type=float, default=2.0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--jit", default=None, help="engine jit mode: auto | always | never")
+    ap.add_argument("--only", default="", help="comma-separated config name prefixes to run")
     args = ap.parse_args()
     import cases
     import gen_tpch
@@ -59,8 +61,20 @@ def main() -> None:
                 .filter(ns.Col("l.l_shipmode").like("%AIR%"))
                 .group_by(ns.Col("o.o_orderpriority")).agg(ns.F.count(), ns.F.sum(ns.Col("l.l_extendedprice")).alias("rev")))
 
-    with CudaExecutionEngine(device=0, shard=(0, 1)) as e:
-        for name, build in (("config4_high_cardinality_group_by", config4), ("config5_join_filter_like_group_by", config5)):
+    def filter_project(e):  # noqa: ANN001, ANN202  (FilterTask + ProjectTask, tasks.py:79-84,167-177: about half of the rows survive)
+        return (ns.DataFrame(e).table(str(lineitem)).filter(ns.Col("l_quantity") > 25.0)
+                .select(ns.Col("l_orderkey"), (ns.Col("l_extendedprice") * ns.Col("l_quantity")).alias("v"), ns.Col("l_shipmode")))
+
+    def project_only(e):  # noqa: ANN001, ANN202
+        return ns.DataFrame(e).table(str(lineitem)).select((ns.Col("l_extendedprice") * ns.Col("l_quantity")).alias("v"))
+
+    configs = (("config4_high_cardinality_group_by", config4), ("config5_join_filter_like_group_by", config5),
+               ("filter_project", filter_project), ("project_only", project_only))
+    only = [x for x in args.only.split(",") if x]
+    with CudaExecutionEngine(device=0, shard=(0, 1), jit=args.jit) as e:
+        for name, build in configs:
+            if only and not any(name.startswith(x) for x in only):
+                continue
             task = build(e).task
             times, rows_out = [], 0
             for i in range(args.reps + 1):
@@ -77,7 +91,8 @@ def main() -> None:
             med = statistics.median(times)
             print(json.dumps({"config": name, "sf": args.sf, "lineitem_rows": nl, "result_rows": rows_out, "ms": round(1e3 * med, 3),
                               "lineitem_rows_per_s": nl / med, "passes_ms": [round(1e3 * t, 2) for t in times],
-                              "last_kernel_ms": stats.get("kernel_ms"), "agg_mode": stats.get("agg_mode")}), flush=True)
+                              "last_kernel_ms": stats.get("kernel_ms"), "agg_mode": stats.get("agg_mode"), "jit": e.jit,
+                              "scan_kind": stats.get("scan_kind"), "jit_compiles": e.ctx.stats().jit_compiles}), flush=True)
     if os.environ.get("MSC_BENCH_KEEP") is None:
         lineitem.unlink(missing_ok=True)
         orders.unlink(missing_ok=True)

@@ -190,6 +190,11 @@ typedef struct msc_scan_desc {
    * an upper bound used for launch geometry and allocation; msc_scan_project returns a pending relation without
    * waiting for the device. */
   const uint64_t* nrows_dev;
+  /* != 0: run this scan on a kernel specialised for its program (compiled with NVRTC on first use, see MSC_DENSE_JIT);
+   * 0: use such a kernel only when this process has already compiled it.  msc_scan_project reads it; the dense
+   * aggregate entry points take MSC_DENSE_JIT in their flags instead. */
+  int32_t want_jit;
+  int32_t _pad2;
 } msc_scan_desc;
 
 typedef struct msc_stats {
@@ -325,6 +330,10 @@ MSC_API int msc_dense_compact_async(msc_ctx* ctx, const void* table, int32_t ngr
  * the exact variant is what MSC_DENSE_EXACT, or a non-finite sum, falls back to). */
 MSC_API int msc_jit_dense_source(const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked, char* buf,
                          size_t cap, size_t* len);
+/* the same for a filter / project scan: count_only != 0 gives the first pass (surviving rows per 256-row tile), else
+ * the pass that writes the output columns at their stable positions */
+MSC_API int msc_jit_project_source(const msc_scan_desc* scan, int32_t count_only, const int32_t* out_phys, int32_t nout, char* buf, size_t cap,
+                           size_t* len);
 MSC_API int msc_jit_compile(const char* source, void* cubin, size_t cap, size_t* len, char* log, size_t log_cap);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,

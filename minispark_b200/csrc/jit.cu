@@ -44,8 +44,12 @@ struct JitParams {  // must match struct JitParams in jit_prelude.inc
   long long consts[32];
   unsigned long long* dense_out;
   int* err;
+  uint32_t* tile_counts;
+  const unsigned long long* tile_offsets;
+  void* out[24];
 };
-static_assert(MSC_VM_MAX_STAGED == 24 && MSC_VM_MAX_GATHER == 16 && MSC_VM_MAX_LUTS == 8 && MSC_VM_MAX_CONSTS == 32, "JitParams layout");
+static_assert(MSC_VM_MAX_STAGED == 24 && MSC_VM_MAX_GATHER == 16 && MSC_VM_MAX_LUTS == 8 && MSC_VM_MAX_CONSTS == 32 && MSC_VM_MAX_OUT == 24,
+              "JitParams layout");
 
 // ---- NVRTC + driver API through dlopen ------------------------------------------------------------------------
 typedef struct _nvrtcProgram* nvrtcProgram;
@@ -163,14 +167,15 @@ struct Gen {
   std::ostringstream o;
   std::string why;
   bool counted[MSC_VM_MAX_AGGS + 1] = {};  // slot is "SUM_I of a constant": counted in a u32 per tile, folded at the tile's end
-  long long count_mul[MSC_VM_MAX_AGGS + 1] = {};
+  int count_const[MSC_VM_MAX_AGGS + 1] = {};  // index of that constant in p.consts (-1: the hidden row counter, times 1)
+  std::string count_mul(int s) { return count_const[s] < 0 ? std::string("1ll") : "p.consts[" + std::to_string(count_const[s]) + "]"; }
 
   std::string operand(uint32_t opnd, bool* ok) {
     const int kind = (opnd >> 12) & 7, idx = opnd & 0xfff;
     const bool i2f = ((opnd >> 12) & MSC_SRC_I2F) != 0;
     std::string s;
     switch (kind) {
-      case MSC_SRC_TEMP: s = "t" + std::to_string(idx); break;
+      case MSC_SRC_TEMP: s = temp(idx); break;
       case MSC_SRC_STAGED: s = "c" + std::to_string(idx) + "[r]"; break;
       case MSC_SRC_CONST: s = "p.consts[" + std::to_string(idx) + "]"; break;
       case MSC_SRC_GATHER:
@@ -225,6 +230,8 @@ struct Gen {
     }
   }
 
+  bool temp_arrays = false;  // project scans run the program in two row loops, so temporaries are arrays over the rows
+  std::string temp(int idx) { return "t" + std::to_string(idx) + (temp_arrays ? "[r]" : ""); }
   std::string acc(int g, int s) { return "a" + std::to_string(g) + "_" + std::to_string(s); }
   std::string cnt(int g, int s) { return "n" + std::to_string(g) + "_" + std::to_string(s); }
 
@@ -245,6 +252,208 @@ struct Gen {
     o << "        }\n";
   }
 
+  // shared text: constants of the stage layout + the tile issue function
+  void emit_layout(const Layout& lay) {
+    o << "constexpr u32 STAGE_BYTES = " << lay.stage_bytes << ", TX_BYTES = " << lay.tx_bytes << ", NSTAGED = " << sd->nstaged << ";\n";
+    o << "__device__ const u32 COL_OFF[" << std::max(1, sd->nstaged) << "] = {";
+    for (int c = 0; c < sd->nstaged; ++c) o << (c ? ", " : "") << lay.off[c];
+    if (!sd->nstaged) o << "0";
+    o << "};\n__device__ const u32 COL_BYTES[" << std::max(1, sd->nstaged) << "] = {";
+    for (int c = 0; c < sd->nstaged; ++c) o << (c ? ", " : "") << lay.tile_bytes[c];
+    if (!sd->nstaged) o << "0";
+    o << "};\n";
+    o << R"(__device__ __forceinline__ void issue_tile(const JitParams& p, unsigned char* stages, u64* full, u32 stage, u64 tile, int lane) {
+  if (lane == 0) mbar_expect_tx(&full[stage], TX_BYTES);
+  __syncwarp();
+  if (lane < (int)NSTAGED) bulk_g2s(stages + stage * STAGE_BYTES + COL_OFF[lane], p.col[lane] + tile * COL_BYTES[lane], COL_BYTES[lane], &full[stage]);
+}
+)";
+  }
+
+  // one instruction of the row program inside a row loop (temporaries through temp()); returns false on an unsupported one.
+  // OUT destinations go to o<dst>[r]; FILTER narrows `valid`.
+  bool emit_row_instruction(int pc, bool allow_out) {
+    const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
+    const int op = w0 & 0x3f;
+    const int dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
+    const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
+    const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+    bool ok = true;
+    const std::string a = operand(oa, &ok), b = lut ? std::string("0ll") : operand(ob, &ok);
+    if (dkind == MSC_DST_OUT && !allow_out) return true;  // a count scan only needs the filters
+    o << "      {  // instruction " << pc / 2 << "\n";
+    if (op == MSC_OP_DIV_F || op == MSC_OP_FLOORDIV_F || op == MSC_OP_MOD_F) o << "        bad |= valid && (l2d(" << b << ") == 0.0);\n";
+    if (op == MSC_OP_FLOORDIV_I || op == MSC_OP_MOD_I) o << "        bad |= valid && ((" << b << ") == 0);\n";
+    o << "        const i64 x = " << compute(op, a, b, ob, &ok) << ";\n";
+    if (tee) o << "        " << temp(tee - 1) << " = x;\n";
+    switch (dkind) {
+      case MSC_DST_TEMP: o << "        " << temp(dst) << " = x;\n"; break;
+      case MSC_DST_FILTER: o << "        valid = valid && (x != 0);\n"; break;
+      case MSC_DST_OUT: o << "        o" << dst << "[r] = x;\n"; break;
+      case MSC_DST_NONE: break;
+      default: why = "destination kind outside a project scan"; return false;
+    }
+    o << "      }\n";
+    if (!ok) why = "operand or opcode outside the generator";
+    return ok;
+  }
+
+  // COUNT (count_only) and PROJECT scans: FilterTask / ProjectTask (tasks.py:79-84, 167-177) with stable compaction.
+  // The program is [filters..] RANK [outputs..] (lowering.py compile_project); without a filter there is no RANK and
+  // a row's output position is its row number.
+  bool generate_project(bool count_only, const int32_t* out_phys, int nout) {
+    const Layout lay = stage_layout(sd);
+    temp_arrays = true;
+    int rank_pc = -1, end_pc = 0;
+    bool has_filter = false;
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+      const int op = sd->code[pc] & 0x3f;
+      if (op == MSC_OP_END) break;
+      end_pc = pc + 2;
+      if (op == MSC_OP_RANK) rank_pc = pc;
+      const int dk = (sd->code[pc] >> 6) & 7;
+      if (dk == MSC_DST_FILTER) {
+        has_filter = true;
+        if (rank_pc >= 0) {
+          why = "filter after RANK";
+          return false;
+        }
+      }
+      if (dk == MSC_DST_GROUP || dk == MSC_DST_AGG) {
+        why = "aggregate destination in a project scan";
+        return false;
+      }
+    }
+    if (has_filter && rank_pc < 0) {
+      why = "filtered projection needs a RANK instruction";
+      return false;
+    }
+    if (count_only && !has_filter) {
+      why = "count scan without a filter";
+      return false;
+    }
+    o << kPrelude;
+    o << "constexpr int NSTAGES = " << nstages << ";\n";
+    emit_layout(lay);
+    o << R"(
+extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_scan(const __grid_constant__ JitParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64* full = reinterpret_cast<u64*>(smem) + warp * 8;
+  unsigned char* stages = smem + SMEM_HEADER + warp * (NSTAGES * STAGE_BYTES);
+  if (lane == 0) {
+    for (u32 st = 0; st < NSTAGES; ++st) mbar_init(&full[st], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const u32 gw = blockIdx.x * NW + warp, nw = gridDim.x * NW;
+  const u32 ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
+  {
+    const u32 pre = ntiles_w < NSTAGES ? ntiles_w : NSTAGES;
+    for (u32 k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + (u64)k * nw, lane);
+  }
+  const u64 nrows = p.nrows_dev ? *p.nrows_dev : p.nrows;
+  bool bad = false;
+  u32 stage = 0, parity = 0;
+  for (u32 k = 0; k < ntiles_w; ++k) {
+    const u64 tile = gw + (u64)k * nw;
+    const unsigned char* sb = stages + stage * STAGE_BYTES;
+    while (!mbar_try_wait(&full[stage], parity)) {
+    }
+    u32 vmask = 0xffu;
+    const u64 tile_row0 = tile * WT;
+    if (tile_row0 + WT > nrows) {
+      vmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (tile_row0 + (r / 4) * 128 + 4 * lane + (r % 4) < nrows) vmask |= 1u << r;
+    }
+)";
+    for (int c = 0; c < sd->nstaged; ++c)
+      o << "    i64 c" << c << "[R]; " << ld_fn(sd->staged[c].phys) << "(sb + " << lay.off[c] << ", lane, c" << c << ");\n";
+    for (int t = 0; t < sd->ntemps; ++t) o << "    i64 t" << t << "[R];\n";
+    if (!count_only)
+      for (int c = 0; c < nout; ++c) o << "    i64 o" << c << "[R];\n";
+    // phase 1: the filters
+    const int phase1_end = rank_pc >= 0 ? rank_pc : 0;
+    o << "    u32 keep = 0;\n#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = (vmask >> r) & 1u;\n";
+    for (int t = 0; t < sd->ntemps; ++t) o << "      t" << t << "[r] = 0;\n";
+    for (int pc = 0; pc < phase1_end; pc += 2)
+      if (!emit_row_instruction(pc, false)) return false;
+    o << "      keep |= (valid ? 1u : 0u) << r;\n    }\n";
+    if (count_only) {
+      o << R"(    {
+      u32 n = __popc(keep);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+      if (lane == 0) p.tile_counts[tile] = n;
+    }
+)";
+    } else {
+      // phase 2: the outputs of the surviving rows (rows that were filtered out compute harmless values; loads through
+      // gathers / lookup tables look at `valid`)
+      o << "#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      const bool valid = (keep >> r) & 1u;\n";
+      for (int pc = rank_pc >= 0 ? rank_pc + 2 : 0; pc < end_pc; pc += 2)
+        if (!emit_row_instruction(pc, true)) return false;
+      o << "    }\n";
+      // stable output positions: rows 4*lane..4*lane+3 of each 128-row half, halves in order
+      if (has_filter) {
+        o << R"(    u64 pos0, pos1;
+    {
+      const u32 c = __popc(keep & 0xfu) | (__popc(keep >> 4) << 16);  // survivors of this lane in half 0 | half 1
+      u32 inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      const u32 total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - c;
+      const u64 base = p.tile_offsets[tile];
+      pos0 = base + (excl & 0xffffu);
+      pos1 = base + (total & 0xffffu) + (excl >> 16);
+    }
+)";
+      } else {
+        o << "    const u64 pos0 = tile_row0 + 4 * lane, pos1 = pos0 + 128;\n";
+      }
+      for (int c = 0; c < nout; ++c) {
+        const bool u32out = out_phys[c] == MSC_P_U32;
+        const std::string ty = u32out ? "u32" : "i64";
+        o << "    {\n      " << ty << "* out = reinterpret_cast<" << ty << "*>(p.out[" << c << "]);\n";
+        if (!has_filter) {  // whole tiles go out as 128-bit stores
+          o << "      if (vmask == 0xffu) {\n";
+          if (u32out) {
+            o << "        *reinterpret_cast<uint4*>(out + pos0) = make_uint4((u32)o" << c << "[0], (u32)o" << c << "[1], (u32)o" << c << "[2], (u32)o" << c << "[3]);\n";
+            o << "        *reinterpret_cast<uint4*>(out + pos1) = make_uint4((u32)o" << c << "[4], (u32)o" << c << "[5], (u32)o" << c << "[6], (u32)o" << c << "[7]);\n";
+          } else {
+            for (int h = 0; h < 2; ++h)
+              for (int j = 0; j < 2; ++j)
+                o << "        *reinterpret_cast<longlong2*>(out + pos" << h << " + " << 2 * j << ") = make_longlong2(o" << c << "[" << 4 * h + 2 * j << "], o" << c
+                  << "[" << 4 * h + 2 * j + 1 << "]);\n";
+          }
+          o << "      } else {\n";
+        } else {
+          o << "      {\n";
+        }
+        o << "        u64 q0 = pos0, q1 = pos1;\n#pragma unroll\n        for (int r = 0; r < 4; ++r) {\n";
+        o << "          if ((keep >> r) & 1u) out[" << (has_filter ? "q0++" : "q0 + r") << "] = (" << ty << ")o" << c << "[r];\n";
+        o << "          if ((keep >> (r + 4)) & 1u) out[" << (has_filter ? "q1++" : "q1 + r") << "] = (" << ty << ")o" << c << "[r + 4];\n";
+        o << "        }\n      }\n    }\n";
+      }
+    }
+    o << R"(    __syncwarp();
+    if (k + NSTAGES < ntiles_w) issue_tile(p, stages, full, stage, gw + (u64)(k + NSTAGES) * nw, lane);
+    if (++stage == NSTAGES) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (bad) atomicOr(p.err, 1);  // MSC_DEVERR_DIV_ZERO
+}
+)";
+    return true;
+  }
+
   bool generate() {
     const Layout lay = stage_layout(sd);
     // which accumulators are SUM_I of a constant (COUNT, plan.py:190-204 / sql.py:463-464)?
@@ -257,7 +466,7 @@ struct Gen {
       const uint32_t a = w1 & 0xffffu;
       if (dkind == MSC_DST_AGG && op == MSC_OP_MOV && tee == 0 && ((a >> 12) & 15) == MSC_SRC_CONST && kinds[dst] == MSC_AGG_SUM_I) {
         counted[dst] = true;
-        count_mul[dst] = sd->consts[a & 0xfff];
+        count_const[dst] = static_cast<int>(a & 0xfff);
       }
     }
     for (int pc = 0, seen[MSC_VM_MAX_AGGS + 1] = {}; pc + 1 < sd->ncode; pc += 2) {  // a slot written twice is not a plain count
@@ -267,7 +476,7 @@ struct Gen {
     }
     if (stride > naggs) {  // hidden per-group row counter
       counted[naggs] = true;
-      count_mul[naggs] = 1;
+      count_const[naggs] = -1;
     }
 
     o << kPrelude;
@@ -394,9 +603,9 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       if (op == MSC_OP_FLOORDIV_I || op == MSC_OP_MOD_I) o << "        bad |= valid && ((" << b << ") == 0);\n";
       const bool plain_count = dkind == MSC_DST_AGG && counted[dst];
       if (!plain_count) o << "        const i64 x = " << compute(op, a, b, ob, &ok) << ";\n";
-      if (tee) o << "        t" << tee - 1 << " = x;\n";
+      if (tee) o << "        " << temp(tee - 1) << " = x;\n";
       switch (dkind) {
-        case MSC_DST_TEMP: o << "        t" << dst << " = x;\n"; break;
+        case MSC_DST_TEMP: o << "        " << temp(dst) << " = x;\n"; break;
         case MSC_DST_FILTER: o << "        valid = valid && (x != 0);\n"; break;
         case MSC_DST_GROUP:
           o << "        grp = (x >= 0 && x < NG) ? (int)x : -1;\n";
@@ -433,7 +642,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     // fold the tile's u32 row counts into their i64 accumulators (8 rows per lane and tile: no overflow)
     for (int g = 0; g < ngroups; ++g)
       for (int s = 0; s < stride; ++s)
-        if (counted[s] && !masked) o << "    " << acc(g, s) << " += (i64)" << cnt(g, s) << " * " << count_mul[s] << "ll; " << cnt(g, s) << " = 0;\n";
+        if (counted[s] && !masked) o << "    " << acc(g, s) << " += (i64)" << cnt(g, s) << " * " << count_mul(s) << "; " << cnt(g, s) << " = 0;\n";
     o << R"(    __syncwarp();
     if (k + NSTAGES < ntiles_w) issue_tile(p, stages, full, stage, gw + (u64)(k + NSTAGES) * nw, lane);
     if (++stage == NSTAGES) {
@@ -446,7 +655,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     if (masked)  // row counts were summed as f64 (exact below 2^53)
       for (int g = 0; g < ngroups; ++g)
         for (int s = 0; s < stride; ++s)
-          if (counted[s]) o << "  " << acc(g, s) << " += (i64)" << cnt(g, s) << " * " << count_mul[s] << "ll;\n";
+          if (counted[s]) o << "  " << acc(g, s) << " += (i64)" << cnt(g, s) << " * " << count_mul(s) << ";\n";
     for (int g = 0; g < ngroups; ++g)
       for (int s = 0; s < stride; ++s) {
         const std::string raw = is_float_kind(kinds[s]) ? "d2l(" + acc(g, s) + ")" : acc(g, s);
@@ -596,17 +805,42 @@ int jit_dense_source(const msc_scan_desc* sd, int ngroups, int naggs, int stride
 
 int jit_compile_source(const std::string& source, std::vector<char>* cubin, std::string* err) { return compile(source, JIT_MIN_CTAS, cubin, err); }
 
-bool jit_dense_cached(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
-                      bool masked) {
-  std::string source, err;
-  if (generate_either(sd, ngroups, naggs, stride, kinds, init, &masked, &source, &err) != MSC_OK) return false;
-  return cache().count(std::to_string(ctx->device) + "#" + source) != 0;
+// Everything the generated source depends on, as bytes: a launch finds its kernel through this key without building
+// the source text again (constants are kernel parameters, so a different date literal reuses the kernel).
+std::string shape_key(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, bool masked) {
+  std::string k;
+  auto put = [&](const void* p, size_t n) { k.append(static_cast<const char*>(p), n); };
+  const int head[8] = {ctx->device, masked ? 1 : 0, ngroups, naggs, stride, sd->nstaged, sd->ngather, sd->ntemps};
+  put(head, sizeof(head));
+  put(kinds, sizeof(int) * stride);
+  put(init, sizeof(long long) * stride);
+  for (int c = 0; c < sd->nstaged; ++c) put(&sd->staged[c].phys, sizeof(int32_t));
+  for (int c = 0; c < sd->ngather; ++c) put(&sd->gather[c].phys, sizeof(int32_t));
+  int n = 0;
+  while (n + 1 < sd->ncode && (sd->code[n] & 0x3f) != MSC_OP_END) n += 2;
+  put(sd->code, sizeof(uint32_t) * n);
+  return k;
 }
 
-int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
-                     unsigned long long* table, bool timed, bool* masked) {
-  std::string source, why;
-  if (generate_either(sd, ngroups, naggs, stride, kinds, init, masked, &source, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
+struct ShapeEntry {
+  Kernel* kernel;
+  bool masked;  // the variant that was generated (a program may refuse the masked form)
+};
+std::unordered_map<std::string, ShapeEntry>& shapes() {
+  static std::unordered_map<std::string, ShapeEntry> m;
+  return m;
+}
+
+bool jit_dense_cached(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
+                      bool masked) {
+  return shapes().count(shape_key(ctx, sd, ngroups, naggs, stride, kinds, init, masked)) != 0;
+}
+
+namespace {
+
+// compile (or find) the kernel of `source`, load it into this device's context and size its launch
+int load_kernel(msc_ctx* ctx, const std::string& source, const char* fn_name, size_t smem, Kernel** out) {
+  std::string why;
   const std::string key = std::to_string(ctx->device) + "#" + source;
   auto it = cache().find(key);
   if (it == cache().end()) {
@@ -618,12 +852,10 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
     Api& a = api();
     int rc = a.cuModuleLoadData(&k->mod, k->cubin.data());
     if (rc != 0) return cu_fail(ctx, "cuModuleLoadData", rc);
-    rc = a.cuModuleGetFunction(&k->fn, k->mod, "msc_jit_dense");
+    rc = a.cuModuleGetFunction(&k->fn, k->mod, fn_name);
     if (rc != 0) return cu_fail(ctx, "cuModuleGetFunction", rc);
-    const Layout lay = stage_layout(sd);
     k->nstages = 2;
-    k->smem = 4 * 8 * 8 + static_cast<size_t>(NW) * k->nstages * lay.stage_bytes + static_cast<size_t>(NW) * ngroups * stride * 8 +
-              static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8;
+    k->smem = smem;
     if (k->smem > 227 * 1024) return ctx->fail(MSC_ERR_ARG, "jit: scan needs more shared memory than an SM has");
     rc = a.cuFuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, static_cast<int>(k->smem));
     if (rc != 0) return cu_fail(ctx, "cuFuncSetAttribute", rc);
@@ -633,27 +865,32 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
     it = cache().emplace(key, std::move(k)).first;
     ctx->stats.jit_compiles += 1;
   }
-  Kernel& k = *it->second;
-  if (sd->nrows == 0) return MSC_OK;
-  JitParams p;
-  memset(&p, 0, sizeof(p));
-  p.nrows = sd->nrows;
-  p.nrows_dev = reinterpret_cast<const unsigned long long*>(sd->nrows_dev);
-  p.ntiles = static_cast<uint32_t>((sd->nrows + 255) / 256);
+  *out = it->second.get();
+  return MSC_OK;
+}
+
+int fill_params(msc_ctx* ctx, const msc_scan_desc* sd, JitParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->nrows = sd->nrows;
+  p->nrows_dev = reinterpret_cast<const unsigned long long*>(sd->nrows_dev);
+  p->ntiles = static_cast<uint32_t>((sd->nrows + 255) / 256);
   for (int c = 0; c < sd->nstaged; ++c) {
     if (!sd->staged[c].data || (reinterpret_cast<uintptr_t>(sd->staged[c].data) & 15) != 0) return ctx->fail(MSC_ERR_ARG, "staged column not 16B aligned");
-    p.col[c] = static_cast<const unsigned char*>(sd->staged[c].data);
+    p->col[c] = static_cast<const unsigned char*>(sd->staged[c].data);
   }
-  for (int c = 0; c < sd->ngather; ++c) p.gather[c] = sd->gather[c].data;
-  for (int c = 0; c < sd->nluts; ++c) p.luts[c] = sd->luts[c];
-  memcpy(p.consts, sd->consts, sizeof(int64_t) * sd->nconsts);
-  p.dense_out = table;
-  p.err = ctx->d_err;
+  for (int c = 0; c < sd->ngather; ++c) p->gather[c] = sd->gather[c].data;
+  for (int c = 0; c < sd->nluts; ++c) p->luts[c] = sd->luts[c];
+  memcpy(p->consts, sd->consts, sizeof(int64_t) * sd->nconsts);
+  p->err = ctx->d_err;
+  return MSC_OK;
+}
+
+int launch(msc_ctx* ctx, Kernel& k, JitParams* p, bool timed) {
   uint64_t grid = static_cast<uint64_t>(ctx->sm_count) * k.occ;
-  const uint64_t need = (p.ntiles + NW - 1) / NW;
+  const uint64_t need = (p->ntiles + NW - 1) / NW;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  void* args[] = {&p};
+  void* args[] = {p};
   if (timed) MSC_CUDA(ctx, cudaEventRecord(ctx->ev_s0, ctx->stream));
   const int rc = api().cuLaunchKernel(k.fn, static_cast<unsigned>(grid), 1, 1, NT, 1, 1, static_cast<unsigned>(k.smem),
                                       reinterpret_cast<CUstream>(ctx->stream), args, nullptr);
@@ -669,6 +906,79 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
     ctx->stats.last_scan_regs = k.regs;
   }
   return MSC_OK;
+}
+
+std::string project_key(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout) {
+  const int kinds[1] = {count_only ? -2 : -3};  // keeps these keys apart from the dense ones
+  const long long init[1] = {nout};
+  std::string k = shape_key(ctx, sd, 0, 0, 1, kinds, init, false);
+  if (!count_only) k.append(reinterpret_cast<const char*>(out_phys), sizeof(int32_t) * nout);
+  return k;
+}
+
+int project_source(const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, std::string* source, std::string* err) {
+  Gen g{sd, 0, 0, 0, nullptr, nullptr, 2, false};
+  if (!g.generate_project(count_only, out_phys, nout)) {
+    *err = g.why;
+    return MSC_ERR_ARG;
+  }
+  *source = g.o.str();
+  return MSC_OK;
+}
+
+}  // namespace
+
+int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
+                     unsigned long long* table, bool timed, bool* masked) {
+  const std::string skey = shape_key(ctx, sd, ngroups, naggs, stride, kinds, init, *masked);
+  auto sit = shapes().find(skey);
+  if (sit == shapes().end()) {
+    std::string source, why;
+    if (generate_either(sd, ngroups, naggs, stride, kinds, init, masked, &source, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
+    const Layout lay = stage_layout(sd);
+    const size_t smem = 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes + static_cast<size_t>(NW) * ngroups * stride * 8 +
+                        static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8;
+    Kernel* k = nullptr;
+    MSC_TRY(load_kernel(ctx, source, "msc_jit_dense", smem, &k));
+    sit = shapes().emplace(skey, ShapeEntry{k, *masked}).first;
+  }
+  *masked = sit->second.masked;
+  Kernel& k = *sit->second.kernel;
+  if (sd->nrows == 0) return MSC_OK;
+  JitParams p;
+  MSC_TRY(fill_params(ctx, sd, &p));
+  p.dense_out = table;
+  return launch(ctx, k, &p, timed);
+}
+
+int jit_project_source(const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, std::string* source, std::string* err) {
+  return project_source(sd, count_only, out_phys, nout, source, err);
+}
+
+bool jit_project_cached(msc_ctx* ctx, const msc_scan_desc* sd, const int32_t* out_phys, int nout) {
+  return shapes().count(project_key(ctx, sd, false, out_phys, nout)) != 0;
+}
+
+int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, uint32_t* tile_counts,
+                       const uint64_t* tile_offsets, void* const* outs, bool timed) {
+  const std::string skey = project_key(ctx, sd, count_only, out_phys, nout);
+  auto sit = shapes().find(skey);
+  if (sit == shapes().end()) {
+    std::string source, why;
+    if (project_source(sd, count_only, out_phys, nout, &source, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
+    const Layout lay = stage_layout(sd);
+    Kernel* k = nullptr;
+    MSC_TRY(load_kernel(ctx, source, "msc_jit_scan", 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes, &k));
+    sit = shapes().emplace(skey, ShapeEntry{k, false}).first;
+  }
+  Kernel& k = *sit->second.kernel;
+  if (sd->nrows == 0) return MSC_OK;
+  JitParams p;
+  MSC_TRY(fill_params(ctx, sd, &p));
+  p.tile_counts = tile_counts;
+  p.tile_offsets = reinterpret_cast<const unsigned long long*>(tile_offsets);
+  for (int c = 0; c < nout && !count_only; ++c) p.out[c] = outs[c];
+  return launch(ctx, k, &p, timed);
 }
 
 }  // namespace mscan

@@ -27,4 +27,13 @@ bool jit_dense_cached(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int na
 int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
                      unsigned long long* table, bool timed, bool* masked);  // *masked in: allowed, out: used
 
+
+// ---- filter / project scans (MODE_COUNT and MODE_PROJECT of scan_kernel.cuh), warp tiles of 256 rows ----------------
+// count_only: write every tile's surviving row count to tile_counts[]; otherwise write the output columns, at
+// tile_offsets[tile] + rank for filtered scans (stable) or at the row number for unfiltered ones
+int jit_project_source(const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, std::string* source, std::string* err);
+bool jit_project_cached(msc_ctx* ctx, const msc_scan_desc* sd, const int32_t* out_phys, int nout);
+int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, uint32_t* tile_counts,
+                       const uint64_t* tile_offsets, void* const* outs, bool timed);
+
 }  // namespace mscan

@@ -642,7 +642,7 @@ int dense_scan_into(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, const in
   static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
   const int ntot = dp.stride;
   if (jit_mode > 0 && jit_dense_supported(sd, ngroups, ntot) &&
-      (want_jit || jit_mode > 1 || jit_dense_cached(ctx, sd, ngroups, naggs, ntot, dp.kinds, dp.init, allow_masked && masked_enabled))) {
+      (want_jit || sd->want_jit != 0 || jit_mode > 1 || jit_dense_cached(ctx, sd, ngroups, naggs, ntot, dp.kinds, dp.init, allow_masked && masked_enabled))) {
     *was_masked = allow_masked && masked_enabled;
     dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table, ngroups, ntot, dense_meta(dp));
     ctx->stats.launches += 1;
@@ -906,6 +906,21 @@ extern "C" int msc_jit_dense_source(const msc_scan_desc* sd, int32_t ngroups, co
   return source.empty() ? MSC_ERR_ARG : MSC_OK;
 }
 
+extern "C" int msc_jit_project_source(const msc_scan_desc* sd, int32_t count_only, const int32_t* out_phys, int32_t nout, char* buf, size_t cap,
+                                      size_t* len) {
+  if (!sd || !len || nout < 0 || nout > MSC_VM_MAX_OUT || (nout && !out_phys)) return MSC_ERR_ARG;
+  std::string source, err;
+  jit_project_source(sd, count_only != 0, out_phys, nout, &source, &err);
+  const std::string& text = source.empty() ? err : source;
+  *len = text.size();
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, text.size());
+    memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return source.empty() ? MSC_ERR_ARG : MSC_OK;
+}
+
 extern "C" int msc_jit_compile(const char* source, void* cubin, size_t cap, size_t* len, char* log, size_t log_cap) {
   if (!source || !len) return MSC_ERR_ARG;
   std::vector<char> bin;
@@ -1054,8 +1069,13 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
                        std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
   };
   if (!pending) MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));  // a pending chain keeps the first call's start mark
+  // specialised kernels (jit.cu) for both passes, or the interpreter for both: the two paths tile the rows differently
+  static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
+  const bool use_jit = jit_mode > 0 && sd->nstaged >= 1 && sd->nrows > 0 && nout > 0 &&
+                       (sd->want_jit != 0 || jit_mode > 1 || jit_project_cached(ctx, sd, out_phys, nout));
   LaunchPlan lp;
   MSC_TRY(plan_launch(ctx, sd, R, 0, &lp));
+  if (use_jit) lp.p.ntiles = static_cast<uint32_t>((sd->nrows + 255) / 256);
   lp.p.nrows_dev = reinterpret_cast<const unsigned long long*>(sd->nrows_dev);
   lp.timed = !pending;  // a pending chain reports the scan it started with (the aggregate), not this follow-up
   uint64_t nout_rows = sd->nrows;
@@ -1067,7 +1087,8 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
     MSC_TRY(counts.alloc(sizeof(uint32_t) * cp.p.ntiles));
     MSC_TRY(offsets.alloc(sizeof(uint64_t) * (cp.p.ntiles + 1)));
     cp.p.tile_counts = counts.as<uint32_t>();
-    MSC_TRY(launch_scan_r<MODE_COUNT>(ctx, &cp));
+    if (use_jit) MSC_TRY(jit_project_launch(ctx, sd, true, out_phys, nout, counts.as<uint32_t>(), nullptr, nullptr, cp.timed));
+    else MSC_TRY(launch_scan_r<MODE_COUNT>(ctx, &cp));
     MSC_TRY(msc_exclusive_scan_u32_u64(ctx, counts.as<uint32_t>(), offsets.as<uint64_t>(), cp.p.ntiles));
     if (!pending) {
       MSC_CUDA(ctx, cudaMemcpyAsync(&nout_rows, offsets.as<uint64_t>() + cp.p.ntiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1092,7 +1113,8 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
     lp.p.out_phys[i] = out_phys[i];
   }
   if (sd->nrows > 0 && nout_rows > 0 && nout > 0) {
-    int rc = launch_scan_r<MODE_PROJECT>(ctx, &lp);
+    int rc = use_jit ? jit_project_launch(ctx, sd, false, out_phys, nout, nullptr, lp.p.tile_offsets, lp.p.out, lp.timed)
+                     : launch_scan_r<MODE_PROJECT>(ctx, &lp);
     if (rc != MSC_OK) {
       msc_rel_free(rel);
       return rc;

@@ -316,6 +316,7 @@ class _ScanResolver:
             d.consts[i] = c
         d.nluts = len(self.luts)
         d.ntemps = program.ntemps
+        d.want_jit = 1 if self.engine.jit == "always" else 0
         d.ncode2 = len(program.regvm)
         d.count_slot2 = program.regvm_count_slot
         for i, w in enumerate(program.regvm):
@@ -370,7 +371,15 @@ class CudaExecutionEngine(ExecutionEngine):
     """
 
     def __init__(self, device: Optional[int] = None, work_folder: Optional[Path] = None, layout: str = "native",
-                 shard: Optional[tuple[int, int]] = None, comm: Optional[Comm] = None) -> None:
+                 shard: Optional[tuple[int, int]] = None, comm: Optional[Comm] = None, jit: Optional[str] = None) -> None:
+        """``jit``: when scans run on kernels compiled for exactly their program (csrc/jit.cu), the counterpart of the
+        reference ThreadEngine compiling one Zig program per query (execution.py:139-160).  "auto" (default): prepared
+        queries, and any scan whose kernel this process has compiled already; "always": every dense aggregate and
+        filter / project scan (0.1-0.3 s per new query shape, cached; MSC_JIT_CACHE=<dir> keeps the cubins on disk);
+        "never": interpreters only.  The environment variable MINISPARK_JIT supplies the default."""
+        self.jit = jit or os.environ.get("MINISPARK_JIT", "auto")
+        if self.jit not in ("auto", "always", "never"):
+            raise ValueError("jit must be 'auto', 'always' or 'never'")
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.ctx = N.Context(device)  # raises when the library or the GPU is missing: no fallback
@@ -947,7 +956,7 @@ class _DenseMerge:
         import torch.distributed as dist  # noqa: PLC0415
 
         e = self.engine
-        flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0) | (N.K["MSC_DENSE_JIT"] if self.persistent else 0)
+        flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0) | (N.K["MSC_DENSE_JIT"] if self.persistent and e.jit != "never" else 0)
         if self.nlocal > 0:
             e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()), flags)
         with torch.cuda.stream(self.stream):
@@ -1032,7 +1041,7 @@ class PreparedAggregate:
                 raw_h = self.merge.enqueue(self.desc, exact)
             else:
                 # a prepared query runs many times: worth a kernel compiled for exactly this program (csrc/jit.cu)
-                flags = N.K["MSC_DENSE_ASYNC"] | N.K["MSC_DENSE_JIT"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
+                flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_JIT"] if e.jit != "never" else 0) | (N.K["MSC_DENSE_EXACT"] if exact else 0)
                 e.ctx.call("msc_scan_dense_table", C.byref(self.desc), self.ngroups, self.kinds, naggs, C.c_void_p(self._table), flags)
                 out = C.c_void_p()
                 e.ctx.call("msc_dense_compact_async", C.c_void_p(self._table), self.ngroups, self._stride, self.kinds, naggs, self._count_slot,

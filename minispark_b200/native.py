@@ -69,6 +69,8 @@ class ScanDesc(C.Structure):
         ("count_slot2", C.c_int32),
         ("code2", C.c_uint32 * K["MSC_VM_MAX_CODE2"]),
         ("nrows_dev", C.c_void_p),
+        ("want_jit", C.c_int32),
+        ("_pad2", C.c_int32),
     ]
 
 
@@ -134,6 +136,7 @@ _SIGNATURES = {
     "msc_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_jit_dense_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t,
                              C.POINTER(C.c_size_t)]),
+    "msc_jit_project_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "msc_jit_compile": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "msc_rel_nrows_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_rel_settle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int32)]),

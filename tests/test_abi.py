@@ -21,7 +21,7 @@ def test_struct_layouts_match_the_header():
     k = native.K
     assert ctypes.sizeof(native.ColBind) == 16
     expect = (8 + 4 + 4 + 16 * (k["MSC_VM_MAX_STAGED"] + k["MSC_VM_MAX_GATHER"]) + 4 + 4 + 4 * k["MSC_VM_MAX_CODE"]
-              + 8 * k["MSC_VM_MAX_CONSTS"] + 4 + 4 + 8 * k["MSC_VM_MAX_LUTS"] + 4 + 4 + 4 * k["MSC_VM_MAX_CODE2"] + 8)  # + nrows_dev
+              + 8 * k["MSC_VM_MAX_CONSTS"] + 4 + 4 + 8 * k["MSC_VM_MAX_LUTS"] + 4 + 4 + 4 * k["MSC_VM_MAX_CODE2"] + 8 + 8)  # + nrows_dev, want_jit + pad
     assert ctypes.sizeof(native.ScanDesc) == expect
 
 

@@ -99,3 +99,72 @@ def test_generator_refuses_too_many_cells(tmp_path):
     buf = C.create_string_buffer(4096)
     rc = lib.msc_jit_dense_source(C.byref(d), 40, N.int32_array(prog.agg_kinds), len(prog.agg_kinds), 1, buf, len(buf), C.byref(n))
     assert rc != 0 and b"register budget" in buf.value
+
+
+def _project_program(tmp_path, sql_tail: str):
+    """Lower `SELECT ... FROM lineitem WHERE ...` with the stub resolver of test_lowering."""
+    import sys
+    from copy import deepcopy
+    from pathlib import Path
+
+    from minispark_b200 import lowering as L
+    from minispark_b200.parser import parse_sql
+    from test_lowering import StubDict, StubResolver
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "bench"))
+    import gen_tpch
+
+    table = tmp_path / "l.bin"
+    gen_tpch.write_table(table, "lineitem", sf=0.0005, columns=gen_tpch.Q1_COLUMNS, rows_per_block=4096)
+    task = deepcopy(parse_sql(sql_tail.format(table=str(table))).task)
+    task.validate_schema()
+    plan = L.lower_task(task)
+    assert isinstance(plan, L.LSelect)
+    base = plan.child
+    res = StubResolver(base.schema)
+    ltype_of = {"INTEGER": "I", "FLOAT": "F", "TIMESTAMP": "T", "STRING": "S"}
+    res.ltypes = [ltype_of[t.name] for _, t in base.schema]
+    res.dict_of = {i: StubDict(["A", "N", "R"]) for i, t in enumerate(res.ltypes) if t == "S"}
+    return L.compile_project(res, list(plan.filters), list(plan.outputs)), res
+
+
+def _project_source(prog, res, count_only: bool) -> str:
+    lib = N.load()
+    d = N.ScanDesc()
+    d.nrows = 1 << 20
+    d.nstaged = len(res.staged)
+    for i, index in enumerate(res.staged):
+        d.staged[i].phys = res.PHYS[res.ltypes[index]]
+    words = prog.program.words()
+    d.ncode = len(words)
+    for i, w in enumerate(words):
+        d.code[i] = w
+    d.nconsts = len(prog.program.consts)
+    for i, c in enumerate(prog.program.consts):
+        d.consts[i] = c
+    d.ntemps = prog.program.ntemps
+    n = C.c_size_t()
+    buf = C.create_string_buffer(1 << 20)
+    rc = lib.msc_jit_project_source(C.byref(d), int(count_only), N.int32_array(prog.out_phys), len(prog.out_phys), buf, len(buf), C.byref(n))
+    assert rc == 0, buf.value.decode()
+    return buf.value.decode()
+
+
+def test_filtered_projection_compiles_as_two_passes(tmp_path):
+    sql = ("SELECT l_returnflag, l_extendedprice * (1 - l_discount) AS disc_price, l_quantity FROM '{table}' "
+           "WHERE (l_quantity > 10) AND (l_tax < l_discount);")  # (the reference types AND by its operands: both FLOAT)
+    prog, res = _project_program(tmp_path, sql)
+    count_src = _project_source(prog, res, True)
+    assert "p.tile_counts[tile]" in count_src and "p.out[" not in count_src
+    proj_src = _project_source(prog, res, False)
+    assert "p.tile_offsets[tile]" in proj_src and proj_src.count("p.out[") == 3
+    assert "reinterpret_cast<u32*>(p.out[0])" in proj_src        # the STRING column leaves as dictionary codes
+    for src in (count_src, proj_src):
+        assert compile_source(src)[:4] == b"\x7fELF"
+
+
+def test_unfiltered_projection_uses_vector_stores(tmp_path):
+    prog, res = _project_program(tmp_path, "SELECT l_quantity * l_extendedprice AS v FROM '{table}';")
+    src = _project_source(prog, res, False)
+    assert "p.tile_offsets" not in src.split("msc_jit_scan")[1] and "make_longlong2" in src
+    compile_source(src)
