@@ -104,7 +104,7 @@ def test_non_finite_inputs_rerun_on_the_exact_variant(tmp_path):
     keys = ["a" if i % 3 == 0 else "b" if i % 3 == 1 else "c" for i in range(n)]
     BlockFile(path, [("k", ColumnType.STRING), ("v", ColumnType.FLOAT)]).write_rows([{"k": k, "v": v} for k, v in zip(keys, vals)])
     with CudaExecutionEngine() as engine:
-        task = engine.sql(f"SELECT k, SUM(v) AS s, COUNT() AS c FROM '{path}' GROUP BY k").task
+        task = engine.sql(f"SELECT k, SUM(v) AS s, COUNT() AS c FROM '{path}' GROUP BY k;").task
         prepared = engine.prepare(task)
         final, _ = prepared.run()
         schema = prepared.plan.schema
