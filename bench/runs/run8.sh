@@ -1,0 +1,14 @@
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo pytest exit $?; tail -3 gpurun_out/pytest.log
+python bench/bench_configs.py --sf 10 --reps 5 --only config4 > gpurun_out/configs3.log 2>&1; echo cfg exit $?; cat gpurun_out/configs3.log | cut -c1-330
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_cfg4.csv python bench/bench_configs.py --sf 10 --reps 1 --only config4 > gpurun_out/ncu_cfg4.log 2>&1; echo "ncu cfg exit $?"
+python - <<PY
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/launches_cfg4.csv')) if len(r)>5]
+hdr=rows[0]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
+seq=[]
+for r in rows[1:]:
+    try: seq.append((r[ki][:90], float(r[vi].replace(',',''))/1000))
+    except: pass
+for k,v in seq[-10:]: print(f"{v:10.1f} us  {k}")
+PY

@@ -80,11 +80,20 @@ __global__ void dense_check_kernel(const unsigned long long* table, int ngroups,
 }
 
 constexpr int HTILE = 1024;  // slots per block in the hash-table compaction
-__global__ void hash_count_kernel(const unsigned long long* keys, uint64_t cap, uint32_t* tile_counts) {
+// slots of the hash aggregate are [key, accumulators...] padded to 1 << shift words (scan_kernel.cuh)
+__global__ void hash_init_kernel(unsigned long long* tbl, uint64_t cap, uint32_t shift, int naggs, const __grid_constant__ DenseMeta m) {
+  const uint64_t words = cap << shift, mask = (1ull << shift) - 1;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < words; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t w = i & mask;
+    tbl[i] = w == 0 ? HASH_EMPTY : (w <= static_cast<uint64_t>(naggs) ? static_cast<unsigned long long>(m.init[w - 1]) : 0ull);
+  }
+}
+
+__global__ void hash_count_kernel(const unsigned long long* tbl, uint64_t cap, uint32_t shift, uint32_t* tile_counts) {
   __shared__ uint32_t wsum[8];
   const uint64_t base = static_cast<uint64_t>(blockIdx.x) * HTILE;
   uint32_t c = 0;
-  for (int i = threadIdx.x; i < HTILE; i += blockDim.x) c += (base + i < cap && keys[base + i] != HASH_EMPTY);
+  for (int i = threadIdx.x; i < HTILE; i += blockDim.x) c += (base + i < cap && tbl[(base + i) << shift] != HASH_EMPTY);
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
   __syncthreads();
@@ -95,9 +104,8 @@ __global__ void hash_count_kernel(const unsigned long long* keys, uint64_t cap, 
   }
 }
 
-__global__ void hash_emit_kernel(const unsigned long long* keys, const unsigned long long* accs, uint64_t cap,
-                                 int naggs, const uint64_t* tile_offsets, long long* out_key,
-                                 unsigned long long* const* out_acc) {
+__global__ void hash_emit_kernel(const unsigned long long* tbl, uint64_t cap, uint32_t shift, int naggs, const uint64_t* tile_offsets,
+                                 long long* out_key, unsigned long long* const* out_acc) {
   // 256 threads, HTILE slots: each thread owns 4 consecutive slots so output order is slot order
   __shared__ uint32_t scratch[8];
   const uint64_t base = static_cast<uint64_t>(blockIdx.x) * HTILE + threadIdx.x * 4;
@@ -105,7 +113,7 @@ __global__ void hash_emit_kernel(const unsigned long long* keys, const unsigned 
   unsigned long long k[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    k[i] = (base + i < cap) ? keys[base + i] : HASH_EMPTY;
+    k[i] = (base + i < cap) ? tbl[(base + i) << shift] : HASH_EMPTY;
     c += (k[i] != HASH_EMPTY);
   }
   // block exclusive scan (256 threads)
@@ -124,9 +132,21 @@ __global__ void hash_emit_kernel(const unsigned long long* keys, const unsigned 
   for (int i = 0; i < 4; ++i) {
     if (k[i] == HASH_EMPTY) continue;
     out_key[pos] = static_cast<long long>(k[i]);
-    for (int a = 0; a < naggs; ++a) out_acc[a][pos] = accs[static_cast<uint64_t>(a) * cap + base + i];
+    const unsigned long long* slot = tbl + ((base + i) << shift) + 1;
+    for (int a = 0; a < naggs; ++a) out_acc[a][pos] = slot[a];
     ++pos;
   }
+}
+
+// runs of equal adjacent values in a column: an upper bound of its distinct values (every value starts at least one
+// run), exact for clustered keys such as lineitem's l_orderkey.  Sizes the hash table of a GROUP BY on a plain column.
+template <class T>
+__global__ void count_runs_kernel(const T* col, uint64_t n, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    c += (i == 0) || (col[i] != col[i - 1]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // ---- generic exclusive scan: 3 kernels, CHUNK elements per block ---------------------------------
@@ -984,32 +1004,60 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
 
   // ---- hash mode ----
   uint64_t want = hash_capacity_hint ? hash_capacity_hint : sd->nrows;
+  if (!hash_capacity_hint && sd->nrows >= (1u << 16)) {
+    // no hint: when the key is a plain staged column, its number of runs bounds the number of groups (one pass over
+    // the key column and one host read; sizing for nrows made the sf10 l_orderkey table 4.3 GB for 15 M groups)
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+      const uint32_t w0 = sd->code[pc], a = sd->code[pc + 1] & 0xffffu;
+      if ((w0 & 0x3f) == MSC_OP_END) break;
+      if (((w0 >> 6) & 7) != MSC_DST_GROUP || (w0 & 0x3f) != MSC_OP_MOV || ((a >> 12) & 15) != MSC_SRC_STAGED) continue;
+      const msc_colbind& kc = sd->staged[a & 0xfff];
+      DevTmp d_runs(ctx);
+      MSC_TRY(d_runs.alloc(sizeof(unsigned long long)));
+      MSC_CUDA(ctx, cudaMemsetAsync(d_runs.p, 0, sizeof(unsigned long long), ctx->stream));
+      const int grid = ctx->sm_count * 8;
+      switch (msc_phys_width(kc.phys)) {
+        case 1: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
+        case 2: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint16_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
+        case 4: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
+        default: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint64_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
+      }
+      ctx->stats.launches += 1;
+      unsigned long long* h = ctx->h_scratch;
+      MSC_CUDA(ctx, cudaMemcpyAsync(h, d_runs.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (h[0] > 0 && h[0] < want) want = h[0];
+      break;
+    }
+  }
   if (want < 16) want = 16;
   uint64_t cap = 64;
   while (cap < want * 2) cap <<= 1;
   if (cap > (1ULL << 31)) return ctx->fail(MSC_ERR_ARG, "hash aggregate: more than 2^30 groups per GPU is not supported");
+  uint32_t shift = 0;
+  while ((1u << shift) < static_cast<uint32_t>(1 + naggs)) ++shift;
   LaunchPlan lp;
   MSC_TRY(plan_launch(ctx, sd, R, 0, &lp));
   lp.p.naggs = naggs;
   memcpy(lp.p.agg_kind, kinds, sizeof(int) * naggs);
-  DevTmp keys(ctx), accs(ctx), counts(ctx), offsets(ctx), d_ptrs(ctx);
-  MSC_TRY(keys.alloc(cap * sizeof(unsigned long long)));
-  MSC_TRY(accs.alloc(cap * sizeof(unsigned long long) * (naggs ? naggs : 1)));
-  const int fill_grid = ctx->sm_count * 8;
-  fill_u64_kernel<<<fill_grid, 256, 0, ctx->stream>>>(keys.as<unsigned long long>(), HASH_EMPTY, cap);
-  for (int a = 0; a < naggs; ++a)
-    fill_u64_kernel<<<fill_grid, 256, 0, ctx->stream>>>(accs.as<unsigned long long>() + static_cast<uint64_t>(a) * cap,
-                                                        static_cast<unsigned long long>(init[a]), cap);
-  ctx->stats.launches += 1 + naggs;
-  lp.p.hkeys = keys.as<unsigned long long>();
-  lp.p.haccs = accs.as<unsigned long long>();
+  DevTmp tbl(ctx), counts(ctx), offsets(ctx), d_ptrs(ctx);
+  MSC_TRY(tbl.alloc((cap << shift) * sizeof(unsigned long long)));
+  {
+    DenseMeta meta;
+    memset(&meta, 0, sizeof(meta));
+    memcpy(meta.init, init, sizeof(long long) * naggs);
+    hash_init_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(tbl.as<unsigned long long>(), cap, shift, naggs, meta);
+  }
+  ctx->stats.launches += 1;
+  lp.p.htbl = tbl.as<unsigned long long>();
+  lp.p.hshift = shift;
   lp.p.hcap = cap;
   if (sd->nrows > 0) MSC_TRY(launch_scan_r<MODE_HASH>(ctx, &lp));
   // compaction of occupied slots
   const uint64_t nht = (cap + HTILE - 1) / HTILE;
   MSC_TRY(counts.alloc(nht * sizeof(uint32_t)));
   MSC_TRY(offsets.alloc((nht + 1) * sizeof(uint64_t)));
-  hash_count_kernel<<<static_cast<unsigned>(nht), 256, 0, ctx->stream>>>(keys.as<unsigned long long>(), cap, counts.as<uint32_t>());
+  hash_count_kernel<<<static_cast<unsigned>(nht), 256, 0, ctx->stream>>>(tbl.as<unsigned long long>(), cap, shift, counts.as<uint32_t>());
   ctx->stats.launches += 1;
   MSC_TRY(msc_exclusive_scan_u32_u64(ctx, counts.as<uint32_t>(), offsets.as<uint64_t>(), nht));
   uint64_t ngrp = 0;
@@ -1029,9 +1077,8 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
   for (int a = 0; a < naggs; ++a) ptrs.push_back(static_cast<unsigned long long*>(rel->cols[1 + a].data));
   MSC_TRY(d_ptrs.alloc(sizeof(void*) * (naggs + 1)));
   if (naggs) MSC_CUDA(ctx, cudaMemcpyAsync(d_ptrs.p, ptrs.data(), sizeof(void*) * naggs, cudaMemcpyHostToDevice, ctx->stream));
-  hash_emit_kernel<<<static_cast<unsigned>(nht), 256, 0, ctx->stream>>>(keys.as<unsigned long long>(), accs.as<unsigned long long>(), cap, naggs,
-                                                                      offsets.as<uint64_t>(), static_cast<long long*>(rel->cols[0].data),
-                                                                      d_ptrs.as<unsigned long long*>());
+  hash_emit_kernel<<<static_cast<unsigned>(nht), 256, 0, ctx->stream>>>(tbl.as<unsigned long long>(), cap, shift, naggs, offsets.as<uint64_t>(),
+                                                                      static_cast<long long*>(rel->cols[0].data), d_ptrs.as<unsigned long long*>());
   ctx->stats.launches += 1;
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
   MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
