@@ -330,11 +330,28 @@ MSC_API int msc_dense_compact_async(msc_ctx* ctx, const void* table, int32_t ngr
  * the exact variant is what MSC_DENSE_EXACT, or a non-finite sum, falls back to). */
 MSC_API int msc_jit_dense_source(const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked, char* buf,
                          size_t cap, size_t* len);
+/* ... and with the final projection fused into the kernel's last CTA (what msc_dense_fused runs) */
+MSC_API int msc_jit_dense_fused_source(const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked,
+                               const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout, char* buf,
+                               size_t cap, size_t* len);
 /* the same for a filter / project scan: count_only != 0 gives the first pass (surviving rows per 256-row tile), else
  * the pass that writes the output columns at their stable positions */
 MSC_API int msc_jit_project_source(const msc_scan_desc* scan, int32_t count_only, const int32_t* out_phys, int32_t nout, char* buf, size_t cap,
                            size_t* len);
 MSC_API int msc_jit_compile(const char* source, void* cubin, size_t cap, size_t* len, char* log, size_t log_cap);
+/* one pass of a prepared dense aggregate in one call: msc_scan_dense_table(flags | ASYNC) -> msc_dense_compact_async ->
+ * msc_scan_project of `final_scan` (its staged slot s is bound to column final_cols[s] of the compacted relation, its
+ * row count to that relation's device count) -> msc_rel_settle of both.  *nonfinite != 0: repeat with MSC_DENSE_EXACT. */
+MSC_API int msc_dense_chain(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table,
+                    int32_t stride, int32_t count_slot, int32_t flags, msc_scan_desc* final_scan, const int32_t* final_cols,
+                    const int32_t* out_phys, int32_t nout, msc_rel** raw, msc_rel** final_rel, int32_t* nonfinite);
+/* the same pass with no launch after the scan: the specialised kernel's last CTA compacts the groups and evaluates
+ * the final projection.  Needs MSC_DENSE_JIT in `flags`; *final_rel comes back NULL (and MSC_OK) when this query cannot
+ * be fused -- no specialised kernel, lookup tables in the final projection, more than 32 groups, no rows -- and the
+ * caller uses msc_dense_chain instead. */
+MSC_API int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table,
+                    int32_t flags, const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                    msc_rel** final_rel, int32_t* nonfinite);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                       int32_t naggs, int32_t count_slot, msc_rel** out);

@@ -29,6 +29,7 @@ struct msc_ctx {
   int* d_err = nullptr;               // device error word (bit flags written by kernels)
   int* h_err = nullptr;               // pinned mirror
   unsigned long long* h_scratch = nullptr;  // pinned, 16 words: small result read-backs
+  uint32_t* d_ticket = nullptr;       // "CTAs done" counter of fused scan + finish kernels (zero between launches)
   std::string err;
   msc_stats stats{};
   // pinned staging ring for file ingest

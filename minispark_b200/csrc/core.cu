@@ -137,6 +137,7 @@ extern "C" void msc_destroy(msc_ctx* ctx) {
     if (r) cudaFreeHost(r);
   for (auto& e : ctx->ring_ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->d_ticket) cudaFreeAsync(ctx->d_ticket, ctx->stream);
   if (ctx->d_err) cudaFree(ctx->d_err);
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);

@@ -47,6 +47,9 @@ struct JitParams {  // must match struct JitParams in jit_prelude.inc
   uint32_t* tile_counts;
   const unsigned long long* tile_offsets;
   void* out[24];
+  long long fconsts[32];
+  unsigned long long* fmeta;
+  uint32_t* ticket;
 };
 static_assert(MSC_VM_MAX_STAGED == 24 && MSC_VM_MAX_GATHER == 16 && MSC_VM_MAX_LUTS == 8 && MSC_VM_MAX_CONSTS == 32 && MSC_VM_MAX_OUT == 24,
               "JitParams layout");
@@ -164,6 +167,12 @@ struct Gen {
   const long long* init;       // [stride]
   int nstages;
   bool masked;  // SUM_F / COUNT as acc = fma(v, m, acc) with one-hot f64 masks m read from a shared-memory table
+  // fused finish (optional): the final projection over the aggregate's groups, run by the last CTA of the scan
+  const msc_scan_desc* fin = nullptr;
+  const int32_t* fin_cols = nullptr;  // staged slot of `fin` -> column of the compacted relation (0 = group id, 1 + s = accumulator s)
+  const int32_t* fin_phys = nullptr;  // physical types of its outputs
+  int fin_nout = 0, count_slot = 0;
+  bool in_finish = false;
   std::ostringstream o;
   std::string why;
   bool counted[MSC_VM_MAX_AGGS + 1] = {};  // slot is "SUM_I of a constant": counted in a u32 per tile, folded at the tile's end
@@ -174,10 +183,14 @@ struct Gen {
     const int kind = (opnd >> 12) & 7, idx = opnd & 0xfff;
     const bool i2f = ((opnd >> 12) & MSC_SRC_I2F) != 0;
     std::string s;
+    if (in_finish && (kind == MSC_SRC_GATHER || kind == MSC_SRC_LUT)) {
+      *ok = false;
+      return "0ll";
+    }
     switch (kind) {
       case MSC_SRC_TEMP: s = temp(idx); break;
-      case MSC_SRC_STAGED: s = "c" + std::to_string(idx) + "[r]"; break;
-      case MSC_SRC_CONST: s = "p.consts[" + std::to_string(idx) + "]"; break;
+      case MSC_SRC_STAGED: s = in_finish ? "f" + std::to_string(idx) : "c" + std::to_string(idx) + "[r]"; break;
+      case MSC_SRC_CONST: s = (in_finish ? "p.fconsts[" : "p.consts[") + std::to_string(idx) + "]"; break;
       case MSC_SRC_GATHER:
         s = "gather_at<" + std::to_string(sd->gather[idx & 63].phys) + ">(p.gather[" + std::to_string(idx & 63) + "], c" +
             std::to_string(idx >> 6) + "[r], valid)";
@@ -231,7 +244,7 @@ struct Gen {
   }
 
   bool temp_arrays = false;  // project scans run the program in two row loops, so temporaries are arrays over the rows
-  std::string temp(int idx) { return "t" + std::to_string(idx) + (temp_arrays ? "[r]" : ""); }
+  std::string temp(int idx) { return (in_finish ? "ft" : "t") + std::to_string(idx) + (temp_arrays ? "[r]" : ""); }
   std::string acc(int g, int s) { return "a" + std::to_string(g) + "_" + std::to_string(s); }
   std::string cnt(int g, int s) { return "n" + std::to_string(g) + "_" + std::to_string(s); }
 
@@ -669,8 +682,104 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     for (int w = 1; w < NW; ++w) v = agg_combine_k(kind, v, red[w * (NG * STRIDE) + cell]);
     if (v != INIT[cell % STRIDE]) atomic_fold(kind, p.dense_out + cell, v);
   }
-}
 )";
+    if (fin != nullptr && !emit_finish()) return false;
+    o << "}\n";
+    return true;
+  }
+
+  // The last CTA to fold its accumulators into the table also finishes the query: lane g of its first warp takes group
+  // g -- compaction of the groups that received rows (dense_finalize_kernel) and the final projection over them (AVG =
+  // SUM / COUNT, HAVING, output order: what msc_scan_project would run as a second scan) -- and leaves the row count,
+  // the non-finite flag and the device error word in p.fmeta.  No launch after the scan: prepared queries need it
+  // (bench/step_probe.py: the three follow-up launches and their gaps cost ~50 us of a 0.44 ms step).
+  bool emit_finish() {
+    if (ngroups > 32) {
+      why = "fused finish handles at most 32 groups";
+      return false;
+    }
+    in_finish = true;
+    temp_arrays = false;
+    o << R"(  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    const int g = lane;
+    const bool in_range = g < NG;
+    const u64* cell = p.dense_out + (in_range ? g : 0) * STRIDE;
+    i64 a[STRIDE];
+#pragma unroll
+    for (int s = 0; s < STRIDE; ++s) a[s] = static_cast<i64>(__ldcg(cell + s));
+)";
+    o << "    bool valid = in_range && a[" << count_slot << "] != 0;\n    bool nonfinite = false, bad = false;\n";
+    for (int s = 0; s < naggs; ++s)
+      if (kinds[s] == MSC_AGG_SUM_F) o << "    nonfinite |= in_range && !isfinite(l2d(a[" << s << "]));\n";
+    for (int c = 0; c < fin->nstaged; ++c) {
+      if (fin_cols[c] < 0 || fin_cols[c] > naggs) {
+        why = "final projection refers to a column the aggregate does not have";
+        return false;
+      }
+      o << "    const i64 f" << c << " = " << (fin_cols[c] == 0 ? std::string("(i64)g") : "a[" + std::to_string(fin_cols[c] - 1) + "]") << ";\n";
+    }
+    for (int t = 0; t < fin->ntemps; ++t) o << "    i64 ft" << t << " = 0;\n";
+    for (int c = 0; c < fin_nout; ++c) o << "    i64 fo" << c << " = 0;\n";
+    bool ok = true;
+    for (int pc = 0; pc + 1 < fin->ncode; pc += 2) {
+      const uint32_t w0 = fin->code[pc], w1 = fin->code[pc + 1];
+      const int op = w0 & 0x3f;
+      if (op == MSC_OP_END) break;
+      if (op == MSC_OP_RANK) continue;  // positions come from the ballot below
+      if (op == MSC_OP_LUT8 || op == MSC_OP_LUT32) {
+        why = "lookup table in the final projection";
+        return false;
+      }
+      const int dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
+      const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
+      const std::string x = compute(op, operand(oa, &ok), operand(ob, &ok), ob, &ok);
+      o << "    {\n";
+      if (op == MSC_OP_DIV_F || op == MSC_OP_FLOORDIV_F || op == MSC_OP_MOD_F) o << "      bad |= valid && (l2d(" << operand(ob, &ok) << ") == 0.0);\n";
+      if (op == MSC_OP_FLOORDIV_I || op == MSC_OP_MOD_I) o << "      bad |= valid && ((" << operand(ob, &ok) << ") == 0);\n";
+      o << "      const i64 x = " << x << ";\n";
+      if (tee) o << "      " << temp(tee - 1) << " = x;\n";
+      switch (dkind) {
+        case MSC_DST_TEMP: o << "      " << temp(dst) << " = x;\n"; break;
+        case MSC_DST_FILTER: o << "      valid = valid && (x != 0);\n"; break;
+        case MSC_DST_OUT:
+          if (dst >= fin_nout) {
+            why = "final projection writes a column it does not have";
+            return false;
+          }
+          o << "      fo" << dst << " = x;\n";
+          break;
+        case MSC_DST_NONE: break;
+        default: why = "destination kind outside a final projection"; return false;
+      }
+      o << "    }\n";
+    }
+    if (!ok) {
+      why = "operand or opcode outside the generator (final projection)";
+      return false;
+    }
+    o << "    const u32 keep = __ballot_sync(0xffffffffu, valid);\n    const int pos = __popc(keep & ((1u << lane) - 1u));\n    if (valid) {\n";
+    for (int c = 0; c < fin_nout; ++c) {
+      const std::string ty = fin_phys[c] == MSC_P_U32 ? "u32" : "i64";
+      o << "      reinterpret_cast<" << ty << "*>(p.out[" << c << "])[pos] = (" << ty << ")fo" << c << ";\n";
+    }
+    o << R"(    }
+    const bool any_nonfinite = __any_sync(0xffffffffu, nonfinite), any_bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      p.fmeta[0] = __popc(keep);
+      p.fmeta[1] = any_nonfinite ? 1 : 0;
+      p.fmeta[2] = static_cast<u64>(*reinterpret_cast<volatile int*>(p.err) | (any_bad ? 1 : 0));
+      *p.err = 0;
+      *p.ticket = 0;
+    }
+  }
+)";
+    in_finish = false;
     return true;
   }
 };
@@ -773,8 +882,15 @@ int cu_fail(msc_ctx* ctx, const char* what, int rc) {
 
 // generated source for this query, or "" with ctx->err set
 int generate(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, int nstages, bool masked,
-             std::string* source, std::string* err) {
+             std::string* source, std::string* err, const JitFinish* fin = nullptr) {
   Gen g{sd, ngroups, naggs, stride, kinds, init, nstages, masked};
+  if (fin) {
+    g.fin = fin->scan;
+    g.fin_cols = fin->cols;
+    g.fin_phys = fin->out_phys;
+    g.fin_nout = fin->nout;
+    g.count_slot = fin->count_slot;
+  }
   if (!g.generate()) {
     *err = g.why;
     return MSC_ERR_ARG;
@@ -792,15 +908,15 @@ bool jit_dense_supported(const msc_scan_desc* sd, int ngroups, int stride) {
 
 // masked: try the mask-table variant first, fall back to the exact one when the program does not allow it
 int generate_either(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, bool* masked,
-                    std::string* source, std::string* err) {
-  if (*masked && generate(sd, ngroups, naggs, stride, kinds, init, 2, true, source, err) == MSC_OK) return MSC_OK;
+                    std::string* source, std::string* err, const JitFinish* fin = nullptr) {
+  if (*masked && generate(sd, ngroups, naggs, stride, kinds, init, 2, true, source, err, fin) == MSC_OK) return MSC_OK;
   *masked = false;
-  return generate(sd, ngroups, naggs, stride, kinds, init, 2, false, source, err);
+  return generate(sd, ngroups, naggs, stride, kinds, init, 2, false, source, err, fin);
 }
 
 int jit_dense_source(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, bool masked,
-                     std::string* source, std::string* err) {
-  return generate_either(sd, ngroups, naggs, stride, kinds, init, &masked, source, err);
+                     std::string* source, std::string* err, const JitFinish* fin) {
+  return generate_either(sd, ngroups, naggs, stride, kinds, init, &masked, source, err, fin);
 }
 
 int jit_compile_source(const std::string& source, std::vector<char>* cubin, std::string* err) { return compile(source, JIT_MIN_CTAS, cubin, err); }
@@ -929,12 +1045,22 @@ int project_source(const msc_scan_desc* sd, bool count_only, const int32_t* out_
 }  // namespace
 
 int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
-                     unsigned long long* table, bool timed, bool* masked) {
-  const std::string skey = shape_key(ctx, sd, ngroups, naggs, stride, kinds, init, *masked);
+                     unsigned long long* table, bool timed, bool* masked, const JitFinish* fin) {
+  std::string skey = shape_key(ctx, sd, ngroups, naggs, stride, kinds, init, *masked);
+  if (fin) {  // the final projection is part of the kernel text
+    const int head[4] = {-7, fin->nout, fin->count_slot, fin->scan->nstaged};
+    skey.append(reinterpret_cast<const char*>(head), sizeof(head));
+    skey.append(reinterpret_cast<const char*>(fin->cols), sizeof(int32_t) * fin->scan->nstaged);
+    skey.append(reinterpret_cast<const char*>(fin->out_phys), sizeof(int32_t) * fin->nout);
+    int n = 0;
+    while (n + 1 < fin->scan->ncode && (fin->scan->code[n] & 0x3f) != MSC_OP_END) n += 2;
+    skey.append(reinterpret_cast<const char*>(fin->scan->code), sizeof(uint32_t) * n);
+  }
   auto sit = shapes().find(skey);
   if (sit == shapes().end()) {
     std::string source, why;
-    if (generate_either(sd, ngroups, naggs, stride, kinds, init, masked, &source, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
+    if (generate_either(sd, ngroups, naggs, stride, kinds, init, masked, &source, &why, fin) != MSC_OK)
+      return ctx->fail(MSC_ERR_ARG, "jit: " + why);
     const Layout lay = stage_layout(sd);
     const size_t smem = 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes + static_cast<size_t>(NW) * ngroups * stride * 8 +
                         static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8;
@@ -948,6 +1074,12 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
   JitParams p;
   MSC_TRY(fill_params(ctx, sd, &p));
   p.dense_out = table;
+  if (fin) {
+    memcpy(p.fconsts, fin->scan->consts, sizeof(int64_t) * fin->scan->nconsts);
+    for (int c = 0; c < fin->nout; ++c) p.out[c] = fin->outs[c];
+    p.fmeta = fin->meta;
+    p.ticket = fin->ticket;
+  }
   return launch(ctx, k, &p, timed);
 }
 

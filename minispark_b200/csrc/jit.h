@@ -10,6 +10,19 @@ namespace mscan {
 constexpr int JIT_MAX_REG_CELLS = 32;  // groups x accumulators kept in registers by the specialised kernel
 constexpr int JIT_MIN_CTAS = 4;        // __launch_bounds__(128, 4): at most 128 registers per thread
 
+// Optional fused finish of a dense aggregate scan: the last CTA compacts the groups and runs the final projection
+// (jit.cu emit_finish).  `scan` supplies the program and constants only.
+struct JitFinish {
+  const msc_scan_desc* scan;
+  const int32_t* cols;      // staged slot of `scan` -> column of the compacted relation (0 = group id, 1 + s = accumulator s)
+  const int32_t* out_phys;  // [nout]
+  int nout;
+  int count_slot;
+  void* const* outs;             // [nout] device columns of the final relation (ngroups rows each)
+  unsigned long long* meta;      // device: {rows, non-finite flag, error word}
+  uint32_t* ticket;              // device counter, zero between launches
+};
+
 // can this scan run on a specialised kernel at all (cheap checks; the generator may still refuse a program)?
 bool jit_dense_supported(const msc_scan_desc* sd, int ngroups, int stride);
 // CUDA C++ source of the specialised kernel (no device needed)
@@ -17,7 +30,7 @@ bool jit_dense_supported(const msc_scan_desc* sd, int ngroups, int stride);
 // input leaks into the other groups as NaN, so the caller must check the sums and rerun unmasked -- as for the masked
 // regvm variants, gen_regvm.py); programs that do not allow it get the exact form anyway
 int jit_dense_source(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, bool masked,
-                     std::string* source, std::string* err);
+                     std::string* source, std::string* err, const JitFinish* fin = nullptr);
 // NVRTC: source -> sm_100a cubin (no device needed)
 int jit_compile_source(const std::string& source, std::vector<char>* cubin, std::string* err);
 // is the kernel for this scan already compiled and loaded in this process?
@@ -25,7 +38,7 @@ bool jit_dense_cached(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int na
                       bool masked);
 // compile (or take from the cache) and launch into `table` ([ngroups][stride], already holding the identities)
 int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init,
-                     unsigned long long* table, bool timed, bool* masked);  // *masked in: allowed, out: used
+                     unsigned long long* table, bool timed, bool* masked, const JitFinish* fin = nullptr);  // *masked in: allowed, out: used
 
 
 // ---- filter / project scans (MODE_COUNT and MODE_PROJECT of scan_kernel.cuh), warp tiles of 256 rows ----------------

@@ -907,6 +907,99 @@ extern "C" int msc_dense_compact_async(msc_ctx* ctx, const void* table, int32_t 
   return dense_compact(ctx, static_cast<const unsigned long long*>(table), ngroups, naggs, dp, out, &nf, true);
 }
 
+// One pass of a prepared dense aggregate in ONE call: scan into `table` -> compaction -> final projection bound to the
+// compacted columns -> a single host wait.  What execution.py's PreparedAggregate.run() otherwise drives through six
+// entry points (each costs a few microseconds of ctypes marshalling on a 0.4 ms step).
+extern "C" int msc_dense_chain(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table,
+                               int32_t stride, int32_t count_slot, int32_t flags, msc_scan_desc* final_scan, const int32_t* final_cols,
+                               const int32_t* out_phys, int32_t nout, msc_rel** raw_out, msc_rel** final_out, int32_t* nonfinite) {
+  if (!ctx || !scan || !table || !final_scan || !final_cols || !raw_out || !final_out || !nonfinite)
+    return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  *raw_out = nullptr;
+  *final_out = nullptr;
+  MSC_TRY(msc_scan_dense_table(ctx, scan, ngroups, agg_kinds, naggs, table, flags | MSC_DENSE_ASYNC));
+  msc_rel* raw = nullptr;
+  MSC_TRY(msc_dense_compact_async(ctx, table, ngroups, stride, agg_kinds, naggs, count_slot, &raw));
+  for (int sl = 0; sl < final_scan->nstaged; ++sl) {
+    const int c = final_cols[sl];
+    if (c < 0 || c >= static_cast<int>(raw->cols.size())) {
+      msc_rel_free(raw);
+      return ctx->fail(MSC_ERR_ARG, "final projection refers to a column the aggregate does not have");
+    }
+    final_scan->staged[sl].data = raw->cols[c].data;
+  }
+  final_scan->nrows = static_cast<uint64_t>(ngroups);
+  final_scan->nrows_dev = reinterpret_cast<const uint64_t*>(raw->d_meta);
+  msc_rel* fin = nullptr;
+  int rc = msc_scan_project(ctx, final_scan, out_phys, nout, &fin);
+  if (rc != MSC_OK) {
+    msc_rel_free(raw);
+    return rc;
+  }
+  msc_rel* rels[2] = {raw, fin};
+  rc = msc_rel_settle(ctx, rels, 2, nonfinite);
+  if (rc != MSC_OK) {
+    msc_rel_free(raw);
+    msc_rel_free(fin);
+    return rc;
+  }
+  *raw_out = raw;
+  *final_out = fin;
+  return MSC_OK;
+}
+
+// The same pass with NO launch after the scan: the specialised kernel's last CTA compacts the groups and runs the final
+// projection (jit.cu emit_finish).  *final_out stays null when this query cannot be fused (no specialised kernel for it,
+// lookup tables in the final projection, more than 32 groups, empty input): the caller then uses msc_dense_chain.
+extern "C" int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table,
+                               int32_t flags, const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                               msc_rel** final_out, int32_t* nonfinite) {
+  if (!ctx || !scan || !table || !final_scan || !final_cols || !final_out || !nonfinite || ngroups <= 0 || nout <= 0 || nout > MSC_VM_MAX_OUT)
+    return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  *final_out = nullptr;
+  *nonfinite = 0;
+  static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
+  static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
+  if (jit_mode == 0 || !(flags & MSC_DENSE_JIT) || scan->nrows == 0 || ngroups > 32) return MSC_OK;
+  MSC_TRY(validate_program(ctx, scan, MODE_DENSE, agg_kinds, naggs, nullptr, 0));
+  MSC_TRY(validate_program(ctx, final_scan, MODE_PROJECT, nullptr, 0, out_phys, nout));
+  DensePlan dp;
+  MSC_TRY(dense_plan(ctx, scan, agg_kinds, naggs, &dp));
+  if (!jit_dense_supported(scan, ngroups, dp.stride)) return MSC_OK;
+  if (!ctx->d_ticket) {
+    MSC_TRY(msc_alloc(ctx, sizeof(uint32_t), reinterpret_cast<void**>(&ctx->d_ticket)));
+    MSC_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), ctx->stream));
+  }
+  msc_rel* rel = new_rel(ctx, static_cast<uint64_t>(ngroups));
+  int rc = add_cols(ctx, rel, out_phys, nout, static_cast<uint64_t>(ngroups));
+  if (rc == MSC_OK) rc = msc_alloc(ctx, 3 * sizeof(unsigned long long), reinterpret_cast<void**>(&rel->d_meta));
+  if (rc != MSC_OK) {
+    msc_rel_free(rel);
+    return rc;
+  }
+  void* outs[MSC_VM_MAX_OUT];
+  for (int i = 0; i < nout; ++i) outs[i] = rel->cols[i].data;
+  JitFinish fin{final_scan, final_cols, out_phys, nout, dp.count_slot, outs, rel->d_meta, ctx->d_ticket};
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  dense_init_kernel<<<1, 256, 0, ctx->stream>>>(static_cast<unsigned long long*>(table), ngroups, dp.stride, dense_meta(dp));
+  ctx->stats.launches += 1;
+  bool masked = !(flags & MSC_DENSE_EXACT) && masked_enabled;
+  rc = jit_dense_launch(ctx, scan, ngroups, naggs, dp.stride, dp.kinds, dp.init, static_cast<unsigned long long*>(table), true, &masked, &fin);
+  if (rc != MSC_OK) {
+    msc_rel_free(rel);
+    return rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0 ? MSC_OK : rc;  // the generator declined: not an error, just not fused
+  }
+  rel->pending = true;
+  msc_rel* rels[1] = {rel};
+  rc = msc_rel_settle(ctx, rels, 1, nonfinite);
+  if (rc != MSC_OK) {
+    msc_rel_free(rel);
+    return rc;
+  }
+  *final_out = rel;
+  return MSC_OK;
+}
+
 extern "C" int msc_jit_dense_source(const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked, char* buf,
                                     size_t cap, size_t* len) {
   if (!sd || !agg_kinds || !len || ngroups <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS) return MSC_ERR_ARG;
@@ -916,6 +1009,27 @@ extern "C" int msc_jit_dense_source(const msc_scan_desc* sd, int32_t ngroups, co
   std::string source, err;
   if (!jit_dense_supported(sd, ngroups, dp.stride)) err = "groups x accumulators exceed the register budget of a specialised kernel";
   else jit_dense_source(sd, ngroups, naggs, dp.stride, dp.kinds, dp.init, masked != 0, &source, &err);
+  const std::string& text = source.empty() ? err : source;
+  *len = text.size();
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, text.size());
+    memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return source.empty() ? MSC_ERR_ARG : MSC_OK;
+}
+
+extern "C" int msc_jit_dense_fused_source(const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked,
+                                          const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                                          char* buf, size_t cap, size_t* len) {
+  if (!sd || !agg_kinds || !len || !final_scan || !final_cols || !out_phys || ngroups <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS) return MSC_ERR_ARG;
+  msc_ctx scratch;
+  DensePlan dp;
+  if (dense_plan(&scratch, sd, agg_kinds, naggs, &dp) != MSC_OK) return MSC_ERR_ARG;
+  std::string source, err;
+  JitFinish fin{final_scan, final_cols, out_phys, nout, dp.count_slot, nullptr, nullptr, nullptr};
+  if (!jit_dense_supported(sd, ngroups, dp.stride)) err = "groups x accumulators exceed the register budget of a specialised kernel";
+  else jit_dense_source(sd, ngroups, naggs, dp.stride, dp.kinds, dp.init, masked != 0, &source, &err, &fin);
   const std::string& text = source.empty() ? err : source;
   *len = text.size();
   if (buf && cap) {

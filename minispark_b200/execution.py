@@ -1024,6 +1024,8 @@ class PreparedAggregate:
         self.nrows = self.source.nrows
         self.scan_stats: dict[str, Any] = {}
         self._final: Optional[tuple] = None  # compiled final projection, re-bound to every pass's aggregate result
+        self._chain_args: Optional[tuple] = None
+        self._fusable = True  # until msc_dense_fused says otherwise
 
     def run(self) -> tuple[DeviceRel, float]:
         """One pass of the hot path; returns (result relation, device milliseconds from the first launch to the result).
@@ -1036,6 +1038,8 @@ class PreparedAggregate:
             return self._run_stepwise()
         key_dict = self.merge.global_dict if self.merge is not None else self.prog.group_dict
         upper = self.merge.nglobal if self.merge is not None else self.ngroups
+        if self.merge is None and self._final is not None:
+            return self._run_chain()
         for exact in (False, True):
             if self.merge is not None:
                 raw_h = self.merge.enqueue(self.desc, exact)
@@ -1073,6 +1077,43 @@ class PreparedAggregate:
                            "regs": st.last_scan_regs}
         e._track(DeviceRel(e.ctx, raw_h, 0, []))
         final = e._track(DeviceRel.from_handle(e.ctx, out2.value, [x.type for x in self.plan.outputs], prog2.out_dicts))
+        return final, st.last_kernel_ms
+
+    def _run_chain(self) -> tuple[DeviceRel, float]:
+        """Second and later passes on one GPU: the whole chain in one library call (msc_dense_chain)."""
+        e = self.engine
+        naggs = len(self.prog.agg_kinds)
+        desc2, prog2, staged_cols = self._final[0], self._final[1], self._final[2]
+        if self._chain_args is None:
+            raw_cols = [0 if ci == 0 else 1 + self.prog.slot_of[ci - 1] for ci in staged_cols]
+            self._chain_args = (N.int32_array(raw_cols), N.int32_array(prog2.out_phys), len(prog2.out_phys),
+                                [x.type for x in self.plan.outputs])
+        raw_cols, out_phys, nout, out_types = self._chain_args
+        raw, fin, nonfinite = C.c_void_p(), C.c_void_p(), C.c_int32()
+        for exact in (False, True):
+            flags = (N.K["MSC_DENSE_JIT"] if e.jit != "never" else 0) | (N.K["MSC_DENSE_EXACT"] if exact else 0)
+            if self._fusable:  # scan + compaction + final projection in ONE kernel (the scan's last CTA finishes the query)
+                e.ctx.call("msc_dense_fused", C.byref(self.desc), self.ngroups, self.kinds, naggs, C.c_void_p(self._table), flags,
+                           C.byref(desc2), raw_cols, out_phys, nout, C.byref(fin), C.byref(nonfinite))
+                if fin.value:
+                    if not nonfinite.value or exact:
+                        break
+                    e.ctx.lib.msc_rel_free(fin)
+                    continue
+                self._fusable = False
+            e.ctx.call("msc_dense_chain", C.byref(self.desc), self.ngroups, self.kinds, naggs, C.c_void_p(self._table), self._stride,
+                       self._count_slot, flags, C.byref(desc2), raw_cols, out_phys, nout, C.byref(raw), C.byref(fin), C.byref(nonfinite))
+            if not nonfinite.value or exact:
+                break
+            e.ctx.lib.msc_rel_free(raw)  # non-finite SUM out of a masked variant: redo the pass the exact way
+            e.ctx.lib.msc_rel_free(fin)
+        st = e.ctx.stats()
+        self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
+                           "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread, "kind": st.last_scan_kind,
+                           "regs": st.last_scan_regs}
+        if raw.value:
+            e._track(DeviceRel(e.ctx, raw.value, 0, []))
+        final = e._track(DeviceRel.from_handle(e.ctx, fin.value, out_types, prog2.out_dicts))
         return final, st.last_kernel_ms
 
     def _final_projection(self, cols: list[DeviceColumn], nrows: int) -> tuple:

@@ -136,8 +136,15 @@ _SIGNATURES = {
     "msc_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_jit_dense_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t,
                              C.POINTER(C.c_size_t)]),
+    "msc_jit_dense_fused_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "msc_jit_project_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "msc_jit_compile": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
+    "msc_dense_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                        C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                        C.POINTER(C.c_int32)]),
+    "msc_dense_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "msc_rel_nrows_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_rel_settle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int32)]),
     "msc_dense_merge_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,

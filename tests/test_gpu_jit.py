@@ -58,7 +58,9 @@ def test_prepared_q1_runs_the_specialised_kernel_and_matches_the_interpreter(tmp
             for k in want:
                 for name, v in want[k].items():
                     assert _close(got[k][name], v), (k, name, got[k][name], v)
-        assert engine.ctx.stats().jit_compiles <= 1      # compiled once (or by an earlier test), then taken from the cache
+        # compiled once each (or by an earlier test), then taken from the cache: the plain kernel of the first pass and
+        # the kernel with the fused finish (compaction + final projection in the scan's last CTA) of the later ones
+        assert engine.ctx.stats().jit_compiles <= 2
         # once compiled, the one-shot path takes the kernel too
         rel, schema = engine.execute_to_device(task)
         assert engine.last_stats["agg_scan_kind"] == 2

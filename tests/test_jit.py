@@ -168,3 +168,47 @@ def test_unfiltered_projection_uses_vector_stores(tmp_path):
     src = _project_source(prog, res, False)
     assert "p.tile_offsets" not in src.split("msc_jit_scan")[1] and "make_longlong2" in src
     compile_source(src)
+
+
+def test_q1_with_fused_finish_compiles(tmp_path):
+    """scan + compaction + final projection (AVG = SUM / COUNT, output order) as ONE kernel: the last CTA finishes the query."""
+    from minispark_b200 import lowering as L
+    from test_lowering import StubDict, StubResolver, _q1_plan
+
+    prog, res = _compile_q1(tmp_path)
+    plan = _q1_plan(tmp_path)
+    agg = plan.child
+
+    class FinalResolver(StubResolver):  # columns of the compacted aggregate: key code (u32) + one f64 / i64 column per aggregate
+        PHYS = {"I": N.P_I64, "F": N.P_F64, "T": N.P_I64, "S": N.P_U32}
+
+    res2 = FinalResolver(agg.schema)
+    ltype_of = {"INTEGER": "I", "FLOAT": "F", "TIMESTAMP": "T", "STRING": "S"}
+    res2.ltypes = [ltype_of[t.name] for _, t in agg.schema]
+    res2.dict_of = {0: StubDict(["A", "N", "R"])}
+    prog2 = L.compile_project(res2, list(plan.filters), list(plan.outputs))
+    d2 = N.ScanDesc()
+    d2.nstaged = len(res2.staged)
+    for i, index in enumerate(res2.staged):
+        d2.staged[i].phys = res2.PHYS[res2.ltypes[index]]
+    words = prog2.program.words()
+    d2.ncode = len(words)
+    for i, w in enumerate(words):
+        d2.code[i] = w
+    d2.nconsts = len(prog2.program.consts)
+    for i, c in enumerate(prog2.program.consts):
+        d2.consts[i] = c
+    d2.ntemps = prog2.program.ntemps
+    raw_cols = [0 if ci == 0 else 1 + prog.slot_of[ci - 1] for ci in res2.staged]
+    lib = N.load()
+    d = _desc(prog, res)
+    n = C.c_size_t()
+    buf = C.create_string_buffer(1 << 20)
+    rc = lib.msc_jit_dense_fused_source(C.byref(d), 3, N.int32_array(prog.agg_kinds), len(prog.agg_kinds), 1, C.byref(d2), N.int32_array(raw_cols),
+                                        N.int32_array(prog2.out_phys), len(prog2.out_phys), buf, len(buf), C.byref(n))
+    src = buf.value.decode()
+    assert rc == 0, src
+    assert "atomicAdd(p.ticket, 1u) == gridDim.x - 1" in src and "p.fmeta[0] = __popc(keep)" in src
+    assert src.count("p.out[") == len(prog2.out_phys)
+    assert " / " in src.split("s_last")[-1]                     # AVG = SUM / COUNT happens in the finish
+    compile_source(src)
