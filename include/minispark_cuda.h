@@ -40,6 +40,7 @@ extern "C" {
 #define MSC_ERR_OVERFLOW (-5)  /* INT result does not fit i32 on write (reference: io.py:87-90) */
 #define MSC_ERR_COLLISION (-6) /* unresolved 64-bit string-hash collision in a dictionary */
 #define MSC_ERR_STRLEN (-7)    /* string longer than 255 bytes (BlockFile limit, io.py:42-44) */
+#define MSC_ERR_PEER (-8)      /* a peer GPU did not deliver its part of a fused exchange in time */
 
 /* ---- logical column types: the BlockFile schema ordinals (constants.py:18-23) ------------- */
 #define MSC_T_INTEGER 0
@@ -332,8 +333,8 @@ MSC_API int msc_jit_dense_source(const msc_scan_desc* scan, int32_t ngroups, con
                          size_t cap, size_t* len);
 /* ... and with the final projection fused into the kernel's last CTA (what msc_dense_fused runs) */
 MSC_API int msc_jit_dense_fused_source(const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked,
-                               const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout, char* buf,
-                               size_t cap, size_t* len);
+                               const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                               int32_t peer /* != 0: the cross-rank variant of msc_dense_fused_peer */, char* buf, size_t cap, size_t* len);
 /* the same for a filter / project scan: count_only != 0 gives the first pass (surviving rows per 256-row tile), else
  * the pass that writes the output columns at their stable positions */
 MSC_API int msc_jit_project_source(const msc_scan_desc* scan, int32_t count_only, const int32_t* out_phys, int32_t nout, char* buf, size_t cap,
@@ -352,6 +353,41 @@ MSC_API int msc_dense_chain(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngr
 MSC_API int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table,
                     int32_t flags, const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
                     msc_rel** final_rel, int32_t* nonfinite);
+/* ---- fused scan + cross-GPU merge over NVLink peer memory -----------------------------------------------------------
+ * One process per GPU.  Every rank owns a small "mailbox" in device memory that its peers can write (CUDA IPC):
+ * msc_peer_alloc creates it and returns the 64-byte handle to send to the other ranks (the host language moves the
+ * handles, e.g. torch.distributed.all_gather_object), msc_peer_open maps a peer's mailbox.  Mailbox layout for a world
+ * of W ranks and tables of C = gmax * stride cells: u64 flag[2][W], then u64 slot[2][W][C]
+ * (MSC_PEER_MAILBOX_BYTES).  It replaces the shuffle files between the pre-aggregate and the final aggregate
+ * (plan.py:94-118, 190-199) for low-cardinality GROUP BY.
+ *
+ * msc_dense_fused_peer is msc_dense_fused across ranks, still ONE kernel per rank and pass: the scan's last CTA stores
+ * this rank's table into slot[epoch & 1][rank] of every mailbox (peer stores over NVLink), publishes flag = epoch,
+ * waits for the W flags of its own mailbox, folds the W tables in rank order through `inv` (inv[r * 32 + G] = rank
+ * r's local group of global group G, or -1) and evaluates the final projection over the `nglobal` <= 32 merged groups.
+ * Every rank ends with the same bits.  `epoch` must grow by one per pass on all ranks (two slot sets: a rank can be at
+ * most one pass ahead of its slowest peer).  compile_only != 0 compiles the kernel and returns (all ranks should agree
+ * that it compiled before the first real pass; a rank that never launches makes its peers time out after ~10 s with
+ * MSC_ERR_PEER).  *final_rel == NULL with MSC_OK: this query cannot be fused (as for msc_dense_fused). */
+#define MSC_PEER_MAX_WORLD 8
+#define MSC_PEER_MAILBOX_BYTES(world, cells) (sizeof(uint64_t) * (2 * (size_t)(world) + 2 * (size_t)(world) * (size_t)(cells)))
+MSC_API int msc_peer_alloc(msc_ctx* ctx, size_t nbytes, void** dev_ptr, void* handle64);
+MSC_API int msc_peer_open(msc_ctx* ctx, const void* handle64, void** peer_ptr);
+MSC_API int msc_peer_close(msc_ctx* ctx, void* peer_ptr);
+MSC_API int msc_peer_free(msc_ctx* ctx, void* dev_ptr);
+typedef struct msc_peer_spec {
+  void* mailbox[MSC_PEER_MAX_WORLD]; /* [rank] = this rank's own mailbox, the others as mapped by msc_peer_open */
+  const int32_t* inv;                /* device, [world][32] */
+  uint64_t epoch;
+  int32_t rank, world;
+  int32_t nlocal;  /* groups of this rank's table */
+  int32_t gmax;    /* groups a slot has room for (max over ranks) */
+  int32_t nglobal; /* merged groups (<= 32) */
+  int32_t compile_only;
+} msc_peer_spec;
+MSC_API int msc_dense_fused_peer(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* agg_kinds, int32_t naggs, void* table, int32_t flags,
+                         const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                         const msc_peer_spec* peer, msc_rel** final_rel, int32_t* nonfinite);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                       int32_t naggs, int32_t count_slot, msc_rel** out);

@@ -69,6 +69,7 @@ int msc_device_error_rc(msc_ctx* ctx, int e) {
   if (e & MSC_DEVERR_OVERFLOW) return ctx->fail(MSC_ERR_OVERFLOW, "int too big to convert");
   if (e & MSC_DEVERR_COLLISION) return ctx->fail(MSC_ERR_COLLISION, "string hash collision in dictionary");
   if (e & MSC_DEVERR_STRLEN) return ctx->fail(MSC_ERR_STRLEN, "string longer than 255 bytes");
+  if (e & MSC_DEVERR_PEER_TIMEOUT) return ctx->fail(MSC_ERR_PEER, "a peer GPU did not deliver its partial aggregate in time");
   return ctx->fail(MSC_ERR_ARG, "hash table full");
 }
 
@@ -253,6 +254,40 @@ extern "C" void msc_rel_free(msc_rel* r) {
     if (c.owned && c.data) msc_free(r->ctx, c.data, c.bytes);
   if (r->d_meta) msc_free(r->ctx, r->d_meta, 3 * sizeof(unsigned long long));
   delete r;
+}
+
+// ---- peer mailboxes: device memory other ranks' GPUs write into over NVLink (CUDA IPC, one process per GPU) ----------
+extern "C" int msc_peer_alloc(msc_ctx* ctx, size_t nbytes, void** dev_ptr, void* handle64) {
+  if (!ctx || !dev_ptr || !handle64 || nbytes == 0) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  MSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MSC_CUDA(ctx, cudaMalloc(dev_ptr, nbytes));  // IPC needs a cudaMalloc allocation, not one from the stream-ordered pool
+  MSC_CUDA(ctx, cudaMemset(*dev_ptr, 0, nbytes));
+  cudaIpcMemHandle_t h;
+  MSC_CUDA(ctx, cudaIpcGetMemHandle(&h, *dev_ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return MSC_OK;
+}
+
+extern "C" int msc_peer_open(msc_ctx* ctx, const void* handle64, void** peer_ptr) {
+  if (!ctx || !handle64 || !peer_ptr) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  MSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MSC_CUDA(ctx, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MSC_OK;
+}
+
+extern "C" int msc_peer_close(msc_ctx* ctx, void* peer_ptr) {
+  if (!ctx) return MSC_ERR_ARG;
+  if (peer_ptr) MSC_CUDA(ctx, cudaIpcCloseMemHandle(peer_ptr));
+  return MSC_OK;
+}
+
+extern "C" int msc_peer_free(msc_ctx* ctx, void* dev_ptr) {
+  if (!ctx) return MSC_ERR_ARG;
+  if (dev_ptr) MSC_CUDA(ctx, cudaFree(dev_ptr));
+  return MSC_OK;
 }
 
 extern "C" int msc_rel_nrows_dev(msc_rel* r, const uint64_t** nrows_dev) {

@@ -50,6 +50,10 @@ struct JitParams {  // must match struct JitParams in jit_prelude.inc
   long long fconsts[32];
   unsigned long long* fmeta;
   uint32_t* ticket;
+  unsigned long long* mailbox[8];
+  const int* inv;
+  unsigned long long epoch;
+  int rank, world, nlocal, slot_cells, nglobal, _pad3;
 };
 static_assert(MSC_VM_MAX_STAGED == 24 && MSC_VM_MAX_GATHER == 16 && MSC_VM_MAX_LUTS == 8 && MSC_VM_MAX_CONSTS == 32 && MSC_VM_MAX_OUT == 24,
               "JitParams layout");
@@ -172,6 +176,7 @@ struct Gen {
   const int32_t* fin_cols = nullptr;  // staged slot of `fin` -> column of the compacted relation (0 = group id, 1 + s = accumulator s)
   const int32_t* fin_phys = nullptr;  // physical types of its outputs
   int fin_nout = 0, count_slot = 0;
+  bool fin_peer = false;  // merge the partial tables of all ranks over NVLink peer memory before the projection
   bool in_finish = false;
   std::ostringstream o;
   std::string why;
@@ -707,13 +712,55 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
   __syncthreads();
   if (s_last && warp == 0) {
     __threadfence();
-    const int g = lane;
+)";
+    if (!fin_peer) {
+      o << R"(    const int g = lane;
     const bool in_range = g < NG;
     const u64* cell = p.dense_out + (in_range ? g : 0) * STRIDE;
     i64 a[STRIDE];
 #pragma unroll
     for (int s = 0; s < STRIDE; ++s) a[s] = static_cast<i64>(__ldcg(cell + s));
 )";
+    } else {
+      // the exchange, inside the same kernel: push this rank's table into every rank's mailbox (peer stores over NVLink),
+      // publish the epoch, wait for the W epochs of the own mailbox, fold the W tables in rank order
+      o << R"(    const u32 set = static_cast<u32>(p.epoch & 1u);
+    const u64 flag_off = static_cast<u64>(set) * p.world, slot_off = 2ull * p.world + (static_cast<u64>(set) * p.world) * p.slot_cells;
+    for (int peer = 0; peer < p.world; ++peer) {
+      u64* dst = p.mailbox[peer] + slot_off + static_cast<u64>(p.rank) * p.slot_cells;
+      for (int i = lane; i < p.nlocal * STRIDE; i += 32) dst[i] = __ldcg(p.dense_out + i);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < p.world) st_release_sys(p.mailbox[lane] + flag_off + p.rank, p.epoch);
+    bool late = false;
+    if (lane < p.world) {
+      const u64* flag = p.mailbox[p.rank] + flag_off + lane;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(flag) != p.epoch) {
+        if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer never launched this pass
+          late = true;
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    if (__any_sync(0xffffffffu, late) && lane == 0) atomicOr(p.err, 32);  // MSC_DEVERR_PEER_TIMEOUT
+    __syncwarp();
+    const int g = lane;  // merged (global) group
+    const bool in_range = g < p.nglobal;
+    i64 a[STRIDE];
+#pragma unroll
+    for (int s = 0; s < STRIDE; ++s) a[s] = INIT[s];
+    for (int r = 0; r < p.world; ++r) {
+      const int lg = in_range ? p.inv[r * 32 + g] : -1;
+      if (lg < 0) continue;
+      const u64* cell = p.mailbox[p.rank] + slot_off + static_cast<u64>(r) * p.slot_cells + static_cast<u64>(lg) * STRIDE;
+#pragma unroll
+      for (int s = 0; s < STRIDE; ++s) a[s] = agg_combine_k(KIND[s], a[s], static_cast<i64>(ld_volatile(cell + s)));
+    }
+)";
+    }
     o << "    bool valid = in_range && a[" << count_slot << "] != 0;\n    bool nonfinite = false, bad = false;\n";
     for (int s = 0; s < naggs; ++s)
       if (kinds[s] == MSC_AGG_SUM_F) o << "    nonfinite |= in_range && !isfinite(l2d(a[" << s << "]));\n";
@@ -890,6 +937,7 @@ int generate(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const 
     g.fin_phys = fin->out_phys;
     g.fin_nout = fin->nout;
     g.count_slot = fin->count_slot;
+    g.fin_peer = fin->peer != nullptr;
   }
   if (!g.generate()) {
     *err = g.why;
@@ -1048,7 +1096,7 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
                      unsigned long long* table, bool timed, bool* masked, const JitFinish* fin) {
   std::string skey = shape_key(ctx, sd, ngroups, naggs, stride, kinds, init, *masked);
   if (fin) {  // the final projection is part of the kernel text
-    const int head[4] = {-7, fin->nout, fin->count_slot, fin->scan->nstaged};
+    const int head[4] = {fin->peer ? -8 : -7, fin->nout, fin->count_slot, fin->scan->nstaged};
     skey.append(reinterpret_cast<const char*>(head), sizeof(head));
     skey.append(reinterpret_cast<const char*>(fin->cols), sizeof(int32_t) * fin->scan->nstaged);
     skey.append(reinterpret_cast<const char*>(fin->out_phys), sizeof(int32_t) * fin->nout);
@@ -1070,10 +1118,22 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
   }
   *masked = sit->second.masked;
   Kernel& k = *sit->second.kernel;
-  if (sd->nrows == 0) return MSC_OK;
+  if (fin && fin->peer && fin->peer->compile_only) return MSC_OK;
+  if (sd->nrows == 0 && !(fin && fin->peer)) return MSC_OK;  // (a rank without rows still takes part in the exchange)
   JitParams p;
   MSC_TRY(fill_params(ctx, sd, &p));
   p.dense_out = table;
+  if (fin && fin->peer) {
+    const msc_peer_spec& ps = *fin->peer;
+    for (int r = 0; r < ps.world; ++r) p.mailbox[r] = static_cast<unsigned long long*>(ps.mailbox[r]);
+    p.inv = ps.inv;
+    p.epoch = ps.epoch;
+    p.rank = ps.rank;
+    p.world = ps.world;
+    p.nlocal = ps.nlocal;
+    p.slot_cells = ps.gmax * stride;
+    p.nglobal = ps.nglobal;
+  }
   if (fin) {
     memcpy(p.fconsts, fin->scan->consts, sizeof(int64_t) * fin->scan->nconsts);
     for (int c = 0; c < fin->nout; ++c) p.out[c] = fin->outs[c];

@@ -948,19 +948,22 @@ extern "C" int msc_dense_chain(msc_ctx* ctx, const msc_scan_desc* scan, int32_t 
   return MSC_OK;
 }
 
-// The same pass with NO launch after the scan: the specialised kernel's last CTA compacts the groups and runs the final
-// projection (jit.cu emit_finish).  *final_out stays null when this query cannot be fused (no specialised kernel for it,
-// lookup tables in the final projection, more than 32 groups, empty input): the caller then uses msc_dense_chain.
-extern "C" int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table,
-                               int32_t flags, const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
-                               msc_rel** final_out, int32_t* nonfinite) {
+namespace {
+int dense_fused_impl(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table, int32_t flags,
+                     const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                     const msc_peer_spec* peer, msc_rel** final_out, int32_t* nonfinite) {
   if (!ctx || !scan || !table || !final_scan || !final_cols || !final_out || !nonfinite || ngroups <= 0 || nout <= 0 || nout > MSC_VM_MAX_OUT)
     return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   *final_out = nullptr;
   *nonfinite = 0;
   static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
   static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
-  if (jit_mode == 0 || !(flags & MSC_DENSE_JIT) || scan->nrows == 0 || ngroups > 32) return MSC_OK;
+  const int out_groups = peer ? peer->nglobal : ngroups;
+  if (jit_mode == 0 || !(flags & MSC_DENSE_JIT) || ngroups > 32 || out_groups > 32 || out_groups <= 0) return MSC_OK;
+  if (!peer && scan->nrows == 0) return MSC_OK;
+  if (peer && (peer->world < 1 || peer->world > MSC_PEER_MAX_WORLD || peer->rank < 0 || peer->rank >= peer->world || peer->nlocal != ngroups ||
+               peer->gmax < ngroups || !peer->inv))
+    return ctx->fail(MSC_ERR_ARG, "bad peer specification");
   MSC_TRY(validate_program(ctx, scan, MODE_DENSE, agg_kinds, naggs, nullptr, 0));
   MSC_TRY(validate_program(ctx, final_scan, MODE_PROJECT, nullptr, 0, out_phys, nout));
   DensePlan dp;
@@ -970,8 +973,9 @@ extern "C" int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t 
     MSC_TRY(msc_alloc(ctx, sizeof(uint32_t), reinterpret_cast<void**>(&ctx->d_ticket)));
     MSC_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), ctx->stream));
   }
-  msc_rel* rel = new_rel(ctx, static_cast<uint64_t>(ngroups));
-  int rc = add_cols(ctx, rel, out_phys, nout, static_cast<uint64_t>(ngroups));
+  const bool compile_only = peer && peer->compile_only;
+  msc_rel* rel = new_rel(ctx, static_cast<uint64_t>(out_groups));
+  int rc = add_cols(ctx, rel, out_phys, nout, static_cast<uint64_t>(out_groups));
   if (rc == MSC_OK) rc = msc_alloc(ctx, 3 * sizeof(unsigned long long), reinterpret_cast<void**>(&rel->d_meta));
   if (rc != MSC_OK) {
     msc_rel_free(rel);
@@ -979,15 +983,22 @@ extern "C" int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t 
   }
   void* outs[MSC_VM_MAX_OUT];
   for (int i = 0; i < nout; ++i) outs[i] = rel->cols[i].data;
-  JitFinish fin{final_scan, final_cols, out_phys, nout, dp.count_slot, outs, rel->d_meta, ctx->d_ticket};
-  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
-  dense_init_kernel<<<1, 256, 0, ctx->stream>>>(static_cast<unsigned long long*>(table), ngroups, dp.stride, dense_meta(dp));
-  ctx->stats.launches += 1;
+  JitFinish fin{final_scan, final_cols, out_phys, nout, dp.count_slot, outs, rel->d_meta, ctx->d_ticket, peer};
+  if (!compile_only) {
+    MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    dense_init_kernel<<<1, 256, 0, ctx->stream>>>(static_cast<unsigned long long*>(table), ngroups, dp.stride, dense_meta(dp));
+    ctx->stats.launches += 1;
+  }
   bool masked = !(flags & MSC_DENSE_EXACT) && masked_enabled;
   rc = jit_dense_launch(ctx, scan, ngroups, naggs, dp.stride, dp.kinds, dp.init, static_cast<unsigned long long*>(table), true, &masked, &fin);
   if (rc != MSC_OK) {
     msc_rel_free(rel);
     return rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0 ? MSC_OK : rc;  // the generator declined: not an error, just not fused
+  }
+  if (compile_only) {  // the kernel exists now; hand back an empty relation as the "yes"
+    rel->nrows = 0;
+    *final_out = rel;
+    return MSC_OK;
   }
   rel->pending = true;
   msc_rel* rels[1] = {rel};
@@ -998,6 +1009,25 @@ extern "C" int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t 
   }
   *final_out = rel;
   return MSC_OK;
+}
+}  // namespace
+
+// The same pass with NO launch after the scan: the specialised kernel's last CTA compacts the groups and runs the final
+// projection (jit.cu emit_finish).  *final_out stays null when this query cannot be fused (no specialised kernel for it,
+// lookup tables in the final projection, more than 32 groups, empty input): the caller then uses msc_dense_chain.
+extern "C" int msc_dense_fused(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, void* table,
+                               int32_t flags, const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                               msc_rel** final_out, int32_t* nonfinite) {
+  return dense_fused_impl(ctx, scan, ngroups, agg_kinds, naggs, table, flags, final_scan, final_cols, out_phys, nout, nullptr, final_out, nonfinite);
+}
+
+// ... and across ranks: the last CTA also exchanges the partial tables over NVLink peer memory and merges them
+// (include/minispark_cuda.h, "fused scan + cross-GPU merge")
+extern "C" int msc_dense_fused_peer(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* agg_kinds, int32_t naggs, void* table, int32_t flags,
+                                    const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                                    const msc_peer_spec* peer, msc_rel** final_out, int32_t* nonfinite) {
+  if (!peer) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  return dense_fused_impl(ctx, scan, peer->nlocal, agg_kinds, naggs, table, flags, final_scan, final_cols, out_phys, nout, peer, final_out, nonfinite);
 }
 
 extern "C" int msc_jit_dense_source(const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked, char* buf,
@@ -1021,13 +1051,15 @@ extern "C" int msc_jit_dense_source(const msc_scan_desc* sd, int32_t ngroups, co
 
 extern "C" int msc_jit_dense_fused_source(const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked,
                                           const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
-                                          char* buf, size_t cap, size_t* len) {
+                                          int32_t peer, char* buf, size_t cap, size_t* len) {
   if (!sd || !agg_kinds || !len || !final_scan || !final_cols || !out_phys || ngroups <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS) return MSC_ERR_ARG;
   msc_ctx scratch;
   DensePlan dp;
   if (dense_plan(&scratch, sd, agg_kinds, naggs, &dp) != MSC_OK) return MSC_ERR_ARG;
   std::string source, err;
-  JitFinish fin{final_scan, final_cols, out_phys, nout, dp.count_slot, nullptr, nullptr, nullptr};
+  msc_peer_spec dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  JitFinish fin{final_scan, final_cols, out_phys, nout, dp.count_slot, nullptr, nullptr, nullptr, peer ? &dummy : nullptr};
   if (!jit_dense_supported(sd, ngroups, dp.stride)) err = "groups x accumulators exceed the register budget of a specialised kernel";
   else jit_dense_source(sd, ngroups, naggs, dp.stride, dp.kinds, dp.init, masked != 0, &source, &err, &fin);
   const std::string& text = source.empty() ? err : source;

@@ -398,6 +398,7 @@ class CudaExecutionEngine(ExecutionEngine):
         self._query_dicts: list[DictHandle] = []
         self._table_dicts: list[DictHandle] = []
         self._result_files: list[Path] = []
+        self._closers: list[Any] = []  # run at close(), before the context goes (peer mailboxes)
         self.last_stats: dict[str, Any] = {}
 
     # ---- ExecutionEngine contract ---------------------------------------------------------------
@@ -421,6 +422,9 @@ class CudaExecutionEngine(ExecutionEngine):
         if getattr(self, "ctx", None) is None:
             return
         self.release_query()
+        for closer in getattr(self, "_closers", []):
+            closer()
+        self._closers = []
         for entry in self._tables.values():
             for rel in entry.rels:
                 rel.free()
@@ -984,6 +988,114 @@ class _DenseMerge:
         return handle, e.ctx.stats().last_kernel_ms
 
 
+class _PeerExchange:
+    """Cross-rank merge of a prepared dense aggregate INSIDE the scan kernel, over NVLink peer memory.
+
+    Every rank owns a mailbox (CUDA IPC device memory its peers map); the scan's last CTA stores the rank's partial table
+    into all mailboxes, publishes the pass number, waits for its peers' and folds the tables in rank order before it
+    evaluates the final projection (csrc/jit.cu emit_finish, include/minispark_cuda.h msc_dense_fused_peer).  One kernel
+    per rank and pass where the NCCL path (_DenseMerge.enqueue) needs scan + all-gather + merge + compaction +
+    projection.  Set up collectively; any rank that cannot (no IPC, kernel not generated, more than 32 merged groups,
+    a rank without rows) sends everyone back to the NCCL path."""
+
+    def __init__(self, prepared: "PreparedAggregate") -> None:
+        import torch  # noqa: PLC0415
+
+        self.ok = False
+        e, m = prepared.engine, prepared.merge
+        comm = e.comm
+        self.engine = e
+        world, rank = comm.world, comm.rank
+        desc2, prog2, staged_cols = prepared._final[0], prepared._final[1], prepared._final[2]
+        self.desc2, self.prog2 = desc2, prog2
+        self.raw_cols = N.int32_array([0 if ci == 0 else 1 + prepared.prog.slot_of[ci - 1] for ci in staged_cols])
+        self.out_phys, self.nout = N.int32_array(prog2.out_phys), len(prog2.out_phys)
+        self.out_types = [x.type for x in prepared.plan.outputs]
+        cells = m.gmax * m.stride
+        self.own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        able = e.jit != "never" and m.nlocal > 0 and 0 < m.nglobal <= 32 and world <= N.K["MSC_PEER_MAX_WORLD"] and m.gmax <= 32
+        if able:
+            try:
+                e.ctx.call("msc_peer_alloc", 8 * (2 * world + 2 * world * cells), C.byref(self.own), handle)
+            except N.NativeError:
+                able = False
+        everyone = comm.all_gather_object((able, bytes(handle.raw)))
+        self.opened: list[int] = []
+        spec = N.PeerSpec()
+        if all(a for a, _ in everyone):
+            try:
+                for r, (_, h) in enumerate(everyone):
+                    if r == rank:
+                        spec.mailbox[r] = self.own.value
+                    else:
+                        ptr = C.c_void_p()
+                        e.ctx.call("msc_peer_open", C.create_string_buffer(h, 64), C.byref(ptr))
+                        self.opened.append(ptr.value)
+                        spec.mailbox[r] = ptr.value
+            except N.NativeError:
+                able = False
+        else:
+            able = False
+        inv = [-1] * (world * 32)
+        for r in range(world):
+            for g in range(m.gmax):
+                dst = m.perm[r * m.gmax + g]
+                if 0 <= dst < 32:
+                    inv[r * 32 + dst] = g
+        self.inv_dev = torch.tensor(inv, dtype=torch.int32, device=torch.device("cuda", e.device))
+        spec.inv = self.inv_dev.data_ptr()
+        spec.rank, spec.world, spec.nlocal, spec.gmax, spec.nglobal = rank, world, m.nlocal, m.gmax, m.nglobal
+        self.spec = spec
+        self.epoch = 0
+        self.prepared = prepared
+        if able:  # compile now, so that no rank waits in the kernel for a peer that is still in NVRTC (or gave up)
+            spec.compile_only = 1
+            fin, nonfinite = C.c_void_p(), C.c_int32()
+            try:
+                e.ctx.call("msc_dense_fused_peer", C.byref(prepared.desc), prepared.kinds, len(prepared.prog.agg_kinds), C.c_void_p(m.local.data_ptr()),
+                           N.K["MSC_DENSE_JIT"], C.byref(desc2), self.raw_cols, self.out_phys, self.nout, C.byref(spec), C.byref(fin),
+                           C.byref(nonfinite))
+                able = bool(fin.value)
+                if fin.value:
+                    e.ctx.lib.msc_rel_free(fin)
+            except N.NativeError:
+                able = False
+            spec.compile_only = 0
+        self.ok = all(comm.all_gather_object(able))
+        e._closers.append(self.close)
+        if not self.ok:
+            self.close()
+
+    def close(self) -> None:
+        e = self.engine
+        if getattr(e, "ctx", None) is None:
+            return
+        for ptr in self.opened:
+            e.ctx.lib.msc_peer_close(e.ctx.handle, C.c_void_p(ptr))
+        self.opened = []
+        if self.own.value:
+            e.ctx.lib.msc_peer_free(e.ctx.handle, self.own)
+            self.own = C.c_void_p()
+
+    def run(self) -> int:
+        """One pass on this rank (every rank must call it); returns the handle of the final relation."""
+        e, p, m = self.engine, self.prepared, self.prepared.merge
+        fin, nonfinite = C.c_void_p(), C.c_int32()
+        for exact in (False, True):
+            self.epoch += 1
+            self.spec.epoch = self.epoch
+            flags = N.K["MSC_DENSE_JIT"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
+            e.ctx.call("msc_dense_fused_peer", C.byref(p.desc), p.kinds, len(p.prog.agg_kinds), C.c_void_p(m.local.data_ptr()), flags,
+                       C.byref(self.desc2), self.raw_cols, self.out_phys, self.nout, C.byref(self.spec), C.byref(fin), C.byref(nonfinite))
+            if not fin.value:
+                raise ExecutionError("fused cross-rank aggregate unavailable after it was set up")
+            if not nonfinite.value or exact:  # (the merged sums are identical on all ranks, so all ranks repeat together)
+                break
+            e.ctx.lib.msc_rel_free(fin)
+        return fin.value
+
+
 class PreparedAggregate:
     """A compiled ``scan -> filter -> GROUP BY -> final projection`` query bound to device-resident columns."""
 
@@ -1026,6 +1138,7 @@ class PreparedAggregate:
         self._final: Optional[tuple] = None  # compiled final projection, re-bound to every pass's aggregate result
         self._chain_args: Optional[tuple] = None
         self._fusable = True  # until msc_dense_fused says otherwise
+        self._peer: Any = None  # _PeerExchange once set up, False when unavailable
 
     def run(self) -> tuple[DeviceRel, float]:
         """One pass of the hot path; returns (result relation, device milliseconds from the first launch to the result).
@@ -1040,6 +1153,17 @@ class PreparedAggregate:
         upper = self.merge.nglobal if self.merge is not None else self.ngroups
         if self.merge is None and self._final is not None:
             return self._run_chain()
+        if self.merge is not None and self._final is not None and self.merge.persistent:
+            if self._peer is None:  # collective: every rank gets here on its second pass
+                self._peer = _PeerExchange(self) if os.environ.get("MINISPARK_PEER_MERGE", "1") != "0" else False
+            if self._peer and self._peer.ok:
+                handle = self._peer.run()
+                st = e.ctx.stats()
+                self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
+                                   "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread, "kind": st.last_scan_kind,
+                                   "regs": st.last_scan_regs, "exchange": "nvlink peer stores inside the scan kernel"}
+                final = e._track(DeviceRel.from_handle(e.ctx, handle, self._peer.out_types, self._peer.prog2.out_dicts))
+                return final, st.last_kernel_ms
         for exact in (False, True):
             if self.merge is not None:
                 raw_h = self.merge.enqueue(self.desc, exact)

@@ -93,6 +93,20 @@ class Stats(C.Structure):
     ]
 
 
+class PeerSpec(C.Structure):
+    _fields_ = [
+        ("mailbox", C.c_void_p * 8),
+        ("inv", C.c_void_p),
+        ("epoch", C.c_uint64),
+        ("rank", C.c_int32),
+        ("world", C.c_int32),
+        ("nlocal", C.c_int32),
+        ("gmax", C.c_int32),
+        ("nglobal", C.c_int32),
+        ("compile_only", C.c_int32),
+    ]
+
+
 class ConcatPart(C.Structure):
     _fields_ = [("codes", ColBind), ("dict", C.c_void_p), ("literal", C.c_char_p), ("literal_len", C.c_uint64)]
 
@@ -137,7 +151,7 @@ _SIGNATURES = {
     "msc_jit_dense_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t,
                              C.POINTER(C.c_size_t)]),
     "msc_jit_dense_fused_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
-                                   C.POINTER(C.c_int32), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+                                   C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "msc_jit_project_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "msc_jit_compile": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "msc_dense_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -145,6 +159,13 @@ _SIGNATURES = {
                         C.POINTER(C.c_int32)]),
     "msc_dense_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "msc_peer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "msc_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "msc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msc_dense_fused_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(PeerSpec), C.POINTER(C.c_void_p),
+                             C.POINTER(C.c_int32)]),
     "msc_rel_nrows_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_rel_settle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int32)]),
     "msc_dense_merge_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,

@@ -44,6 +44,25 @@ def main() -> None:
         got = cases.q1(ns, str(lineitem), engine).collect()
         assert engine.last_stats["exchange"] == "all_gather"
         O.assert_rows_equal(got, O.run_task(cases.q1(ns, str(lineitem)).task, wire=True), rel=5e-7)
+        # the same query prepared: pass 1 merges through NCCL, later passes exchange the partial tables over NVLink peer
+        # memory inside the specialised scan kernel (msc_dense_fused_peer); every rank must hold the same complete answer
+        prepared = engine.prepare(cases.q1(ns, str(lineitem)).task)
+        want_f64 = {r["l_returnflag"]: r for r in O.run_task(cases.q1(ns, str(lineitem)).task, wire=False)}
+        exchanges = []
+        for _ in range(4):
+            final, _ms = prepared.run()
+            names = [n for n, _ in prepared.plan.schema]
+            keys = final.cols[0].dict.export()
+            cols = [final.column_numpy(i) for i in range(len(names))]
+            rows = {keys[int(cols[0][r])]: {n: cols[i][r].item() for i, n in enumerate(names) if i} for r in range(final.nrows)}
+            exchanges.append(prepared.scan_stats.get("exchange", "nccl"))
+            engine.release_query()
+            assert sorted(rows) == sorted(want_f64), (sorted(rows), sorted(want_f64))
+            for k, ref in want_f64.items():
+                for name, v in rows[k].items():
+                    assert abs(v - ref[name]) <= 1e-9 * max(abs(ref[name]), 1e-300), (k, name, v, ref[name])
+        if os.environ.get("MINISPARK_PEER_MERGE", "1") != "0":
+            assert exchanges[0] == "nccl" and all(x.startswith("nvlink") for x in exchanges[1:]), exchanges
         # high-cardinality GROUP BY through hash partitioning + all-to-all: ranks hold disjoint key ranges
         os.environ["MSC_EXCHANGE_GATHER_MAX"] = "0"
         part = high_card(engine).collect()

@@ -205,10 +205,19 @@ def test_q1_with_fused_finish_compiles(tmp_path):
     n = C.c_size_t()
     buf = C.create_string_buffer(1 << 20)
     rc = lib.msc_jit_dense_fused_source(C.byref(d), 3, N.int32_array(prog.agg_kinds), len(prog.agg_kinds), 1, C.byref(d2), N.int32_array(raw_cols),
-                                        N.int32_array(prog2.out_phys), len(prog2.out_phys), buf, len(buf), C.byref(n))
+                                        N.int32_array(prog2.out_phys), len(prog2.out_phys), 0, buf, len(buf), C.byref(n))
     src = buf.value.decode()
     assert rc == 0, src
+    assert "p.mailbox" not in src.split("msc_jit_dense(")[1]
     assert "atomicAdd(p.ticket, 1u) == gridDim.x - 1" in src and "p.fmeta[0] = __popc(keep)" in src
     assert src.count("p.out[") == len(prog2.out_phys)
     assert " / " in src.split("s_last")[-1]                     # AVG = SUM / COUNT happens in the finish
     compile_source(src)
+    # the cross-rank variant: the same last CTA first exchanges the partial tables over NVLink peer memory
+    rc = lib.msc_jit_dense_fused_source(C.byref(d), 3, N.int32_array(prog.agg_kinds), len(prog.agg_kinds), 1, C.byref(d2), N.int32_array(raw_cols),
+                                        N.int32_array(prog2.out_phys), len(prog2.out_phys), 1, buf, len(buf), C.byref(n))
+    peer_src = buf.value.decode()
+    assert rc == 0, peer_src
+    body = peer_src.split("msc_jit_dense(")[1]
+    assert "st_release_sys(p.mailbox[lane]" in body and "ld_acquire_sys(flag) != p.epoch" in body and "p.inv[r * 32 + g]" in body
+    compile_source(peer_src)
