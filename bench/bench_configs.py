@@ -42,9 +42,9 @@ def main() -> None:
     base = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
     folder = base / f"minispark_b200_cfg_{os.getuid()}"
     folder.mkdir(parents=True, exist_ok=True)
-    lineitem, orders = folder / f"lineitem_sf{args.sf:g}.bin", folder / f"orders_sf{args.sf:g}.bin"
+    lineitem, orders = folder / f"lineitem6_sf{args.sf:g}.bin", folder / f"orders_sf{args.sf:g}.bin"
     if not lineitem.exists():
-        gen_tpch.write_table(lineitem, "lineitem", sf=args.sf, columns=["l_orderkey", "l_quantity", "l_extendedprice", "l_shipmode"])
+        gen_tpch.write_table(lineitem, "lineitem", sf=args.sf, columns=["l_orderkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_shipmode"])
     if not orders.exists():
         gen_tpch.write_table(orders, "orders", sf=args.sf, columns=["o_orderkey", "o_orderdate", "o_orderpriority"])
     ns = cases.namespace()
@@ -68,7 +68,13 @@ def main() -> None:
     def project_only(e):  # noqa: ANN001, ANN202
         return ns.DataFrame(e).table(str(lineitem)).select((ns.Col("l_extendedprice") * ns.Col("l_quantity")).alias("v"))
 
-    configs = (("config4_high_cardinality_group_by", config4), ("config5_join_filter_like_group_by", config5),
+    def q1_by_shipmode(e):  # noqa: ANN001, ANN202  (Q1's aggregates over 7 groups: 49 accumulator cells)
+        disc = ns.Col("l_extendedprice") * (ns.Lit(1) - ns.Col("l_discount"))
+        return ns.DataFrame(e).table(str(lineitem)).group_by(ns.Col("l_shipmode")).agg(
+            ns.F.sum(ns.Col("l_quantity")).alias("q"), ns.F.sum(ns.Col("l_extendedprice")).alias("p"), ns.F.sum(disc).alias("dp"),
+            ns.F.sum(disc * (ns.Lit(1) + ns.Col("l_tax"))).alias("ch"), ns.F.avg(ns.Col("l_discount")).alias("d"), ns.F.count().alias("n"))
+
+    configs = (("q1_by_shipmode", q1_by_shipmode), ("config4_high_cardinality_group_by", config4), ("config5_join_filter_like_group_by", config5),
                ("filter_project", filter_project), ("project_only", project_only))
     only = [x for x in args.only.split(",") if x]
     with CudaExecutionEngine(device=0, shard=(0, 1), jit=args.jit) as e:
@@ -92,7 +98,7 @@ def main() -> None:
             print(json.dumps({"config": name, "sf": args.sf, "lineitem_rows": nl, "result_rows": rows_out, "ms": round(1e3 * med, 3),
                               "lineitem_rows_per_s": nl / med, "passes_ms": [round(1e3 * t, 2) for t in times],
                               "last_kernel_ms": stats.get("kernel_ms"), "agg_mode": stats.get("agg_mode"), "jit": e.jit,
-                              "scan_kind": stats.get("scan_kind"), "jit_compiles": e.ctx.stats().jit_compiles}), flush=True)
+                              "scan_kind": stats.get("scan_kind"), "agg_scan_kind": stats.get("agg_scan_kind"), "agg_scan_ms": stats.get("agg_scan_ms"), "jit_compiles": e.ctx.stats().jit_compiles}), flush=True)
     if os.environ.get("MSC_BENCH_KEEP") is None:
         lineitem.unlink(missing_ok=True)
         orders.unlink(missing_ok=True)

@@ -350,7 +350,7 @@ struct Gen {
       why = "count scan without a filter";
       return false;
     }
-    o << kPrelude;
+    o << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
     o << "constexpr int NSTAGES = " << nstages << ";\n";
     emit_layout(lay);
     o << R"(
@@ -497,7 +497,8 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_scan(const __g
       count_const[naggs] = -1;
     }
 
-    o << kPrelude;
+    // registers: 2 per accumulator cell; up to 32 cells fit 4 CTAs of 128 threads per SM (128 registers), more need 3 (168)
+    o << "#define MINCTAS " << (ngroups * stride <= JIT_REG_CELLS_4CTAS ? 4 : 3) << "\n" << kPrelude;
     if (masked) {  // the masks are fixed at GROUP: a later filter would not reach them
       bool grouped_seen = false;
       for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
@@ -891,10 +892,10 @@ int compile(const std::string& source, int minctas, std::vector<char>* cubin, st
     *err = "nvrtcCreateProgram failed";
     return MSC_ERR_ARG;
   }
-  const std::string minb = "-DMINCTAS=" + std::to_string(minctas);
+  (void)minctas;  // the source defines MINCTAS itself (it depends on the number of accumulator cells)
   // --fmad=false: Python rounds every operation (sql.py:262-266); a contracted a * b + c would not
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "--fmad=false", minb.c_str()};
-  const int rc = a.nvrtcCompileProgram(prog, 6, opts);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "--fmad=false"};
+  const int rc = a.nvrtcCompileProgram(prog, 5, opts);
   if (rc != 0) {
     size_t n = 0;
     a.nvrtcGetProgramLogSize(prog, &n);

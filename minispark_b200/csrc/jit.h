@@ -7,7 +7,8 @@
 
 namespace mscan {
 
-constexpr int JIT_MAX_REG_CELLS = 32;  // groups x accumulators kept in registers by the specialised kernel
+constexpr int JIT_MAX_REG_CELLS = 56;    // groups x accumulators kept in registers by the specialised kernel
+constexpr int JIT_REG_CELLS_4CTAS = 32;  // up to here 128 registers per thread suffice (4 CTAs per SM), beyond: 168 (3 CTAs)
 constexpr int JIT_MIN_CTAS = 4;        // __launch_bounds__(128, 4): at most 128 registers per thread
 
 // Optional fused finish of a dense aggregate scan: the last CTA compacts the groups and runs the final projection

@@ -720,6 +720,7 @@ class CudaExecutionEngine(ExecutionEngine):
             self.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), hint, C.byref(out))
             self._note_kernel()
             self.last_stats["agg_scan_kind"] = self.last_stats["scan_kind"]  # later scans (final projection) overwrite scan_kind
+            self.last_stats["agg_scan_ms"] = self.last_stats["scan_ms"]
             raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
             if self.comm.world > 1:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
                 raw = self._merge_partials(raw, prog.agg_kinds, slot_types, group.type)

@@ -1,3 +1,4 @@
+#define MINCTAS 4
 
 // jit_prelude.inc -- fixed part of the source handed to NVRTC by jit.cu (a C++ raw string literal body).
 //
@@ -21,7 +22,30 @@ struct JitParams {  // must match struct JitParams in jit.cu
   i64 consts[32];
   u64* dense_out;  // [ngroups][stride]
   int* err;
+  u32* tile_counts;         // count scans: surviving rows of every warp tile
+  const u64* tile_offsets;  // project scans with a filter: output position of every warp tile's first surviving row
+  void* out[24];            // project scans: output columns (u32, or raw 64-bit); fused finish: columns of the final relation
+  i64 fconsts[32];          // fused finish: constants of the final projection
+  u64* fmeta;               // fused finish: {result rows, 1 if a SUM came out non-finite, device error word}
+  u32* ticket;              // fused finish: CTAs done (the last one finishes; it resets the counter)
+  // fused finish across ranks (NVLink peer memory): every rank's mailbox = u64 flag[2][world], u64 slot[2][world][cells]
+  u64* mailbox[8];
+  const int* inv;           // [world][32]: rank r's local group of merged group G, or -1
+  u64 epoch;
+  int rank, world, nlocal, slot_cells, nglobal, _pad3;
 };
+
+__device__ __forceinline__ void st_release_sys(u64* addr, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* addr) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ u64 ld_volatile(const u64* addr) {
+  u64 v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+  return v;
+}
 
 constexpr int NT = 128, NW = 4, R = 8, WT = 256;
 constexpr int SMEM_HEADER = NW * 8 * 8;  // mbarriers: full[warp][stage], up to 8 stages
@@ -375,9 +399,9 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     }
   }
   if (bad) atomicOr(p.err, 1);  // MSC_DEVERR_DIV_ZERO
-  a0_5 += (i64)n0_5 * 1ll;
-  a1_5 += (i64)n1_5 * 1ll;
-  a2_5 += (i64)n2_5 * 1ll;
+  a0_5 += (i64)n0_5 * p.consts[2];
+  a1_5 += (i64)n1_5 * p.consts[2];
+  a2_5 += (i64)n2_5 * p.consts[2];
   { const i64 v = warp_fold<0>(d2l(a0_0)); if (lane == 0) red[warp * (NG * STRIDE) + 0] = v; }
   { const i64 v = warp_fold<0>(d2l(a0_1)); if (lane == 0) red[warp * (NG * STRIDE) + 1] = v; }
   { const i64 v = warp_fold<0>(d2l(a0_2)); if (lane == 0) red[warp * (NG * STRIDE) + 2] = v; }
@@ -403,5 +427,102 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
 #pragma unroll
     for (int w = 1; w < NW; ++w) v = agg_combine_k(kind, v, red[w * (NG * STRIDE) + cell]);
     if (v != INIT[cell % STRIDE]) atomic_fold(kind, p.dense_out + cell, v);
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    const int g = lane;
+    const bool in_range = g < NG;
+    const u64* cell = p.dense_out + (in_range ? g : 0) * STRIDE;
+    i64 a[STRIDE];
+#pragma unroll
+    for (int s = 0; s < STRIDE; ++s) a[s] = static_cast<i64>(__ldcg(cell + s));
+    bool valid = in_range && a[5] != 0;
+    bool nonfinite = false, bad = false;
+    nonfinite |= in_range && !isfinite(l2d(a[0]));
+    nonfinite |= in_range && !isfinite(l2d(a[1]));
+    nonfinite |= in_range && !isfinite(l2d(a[2]));
+    nonfinite |= in_range && !isfinite(l2d(a[3]));
+    nonfinite |= in_range && !isfinite(l2d(a[4]));
+    const i64 f0 = (i64)g;
+    const i64 f1 = a[0];
+    const i64 f2 = a[1];
+    const i64 f3 = a[3];
+    const i64 f4 = a[4];
+    const i64 f5 = a[5];
+    const i64 f6 = a[2];
+    i64 fo0 = 0;
+    i64 fo1 = 0;
+    i64 fo2 = 0;
+    i64 fo3 = 0;
+    i64 fo4 = 0;
+    i64 fo5 = 0;
+    i64 fo6 = 0;
+    i64 fo7 = 0;
+    i64 fo8 = 0;
+    {
+      const i64 x = f0;
+      fo0 = x;
+    }
+    {
+      const i64 x = f1;
+      fo1 = x;
+    }
+    {
+      const i64 x = f2;
+      fo2 = x;
+    }
+    {
+      const i64 x = f3;
+      fo3 = x;
+    }
+    {
+      const i64 x = f4;
+      fo4 = x;
+    }
+    {
+      bad |= valid && (l2d(d2l((double)(f5))) == 0.0);
+      const i64 x = (l2d(d2l((double)(f5))) == 0.0 ? d2l(0.0) : d2l(l2d(f1) / l2d(d2l((double)(f5)))));
+      fo5 = x;
+    }
+    {
+      bad |= valid && (l2d(d2l((double)(f5))) == 0.0);
+      const i64 x = (l2d(d2l((double)(f5))) == 0.0 ? d2l(0.0) : d2l(l2d(f2) / l2d(d2l((double)(f5)))));
+      fo6 = x;
+    }
+    {
+      bad |= valid && (l2d(d2l((double)(f5))) == 0.0);
+      const i64 x = (l2d(d2l((double)(f5))) == 0.0 ? d2l(0.0) : d2l(l2d(f6) / l2d(d2l((double)(f5)))));
+      fo7 = x;
+    }
+    {
+      const i64 x = f5;
+      fo8 = x;
+    }
+    const u32 keep = __ballot_sync(0xffffffffu, valid);
+    const int pos = __popc(keep & ((1u << lane) - 1u));
+    if (valid) {
+      reinterpret_cast<u32*>(p.out[0])[pos] = (u32)fo0;
+      reinterpret_cast<i64*>(p.out[1])[pos] = (i64)fo1;
+      reinterpret_cast<i64*>(p.out[2])[pos] = (i64)fo2;
+      reinterpret_cast<i64*>(p.out[3])[pos] = (i64)fo3;
+      reinterpret_cast<i64*>(p.out[4])[pos] = (i64)fo4;
+      reinterpret_cast<i64*>(p.out[5])[pos] = (i64)fo5;
+      reinterpret_cast<i64*>(p.out[6])[pos] = (i64)fo6;
+      reinterpret_cast<i64*>(p.out[7])[pos] = (i64)fo7;
+      reinterpret_cast<i64*>(p.out[8])[pos] = (i64)fo8;
+    }
+    const bool any_nonfinite = __any_sync(0xffffffffu, nonfinite), any_bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      p.fmeta[0] = __popc(keep);
+      p.fmeta[1] = any_nonfinite ? 1 : 0;
+      p.fmeta[2] = static_cast<u64>(*reinterpret_cast<volatile int*>(p.err) | (any_bad ? 1 : 0));
+      *p.err = 0;
+      *p.ticket = 0;
+    }
   }
 }

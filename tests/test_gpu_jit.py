@@ -119,3 +119,26 @@ def test_non_finite_inputs_rerun_on_the_exact_variant(tmp_path):
             assert math.isinf(got[k]["s"])
         else:
             assert math.isfinite(got[k]["s"]) and abs(got[k]["s"] - math.fsum(mine)) <= 1e-9 * math.fsum(mine)
+
+
+def test_seven_groups_take_the_three_cta_variant(small_lineitem):
+    """49 accumulator cells: still registers, at 168 per thread (3 CTAs per SM instead of 4)."""
+    from minispark_b200.execution import CudaExecutionEngine
+    from oracle import py_oracle as O
+    from test_gpu_dense_variants import _query
+
+    ns = cases.namespace()
+    want = {r["l_shipmode"]: r for r in O.run_task(_query(ns, small_lineitem, "l_shipmode").task, wire=False)}
+    assert len(want) == 7
+    with CudaExecutionEngine() as engine:
+        prepared = engine.prepare(_query(ns, small_lineitem, "l_shipmode").task)
+        for _ in range(2):  # the second pass runs the kernel with the fused finish
+            final, _ms = prepared.run()
+            got = _rows(engine, final, prepared.plan.schema)
+            assert prepared.scan_stats["kind"] == 2 and prepared.scan_stats["regs"] > 128
+            engine.release_query()
+            assert sorted(got) == sorted(want)
+            for k, ref in want.items():
+                assert got[k]["n"] == ref["n"]
+                for name in ("q", "dp", "ch", "t"):
+                    assert abs(got[k][name] - ref[name]) <= 1e-9 * abs(ref[name]), (k, name, got[k][name], ref[name])
