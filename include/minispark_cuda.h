@@ -217,6 +217,7 @@ typedef struct msc_stats {
 #define MSC_SCAN_KIND_VM 0    /* C++ three-address interpreter (scan_kernel.cuh) */
 #define MSC_SCAN_KIND_REGVM 1 /* register-resident PTX interpreter (scan_regvm_impl.cuh) */
 #define MSC_SCAN_KIND_JIT 2   /* query-specialised kernel compiled at run time (jit.cu) */
+#define MSC_SCAN_KIND_RUNS 3  /* the C++ interpreter as a streaming aggregate over the runs of a sorted key (MODE_RUNS) */
 
 /* ---- context ---------------------------------------------------------------------------- */
 MSC_API int msc_abi_version(void);

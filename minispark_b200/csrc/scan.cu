@@ -138,15 +138,36 @@ __global__ void hash_emit_kernel(const unsigned long long* tbl, uint64_t cap, ui
   }
 }
 
-// runs of equal adjacent values in a column: an upper bound of its distinct values (every value starts at least one
-// run), exact for clustered keys such as lineitem's l_orderkey.  Sizes the hash table of a GROUP BY on a plain column.
+// Runs of equal adjacent values of a column, counted per 256-row tile (one block per tile), plus the number of
+// descents.  The total bounds the column's distinct values (every value starts at least one run; exact for clustered
+// keys such as lineitem's l_orderkey) and sizes the hash table of a GROUP BY on that column; with no descent the column
+// is sorted, every run IS a group, and the aggregate needs no table at all (MODE_RUNS).
+constexpr int RUN_TILE = 256;
 template <class T>
-__global__ void count_runs_kernel(const T* col, uint64_t n, unsigned long long* out) {
-  unsigned long long c = 0;
-  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
-    c += (i == 0) || (col[i] != col[i - 1]);
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+__global__ void run_heads_kernel(const T* col, uint64_t n, uint32_t* tile_counts, unsigned long long* descents) {
+  __shared__ uint32_t wsum[RUN_TILE / 32];
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * RUN_TILE + threadIdx.x;
+  uint32_t head = 0, desc = 0;
+  if (i < n) {
+    if (i == 0) {
+      head = 1;
+    } else {
+      const T cur = col[i], prev = col[i - 1];
+      head = cur != prev;
+      desc = cur < prev;
+    }
+  }
+  const uint32_t hb = __ballot_sync(0xffffffffu, head), db = __ballot_sync(0xffffffffu, desc);
+  if ((threadIdx.x & 31) == 0) {
+    wsum[threadIdx.x >> 5] = __popc(hb);
+    if (db) atomicAdd(descents, static_cast<unsigned long long>(__popc(db)));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int w = 0; w < RUN_TILE / 32; ++w) tot += wsum[w];
+    tile_counts[blockIdx.x] = tot;
+  }
 }
 
 // ---- generic exclusive scan: 3 kernels, CHUNK elements per block ---------------------------------
@@ -366,10 +387,10 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, const int3
         break;
       case MSC_DST_FILTER: case MSC_DST_NONE: break;
       case MSC_DST_GROUP:
-        if (mode != MODE_DENSE && mode != MODE_HASH) return ctx->fail(MSC_ERR_ARG, "GROUP outside an aggregate scan");
+        if (mode != MODE_DENSE && mode != MODE_HASH && mode != MODE_RUNS) return ctx->fail(MSC_ERR_ARG, "GROUP outside an aggregate scan");
         break;
       case MSC_DST_AGG:
-        if (mode != MODE_DENSE && mode != MODE_HASH) return ctx->fail(MSC_ERR_ARG, "AGG outside an aggregate scan");
+        if (mode != MODE_DENSE && mode != MODE_HASH && mode != MODE_RUNS) return ctx->fail(MSC_ERR_ARG, "AGG outside an aggregate scan");
         if (dst >= naggs) return ctx->fail(MSC_ERR_ARG, "AGG: bad accumulator");
         break;
       case MSC_DST_OUT:
@@ -533,6 +554,7 @@ bool regvm_enabled() {
 
 template <int MODE>
 int launch_scan_r(msc_ctx* ctx, LaunchPlan* lp) {
+  if constexpr (MODE == MODE_RUNS) return launch_scan<8, MODE>(ctx, lp);  // its per-tile run counts are for 256-row tiles
   if constexpr (MODE == MODE_DENSE || MODE == MODE_HASH) {
     if (lp->R == 8) return launch_scan<8, MODE>(ctx, lp);
   }
@@ -1150,30 +1172,90 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
 
   // ---- hash mode ----
   uint64_t want = hash_capacity_hint ? hash_capacity_hint : sd->nrows;
-  if (!hash_capacity_hint && sd->nrows >= (1u << 16)) {
-    // no hint: when the key is a plain staged column, its number of runs bounds the number of groups (one pass over
-    // the key column and one host read; sizing for nrows made the sf10 l_orderkey table 4.3 GB for 15 M groups)
+  if (!hash_capacity_hint && sd->nrows >= (1u << 16) && !sd->nrows_dev) {
+    // No hint.  When the key is a plain integer column, one pass over it counts its runs of equal adjacent values:
+    //  * their number bounds the number of groups (sizing for nrows made the sf10 l_orderkey table 4.3 GB for 15 M groups);
+    //  * a column without descents is sorted, so every run is exactly one group: a streaming aggregate (MODE_RUNS) writes
+    //    group r's key and accumulators straight to row r of the result -- no table, no probing, no compaction.
+    static const bool runs_enabled = !(getenv("MSC_SCAN_RUNS") && atoi(getenv("MSC_SCAN_RUNS")) == 0);
+    int key_col = -1;
+    bool filtered = false;
     for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
       const uint32_t w0 = sd->code[pc], a = sd->code[pc + 1] & 0xffffu;
       if ((w0 & 0x3f) == MSC_OP_END) break;
-      if (((w0 >> 6) & 7) != MSC_DST_GROUP || (w0 & 0x3f) != MSC_OP_MOV || ((a >> 12) & 15) != MSC_SRC_STAGED) continue;
-      const msc_colbind& kc = sd->staged[a & 0xfff];
-      DevTmp d_runs(ctx);
-      MSC_TRY(d_runs.alloc(sizeof(unsigned long long)));
-      MSC_CUDA(ctx, cudaMemsetAsync(d_runs.p, 0, sizeof(unsigned long long), ctx->stream));
-      const int grid = ctx->sm_count * 8;
-      switch (msc_phys_width(kc.phys)) {
-        case 1: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
-        case 2: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint16_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
-        case 4: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
-        default: count_runs_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint64_t*>(kc.data), sd->nrows, d_runs.as<unsigned long long>()); break;
+      if (((w0 >> 6) & 7) == MSC_DST_FILTER) filtered = true;
+      if (((w0 >> 6) & 7) == MSC_DST_GROUP && (w0 & 0x3f) == MSC_OP_MOV && ((a >> 12) & 15) == MSC_SRC_STAGED) key_col = a & 0xfff;
+    }
+    const int kphys = key_col >= 0 ? sd->staged[key_col].phys : -1;
+    if (kphys == MSC_P_U8 || kphys == MSC_P_U16 || kphys == MSC_P_U32 || kphys == MSC_P_I32 || kphys == MSC_P_I64) {
+      const void* kdata = sd->staged[key_col].data;
+      const uint64_t ntiles = (sd->nrows + RUN_TILE - 1) / RUN_TILE;
+      DevTmp d_desc(ctx), rcounts(ctx), roffsets(ctx);
+      MSC_TRY(d_desc.alloc(sizeof(unsigned long long)));
+      MSC_TRY(rcounts.alloc(sizeof(uint32_t) * ntiles));
+      MSC_TRY(roffsets.alloc(sizeof(uint64_t) * (ntiles + 1)));
+      MSC_CUDA(ctx, cudaMemsetAsync(d_desc.p, 0, sizeof(unsigned long long), ctx->stream));
+      const unsigned grid = static_cast<unsigned>(ntiles);
+      unsigned long long* dd = d_desc.as<unsigned long long>();
+      uint32_t* rc_ = rcounts.as<uint32_t>();
+      switch (kphys) {
+        case MSC_P_U8: run_heads_kernel<<<grid, RUN_TILE, 0, ctx->stream>>>(static_cast<const uint8_t*>(kdata), sd->nrows, rc_, dd); break;
+        case MSC_P_U16: run_heads_kernel<<<grid, RUN_TILE, 0, ctx->stream>>>(static_cast<const uint16_t*>(kdata), sd->nrows, rc_, dd); break;
+        case MSC_P_U32: run_heads_kernel<<<grid, RUN_TILE, 0, ctx->stream>>>(static_cast<const uint32_t*>(kdata), sd->nrows, rc_, dd); break;
+        case MSC_P_I32: run_heads_kernel<<<grid, RUN_TILE, 0, ctx->stream>>>(static_cast<const int32_t*>(kdata), sd->nrows, rc_, dd); break;
+        default: run_heads_kernel<<<grid, RUN_TILE, 0, ctx->stream>>>(static_cast<const long long*>(kdata), sd->nrows, rc_, dd); break;
       }
       ctx->stats.launches += 1;
+      MSC_TRY(msc_exclusive_scan_u32_u64(ctx, rc_, roffsets.as<uint64_t>(), ntiles));
       unsigned long long* h = ctx->h_scratch;
-      MSC_CUDA(ctx, cudaMemcpyAsync(h, d_runs.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      MSC_CUDA(ctx, cudaMemcpyAsync(h, roffsets.as<uint64_t>() + ntiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      MSC_CUDA(ctx, cudaMemcpyAsync(h + 1, d_desc.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
       MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      if (h[0] > 0 && h[0] < want) want = h[0];
-      break;
+      const uint64_t runs = h[0];
+      const bool sorted = h[1] == 0;
+      if (runs > 0 && runs < want) want = runs;
+      if (sorted && !filtered && runs_enabled && runs > 0 && runs < (1ull << 31)) {
+        // ---- streaming aggregate over the runs of a sorted key ----
+        LaunchPlan lp;
+        MSC_TRY(plan_launch(ctx, sd, 8, 0, &lp));
+        lp.p.naggs = naggs;
+        memcpy(lp.p.agg_kind, kinds, sizeof(int) * naggs);
+        msc_rel* rel = new_rel(ctx, runs);
+        int rc = add_col(ctx, rel, MSC_P_I64, runs);
+        for (int a = 0; rc == MSC_OK && a < naggs; ++a)
+          rc = add_col(ctx, rel, (kinds[a] == MSC_AGG_SUM_F || kinds[a] == MSC_AGG_MIN_F || kinds[a] == MSC_AGG_MAX_F) ? MSC_P_F64 : MSC_P_I64, runs);
+        if (rc != MSC_OK) {
+          msc_rel_free(rel);
+          return rc;
+        }
+        lp.p.out[0] = rel->cols[0].data;
+        for (int a = 0; a < naggs; ++a) {
+          lp.p.out[1 + a] = rel->cols[1 + a].data;
+          fill_u64_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(static_cast<unsigned long long*>(rel->cols[1 + a].data),
+                                                                     static_cast<unsigned long long>(init[a]), runs);
+        }
+        ctx->stats.launches += naggs;
+        lp.p.tile_offsets = roffsets.as<uint64_t>();
+        lp.p.run_key_col = key_col;
+        rc = launch_scan_r<MODE_RUNS>(ctx, &lp);
+        if (rc != MSC_OK) {
+          msc_rel_free(rel);
+          return rc;
+        }
+        ctx->stats.last_scan_kind = MSC_SCAN_KIND_RUNS;
+        MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+        const int drc = msc_check_device_error(ctx);  // synchronises the stream
+        if (drc != MSC_OK) {
+          msc_rel_free(rel);
+          return drc;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+        ctx->stats.last_kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
+        *out = rel;
+        return MSC_OK;
+      }
     }
   }
   if (want < 16) want = 16;

@@ -24,7 +24,8 @@ constexpr int NW = NT / 32;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_HEADER = NW * MAX_STAGES * 8;  // mbarriers: full[warp][stage]
 
-enum Mode { MODE_DENSE = 0, MODE_HASH = 1, MODE_COUNT = 2, MODE_PROJECT = 3 };
+// MODE_RUNS: GROUP BY a sorted key column -- every run of equal keys is a group, its output row is its run number
+enum Mode { MODE_DENSE = 0, MODE_HASH = 1, MODE_COUNT = 2, MODE_PROJECT = 3, MODE_RUNS = 4 };
 
 struct StagedCol {
   const unsigned char* base;
@@ -69,6 +70,9 @@ struct ScanParams {
   void* out[MSC_VM_MAX_OUT];
   int out_phys[MSC_VM_MAX_OUT];
   const unsigned long long* nrows_dev;  // when set: the row count is the device's (nrows is an upper bound)
+  // MODE_RUNS: staged slot of the key column; tile_offsets[] = runs that start before each warp tile; out[0] = key
+  // column of the result (i64), out[1 + a] = accumulator column a, already holding its identity
+  int run_key_col;
 };
 
 struct LaunchPlan {
@@ -419,6 +423,7 @@ struct Ctx {
   long long* acc;              // CTA accumulators: [(group * naggs + slot) * NT + tid]
   int lane;
   int tid;
+  uint64_t tile;  // warp tile being evaluated
 };
 
 template <int R>
@@ -512,6 +517,7 @@ __device__ __forceinline__ void agg_any(const Ctx& c, int slot, int kind, const 
   case KIND:                                                                                        \
     if constexpr (MODE == MODE_DENSE) agg_dense_k<R, KIND>(c, slot, grp, v);                        \
     else if constexpr (MODE == MODE_HASH) agg_hash<R, KIND>(c.p.htbl, c.p.hshift, slot, grp, v);     \
+    else if constexpr (MODE == MODE_RUNS) agg_hash<R, KIND>(static_cast<unsigned long long*>(c.p.out[1 + slot]) - 1, 0, 0, grp, v); \
     break;
     AGG_ANY_CASE(MSC_AGG_SUM_F)
     AGG_ANY_CASE(MSC_AGG_SUM_I)
@@ -521,6 +527,7 @@ __device__ __forceinline__ void agg_any(const Ctx& c, int slot, int kind, const 
     default:
       if constexpr (MODE == MODE_DENSE) agg_dense_k<R, MSC_AGG_MAX_I>(c, slot, grp, v);
       else if constexpr (MODE == MODE_HASH) agg_hash<R, MSC_AGG_MAX_I>(c.p.htbl, c.p.hshift, slot, grp, v);
+      else if constexpr (MODE == MODE_RUNS) agg_hash<R, MSC_AGG_MAX_I>(static_cast<unsigned long long*>(c.p.out[1 + slot]) - 1, 0, 0, grp, v);
       break;
 #undef AGG_ANY_CASE
   }
@@ -594,6 +601,41 @@ __device__ __forceinline__ void set_group(const Ctx& c, const long long (&x)[R],
       }
       grp[r] = sl;
     }
+  } else if constexpr (MODE == MODE_RUNS) {
+    // Sorted key column (the host checked): a row's group is the number of runs that started at or before it, minus one.
+    // Runs before the tile come from a prefix sum over per-tile counts (run_heads_kernel in scan.cu), runs before the
+    // lane from a warp scan; a row starts a run when its key differs from the previous ROW's, which for a lane's first
+    // row is the previous lane's last (a shuffle) and for the tile's first row the column element before the tile.
+    constexpr int WT = 32 * R;
+    const uint64_t row0 = c.tile * WT + static_cast<uint64_t>(c.lane) * R;
+    long long prev = __shfl_up_sync(0xffffffffu, x[R - 1], 1);
+    if (c.lane == 0 && row0 > 0) {
+      const StagedCol& kc = c.p.staged[c.p.run_key_col];
+      const unsigned char* e = kc.base + (row0 - 1) * kc.width;
+      switch (kc.phys) {
+        case MSC_P_U8: prev = *e; break;
+        case MSC_P_U16: prev = *reinterpret_cast<const uint16_t*>(e); break;
+        case MSC_P_U32: prev = *reinterpret_cast<const uint32_t*>(e); break;
+        case MSC_P_I32: prev = *reinterpret_cast<const int*>(e); break;
+        default: prev = *reinterpret_cast<const long long*>(e); break;
+      }
+    }
+    bool head[R];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool valid = (vmask >> r) & 1u;
+      head[r] = valid && (row0 + r == 0 || x[r] != (r > 0 ? x[r > 0 ? r - 1 : 0] : prev));
+      mine += head[r];
+    }
+    uint32_t total;
+    uint64_t run = c.p.tile_offsets[c.tile] + warp_exclusive_scan(mine, c.lane, &total);  // runs started before this lane's rows
+    long long* out_key = static_cast<long long*>(c.p.out[0]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (head[r]) out_key[run++] = x[r];
+      grp[r] = ((vmask >> r) & 1u) ? static_cast<int>(run) - 1 : -1;  // the run this row belongs to
+    }
   }
 }
 
@@ -641,6 +683,8 @@ template <int R, int MODE, int KIND>
 __device__ __forceinline__ void fast_agg(const Ctx& c, int slot, const int (&grp)[R], const long long (&v)[R]) {
   if constexpr (MODE == MODE_DENSE) agg_dense_k<R, KIND>(c, slot, grp, v);
   else if constexpr (MODE == MODE_HASH) agg_hash<R, KIND>(c.p.htbl, c.p.hshift, slot, grp, v);
+  // a run's accumulator is element [run] of its output column: agg_hash with one-word slots and no key word
+  else if constexpr (MODE == MODE_RUNS) agg_hash<R, KIND>(static_cast<unsigned long long*>(c.p.out[1 + slot]) - 1, 0, 0, grp, v);
 }
 
 // dst <- A (+|-|*) B on f64; DK: 0 TEMP, 1 AGG(SUM_F), 2 AGG(SUM_F) + tee TEMP
@@ -723,7 +767,7 @@ __host__ __device__ constexpr bool out_valid(int fk, int u32) {
 template <int R, int MODE>
 __device__ __forceinline__ bool run_fast(const Ctx& c, int fast, uint32_t w0, uint32_t w1, uint32_t& vmask, int (&grp)[R],
                                          uint64_t out_pos) {
-  constexpr bool AGG = MODE == MODE_DENSE || MODE == MODE_HASH;
+  constexpr bool AGG = MODE == MODE_DENSE || MODE == MODE_HASH || MODE == MODE_RUNS;
   switch (fast) {
 #define ARITH_CASE(OPI, AK, BK, DK)                                                      \
   case MSC_FAST_ARITH + (((OPI) * 5 + (AK)) * 5 + (BK)) * 3 + (DK):                      \
@@ -858,7 +902,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
 #pragma unroll
     for (int r = 0; r < R; ++r) grp[r] = (MODE == MODE_DENSE) ? p.ngroups : -1;
     uint64_t out_pos = row0;  // project: output position of this lane's first surviving row
-    const Ctx c{p, sbase, temps, acc, lane, tid};
+    const Ctx c{p, sbase, temps, acc, lane, tid, tile};
 
     for (int pc = 0;; pc += 2) {
       const uint32_t w0 = p.code[pc];
