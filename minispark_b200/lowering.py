@@ -344,14 +344,59 @@ def identity_select(node: LNode) -> LSelect:
     return LSelect(list(node.schema), node, [], [EInput(_FROM_COLUMN_TYPE[t], i) for i, (_, t) in enumerate(node.schema)])
 
 
+_MAY_RAISE = {"truediv", "floordiv", "mod"}  # ZeroDivisionError in the reference (sql.py:262-266)
+
+
+def _cannot_raise(e: Expr) -> bool:
+    if isinstance(e, EBin) and e.op in _MAY_RAISE:
+        return False
+    return all(_cannot_raise(c) for c in expr_children(e))
+
+
+def push_filters_below_join(filters: Sequence[Expr], join: "LJoin") -> tuple[list[Expr], "LJoin"]:
+    """Predicate pushdown through an (inner) join: a conjunct that reads columns of one side only filters that side
+    BEFORE the join.  The reference filters after it (`FilterTask` above `BroadcastHashJoinTask`), which gives the same
+    rows for an inner join; here it decides whether sf10 builds on 15 M orders and probes 60 M lineitems or on the 2.3 M
+    and 17 M that pass `o_orderdate BETWEEN ..` / `l_shipmode LIKE ..`.  Conjuncts that could raise (division, modulo)
+    stay above the join, so a row the join would have dropped can never report a division by zero."""
+    nl = len(join.left.schema)
+    left_f: list[Expr] = []
+    right_f: list[Expr] = []
+    keep: list[Expr] = []
+    for conjunct in split_conjunctions(filters):
+        ins = expr_inputs(conjunct)
+        if ins and _cannot_raise(conjunct) and all(i < nl for i in ins):
+            left_f.append(conjunct)
+        elif ins and _cannot_raise(conjunct) and all(i >= nl for i in ins):
+            right_f.append(remap(conjunct, {i: i - nl for i in ins}))
+        else:
+            keep.append(conjunct)
+    if not left_f and not right_f:
+        return list(filters), join
+
+    def filtered(side: LNode, extra: list[Expr]) -> LNode:
+        if not extra:
+            return side
+        sel = identity_select(side)
+        sel.filters = extra
+        return fuse_selects(sel)
+
+    return keep, LJoin(join.schema, filtered(join.left, left_f), filtered(join.right, right_f), join.left_key, join.right_key)
+
+
 def fuse_selects(node: LNode) -> LNode:
-    """Merge stacked LSelects bottom-up by inlining the inner projection into the outer one."""
+    """Merge stacked LSelects bottom-up by inlining the inner projection into the outer one; filters above a join move
+    below it where they can (push_filters_below_join)."""
     if isinstance(node, LSelect):
         child = fuse_selects(node.child)
         if isinstance(child, LSelect):
             filters = list(child.filters) + [substitute(f, child.outputs) for f in node.filters]
             outputs = [substitute(o, child.outputs) for o in node.outputs]
-            return LSelect(node.schema, child.child, filters, outputs)
+            node = LSelect(node.schema, child.child, filters, outputs)
+            child = node.child
+        if isinstance(child, LJoin) and node.filters and os.environ.get("MINISPARK_JOIN_PUSHDOWN", "1") != "0":
+            filters, child = push_filters_below_join(node.filters, child)
+            return LSelect(node.schema, child, filters, node.outputs)
         return LSelect(node.schema, child, node.filters, node.outputs)
     if isinstance(node, LAggregate):
         return LAggregate(node.schema, fuse_selects(node.child), node.group, node.aggs)

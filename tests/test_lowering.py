@@ -112,3 +112,33 @@ def test_q1_regvm_program_uses_the_fused_forms(tmp_path):
     for word, line in zip(prog.program.regvm, rv):
         name, a1, a2 = line.split()
         assert word == N.RV[name] | (int(a1) << 8) | (int(a2) << 16)
+
+
+def _lower_sql(sql: str):
+    task = deepcopy(parse_sql(sql).task)
+    task.validate_schema()
+    return L.lower_task(task)
+
+
+def test_filters_move_below_an_inner_join(tmp_path):
+    """One-sided conjuncts of a WHERE above a join filter that side BEFORE the join (the reference filters after it,
+    tasks.py:167-177 above :201-240; same rows for an inner join, a much smaller build / probe)."""
+    paths = cases.write_tables(tmp_path)
+    plan = _lower_sql("SELECT u.first_name, o.product, o.price FROM '{users}' AS u JOIN '{orders}' AS o ON u.user_id=o.user_id "
+                      "WHERE (o.price > 100) AND (o.quantity < u.age);".format(**paths))
+    assert isinstance(plan, L.LSelect) and isinstance(plan.child, L.LJoin)
+    join = plan.child
+    assert isinstance(join.left, L.LTable)                                   # nothing to push to the users side
+    assert isinstance(join.right, L.LSelect) and len(join.right.filters) == 1  # price > 100 runs on orders alone
+    assert len(plan.filters) == 1                                            # quantity < age needs both sides: stays above
+    nl = len(join.left.schema)
+    ins = L.expr_inputs(plan.filters[0])
+    assert any(i < nl for i in ins) and any(i >= nl for i in ins)
+
+
+def test_a_filter_that_could_raise_stays_above_the_join(tmp_path):
+    paths = cases.write_tables(tmp_path)
+    plan = _lower_sql("SELECT u.first_name, o.product FROM '{users}' AS u JOIN '{orders}' AS o ON u.user_id=o.user_id "
+                      "WHERE 100 / o.quantity > 20;".format(**paths))
+    join = plan.child
+    assert isinstance(join, L.LJoin) and isinstance(join.right, L.LTable) and len(plan.filters) == 1
