@@ -1152,8 +1152,8 @@ bool jit_project_cached(msc_ctx* ctx, const msc_scan_desc* sd, const int32_t* ou
   return shapes().count(project_key(ctx, sd, false, out_phys, nout)) != 0;
 }
 
-int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, uint32_t* tile_counts,
-                       const uint64_t* tile_offsets, void* const* outs, bool timed) {
+namespace {
+int project_kernel(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, Kernel** out) {
   const std::string skey = project_key(ctx, sd, count_only, out_phys, nout);
   auto sit = shapes().find(skey);
   if (sit == shapes().end()) {
@@ -1164,7 +1164,22 @@ int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, c
     MSC_TRY(load_kernel(ctx, source, "msc_jit_scan", 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes, &k));
     sit = shapes().emplace(skey, ShapeEntry{k, false}).first;
   }
-  Kernel& k = *sit->second.kernel;
+  *out = sit->second.kernel;
+  return MSC_OK;
+}
+}  // namespace
+
+int jit_project_compile(msc_ctx* ctx, const msc_scan_desc* sd, bool with_count_pass, const int32_t* out_phys, int nout) {
+  Kernel* k = nullptr;
+  if (with_count_pass) MSC_TRY(project_kernel(ctx, sd, true, out_phys, nout, &k));
+  return project_kernel(ctx, sd, false, out_phys, nout, &k);
+}
+
+int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, uint32_t* tile_counts,
+                       const uint64_t* tile_offsets, void* const* outs, bool timed) {
+  Kernel* kp = nullptr;
+  MSC_TRY(project_kernel(ctx, sd, count_only, out_phys, nout, &kp));
+  Kernel& k = *kp;
   if (sd->nrows == 0) return MSC_OK;
   JitParams p;
   MSC_TRY(fill_params(ctx, sd, &p));

@@ -48,6 +48,8 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
 // tile_offsets[tile] + rank for filtered scans (stable) or at the row number for unfiltered ones
 int jit_project_source(const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, std::string* source, std::string* err);
 bool jit_project_cached(msc_ctx* ctx, const msc_scan_desc* sd, const int32_t* out_phys, int nout);
+// compile (or find) both passes' kernels without launching: lets the caller fall back to the interpreter as a whole
+int jit_project_compile(msc_ctx* ctx, const msc_scan_desc* sd, bool with_count_pass, const int32_t* out_phys, int nout);
 int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, uint32_t* tile_counts,
                        const uint64_t* tile_offsets, void* const* outs, bool timed);
 

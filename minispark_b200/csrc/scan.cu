@@ -688,7 +688,16 @@ int dense_scan_into(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, const in
     *was_masked = allow_masked && masked_enabled;
     dense_init_kernel<<<1, 256, 0, ctx->stream>>>(table, ngroups, ntot, dense_meta(dp));
     ctx->stats.launches += 1;
-    return jit_dense_launch(ctx, sd, ngroups, naggs, ntot, dp.kinds, dp.init, table, true, was_masked);
+    const int jrc = jit_dense_launch(ctx, sd, ngroups, naggs, ntot, dp.kinds, dp.init, table, true, was_masked);
+    // No compiler on this machine, or a program the generator declines: the interpreters below run the scan instead
+    // (still on the GPU -- there is no CPU path); anything else is a real error.
+    if (!(jrc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) && !(jrc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0)) return jrc;
+    static bool warned = false;
+    if (!warned) {
+      fprintf(stderr, "minispark_cuda: scan not specialised (%s); using the interpreter kernels\n", ctx->err.c_str());
+      warned = true;
+    }
+    *was_masked = false;
   }
   LaunchPlan lp;
   RegvmProgram rv;
@@ -1015,7 +1024,8 @@ int dense_fused_impl(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, c
   rc = jit_dense_launch(ctx, scan, ngroups, naggs, dp.stride, dp.kinds, dp.init, static_cast<unsigned long long*>(table), true, &masked, &fin);
   if (rc != MSC_OK) {
     msc_rel_free(rel);
-    return rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0 ? MSC_OK : rc;  // the generator declined: not an error, just not fused
+    // the generator declined, or there is no compiler on this machine: not an error, just not fused
+    return (rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) || (rc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0) ? MSC_OK : rc;
   }
   if (compile_only) {  // the kernel exists now; hand back an empty relation as the "yes"
     rel->nrows = 0;
@@ -1346,8 +1356,15 @@ extern "C" int msc_scan_project(msc_ctx* ctx, const msc_scan_desc* sd, const int
   if (!pending) MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));  // a pending chain keeps the first call's start mark
   // specialised kernels (jit.cu) for both passes, or the interpreter for both: the two paths tile the rows differently
   static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
-  const bool use_jit = jit_mode > 0 && sd->nstaged >= 1 && sd->nrows > 0 && nout > 0 &&
-                       (sd->want_jit != 0 || jit_mode > 1 || jit_project_cached(ctx, sd, out_phys, nout));
+  bool use_jit = jit_mode > 0 && sd->nstaged >= 1 && sd->nrows > 0 && nout > 0 &&
+                 (sd->want_jit != 0 || jit_mode > 1 || jit_project_cached(ctx, sd, out_phys, nout));
+  if (use_jit) {  // both passes or none: no compiler here, or a program the generator declines -> the interpreter runs the scan
+    const int jrc = jit_project_compile(ctx, sd, has_filter, out_phys, nout);
+    if (jrc != MSC_OK) {
+      if (!(jrc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) && !(jrc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0)) return jrc;
+      use_jit = false;
+    }
+  }
   LaunchPlan lp;
   MSC_TRY(plan_launch(ctx, sd, R, 0, &lp));
   if (use_jit) lp.p.ntiles = static_cast<uint32_t>((sd->nrows + 255) / 256);
