@@ -113,6 +113,36 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NumaLocal:
+    """Run a block on the CPUs next to GPU `index` (NVML's ideal affinity), so that memory first touched inside it --
+    the pinned BlockFile image -- lands on the GPU's NUMA node; the previous affinity comes back afterwards (the CPU
+    baseline must see all host cores).  With eight ranks reading their images from one socket's memory the host side
+    of the PCIe copies, not the links, set the e2e rate."""
+
+    def __init__(self, index: int) -> None:
+        self.index, self.old, self.cpus = index, None, None
+
+    def __enter__(self) -> "NumaLocal":
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            old = os.sched_getaffinity(0)
+            if cpus & old and (cpus & old) != old:
+                os.sched_setaffinity(0, cpus & old)
+                self.old, self.cpus = old, sorted(cpus & old)
+        except Exception:  # noqa: BLE001  (no NVML, no permission: keep the default placement)
+            self.old = None
+        return self
+
+    def __exit__(self, *exc) -> None:  # noqa: ANN002
+        if self.old is not None:
+            os.sched_setaffinity(0, self.old)
+
+
 def captured_traffic(sf: float, layout: str, rows: int, bytes_per_row: int, kernel: str) -> tuple[float | None, str | None]:
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very workload and kernel (profiles/)."""
     path = ROOT / "profiles" / "r01_traffic.json"
@@ -262,10 +292,11 @@ def cuda_arm(args: argparse.Namespace) -> None:
         # BlockFile image in pinned host memory: the "host buffers" of the e2e measurement
         nbytes = path.stat().st_size
         pinned = C.c_void_p()
-        engine.ctx.call("msc_host_alloc", nbytes, C.byref(pinned))
-        view = (C.c_char * nbytes).from_address(pinned.value)
-        with open(path, "rb") as f:
-            got = f.readinto(view)
+        with NumaLocal(local_rank) as numa:  # the image's pages belong on the NUMA node this GPU hangs off
+            engine.ctx.call("msc_host_alloc", nbytes, C.byref(pinned))
+            view = (C.c_char * nbytes).from_address(pinned.value)
+            with open(path, "rb") as f:
+                got = f.readinto(view)
         assert got == nbytes
         engine.register_table_image(str(path), pinned.value, nbytes)
 
@@ -397,7 +428,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
                         "passes_ms": [round(1e3 * t, 2) for t in e2e_times], "statistic": "median of the passes (wall clock, rank-local)"},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "clocks": clocks.summary(),
-                "setup": {"generate_s": gen_s},
+                "setup": {"generate_s": gen_s, "pinned_image_numa_cpus": (f"{numa.cpus[0]}-{numa.cpus[-1]} ({len(numa.cpus)} CPUs next to the GPU)"
+                                                                          if numa.cpus else "default placement")},
             }
             print(json.dumps(line))
         engine.ctx.call("msc_host_free", pinned)
