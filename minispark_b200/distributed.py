@@ -39,6 +39,21 @@ def unify_keys(per_rank_keys: Sequence[Sequence[str]]) -> tuple[list[str], list[
     return universe, [[index[k] for k in keys] for keys in per_rank_keys]
 
 
+def invert_code_maps(maps: Sequence[Sequence[int]], width: int = 32) -> list[int]:
+    """For the in-kernel merge of partial aggregate tables (msc_dense_fused_peer): ``maps[r][g]`` is the merged group of
+    rank r's local group g (unify_keys); the kernel wants the opposite direction as a flat [world][width] table --
+    entry r * width + G = rank r's local group of merged group G, or -1 when rank r never saw it."""
+    inv = [-1] * (len(maps) * width)
+    for r, m in enumerate(maps):
+        for g, merged in enumerate(m):
+            if merged < 0:
+                continue
+            if merged >= width:
+                raise ValueError(f"merged group {merged} does not fit the {width}-wide exchange table")
+            inv[r * width + merged] = g
+    return inv
+
+
 def exchange_plan(counts_matrix: Sequence[Sequence[int]], rank: int) -> tuple[list[int], list[int]]:
     """(send_counts, recv_counts) of ``rank`` given counts_matrix[src][dst] rows routed src -> dst."""
     world = len(counts_matrix)

@@ -31,7 +31,7 @@ from typing import TYPE_CHECKING, Any, Iterable, Optional
 
 from . import lowering as L
 from . import native as N
-from .distributed import Comm, unify_keys
+from .distributed import Comm, invert_code_maps, unify_keys
 from .constants import ColumnType, Row, Schema
 from .io import BlockFile
 from .jobs import JobResult, OutputFile
@@ -1038,12 +1038,7 @@ class _PeerExchange:
                 able = False
         else:
             able = False
-        inv = [-1] * (world * 32)
-        for r in range(world):
-            for g in range(m.gmax):
-                dst = m.perm[r * m.gmax + g]
-                if 0 <= dst < 32:
-                    inv[r * 32 + dst] = g
+        inv = invert_code_maps([[m.perm[r * m.gmax + g] for g in range(m.gmax)] for r in range(world)]) if able else [-1] * (world * 32)
         self.inv_dev = torch.tensor(inv, dtype=torch.int32, device=torch.device("cuda", e.device))
         spec.inv = self.inv_dev.data_ptr()
         spec.rank, spec.world, spec.nlocal, spec.gmax, spec.nglobal = rank, world, m.nlocal, m.gmax, m.nglobal

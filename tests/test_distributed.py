@@ -69,3 +69,22 @@ def _worker(rank: int, world: int, port: int) -> None:
 
 def test_comm_world_size_2_gloo():
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_invert_code_maps_for_the_in_kernel_merge():
+    """Host side of msc_dense_fused_peer: per-rank local -> merged code maps, inverted into the [world][32] table the
+    scan kernel's last CTA indexes by merged group."""
+    from minispark_b200.distributed import invert_code_maps, unify_keys
+
+    universe, maps = unify_keys([["A", "N"], ["N", "R"], []])
+    assert universe == ["A", "N", "R"] and maps == [[0, 1], [1, 2], []]
+    padded = [m + [-1] * (2 - len(m)) for m in maps]         # every rank's slot has room for gmax = 2 groups
+    inv = invert_code_maps(padded)
+    assert len(inv) == 3 * 32
+    assert inv[0:3] == [0, 1, -1]                               # rank 0: A -> local 0, N -> local 1, no R
+    assert inv[32:35] == [-1, 0, 1]                             # rank 1: no A, N -> local 0, R -> local 1
+    assert inv[64:67] == [-1, -1, -1]                           # rank 2 holds no group at all
+    import pytest
+
+    with pytest.raises(ValueError):
+        invert_code_maps([[40]])
