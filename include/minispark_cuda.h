@@ -389,6 +389,19 @@ typedef struct msc_peer_spec {
 MSC_API int msc_dense_fused_peer(msc_ctx* ctx, const msc_scan_desc* scan, const int32_t* agg_kinds, int32_t naggs, void* table, int32_t flags,
                          const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
                          const msc_peer_spec* peer, msc_rel** final_rel, int32_t* nonfinite);
+/* ---- prepared dense aggregate ---------------------------------------------------------------------------------------
+ * msc_dense_fused / msc_dense_fused_peer with everything that does not change between passes done once: programs
+ * validated and copied, accumulator table and result relation allocated, kernel compiled.  A pass is then ONE kernel
+ * launch (the kernel's finish leaves the table's identities behind for the next pass), one 24-byte read and one host
+ * wait.  *out == NULL with MSC_OK: this query cannot be fused (see msc_dense_fused).  The result relation handed out by
+ * msc_prepared_run belongs to the prepared object and is overwritten by the next pass; `peer` may be NULL (one GPU),
+ * `epoch` is ignored then. */
+typedef struct msc_prepared msc_prepared;
+MSC_API int msc_prepared_create(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs,
+                        const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                        const msc_peer_spec* peer, msc_prepared** out);
+MSC_API int msc_prepared_run(msc_prepared* p, int32_t flags, uint64_t epoch, msc_rel** result, uint64_t* nrows, int32_t* nonfinite);
+MSC_API void msc_prepared_free(msc_prepared* p);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,
                       int32_t naggs, int32_t count_slot, msc_rel** out);

@@ -721,6 +721,10 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     i64 a[STRIDE];
 #pragma unroll
     for (int s = 0; s < STRIDE; ++s) a[s] = static_cast<i64>(__ldcg(cell + s));
+    if (in_range) {  // leave the identities behind: the next pass of a prepared query needs no initialisation launch
+#pragma unroll
+      for (int s = 0; s < STRIDE; ++s) p.dense_out[g * STRIDE + s] = static_cast<u64>(INIT[s]);
+    }
 )";
     } else {
       // the exchange, inside the same kernel: push this rank's table into every rank's mailbox (peer stores over NVLink),
@@ -731,6 +735,8 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       u64* dst = p.mailbox[peer] + slot_off + static_cast<u64>(p.rank) * p.slot_cells;
       for (int i = lane; i < p.nlocal * STRIDE; i += 32) dst[i] = __ldcg(p.dense_out + i);
     }
+    __syncwarp();
+    for (int i = lane; i < p.nlocal * STRIDE; i += 32) p.dense_out[i] = static_cast<u64>(INIT[i % STRIDE]);  // identities for the next pass
     __threadfence_system();
     __syncwarp();
     if (lane < p.world) st_release_sys(p.mailbox[lane] + flag_off + p.rank, p.epoch);

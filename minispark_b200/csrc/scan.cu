@@ -5,6 +5,7 @@
 #define MSCAN_DECL_ONLY  // the kernel is instantiated in scan_inst_*.cu
 #include <algorithm>
 #include <chrono>
+#include <memory>
 
 #include "jit.h"
 #include "scan_kernel.cuh"
@@ -1060,6 +1061,130 @@ extern "C" int msc_dense_fused_peer(msc_ctx* ctx, const msc_scan_desc* scan, con
                                     const msc_peer_spec* peer, msc_rel** final_out, int32_t* nonfinite) {
   if (!peer) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   return dense_fused_impl(ctx, scan, peer->nlocal, agg_kinds, naggs, table, flags, final_scan, final_cols, out_phys, nout, peer, final_out, nonfinite);
+}
+
+// ---- prepared dense aggregate: everything a pass needs, decided and allocated once --------------------------------
+struct msc_prepared {
+  msc_ctx* ctx = nullptr;
+  msc_scan_desc scan, fin;
+  int ngroups = 0, naggs = 0, nout = 0;
+  int32_t kinds[MSC_VM_MAX_AGGS + 1], out_phys[MSC_VM_MAX_OUT], fin_cols[MSC_VM_MAX_STAGED];
+  DensePlan dp;
+  unsigned long long* table = nullptr;  // [ngroups][stride]; holds the identities between passes (the finish resets it)
+  size_t table_bytes = 0;
+  msc_rel* result = nullptr;            // its columns are rewritten by every pass
+  bool table_clean = false;
+  bool has_peer = false;
+  msc_peer_spec peer;
+};
+
+extern "C" int msc_prepared_create(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs,
+                                   const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
+                                   const msc_peer_spec* peer, msc_prepared** out) {
+  if (!ctx || !scan || !agg_kinds || !final_scan || !final_cols || !out_phys || !out || ngroups <= 0 || naggs < 0 || naggs > MSC_VM_MAX_AGGS ||
+      nout <= 0 || nout > MSC_VM_MAX_OUT)
+    return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  *out = nullptr;
+  static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
+  const int out_groups = peer ? peer->nglobal : ngroups;
+  if (jit_mode == 0 || ngroups > 32 || out_groups > 32 || out_groups <= 0 || (!peer && scan->nrows == 0)) return MSC_OK;
+  if (peer && (peer->world < 1 || peer->world > MSC_PEER_MAX_WORLD || peer->rank < 0 || peer->rank >= peer->world || peer->nlocal != ngroups ||
+               peer->gmax < ngroups || !peer->inv))
+    return ctx->fail(MSC_ERR_ARG, "bad peer specification");
+  MSC_TRY(validate_program(ctx, scan, MODE_DENSE, agg_kinds, naggs, nullptr, 0));
+  MSC_TRY(validate_program(ctx, final_scan, MODE_PROJECT, nullptr, 0, out_phys, nout));
+  auto p = std::make_unique<msc_prepared>();
+  p->ctx = ctx;
+  p->scan = *scan;
+  p->fin = *final_scan;
+  p->ngroups = ngroups;
+  p->naggs = naggs;
+  p->nout = nout;
+  memcpy(p->kinds, agg_kinds, sizeof(int32_t) * naggs);
+  memcpy(p->out_phys, out_phys, sizeof(int32_t) * nout);
+  memcpy(p->fin_cols, final_cols, sizeof(int32_t) * final_scan->nstaged);
+  MSC_TRY(dense_plan(ctx, scan, agg_kinds, naggs, &p->dp));
+  if (!jit_dense_supported(scan, ngroups, p->dp.stride)) return MSC_OK;
+  if (peer) {
+    p->has_peer = true;
+    p->peer = *peer;
+  }
+  if (!ctx->d_ticket) {
+    MSC_TRY(msc_alloc(ctx, sizeof(uint32_t), reinterpret_cast<void**>(&ctx->d_ticket)));
+    MSC_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), ctx->stream));
+  }
+  // compile both variants' worth lazily: the masked one now (the common case), the exact one if a pass ever needs it
+  msc_rel* rel = new_rel(ctx, static_cast<uint64_t>(out_groups));
+  int rc = add_cols(ctx, rel, out_phys, nout, static_cast<uint64_t>(out_groups));
+  if (rc == MSC_OK) rc = msc_alloc(ctx, 3 * sizeof(unsigned long long), reinterpret_cast<void**>(&rel->d_meta));
+  p->table_bytes = sizeof(unsigned long long) * ngroups * p->dp.stride;
+  if (rc == MSC_OK) rc = msc_alloc(ctx, p->table_bytes, reinterpret_cast<void**>(&p->table));
+  if (rc != MSC_OK) {
+    msc_rel_free(rel);
+    return rc;
+  }
+  p->result = rel;
+  void* outs[MSC_VM_MAX_OUT];
+  for (int i = 0; i < nout; ++i) outs[i] = rel->cols[i].data;
+  msc_peer_spec probe;
+  memset(&probe, 0, sizeof(probe));
+  if (peer) probe = *peer;
+  probe.compile_only = 1;
+  JitFinish fin{&p->fin, p->fin_cols, p->out_phys, nout, p->dp.count_slot, outs, rel->d_meta, ctx->d_ticket, &probe};
+  static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
+  bool masked = masked_enabled;
+  if (!peer) fin.peer = nullptr;
+  if (peer) {
+    rc = jit_dense_launch(ctx, scan, ngroups, naggs, p->dp.stride, p->dp.kinds, p->dp.init, p->table, false, &masked, &fin);
+  } else {
+    // (no compile-only switch without a peer spec: generating the source and loading the kernel is what the first launch does,
+    // so let the first pass pay it -- but find out now whether the generator accepts the pair of programs)
+    std::string source, err;
+    rc = jit_dense_source(scan, ngroups, naggs, p->dp.stride, p->dp.kinds, p->dp.init, masked, &source, &err, &fin);
+    if (rc != MSC_OK) rc = ctx->fail(MSC_ERR_ARG, "jit: " + err);
+  }
+  if (rc != MSC_OK) {
+    const bool declined = (rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) || (rc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0);
+    msc_rel_free(rel);
+    msc_free(ctx, p->table, p->table_bytes);
+    return declined ? MSC_OK : rc;
+  }
+  *out = p.release();
+  return MSC_OK;
+}
+
+extern "C" int msc_prepared_run(msc_prepared* p, int32_t flags, uint64_t epoch, msc_rel** result, uint64_t* nrows, int32_t* nonfinite) {
+  if (!p || !result || !nrows || !nonfinite) return MSC_ERR_ARG;
+  msc_ctx* ctx = p->ctx;
+  static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
+  msc_rel* rel = p->result;
+  void* outs[MSC_VM_MAX_OUT];
+  for (int i = 0; i < p->nout; ++i) outs[i] = rel->cols[i].data;
+  p->peer.epoch = epoch;
+  p->peer.compile_only = 0;
+  JitFinish fin{&p->fin, p->fin_cols, p->out_phys, p->nout, p->dp.count_slot, outs, rel->d_meta, ctx->d_ticket, p->has_peer ? &p->peer : nullptr};
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  if (!p->table_clean) {
+    dense_init_kernel<<<1, 256, 0, ctx->stream>>>(p->table, p->ngroups, p->dp.stride, dense_meta(p->dp));
+    ctx->stats.launches += 1;
+  }
+  p->table_clean = false;
+  bool masked = !(flags & MSC_DENSE_EXACT) && masked_enabled;
+  MSC_TRY(jit_dense_launch(ctx, &p->scan, p->ngroups, p->naggs, p->dp.stride, p->dp.kinds, p->dp.init, p->table, true, &masked, &fin));
+  rel->pending = true;
+  msc_rel* rels[1] = {rel};
+  MSC_TRY(msc_rel_settle(ctx, rels, 1, nonfinite));
+  p->table_clean = true;  // the finish left the identities behind
+  *result = rel;
+  *nrows = rel->nrows;
+  return MSC_OK;
+}
+
+extern "C" void msc_prepared_free(msc_prepared* p) {
+  if (!p) return;
+  if (p->result) msc_rel_free(p->result);
+  if (p->table) msc_free(p->ctx, p->table, p->table_bytes);
+  delete p;
 }
 
 extern "C" int msc_jit_dense_source(const msc_scan_desc* sd, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked, char* buf,

@@ -989,6 +989,42 @@ class _DenseMerge:
         return handle, e.ctx.stats().last_kernel_ms
 
 
+class _PreparedPass:
+    """A library-side prepared dense aggregate (msc_prepared_*): one kernel launch and one host wait per pass.  The
+    result relation belongs to the library object and is overwritten by the next pass."""
+
+    def __init__(self, engine: "CudaExecutionEngine", handle: int, out_types: list[str], out_dicts: list) -> None:
+        self.engine, self.handle = engine, handle
+        self.out_types, self.out_dicts = out_types, out_dicts
+        self.cols: Optional[list[DeviceColumn]] = None
+        engine._closers.append(self.close)
+
+    def close(self) -> None:
+        e = self.engine
+        if self.handle and getattr(e, "ctx", None) is not None:
+            e.ctx.lib.msc_prepared_free(C.c_void_p(self.handle))
+        self.handle = 0
+
+    def run(self, epoch: int, bump: Any = None) -> DeviceRel:
+        """One pass; repeats it with the exact kernel when the masked one met a non-finite value.  `bump` supplies the
+        next epoch for such a repeat (every rank repeats: the merged sums are identical everywhere)."""
+        e = self.engine
+        res, nrows, nonfinite = C.c_void_p(), C.c_uint64(), C.c_int32()
+        for exact in (False, True):
+            flags = N.K["MSC_DENSE_EXACT"] if exact else 0
+            e.ctx.check(e.ctx.lib.msc_prepared_run(C.c_void_p(self.handle), flags, epoch, C.byref(res), C.byref(nrows), C.byref(nonfinite)))
+            if not nonfinite.value or exact:
+                break
+            if bump is not None:
+                epoch = bump()
+        if self.cols is None:
+            n = len(self.out_types)
+            binds = (N.ColBind * n)()
+            e.ctx.check(e.ctx.lib.msc_rel_cols(res, binds, n))
+            self.cols = [DeviceColumn(binds[i].data or 0, binds[i].phys, self.out_types[i], self.out_dicts[i]) for i in range(n)]
+        return DeviceRel(e.ctx, None, nrows.value, self.cols)
+
+
 class _PeerExchange:
     """Cross-rank merge of a prepared dense aggregate INSIDE the scan kernel, over NVLink peer memory.
 
@@ -1045,22 +1081,22 @@ class _PeerExchange:
         self.spec = spec
         self.epoch = 0
         self.prepared = prepared
+        self.pass_ = None
         if able:  # compile now, so that no rank waits in the kernel for a peer that is still in NVRTC (or gave up)
-            spec.compile_only = 1
-            fin, nonfinite = C.c_void_p(), C.c_int32()
+            handle = C.c_void_p()
             try:
-                e.ctx.call("msc_dense_fused_peer", C.byref(prepared.desc), prepared.kinds, len(prepared.prog.agg_kinds), C.c_void_p(m.local.data_ptr()),
-                           N.K["MSC_DENSE_JIT"], C.byref(desc2), self.raw_cols, self.out_phys, self.nout, C.byref(spec), C.byref(fin),
-                           C.byref(nonfinite))
-                able = bool(fin.value)
-                if fin.value:
-                    e.ctx.lib.msc_rel_free(fin)
+                e.ctx.call("msc_prepared_create", C.byref(prepared.desc), m.nlocal, prepared.kinds, len(prepared.prog.agg_kinds), C.byref(desc2),
+                           self.raw_cols, self.out_phys, self.nout, C.byref(spec), C.byref(handle))
+                able = bool(handle.value)
+                if handle.value:
+                    self.pass_ = _PreparedPass(e, handle.value, self.out_types, prog2.out_dicts)
             except N.NativeError:
                 able = False
-            spec.compile_only = 0
         self.ok = all(comm.all_gather_object(able))
         e._closers.append(self.close)
         if not self.ok:
+            if self.pass_ is not None:
+                self.pass_.close()
             self.close()
 
     def close(self) -> None:
@@ -1074,22 +1110,13 @@ class _PeerExchange:
             e.ctx.lib.msc_peer_free(e.ctx.handle, self.own)
             self.own = C.c_void_p()
 
-    def run(self) -> int:
-        """One pass on this rank (every rank must call it); returns the handle of the final relation."""
-        e, p, m = self.engine, self.prepared, self.prepared.merge
-        fin, nonfinite = C.c_void_p(), C.c_int32()
-        for exact in (False, True):
-            self.epoch += 1
-            self.spec.epoch = self.epoch
-            flags = N.K["MSC_DENSE_JIT"] | (N.K["MSC_DENSE_EXACT"] if exact else 0)
-            e.ctx.call("msc_dense_fused_peer", C.byref(p.desc), p.kinds, len(p.prog.agg_kinds), C.c_void_p(m.local.data_ptr()), flags,
-                       C.byref(self.desc2), self.raw_cols, self.out_phys, self.nout, C.byref(self.spec), C.byref(fin), C.byref(nonfinite))
-            if not fin.value:
-                raise ExecutionError("fused cross-rank aggregate unavailable after it was set up")
-            if not nonfinite.value or exact:  # (the merged sums are identical on all ranks, so all ranks repeat together)
-                break
-            e.ctx.lib.msc_rel_free(fin)
-        return fin.value
+    def _next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def run(self) -> DeviceRel:
+        """One pass on this rank (every rank must call it); returns the final relation (owned by the library object)."""
+        return self.pass_.run(self._next_epoch(), self._next_epoch)
 
 
 class PreparedAggregate:
@@ -1134,6 +1161,7 @@ class PreparedAggregate:
         self._final: Optional[tuple] = None  # compiled final projection, re-bound to every pass's aggregate result
         self._chain_args: Optional[tuple] = None
         self._fusable = True  # until msc_dense_fused says otherwise
+        self._prep: Any = None  # _PreparedPass (msc_prepared_*) once created, False when this query cannot use it
         self._peer: Any = None  # _PeerExchange once set up, False when unavailable
 
     def run(self) -> tuple[DeviceRel, float]:
@@ -1153,12 +1181,11 @@ class PreparedAggregate:
             if self._peer is None:  # collective: every rank gets here on its second pass
                 self._peer = _PeerExchange(self) if os.environ.get("MINISPARK_PEER_MERGE", "1") != "0" else False
             if self._peer and self._peer.ok:
-                handle = self._peer.run()
+                final = self._peer.run()
                 st = e.ctx.stats()
                 self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
                                    "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread, "kind": st.last_scan_kind,
                                    "regs": st.last_scan_regs, "exchange": "nvlink peer stores inside the scan kernel"}
-                final = e._track(DeviceRel.from_handle(e.ctx, handle, self._peer.out_types, self._peer.prog2.out_dicts))
                 return final, st.last_kernel_ms
         for exact in (False, True):
             if self.merge is not None:
@@ -1209,6 +1236,21 @@ class PreparedAggregate:
             self._chain_args = (N.int32_array(raw_cols), N.int32_array(prog2.out_phys), len(prog2.out_phys),
                                 [x.type for x in self.plan.outputs])
         raw_cols, out_phys, nout, out_types = self._chain_args
+        if self._prep is None:  # everything that does not change between passes, once (msc_prepared_create)
+            self._prep = False
+            if e.jit != "never":
+                handle = C.c_void_p()
+                e.ctx.call("msc_prepared_create", C.byref(self.desc), self.ngroups, self.kinds, naggs, C.byref(desc2), raw_cols, out_phys, nout,
+                           None, C.byref(handle))
+                if handle.value:
+                    self._prep = _PreparedPass(e, handle.value, out_types, prog2.out_dicts)
+        if self._prep:
+            final = self._prep.run(0)
+            st = e.ctx.stats()
+            self.scan_stats = {"scan_ms": st.last_scan_ms, "grid": st.last_scan_grid, "stages": st.last_scan_stages,
+                               "smem": st.last_scan_smem, "rows_per_thread": st.last_scan_rows_per_thread, "kind": st.last_scan_kind,
+                               "regs": st.last_scan_regs}
+            return final, st.last_kernel_ms
         raw, fin, nonfinite = C.c_void_p(), C.c_void_p(), C.c_int32()
         for exact in (False, True):
             flags = (N.K["MSC_DENSE_JIT"] if e.jit != "never" else 0) | (N.K["MSC_DENSE_EXACT"] if exact else 0)
