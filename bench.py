@@ -414,7 +414,7 @@ def cuda_arm(args: argparse.Namespace) -> None:
                     "workload": f"TPC-H Q1 (examples/benchmark.py:51-68) on synthetic lineitem sf{args.sf:g} per GPU, sharded by row-block",
                     "sf_per_gpu": args.sf, "rows_per_gpu": nrows_table, "layout": args.layout, "bytes_per_row_scanned": bytes_per_row,
                     "l2": "inputs larger than L2 (scanned columns %.2f GB per GPU vs 126 MB L2)" % (nrows_table * bytes_per_row / 1e9),
-                    "timing": "two CUDA events on the library's stream bracketing all timed steps (host gaps and the NCCL merge included), max over ranks",
+                    "timing": "two CUDA events on the library's stream bracketing all timed steps (host gaps and the cross-rank exchange included), max over ranks",
                     "wall_ms_per_step": 1e3 * wall_max / args.steps, "parity_check": check,
                 },
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
