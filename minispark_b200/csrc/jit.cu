@@ -100,6 +100,10 @@ bool sym(void* lib, const char* name, F* out, std::string* why) {
 bool load_nvrtc(std::string* why) {
   Api& a = api();
   if (a.nvrtc) return true;
+  if (getenv("MSC_JIT_NO_NVRTC")) {  // tests: behave like a machine without the compiler library
+    *why = "libnvrtc.so.12 not found (MSC_JIT_NO_NVRTC is set)";
+    return false;
+  }
   const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"};
   for (const char* n : names)
     if ((a.nvrtc = dlopen(n, RTLD_NOW | RTLD_LOCAL)) != nullptr) break;
@@ -1125,7 +1129,7 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
   }
   *masked = sit->second.masked;
   Kernel& k = *sit->second.kernel;
-  if (fin && fin->peer && fin->peer->compile_only) return MSC_OK;
+  if (fin && (fin->compile_only || (fin->peer && fin->peer->compile_only))) return MSC_OK;
   if (sd->nrows == 0 && !(fin && fin->peer)) return MSC_OK;  // (a rank without rows still takes part in the exchange)
   JitParams p;
   MSC_TRY(fill_params(ctx, sd, &p));

@@ -23,6 +23,7 @@ struct JitFinish {
   unsigned long long* meta;      // device: {rows, non-finite flag, error word}
   uint32_t* ticket;              // device counter, zero between launches
   const msc_peer_spec* peer = nullptr;  // merge all ranks' tables over NVLink peer memory first (msc_dense_fused_peer)
+  bool compile_only = false;            // generate, compile and load the kernel, do not launch it
 };
 
 // can this scan run on a specialised kernel at all (cheap checks; the generator may still refuse a program)?

@@ -1134,15 +1134,8 @@ extern "C" int msc_prepared_create(msc_ctx* ctx, const msc_scan_desc* scan, int3
   static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
   bool masked = masked_enabled;
   if (!peer) fin.peer = nullptr;
-  if (peer) {
-    rc = jit_dense_launch(ctx, scan, ngroups, naggs, p->dp.stride, p->dp.kinds, p->dp.init, p->table, false, &masked, &fin);
-  } else {
-    // (no compile-only switch without a peer spec: generating the source and loading the kernel is what the first launch does,
-    // so let the first pass pay it -- but find out now whether the generator accepts the pair of programs)
-    std::string source, err;
-    rc = jit_dense_source(scan, ngroups, naggs, p->dp.stride, p->dp.kinds, p->dp.init, masked, &source, &err, &fin);
-    if (rc != MSC_OK) rc = ctx->fail(MSC_ERR_ARG, "jit: " + err);
-  }
+  fin.compile_only = true;  // find out NOW whether the generator accepts the pair of programs and a compiler exists
+  rc = jit_dense_launch(ctx, scan, ngroups, naggs, p->dp.stride, p->dp.kinds, p->dp.init, p->table, false, &masked, &fin);
   if (rc != MSC_OK) {
     const bool declined = (rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) || (rc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0);
     msc_rel_free(rel);

@@ -68,11 +68,16 @@ def _queries(ns, table, engine=None):
     }
 
 
+# jit="always": every dense aggregate and filter / project scan below runs on a kernel compiled for its program (csrc/jit.cu)
+JIT_MODES = pytest.mark.parametrize("jit", ["auto", "always"], ids=["interpreted", "specialised"])
+
+
+@JIT_MODES
 @pytest.mark.parametrize("nrows", [0, 1, 255, 256, 257, 8191, 8192, 8193, 20000])
-def test_row_counts_around_tile_sizes(tmp_path, nrows):
+def test_row_counts_around_tile_sizes(tmp_path, nrows, jit):
     ns = cases.namespace()
     table = _write(tmp_path / f"t{nrows}.bin", nrows)
-    with CudaExecutionEngine() as e:
+    with CudaExecutionEngine(jit=jit) as e:
         for name, q in _queries(ns, table, e).items():
             got = q.collect()
             want = O.run_task(_queries(ns, table)[name].task, wire=True)
@@ -90,12 +95,15 @@ def test_ragged_blocks_and_many_groups(tmp_path):
                                 rel=0.0 if name == "project" else 5e-7)
 
 
+@JIT_MODES
 @pytest.mark.parametrize("nkeys", [1, 2, 4, 5, 12, 300])
-def test_group_counts_across_kernel_variants(tmp_path, nkeys):
-    """1..4 groups: masked regvm variants; 5, 12: generic variant; 300: u16 codes, too many cells -> hash mode on codes."""
+def test_group_counts_across_kernel_variants(tmp_path, nkeys, jit):
+    """Interpreted: 1..4 groups take the masked regvm variants, 5 and 12 the generic one; specialised: up to 32 accumulator
+    cells compile for 128 registers, up to 56 for 168, more go back to the interpreter; 300 keys: u16 codes, too many cells
+    -> hash mode on the codes."""
     ns = cases.namespace()
     table = _write(tmp_path / f"g{nkeys}.bin", 3000, nkeys=nkeys)
-    with CudaExecutionEngine() as e:
+    with CudaExecutionEngine(jit=jit) as e:
         for name in ("dense", "dense_sum_only", "one_group_survives"):
             got = _queries(ns, table, e)[name].collect()
             O.assert_rows_equal(got, O.run_task(_queries(ns, table)[name].task, wire=True))
