@@ -336,6 +336,10 @@ MSC_API int msc_jit_dense_source(const msc_scan_desc* scan, int32_t ngroups, con
 MSC_API int msc_jit_dense_fused_source(const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs, int32_t masked,
                                const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
                                int32_t peer /* != 0: the cross-rank variant of msc_dense_fused_peer */, char* buf, size_t cap, size_t* len);
+/* ... for the streaming aggregate over the runs of sorted key column `key_col` (a staged slot; what msc_scan_aggregate runs in
+ * hash mode when it finds the key column sorted and the scan asks for a specialised kernel) */
+MSC_API int msc_jit_runs_source(const msc_scan_desc* scan, const int32_t* agg_kinds, int32_t naggs, int32_t key_col, char* buf, size_t cap,
+                        size_t* len);
 /* the same for a filter / project scan: count_only != 0 gives the first pass (surviving rows per 256-row tile), else
  * the pass that writes the output columns at their stable positions */
 MSC_API int msc_jit_project_source(const msc_scan_desc* scan, int32_t count_only, const int32_t* out_phys, int32_t nout, char* buf, size_t cap,

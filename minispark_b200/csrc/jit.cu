@@ -476,6 +476,148 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_scan(const __g
     return true;
   }
 
+  // GROUP BY a sorted integer key column (scan.cu checked: no descents, no filter): every run of equal keys is a group and
+  // its run number is its output row (scan_kernel.cuh MODE_RUNS is the interpreted twin).
+  bool generate_runs(int key_col) {
+    const Layout lay = stage_layout(sd);
+    temp_arrays = false;
+    o << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
+    o << "constexpr int NSTAGES = " << nstages << ";\n";
+    emit_layout(lay);
+    o << R"(
+extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __grid_constant__ JitParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64* full = reinterpret_cast<u64*>(smem) + warp * 8;
+  unsigned char* stages = smem + SMEM_HEADER + warp * (NSTAGES * STAGE_BYTES);
+  if (lane == 0) {
+    for (u32 st = 0; st < NSTAGES; ++st) mbar_init(&full[st], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const u32 gw = blockIdx.x * NW + warp, nw = gridDim.x * NW;
+  const u32 ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
+  {
+    const u32 pre = ntiles_w < NSTAGES ? ntiles_w : NSTAGES;
+    for (u32 k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + (u64)k * nw, lane);
+  }
+  const u64 nrows = p.nrows;
+  bool bad = false;
+  i64* out_key = reinterpret_cast<i64*>(p.out[0]);
+  u32 stage = 0, parity = 0;
+  for (u32 k = 0; k < ntiles_w; ++k) {
+    const u64 tile = gw + (u64)k * nw;
+    const unsigned char* sb = stages + stage * STAGE_BYTES;
+    while (!mbar_try_wait(&full[stage], parity)) {
+    }
+    u32 vmask = 0xffu;
+    const u64 tile_row0 = tile * WT;
+    if (tile_row0 + WT > nrows) {
+      vmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (tile_row0 + (r / 4) * 128 + 4 * lane + (r % 4) < nrows) vmask |= 1u << r;
+    }
+)";
+    for (int c = 0; c < sd->nstaged; ++c)
+      o << "    i64 c" << c << "[R]; " << ld_fn(sd->staged[c].phys) << "(sb + " << lay.off[c] << ", lane, c" << c << ");\n";
+    o << "    i64 key[R];\n";
+    bool used[MSC_VM_MAX_AGGS] = {};
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+      const uint32_t w0 = sd->code[pc];
+      if ((w0 & 0x3f) == MSC_OP_END) break;
+      if (((w0 >> 6) & 7) == MSC_DST_AGG) used[(w0 >> 13) & 0x7f] = true;
+    }
+    for (int a = 0; a < naggs; ++a)
+      if (used[a]) o << "    i64 v" << a << "[R];\n";
+    o << "#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      const bool valid = (vmask >> r) & 1u;\n";
+    for (int t = 0; t < sd->ntemps; ++t) o << "      i64 t" << t << " = 0;\n";
+    bool ok = true, grouped = false;
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+      const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
+      const int op = w0 & 0x3f;
+      if (op == MSC_OP_END) break;
+      const int dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
+      const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
+      const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+      if (op == MSC_OP_RANK || dkind == MSC_DST_FILTER || dkind == MSC_DST_OUT) {
+        why = "filter / projection instruction in a streaming aggregate";
+        return false;
+      }
+      const std::string a = operand(oa, &ok), b = lut ? std::string("0ll") : operand(ob, &ok);
+      o << "      {\n";
+      if (op == MSC_OP_DIV_F || op == MSC_OP_FLOORDIV_F || op == MSC_OP_MOD_F) o << "        bad |= valid && (l2d(" << b << ") == 0.0);\n";
+      if (op == MSC_OP_FLOORDIV_I || op == MSC_OP_MOD_I) o << "        bad |= valid && ((" << b << ") == 0);\n";
+      o << "        const i64 x = " << compute(op, a, b, ob, &ok) << ";\n";
+      if (tee) o << "        " << temp(tee - 1) << " = x;\n";
+      switch (dkind) {
+        case MSC_DST_TEMP: o << "        " << temp(dst) << " = x;\n"; break;
+        case MSC_DST_GROUP: o << "        key[r] = x;\n"; grouped = true; break;
+        case MSC_DST_AGG: o << "        v" << dst << "[r] = x;\n"; break;
+        case MSC_DST_NONE: break;
+        default: why = "destination kind outside an aggregate scan"; return false;
+      }
+      o << "      }\n";
+    }
+    o << "    }\n";
+    if (!ok || !grouped) {
+      why = ok ? "program has no GROUP" : "operand or opcode outside the generator";
+      return false;
+    }
+    const int kphys = sd->staged[key_col].phys;
+    const char* kty = kphys == MSC_P_U8 ? "unsigned char" : kphys == MSC_P_U16 ? "unsigned short" : kphys == MSC_P_U32 ? "u32"
+                      : kphys == MSC_P_I32 ? "int" : "i64";
+    o << "    // a row starts a run when its key differs from the previous ROW's: rows 4*lane..4*lane+3 of each 128-row half\n";
+    o << "    i64 prev0 = __shfl_up_sync(0xffffffffu, key[3], 1), prev1 = __shfl_up_sync(0xffffffffu, key[7], 1);\n";
+    o << "    const i64 row127 = __shfl_sync(0xffffffffu, key[3], 31);\n";
+    o << "    if (lane == 0) {\n      prev1 = row127;\n      prev0 = tile_row0 > 0 ? (i64)reinterpret_cast<const " << kty << "*>(p.col[" << key_col
+      << "])[tile_row0 - 1] : ~key[0];\n    }\n";
+    o << R"(    bool h[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const i64 before = (r == 0) ? prev0 : (r == 4) ? prev1 : key[r > 0 ? r - 1 : 0];
+      h[r] = ((vmask >> r) & 1u) && key[r] != before;
+    }
+    int idx[R];
+    {
+      const u32 c = (u32)(h[0] + h[1] + h[2] + h[3]) | ((u32)(h[4] + h[5] + h[6] + h[7]) << 16);  // runs starting in this lane: half 0 | half 1
+      u32 inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      const u32 total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - c;
+      const u64 base = p.tile_offsets[tile];  // runs that start before this tile
+      u64 run0 = base + (excl & 0xffffu), run1 = base + (total & 0xffffu) + (excl >> 16);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (h[r]) out_key[run0] = key[r];
+        run0 += h[r];
+        idx[r] = ((vmask >> r) & 1u) ? (int)run0 - 1 : -1;
+        if (h[r + 4]) out_key[run1] = key[r + 4];
+        run1 += h[r + 4];
+        idx[r + 4] = ((vmask >> (r + 4)) & 1u) ? (int)run1 - 1 : -1;
+      }
+    }
+)";
+    for (int a = 0; a < naggs; ++a)
+      if (used[a])
+        o << "    fold_segment<" << kinds[a] << ">(reinterpret_cast<u64*>(p.out[" << 1 + a << "]), idx, v" << a << "); fold_segment<" << kinds[a]
+          << ">(reinterpret_cast<u64*>(p.out[" << 1 + a << "]), idx + 4, v" << a << " + 4);\n";
+    o << R"(    __syncwarp();
+    if (k + NSTAGES < ntiles_w) issue_tile(p, stages, full, stage, gw + (u64)(k + NSTAGES) * nw, lane);
+    if (++stage == NSTAGES) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (bad) atomicOr(p.err, 1);  // MSC_DEVERR_DIV_ZERO
+}
+)";
+    return true;
+  }
+
   bool generate() {
     const Layout lay = stage_layout(sd);
     // which accumulators are SUM_I of a constant (COUNT, plan.py:190-204 / sql.py:463-464)?
@@ -1152,6 +1294,58 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
     p.ticket = fin->ticket;
   }
   return launch(ctx, k, &p, timed);
+}
+
+namespace {
+std::string runs_key(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col) {
+  const long long init[1] = {key_col};
+  int k2[MSC_VM_MAX_AGGS + 1];
+  k2[0] = -4;  // keeps these keys apart from the dense / project ones
+  for (int a = 0; a < naggs; ++a) k2[1 + a] = kinds[a];
+  (void)init;
+  std::string k = shape_key(ctx, sd, 0, naggs, 1, k2, init, false);
+  k.append(reinterpret_cast<const char*>(k2), sizeof(int) * (1 + naggs));
+  return k;
+}
+int runs_kernel(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, Kernel** out) {
+  const std::string skey = runs_key(ctx, sd, naggs, kinds, key_col);
+  auto sit = shapes().find(skey);
+  if (sit == shapes().end()) {
+    Gen g{sd, 0, naggs, naggs, kinds, nullptr, 2, false};
+    if (!g.generate_runs(key_col)) return ctx->fail(MSC_ERR_ARG, "jit: " + g.why);
+    const Layout lay = stage_layout(sd);
+    Kernel* k = nullptr;
+    MSC_TRY(load_kernel(ctx, g.o.str(), "msc_jit_runs", 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes, &k));
+    sit = shapes().emplace(skey, ShapeEntry{k, false}).first;
+  }
+  *out = sit->second.kernel;
+  return MSC_OK;
+}
+}  // namespace
+
+bool jit_runs_cached(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col) {
+  return shapes().count(runs_key(ctx, sd, naggs, kinds, key_col)) != 0;
+}
+
+int jit_runs_source(const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, std::string* source, std::string* err) {
+  Gen g{sd, 0, naggs, naggs, kinds, nullptr, 2, false};
+  if (!g.generate_runs(key_col)) {
+    *err = g.why;
+    return MSC_ERR_ARG;
+  }
+  *source = g.o.str();
+  return MSC_OK;
+}
+
+int jit_runs_launch(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, const uint64_t* tile_offsets, void* const* outs,
+                    bool timed) {
+  Kernel* k = nullptr;
+  MSC_TRY(runs_kernel(ctx, sd, naggs, kinds, key_col, &k));
+  JitParams p;
+  MSC_TRY(fill_params(ctx, sd, &p));
+  p.tile_offsets = reinterpret_cast<const unsigned long long*>(tile_offsets);
+  for (int c = 0; c < 1 + naggs; ++c) p.out[c] = outs[c];
+  return launch(ctx, *k, &p, timed);
 }
 
 int jit_project_source(const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, std::string* source, std::string* err) {

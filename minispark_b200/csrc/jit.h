@@ -54,4 +54,13 @@ int jit_project_compile(msc_ctx* ctx, const msc_scan_desc* sd, bool with_count_p
 int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, const int32_t* out_phys, int nout, uint32_t* tile_counts,
                        const uint64_t* tile_offsets, void* const* outs, bool timed);
 
+
+// ---- streaming aggregate over the runs of a sorted key (MODE_RUNS of scan_kernel.cuh), 256-row tiles ------------------
+// outs[0] = key column of the result (i64), outs[1 + a] = accumulator column a holding its identity; tile_offsets[t] = runs
+// that start before tile t
+bool jit_runs_cached(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col);
+int jit_runs_source(const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, std::string* source, std::string* err);
+int jit_runs_launch(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, const uint64_t* tile_offsets, void* const* outs,
+                    bool timed);
+
 }  // namespace mscan

@@ -1222,6 +1222,20 @@ extern "C" int msc_jit_dense_fused_source(const msc_scan_desc* sd, int32_t ngrou
   return source.empty() ? MSC_ERR_ARG : MSC_OK;
 }
 
+extern "C" int msc_jit_runs_source(const msc_scan_desc* sd, const int32_t* agg_kinds, int32_t naggs, int32_t key_col, char* buf, size_t cap, size_t* len) {
+  if (!sd || !agg_kinds || !len || naggs < 0 || naggs > MSC_VM_MAX_AGGS || key_col < 0 || key_col >= sd->nstaged) return MSC_ERR_ARG;
+  std::string source, err;
+  jit_runs_source(sd, naggs, agg_kinds, key_col, &source, &err);
+  const std::string& text = source.empty() ? err : source;
+  *len = text.size();
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, text.size());
+    memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return source.empty() ? MSC_ERR_ARG : MSC_OK;
+}
+
 extern "C" int msc_jit_project_source(const msc_scan_desc* sd, int32_t count_only, const int32_t* out_phys, int32_t nout, char* buf, size_t cap,
                                       size_t* len) {
   if (!sd || !len || nout < 0 || nout > MSC_VM_MAX_OUT || (nout && !out_phys)) return MSC_ERR_ARG;
@@ -1365,12 +1379,25 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
         ctx->stats.launches += naggs;
         lp.p.tile_offsets = roffsets.as<uint64_t>();
         lp.p.run_key_col = key_col;
-        rc = launch_scan_r<MODE_RUNS>(ctx, &lp);
-        if (rc != MSC_OK) {
-          msc_rel_free(rel);
-          return rc;
+        static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
+        bool jitted = false;
+        if (jit_mode > 0 && naggs + 1 <= MSC_VM_MAX_OUT && (sd->want_jit != 0 || jit_mode > 1 || jit_runs_cached(ctx, sd, naggs, kinds, key_col))) {
+          rc = jit_runs_launch(ctx, sd, naggs, kinds, key_col, roffsets.as<uint64_t>(), lp.p.out, true);
+          jitted = rc == MSC_OK;
+          const bool declined = (rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) || (rc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0);
+          if (rc != MSC_OK && !declined) {
+            msc_rel_free(rel);
+            return rc;
+          }
         }
-        ctx->stats.last_scan_kind = MSC_SCAN_KIND_RUNS;
+        if (!jitted) {
+          rc = launch_scan_r<MODE_RUNS>(ctx, &lp);
+          if (rc != MSC_OK) {
+            msc_rel_free(rel);
+            return rc;
+          }
+          ctx->stats.last_scan_kind = MSC_SCAN_KIND_RUNS;
+        }
         MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
         const int drc = msc_check_device_error(ctx);  // synchronises the stream
         if (drc != MSC_OK) {

@@ -217,6 +217,9 @@ def merge_data_blocks(data_block_1: Columns, data_block_2: Columns) -> Columns:
     return tuple(list(a) + list(b) for a, b in zip(data_block_1, data_block_2))
 
 
+_SCHEMA_CACHE: dict[tuple, Schema] = {}
+
+
 class BlockFile:
     """Reader/writer with the reference's method names (``io.py:180-313``)."""
 
@@ -245,8 +248,22 @@ class BlockFile:
     @property
     def file_schema(self) -> Schema:
         if self._file_schema is None:
-            with self.file.open("rb") as f:
-                self._file_schema = _deserialize_schema(f)
+            # planning asks for a table's schema several times per query (validate_schema, the lowering, the engine), each
+            # time through a fresh BlockFile object: remember the header per (path, mtime, size)
+            try:
+                st = self.file.stat()
+                key = (str(self.file), st.st_mtime_ns, st.st_size)
+            except OSError:
+                key = None
+            cached = _SCHEMA_CACHE.get(key) if key else None
+            if cached is None:
+                with self.file.open("rb") as f:
+                    cached = _deserialize_schema(f)
+                if key:
+                    if len(_SCHEMA_CACHE) > 256:
+                        _SCHEMA_CACHE.clear()
+                    _SCHEMA_CACHE[key] = cached
+            self._file_schema = list(cached)
         return self._file_schema
 
     def rows(self) -> int:

@@ -152,6 +152,7 @@ _SIGNATURES = {
                              C.POINTER(C.c_size_t)]),
     "msc_jit_dense_fused_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "msc_jit_runs_source": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "msc_jit_project_source": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "msc_jit_compile": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "msc_dense_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -33,11 +33,12 @@ def _query(ns, table, key, engine=None):
         ns.F.min(ns.Col("l_quantity")).alias("lo"), ns.F.max(ns.Col("l_extendedprice")).alias("hi"))
 
 
-@pytest.mark.parametrize(("key", "kind"), [("l_orderkey", "RUNS"), ("l_suppkey", "VM")], ids=["sorted_key_streams", "unsorted_key_hashes"])
-def test_high_cardinality_group_by_matches_f64_oracle(lineitem_72k, key, kind):
+@pytest.mark.parametrize(("key", "kind", "jit"), [("l_orderkey", "RUNS", "auto"), ("l_orderkey", "JIT", "always"), ("l_suppkey", "VM", "auto")],
+                         ids=["sorted_key_streams", "sorted_key_streams_specialised", "unsorted_key_hashes"])
+def test_high_cardinality_group_by_matches_f64_oracle(lineitem_72k, key, kind, jit):
     ns = cases.namespace()
     want = {r[key]: r for r in O.run_task(_query(ns, lineitem_72k, key).task, wire=False)}
-    with CudaExecutionEngine() as e:
+    with CudaExecutionEngine(jit=jit) as e:
         rel, schema = e.execute_to_device(_query(ns, lineitem_72k, key).task)
         assert e.last_stats["agg_mode"] == "hash"
         assert e.last_stats["agg_scan_kind"] == N.K[f"MSC_SCAN_KIND_{kind}"]

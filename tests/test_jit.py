@@ -221,3 +221,42 @@ def test_q1_with_fused_finish_compiles(tmp_path):
     body = peer_src.split("msc_jit_dense(")[1]
     assert "st_release_sys(p.mailbox[lane]" in body and "ld_acquire_sys(flag) != p.epoch" in body and "p.inv[r * 32 + g]" in body
     compile_source(peer_src)
+
+
+def test_streaming_aggregate_over_sorted_runs_compiles(tmp_path):
+    """GROUP BY l_orderkey (a sorted key): run heads by comparison with the previous row, run numbers by a warp scan, one
+    atomic per (run, accumulator) segment."""
+    import sys
+    from copy import deepcopy
+    from pathlib import Path
+
+    from minispark_b200 import lowering as L
+    from test_lowering import StubResolver
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "bench"))
+    import gen_tpch
+
+    table = tmp_path / "l.bin"
+    gen_tpch.write_table(table, "lineitem", sf=0.0005, columns=["l_orderkey", "l_quantity", "l_extendedprice"], rows_per_block=4096)
+    from minispark_b200.parser import parse_sql
+
+    task = deepcopy(parse_sql(f"SELECT l_orderkey, SUM(l_quantity) AS q, AVG(l_extendedprice) AS p, MAX(l_quantity) AS hi FROM '{table}' "
+                              "GROUP BY l_orderkey;").task)
+    task.validate_schema()
+    plan = L.lower_task(task)
+    agg = plan.child
+    res = StubResolver(agg.child.schema)
+    ltype_of = {"INTEGER": "I", "FLOAT": "F", "TIMESTAMP": "T", "STRING": "S"}
+    res.ltypes = [ltype_of[t.name] for _, t in agg.child.schema]
+    prog = L.compile_aggregate(res, [], agg.group, list(agg.aggs))
+    d = _desc(prog, res)
+    lib = N.load()
+    n = C.c_size_t()
+    buf = C.create_string_buffer(1 << 20)
+    key_slot = res.staged.index(0)
+    rc = lib.msc_jit_runs_source(C.byref(d), N.int32_array(prog.agg_kinds), len(prog.agg_kinds), key_slot, buf, len(buf), C.byref(n))
+    src = buf.value.decode()
+    assert rc == 0, src
+    assert "msc_jit_runs" in src and "fold_segment<0>" in src and "fold_segment<3>" in src   # SUM_F and MAX_F accumulators
+    assert "p.tile_offsets[tile]" in src and "out_key[run0] = key[r]" in src
+    compile_source(src)
