@@ -237,6 +237,23 @@ __device__ __forceinline__ void atomic_fold(int kind, u64* addr, i64 v) {
     }
   }
 }
+
+// ---- streaming aggregate over the runs of a sorted key (msc_jit_runs): fold the rows of one 4-row segment that belong
+// to the same run in registers, then one atomic per (run, accumulator) -- a run may continue in the next lane or tile ----
+template <int KIND>
+__device__ __forceinline__ void fold_segment(u64* col, const int* idx, const i64* v) {
+  i64 run = v[0];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const bool same_next = r < 3 && idx[r] >= 0 && idx[r + 1] == idx[r];
+    if (same_next) {
+      run = agg_combine<KIND>(run, v[r + 1]);
+    } else {
+      if (idx[r] >= 0) atomic_fold(KIND, col + idx[r], run);
+      run = v[r < 3 ? r + 1 : r];
+    }
+  }
+}
 constexpr int NG = 3, NGP = 4, STRIDE = 6, NSTAGES = 2;
 constexpr u32 STAGE_BYTES = 6400, TX_BYTES = 6400, NSTAGED = 6;
 __device__ const u32 COL_OFF[6] = {0, 2048, 2304, 3328, 4352, 5376};
@@ -441,6 +458,10 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     i64 a[STRIDE];
 #pragma unroll
     for (int s = 0; s < STRIDE; ++s) a[s] = static_cast<i64>(__ldcg(cell + s));
+    if (in_range) {  // leave the identities behind: the next pass of a prepared query needs no initialisation launch
+#pragma unroll
+      for (int s = 0; s < STRIDE; ++s) p.dense_out[g * STRIDE + s] = static_cast<u64>(INIT[s]);
+    }
     bool valid = in_range && a[5] != 0;
     bool nonfinite = false, bad = false;
     nonfinite |= in_range && !isfinite(l2d(a[0]));
