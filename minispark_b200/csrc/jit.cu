@@ -65,8 +65,6 @@ typedef struct CUfunc_st* CUfunction;
 typedef struct CUstream_st* CUstream;
 
 struct Api {
-  bool tried = false;
-  std::string why;
   void *nvrtc = nullptr, *cuda = nullptr;
   int (*nvrtcCreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
   int (*nvrtcCompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
@@ -1017,9 +1015,9 @@ std::string disk_cache_path(const std::string& source) {
   return std::string(dir) + name;
 }
 
-int compile(const std::string& source, int minctas, std::vector<char>* cubin, std::string* err) {
+int compile(const std::string& source, std::vector<char>* cubin, std::string* err) {
   if (!load_nvrtc(err)) return MSC_ERR_ARG;
-  const std::string path = disk_cache_path(source + "#" + std::to_string(minctas));
+  const std::string path = disk_cache_path(source);
   if (!path.empty()) {
     std::ifstream f(path, std::ios::binary);
     if (f) {
@@ -1044,7 +1042,6 @@ int compile(const std::string& source, int minctas, std::vector<char>* cubin, st
     *err = "nvrtcCreateProgram failed";
     return MSC_ERR_ARG;
   }
-  (void)minctas;  // the source defines MINCTAS itself (it depends on the number of accumulator cells)
   // --fmad=false: Python rounds every operation (sql.py:262-266); a contracted a * b + c would not
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "--fmad=false"};
   const int rc = a.nvrtcCompileProgram(prog, 5, opts);
@@ -1120,7 +1117,7 @@ int jit_dense_source(const msc_scan_desc* sd, int ngroups, int naggs, int stride
   return generate_either(sd, ngroups, naggs, stride, kinds, init, &masked, source, err, fin);
 }
 
-int jit_compile_source(const std::string& source, std::vector<char>* cubin, std::string* err) { return compile(source, JIT_MIN_CTAS, cubin, err); }
+int jit_compile_source(const std::string& source, std::vector<char>* cubin, std::string* err) { return compile(source, cubin, err); }
 
 // Everything the generated source depends on, as bytes: a launch finds its kernel through this key without building
 // the source text again (constants are kernel parameters, so a different date literal reuses the kernel).
@@ -1164,7 +1161,7 @@ int load_kernel(msc_ctx* ctx, const std::string& source, const char* fn_name, si
     if (!load_driver(&why)) return ctx->fail(MSC_ERR_CUDA, "jit: " + why);
     auto k = std::make_unique<Kernel>();
     const auto t0 = std::chrono::steady_clock::now();
-    if (compile(source, JIT_MIN_CTAS, &k->cubin, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
+    if (compile(source, &k->cubin, &why) != MSC_OK) return ctx->fail(MSC_ERR_ARG, "jit: " + why);
     ctx->stats.last_jit_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     Api& a = api();
     int rc = a.cuModuleLoadData(&k->mod, k->cubin.data());

@@ -383,24 +383,6 @@ __device__ __forceinline__ void agg_hash(unsigned long long* htbl, uint32_t hshi
   }
 }
 
-__device__ __forceinline__ int hash_find_or_insert(unsigned long long* tbl, uint32_t shift, uint64_t cap, long long key, int* err) {
-  const uint64_t mask = cap - 1;
-  uint64_t pos = msc_mix64(static_cast<uint64_t>(key)) & mask;
-  const unsigned long long k = static_cast<unsigned long long>(key);
-  for (uint64_t probe = 0; probe < cap; ++probe) {
-    unsigned long long* slot = tbl + (pos << shift);
-    unsigned long long cur = *slot;
-    if (cur == k) return static_cast<int>(pos);
-    if (cur == HASH_EMPTY) {
-      const unsigned long long prev = atomicCAS(slot, HASH_EMPTY, k);
-      if (prev == HASH_EMPTY || prev == k) return static_cast<int>(pos);
-    }
-    pos = (pos + 1) & mask;
-  }
-  atomicOr(err, MSC_DEVERR_TABLE_FULL);
-  return -1;
-}
-
 // exclusive prefix sum of one u32 per lane across the warp; total in *total
 __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, int lane, uint32_t* total) {
   uint32_t inc = v;
