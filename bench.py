@@ -421,6 +421,8 @@ def cuda_arm(args: argparse.Namespace) -> None:
                              "kernel": kernel, "launch": agg_launch,
                              "program": prepared.prog.program.text,
                              "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": nrows_table * bytes_per_row, "peak_source": peak_src,
+                             "kernel_ms_includes": ("the in-kernel wait for the slowest rank's partial table (fused exchange): quote the roofline at N=1"
+                                                    if world > 1 and str(agg_launch.get("exchange", "")).startswith("nvlink") else "the scan kernel alone"),
                              "north_star_layout_equiv_gbs": nrows_table * Q1_WIDE_BYTES_PER_ROW / (scan_ms * 1e-3) / 1e9 if args.layout == "native" else None},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
