@@ -175,3 +175,40 @@ def test_without_a_compiler_prepared_queries_run_on_the_interpreter(tmp_path):
     """)
     out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "interpreted ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("threshold", [0.0, 8000.0, 1e12], ids=["all_groups", "some_groups", "no_group"])
+def test_fused_finish_applies_having_in_group_order(tmp_path, threshold):
+    """The scan's last CTA also runs the final projection: a HAVING filter there is a ballot + rank over the groups."""
+    from minispark_b200 import BlockFile
+    from minispark_b200.constants import ColumnType
+    from minispark_b200.execution import CudaExecutionEngine
+    from oracle import py_oracle as O
+
+    path = tmp_path / "h.bin"
+    n = 6000
+    rng = np.random.default_rng(11)
+    keys = [f"k{int(j)}" for j in rng.integers(0, 6, n)]
+    vals = (rng.integers(0, 800, n) / 4.0 * (1 + np.array([int(k[1]) for k in keys]) % 3)).tolist()
+    BlockFile(path, [("k", ColumnType.STRING), ("v", ColumnType.FLOAT)]).write_rows([{"k": k, "v": v} for k, v in zip(keys, vals)])
+    sql = f"SELECT k, SUM(v) AS s, AVG(v) AS a, COUNT() AS c FROM '{path}' GROUP BY k HAVING SUM(v) > {int(threshold)};"
+    with CudaExecutionEngine() as engine:
+        task = engine.sql(sql).task
+        want = {r["k"]: r for r in O.run_task(engine.sql(sql).task, wire=False)}
+        prepared = engine.prepare(task)
+        for i in range(3):
+            final, _ms = prepared.run()
+            names = [name for name, _ in prepared.plan.schema]
+            got = {}
+            if final.nrows:
+                keys_out = final.cols[0].dict.export()
+                cols = [final.column_numpy(c) for c in range(len(names))]
+                got = {keys_out[int(cols[0][r])]: {name: cols[c][r].item() for c, name in enumerate(names) if c} for r in range(final.nrows)}
+            engine.release_query()
+            if i:
+                assert prepared.scan_stats["kind"] == 2
+            assert sorted(got) == sorted(want), (i, sorted(got), sorted(want))
+            for k, ref in want.items():
+                assert got[k]["c"] == ref["c"]
+                for name in ("s", "a"):
+                    assert abs(got[k][name] - ref[name]) <= 1e-9 * abs(ref[name]), (k, name, got[k][name], ref[name])
