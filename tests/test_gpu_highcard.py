@@ -4,6 +4,7 @@ table), an unsorted one the hash table sized by the run count.  Both against the
 
 from __future__ import annotations
 
+import os
 import sys
 from pathlib import Path
 
@@ -41,7 +42,10 @@ def test_high_cardinality_group_by_matches_f64_oracle(lineitem_72k, key, kind, j
     with CudaExecutionEngine(jit=jit) as e:
         rel, schema = e.execute_to_device(_query(ns, lineitem_72k, key).task)
         assert e.last_stats["agg_mode"] == "hash"
-        assert e.last_stats["agg_scan_kind"] == N.K[f"MSC_SCAN_KIND_{kind}"]
+        expected = {N.K[f"MSC_SCAN_KIND_{kind}"]}
+        if kind == "RUNS" and os.environ.get("MSC_SCAN_JIT") == "2":  # the whole-suite rerun that forces specialised kernels
+            expected.add(N.K["MSC_SCAN_KIND_JIT"])
+        assert e.last_stats["agg_scan_kind"] in expected
         names = [n for n, _ in schema]
         cols = [rel.column_numpy(i) for i in range(len(names))]
         got = {int(cols[0][r]): {n: cols[i][r].item() for i, n in enumerate(names)} for r in range(rel.nrows)}
