@@ -26,11 +26,12 @@ CASES = [
 
 
 @pytest.mark.parametrize(("name", "extra", "at_least"), CASES, ids=[c[0] for c in CASES])
-def test_reference_test_file_passes_against_the_mirror(name, extra, at_least):
+def test_reference_test_file_passes_against_the_mirror(name, extra, at_least, tmp_path):
     path = REF_TESTS / name
     if not path.exists():
         pytest.skip("reference checkout not present")
-    out = subprocess.run([sys.executable, str(RUNNER), str(path), *extra], capture_output=True, text=True, timeout=600, cwd="/tmp")
+    # (run from a scratch folder: the reference's tasks write their shuffle files relative to the working directory)
+    out = subprocess.run([sys.executable, str(RUNNER), str(path), *extra], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     passed = re.search(r"(\d+) passed", out.stdout)
     assert passed and int(passed.group(1)) >= at_least, out.stdout[-1500:]
