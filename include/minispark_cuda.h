@@ -454,10 +454,49 @@ MSC_API int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nleft
 
 /* ---- shuffle partitioning: replaces WriteToShufflePartitions.write (tasks.py:347-375) and zig
  * fill_buckets (task_utils.zig:53-98).  Rows are routed by hash(key) % nparts; every column is
- * scattered into partition-contiguous order.  counts[nparts] (host) receives rows per partition.
- * Output relation has the same columns, permuted. ------------------------------------------- */
+ * scattered into partition-contiguous order, STABLE (rows of a partition keep their input order, as the reference's
+ * per-bucket appends do).  counts[nparts] (host) receives rows per partition.  Output relation has the same columns,
+ * permuted. ---------------------------------------------------------------------------------- */
 MSC_API int msc_partition(msc_ctx* ctx, msc_rel* rel, int32_t key_col, int32_t nparts, uint64_t* counts,
                   msc_rel** out);
+
+/* ---- row exchange between ranks over NVLink peer memory: replaces the shuffle FILES between stages --
+ * WriteToShufflePartitions.write (tasks.py:347-375) on the sending side, LoadShuffleFilesTask (tasks.py:144-150,
+ * plan.py:94-118) on the receiving side.  One process per GPU; a rank's rows are partitioned on its GPU (msc_partition)
+ * and every partition-contiguous column segment is copied by ONE push kernel straight into the receiving rank's buffer
+ * (plain coalesced stores into CUDA-IPC peer memory): no collective library call, no staging copy.
+ *
+ * Set-up (collective; the host language moves the 64-byte handles, e.g. torch.distributed.all_gather_object):
+ *   msc_shuffle_create -> handle of this rank's control block;  msc_shuffle_attach(all ranks' handles, rank-major)
+ *   msc_shuffle_slot_alloc(slot, bytes) -> handle of a receive buffer;  msc_shuffle_slot_attach(slot, all handles)
+ *   (to grow a slot: every rank msc_shuffle_slot_detach, a host barrier, then alloc + attach again)
+ * One exchange (`epoch` = 1, 2, 3, ... the same on every rank):
+ *   msc_shuffle_begin   partitions `rel` on column key_col by hash(key) % world (key_col < 0: every row goes to every
+ *                       rank), publishes this rank's row of the rows[src][dst] matrix to all ranks, waits for theirs and
+ *                       returns the matrix (world x world, src-major) and need_bytes[dst] = slot bytes rank dst needs.
+ *                       All ranks see the same numbers, so they can size their slots without talking again.
+ *   msc_shuffle_finish  pushes this rank's segments into the receivers' slot `slot`, tells them, waits (on the device)
+ *                       for everybody's rows and returns a relation that WRAPS this rank's slot (columns in the order
+ *                       and physical types of `rel`, rows ordered by sending rank, then input order).  Stream-ordered:
+ *                       the host does not wait.  The relation is valid until the slot is used by another exchange.
+ *   msc_shuffle_wait    optional: host wait + device error word (MSC_ERR_PEER when a rank never arrived) + the device
+ *                       milliseconds of the last finish.
+ * msc_shuffle_allgather: `nbytes` (<= MSC_SHUFFLE_TABLE_BYTES, a multiple of 8) from every rank into dst[world][nbytes]
+ * through the control blocks, one small kernel, no host wait (its own `epoch` sequence 1, 2, ...): the partial tables of a
+ * low-cardinality GROUP BY (plan.py:190-199) in one-shot queries. */
+#define MSC_SHUFFLE_TABLE_BYTES 16384
+typedef struct msc_shuffle msc_shuffle;
+MSC_API int msc_shuffle_create(msc_ctx* ctx, int32_t rank, int32_t world, msc_shuffle** out, void* handle64);
+MSC_API int msc_shuffle_attach(msc_shuffle* sh, const void* handles /* world x 64 bytes */);
+MSC_API int msc_shuffle_slot_alloc(msc_shuffle* sh, int32_t slot, size_t nbytes, void* handle64);
+MSC_API int msc_shuffle_slot_attach(msc_shuffle* sh, int32_t slot, const void* handles /* world x 64 bytes */);
+MSC_API int msc_shuffle_slot_detach(msc_shuffle* sh, int32_t slot);
+MSC_API int msc_shuffle_slot_bytes(msc_shuffle* sh, int32_t slot, size_t* nbytes);
+MSC_API int msc_shuffle_begin(msc_shuffle* sh, msc_rel* rel, int32_t key_col, uint64_t epoch, uint64_t* matrix, uint64_t* need_bytes);
+MSC_API int msc_shuffle_finish(msc_shuffle* sh, int32_t slot, uint64_t epoch, msc_rel** out);
+MSC_API int msc_shuffle_wait(msc_shuffle* sh, double* ms);
+MSC_API int msc_shuffle_allgather(msc_shuffle* sh, const void* src_dev, size_t nbytes, uint64_t epoch, void* dst_dev);
+MSC_API void msc_shuffle_free(msc_shuffle* sh);
 
 /* ---- results: replaces WriteToLocalFileTask.write (tasks.py:399-410) / zig BlockFile.appendData
  * (block_file.zig:413-456).  INTEGER narrows to i32 (error on overflow), FLOAT to f32. ------- */

@@ -8,8 +8,8 @@
 // tasks.py:216-218) the build side may be of any size.
 //
 // msc_partition replaces WriteToShufflePartitions.write (tasks.py:347-375) / zig fill_buckets
-// (task_utils.zig:53-98): rows are routed by hash(key) % nparts into partition-contiguous order,
-// ready for an all-to-all between ranks.
+// (task_utils.zig:53-98): rows are routed by hash(key) % nparts into partition-contiguous order (stable: input order
+// inside every partition), ready for the exchange between ranks (shuffle.cu).
 #include "common.cuh"
 
 namespace {
@@ -162,18 +162,44 @@ __global__ void part_hist_kernel(const void* key, int phys, uint64_t n, int npar
   if (threadIdx.x < nparts) hist[static_cast<uint64_t>(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// Output position of every row, STABLE: rows of one partition keep their input order (the reference appends the rows of
+// a chunk to each bucket in row order, tasks.py:357-368 / task_utils.zig:60-98).  A block walks its rows 256 at a time;
+// inside a warp equal partitions find each other with match.any, the lane's rank among them is a popcount, the warps'
+// counts are prefix-summed in shared memory, and the per-partition cursor moves on once per step.
 __global__ void part_pos_kernel(const void* key, int phys, uint64_t n, int nparts, uint32_t nblocks,
-                                const uint64_t* offsets, uint32_t* pos) {
+                                const uint64_t* offsets, uint32_t* pos, uint8_t* part) {
+  constexpr int NW = PTHREADS / 32;
   __shared__ unsigned long long cursor[MAX_PARTS];
-  if (threadIdx.x < nparts) cursor[threadIdx.x] = offsets[static_cast<uint64_t>(threadIdx.x) * nblocks + blockIdx.x];
-  __syncthreads();
+  __shared__ uint32_t wcount[NW][MAX_PARTS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < nparts) cursor[tid] = offsets[static_cast<uint64_t>(tid) * nblocks + blockIdx.x];
   const uint64_t base = static_cast<uint64_t>(blockIdx.x) * PBLOCK;
-  for (int i = threadIdx.x; i < PBLOCK; i += PTHREADS) {
-    const uint64_t r = base + i;
-    if (r < n) {
-      const int p = part_of(read_key(key, phys, r), nparts);
-      pos[r] = static_cast<uint32_t>(atomicAdd(&cursor[p], 1ULL));
+  for (int it = 0; it < PBLOCK / PTHREADS; ++it) {
+    const uint64_t r = base + static_cast<uint64_t>(it) * PTHREADS + tid;
+    if (base + static_cast<uint64_t>(it) * PTHREADS >= n) break;  // (uniform per block)
+    for (int i = tid; i < NW * MAX_PARTS; i += PTHREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const bool valid = r < n;
+    const int p = valid ? part_of(read_key(key, phys, r), nparts) : MAX_PARTS;  // rows past the end group among themselves
+    const unsigned same = __match_any_sync(0xffffffffu, p);
+    const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+    if (valid && rank == 0) wcount[warp][p] = __popc(same);
+    __syncthreads();
+    uint32_t total = 0;
+    if (tid < nparts) {
+      for (int w = 0; w < NW; ++w) {
+        const uint32_t c = wcount[w][tid];
+        wcount[w][tid] = total;
+        total += c;
+      }
     }
+    __syncthreads();
+    if (valid) {
+      pos[r] = static_cast<uint32_t>(cursor[p] + wcount[warp][p] + rank);
+      if (part) part[r] = static_cast<uint8_t>(p);
+    }
+    __syncthreads();
+    if (tid < nparts) cursor[tid] += total;
   }
 }
 
@@ -288,7 +314,7 @@ extern "C" int msc_partition(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t
   part_hist_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, hist.as<uint32_t>());
   ctx->stats.launches += 1;
   if ((rc = msc_exclusive_scan_u32_u64(ctx, hist.as<uint32_t>(), offsets.as<uint64_t>(), cells)) != MSC_OK) return fail(rc);
-  part_pos_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, offsets.as<uint64_t>(), pos.as<uint32_t>());
+  part_pos_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, offsets.as<uint64_t>(), pos.as<uint32_t>(), nullptr);
   ctx->stats.launches += 1;
   const unsigned grid = static_cast<unsigned>(ctx->sm_count * 8);
   for (size_t c = 0; c < in->cols.size(); ++c) {

@@ -1,19 +1,20 @@
-"""Multi-GPU plumbing: one process (rank) per GPU, ``torch.distributed`` for the exchange.
+"""Multi-GPU plumbing: one process (rank) per GPU.
 
 The reference's only parallelism is data-parallel row-blocks plus a hash-partitioned shuffle through
 files (``src/mini_spark/plan.py:90-109``: one ``ScanJob`` per block, partitions re-read per
 ``LoadShuffleFilesJob``; ``tasks.py:347-375`` writes ``hash(key) % 10`` buckets).  Here:
 
-* row-blocks are dealt round-robin to ranks (:func:`shard_blocks`); every rank scans only its blocks;
+* row-blocks are dealt to ranks as contiguous ranges (:func:`shard_blocks`), so that the rank-ordered union of
+  rank-local filter / project results is the table's input order (tests/test_execution.py:40-46 of the reference);
 * a low-cardinality GROUP BY merges tiny per-rank partial tables: string keys are unified through
-  their dictionary *entries* (:func:`unify_keys`), the partial rows are all-gathered and re-aggregated
-  on every GPU -- no row-level data crosses the fabric;
-* a high-cardinality GROUP BY / JOIN routes rows by ``hash(key) % world`` (``msc_partition``) and
-  exchanges them with one all-to-all (:meth:`Comm.all_to_all_rows`), the GPU analogue of the
-  reference's shuffle files.
+  their dictionary *entries* (:func:`unify_keys`); no row-level data crosses the fabric;
+* a high-cardinality GROUP BY / JOIN routes rows by ``hash(key) % world`` (``msc_partition``) and exchanges them
+  over NVLink peer memory (:class:`PeerShuffle`: the library's push kernel stores every column segment straight into
+  the receiving rank's buffer, csrc/shuffle.cu) -- the GPU analogue of the reference's shuffle files.  Where CUDA IPC
+  is not available the same rows travel through ONE group of NCCL sends / receives (:meth:`Comm.all_to_all_rows`).
 
-This module holds only host logic on ``torch`` tensors, so it runs under ``gloo`` on CPU (tests) and
-under ``nccl`` on GPUs unchanged.  PyTorch is plumbing here (buffers + collectives), not compute.
+``torch.distributed`` carries the rendezvous and the small host-side metadata (IPC handles, dictionary entries, row
+counts under gloo); the host logic runs under ``gloo`` on CPU (tests) and under ``nccl`` on GPUs unchanged.
 """
 
 from __future__ import annotations
@@ -24,10 +25,12 @@ from typing import Any, Optional, Sequence
 
 
 def shard_blocks(nblocks: int, rank: int, world: int) -> list[int]:
-    """Row-blocks owned by ``rank``: block ``b`` goes to rank ``b % world`` (cf. plan.py:90-93)."""
+    """Row-blocks owned by ``rank``: one job per block as in the reference (plan.py:90-93), dealt as balanced CONTIGUOUS
+    ranges -- rank r owns blocks [r * n // world, (r + 1) * n // world) -- so that concatenating rank-local results in rank
+    order keeps the table's row order."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError(f"bad rank/world {rank}/{world}")
-    return [b for b in range(nblocks) if b % world == rank]
+    return list(range(rank * nblocks // world, (rank + 1) * nblocks // world))
 
 
 def unify_keys(per_rank_keys: Sequence[Sequence[str]]) -> tuple[list[str], list[list[int]]]:
@@ -102,52 +105,149 @@ class Comm:
 
             dist.barrier()
 
-    def all_gather_rows(self, columns: Sequence[Any], nrows: int) -> tuple[list[Any], list[int]]:
-        """All-gather a small relation given as 1-D tensors of ``nrows`` elements each.
-
-        Returns (concatenated columns, rows per rank).  Ragged row counts are padded to the maximum."""
-        import torch
-
-        counts = self.all_gather_object(int(nrows))
+    def all_gather_counts(self, values: Sequence[int]) -> list[list[int]]:
+        """[rank][i] = ``values[i]`` of that rank: a tensor all-gather (on the device under NCCL: no pickling)."""
         if self.world == 1:
-            return [c[:nrows].clone() for c in columns], counts
+            return [[int(v) for v in values]]
+        import torch
         import torch.distributed as dist
 
-        width = max(max(counts), 1)
-        out = []
-        for col in columns:
-            padded = torch.zeros(width, dtype=col.dtype, device=col.device)
-            padded[:nrows] = col[:nrows]
-            parts = [torch.empty_like(padded) for _ in range(self.world)]
-            dist.all_gather(parts, padded)
-            out.append(torch.cat([p[:n] for p, n in zip(parts, counts)]))
+        mine = torch.tensor([int(v) for v in values], dtype=torch.int64, device=self.device)
+        out = torch.empty(self.world * len(values), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, mine)
+        return out.view(self.world, len(values)).cpu().tolist()
+
+    def all_gather_rows(self, columns: Sequence[Any], nrows: int) -> tuple[list[Any], list[int]]:
+        """All-gather a small relation given as 1-D tensors of ``nrows`` elements each (rank order).
+
+        Returns (concatenated columns, rows per rank)."""
+        counts = [c[0] for c in self.all_gather_counts([nrows])]
+        if self.world == 1:
+            return [c[:nrows].clone() for c in columns], counts
+        out, _ = self.all_to_all_rows([c[:nrows].repeat(self.world) for c in columns], [nrows] * self.world, matrix=[[n] * self.world for n in counts])
         return out, counts
 
-    def all_to_all_rows(self, columns: Sequence[Any], send_counts: Sequence[int]) -> tuple[list[Any], list[int]]:
+    def all_to_all_rows(self, columns: Sequence[Any], send_counts: Sequence[int], pad_rows: int = 0,
+                        matrix: Optional[Sequence[Sequence[int]]] = None) -> tuple[list[Any], list[int]]:
         """Exchange partition-contiguous rows: the first ``send_counts[0]`` rows of every column go to
-        rank 0, the next ``send_counts[1]`` to rank 1, ...  Returns (received columns, recv_counts)."""
+        rank 0, the next ``send_counts[1]`` to rank 1, ...  Returns (received columns, recv_counts); rows arrive
+        ordered by sending rank.  All columns and peers travel in ONE group of point-to-point operations (one NCCL
+        launch).  ``pad_rows``: zero rows appended to every received column (tile padding of the scan kernels)."""
         import torch
 
         if self.world == 1:
             return [c[:send_counts[0]].clone() for c in columns], [int(send_counts[0])]
         import torch.distributed as dist
 
-        matrix = self.all_gather_object([int(c) for c in send_counts])
+        if matrix is None:
+            matrix = self.all_gather_counts(send_counts)
         send, recv = exchange_plan(matrix, self.rank)
         total = sum(recv)
-        out = []
+        send_off = [sum(send[:d]) for d in range(self.world)]
+        recv_off = [sum(recv[:s]) for s in range(self.world)]
+        out, ops = [], []
         for col in columns:
-            dst = torch.empty(total, dtype=col.dtype, device=col.device)
-            src = col[:sum(send)].contiguous()
-            if dist.get_backend() == "gloo":  # gloo has no all_to_all_single: emulate with per-peer broadcasts of slices
-                pieces = self.all_gather_object(src.cpu())
-                offs = 0
-                for s in range(self.world):
-                    lo = sum(matrix[s][:self.rank])
-                    n = matrix[s][self.rank]
-                    dst[offs:offs + n] = pieces[s][lo:lo + n].to(dst.device)
-                    offs += n
-            else:
-                dist.all_to_all_single(dst, src, output_split_sizes=recv, input_split_sizes=send)
+            dst = torch.zeros(total + pad_rows, dtype=col.dtype, device=col.device)
             out.append(dst)
-        return out, recv
+            me = self.rank
+            dst[recv_off[me]:recv_off[me] + recv[me]] = col[send_off[me]:send_off[me] + send[me]]
+            for peer in range(self.world):
+                if peer == me:
+                    continue
+                if send[peer]:
+                    ops.append(dist.P2POp(dist.isend, col[send_off[peer]:send_off[peer] + send[peer]], peer))
+                if recv[peer]:
+                    ops.append(dist.P2POp(dist.irecv, dst[recv_off[peer]:recv_off[peer] + recv[peer]], peer))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return [c[:total] if pad_rows == 0 else c for c in out], recv
+
+
+class PeerShuffle:
+    """Host side of the library's row exchange over NVLink peer memory (csrc/shuffle.cu, msc_shuffle_*).
+
+    Created collectively by all ranks.  ``exchange`` = one shuffle of a device relation: rows travel to rank
+    ``hash(key) % world`` (or, with ``key_col=None``, every row to every rank: the all-gather of small partial results).
+    Receive buffers ("slots") live as long as the engine; they only grow, and because every rank sees the same
+    rows[src][dst] matrix all ranks take the same sizing decisions without another message.  A slot is busy until the
+    query that received into it releases it (:meth:`release_all`)."""
+
+    GRANULE = 2 << 20
+
+    def __init__(self, ctx: Any, comm: "Comm") -> None:
+        import ctypes as C
+
+        self.ctx, self.comm = ctx, comm
+        self.handle = C.c_void_p()
+        self.epoch = 0
+        self.table_epoch = 0
+        self.slot_bytes: dict[int, int] = {}
+        self.busy: set[int] = set()
+        self.last_matrix: list[list[int]] = []
+        ipc = C.create_string_buffer(64)
+        ok = True
+        try:
+            ctx.call("msc_shuffle_create", comm.rank, comm.world, C.byref(self.handle), ipc)
+        except Exception:  # noqa: BLE001  (no IPC on this system: every rank must learn it)
+            ok = False
+        everyone = comm.all_gather_object((ok, bytes(ipc.raw)))
+        if ok and all(o for o, _ in everyone):
+            try:
+                ctx.check(ctx.lib.msc_shuffle_attach(self.handle, b"".join(h for _, h in everyone)))
+            except Exception:  # noqa: BLE001
+                ok = False
+        else:
+            ok = False
+        self.ok = all(comm.all_gather_object(ok))
+        if not self.ok:
+            self.close()
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.msc_shuffle_free(self.handle)
+            self.handle = None
+
+    def release_all(self) -> None:
+        self.busy.clear()
+
+    def _ensure_slot(self, slot: int, want: int) -> None:
+        """Collective: every rank calls it with the same arguments."""
+        import ctypes as C
+
+        if self.slot_bytes.get(slot, 0) >= want:
+            return
+        size = -(-max(want + want // 4, 16 * self.GRANULE) // self.GRANULE) * self.GRANULE
+        if slot in self.slot_bytes:  # peers must unmap the old buffer before its owner frees it
+            self.ctx.check(self.ctx.lib.msc_shuffle_slot_detach(self.handle, slot))
+            self.comm.barrier()
+        ipc = C.create_string_buffer(64)
+        self.ctx.check(self.ctx.lib.msc_shuffle_slot_alloc(self.handle, slot, size, ipc))
+        handles = self.comm.all_gather_object(bytes(ipc.raw))
+        self.ctx.check(self.ctx.lib.msc_shuffle_slot_attach(self.handle, slot, b"".join(handles)))
+        self.slot_bytes[slot] = size
+
+    def exchange(self, rel_handle: int, key_col: Optional[int]) -> tuple[int, int]:
+        """-> (handle of the received relation -- it wraps the slot, free it with msc_rel_free --, rows received)."""
+        import ctypes as C
+
+        world = self.comm.world
+        self.epoch += 1
+        matrix = (C.c_uint64 * (world * world))()
+        need = (C.c_uint64 * world)()
+        self.ctx.check(self.ctx.lib.msc_shuffle_begin(self.handle, C.c_void_p(rel_handle), -1 if key_col is None else key_col, self.epoch,
+                                                      matrix, need))
+        slot = next(i for i in range(64) if i not in self.busy)
+        self._ensure_slot(slot, max(need))
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.lib.msc_shuffle_finish(self.handle, slot, self.epoch, C.byref(out)))
+        self.busy.add(slot)
+        self.last_matrix = [[int(matrix[s * world + d]) for d in range(world)] for s in range(world)]
+        return out.value, sum(row[self.comm.rank] for row in self.last_matrix)
+
+    def allgather_table(self, src_ptr: int, nbytes: int, dst_ptr: int) -> None:
+        """`nbytes` from every rank into dst[world][nbytes] (device), stream-ordered, no host wait."""
+        import ctypes as C
+
+        self.table_epoch += 1
+        self.ctx.check(self.ctx.lib.msc_shuffle_allgather(self.handle, C.c_void_p(src_ptr), nbytes, self.table_epoch, C.c_void_p(dst_ptr)))

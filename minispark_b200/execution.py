@@ -31,7 +31,7 @@ from typing import TYPE_CHECKING, Any, Iterable, Optional
 
 from . import lowering as L
 from . import native as N
-from .distributed import Comm, invert_code_maps, unify_keys
+from .distributed import Comm, PeerShuffle, invert_code_maps, shard_blocks, unify_keys
 from .constants import ColumnType, Row, Schema
 from .io import BlockFile
 from .jobs import JobResult, OutputFile
@@ -78,7 +78,11 @@ class ExecutionEngine(AbstractContextManager, ABC):
 class DictHandle:
     """A device string dictionary plus host-side caches of the tables derived from it."""
 
+    _serials = 0
+
     def __init__(self, ctx: N.Context, handle: Optional[int] = None) -> None:
+        DictHandle._serials += 1
+        self.serial = DictHandle._serials  # never reused, unlike id(): cache keys of derived tables must not alias
         self.ctx = ctx
         if handle is None:
             h = C.c_void_p()
@@ -87,6 +91,7 @@ class DictHandle:
         self.handle = handle
         self._luts: dict[tuple, int] = {}
         self._codes: dict[tuple, int] = {}
+        self._translated_from: list[tuple["DictHandle", tuple]] = []  # translation tables other dictionaries cache INTO this one
 
     @property
     def size(self) -> int:
@@ -116,11 +121,16 @@ class DictHandle:
 
     def translate_lut(self, target: "DictHandle", insert: bool = False) -> int:
         """u32 LUT mapping this dictionary's codes to ``target``'s codes."""
-        key = ("tr", id(target), self.size, target.size, insert)
+        key = ("tr", target.serial, self.size, target.size, insert)
         if key not in self._luts or insert:
             out = C.c_void_p()
             self.ctx.call("msc_dict_translate", C.c_void_p(self.handle), C.c_void_p(target.handle), int(insert), C.byref(out))
-            self._luts[("tr", id(target), self.size, target.size, insert)] = out.value
+            key = ("tr", target.serial, self.size, target.size, insert)
+            stale = self._luts.pop(key, None)
+            if stale:
+                self.ctx.dev_free(stale)
+            self._luts[key] = out.value
+            target._translated_from.append((self, key))
             return out.value
         return self._luts[key]
 
@@ -156,6 +166,13 @@ class DictHandle:
             for ptr in self._luts.values():
                 self.ctx.dev_free(ptr)
             self._luts.clear()
+            # translation tables that map INTO this dictionary die with it (a long-lived table dictionary would otherwise
+            # keep one per query-scoped target)
+            for source, key in self._translated_from:
+                ptr = source._luts.pop(key, None) if source.handle else None
+                if ptr:
+                    self.ctx.dev_free(ptr)
+            self._translated_from.clear()
             self.ctx.lib.msc_dict_free(C.c_void_p(self.handle))
             self.handle = None
 
@@ -179,6 +196,9 @@ class DeviceRel:
         self.nrows = nrows
         self.cols = cols
         self.keep = keep or []  # relations / dictionaries whose memory these columns reference
+        # several ranks: True = this rank holds only its part of the relation (the rank-ordered union is the relation),
+        # False = every rank holds all of it
+        self.partitioned = False
 
     @classmethod
     def from_handle(cls, ctx: N.Context, handle: int, ltypes: list[str], dicts: list[Optional[DictHandle]]) -> "DeviceRel":
@@ -223,11 +243,12 @@ class _Source:
     """Input of one fused scan: ``nrows`` rows whose column ``i`` is ``columns[i]``."""
 
     def __init__(self, nrows: int, columns: dict[int, DeviceColumn], index_vectors: Optional[list[DeviceColumn]] = None,
-                 keep: Optional[list] = None) -> None:
+                 keep: Optional[list] = None, partitioned: bool = False) -> None:
         self.nrows = nrows
         self.columns = columns
         self.index_vectors = index_vectors or []
         self.keep = keep or []
+        self.partitioned = partitioned  # see DeviceRel.partitioned
 
 
 class _ScanResolver:
@@ -389,7 +410,11 @@ class CudaExecutionEngine(ExecutionEngine):
             comm = _comm_from_torch(device)
         self.comm = comm
         self.shard = shard if shard is not None else (comm.rank, comm.world)
-        self.replicate_results = True  # multi-rank: every rank ends up with the complete result
+        # several ranks: collect() / execute_full_task return the COMPLETE result on every rank (rows a rank does not hold
+        # -- a sharded scan's, a partitioned GROUP BY's or join's -- are gathered in rank order); execute_to_device leaves
+        # the rank-local part on the device unless asked (last_stats["result_partitioned"] says which it is)
+        self.replicate_results = True
+        self._shuffle: Any = None  # PeerShuffle once several ranks exchange rows; False when CUDA IPC is unavailable
         self._own_work = work_folder is None
         self.work_folder = Path(work_folder) if work_folder is not None else Path(tempfile.mkdtemp(prefix="minispark_cuda_"))
         self.work_folder.mkdir(parents=True, exist_ok=True)
@@ -403,9 +428,9 @@ class CudaExecutionEngine(ExecutionEngine):
 
     # ---- ExecutionEngine contract ---------------------------------------------------------------
     def execute_full_task(self, full_task: Any) -> list[JobResult]:
-        rel, schema = self.execute_to_device(full_task)
+        rel, schema = self.execute_to_device(full_task, replicate=self.replicate_results)
         try:
-            job = JobResult(str(uuid.uuid4()), f"cuda:{self.device}", [])
+            job = JobResult(str(uuid.uuid4()), f"cuda:{self.device}", [], result_partitioned=rel.partitioned)
             if rel.nrows > 0:  # empty result -> no output file (reference tasks.py:405-406)
                 path = self.work_folder / f"result_{job.job_id}.bin"
                 self.write_blockfile(rel, schema, path)
@@ -425,6 +450,9 @@ class CudaExecutionEngine(ExecutionEngine):
         for closer in getattr(self, "_closers", []):
             closer()
         self._closers = []
+        if getattr(self, "_shuffle", None):
+            self._shuffle.close()
+        self._shuffle = None
         for entry in self._tables.values():
             for rel in entry.rels:
                 rel.free()
@@ -448,15 +476,20 @@ class CudaExecutionEngine(ExecutionEngine):
             pass
 
     # ---- public extras ----------------------------------------------------------------------------
-    def execute_to_device(self, full_task: Any) -> tuple[DeviceRel, Schema]:
-        """Run the query and leave the (full-precision) result on the device."""
+    def execute_to_device(self, full_task: Any, replicate: bool = False) -> tuple[DeviceRel, Schema]:
+        """Run the query and leave the (full-precision) result on the device.  Several ranks: a result that is spread
+        over the ranks (``rel.partitioned``) stays so unless ``replicate`` asks for the rank-ordered gather."""
         try:
             task = deepcopy(full_task)  # planning mutates the tree (reference plan.py:181-204)
             task.validate_schema()      # the reference's own validation and its errors
             plan = L.lower_task(task)
             self.last_plan = plan
             t0 = time.perf_counter()
+            self.last_stats["exchange"] = None
             rel = self._run(plan)
+            if replicate and rel.partitioned:
+                rel = self._gather_rows(rel)
+            self.last_stats["result_partitioned"] = rel.partitioned
             self.last_stats["query_s"] = time.perf_counter() - t0
             return rel, plan.schema
         except N.NativeError as e:
@@ -473,6 +506,8 @@ class CudaExecutionEngine(ExecutionEngine):
         for d in self._query_dicts:
             d.free()
         self._query_dicts.clear()
+        if self._shuffle:
+            self._shuffle.release_all()
 
     def write_blockfile(self, rel: DeviceRel, schema: Schema, path: Path) -> None:
         from . import io as _io  # noqa: PLC0415
@@ -520,7 +555,7 @@ class CudaExecutionEngine(ExecutionEngine):
             self.ctx.check(self.ctx.lib.msc_table_col_info(C.c_void_p(handle), c, C.byref(ty), buf, 256))
             schema.append((buf.value.decode("utf-8"), ColumnType.from_ordinal(ty.value)))
         rank, world = self.shard
-        blocks = [b for b in range(nblocks.value) if b % world == rank]
+        blocks = shard_blocks(nblocks.value, rank, world)
         local_rows = 0
         for b in blocks:
             rows = C.c_uint32()
@@ -590,11 +625,11 @@ class CudaExecutionEngine(ExecutionEngine):
         if isinstance(node, L.LTable):
             entry = self._table(node.path)
             self._ensure_columns(entry, needed)
-            return _Source(entry.nrows, {i: entry.columns[i] for i in needed})
+            return _Source(entry.nrows, {i: entry.columns[i] for i in needed}, partitioned=self.comm.world > 1)
         if isinstance(node, L.LJoin):
             return self._join_source(node, needed)
         rel = self._run(node)
-        return _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel])
+        return _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel], partitioned=rel.partitioned)
 
     def _prepare(self, base: L.LNode, exprs: list[L.Expr]) -> tuple[_Source, list[L.Expr]]:
         """Resolve the scan input and materialise string concatenations the program cannot compute."""
@@ -664,7 +699,9 @@ class CudaExecutionEngine(ExecutionEngine):
         phys = N.int32_array(prog.out_phys)
         self.ctx.call("msc_scan_project", C.byref(desc), phys, len(prog.out_phys), C.byref(out))
         self._note_kernel()
-        return self._track(DeviceRel.from_handle(self.ctx, out.value, ltypes, prog.out_dicts))
+        rel = self._track(DeviceRel.from_handle(self.ctx, out.value, ltypes, prog.out_dicts))
+        rel.partitioned = resolver.source.partitioned
+        return rel
 
     def _note_kernel(self) -> None:
         st = self.ctx.stats()
@@ -708,12 +745,13 @@ class CudaExecutionEngine(ExecutionEngine):
         # raw result: key + one column per unique accumulator slot; expose it in the aggregate's schema order
         slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog.agg_kinds]
         self.last_stats["agg_mode"] = "dense" if ngroups else "hash"
-        if ngroups and self.comm.world > 1:  # dense tables merge across ranks without moving rows (_DenseMerge)
+        spread = source.partitioned and self.comm.world > 1  # the rows are spread over the ranks: partial results must merge
+        partitioned = False
+        if ngroups and spread:  # dense tables merge across ranks without moving rows (_DenseMerge)
             merge = _DenseMerge(self, prog.group_dict, desc, kinds, len(prog.agg_kinds))
             handle, _ = merge.run(desc)
             self._note_kernel()
-            self.last_stats["exchange"] = "all_gather"
-            self.last_stats["result_partitioned"] = False
+            self.last_stats["exchange"] = merge.exchange_kind
             raw = self._track(DeviceRel.from_handle(self.ctx, handle, [group.type, *slot_types], [merge.global_dict] + [None] * len(slot_types)))
         else:
             out = C.c_void_p()
@@ -722,13 +760,16 @@ class CudaExecutionEngine(ExecutionEngine):
             self.last_stats["agg_scan_kind"] = self.last_stats["scan_kind"]  # later scans (final projection) overwrite scan_kind
             self.last_stats["agg_scan_ms"] = self.last_stats["scan_ms"]
             raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
-            if self.comm.world > 1:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
+            if spread:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
                 raw = self._merge_partials(raw, prog.agg_kinds, slot_types, group.type)
+                partitioned = raw.partitioned
         key = raw.cols[0]
         if group.type == L.FLOAT and key.phys == N.P_I64:
             key = DeviceColumn(key.ptr, N.P_F64, L.FLOAT)  # hash mode stores the f64 bit pattern
         cols = [key] + [raw.cols[1 + s] for s in prog.slot_of]
-        return DeviceRel(self.ctx, None, raw.nrows, cols, keep=[raw, *source.keep])
+        rel = DeviceRel(self.ctx, None, raw.nrows, cols, keep=[raw, *source.keep])
+        rel.partitioned = partitioned
+        return rel
 
     def _dense_groups(self, prog: L.AggregateProgram) -> tuple[int, int]:
         """(groups of the dense table or 0 for hash mode, capacity hint).  Dense mode needs a dictionary-coded key and a
@@ -769,11 +810,11 @@ class CudaExecutionEngine(ExecutionEngine):
             targets = {"join": key_dict}
             rkey = L.ETranslate(L.STR, rkey, "join")
         rrel = side(join.right, right_needed, rkey, targets)
+        partitioned = False
         if self.comm.world > 1:  # the reference shuffles both sides on the key (plan.py:186-189): same here, over NVLink
             lrel = self._exchange_on_key(lrel)
             rrel = self._exchange_on_key(rrel)
-            self.last_stats["exchange"] = "all_to_all"
-            self.last_stats["result_partitioned"] = True
+            partitioned = True
         pairs = C.c_void_p()
         self.ctx.call("msc_hash_join", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.c_void_p(rrel.cols[-1].ptr), rrel.nrows, C.byref(pairs))
         self._note_kernel()
@@ -785,7 +826,7 @@ class CudaExecutionEngine(ExecutionEngine):
         for pos, i in enumerate(right_needed):
             c = rrel.cols[pos]
             columns[nl + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via=1)
-        return _Source(prel.nrows, columns, index_vectors=[prel.cols[0], prel.cols[1]], keep=[lrel, rrel, prel])
+        return _Source(prel.nrows, columns, index_vectors=[prel.cols[0], prel.cols[1]], keep=[lrel, rrel, prel], partitioned=partitioned)
 
     def _unified_dictionary(self, local: DictHandle) -> DictHandle:
         """The same dictionary on every rank: the sorted union of all ranks' entries (code = position)."""
@@ -794,34 +835,128 @@ class CudaExecutionEngine(ExecutionEngine):
         self._query_dicts.append(unified)
         return unified
 
-    def _exchange_on_key(self, rel: DeviceRel) -> DeviceRel:
-        """Multi-rank join: send every row to rank hash(key) % world (key = last column, an integer), so that equal
-        keys of both sides meet on one GPU.  STR columns are re-coded into rank-independent dictionaries first."""
+    def _rank_independent(self, rel: DeviceRel) -> DeviceRel:
+        """STR columns re-coded into dictionaries that are the same on every rank, so that codes can travel."""
+        recode = [c.dict is not None and c.ltype == L.STR for c in rel.cols]
+        if not any(recode):
+            return rel
+        ltypes = [c.ltype for c in rel.cols]
+        targets: dict[str, DictHandle] = {}
+        outs: list[L.Expr] = []
+        for i, c in enumerate(rel.cols):
+            if not recode[i]:
+                outs.append(L.EInput(c.ltype, i))
+                continue
+            targets[f"x{i}"] = self._unified_dictionary(c.dict)
+            outs.append(L.ETranslate(L.STR, L.EInput(L.STR, i), f"x{i}"))
+        source = _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel], partitioned=rel.partitioned)
+        resolver = _ScanResolver(self, source, targets)
+        return self._scan_project(resolver, L.compile_project(resolver, [], outs), ltypes)
+
+    def _local_part(self, rel: DeviceRel) -> DeviceRel:
+        """A relation every rank holds in full enters an exchange from rank 0 only (the other ranks contribute no rows)."""
+        if rel.partitioned or self.comm.rank == 0:
+            return rel
+        out = C.c_void_p()
+        self.ctx.call("msc_rel_alloc", 0, N.int32_array([c.phys for c in rel.cols]), len(rel.cols), C.byref(out))
+        return self._track(DeviceRel.from_handle(self.ctx, out.value, [c.ltype for c in rel.cols], [c.dict for c in rel.cols]))
+
+    def _materialised(self, rel: DeviceRel) -> DeviceRel:
+        """The relation as ONE library relation of directly readable columns (exchanges take an msc_rel)."""
+        if rel.handle and all(c.via is None for c in rel.cols):
+            return rel
+        binds = (N.ColBind * max(len(rel.cols), 1))()
+        for i, c in enumerate(rel.cols):
+            binds[i].data, binds[i].phys = c.ptr, c.phys
+        out = C.c_void_p()
+        self.ctx.call("msc_rel_wrap", rel.nrows, binds, len(rel.cols), C.byref(out))
+        wrapped = self._track(DeviceRel.from_handle(self.ctx, out.value, [c.ltype for c in rel.cols], [c.dict for c in rel.cols]))
+        wrapped.keep.append(rel)
+        wrapped.partitioned = rel.partitioned
+        return wrapped
+
+    def _peer_shuffle(self) -> Any:
+        """The library's exchange over NVLink peer memory, set up collectively on first use (False: not available)."""
+        if self._shuffle is None:
+            self._shuffle = False
+            if os.environ.get("MINISPARK_PEER_EXCHANGE", "1") != "0":
+                sh = PeerShuffle(self.ctx, self.comm)
+                if sh.ok:
+                    self._shuffle = sh
+        return self._shuffle
+
+    def _exchange_rows(self, rel: DeviceRel, key_col: Optional[int]) -> DeviceRel:
+        """One shuffle: every row to rank hash(column key_col) % world, or with key_col None every row to every rank
+        (rows arrive ordered by sending rank, then input order).  The reference writes and re-reads shuffle files here
+        (tasks.py:347-375, 144-150); this is a push over NVLink into the receiver's memory (csrc/shuffle.cu), or one group
+        of NCCL sends / receives where CUDA IPC is unavailable."""
+        rel = self._materialised(rel)
+        ltypes, dicts = [c.ltype for c in rel.cols], [c.dict for c in rel.cols]
+        sh = self._peer_shuffle()
+        t0 = time.perf_counter()
+        if sh:
+            handle, _ = sh.exchange(rel.handle, key_col)
+            out = self._track(DeviceRel.from_handle(self.ctx, handle, ltypes, dicts))
+            out.keep.append(rel)
+            self.last_stats["exchange"] = "nvlink peer push" + (" (all rows to all ranks)" if key_col is None else " (hash partitioned)")
+            matrix = sh.last_matrix
+        else:
+            out, matrix = self._exchange_rows_nccl(rel, key_col)
+            self.last_stats["exchange"] = "nccl send/recv group" + (" (all rows to all ranks)" if key_col is None else " (hash partitioned)")
+        widths = sum(N.PHYS_WIDTH[c.phys] for c in rel.cols)
+        me = self.comm.rank
+        self.last_stats["exchange_rows_sent"] = sum(n for d, n in enumerate(matrix[me]) if d != me)
+        self.last_stats["exchange_bytes_sent"] = self.last_stats["exchange_rows_sent"] * widths
+        self.last_stats["exchange_host_s"] = time.perf_counter() - t0
+        out.partitioned = key_col is not None
+        return out
+
+    def _exchange_rows_nccl(self, rel: DeviceRel, key_col: Optional[int]) -> tuple[DeviceRel, list[list[int]]]:
         import torch  # noqa: PLC0415
 
         comm = self.comm
-        ltypes = [c.ltype for c in rel.cols]
-        # (the key column is an integer already: a STR key was coded in the unified key dictionary by the caller)
-        recode = [c.dict is not None and c.ltype == L.STR for c in rel.cols]
-        if any(recode):
-            targets: dict[str, DictHandle] = {}
-            outs: list[L.Expr] = []
-            for i, c in enumerate(rel.cols):
-                if not recode[i]:
-                    outs.append(L.EInput(c.ltype, i))
-                    continue
-                targets[f"x{i}"] = self._unified_dictionary(c.dict)
-                outs.append(L.ETranslate(L.STR, L.EInput(L.STR, i), f"x{i}"))
-            source = _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel])
-            resolver = _ScanResolver(self, source, targets)
-            rel = self._scan_project(resolver, L.compile_project(resolver, [], outs), ltypes)
-        counts = (C.c_uint64 * comm.world)()
-        part = C.c_void_p()
-        self.ctx.call("msc_partition", C.c_void_p(rel.handle), len(rel.cols) - 1, comm.world, counts, C.byref(part))
-        prel = self._track(DeviceRel.from_handle(self.ctx, part.value, ltypes, [c.dict for c in rel.cols]))
-        cols, _ = comm.all_to_all_rows([self._torch_column(c, prel.nrows) for c in prel.cols], [int(c) for c in counts])
-        torch.cuda.synchronize(self.device)
-        return self._rel_from_torch(cols, [c.phys for c in prel.cols], ltypes, [c.dict for c in prel.cols])
+        if key_col is None:
+            prel, counts = rel, [rel.nrows] * comm.world
+            cols = [self._torch_column(c, rel.nrows).repeat(comm.world) for c in rel.cols]
+        else:
+            host_counts = (C.c_uint64 * comm.world)()
+            part = C.c_void_p()
+            self.ctx.call("msc_partition", C.c_void_p(rel.handle), key_col, comm.world, host_counts, C.byref(part))
+            prel = self._track(DeviceRel.from_handle(self.ctx, part.value, [c.ltype for c in rel.cols], [c.dict for c in rel.cols]))
+            counts = [int(c) for c in host_counts]
+            cols = [self._torch_column(c, prel.nrows) for c in prel.cols]
+        stream = C.c_void_p()
+        self.ctx.call("msc_stream_handle", C.byref(stream))
+        dev = torch.device("cuda", self.device)
+        matrix = comm.all_gather_counts(counts)
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream.value, device=dev)):  # ordered with the library's own work
+            pad = 2 * 8192  # tile padding the scan kernels may read past the last row (common.cuh MSC_ROW_PAD)
+            received, _ = comm.all_to_all_rows(cols, counts, pad_rows=pad, matrix=matrix)
+        nrows = sum(row[comm.rank] for row in matrix)
+        binds = (N.ColBind * max(len(received), 1))()
+        for i, (t, c) in enumerate(zip(received, prel.cols)):
+            binds[i].data, binds[i].phys = t.data_ptr(), c.phys
+        out = C.c_void_p()
+        self.ctx.call("msc_rel_wrap", nrows, binds, len(received), C.byref(out))
+        got = self._track(DeviceRel.from_handle(self.ctx, out.value, [c.ltype for c in prel.cols], [c.dict for c in prel.cols]))
+        got.keep.extend([received, prel])
+        return got, matrix
+
+    def _exchange_on_key(self, rel: DeviceRel) -> DeviceRel:
+        """Multi-rank join: send every row to rank hash(key) % world (key = last column, an integer), so that equal
+        keys of both sides meet on one GPU.  STR columns are re-coded into rank-independent dictionaries first.
+        (the key column is an integer already: a STR key was coded in the unified key dictionary by the caller)"""
+        rel = self._local_part(self._rank_independent(rel))
+        return self._exchange_rows(rel, len(rel.cols) - 1)
+
+    def _gather_rows(self, rel: DeviceRel) -> DeviceRel:
+        """The complete relation on every rank: the rank-local parts concatenated in rank order (for sharded scans that is
+        the table's row order, see distributed.shard_blocks)."""
+        if self.comm.world == 1 or not rel.partitioned:
+            return rel
+        out = self._exchange_rows(self._rank_independent(rel), None)
+        out.partitioned = False
+        return out
 
     # ---- prepared queries ------------------------------------------------------------------------------
     def prepare(self, full_task: Any) -> "PreparedAggregate":
@@ -843,25 +978,10 @@ class CudaExecutionEngine(ExecutionEngine):
         raw = torch.as_tensor(_DevView(col.ptr, nrows * width), device=f"cuda:{self.device}")
         return raw[: nrows * width].view(_torch_dtype(col.phys))
 
-    def _rel_from_torch(self, columns: list, physes: list[int], ltypes: list[str], dicts: list) -> DeviceRel:
-        """Library-owned, tile-padded relation filled from torch tensors (rows received from other ranks)."""
-        import torch  # noqa: PLC0415
-
-        nrows = int(columns[0].shape[0]) if columns else 0
-        out = C.c_void_p()
-        self.ctx.call("msc_rel_alloc", nrows, N.int32_array(physes), len(physes), C.byref(out))
-        rel = self._track(DeviceRel.from_handle(self.ctx, out.value, ltypes, dicts))
-        for col, src in zip(rel.cols, columns):
-            if nrows:
-                self._torch_column(col, nrows).copy_(src.view(_torch_dtype(col.phys)))
-        torch.cuda.synchronize(self.device)
-        return rel
-
     def _merge_partials(self, raw: DeviceRel, agg_kinds: list[int], slot_types: list[str], group_type: str) -> DeviceRel:
-        """Combine per-rank partial aggregates: small tables are all-gathered and re-aggregated on every
-        GPU; large ones are hash-partitioned on the key (msc_partition) and exchanged with one all-to-all."""
-        import torch  # noqa: PLC0415
-
+        """Combine per-rank partial aggregates (the reference's shuffle + final aggregate, plan.py:190-199): small tables
+        go to every rank and are re-aggregated there; large ones are hash-partitioned on the key and exchanged
+        (_exchange_rows), which leaves every rank with the final groups of its share of the keys."""
         comm = self.comm
         key_dict = raw.cols[0].dict
         global_dict = None
@@ -875,18 +995,8 @@ class CudaExecutionEngine(ExecutionEngine):
             outs += [L.EInput(t, i + 1) for i, t in enumerate(slot_types)]
             prog = L.compile_project(resolver, [], outs)
             raw = self._scan_project(resolver, prog, [L.INT, *slot_types])
-        physes = [N.P_I64] + [N.P_F64 if t == L.FLOAT else N.P_I64 for t in slot_types]
-        small = comm.max_int(raw.nrows) <= int(os.environ.get("MSC_EXCHANGE_GATHER_MAX", "65536"))
-        if small:
-            cols, _ = comm.all_gather_rows([self._torch_column(c, raw.nrows) for c in raw.cols], raw.nrows)
-        else:
-            counts = (C.c_uint64 * comm.world)()
-            part = C.c_void_p()
-            self.ctx.call("msc_partition", C.c_void_p(raw.handle), 0, comm.world, counts, C.byref(part))
-            prel = self._track(DeviceRel.from_handle(self.ctx, part.value, [c.ltype for c in raw.cols], [None] * len(raw.cols)))
-            cols, _ = comm.all_to_all_rows([self._torch_column(c, prel.nrows) for c in prel.cols], [int(c) for c in counts])
-        torch.cuda.synchronize(self.device)
-        gathered = self._rel_from_torch(cols, physes, [L.INT, *slot_types], [None] * len(physes))
+        small = max(r[0] for r in comm.all_gather_counts([raw.nrows])) <= int(os.environ.get("MSC_EXCHANGE_GATHER_MAX", "65536"))
+        gathered = self._exchange_rows(raw, None if small else 0)
         # final aggregate over the partial rows: SUM of sums / counts, MIN of mins, MAX of maxes
         merge_kind = {N.K["MSC_AGG_SUM_F"]: "sum", N.K["MSC_AGG_SUM_I"]: "sum", N.K["MSC_AGG_MIN_F"]: "min", N.K["MSC_AGG_MIN_I"]: "min",
                       N.K["MSC_AGG_MAX_F"]: "max", N.K["MSC_AGG_MAX_I"]: "max"}
@@ -902,8 +1012,7 @@ class CudaExecutionEngine(ExecutionEngine):
         types2 = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog2.agg_kinds]
         merged = self._track(DeviceRel.from_handle(self.ctx, out.value, [group_type, *types2], [global_dict] + [None] * len(types2)))
         merged.cols = [merged.cols[0]] + [merged.cols[1 + s] for s in prog2.slot_of]
-        self.last_stats["exchange"] = "all_gather" if small else "all_to_all"
-        self.last_stats["result_partitioned"] = not small  # all_to_all leaves every rank with a disjoint key range
+        merged.partitioned = not small  # the hash-partitioned exchange leaves every rank with a disjoint set of keys
         return merged
 
 
@@ -911,7 +1020,8 @@ class _DenseMerge:
     """Cross-rank merge of a low-cardinality (dense) GROUP BY, set up once per query.
 
     Every rank scans its row-blocks into a [groups][stride] table of its own dictionary codes; the tables are
-    all-gathered (NCCL over NVLink: a few hundred bytes per rank), folded in rank order by ``msc_dense_merge`` through
+    all-gathered (a few hundred bytes per rank: one small kernel that stores into the peers' control blocks over NVLink,
+    msc_shuffle_allgather; NCCL where CUDA IPC is unavailable), folded in rank order by ``msc_dense_merge`` through
     per-rank code permutations into the unified dictionary, and compacted.  Every rank ends up with the complete,
     bit-identical result.  This is the reference's pre-aggregate -> shuffle -> final aggregate (plan.py:190-199)
     without a row ever leaving its GPU."""
@@ -953,6 +1063,9 @@ class _DenseMerge:
         engine.ctx.call("msc_stream_handle", C.byref(stream))
         self.stream = torch.cuda.ExternalStream(stream.value, device=dev)
         torch.cuda.synchronize(dev)
+        shuffle = engine._peer_shuffle()  # (collective on first use: every rank builds its _DenseMerge at the same point)
+        self.shuffle = shuffle if shuffle and cells * 8 <= N.K["MSC_SHUFFLE_TABLE_BYTES"] else None
+        self.exchange_kind = "nvlink peer stores (partial tables)" if self.shuffle else "nccl all-gather (partial tables)"
 
     def enqueue(self, desc: N.ScanDesc, exact: bool = False) -> int:
         """scan (enqueued) -> all-gather of the tables -> merge + compaction, all ordered on one stream and none waited
@@ -964,8 +1077,11 @@ class _DenseMerge:
         flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0) | (N.K["MSC_DENSE_JIT"] if self.persistent and e.jit != "never" else 0)
         if self.nlocal > 0:
             e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()), flags)
-        with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(self.gathered, self.local)
+        if self.shuffle:
+            self.shuffle.allgather_table(self.local.data_ptr(), self.local.numel() * 8, self.gathered.data_ptr())
+        else:
+            with torch.cuda.stream(self.stream):
+                dist.all_gather_into_tensor(self.gathered, self.local)
         out = C.c_void_p()
         e.ctx.call("msc_dense_merge_compact_async", C.c_void_p(self.gathered.data_ptr()), e.comm.world, self.gmax, self.stride, self.kinds,
                    self.naggs, C.c_void_p(self.perm_dev.data_ptr()), self.nglobal, self.count_slot, C.c_void_p(self.merged.data_ptr()),

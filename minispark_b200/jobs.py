@@ -24,3 +24,6 @@ class JobResult:
     job_id: str
     executor_id: str
     output_files: list[OutputFile] = field(default_factory=list)
+    # CudaExecutionEngine with several ranks and replicate_results=False: True = the files hold this rank's part of the
+    # result only (the union over ranks is the result); always False otherwise, as in the reference (jobs.py:27-31)
+    result_partitioned: bool = False

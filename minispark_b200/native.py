@@ -197,6 +197,17 @@ _SIGNATURES = {
     "msc_str_concat": (C.c_int, [C.c_void_p, C.POINTER(ConcatPart), C.c_int32, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_hash_join": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "msc_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]),
+    "msc_shuffle_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
+    "msc_shuffle_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msc_shuffle_slot_alloc": (C.c_int, [C.c_void_p, C.c_int32, C.c_size_t, C.c_void_p]),
+    "msc_shuffle_slot_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "msc_shuffle_slot_detach": (C.c_int, [C.c_void_p, C.c_int32]),
+    "msc_shuffle_slot_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]),
+    "msc_shuffle_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "msc_shuffle_finish": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "msc_shuffle_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "msc_shuffle_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),
+    "msc_shuffle_free": (None, [C.c_void_p]),
     "msc_rel_copy_column": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
     "msc_write_blockfile": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(OutCol), C.c_int32, C.c_char_p, C.c_uint32]),
 }

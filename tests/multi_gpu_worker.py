@@ -1,4 +1,7 @@
-"""Worker for tests/test_gpu_multi.py: run under torchrun with one rank per GPU (NCCL)."""
+"""Worker for tests/test_gpu_multi.py: run under torchrun, one rank per GPU (NCCL carries the rendezvous and the host-side
+metadata).  On a box with fewer GPUs than ranks the ranks SHARE a GPU: NCCL refuses two ranks on one device, so the
+rendezvous runs on gloo, and every row still moves the way it does between GPUs -- through the library's peer-memory
+exchange (CUDA IPC works between two processes on one device), only time-sliced."""
 
 from __future__ import annotations
 
@@ -24,8 +27,13 @@ from oracle import py_oracle as O  # noqa: E402
 
 def main() -> None:
     local_rank = int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    shared = torch.cuda.device_count() < int(os.environ["WORLD_SIZE"])
+    device = local_rank % torch.cuda.device_count()
+    torch.cuda.set_device(device)
+    if shared:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     rank, world = dist.get_rank(), dist.get_world_size()
     folder = Path(sys.argv[1])
     lineitem = folder / "lineitem.bin"
@@ -38,14 +46,17 @@ def main() -> None:
         return ns.DataFrame(engine).table(str(lineitem)).group_by(ns.Col("l_orderkey")).agg(
             ns.F.sum(ns.Col("l_quantity")).alias("q"), ns.F.avg(ns.Col("l_extendedprice")).alias("p"), ns.F.count())
 
-    with CudaExecutionEngine() as engine:
+    with CudaExecutionEngine(device=device) as engine:
         assert engine.shard == (rank, world)
-        # low-cardinality GROUP BY: partial tables merged with an all-gather, every rank gets the full answer
+        peer = os.environ.get("MINISPARK_PEER_EXCHANGE", "1") != "0"
+        # low-cardinality GROUP BY: partial tables merged on every rank, every rank gets the full answer
         got = cases.q1(ns, str(lineitem), engine).collect()
-        assert engine.last_stats["exchange"] == "all_gather"
+        assert engine.last_stats["exchange"].startswith("nvlink peer stores" if peer else "nccl all-gather"), engine.last_stats
+        assert engine.last_stats["result_partitioned"] is False
         O.assert_rows_equal(got, O.run_task(cases.q1(ns, str(lineitem)).task, wire=True), rel=5e-7)
-        # the same query prepared: pass 1 merges through NCCL, later passes exchange the partial tables over NVLink peer
-        # memory inside the specialised scan kernel (msc_dense_fused_peer); every rank must hold the same complete answer
+        # the same query prepared: pass 1 merges through the partial-table all-gather, later passes exchange the partial
+        # tables over NVLink peer memory inside the specialised scan kernel (msc_dense_fused_peer); every rank must hold
+        # the same complete answer
         prepared = engine.prepare(cases.q1(ns, str(lineitem)).task)
         want_f64 = {r["l_returnflag"]: r for r in O.run_task(cases.q1(ns, str(lineitem)).task, wire=False)}
         exchanges = []
@@ -63,23 +74,36 @@ def main() -> None:
                     assert abs(v - ref[name]) <= 1e-9 * max(abs(ref[name]), 1e-300), (k, name, v, ref[name])
         if os.environ.get("MINISPARK_PEER_MERGE", "1") != "0":
             assert exchanges[0] == "nccl" and all(x.startswith("nvlink") for x in exchanges[1:]), exchanges
-        # high-cardinality GROUP BY through hash partitioning + all-to-all: ranks hold disjoint key ranges
+        # high-cardinality GROUP BY through hash partitioning + the row exchange: ranks hold disjoint sets of keys ...
         os.environ["MSC_EXCHANGE_GATHER_MAX"] = "0"
-        part = high_card(engine).collect()
-        assert engine.last_stats["exchange"] == "all_to_all"
-        os.environ.pop("MSC_EXCHANGE_GATHER_MAX")
+        rel, schema = engine.execute_to_device(high_card(engine).task)
+        assert engine.last_stats["exchange"].startswith("nvlink peer push (hash" if peer else "nccl send/recv group (hash"), engine.last_stats
+        assert engine.last_stats["result_partitioned"] is True and rel.partitioned
+        assert engine.last_stats["exchange_rows_sent"] > 0
+        mine = rel.column_numpy(0).tolist()
+        engine.release_query()
         gathered: list = [None] * world
-        dist.all_gather_object(gathered, part)
-        merged = [row for rows in gathered for row in rows]
-        keys = [r["l_orderkey"] for r in merged]
+        dist.all_gather_object(gathered, mine)
+        keys = [k for part in gathered for k in part]
         assert len(keys) == len(set(keys)), "a key was aggregated on two ranks"
-        O.assert_rows_equal(merged, O.run_task(high_card(None).task, wire=True), rel=5e-7)
-        # filter / project scans stay rank-local: the union over ranks is the table
-        rows = ns.DataFrame(engine).table(str(lineitem)).filter(ns.Col("l_quantity") > 49).select(ns.Col("l_orderkey"), ns.Col("l_linenumber")).collect()
-        dist.all_gather_object(gathered, rows)
-        union = [row for rows_r in gathered for row in rows_r]
-        want = O.run_task(ns.DataFrame(None).table(str(lineitem)).filter(ns.Col("l_quantity") > 49).select(ns.Col("l_orderkey"), ns.Col("l_linenumber")).task)
-        O.assert_rows_equal(union, want)
+        # ... and collect() gathers them: every rank returns the complete result
+        full = high_card(engine).collect()
+        assert engine.last_stats["result_partitioned"] is False
+        os.environ.pop("MSC_EXCHANGE_GATHER_MAX")
+        assert sorted(r["l_orderkey"] for r in full) == sorted(keys)
+        O.assert_rows_equal(full, O.run_task(high_card(None).task, wire=True), rel=5e-7)
+        # the same through the small-table path (every partial row to every rank)
+        O.assert_rows_equal(high_card(engine).collect(), O.run_task(high_card(None).task, wire=True), rel=5e-7)
+        # filter / project scans run rank-local; collect() gathers the parts in rank order = the table's row order
+        def scan(e):  # noqa: ANN001, ANN202
+            return (ns.DataFrame(e).table(str(lineitem)).filter(ns.Col("l_quantity") > 49)
+                    .select(ns.Col("l_orderkey"), ns.Col("l_linenumber"), ns.Col("l_shipmode"), (ns.Col("l_extendedprice") * 2).alias("p2")))
+
+        rows = scan(engine).collect()
+        O.assert_rows_equal(rows, O.run_task(scan(None).task, wire=True), ordered=True)
+        rel, _ = engine.execute_to_device(scan(engine).task)
+        assert rel.partitioned and 0 < rel.nrows < len(rows)
+        engine.release_query()
         # JOIN: both sides are co-partitioned on the key (msc_partition + all-to-all), joined locally, and the
         # aggregate above merges the per-rank partials; string columns travel as codes of rank-independent dictionaries
         orders = folder / "orders.bin"
@@ -108,9 +132,19 @@ def main() -> None:
                     .select(ns.Col("o.o_orderkey"), ns.Col("o.o_orderstatus"), ns.Col("l.l_linenumber"), ns.Col("l.l_shipmode")))
 
         rows = join_rows(engine).collect()
-        dist.all_gather_object(gathered, rows)
-        union = [row for rows_r in gathered for row in rows_r]
-        O.assert_rows_equal(union, O.run_task(join_rows(None).task, wire=True))
+        O.assert_rows_equal(rows, O.run_task(join_rows(None).task, wire=True))
+        rel, _ = engine.execute_to_device(join_rows(engine).task)  # without the gather every rank holds the pairs of its keys
+        assert rel.partitioned
+        part_rows = [None] * world
+        dist.all_gather_object(part_rows, rel.nrows)
+        engine.release_query()
+        assert sum(part_rows) == len(rows) and max(part_rows) < len(rows)
+
+        def agg_then_join(e):  # noqa: ANN001, ANN202  -- a REPLICATED relation (a merged GROUP BY) as a join side: it must enter once
+            per_order = (ns.DataFrame(e).table(str(lineitem)).group_by(ns.Col("l_shipmode")).agg(ns.F.count().alias("n"))
+                         .select(ns.Col("l_shipmode").alias("mode2"), ns.Col("n")))
+            m = ns.DataFrame().table(str(folder / "modes.bin"))
+            return per_order.join(m, on=ns.Col("mode2") == ns.Col("mode"), how="inner")
 
         def join_str_key(e):  # noqa: ANN001, ANN202  -- string join key: lineitem's ship modes against a 3-row lookup table
             m = ns.DataFrame(e).table(str(folder / "modes.bin")).alias("m")
@@ -124,6 +158,8 @@ def main() -> None:
         dist.barrier()
         got = join_str_key(engine).collect()
         O.assert_rows_equal(got, O.run_task(join_str_key(None).task, wire=True), rel=5e-7)
+        got = agg_then_join(engine).collect()
+        O.assert_rows_equal(got, O.run_task(agg_then_join(None).task, wire=True))
     dist.barrier()
     if rank == 0:
         print("multi-gpu ok", world)

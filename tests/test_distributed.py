@@ -17,7 +17,8 @@ def test_shard_blocks_cover_every_block_once():
     for world in (1, 2, 3, 8):
         seen = sorted(b for r in range(world) for b in shard_blocks(43, r, world))
         assert seen == list(range(43))
-    assert shard_blocks(5, 1, 2) == [1, 3]
+    assert shard_blocks(5, 1, 2) == [2, 3, 4] and shard_blocks(5, 0, 2) == [0, 1]  # contiguous ranges: rank order = row order
+    assert [len(shard_blocks(43, r, 8)) for r in range(8)] == [5, 5, 6, 5, 5, 6, 5, 6]
     with pytest.raises(ValueError):
         shard_blocks(5, 2, 2)
 
