@@ -251,11 +251,53 @@ def write_stream(f: BinaryIO, schema: list[tuple[str, ColumnType]], blocks: Iter
     return total
 
 
+def _block_payloads(args: tuple) -> tuple[int, list[bytes]]:
+    """Worker of the parallel writer: one block's column payloads, serialised (generation is seed-stable per block)."""
+    table, sf, names, types, block_id, lo, hi, seed = args
+    if table == "lineitem":
+        cum = _block_payloads.cum  # type: ignore[attr-defined]
+        cols = lineitem_block(sf, block_id, lo, hi, cum, seed, names)
+    else:
+        cols = orders_block(sf, block_id, lo, hi, seed, names)
+    return hi - lo, [_payload(t, cols[n]) for n, t in zip(names, types)]
+
+
+def _init_worker(table: str, sf: float, seed: int) -> None:
+    _block_payloads.cum = np.cumsum(lines_per_order(sf, seed)) if table == "lineitem" else None  # type: ignore[attr-defined]
+
+
 def write_table(path: Path | str, table: str = "lineitem", sf: float = 1.0, columns: Optional[Sequence[str]] = None,
-                rows_per_block: int = ROWS_PER_BLOCK, seed: int = 1234, max_rows: Optional[int] = None) -> int:
-    schema, _, blocks = table_blocks(table, sf, columns, rows_per_block, seed, max_rows)
-    with open(path, "wb") as f:
-        return write_stream(f, schema, blocks)
+                rows_per_block: int = ROWS_PER_BLOCK, seed: int = 1234, max_rows: Optional[int] = None, workers: int = 1) -> int:
+    """Write the table as a BlockFile.  ``workers`` > 1 generates the row-blocks in that many processes (the bytes are the
+    same: every block has its own seed) and writes them in order."""
+    schema, total, blocks = table_blocks(table, sf, columns, rows_per_block, seed, max_rows)
+    nblocks = -(-total // rows_per_block)
+    if workers <= 1 or nblocks < 4:
+        with open(path, "wb") as f:
+            return write_stream(f, schema, blocks)
+    import multiprocessing as mp
+
+    names, types = [n for n, _ in schema], [t for _, t in schema]
+    jobs = [(table, sf, names, types, b, lo, min(lo + rows_per_block, total), seed) for b, lo in enumerate(range(0, total, rows_per_block))]
+    with open(path, "wb") as f, mp.get_context("fork").Pool(min(workers, nblocks), initializer=_init_worker, initargs=(table, sf, seed)) as pool:
+        header = bytearray((len(schema),))
+        for name, ctype in schema:
+            raw = name.encode("utf-8")
+            header += bytes((ctype.ordinal, len(raw))) + raw
+        f.write(header)
+        pos, starts, rows_total = len(header), [], 0
+        for rows, payloads in pool.imap(_block_payloads, jobs):
+            starts.append(pos)
+            f.write(struct.pack("<I", rows))
+            pos += 4
+            for payload in payloads:
+                f.write(struct.pack("<Q", len(payload)))
+                f.write(payload)
+                pos += 8 + len(payload)
+            rows_total += rows
+        f.write(np.asarray(starts, dtype="<u8").tobytes())
+        f.write(struct.pack("<I", len(starts)))
+    return rows_total
 
 
 def table_image(table: str = "lineitem", sf: float = 1.0, columns: Optional[Sequence[str]] = None,
@@ -275,11 +317,12 @@ def main() -> None:
     ap.add_argument("--rows-per-block", type=int, default=ROWS_PER_BLOCK)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--max-rows", type=int, default=None)
+    ap.add_argument("--workers", type=int, default=1)
     args = ap.parse_args()
     columns = None
     if args.columns:
         columns = Q1_COLUMNS if args.columns == "q1" else args.columns.split(",")
-    rows = write_table(args.out, args.table, args.sf, columns, args.rows_per_block, args.seed, args.max_rows)
+    rows = write_table(args.out, args.table, args.sf, columns, args.rows_per_block, args.seed, args.max_rows, args.workers)
     print(f"{args.out}: {rows} rows")
 
 

@@ -183,8 +183,9 @@ static int run_highcard(const char* path, const char* out_path) {
     const float* p = (const float*)blk.payload[c_p];
     /* pre-aggregation of this block (AggregateTask before the shuffle): sums in row order, f64 */
     table_t part;
-    table_init(&part, 2ULL * blk.rows + 64);
+    table_init(&part, 1 << 16);
     for (uint32_t r = 0; r < blk.rows; ++r) {
+      if (part.used * 2 >= part.cap) table_grow(&part);
       cell_t* c = table_find(&part, key[r]);
       c->sum_q += (double)q[r];
       c->sum_p += (double)p[r];
