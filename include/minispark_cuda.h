@@ -87,7 +87,10 @@ enum msc_opcode {
   MSC_OP_LUT8 = 27,  /* result = luts[B.index][A]  (u8 table: LIKE over dictionary codes) */
   MSC_OP_LUT32 = 28, /* result = luts[B.index][A]  (u32 table: code translation between dictionaries) */
   MSC_OP_RANK = 29,  /* no operands: fix each surviving row's stable output position (project scans) */
-  MSC_OP__COUNT = 30
+  MSC_OP_PROBE = 30, /* result = build-side row of key A in the join table luts[B.index] (msc_join_build), or -1: the probe
+                      * half of a hash join evaluated per scanned row (BroadcastHashJoinTask, tasks.py:219-240), for build
+                      * sides without duplicate keys */
+  MSC_OP__COUNT = 31
 };
 
 /* operand (source) kinds */
@@ -96,7 +99,9 @@ enum msc_opcode {
 #define MSC_SRC_STAGED 2 /* staged column `index` of the current row (converted from its physical type) */
 #define MSC_SRC_CONST 3  /* consts[index] */
 #define MSC_SRC_GATHER 4 /* gather column (index & 63) read through staged index vector (index >> 6) */
-#define MSC_SRC_LUT 5    /* luts[index]: only as operand B of LUT8 / LUT32 */
+#define MSC_SRC_LUT 5    /* luts[index]: only as operand B of LUT8 / LUT32 / PROBE */
+#define MSC_SRC_GATHER_T 6 /* gather column (index & 63) read through the row index held in TEMPORARY (index >> 6): the
+                            * build-side columns of a row that MSC_OP_PROBE matched (negative index: 0) */
 #define MSC_SRC_I2F 8    /* flag: convert the fetched i64 to f64 (INT->FLOAT coercion, sql.py:277-290) */
 
 /* destination kinds */
@@ -451,6 +456,12 @@ MSC_API int msc_str_concat(msc_ctx* ctx, const msc_concat_part* parts, int32_t n
  * one row per matching pair, right-row major like the reference. ---------------------------- */
 MSC_API int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nleft,
                   const int64_t* right_keys, uint64_t nright, msc_rel** out_pairs);
+
+/* The build half alone: key -> build row, for scans that carry the probe half in their row program (MSC_OP_PROBE with the
+ * table as a LUT operand, build-side columns read through MSC_SRC_GATHER_T).  *out_table is a relation that owns the table
+ * (free it with msc_rel_free; its one column's data pointer is what goes into msc_scan_desc.luts[]).  *unique == 0: some
+ * key occurs more than once on the build side -- such a join must use msc_hash_join, which emits every pair. */
+MSC_API int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, msc_rel** out_table, int32_t* unique);
 
 /* ---- shuffle partitioning: replaces WriteToShufflePartitions.write (tasks.py:347-375) and zig
  * fill_buckets (task_utils.zig:53-98).  Rows are routed by hash(key) % nparts; every column is

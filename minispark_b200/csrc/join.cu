@@ -11,23 +11,15 @@
 // (task_utils.zig:53-98): rows are routed by hash(key) % nparts into partition-contiguous order (stable: input order
 // inside every partition), ready for the exchange between ranks (shuffle.cu).
 #include "common.cuh"
+#include "join_table.cuh"
 
 namespace {
 
-constexpr unsigned long long J_EMPTY = 0x8000000000000000ULL;
-constexpr uint32_t NIL = 0xFFFFFFFFu;
+constexpr unsigned long long J_EMPTY = MSC_J_EMPTY;
+constexpr uint32_t NIL = MSC_J_NIL;
+using JoinSlot = MscJoinSlot;
 
-__device__ __forceinline__ unsigned long long norm_key(long long k) {
-  return (static_cast<unsigned long long>(k) == J_EMPTY) ? 0ULL : static_cast<unsigned long long>(k);
-}
-
-// One 16-byte slot per key: the key and the head of its chain of left rows share a sector, so an insert (CAS on the key,
-// exchange on the head) and a probe (one 128-bit load) touch one random sector each instead of two.
-struct __align__(16) JoinSlot {
-  unsigned long long key;
-  uint32_t head;
-  uint32_t len;  // left rows with this key: a probe knows its match count without walking the chain
-};
+__device__ __forceinline__ unsigned long long norm_key(long long k) { return msc_join_norm_key(k); }
 
 __global__ void join_init_kernel(JoinSlot* slots, uint64_t cap) {
   for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < cap;
@@ -41,7 +33,8 @@ __global__ void join_init_kernel(JoinSlot* slots, uint64_t cap) {
 }
 
 // build: key -> chain of left rows (slot.head -> next[row] -> ...)
-__global__ void join_build_kernel(const long long* keys, uint32_t n, JoinSlot* slots, uint32_t* next, uint64_t cap) {
+__global__ void join_build_kernel(const long long* keys, uint32_t n, JoinSlot* slots, uint32_t* next, uint64_t cap,
+                                  unsigned long long* duplicates = nullptr) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long k = norm_key(keys[i]);
@@ -52,8 +45,9 @@ __global__ void join_build_kernel(const long long* keys, uint32_t n, JoinSlot* s
     if (prev == J_EMPTY || prev == k) break;
     pos = (pos + 1) & mask;
   }
-  next[i] = atomicExch(&slots[pos].head, i);
-  atomicAdd(&slots[pos].len, 1u);
+  const uint32_t before = atomicExch(&slots[pos].head, i);
+  if (next) next[i] = before;
+  if (atomicAdd(&slots[pos].len, 1u) != 0 && duplicates) *duplicates = 1;  // (any writer stores the same value)
 }
 
 // chain head of key k (NIL: no match) and the chain's length
@@ -277,6 +271,46 @@ extern "C" int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nl
   cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
   ctx->stats.last_kernel_ms = ms;
   *out_pairs = rel;
+  return MSC_OK;
+}
+
+// The build half alone, for scans that probe per row (MSC_OP_PROBE): a 1-column relation that owns [header][slots].
+extern "C" int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, msc_rel** out_table, int32_t* unique) {
+  if (!ctx || !out_table || !unique || (nkeys && !keys)) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  if (nkeys >= NIL) return ctx->fail(MSC_ERR_ARG, "join side exceeds 2^32-1 rows");
+  uint64_t cap = 64;
+  while (cap < nkeys * 2) cap <<= 1;
+  msc_rel* rel = new msc_rel();
+  rel->ctx = ctx;
+  rel->nrows = cap;
+  msc_col c;
+  c.phys = MSC_P_U8;
+  c.bytes = sizeof(MscJoinTableHeader) + cap * sizeof(JoinSlot);
+  int rc = msc_alloc(ctx, c.bytes, &c.data);
+  if (rc != MSC_OK) {
+    delete rel;
+    return rc;
+  }
+  rel->cols.push_back(c);
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  MscJoinTableHeader h{cap, 0};
+  MSC_CUDA(ctx, cudaMemcpyAsync(c.data, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  JoinSlot* slots = reinterpret_cast<JoinSlot*>(static_cast<char*>(c.data) + sizeof(MscJoinTableHeader));
+  join_init_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(slots, cap);
+  ctx->stats.launches += 1;
+  if (nkeys) {
+    join_build_kernel<<<grid_for(nkeys, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(keys), static_cast<uint32_t>(nkeys), slots,
+                                                                   nullptr, cap, &static_cast<MscJoinTableHeader*>(c.data)->duplicates);
+    ctx->stats.launches += 1;
+  }
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  MSC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, c.data, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MSC_CUDA(ctx, cudaGetLastError());
+  *unique = ctx->h_scratch[1] == 0;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+  *out_table = rel;
   return MSC_OK;
 }
 

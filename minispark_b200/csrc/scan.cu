@@ -296,6 +296,9 @@ int validate_operand(msc_ctx* ctx, const msc_scan_desc* sd, uint32_t operand, bo
       if ((idx & 63) >= sd->ngather || (idx >> 6) >= sd->nstaged) return ctx->fail(MSC_ERR_ARG, "operand: bad gather column");
       if (sd->staged[idx >> 6].phys != MSC_P_U32) return ctx->fail(MSC_ERR_ARG, "operand: index vector must be U32");
       return MSC_OK;
+    case MSC_SRC_GATHER_T:
+      if ((idx & 63) >= sd->ngather || (idx >> 6) >= sd->ntemps) return ctx->fail(MSC_ERR_ARG, "operand: bad gather column / index temporary");
+      return MSC_OK;
     case MSC_SRC_LUT:
       if (!allow_lut) return ctx->fail(MSC_ERR_ARG, "operand: LUT reference outside a LUT instruction");
       return idx < sd->nluts ? MSC_OK : ctx->fail(MSC_ERR_ARG, "operand: bad LUT");
@@ -391,10 +394,10 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, const int3
     const uint32_t w1 = sd->code[pc + 1];
     if (op >= MSC_OP__COUNT) return ctx->fail(MSC_ERR_ARG, "unknown opcode");
     if (op == MSC_OP_RANK) continue;
-    const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+    const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || op == MSC_OP_PROBE;
     MSC_TRY(validate_operand(ctx, sd, w1 & 0xffffu, false));
     MSC_TRY(validate_operand(ctx, sd, w1 >> 16, lut));
-    if (lut && ((w1 >> 28) & 7) != MSC_SRC_LUT) return ctx->fail(MSC_ERR_ARG, "LUT instruction needs a LUT operand");
+    if (lut && ((w1 >> 28) & 7) != MSC_SRC_LUT) return ctx->fail(MSC_ERR_ARG, "LUT / PROBE instruction needs a LUT operand");
     const int tee = (w0 >> 9) & 0xf, dkind = (w0 >> 6) & 7, dst = (w0 >> 13) & 0x7f;
     if (tee > sd->ntemps) return ctx->fail(MSC_ERR_ARG, "tee: bad temporary");
     switch (dkind) {
@@ -419,6 +422,37 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, const int3
   }
   if (!ended) return ctx->fail(MSC_ERR_ARG, "program has no END");
   return MSC_OK;
+}
+
+// Is this fast id one of the handlers scan_kernel.cuh compiles (run_fast: aggmov_valid / cmp_valid / group_valid /
+// out_valid)?  An id outside that set falls back to the generic path IN the kernel, which reads operand indices as slot
+// numbers -- so such an instruction must keep its slot numbers (no patching below) and lose its fast id.
+bool fast_shape_compiled(int fast) {
+  auto is_float = [](int fk) { return fk == MSC_FK_F32 || fk == MSC_FK_F64 || fk == MSC_FK_I32F; };
+  auto is_int_col = [](int fk) { return fk == MSC_FK_I32 || fk == MSC_FK_I64; };
+  auto is_code = [](int fk) { return fk == MSC_FK_U8 || fk == MSC_FK_U16 || fk == MSC_FK_U32; };
+  if (fast >= MSC_FAST_ARITH && fast < MSC_FAST_AGGMOV) return true;
+  if (fast >= MSC_FAST_AGGMOV && fast < MSC_FAST_CMP) {
+    const int id = fast - MSC_FAST_AGGMOV, fk = id % 10, kind = id / 10;
+    const bool fkind = kind == MSC_AGG_SUM_F || kind == MSC_AGG_MIN_F || kind == MSC_AGG_MAX_F;
+    if (fk == MSC_FK_TEMP) return true;
+    if (fkind) return is_float(fk);
+    return is_int_col(fk) || (fk == MSC_FK_CONST && kind == MSC_AGG_SUM_I);
+  }
+  if (fast >= MSC_FAST_CMP && fast < MSC_FAST_GROUP) {
+    const int fk = (fast - MSC_FAST_CMP) % 10;
+    return fk != MSC_FK_TEMP && fk != MSC_FK_CONST;
+  }
+  if (fast >= MSC_FAST_GROUP && fast < MSC_FAST_OUT) {
+    const int fk = fast - MSC_FAST_GROUP;
+    return fk == MSC_FK_TEMP || is_int_col(fk) || is_code(fk);
+  }
+  if (fast >= MSC_FAST_OUT && fast < MSC_FAST_OUT + 20) {
+    const int id = fast - MSC_FAST_OUT, u32 = id % 2, fk = id / 2;
+    if (fk == MSC_FK_CONST) return false;
+    return u32 ? (is_code(fk) || fk == MSC_FK_TEMP) : !is_code(fk);
+  }
+  return false;
 }
 
 // Build kernel params + launch geometry.  extra_smem = CTA-wide bytes after the warp regions.
@@ -460,6 +494,10 @@ int plan_launch(msc_ctx* ctx, const msc_scan_desc* sd, int R, size_t extra_smem,
     const uint32_t w0 = p.code[pc];
     if ((w0 & 0x3f) == MSC_OP_END) break;
     if ((w0 >> 20) == 0) continue;
+    if (!fast_shape_compiled(static_cast<int>(w0 >> 20))) {  // (e.g. a dictionary code widened into an I64 output column)
+      p.code[pc] = w0 & 0xFFFFFu;
+      continue;
+    }
     uint32_t w1 = p.code[pc + 1];
     for (int side = 0; side < 2; ++side) {
       const uint32_t operand = (w1 >> (16 * side)) & 0xffffu;

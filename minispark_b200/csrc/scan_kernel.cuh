@@ -16,6 +16,7 @@
 //   Col.execute_row         src/mini_spark/sql.py:262-266
 #pragma once
 #include "common.cuh"
+#include "join_table.cuh"
 
 namespace mscan {
 
@@ -453,6 +454,72 @@ __device__ __forceinline__ void fetch_gather(const Ctx& c, int idx, uint32_t vma
   }
 }
 
+// Load through per-row indices held in a temporary (the build-side row a PROBE found): dst[r] = column[temp[r]].
+template <int R>
+__device__ __forceinline__ void fetch_gather_temp(const Ctx& c, int idx, uint32_t vmask, long long (&v)[R]) {
+  long long ix[R];
+  fetch_temp<R>(c, idx >> 6, ix);
+  const void* col = c.p.gather[idx & 63];
+  const int phys = c.p.gather_phys[idx & 63];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    long long x = 0;
+    if (((vmask >> r) & 1u) && ix[r] >= 0) {
+      const uint64_t i = static_cast<uint64_t>(ix[r]);
+      switch (phys) {
+        case MSC_P_U8: x = __ldg(reinterpret_cast<const uint8_t*>(col) + i); break;
+        case MSC_P_U16: x = __ldg(reinterpret_cast<const uint16_t*>(col) + i); break;
+        case MSC_P_U32: x = __ldg(reinterpret_cast<const uint32_t*>(col) + i); break;
+        case MSC_P_I32: x = __ldg(reinterpret_cast<const int*>(col) + i); break;
+        case MSC_P_F32: x = d2l(static_cast<double>(__ldg(reinterpret_cast<const float*>(col) + i))); break;
+        default: x = __ldg(reinterpret_cast<const long long*>(col) + i); break;
+      }
+    }
+    v[r] = x;
+  }
+}
+
+// MSC_OP_PROBE: x[r] <- build-side row of key x[r] in a join table (msc_join_build), or -1.  The lane's R lookups advance
+// together, one table sector per row and step, so a tile waits for its longest probe sequence and not for R in turn.
+template <int R>
+__device__ __forceinline__ void op_probe(long long (&x)[R], const void* table, uint32_t vmask) {
+  const MscJoinTableHeader* h = static_cast<const MscJoinTableHeader*>(table);
+  const uint64_t mask = h->cap - 1;
+  const uint4* slots = reinterpret_cast<const uint4*>(h + 1);
+  unsigned long long key[R];
+  uint64_t pos[R];
+  bool pend[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    key[r] = msc_join_norm_key(x[r]);
+    pend[r] = (vmask >> r) & 1u;
+    pos[r] = msc_mix64(key[r]) & mask;
+    x[r] = -1;
+  }
+  while (true) {
+    uint4 raw[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (pend[r]) raw[r] = __ldg(slots + pos[r]);
+    bool more = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!pend[r]) continue;
+      const unsigned long long cur = (static_cast<unsigned long long>(raw[r].y) << 32) | raw[r].x;
+      if (cur == key[r]) {
+        x[r] = static_cast<long long>(raw[r].z);
+        pend[r] = false;
+      } else if (cur == MSC_J_EMPTY) {
+        pend[r] = false;
+      } else {
+        pos[r] = (pos[r] + 1) & mask;
+        more = true;
+      }
+    }
+    if (!more) break;
+  }
+}
+
 // generic operand fetch: the i2f variants are separate switch targets (a flag test would be
 // if-converted into R predicated 64-bit conversions on every fetch)
 template <int R>
@@ -465,6 +532,8 @@ __device__ __forceinline__ void fetch(const Ctx& c, uint32_t operand, uint32_t v
     case MSC_SRC_STAGED | MSC_SRC_I2F: fetch_staged<R>(c, idx, v); to_f64<R>(v); break;
     case MSC_SRC_GATHER: fetch_gather<R>(c, idx, vmask, v); break;
     case MSC_SRC_GATHER | MSC_SRC_I2F: fetch_gather<R>(c, idx, vmask, v); to_f64<R>(v); break;
+    case MSC_SRC_GATHER_T: fetch_gather_temp<R>(c, idx, vmask, v); break;
+    case MSC_SRC_GATHER_T | MSC_SRC_I2F: fetch_gather_temp<R>(c, idx, vmask, v); to_f64<R>(v); break;
     case MSC_SRC_CONST: {
       const long long k = c.p.consts[idx];
 #pragma unroll
@@ -898,6 +967,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
           uint32_t total;
           (void)warp_exclusive_scan(__popc(vmask), lane, &total);
           if (lane == 0) p.tile_counts[tile] = total;
+          break;  // everything after RANK computes output columns: nothing the count pass needs
         } else if constexpr (MODE == MODE_PROJECT) {
           if (p.tile_offsets != nullptr) {
             uint32_t total;
@@ -917,6 +987,8 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
         op_lut<R, uint8_t>(a, reinterpret_cast<const uint8_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
       } else if (op == MSC_OP_LUT32) {
         op_lut<R, uint32_t>(a, reinterpret_cast<const uint32_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
+      } else if (op == MSC_OP_PROBE) {
+        op_probe<R>(a, p.luts[(w1 >> 16) & 0xfff], vmask);
       }
       const int tee = (w0 >> 9) & 0xf;
       if (tee) store_temp<R>(c, tee - 1, a);

@@ -240,6 +240,32 @@ class TableEntry:
     keepalive: Any = None  # pinned image for in-memory tables
 
 
+_PROBE_BASE = 1 << 20  # column indices of a fused join's build side inside the consuming scan's source
+
+
+def _has_concat(e: L.Expr) -> bool:
+    return isinstance(e, L.EConcat) or any(_has_concat(c) for c in L.expr_children(e))
+
+
+def _path_stamp(path: str) -> tuple:
+    try:
+        st = os.stat(path)
+        return (st.st_mtime_ns, st.st_size)
+    except OSError:
+        return ()
+
+
+def _plan_tables(node: L.LNode) -> list[str]:
+    if isinstance(node, L.LTable):
+        return [str(node.path)]
+    out: list[str] = []
+    for attr in ("child", "left", "right"):
+        sub = getattr(node, attr, None)
+        if sub is not None:
+            out += _plan_tables(sub)
+    return out
+
+
 def _file_stamp(entry: "TableEntry") -> tuple:
     if entry.stamp and entry.stamp[0] == "mem":
         return entry.stamp
@@ -260,6 +286,13 @@ class _Source:
         self.index_vectors = index_vectors or []
         self.keep = keep or []
         self.partitioned = partitioned  # see DeviceRel.partitioned
+        # a join fused into this scan (CudaExecutionEngine._probe_source): the scan walks the probe side's rows, runs the
+        # probe side's own filters, looks every row's key up in the build side's table and reads build-side columns
+        # (via == "probe") through the matched row
+        self.pre_filters: list[L.Expr] = []
+        self.probe_key: Optional[L.Expr] = None
+        self.probe_table: Optional[int] = None
+        self.translate_targets: Optional[dict[str, "DictHandle"]] = None
 
 
 class _ScanResolver:
@@ -274,7 +307,7 @@ class _ScanResolver:
         self._staged_slot: dict[int, int] = {}
         self._gather_slot: dict[int, int] = {}
         self._bindings: dict[int, L.Binding] = {}
-        self.translate_targets = translate_targets or {}
+        self.translate_targets = translate_targets or source.translate_targets or {}
 
     def _stage(self, col: DeviceColumn) -> int:
         if col.ptr not in self._staged_slot:
@@ -289,6 +322,13 @@ class _ScanResolver:
             col = self.source.columns[index]
             if col.via is None:
                 b = L.Binding(col.phys, staged=self._stage(col), dict_id=col.dict)
+            elif col.via == "probe":
+                if col.ptr not in self._gather_slot:
+                    if len(self.gather) >= N.K["MSC_VM_MAX_GATHER"]:
+                        raise L.LoweringError("query gathers more columns than one scan supports")
+                    self._gather_slot[col.ptr] = len(self.gather)
+                    self.gather.append(col)
+                b = L.Binding(col.phys, gather=self._gather_slot[col.ptr], dict_id=col.dict, probe=True)
             else:
                 if col.ptr not in self._gather_slot:
                     if len(self.gather) >= N.K["MSC_VM_MAX_GATHER"]:
@@ -306,6 +346,11 @@ class _ScanResolver:
                 raise L.LoweringError("too many string predicates in one scan")
             self.luts.append(ptr)
         return self.luts.index(ptr)
+
+    def probe_spec(self) -> Optional[L.ProbeSpec]:
+        if self.source.probe_key is None:
+            return None
+        return L.ProbeSpec(self.source.probe_key, self._lut(self.source.probe_table))
 
     def literal_code(self, dict_id: DictHandle, text: str) -> int:
         return dict_id.literal_code(text)
@@ -385,6 +430,22 @@ def _torch_dtype(phys: int):  # noqa: ANN202
             N.P_F32: torch.float32, N.P_F64: torch.float64}[phys]
 
 
+class _Fingerprint:
+    """A task tree's structural description with its hash computed once (tuples re-hash on every dictionary lookup)."""
+
+    __slots__ = ("tree", "hash")
+
+    def __init__(self, tree: Any) -> None:
+        self.tree = tree
+        self.hash = hash(tree)
+
+    def __hash__(self) -> int:
+        return self.hash
+
+    def __eq__(self, other: Any) -> bool:
+        return self is other or (isinstance(other, _Fingerprint) and self.hash == other.hash and self.tree == other.tree)
+
+
 def task_fingerprint(obj: Any, _depth: int = 0) -> Any:
     """A hashable structural description of a task / column tree (class names + attribute values, recursively): two trees
     with the same fingerprint lower to the same plan.  Works on the reference's own classes as well as the mirror's."""
@@ -409,7 +470,7 @@ def task_fingerprint(obj: Any, _depth: int = 0) -> Any:
     fields = getattr(obj, "__dict__", None)
     if fields is None:
         fields = {k: getattr(obj, k) for k in getattr(obj, "__slots__", ())}
-    return (type(obj).__name__, tuple(sorted((k, task_fingerprint(v, _depth + 1)) for k, v in fields.items() if not k.startswith("_cache"))))
+    return (type(obj).__name__, tuple(sorted((k, task_fingerprint(v, _depth + 1)) for k, v in fields.items() if not k.startswith("_msc"))))
 
 
 _LTYPE_OF = {ColumnType.INTEGER: L.INT, ColumnType.FLOAT: L.FLOAT, ColumnType.TIMESTAMP: L.TS, ColumnType.STRING: L.STR}
@@ -458,6 +519,10 @@ class CudaExecutionEngine(ExecutionEngine):
         # kernel specialised for it, result buffers) and every later one is a single launch.  fingerprint -> [runs, prepared]
         self._plan_cache: dict[Any, list] = {}
         self.plan_cache_enabled = os.environ.get("MINISPARK_PLAN_CACHE", "1") != "0"
+        # joins whose build side has no duplicate keys run as a lookup inside the consuming scan (MSC_OP_PROBE) instead of
+        # materialising both sides and the pair list
+        self.fused_probe = os.environ.get("MINISPARK_FUSED_PROBE", "1") != "0"
+        self._probe_declined: Optional[DeviceRel] = None
         self._own_work = work_folder is None
         self.work_folder = Path(work_folder) if work_folder is not None else Path(tempfile.mkdtemp(prefix="minispark_cuda_"))
         self.work_folder.mkdir(parents=True, exist_ok=True)
@@ -524,14 +589,13 @@ class CudaExecutionEngine(ExecutionEngine):
         over the ranks (``rel.partitioned``) stays so unless ``replicate`` asks for the rank-ordered gather."""
         try:
             t0 = time.perf_counter()
-            cached = self._cached_run(full_task)
+            entry = self._plan_entry(full_task)
+            cached = self._cached_run(full_task, entry)
             if cached is not None:
                 self.last_stats["result_partitioned"] = False
                 self.last_stats["query_s"] = time.perf_counter() - t0
                 return cached
-            task = deepcopy(full_task)  # planning mutates the tree (reference plan.py:181-204)
-            task.validate_schema()      # the reference's own validation and its errors
-            plan = L.lower_task(task)
+            plan = self._lowered(full_task, entry)
             self.last_plan = plan
             self.last_stats["exchange"] = None
             self.last_stats["exchanges"] = []  # every cross-rank step of this query, in order
@@ -549,32 +613,54 @@ class CudaExecutionEngine(ExecutionEngine):
             self.release_query()
             raise
 
-    def _cached_run(self, full_task: Any) -> Optional[tuple[DeviceRel, Schema]]:
-        """Second and later executions of an identical aggregate query run as a prepared pass (see _plan_cache)."""
-        if not self.plan_cache_enabled or self.jit == "never":
+    def _plan_entry(self, full_task: Any) -> Optional[list]:
+        """The plan cache's entry for this task tree: [runs, prepared pass | None | False, lowered plan | None, table stamps].
+        The fingerprint is remembered on the task object, so re-executing the same DataFrame costs a dictionary lookup."""
+        if not self.plan_cache_enabled:
             return None
         try:
-            key = task_fingerprint(full_task)
-            hash(key)
+            key = getattr(full_task, "_msc_fingerprint", None)
+            if key is None:
+                key = _Fingerprint(task_fingerprint(full_task))
+                try:
+                    full_task._msc_fingerprint = key
+                except Exception:  # noqa: BLE001  (slots / frozen classes: recompute next time)
+                    pass
         except Exception:  # noqa: BLE001  (an exotic tree: just run it the one-shot way)
             return None
-        slot = self._plan_cache.setdefault(key, [0, None])
-        slot[0] += 1
-        if slot[0] < 2 or slot[1] is False:
+        entry = self._plan_cache.setdefault(key, [0, None, None, []])
+        entry[0] += 1
+        return entry
+
+    def _lowered(self, full_task: Any, entry: Optional[list]) -> L.LNode:
+        """deepcopy + the reference's own validation + lowering, once per task tree (and again when a table file changed)."""
+        if entry is not None and entry[2] is not None and all(_path_stamp(p) == st for p, st in entry[3]):
+            return entry[2]
+        task = deepcopy(full_task)  # planning mutates the tree (reference plan.py:181-204)
+        task.validate_schema()      # the reference's own validation and its errors
+        plan = L.lower_task(task)
+        if entry is not None:
+            entry[2] = plan
+            entry[3] = [(p, _path_stamp(p)) for p in _plan_tables(plan)]
+        return plan
+
+    def _cached_run(self, full_task: Any, entry: Optional[list]) -> Optional[tuple[DeviceRel, Schema]]:
+        """Second and later executions of an identical aggregate query run as a prepared pass (see _plan_cache)."""
+        if entry is None or self.jit == "never" or entry[0] < 2 or entry[1] is False:
             return None
-        if slot[1] is None:
-            slot[1] = False
+        if entry[1] is None:
+            entry[1] = False
             try:
                 prepared = self.prepare(full_task)
                 if prepared.ngroups and prepared.reusable:  # the dense (low-cardinality) form is what a prepared pass accelerates
-                    slot[1] = prepared
+                    entry[1] = prepared
             except (L.LoweringError, N.NativeError):
                 self.release_query()
-            if slot[1] is False:
+            if entry[1] is False:
                 return None
-        prepared = slot[1]
+        prepared = entry[1]
         if any(self._tables.get(k) is not e or e.stamp != _file_stamp(e) for k, e in prepared.tables):  # a table changed
-            slot[0], slot[1] = 1, None
+            entry[0], entry[1] = 1, None
             return None
         rel, _ = prepared.run()
         self.last_plan = prepared.plan
@@ -716,11 +802,17 @@ class CudaExecutionEngine(ExecutionEngine):
         rel = self._run(node)
         return _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel], partitioned=rel.partitioned)
 
-    def _prepare(self, base: L.LNode, exprs: list[L.Expr]) -> tuple[_Source, list[L.Expr]]:
-        """Resolve the scan input and materialise string concatenations the program cannot compute."""
+    def _prepare(self, base: L.LNode, exprs: list[L.Expr], fuse_probe: bool = True) -> tuple[_Source, list[L.Expr]]:
+        """Resolve the scan input and materialise string concatenations the program cannot compute.  A join directly below
+        the scan is fused into it where possible (_probe_source): the returned expressions are then rewritten to the probe
+        side's columns and source.pre_filters / probe_key describe the rest."""
         needed: set[int] = set()
         for e in exprs:
             needed |= L.expr_inputs(e)
+        if fuse_probe and isinstance(base, L.LJoin) and self.fused_probe:
+            fused = self._probe_source(base, exprs, needed)
+            if fused is not None:
+                return fused
         source = self._source(base, needed)
         concats: dict[L.EConcat, int] = {}
 
@@ -803,7 +895,7 @@ class CudaExecutionEngine(ExecutionEngine):
         source, exprs = self._prepare(sel.child, [*sel.filters, *sel.outputs])
         filters, outputs = exprs[:nf], exprs[nf:]
         resolver = _ScanResolver(self, source, translate_targets)
-        prog = L.compile_project(resolver, filters, outputs)
+        prog = L.compile_project(resolver, filters, outputs, probe=resolver.probe_spec(), pre_filters=source.pre_filters)
         rel = self._scan_project(resolver, prog, [e.type for e in outputs])
         rel.keep.extend(source.keep)
         return rel
@@ -823,7 +915,7 @@ class CudaExecutionEngine(ExecutionEngine):
         filters, group = exprs[:nf], exprs[nf]
         aggs = [(k, e) for (k, _), e in zip(aggs, exprs[nf + 1:])]
         resolver = _ScanResolver(self, source)
-        prog = L.compile_aggregate(resolver, filters, group, aggs)
+        prog = L.compile_aggregate(resolver, filters, group, aggs, probe=resolver.probe_spec(), pre_filters=source.pre_filters)
         ngroups, hint = self._dense_groups(prog)
         desc = resolver.desc(prog.program)
         kinds = N.int32_array(prog.agg_kinds)
@@ -871,21 +963,74 @@ class CudaExecutionEngine(ExecutionEngine):
             dense = dense and size > 0
         return (max(size, 1) if dense else 0), max(size, 1)
 
+    def _join_side(self, node: L.LNode, idxs: list[int], key: L.Expr, targets: Optional[dict[str, DictHandle]]) -> DeviceRel:
+        """One side of a join as a relation: the needed columns, then the key (a STR key as its dictionary code)."""
+        outs = [L.EInput(_LTYPE_OF[node.schema[i][1]], i) for i in idxs]
+        key_out = L.ECode(L.INT, key) if key.type == L.STR else key
+        schema = [node.schema[i] for i in idxs] + [("__key", ColumnType.INTEGER)]
+        sel = L.fuse_selects(L.LSelect(schema, node, [], [*outs, key_out]))
+        return self._run_select(sel, targets)
+
+    def _probe_source(self, join: L.LJoin, exprs: list[L.Expr], needed: set[int]) -> Optional[tuple[_Source, list[L.Expr]]]:
+        """A join as a LOOKUP inside the scan that consumes it.  The reference builds key -> [left rows] and streams the right
+        rows through it (tasks.py:201-240); when no key repeats on the left, every right row has at most one partner, so the
+        consumer can walk the right side itself: its own filters, then the probe (MSC_OP_PROBE), then everything above the
+        join, with left columns read through the matched row.  Neither side's rows nor the pair list are materialised beyond
+        the (filtered) build side; output order is the right side's row order, which is the reference's right-row-major
+        order.  None: not applicable here (several ranks, duplicate build keys, expressions that must be evaluated on
+        unmatched rows too) -- the caller runs the materialising join."""
+        if self.comm.world > 1:
+            return None
+        right = join.right
+        rsel = right if isinstance(right, L.LSelect) else L.identity_select(right)
+        if not all(L._cannot_raise(e) for e in rsel.outputs) or any(_has_concat(e) for e in [*exprs, *rsel.outputs, *rsel.filters]):
+            return None
+        nl = len(join.left.schema)
+        left_needed = sorted(i for i in needed if i < nl)
+        lrel = self._join_side(join.left, left_needed, join.left_key, None)
+        table, unique = C.c_void_p(), C.c_int32()
+        self.ctx.call("msc_join_build", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.byref(table), C.byref(unique))
+        trel = self._track(DeviceRel.from_handle(self.ctx, table.value, [L.INT], [None]))
+        if not unique.value:
+            self._probe_declined = lrel  # (the materialising join reuses the build side it already has)
+            return None
+        inputs: list[L.Expr] = [L.EInput(_LTYPE_OF[t], _PROBE_BASE + i) for i, (_, t) in enumerate(join.left.schema)] + list(rsel.outputs)
+        new_exprs = [L.substitute(e, inputs) for e in exprs]
+        rkey = L.substitute(join.right_key, list(rsel.outputs))
+        targets = None
+        if rkey.type == L.STR:  # joined on the code in the LEFT key column's dictionary
+            targets = {"join": lrel.cols[-1].dict}
+            rkey = L.ECode(L.INT, L.ETranslate(L.STR, rkey, "join"))
+        rneeded: set[int] = set()
+        for e in [*new_exprs, *rsel.filters, rkey]:
+            rneeded |= {i for i in L.expr_inputs(e) if i < _PROBE_BASE}
+        rsource = self._source(rsel.child, rneeded)
+        columns = dict(rsource.columns)
+        for pos, i in enumerate(left_needed):
+            c = lrel.cols[pos]
+            columns[_PROBE_BASE + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via="probe")
+        source = _Source(rsource.nrows, columns, rsource.index_vectors, keep=[*rsource.keep, lrel, trel], partitioned=rsource.partitioned)
+        source.pre_filters = list(rsel.filters)
+        source.probe_key = rkey
+        source.probe_table = trel.cols[0].ptr
+        source.translate_targets = targets
+        self.last_stats["join"] = "lookup fused into the consuming scan (MSC_OP_PROBE)"
+        return source, new_exprs
+
     def _join_source(self, join: L.LJoin, needed: set[int]) -> _Source:
         nl = len(join.left.schema)
         left_needed = sorted(i for i in needed if i < nl)
         right_needed = sorted(i - nl for i in needed if i >= nl)
-
-        def side(node: L.LNode, idxs: list[int], key: L.Expr, targets: Optional[dict[str, DictHandle]]) -> DeviceRel:
-            outs = [L.EInput(_LTYPE_OF[node.schema[i][1]], i) for i in idxs]
-            key_out = L.ECode(L.INT, key) if key.type == L.STR else key
-            schema = [node.schema[i] for i in idxs] + [("__key", ColumnType.INTEGER)]
-            sel = L.fuse_selects(L.LSelect(schema, node, [], [*outs, key_out]))
-            return self._run_select(sel, targets)
+        side = self._join_side
+        self.last_stats["join"] = "build / probe / emit pairs (msc_hash_join)"
 
         # A STR key is joined on its dictionary code (key_out above), so both sides must be coded in ONE dictionary:
         # the left key column's -- unified over all ranks first when the tables are sharded.
-        lrel = side(join.left, left_needed, join.left_key, None)
+        declined, self._probe_declined = getattr(self, "_probe_declined", None), None
+        if declined is not None and len(declined.cols) == len(left_needed) + 1:
+            lrel = declined
+        else:
+            lrel = side(join.left, left_needed, join.left_key, None)
         key_dict = lrel.cols[-1].dict if join.left_key.type == L.STR else None
         if key_dict is not None and self.comm.world > 1:
             key_dict = self._unified_dictionary(key_dict)
@@ -1340,7 +1485,7 @@ class PreparedAggregate:
         else:
             filters, group, aggs, base = [], agg.group, list(agg.aggs), child
         tracked = len(engine._query_rels)
-        self.source, exprs = engine._prepare(base, [*filters, group, *[e for _, e in aggs]])
+        self.source, exprs = engine._prepare(base, [*filters, group, *[e for _, e in aggs]], fuse_probe=False)
         # what the pass is bound to: device-resident table columns outlive a query; anything the preparation had to compute
         # (a join below the aggregate, a concatenation) is released with the query, so such a plan must not be kept
         self.tables = [(str(base.path), engine._tables[str(base.path)])] if isinstance(base, L.LTable) else []

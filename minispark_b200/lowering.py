@@ -538,6 +538,16 @@ class Binding:
     gather: Optional[int] = None  # slot in desc.gather ...
     index: Optional[int] = None   # ... through this staged index-vector slot
     dict_id: Any = None           # dictionary handle for STR columns
+    probe: bool = False           # gather column of the build side of a fused join: read through the program's PROBE result
+
+
+@dataclass
+class ProbeSpec:
+    """The probe half of a hash join carried by a scan's row program (MSC_OP_PROBE): after the scan's own `pre_filters`,
+    every row looks its key up in the join table (LUT slot `lut`); rows without a match are filtered out, and the
+    build-side columns (bindings with probe=True) are read through the matched build row."""
+    key: "Expr"
+    lut: int
 
 
 class Resolver(Protocol):
@@ -558,10 +568,11 @@ _F_OPS = {"add": "ADD_F", "sub": "SUB_F", "mul": "MUL_F", "truediv": "DIV_F", "f
 _I_OPS = {"add": "ADD_I", "sub": "SUB_I", "mul": "MUL_I", "floordiv": "FLOORDIV_I", "mod": "MOD_I",
           "lt": "LT_I", "le": "LE_I", "gt": "GT_I", "ge": "GE_I", "eq": "EQ_I", "ne": "NE_I", "and": "AND", "or": "OR"}
 SRC_TEMP, SRC_STAGED, SRC_CONST, SRC_GATHER, SRC_LUT = (K[f"MSC_SRC_{n}"] for n in ("TEMP", "STAGED", "CONST", "GATHER", "LUT"))
+SRC_GATHER_T = K["MSC_SRC_GATHER_T"]
 SRC_I2F = K["MSC_SRC_I2F"]
 DST_TEMP, DST_FILTER, DST_GROUP, DST_AGG, DST_OUT, DST_NONE = (K[f"MSC_DST_{n}"] for n in ("TEMP", "FILTER", "GROUP", "AGG", "OUT", "NONE"))
 _DST_NAME = {DST_TEMP: "t", DST_FILTER: "filter", DST_GROUP: "group", DST_AGG: "agg", DST_OUT: "out", DST_NONE: "none"}
-_SRC_NAME = {SRC_TEMP: "t", SRC_STAGED: "col", SRC_CONST: "const", SRC_GATHER: "gather", SRC_LUT: "lut", 0: "-"}
+_SRC_NAME = {SRC_TEMP: "t", SRC_STAGED: "col", SRC_CONST: "const", SRC_GATHER: "gather", SRC_LUT: "lut", SRC_GATHER_T: "gather", 0: "-"}
 
 
 def f64_bits(x: float) -> int:
@@ -592,7 +603,10 @@ def _fmt_operand(o: int) -> str:
     kind, idx = (o >> 12) & 7, o & 0xFFF
     if kind == 0:
         return "-"
-    body = f"{_SRC_NAME[kind]}{idx & 63}[ix{idx >> 6}]" if kind == SRC_GATHER else f"{_SRC_NAME[kind]}{idx}"
+    if kind == SRC_GATHER_T:
+        body = f"gather{idx & 63}[t{idx >> 6}]"
+    else:
+        body = f"{_SRC_NAME[kind]}{idx & 63}[ix{idx >> 6}]" if kind == SRC_GATHER else f"{_SRC_NAME[kind]}{idx}"
     return f"f64({body})" if o & 0x8000 else body
 
 
@@ -608,6 +622,7 @@ class ProgramBuilder:
         self.uses_left: dict[Expr, int] = {}
         self.candidates: dict[Expr, int] = {}
         self.staged_phys: dict[int, int] = {}
+        self.probe_temp: Optional[int] = None  # temporary that holds the build row a PROBE matched (kept until END)
 
     # -- low level ------------------------------------------------------------------------------
     def alloc(self) -> int:
@@ -690,7 +705,9 @@ class ProgramBuilder:
         if opname == "MOV" and dkind == DST_GROUP and fa not in float_kinds and fa != K["MSC_FK_CONST"]:
             return K["MSC_FAST_GROUP"] + fa
         if opname == "MOV" and dkind == DST_OUT and fa != K["MSC_FK_CONST"]:
-            if out_u32 and fa in float_kinds:
+            code_kinds = (K["MSC_FK_U8"], K["MSC_FK_U16"], K["MSC_FK_U32"])
+            # (the handlers the kernel compiles, scan_kernel.cuh out_valid: a code goes to a U32 column, numbers to 64-bit ones)
+            if (out_u32 and fa not in (*code_kinds, K["MSC_FK_TEMP"])) or (not out_u32 and fa in code_kinds):
                 return 0
             return K["MSC_FAST_OUT"] + fa * 2 + int(out_u32)
         return 0
@@ -726,6 +743,10 @@ class ProgramBuilder:
             if b.staged is not None:
                 self.staged_phys[b.staged] = b.phys
                 return src(SRC_STAGED, b.staged)
+            if b.probe:
+                if self.probe_temp is None:
+                    raise LoweringError("a build-side column is read before the join's probe")
+                return src(SRC_GATHER_T, b.gather | (self.probe_temp << 6))
             return src(SRC_GATHER, b.gather | (b.index << 6))
         if isinstance(e, EConst):
             if e.type == STR:
@@ -843,6 +864,18 @@ class ProgramBuilder:
         self.release(frees)
         return dict_id
 
+    def emit_probe(self, spec: ProbeSpec) -> None:
+        """t <- PROBE(key, table); FILTER <- t >= 0.  The temporary stays allocated: every build-side column reads through it."""
+        if spec.key.type == STR or isinstance(spec.key, ECode):
+            a, frees, _ = self.string_operand(spec.key)
+        else:
+            a, frees = self.operand(spec.key)
+        t = self.alloc()
+        self.emit("PROBE", a, src(SRC_LUT, spec.lut), DST_TEMP, t)
+        self.release(frees)
+        self.emit("GE_I", src(SRC_TEMP, t), src(SRC_CONST, self.const(0)), DST_FILTER)
+        self.probe_temp = t
+
     def end(self) -> Program:
         self.p.code.extend([OP["END"], 0])
         self.p.text.append("END")
@@ -877,7 +910,10 @@ class AggregateProgram:
     group_dict: Any            # dictionary of a STR group key (None otherwise)
 
 
-def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, aggs: Sequence[tuple[str, Expr]]) -> AggregateProgram:
+def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, aggs: Sequence[tuple[str, Expr]],
+                      probe: Optional[ProbeSpec] = None, pre_filters: Sequence[Expr] = ()) -> AggregateProgram:
+    """``probe``: the scan also carries the probe half of a join -- `pre_filters` (the probe side's own) run first, then the
+    probe, then `filters` (which may read build-side columns)."""
     b = ProgramBuilder(resolver)
     norm = [(k, EConst(INT, 1) if k == "count" else (EBin(INT, "add", e, EConst(INT, 0)) if e.type == BOOL else e)) for k, e in aggs]
     # accumulator slots: plain SUM(column) aggregates first and next to each other, so that the register interpreter
@@ -896,7 +932,12 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
     if REGVM_ENABLED and count_key not in unique and len(unique) < K["MSC_VM_MAX_AGGS"]:
         unique[count_key] = len(unique)  # the regvm kernel tells present groups by their row count
     filters = split_conjunctions(filters)
-    b.plan_cse([*filters, group, *[e for (k, e) in unique if k != "count"]])
+    pre_filters = split_conjunctions(pre_filters)
+    b.plan_cse([*pre_filters, *([probe.key] if probe else []), *filters, group, *[e for (k, e) in unique if k != "count"]])
+    for f in pre_filters:
+        b.materialize(f, DST_FILTER)
+    if probe is not None:
+        b.emit_probe(probe)
     for f in filters:
         b.materialize(f, DST_FILTER)
     group_dict = b.materialize(group, DST_GROUP)
@@ -913,7 +954,7 @@ def compile_aggregate(resolver: Resolver, filters: Sequence[Expr], group: Expr, 
         kinds.append(_AGG_KINDS[(kind, FLOAT if e.type == FLOAT else INT)])
         b.materialize(e, DST_AGG, slot, agg_kind=kinds[-1])
     program = b.end()
-    if REGVM_ENABLED:
+    if REGVM_ENABLED and probe is None:
         try:
             program.regvm, program.regvm_text = compile_regvm(b, filters, group, unique)
             program.regvm_count_slot = unique.get(count_key, -1)
@@ -1145,13 +1186,19 @@ class ProjectProgram:
     out_dicts: list[Any]
 
 
-def compile_project(resolver: Resolver, filters: Sequence[Expr], outputs: Sequence[Expr]) -> ProjectProgram:
+def compile_project(resolver: Resolver, filters: Sequence[Expr], outputs: Sequence[Expr], probe: Optional[ProbeSpec] = None,
+                    pre_filters: Sequence[Expr] = ()) -> ProjectProgram:
     b = ProgramBuilder(resolver)
     filters = split_conjunctions(filters)
-    b.plan_cse([*filters, *outputs])
+    pre_filters = split_conjunctions(pre_filters)
+    b.plan_cse([*pre_filters, *([probe.key] if probe else []), *filters, *outputs])
+    for f in pre_filters:
+        b.materialize(f, DST_FILTER)
+    if probe is not None:
+        b.emit_probe(probe)
     for f in filters:
         b.materialize(f, DST_FILTER)
-    if filters:
+    if filters or pre_filters or probe is not None:
         b.emit("RANK")
     if len(outputs) > K["MSC_VM_MAX_OUT"]:
         raise LoweringError("too many output columns in one projection")
