@@ -12,8 +12,9 @@ from .execution import CudaExecutionEngine, ExecutionEngine, ExecutionError
 from .io import BlockFile
 from .jobs import JobResult, OutputFile
 from .sql import AggCol, Col, Functions, Lit
+from .utils import TRACER, trace
 
 __all__ = [
     "AggCol", "BlockFile", "Col", "ColumnType", "CudaExecutionEngine", "DataFrame", "ExecutionEngine",
-    "ExecutionError", "Functions", "JobResult", "Lit", "OutputFile",
+    "ExecutionError", "Functions", "JobResult", "Lit", "OutputFile", "TRACER", "trace",
 ]

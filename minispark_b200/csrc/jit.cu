@@ -190,7 +190,7 @@ struct Gen {
     const int kind = (opnd >> 12) & 7, idx = opnd & 0xfff;
     const bool i2f = ((opnd >> 12) & MSC_SRC_I2F) != 0;
     std::string s;
-    if (in_finish && (kind == MSC_SRC_GATHER || kind == MSC_SRC_LUT)) {
+    if (in_finish && (kind == MSC_SRC_GATHER || kind == MSC_SRC_GATHER_T || kind == MSC_SRC_LUT)) {
       *ok = false;
       return "0ll";
     }
@@ -201,6 +201,10 @@ struct Gen {
       case MSC_SRC_GATHER:
         s = "gather_at<" + std::to_string(sd->gather[idx & 63].phys) + ">(p.gather[" + std::to_string(idx & 63) + "], c" +
             std::to_string(idx >> 6) + "[r], valid)";
+        break;
+      case MSC_SRC_GATHER_T:  // a build-side column of a fused join, read through the row its PROBE matched
+        s = "gather_at<" + std::to_string(sd->gather[idx & 63].phys) + ">(p.gather[" + std::to_string(idx & 63) + "], " + temp(idx >> 6) +
+            ", valid && " + temp(idx >> 6) + " >= 0)";
         break;
       case MSC_SRC_NONE: s = "0ll"; break;
       default: *ok = false; return "0ll";
@@ -246,6 +250,12 @@ struct Gen {
         return "(valid ? (i64)__ldg(reinterpret_cast<const unsigned char*>(p.luts[" + std::to_string(opnd_b & 0xfff) + "]) + (" + a + ")) : 0ll)";
       case MSC_OP_LUT32:
         return "(valid ? (i64)__ldg(reinterpret_cast<const u32*>(p.luts[" + std::to_string(opnd_b & 0xfff) + "]) + (" + a + ")) : 0ll)";
+      case MSC_OP_PROBE:
+        if (in_finish) {
+          *ok = false;
+          return "0ll";
+        }
+        return "join_probe(p.luts[" + std::to_string(opnd_b & 0xfff) + "], " + a + ", valid)";
       default: *ok = false; return "0ll";
     }
   }
@@ -297,7 +307,7 @@ struct Gen {
     const int op = w0 & 0x3f;
     const int dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
     const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
-    const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+    const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || op == MSC_OP_PROBE;
     bool ok = true;
     const std::string a = operand(oa, &ok), b = lut ? std::string("0ll") : operand(ob, &ok);
     if (dkind == MSC_DST_OUT && !allow_out) return true;  // a count scan only needs the filters
@@ -537,7 +547,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
       if (op == MSC_OP_END) break;
       const int dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
       const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
-      const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+      const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || op == MSC_OP_PROBE;
       if (op == MSC_OP_RANK || dkind == MSC_DST_FILTER || dkind == MSC_DST_OUT) {
         why = "filter / projection instruction in a streaming aggregate";
         return false;
@@ -730,7 +740,9 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       const int op = w0 & 0x3f;
       if (op == MSC_OP_END) break;
       const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
-      if (op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || ((oa >> 12) & 7) == MSC_SRC_GATHER || ((ob >> 12) & 7) == MSC_SRC_GATHER) derefs = true;
+      if (op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || op == MSC_OP_PROBE || ((oa >> 12) & 7) == MSC_SRC_GATHER || ((ob >> 12) & 7) == MSC_SRC_GATHER ||
+          ((oa >> 12) & 7) == MSC_SRC_GATHER_T || ((ob >> 12) & 7) == MSC_SRC_GATHER_T)
+        derefs = true;
       if (((w0 >> 6) & 7) == MSC_DST_GROUP && op == MSC_OP_MOV && ((oa >> 12) & 15) == MSC_SRC_STAGED) key_col = oa & 0xfff;
     }
     const bool valid_bits = derefs || key_col < 0;
@@ -740,15 +752,63 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       o << "    if (vmask != 0xffu) {\n#pragma unroll\n      for (int r = 0; r < R; ++r)\n        if (!((vmask >> r) & 1u)) c" << key_col
         << "[r] = -1;\n    }\n";
     }
-    o << "#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = " << (valid_bits ? "(vmask >> r) & 1u" : "true") << ";\n      int grp = -1;\n";
+    // A join probe (MSC_OP_PROBE) is a dependent random read: run the program in TWO row loops around the first one --
+    // loop 1 evaluates what precedes it and ISSUES the table read of every row of the lane, loop 2 resolves the probes and
+    // runs the rest -- so that a lane's 8 lookups are in flight together instead of one after the other.
+    int probe_pc = -1;
+    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+      const int op = sd->code[pc] & 0x3f, dkind = (sd->code[pc] >> 6) & 7;
+      if (op == MSC_OP_END) break;
+      if (op == MSC_OP_PROBE) {
+        if (dkind == MSC_DST_TEMP && ((sd->code[pc] >> 9) & 0xf) == 0) probe_pc = pc;
+        break;
+      }
+      if (dkind != MSC_DST_TEMP && dkind != MSC_DST_FILTER) break;  // only filters and temporaries may precede a split
+    }
+    temp_arrays = probe_pc >= 0;
+    bool ok = true, grouped = false;
+    if (probe_pc >= 0) {
+      for (int t = 0; t < sd->ntemps; ++t) o << "    i64 t" << t << "[R];\n";
+      o << "    u64 pkey[R], ppos[R]; uint4 praw[R]; u32 vm = 0;\n#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = (vmask >> r) & 1u;\n";
+      for (int t = 0; t < sd->ntemps; ++t) o << "      t" << t << "[r] = 0;\n";
+      for (int pc = 0; pc < probe_pc; pc += 2) {
+        const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
+        const int op = w0 & 0x3f, dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
+        const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
+        const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+        const std::string a = operand(oa, &ok), b = lut ? std::string("0ll") : operand(ob, &ok);
+        o << "      {  // instruction " << pc / 2 << "\n";
+        if (op == MSC_OP_DIV_F || op == MSC_OP_FLOORDIV_F || op == MSC_OP_MOD_F) o << "        bad |= valid && (l2d(" << b << ") == 0.0);\n";
+        if (op == MSC_OP_FLOORDIV_I || op == MSC_OP_MOD_I) o << "        bad |= valid && ((" << b << ") == 0);\n";
+        o << "        const i64 x = " << compute(op, a, b, ob, &ok) << ";\n";
+        if (tee) o << "        " << temp(tee - 1) << " = x;\n";
+        if (dkind == MSC_DST_TEMP) o << "        " << temp(dst) << " = x;\n";
+        else o << "        valid = valid && (x != 0);\n";
+        o << "      }\n";
+      }
+      {
+        const uint32_t w1 = sd->code[probe_pc + 1];
+        const std::string a = operand(w1 & 0xffffu, &ok);
+        o << "      join_probe_issue(p.luts[" << ((w1 >> 16) & 0xfff) << "], " << a << ", valid, pkey[r], ppos[r], praw[r]);  // instruction "
+          << probe_pc / 2 << ", first half\n";
+      }
+      o << "      vm |= (valid ? 1u : 0u) << r;\n    }\n";
+    }
+    o << "#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = "
+      << (probe_pc >= 0 ? "(vm >> r) & 1u" : (valid_bits ? "(vmask >> r) & 1u" : "true")) << ";\n      int grp = -1;\n";
     if (masked) {
       o << "      double";
       for (int g = 0; g < (ngroups + 1) / 2 * 2; ++g) o << (g ? ", m" : " m") << g << " = 0.0";
       o << ";\n";
     }
-    for (int t = 0; t < sd->ntemps; ++t) o << "      i64 t" << t << " = 0;\n";
-    bool ok = true, grouped = false;
-    for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+    if (probe_pc < 0) {
+      for (int t = 0; t < sd->ntemps; ++t) o << "      i64 t" << t << " = 0;\n";
+    } else {
+      const uint32_t w0 = sd->code[probe_pc], w1 = sd->code[probe_pc + 1];
+      o << "      " << temp((w0 >> 13) & 0x7f) << " = join_probe_resolve(p.luts[" << ((w1 >> 16) & 0xfff) << "], pkey[r], ppos[r], praw[r], valid);  // instruction "
+        << probe_pc / 2 << ", second half\n";
+    }
+    for (int pc = probe_pc >= 0 ? probe_pc + 2 : 0; pc + 1 < sd->ncode; pc += 2) {
       const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
       const int op = w0 & 0x3f;
       if (op == MSC_OP_END) break;
@@ -758,7 +818,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       }
       const int dkind = (w0 >> 6) & 7, tee = (w0 >> 9) & 0xf, dst = (w0 >> 13) & 0x7f;
       const uint32_t oa = w1 & 0xffffu, ob = w1 >> 16;
-      const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32;
+      const bool lut = op == MSC_OP_LUT8 || op == MSC_OP_LUT32 || op == MSC_OP_PROBE;
       const std::string a = operand(oa, &ok), b = lut ? std::string("0ll") : operand(ob, &ok);
       o << "      {  // instruction " << pc / 2 << "\n";
       if (op == MSC_OP_DIV_F || op == MSC_OP_FLOORDIV_F || op == MSC_OP_MOD_F)

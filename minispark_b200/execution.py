@@ -35,6 +35,7 @@ from .distributed import Comm, PeerShuffle, invert_code_maps, shard_blocks, unif
 from .constants import ColumnType, Row, Schema
 from .io import BlockFile
 from .jobs import JobResult, OutputFile
+from .utils import TRACER
 
 if TYPE_CHECKING:
     from .dataframe import DataFrame
@@ -117,6 +118,37 @@ class DictHandle:
             out = C.c_void_p()
             self.ctx.call("msc_dict_like", C.c_void_p(self.handle), raw, len(raw), C.byref(out))
             self._luts[key] = out.value
+        return self._luts[key]
+
+    def _upload(self, array: Any) -> int:
+        ptr = C.c_void_p()
+        self.ctx.call("msc_dev_alloc", max(array.nbytes, 16), C.byref(ptr))
+        if array.nbytes:
+            self.ctx.call("msc_memcpy_h2d", ptr, array.ctypes.data_as(C.c_void_p), array.nbytes)
+        return ptr.value
+
+    def order_lut(self, op: str, text: str) -> int:
+        """u8 LUT over the entries: 1 where ``entry <op> text`` (op in lt / le / gt / ge), Python string order."""
+        import operator as _op
+
+        import numpy as np  # noqa: PLC0415
+
+        key = ("order", op, text, self.size)
+        if key not in self._luts:
+            fn = getattr(_op, op)
+            self._luts[key] = self._upload(np.fromiter((fn(entry, text) for entry in self.export()), dtype=np.uint8, count=self.size))
+        return self._luts[key]
+
+    def rank_lut(self, other: "DictHandle") -> int:
+        """u32 LUT: rank of every entry in the sorted union of this dictionary's and ``other``'s entries."""
+        import numpy as np  # noqa: PLC0415
+
+        key = ("rank", other.serial, self.size, other.size)
+        if key not in self._luts:
+            mine = self.export()
+            order = {s: i for i, s in enumerate(sorted(set(mine) | set(other.export() if other is not self else mine)))}
+            self._luts[key] = self._upload(np.fromiter((order[s] for s in mine), dtype=np.uint32, count=len(mine)))
+            other._translated_from.append((self, key))  # dies with `other`
         return self._luts[key]
 
     def translate_lut(self, target: "DictHandle", insert: bool = False) -> int:
@@ -364,6 +396,12 @@ class _ScanResolver:
     def recode_lut(self, src: DictHandle, dst: DictHandle) -> int:
         return self._lut(src.translate_lut(dst, insert=False))
 
+    def order_lut(self, dict_id: DictHandle, op: str, text: str) -> int:
+        return self._lut(dict_id.order_lut(op, text))
+
+    def rank_luts(self, a: DictHandle, b: DictHandle) -> tuple[int, int]:
+        return self._lut(a.rank_lut(b)), self._lut(b.rank_lut(a))
+
     def translate_lut(self, dict_id: DictHandle, token: str) -> tuple[int, DictHandle]:
         target = self.translate_targets[token]
         if target is dict_id:
@@ -393,7 +431,7 @@ class _ScanResolver:
             d.consts[i] = c
         d.nluts = len(self.luts)
         d.ntemps = program.ntemps
-        d.want_jit = 1 if self.engine.jit == "always" else 0
+        d.want_jit = 1 if self.engine.jit == "always" or self.engine._specialise_now else 0
         d.ncode2 = len(program.regvm)
         d.count_slot2 = program.regvm_count_slot
         for i, w in enumerate(program.regvm):
@@ -523,6 +561,10 @@ class CudaExecutionEngine(ExecutionEngine):
         # materialising both sides and the pair list
         self.fused_probe = os.environ.get("MINISPARK_FUSED_PROBE", "1") != "0"
         self._probe_declined: Optional[DeviceRel] = None
+        self._trace_track: Optional[int] = None
+        # jit="auto": a task tree that comes back is worth kernels compiled for exactly its scans (0.1-0.3 s each, once per
+        # process and shape) -- the reference's ThreadEngine compiles every query before it runs it (execution.py:139-160)
+        self._specialise_now = False
         self._own_work = work_folder is None
         self.work_folder = Path(work_folder) if work_folder is not None else Path(tempfile.mkdtemp(prefix="minispark_cuda_"))
         self.work_folder.mkdir(parents=True, exist_ok=True)
@@ -536,17 +578,23 @@ class CudaExecutionEngine(ExecutionEngine):
 
     # ---- ExecutionEngine contract ---------------------------------------------------------------
     def execute_full_task(self, full_task: Any) -> list[JobResult]:
-        rel, schema = self.execute_to_device(full_task, replicate=self.replicate_results)
+        TRACER.start("execute full task")  # (the reference's slice names, execution.py:69-78)
         try:
+            rel, schema = self.execute_to_device(full_task, replicate=self.replicate_results)
             job = JobResult(str(uuid.uuid4()), f"cuda:{self.device}", [], result_partitioned=rel.partitioned)
             if rel.nrows > 0:  # empty result -> no output file (reference tasks.py:405-406)
                 path = self.work_folder / f"result_{job.job_id}.bin"
-                self.write_blockfile(rel, schema, path)
+                TRACER.start("write result BlockFile")
+                try:
+                    self.write_blockfile(rel, schema, path)
+                finally:
+                    TRACER.end()
                 self._result_files.append(path)
                 job.output_files.append(OutputFile(path))
             return [job]
         finally:
             self.release_query()
+            TRACER.end()
 
     def __exit__(self, exc_type, exc_value, traceback) -> None:  # noqa: ANN001
         self.close()
@@ -595,14 +643,25 @@ class CudaExecutionEngine(ExecutionEngine):
                 self.last_stats["result_partitioned"] = False
                 self.last_stats["query_s"] = time.perf_counter() - t0
                 return cached
-            plan = self._lowered(full_task, entry)
+            TRACER.start("lower task tree")
+            try:
+                plan = self._lowered(full_task, entry)
+            finally:
+                TRACER.end()
             self.last_plan = plan
             self.last_stats["exchange"] = None
             self.last_stats["exchanges"] = []  # every cross-rank step of this query, in order
             self.last_stats["plan"] = "one-shot"
-            rel = self._run(plan)
-            if replicate and rel.partitioned:
-                rel = self._gather_rows(rel)
+            self._specialise_now = self.jit == "auto" and entry is not None and entry[0] >= 2
+            if self._specialise_now:
+                self.last_stats["plan"] = "one-shot, scans on kernels specialised for this task tree (it came back)"
+            TRACER.start("Execution")
+            try:
+                rel = self._run(plan)
+                if replicate and rel.partitioned:
+                    rel = self._gather_rows(rel)
+            finally:
+                TRACER.end()
             self.last_stats["result_partitioned"] = rel.partitioned
             self.last_stats["query_s"] = time.perf_counter() - t0
             return rel, plan.schema
@@ -779,6 +838,8 @@ class CudaExecutionEngine(ExecutionEngine):
         st = self.ctx.stats()
         self.last_stats["ingest_ms"] = st.last_ingest_ms
         self.last_stats["ingest_bytes"] = st.last_ingest_bytes
+        if TRACER.enabled:
+            TRACER.device_slice(f"load table block columns {missing} of {entry.path.name} ({st.last_ingest_bytes} bytes)", st.last_ingest_ms, self._gpu_track())
 
     # ---- plan execution -----------------------------------------------------------------------------
     def _track(self, rel: DeviceRel) -> DeviceRel:
@@ -875,13 +936,20 @@ class CudaExecutionEngine(ExecutionEngine):
         out = C.c_void_p()
         phys = N.int32_array(prog.out_phys)
         self.ctx.call("msc_scan_project", C.byref(desc), phys, len(prog.out_phys), C.byref(out))
-        self._note_kernel()
+        self._note_kernel("scan: filter + project")
         rel = self._track(DeviceRel.from_handle(self.ctx, out.value, ltypes, prog.out_dicts))
         rel.partitioned = resolver.source.partitioned
         return rel
 
-    def _note_kernel(self) -> None:
+    def _gpu_track(self) -> int:
+        if self._trace_track is None:
+            self._trace_track = TRACER.new_track(f"GPU {self.device} (device time)")
+        return self._trace_track
+
+    def _note_kernel(self, what: str = "kernels") -> None:
         st = self.ctx.stats()
+        if TRACER.enabled:
+            TRACER.device_slice(what, st.last_kernel_ms, self._gpu_track())
         self.last_stats["kernel_ms"] = st.last_kernel_ms
         self.last_stats["scan_ms"] = st.last_scan_ms
         self.last_stats["scan_grid"] = st.last_scan_grid
@@ -934,7 +1002,7 @@ class CudaExecutionEngine(ExecutionEngine):
         else:
             out = C.c_void_p()
             self.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), hint, C.byref(out))
-            self._note_kernel()
+            self._note_kernel("scan: filter + aggregate")
             self.last_stats["agg_scan_kind"] = self.last_stats["scan_kind"]  # later scans (final projection) overwrite scan_kind
             self.last_stats["agg_scan_ms"] = self.last_stats["scan_ms"]
             raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
@@ -990,6 +1058,7 @@ class CudaExecutionEngine(ExecutionEngine):
         lrel = self._join_side(join.left, left_needed, join.left_key, None)
         table, unique = C.c_void_p(), C.c_int32()
         self.ctx.call("msc_join_build", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.byref(table), C.byref(unique))
+        self._note_kernel("hash join: build")
         trel = self._track(DeviceRel.from_handle(self.ctx, table.value, [L.INT], [None]))
         if not unique.value:
             self._probe_declined = lrel  # (the materialising join reuses the build side it already has)
@@ -1048,7 +1117,7 @@ class CudaExecutionEngine(ExecutionEngine):
             partitioned = True
         pairs = C.c_void_p()
         self.ctx.call("msc_hash_join", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.c_void_p(rrel.cols[-1].ptr), rrel.nrows, C.byref(pairs))
-        self._note_kernel()
+        self._note_kernel("hash join: build + probe + emit")
         prel = self._track(DeviceRel.from_handle(self.ctx, pairs.value, [L.INT, L.INT], [None, None]))
         columns: dict[int, DeviceColumn] = {}
         for pos, i in enumerate(left_needed):

@@ -266,9 +266,7 @@ def _lower_binary(col: Any, schema: Schema) -> Expr:
     if lt != rt:
         raise TypeError(f"Type mismatch in binary operation: {lt} {op} {rt}")
     if op in _CMP:
-        if lt == STR and op not in ("eq", "ne"):
-            raise LoweringError("ordering comparisons on STRING are not implemented on the GPU engine")
-        return EBin(BOOL, op, left, right)
+        return EBin(BOOL, op, left, right)  # (STRING <, <=, >, >= compare like Python strings: through the dictionaries' order)
     if lt == STR:
         if op != "add":
             raise TypeError(f"unsupported operand type(s) for {op}: 'str' and 'str'")
@@ -559,6 +557,8 @@ class Resolver(Protocol):
     def translate_lut(self, dict_id: Any, token: str) -> tuple[int, Any]: ...  # -> (LUT slot, target dict)
     def same_dict(self, a: Any, b: Any) -> bool: ...
     def recode_lut(self, src: Any, dst: Any) -> int: ...                  # LUT slot: codes of src -> codes of dst
+    def order_lut(self, dict_id: Any, op: str, text: str) -> int: ...     # LUT slot (u8): entry <op> text, op in lt/le/gt/ge
+    def rank_luts(self, a: Any, b: Any) -> tuple[int, int]: ...           # LUT slots (u32): ranks of both dictionaries' entries in their common order
 
 
 MAX_TEMPS = K["MSC_VM_MAX_TEMPS"]
@@ -795,6 +795,8 @@ class ProgramBuilder:
 
     def _string_compare(self, e: EBin) -> tuple[str, int, int, list[int]]:
         left, right = e.left, e.right
+        if e.op in ("lt", "le", "gt", "ge"):
+            return self._string_order(e)
         if isinstance(left, EConst) and not isinstance(right, EConst):
             left, right = right, left
         opname = "EQ_I" if e.op == "eq" else "NE_I"
@@ -811,6 +813,28 @@ class ProgramBuilder:
             self.release(frees_b)
             b, frees_b = src(SRC_TEMP, t), [t]
         return opname, a, b, frees + frees_b
+
+    def _string_order(self, e: EBin) -> tuple[str, int, int, list[int]]:
+        """STRING <, <=, >, >= (Python compares code points, sql.py:262-266; the format is ASCII, io.py:101): against a
+        literal a u8 lookup table over the column's dictionary entries, between two columns the entries' ranks in the
+        common order of both dictionaries."""
+        import operator as _op
+
+        left, right, op = e.left, e.right, e.op
+        if isinstance(left, EConst) and isinstance(right, EConst):
+            return "MOV", src(SRC_CONST, self.const(int(getattr(_op, op)(left.value, right.value)))), 0, []
+        if isinstance(left, EConst):  # literal <op> column  ==  column <flipped op> literal
+            left, right, op = right, left, {"lt": "gt", "le": "ge", "gt": "lt", "ge": "le"}[op]
+        a, frees, d = self.string_operand(left)
+        if isinstance(right, EConst):
+            return "LUT8", a, src(SRC_LUT, self.r.order_lut(d, op, right.value)), frees
+        b, frees_b, d2 = self.string_operand(right)
+        slot_a, slot_b = self.r.rank_luts(d, d2)
+        ta, tb = self.alloc(), self.alloc()
+        self.emit("LUT32", a, src(SRC_LUT, slot_a), DST_TEMP, ta)
+        self.emit("LUT32", b, src(SRC_LUT, slot_b), DST_TEMP, tb)
+        self.release(frees + frees_b)
+        return _I_OPS[op], src(SRC_TEMP, ta), src(SRC_TEMP, tb), [ta, tb]
 
     # -- one expression root into a destination -------------------------------------------------
     def materialize(self, e: Expr, dkind: int, didx: int = 0, agg_kind: Optional[int] = None, out_u32: bool = False) -> Any:

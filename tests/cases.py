@@ -235,6 +235,13 @@ DF_CASES: dict[str, tuple[Callable[[Any, dict, Any], Any], Any, bool]] = {
         ns.F.sum(ns.Col("quantity")).alias("k"), ns.F.max(ns.Col("quantity")).alias("l"), ns.F.count()), None, False),
     "agg_float_filter": (lambda ns, t, e: _df(ns, e, t["orders"]).filter(ns.Col("price") <= 300.0).filter(ns.Col("order_date") > "2025-01-01")
         .group_by(ns.Col("product")).agg(ns.F.sum(ns.Col("price")).alias("s"), ns.F.min(ns.Col("price")).alias("lo")), None, False),
+    # STRING ordering (Python string order, sql.py:262-266): against a literal, literal on the left, between two columns
+    "string_order_literal": (lambda ns, t, e: _df(ns, e, t["users"]).filter((ns.Col("first_name") >= "F") & (ns.Col("last_name") < "Smith"))
+                             .select(ns.Col("first_name"), ns.Col("last_name")), None, True),
+    "string_order_columns": (lambda ns, t, e: _df(ns, e, t["users"]).filter(ns.Col("first_name") > ns.Col("last_name"))
+                             .filter(ns.Col("country") <= ns.Col("first_name")).select(ns.Col("first_name"), ns.Col("last_name"), ns.Col("country")), None, True),
+    "string_order_group": (lambda ns, t, e: _df(ns, e, t["orders"]).filter(ns.Lit("Laptop") < ns.Col("product")).group_by(ns.Col("product"))
+                           .agg(ns.F.count(), ns.F.sum(ns.Col("quantity")).alias("q")), None, False),
     "empty_result": (lambda ns, t, e: _df(ns, e, t["orders"]).filter(ns.Col("price") > 1e9), [], True),
     "concat_filter": (lambda ns, t, e: _df(ns, e, t["users"]).filter(ns.Col("age") < 30).select(
         (ns.Col("first_name") + "-" + ns.Col("country")).alias("tag"), ns.Col("age")), None, True),

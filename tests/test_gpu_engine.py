@@ -146,3 +146,30 @@ def test_table_cache_and_reingest(engine, tables):
     a = df().collect()
     engine.drop_table_cache()
     assert df().collect() == a
+
+
+def test_trace_of_a_query(tables, tmp_path):
+    """TRACER.save() after a query gives a Perfetto trace with the reference's slices (execution.py:69-78) on the main
+    track and the library's CUDA-event durations on the GPU's track."""
+    from minispark_b200.utils import TRACER, parse_trace
+
+    TRACER.enable()
+    try:
+        with CudaExecutionEngine() as engine:
+            build = cases.DF_CASES["groupby_multi"][0]
+            rows = build(cases.namespace(), tables, engine).collect()
+            assert len(rows) == 3
+            TRACER.save(str(tmp_path / "trace.pftrace"))
+    finally:
+        TRACER.enable(False)
+    packets = parse_trace((tmp_path / "trace.pftrace").read_bytes())
+    names = [p["event"]["name"] for p in packets if "event" in p and p["event"]["name"]]
+    assert "execute full task" in names and "Execution" in names and "write result BlockFile" in names
+    assert any(n.startswith("scan: filter + aggregate") for n in names) and any(n.startswith("load table block") for n in names)
+    gpu_tracks = [p["track"]["uuid"] for p in packets if "track" in p and p["track"]["name"].startswith("GPU")]
+    assert len(gpu_tracks) == 1
+    on_gpu = [p for p in packets if "event" in p and p["event"]["track"] == gpu_tracks[0]]
+    assert len(on_gpu) >= 4 and len(on_gpu) % 2 == 0
+    begins = sum(1 for p in packets if "event" in p and p["event"]["type"] == 1)
+    ends = sum(1 for p in packets if "event" in p and p["event"]["type"] == 2)
+    assert begins == ends

@@ -73,7 +73,7 @@ def test_queries_that_are_not_kept(tmp_path, tables):
             want = O.run_task(build(ns, tables, None).task, wire=True)
             for _ in range(3):
                 O.assert_rows_equal(build(ns, tables, engine).collect(), want, ordered=ordered)
-            assert engine.last_stats["plan"] == "one-shot", name
+            assert engine.last_stats["plan"].startswith("one-shot"), name  # (never a prepared pass; repeats get specialised kernels)
         # with the cache off nothing is prepared
         engine.plan_cache_enabled = False
         build = cases.DF_CASES["groupby_multi"][0]

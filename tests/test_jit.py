@@ -260,3 +260,95 @@ def test_streaming_aggregate_over_sorted_runs_compiles(tmp_path):
     assert "msc_jit_runs" in src and "fold_segment<0>" in src and "fold_segment<3>" in src   # SUM_F and MAX_F accumulators
     assert "p.tile_offsets[tile]" in src and "out_key[run0] = key[r]" in src
     compile_source(src)
+
+
+class _ProbeResolver:
+    """Probe side: l_orderkey (i32), l_shipmode (u8 code), l_extendedprice (f32) staged; build side: o_orderpriority (u32 code)
+    read through the probe's match (Binding.probe) -- the consumer scan of BASELINE config 5."""
+
+    def __init__(self):
+        from test_lowering import StubDict
+
+        self.staged: list[int] = []
+        self.gather: list[int] = []
+        self.dicts = {1: StubDict(["AIR", "MAIL", "REG AIR"]), 100: StubDict(["1-URGENT", "2-HIGH", "3-MEDIUM", "4-NOT SPECIFIED", "5-LOW"])}
+        self.phys = {0: N.P_I32, 1: N.P_U8, 2: N.P_F32, 100: N.P_U32}
+
+    def binding(self, index):
+        from minispark_b200 import lowering as L
+
+        if index >= 100:
+            if index not in self.gather:
+                self.gather.append(index)
+            return L.Binding(self.phys[index], gather=self.gather.index(index), dict_id=self.dicts.get(index), probe=True)
+        if index not in self.staged:
+            self.staged.append(index)
+        return L.Binding(self.phys[index], staged=self.staged.index(index), dict_id=self.dicts.get(index))
+
+    def like_lut(self, dict_id, pattern):
+        return 1
+
+    def literal_code(self, dict_id, text):
+        return dict_id.entries.index(text)
+
+    def same_dict(self, a, b):
+        return a is b
+
+
+def _probe_desc(prog, res) -> N.ScanDesc:
+    d = N.ScanDesc()
+    d.nrows = 1 << 20
+    d.nstaged, d.ngather, d.nluts = len(res.staged), len(res.gather), 2
+    for i, index in enumerate(res.staged):
+        d.staged[i].phys = res.phys[index]
+    for i, index in enumerate(res.gather):
+        d.gather[i].phys = res.phys[index]
+    words = prog.program.words()
+    d.ncode = len(words)
+    for i, w in enumerate(words):
+        d.code[i] = w
+    d.nconsts = len(prog.program.consts)
+    for i, c in enumerate(prog.program.consts):
+        d.consts[i] = c
+    d.ntemps = prog.program.ntemps
+    return d
+
+
+def test_fused_join_probe_compiles(tmp_path):
+    """A join carried by the consuming scan (MSC_OP_PROBE + build-side columns through the matched row): the program the
+    lowering emits and the specialised kernels generated from it, as a dense aggregate and as a filter / project scan."""
+    from minispark_b200 import lowering as L
+
+    res = _ProbeResolver()
+    like = L.ELike(L.BOOL, L.EInput(L.STR, 1), "%AIR%")
+    probe = L.ProbeSpec(L.EInput(L.INT, 0), 0)
+    prog = L.compile_aggregate(res, [], L.EInput(L.STR, 100), [("count", L.EConst(L.INT, 1)), ("sum", L.EInput(L.FLOAT, 2))],
+                               probe=probe, pre_filters=[like])
+    text = prog.program.text
+    assert text[0].startswith("filter <- LUT8(col0, lut1)") and text[1].startswith("t0 <- PROBE(col1, lut0)")
+    assert text[2].startswith("filter <- GE_I(t0, const0)") and text[3].startswith("group <- MOV(gather0[t0], -)")
+    assert prog.program.regvm == []  # the register interpreter has no probe: the C++ interpreter or a specialised kernel runs it
+    lib = N.load()
+    d = _probe_desc(prog, res)
+    n = C.c_size_t()
+    buf = C.create_string_buffer(1 << 20)
+    for masked in (1, 0):
+        rc = lib.msc_jit_dense_source(C.byref(d), 5, N.int32_array(prog.agg_kinds), len(prog.agg_kinds), masked, buf, len(buf), C.byref(n))
+        src = buf.value.decode()
+        assert rc == 0, src
+        # the dense scan splits its row loop around the probe: all of a lane's table reads are issued, then resolved
+        assert "join_probe_issue(p.luts[0], c1[r], valid, pkey[r], ppos[r], praw[r])" in src
+        assert "t0[r] = join_probe_resolve(p.luts[0], pkey[r], ppos[r], praw[r], valid)" in src
+        assert "gather_at<2>(p.gather[0], t0[r], valid && t0[r] >= 0)" in src
+        compile_source(src)
+    res2 = _ProbeResolver()
+    proj = L.compile_project(res2, [L.EBin(L.BOOL, "gt", L.EInput(L.FLOAT, 2), L.EConst(L.FLOAT, 10.0))],
+                             [L.EInput(L.INT, 0), L.EInput(L.STR, 100), L.EInput(L.FLOAT, 2)], probe=L.ProbeSpec(L.EInput(L.INT, 0), 0), pre_filters=[])
+    assert any("RANK" in t for t in proj.program.text), proj.program.text
+    d2 = _probe_desc(proj, res2)
+    for count_only in (1, 0):
+        rc = lib.msc_jit_project_source(C.byref(d2), count_only, N.int32_array(proj.out_phys), len(proj.out_phys), buf, len(buf), C.byref(n))
+        src = buf.value.decode()
+        assert rc == 0, src
+        assert "join_probe(p.luts[0]" in src
+        compile_source(src)
