@@ -166,6 +166,16 @@ const char* ld_fn(int phys) {
 
 bool is_float_kind(int k) { return k == MSC_AGG_SUM_F || k == MSC_AGG_MIN_F || k == MSC_AGG_MAX_F; }
 
+// a scan that probes a join table keeps the table in L2 by streaming its columns through with an evict-first policy
+bool program_probes(const msc_scan_desc* sd) {
+  for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+    const int op = sd->code[pc] & 0x3f;
+    if (op == MSC_OP_END) break;
+    if (op == MSC_OP_PROBE) return true;
+  }
+  return false;
+}
+
 struct Gen {
   const msc_scan_desc* sd;
   int ngroups, naggs, stride;  // stride = naggs, or naggs + 1 with the hidden per-group row counter in slot naggs
@@ -362,7 +372,7 @@ struct Gen {
       why = "count scan without a filter";
       return false;
     }
-    o << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
+    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
     o << "constexpr int NSTAGES = " << nstages << ";\n";
     emit_layout(lay);
     o << R"(
@@ -489,7 +499,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_scan(const __g
   bool generate_runs(int key_col) {
     const Layout lay = stage_layout(sd);
     temp_arrays = false;
-    o << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
+    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
     o << "constexpr int NSTAGES = " << nstages << ";\n";
     emit_layout(lay);
     o << R"(
@@ -652,7 +662,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
     }
 
     // registers: 2 per accumulator cell; up to 32 cells fit 4 CTAs of 128 threads per SM (128 registers), more need 3 (168)
-    o << "#define MINCTAS " << (ngroups * stride <= JIT_REG_CELLS_4CTAS ? 4 : 3) << "\n" << kPrelude;
+    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << (ngroups * stride <= JIT_REG_CELLS_4CTAS ? 4 : 3) << "\n" << kPrelude;
     if (masked) {  // the masks are fixed at GROUP: a later filter would not reach them
       bool grouped_seen = false;
       for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
@@ -769,7 +779,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     bool ok = true, grouped = false;
     if (probe_pc >= 0) {
       for (int t = 0; t < sd->ntemps; ++t) o << "    i64 t" << t << "[R];\n";
-      o << "    u64 pkey[R], ppos[R]; uint4 praw[R]; u32 vm = 0;\n#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = (vmask >> r) & 1u;\n";
+      o << "    JoinProbe pq[R]; u32 vm = 0;\n#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = (vmask >> r) & 1u;\n";
       for (int t = 0; t < sd->ntemps; ++t) o << "      t" << t << "[r] = 0;\n";
       for (int pc = 0; pc < probe_pc; pc += 2) {
         const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
@@ -789,7 +799,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       {
         const uint32_t w1 = sd->code[probe_pc + 1];
         const std::string a = operand(w1 & 0xffffu, &ok);
-        o << "      join_probe_issue(p.luts[" << ((w1 >> 16) & 0xfff) << "], " << a << ", valid, pkey[r], ppos[r], praw[r]);  // instruction "
+        o << "      join_probe_issue(p.luts[" << ((w1 >> 16) & 0xfff) << "], " << a << ", valid, pq[r]);  // instruction "
           << probe_pc / 2 << ", first half\n";
       }
       o << "      vm |= (valid ? 1u : 0u) << r;\n    }\n";
@@ -805,7 +815,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       for (int t = 0; t < sd->ntemps; ++t) o << "      i64 t" << t << " = 0;\n";
     } else {
       const uint32_t w0 = sd->code[probe_pc], w1 = sd->code[probe_pc + 1];
-      o << "      " << temp((w0 >> 13) & 0x7f) << " = join_probe_resolve(p.luts[" << ((w1 >> 16) & 0xfff) << "], pkey[r], ppos[r], praw[r], valid);  // instruction "
+      o << "      " << temp((w0 >> 13) & 0x7f) << " = join_probe_resolve(p.luts[" << ((w1 >> 16) & 0xfff) << "], pq[r], valid);  // instruction "
         << probe_pc / 2 << ", second half\n";
     }
     for (int pc = probe_pc >= 0 ? probe_pc + 2 : 0; pc + 1 < sd->ncode; pc += 2) {

@@ -10,6 +10,8 @@
 // msc_partition replaces WriteToShufflePartitions.write (tasks.py:347-375) / zig fill_buckets
 // (task_utils.zig:53-98): rows are routed by hash(key) % nparts into partition-contiguous order (stable: input order
 // inside every partition), ready for the exchange between ranks (shuffle.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "join_table.cuh"
 
@@ -34,12 +36,17 @@ __global__ void join_init_kernel(JoinSlot* slots, uint64_t cap) {
 
 // build: key -> chain of left rows (slot.head -> next[row] -> ...)
 __global__ void join_build_kernel(const long long* keys, uint32_t n, JoinSlot* slots, uint32_t* next, uint64_t cap,
-                                  unsigned long long* duplicates = nullptr) {
+                                  unsigned long long* duplicates = nullptr, uint32_t* bitmap = nullptr, uint64_t bitmap_bits = 0) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long k = norm_key(keys[i]);
   const uint64_t mask = cap - 1;
-  uint64_t pos = msc_mix64(k) & mask;
+  const uint64_t hash = msc_mix64(k);
+  if (bitmap) {
+    const uint64_t bit = (hash >> 32) & (bitmap_bits - 1);
+    atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+  }
+  uint64_t pos = hash & mask;
   while (true) {  // find-or-insert in one atomic per step: the old value says "inserted", "found" or "someone else's"
     const unsigned long long prev = atomicCAS(&slots[pos].key, J_EMPTY, k);
     if (prev == J_EMPTY || prev == k) break;
@@ -48,6 +55,38 @@ __global__ void join_build_kernel(const long long* keys, uint32_t n, JoinSlot* s
   const uint32_t before = atomicExch(&slots[pos].head, i);
   if (next) next[i] = before;
   if (atomicAdd(&slots[pos].len, 1u) != 0 && duplicates) *duplicates = 1;  // (any writer stores the same value)
+}
+
+// compact table (8-byte slots, 32-bit keys, no chains: a second row with the same key only raises the flag)
+__global__ void join_init8_kernel(unsigned long long* slots, uint64_t cap) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < cap; i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    slots[i] = MSC_J_EMPTY8;
+}
+
+__global__ void join_build8_kernel(const long long* keys, uint32_t n, unsigned long long* slots, uint64_t cap, MscJoinTableHeader* header,
+                                   uint32_t* bitmap, uint64_t bitmap_bits) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long key = keys[i];
+  if (!msc_join_key_is_32bit(key)) {
+    header->wide_keys = 1;
+    return;
+  }
+  const uint32_t k32 = static_cast<uint32_t>(key);
+  const unsigned long long mine = (static_cast<unsigned long long>(i) << 32) | k32;
+  const uint64_t mask = cap - 1;
+  const uint64_t bit = msc_fmix32(k32 ^ 0x9e3779b9u) & (bitmap_bits - 1);
+  atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+  uint64_t pos = msc_fmix32(k32) & mask;
+  while (true) {
+    const unsigned long long prev = atomicCAS(&slots[pos], MSC_J_EMPTY8, mine);
+    if (prev == MSC_J_EMPTY8) break;
+    if (static_cast<uint32_t>(prev) == k32) {
+      header->duplicates = 1;
+      break;
+    }
+    pos = (pos + 1) & mask;
+  }
 }
 
 // chain head of key k (NIL: no match) and the chain's length
@@ -275,43 +314,61 @@ extern "C" int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nl
 }
 
 // The build half alone, for scans that probe per row (MSC_OP_PROBE): a 1-column relation that owns [header][slots].
+// Compact 8-byte slots first (32-bit keys: INTEGER columns, dictionary codes); a key outside that range rebuilds wide.
 extern "C" int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, msc_rel** out_table, int32_t* unique) {
   if (!ctx || !out_table || !unique || (nkeys && !keys)) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   if (nkeys >= NIL) return ctx->fail(MSC_ERR_ARG, "join side exceeds 2^32-1 rows");
   uint64_t cap = 64;
-  while (cap < nkeys * 2) cap <<= 1;
-  msc_rel* rel = new msc_rel();
-  rel->ctx = ctx;
-  rel->nrows = cap;
-  msc_col c;
-  c.phys = MSC_P_U8;
-  c.bytes = sizeof(MscJoinTableHeader) + cap * sizeof(JoinSlot);
-  int rc = msc_alloc(ctx, c.bytes, &c.data);
-  if (rc != MSC_OK) {
-    delete rel;
-    return rc;
-  }
-  rel->cols.push_back(c);
+  while (cap < nkeys + nkeys / 2) cap <<= 1;  // load <= 2/3: the smaller the table, the more of it stays in L2
+  static const bool compact_enabled = !(getenv("MSC_JOIN_COMPACT") && atoi(getenv("MSC_JOIN_COMPACT")) == 0);
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
-  MscJoinTableHeader h{cap, 0};
-  MSC_CUDA(ctx, cudaMemcpyAsync(c.data, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-  JoinSlot* slots = reinterpret_cast<JoinSlot*>(static_cast<char*>(c.data) + sizeof(MscJoinTableHeader));
-  join_init_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(slots, cap);
-  ctx->stats.launches += 1;
-  if (nkeys) {
-    join_build_kernel<<<grid_for(nkeys, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(keys), static_cast<uint32_t>(nkeys), slots,
-                                                                   nullptr, cap, &static_cast<MscJoinTableHeader*>(c.data)->duplicates);
-    ctx->stats.launches += 1;
+  for (int attempt = compact_enabled ? 0 : 1; attempt < 2; ++attempt) {
+    const bool compact = attempt == 0;
+    msc_rel* rel = new msc_rel();
+    rel->ctx = ctx;
+    rel->nrows = cap;
+    msc_col c;
+    c.phys = MSC_P_U8;
+    uint64_t bitmap_bits = 1024;
+    while (bitmap_bits < nkeys * 16 && bitmap_bits < (1ull << 32)) bitmap_bits <<= 1;
+    c.bytes = sizeof(MscJoinTableHeader) + bitmap_bits / 8 + cap * (compact ? 8 : sizeof(JoinSlot));
+    int rc = msc_alloc(ctx, c.bytes, &c.data);
+    if (rc != MSC_OK) {
+      delete rel;
+      return rc;
+    }
+    rel->cols.push_back(c);
+    MscJoinTableHeader* header = static_cast<MscJoinTableHeader*>(c.data);
+    MscJoinTableHeader* h = reinterpret_cast<MscJoinTableHeader*>(ctx->h_scratch);  // pinned, 16 words
+    *h = MscJoinTableHeader{cap, 0, compact ? 8ull : 16ull, 0, bitmap_bits, {0, 0, 0}};
+    MSC_CUDA(ctx, cudaMemcpyAsync(header, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(static_cast<char*>(c.data) + sizeof(MscJoinTableHeader));
+    MSC_CUDA(ctx, cudaMemsetAsync(bitmap, 0, bitmap_bits / 8, ctx->stream));
+    void* slots = static_cast<char*>(c.data) + sizeof(MscJoinTableHeader) + bitmap_bits / 8;
+    const uint32_t n = static_cast<uint32_t>(nkeys);
+    if (compact) {
+      join_init8_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(static_cast<unsigned long long*>(slots), cap);
+      if (n) join_build8_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(keys), n, static_cast<unsigned long long*>(slots), cap, header, bitmap, bitmap_bits);
+    } else {
+      join_init_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(static_cast<JoinSlot*>(slots), cap);
+      if (n) join_build_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(keys), n, static_cast<JoinSlot*>(slots), nullptr, cap, &header->duplicates, bitmap, bitmap_bits);
+    }
+    ctx->stats.launches += n ? 2 : 1;
+    MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    MSC_CUDA(ctx, cudaMemcpyAsync(h, header, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+    MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MSC_CUDA(ctx, cudaGetLastError());
+    if (compact && h->wide_keys) {  // (INTEGER arithmetic, TIMESTAMP or FLOAT keys)
+      msc_rel_free(rel);
+      continue;
+    }
+    *unique = h->duplicates == 0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+    *out_table = rel;
+    return MSC_OK;
   }
-  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
-  MSC_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, c.data, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  MSC_CUDA(ctx, cudaGetLastError());
-  *unique = ctx->h_scratch[1] == 0;
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
-  *out_table = rel;
-  return MSC_OK;
+  return ctx->fail(MSC_ERR_ARG, "join build: unreachable");
 }
 
 extern "C" int msc_partition(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t nparts, uint64_t* counts_host, msc_rel** out) {

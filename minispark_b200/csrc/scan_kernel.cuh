@@ -485,10 +485,43 @@ template <int R>
 __device__ __forceinline__ void op_probe(long long (&x)[R], const void* table, uint32_t vmask) {
   const MscJoinTableHeader* h = static_cast<const MscJoinTableHeader*>(table);
   const uint64_t mask = h->cap - 1;
-  const uint4* slots = reinterpret_cast<const uint4*>(h + 1);
-  unsigned long long key[R];
   uint64_t pos[R];
   bool pend[R];
+  if (h->slot_bytes == 8) {  // compact: u64 = build row << 32 | (u32)key
+    const unsigned long long* slots = reinterpret_cast<const unsigned long long*>(msc_join_slots(h));
+    uint32_t key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      pend[r] = ((vmask >> r) & 1u) && msc_join_key_is_32bit(x[r]);
+      key[r] = static_cast<uint32_t>(x[r]);
+      pos[r] = msc_fmix32(key[r]) & mask;
+      x[r] = -1;
+    }
+    while (true) {
+      unsigned long long raw[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (pend[r]) raw[r] = __ldg(slots + pos[r]);
+      bool more = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!pend[r]) continue;
+        if (raw[r] == MSC_J_EMPTY8) {
+          pend[r] = false;
+        } else if (static_cast<uint32_t>(raw[r]) == key[r]) {
+          x[r] = static_cast<long long>(raw[r] >> 32);
+          pend[r] = false;
+        } else {
+          pos[r] = (pos[r] + 1) & mask;
+          more = true;
+        }
+      }
+      if (!more) break;
+    }
+    return;
+  }
+  const uint4* slots = reinterpret_cast<const uint4*>(msc_join_slots(h));
+  unsigned long long key[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     key[r] = msc_join_norm_key(x[r]);

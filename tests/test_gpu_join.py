@@ -87,10 +87,30 @@ def _star_queries(ns, t, e):
         "three_tables_rows": (tbl("codes", True).join(tbl("facts").filter(C("f_x") > 950), on=C("k_code") == C("f_code"), how="inner")
                               .select(C("f_id"), C("f_dim"), C("k_region"))
                               .join(tbl("dims").select(C("d_id"), C("d_name")), on=C("f_dim") == C("d_id"), how="inner"), False),
+        # computed, negative keys (they still fit the compact 8-byte-slot table) ...
+        "negative_keys": (tbl("dims", True).select((C("d_id") - 300).alias("k1"), C("d_name"))
+                          .join(tbl("facts").select((C("f_dim") - 300).alias("k2"), C("f_x")), on=C("k1") == C("k2"), how="inner")
+                          .group_by(C("d_name")).agg(F.count(), F.min(C("k2")).alias("lo")), False),
+        # ... and keys that do not: FLOAT keys are f64 bit patterns (the build falls back to 16-byte slots)
+        "wide_keys": (tbl("dims", True).select((C("d_id") * 0.5).alias("k1"), C("d_w"))
+                      .join(tbl("facts").select((C("f_dim") * 0.5).alias("k2"), C("f_id")), on=C("k1") == C("k2"), how="inner")
+                      .filter(C("f_id") < 2000).group_by(C("d_w")).agg(F.count(), F.max(C("f_id")).alias("m")), False),
     }
 
 
-@pytest.mark.parametrize("name", ["rows_int_key", "agg_int_key", "str_key", "no_build_columns", "duplicate_build_keys", "filtered_build_side",
+def test_timestamp_join_keys(engine, tables):
+    """TIMESTAMP keys are 64-bit microsecond counts: the wide table format; every order date is unique."""
+    ns = cases.namespace()
+
+    def q(e):
+        a = ns.DataFrame(e).table(tables["orders"]).select(ns.Col("order_date").alias("d1"), ns.Col("product"))
+        b = ns.DataFrame().table(tables["orders"]).select(ns.Col("order_date").alias("d2"), ns.Col("price"))
+        return a.join(b, on=ns.Col("d1") == ns.Col("d2"), how="inner").filter(ns.Col("price") > 40).select(ns.Col("product"), ns.Col("price"), ns.Col("d2"))
+
+    O.assert_rows_equal(q(engine).collect(), O.run_task(q(None).task, wire=True))
+
+
+@pytest.mark.parametrize("name", ["negative_keys", "wide_keys", "rows_int_key", "agg_int_key", "str_key", "no_build_columns", "duplicate_build_keys", "filtered_build_side",
                                   "three_tables", "three_tables_rows"])
 def test_star_schema_joins(engine, star, name):
     ns = cases.namespace()

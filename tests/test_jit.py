@@ -337,8 +337,8 @@ def test_fused_join_probe_compiles(tmp_path):
         src = buf.value.decode()
         assert rc == 0, src
         # the dense scan splits its row loop around the probe: all of a lane's table reads are issued, then resolved
-        assert "join_probe_issue(p.luts[0], c1[r], valid, pkey[r], ppos[r], praw[r])" in src
-        assert "t0[r] = join_probe_resolve(p.luts[0], pkey[r], ppos[r], praw[r], valid)" in src
+        assert "join_probe_issue(p.luts[0], c1[r], valid, pq[r])" in src
+        assert "t0[r] = join_probe_resolve(p.luts[0], pq[r], valid)" in src
         assert "gather_at<2>(p.gather[0], t0[r], valid && t0[r] >= 0)" in src
         compile_source(src)
     res2 = _ProbeResolver()
