@@ -36,10 +36,15 @@ def main() -> None:
     folder = base / f"minispark_b200_cfg_{os.getuid()}"
     folder.mkdir(parents=True, exist_ok=True)
     lineitem, orders = folder / f"lineitem6_sf{args.sf:g}.bin", folder / f"orders_sf{args.sf:g}.bin"
+    if int(os.environ.get("RANK", "0")) != 0:
+        time.sleep(1.0)
+        while not (lineitem.exists() and orders.exists() and (folder / "ready").exists()):
+            time.sleep(0.2)
     if not lineitem.exists():
         gen_tpch.write_table(lineitem, "lineitem", sf=args.sf, columns=["l_orderkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_shipmode"], workers=16)
     if not orders.exists():
         gen_tpch.write_table(orders, "orders", sf=args.sf, columns=["o_orderkey", "o_orderdate", "o_orderpriority"], workers=16)
+    (folder / "ready").touch()
     ns = cases.namespace()
 
     def build(e):  # noqa: ANN001, ANN202
@@ -53,7 +58,14 @@ def main() -> None:
                 .group_by(ns.Col("o.o_orderpriority")).agg(ns.F.count(), ns.F.sum(ns.Col("l.l_extendedprice")).alias("rev")))
 
     log: list[tuple[str, float, float]] = []
-    with CudaExecutionEngine(device=0, shard=(0, 1), jit=args.jit) as e:
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # under torchrun: ONE table, sharded by the engine; rank 0 prints
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    with CudaExecutionEngine(device=local, shard=None if world > 1 else (0, 1), jit=args.jit) as e:
         task = build(e).task
         for _ in range(3):
             e.execute_to_device(task)
@@ -70,7 +82,7 @@ def main() -> None:
 
         N.Context.call = call
         lib = e.ctx.lib
-        for fname in ("msc_rel_info", "msc_rel_cols", "msc_dict_size", "msc_rel_free"):
+        for fname in ("msc_rel_info", "msc_rel_cols", "msc_dict_size", "msc_rel_free", "msc_shuffle_begin", "msc_shuffle_finish", "msc_shuffle_allgather"):
             orig = getattr(lib, fname)
 
             def wrap(*a, _orig=orig, _n=fname):  # noqa: ANN002, ANN202
@@ -92,9 +104,10 @@ def main() -> None:
             total = time.perf_counter() - t_base[0]
             e.release_query()
             in_calls = sum(d for _, _, d in log)
-            if rep == args.reps - 1:
+            if rep == args.reps - 1 and rank == 0:
                 print(f"config {args.config} sf{args.sf:g} jit={e.jit}: wall {1e3 * total:.3f} ms, inside library calls {1e3 * in_calls:.3f} ms, "
                       f"python {1e3 * (total - in_calls):.3f} ms, {len(log)} calls")
+                print("  join:", e.last_stats.get("join"), "| exchanges:", e.last_stats.get("exchanges"), "| plan:", e.last_stats.get("plan"))
                 for name, at, d in log:
                     print(f"  {1e3 * at:8.3f} ms  +{1e3 * d:7.3f}  {name}")
         N.Context.call, N.Context.check = orig_call, orig_check

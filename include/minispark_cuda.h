@@ -218,6 +218,9 @@ typedef struct msc_stats {
   int32_t last_scan_regs;   /* registers per thread of a specialised kernel (0 otherwise) */
   uint64_t jit_compiles;    /* specialised kernels compiled by this ctx since creation */
   double last_jit_compile_ms; /* host time of the last NVRTC compilation (or on-disk cache hit) */
+  int32_t last_agg_runs;    /* != 0: the last msc_scan_aggregate streamed over the runs of a sorted key, so its result rows
+                             * ascend by key (what a range-partitioned shuffle of partial results builds on) */
+  int32_t _pad;
 } msc_stats;
 #define MSC_SCAN_KIND_VM 0    /* C++ three-address interpreter (scan_kernel.cuh) */
 #define MSC_SCAN_KIND_REGVM 1 /* register-resident PTX interpreter (scan_regvm_impl.cuh) */
@@ -467,9 +470,16 @@ MSC_API int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, ms
  * fill_buckets (task_utils.zig:53-98).  Rows are routed by hash(key) % nparts; every column is
  * scattered into partition-contiguous order, STABLE (rows of a partition keep their input order, as the reference's
  * per-bucket appends do).  counts[nparts] (host) receives rows per partition.  Output relation has the same columns,
- * permuted. ---------------------------------------------------------------------------------- */
+ * permuted.  When the rows are partition-contiguous already (one partition; a sorted key routed by range) nothing is
+ * copied: the result SHARES the input's columns, and `rel` must stay alive as long as `*out` is used. -------------- */
 MSC_API int msc_partition(msc_ctx* ctx, msc_rel* rel, int32_t key_col, int32_t nparts, uint64_t* counts,
                   msc_rel** out);
+/* the same by key RANGE: partition p receives the rows with lower_bounds[p] <= key < lower_bounds[p + 1] (signed 64-bit
+ * compare; lower_bounds[0] is ignored = -infinity; the bounds must not decrease).  A sorted input stays sorted inside
+ * every partition -- what lets the final aggregate after a shuffle of sorted partial results stream over runs instead of
+ * probing a hash table. */
+MSC_API int msc_partition_range(msc_ctx* ctx, msc_rel* rel, int32_t key_col, int32_t nparts, const int64_t* lower_bounds,
+                        uint64_t* counts, msc_rel** out);
 
 /* ---- row exchange between ranks over NVLink peer memory: replaces the shuffle FILES between stages --
  * WriteToShufflePartitions.write (tasks.py:347-375) on the sending side, LoadShuffleFilesTask (tasks.py:144-150,
@@ -504,6 +514,9 @@ MSC_API int msc_shuffle_slot_attach(msc_shuffle* sh, int32_t slot, const void* h
 MSC_API int msc_shuffle_slot_detach(msc_shuffle* sh, int32_t slot);
 MSC_API int msc_shuffle_slot_bytes(msc_shuffle* sh, int32_t slot, size_t* nbytes);
 MSC_API int msc_shuffle_begin(msc_shuffle* sh, msc_rel* rel, int32_t key_col, uint64_t epoch, uint64_t* matrix, uint64_t* need_bytes);
+/* msc_shuffle_begin with rank r receiving the keys in [lower_bounds[r], lower_bounds[r + 1]) (msc_partition_range) */
+MSC_API int msc_shuffle_begin_range(msc_shuffle* sh, msc_rel* rel, int32_t key_col, const int64_t* lower_bounds, uint64_t epoch,
+                            uint64_t* matrix, uint64_t* need_bytes);
 MSC_API int msc_shuffle_finish(msc_shuffle* sh, int32_t slot, uint64_t epoch, msc_rel** out);
 MSC_API int msc_shuffle_wait(msc_shuffle* sh, double* ms);
 MSC_API int msc_shuffle_allgather(msc_shuffle* sh, const void* src_dev, size_t nbytes, uint64_t epoch, void* dst_dev);

@@ -177,20 +177,40 @@ __device__ __forceinline__ long long read_key(const void* col, int phys, uint64_
   }
 }
 
-// partition id from the HIGH hash bits: the aggregation / join tables index with the low bits
-__device__ __forceinline__ int part_of(long long key, int nparts) {
+// Range partitioning: partition p holds the keys in [lo[p], lo[p + 1]) (lo[0] = -inf); use == 0: hash partitioning.
+struct PartBounds {
+  long long lo[MAX_PARTS];
+  int use;
+};
+
+// partition id from the HIGH hash bits (the aggregation / join tables index with the low bits), or by key range
+__device__ __forceinline__ int part_of(long long key, int nparts, const PartBounds& b) {
+  if (b.use) {
+    int p = 0;
+    for (int i = 1; i < nparts; ++i) p += key >= b.lo[i];
+    return p;
+  }
   return static_cast<int>((msc_mix64(norm_key(key)) >> 32) % static_cast<unsigned>(nparts));
 }
 
-__global__ void part_hist_kernel(const void* key, int phys, uint64_t n, int nparts, uint32_t nblocks, uint32_t* hist) {
+// per-block histogram; *disorder is raised when some row's partition is lower than its predecessor's (rows that are not
+// yet partition-contiguous)
+__global__ void part_hist_kernel(const void* key, int phys, uint64_t n, int nparts, uint32_t nblocks, uint32_t* hist,
+                                 const __grid_constant__ PartBounds bounds, int* disorder) {
   __shared__ uint32_t h[MAX_PARTS];
   if (threadIdx.x < MAX_PARTS) h[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t base = static_cast<uint64_t>(blockIdx.x) * PBLOCK;
+  bool down = false;
   for (int i = threadIdx.x; i < PBLOCK; i += PTHREADS) {
     const uint64_t r = base + i;
-    if (r < n) atomicAdd(&h[part_of(read_key(key, phys, r), nparts)], 1u);
+    if (r < n) {
+      const int p = part_of(read_key(key, phys, r), nparts, bounds);
+      atomicAdd(&h[p], 1u);
+      if (r > 0 && part_of(read_key(key, phys, r - 1), nparts, bounds) > p) down = true;
+    }
   }
+  if (down) *disorder = 1;
   __syncthreads();
   if (threadIdx.x < nparts) hist[static_cast<uint64_t>(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];
 }
@@ -200,7 +220,7 @@ __global__ void part_hist_kernel(const void* key, int phys, uint64_t n, int npar
 // inside a warp equal partitions find each other with match.any, the lane's rank among them is a popcount, the warps'
 // counts are prefix-summed in shared memory, and the per-partition cursor moves on once per step.
 __global__ void part_pos_kernel(const void* key, int phys, uint64_t n, int nparts, uint32_t nblocks,
-                                const uint64_t* offsets, uint32_t* pos, uint8_t* part) {
+                                const uint64_t* offsets, uint32_t* pos, uint8_t* part, const __grid_constant__ PartBounds bounds) {
   constexpr int NW = PTHREADS / 32;
   __shared__ unsigned long long cursor[MAX_PARTS];
   __shared__ uint32_t wcount[NW][MAX_PARTS];
@@ -213,7 +233,7 @@ __global__ void part_pos_kernel(const void* key, int phys, uint64_t n, int npart
     for (int i = tid; i < NW * MAX_PARTS; i += PTHREADS) (&wcount[0][0])[i] = 0;
     __syncthreads();
     const bool valid = r < n;
-    const int p = valid ? part_of(read_key(key, phys, r), nparts) : MAX_PARTS;  // rows past the end group among themselves
+    const int p = valid ? part_of(read_key(key, phys, r), nparts, bounds) : MAX_PARTS;  // rows past the end group among themselves
     const unsigned same = __match_any_sync(0xffffffffu, p);
     const uint32_t rank = __popc(same & ((1u << lane) - 1u));
     if (valid && rank == 0) wcount[warp][p] = __popc(same);
@@ -371,10 +391,33 @@ extern "C" int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys,
   return ctx->fail(MSC_ERR_ARG, "join build: unreachable");
 }
 
+static int partition_impl(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t nparts, const int64_t* lower_bounds, uint64_t* counts_host,
+                          msc_rel** out);
+
 extern "C" int msc_partition(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t nparts, uint64_t* counts_host, msc_rel** out) {
+  return partition_impl(ctx, in, key_col, nparts, nullptr, counts_host, out);
+}
+
+extern "C" int msc_partition_range(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t nparts, const int64_t* lower_bounds, uint64_t* counts_host,
+                                   msc_rel** out) {
+  if (!lower_bounds) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  return partition_impl(ctx, in, key_col, nparts, lower_bounds, counts_host, out);
+}
+
+static int partition_impl(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t nparts, const int64_t* lower_bounds, uint64_t* counts_host,
+                          msc_rel** out) {
   if (!ctx || !in || !out || !counts_host || nparts < 1 || nparts > MAX_PARTS || key_col < 0 ||
       key_col >= static_cast<int32_t>(in->cols.size()))
     return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  PartBounds pb;
+  memset(&pb, 0, sizeof(pb));
+  if (lower_bounds) {
+    pb.use = 1;
+    for (int p = 1; p < nparts; ++p) {
+      if (p > 1 && lower_bounds[p] < lower_bounds[p - 1]) return ctx->fail(MSC_ERR_ARG, "partition bounds must not decrease");
+      pb.lo[p] = lower_bounds[p];
+    }
+  }
   const uint64_t n = in->nrows;
   msc_rel* rel = new msc_rel();
   rel->ctx = ctx;
@@ -398,14 +441,41 @@ extern "C" int msc_partition(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
   const uint32_t nblocks = static_cast<uint32_t>((n + PBLOCK - 1) / PBLOCK);
   const uint64_t cells = static_cast<uint64_t>(nblocks) * nparts;
-  DevTmp hist(ctx), offsets(ctx), pos(ctx);
-  if ((rc = hist.alloc(cells * 4)) != MSC_OK || (rc = offsets.alloc((cells + 1) * 8)) != MSC_OK || (rc = pos.alloc(n * 4)) != MSC_OK)
+  DevTmp hist(ctx), offsets(ctx), pos(ctx), disorder(ctx);
+  if ((rc = hist.alloc(cells * 4)) != MSC_OK || (rc = offsets.alloc((cells + 1) * 8)) != MSC_OK || (rc = disorder.alloc(sizeof(int))) != MSC_OK)
     return fail(rc);
   const msc_col& key = in->cols[key_col];
-  part_hist_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, hist.as<uint32_t>());
+  MSC_CUDA(ctx, cudaMemsetAsync(disorder.p, 0, sizeof(int), ctx->stream));
+  part_hist_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, hist.as<uint32_t>(), pb, disorder.as<int>());
   ctx->stats.launches += 1;
   if ((rc = msc_exclusive_scan_u32_u64(ctx, hist.as<uint32_t>(), offsets.as<uint64_t>(), cells)) != MSC_OK) return fail(rc);
-  part_pos_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, offsets.as<uint64_t>(), pos.as<uint32_t>(), nullptr);
+  // rows per partition = difference of the partition-major offsets
+  std::vector<uint64_t> bounds(nparts + 1);
+  for (int p = 0; p <= nparts; ++p) {
+    const uint64_t idx = static_cast<uint64_t>(p) * nblocks;
+    MSC_CUDA(ctx, cudaMemcpyAsync(&bounds[p], offsets.as<uint64_t>() + idx, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  int h_disorder = 0;
+  MSC_CUDA(ctx, cudaMemcpyAsync(&h_disorder, disorder.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int p = 0; p < nparts; ++p) counts_host[p] = bounds[p + 1] - bounds[p];
+  if (!h_disorder) {
+    // The rows are partition-contiguous as they are (one partition, or a sorted key routed by range): the result SHARES the
+    // input's columns instead of copying them -- the input relation must stay alive as long as the result is used.
+    for (size_t c = 0; c < in->cols.size(); ++c) {
+      if (rel->cols[c].owned && rel->cols[c].data) msc_free(ctx, rel->cols[c].data, rel->cols[c].bytes);
+      rel->cols[c].data = in->cols[c].data;
+      rel->cols[c].bytes = in->cols[c].bytes;
+      rel->cols[c].owned = false;
+    }
+    MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    MSC_CUDA(ctx, cudaGetLastError());
+    ctx->stats.last_kernel_ms = 0;
+    *out = rel;
+    return MSC_OK;
+  }
+  if ((rc = pos.alloc(n * 4)) != MSC_OK) return fail(rc);
+  part_pos_kernel<<<nblocks, PTHREADS, 0, ctx->stream>>>(key.data, key.phys, n, nparts, nblocks, offsets.as<uint64_t>(), pos.as<uint32_t>(), nullptr, pb);
   ctx->stats.launches += 1;
   const unsigned grid = static_cast<unsigned>(ctx->sm_count * 8);
   for (size_t c = 0; c < in->cols.size(); ++c) {
@@ -420,15 +490,8 @@ extern "C" int msc_partition(msc_ctx* ctx, msc_rel* in, int32_t key_col, int32_t
     ctx->stats.launches += 1;
   }
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
-  // rows per partition = difference of the partition-major offsets
-  std::vector<uint64_t> bounds(nparts + 1);
-  for (int p = 0; p <= nparts; ++p) {
-    const uint64_t idx = static_cast<uint64_t>(p) * nblocks;
-    MSC_CUDA(ctx, cudaMemcpyAsync(&bounds[p], offsets.as<uint64_t>() + idx, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  }
   MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   MSC_CUDA(ctx, cudaGetLastError());
-  for (int p = 0; p < nparts; ++p) counts_host[p] = bounds[p + 1] - bounds[p];
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
   ctx->stats.last_kernel_ms = ms;

@@ -1364,10 +1364,12 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     MSC_TRY(agg_identity(ctx, agg_kinds[a], &init[a]));
   }
   const int R = pick_rows_per_thread(sd->nrows);
+  ctx->stats.last_agg_runs = 0;
 
   // ---- hash mode ----
   uint64_t want = hash_capacity_hint ? hash_capacity_hint : sd->nrows;
-  if (!hash_capacity_hint && sd->nrows >= (1u << 16) && !sd->nrows_dev) {
+  static const uint64_t runs_min_rows = getenv("MSC_SCAN_RUNS_MIN_ROWS") ? strtoull(getenv("MSC_SCAN_RUNS_MIN_ROWS"), nullptr, 10) : (1u << 16);
+  if (!hash_capacity_hint && sd->nrows >= runs_min_rows && !sd->nrows_dev) {
     // No hint.  When the key is a plain integer column, one pass over it counts its runs of equal adjacent values:
     //  * their number bounds the number of groups (sizing for nrows made the sf10 l_orderkey table 4.3 GB for 15 M groups);
     //  * a column without descents is sorted, so every run is exactly one group: a streaming aggregate (MODE_RUNS) writes
@@ -1451,6 +1453,7 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
           }
           ctx->stats.last_scan_kind = MSC_SCAN_KIND_RUNS;
         }
+        ctx->stats.last_agg_runs = 1;
         MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
         const int drc = msc_check_device_error(ctx);  // synchronises the stream
         if (drc != MSC_OK) {

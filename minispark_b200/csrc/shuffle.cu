@@ -272,7 +272,21 @@ static void drop_staged(msc_shuffle* sh) {
   sh->staged_owned = false;
 }
 
+static int shuffle_begin(msc_shuffle* sh, msc_rel* rel, int32_t key_col, const int64_t* lower_bounds, uint64_t epoch, uint64_t* matrix,
+                         uint64_t* need_bytes);
+
 extern "C" int msc_shuffle_begin(msc_shuffle* sh, msc_rel* rel, int32_t key_col, uint64_t epoch, uint64_t* matrix, uint64_t* need_bytes) {
+  return shuffle_begin(sh, rel, key_col, nullptr, epoch, matrix, need_bytes);
+}
+
+extern "C" int msc_shuffle_begin_range(msc_shuffle* sh, msc_rel* rel, int32_t key_col, const int64_t* lower_bounds, uint64_t epoch,
+                                       uint64_t* matrix, uint64_t* need_bytes) {
+  if (!lower_bounds || key_col < 0) return sh ? sh->ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  return shuffle_begin(sh, rel, key_col, lower_bounds, epoch, matrix, need_bytes);
+}
+
+static int shuffle_begin(msc_shuffle* sh, msc_rel* rel, int32_t key_col, const int64_t* lower_bounds, uint64_t epoch, uint64_t* matrix,
+                         uint64_t* need_bytes) {
   if (!sh || !rel || !matrix || !need_bytes || epoch == 0) return sh ? sh->ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   msc_ctx* ctx = sh->ctx;
   const int W = sh->world;
@@ -287,7 +301,8 @@ extern "C" int msc_shuffle_begin(msc_shuffle* sh, msc_rel* rel, int32_t key_col,
     for (int d = 0; d < W; ++d) counts[d] = rel->nrows;
   } else {
     msc_rel* part = nullptr;
-    MSC_TRY(msc_partition(ctx, rel, key_col, W, counts, &part));
+    if (lower_bounds) MSC_TRY(msc_partition_range(ctx, rel, key_col, W, lower_bounds, counts, &part));
+    else MSC_TRY(msc_partition(ctx, rel, key_col, W, counts, &part));
     sh->staged = part;
     sh->staged_owned = true;
     sh->bounds[0] = 0;

@@ -31,7 +31,7 @@ from typing import TYPE_CHECKING, Any, Iterable, Optional
 
 from . import lowering as L
 from . import native as N
-from .distributed import Comm, PeerShuffle, invert_code_maps, shard_blocks, unify_keys
+from .distributed import Comm, PeerShuffle, invert_code_maps, range_bounds, shard_blocks, unify_keys
 from .constants import ColumnType, Row, Schema
 from .io import BlockFile
 from .jobs import JobResult, OutputFile
@@ -93,6 +93,8 @@ class DictHandle:
         self._luts: dict[tuple, int] = {}
         self._codes: dict[tuple, int] = {}
         self._translated_from: list[tuple["DictHandle", tuple]] = []  # translation tables other dictionaries cache INTO this one
+        self.persistent = False  # a table column's dictionary (lives as long as the engine): results derived from it may be kept
+        self._unified: Optional[tuple[int, "DictHandle"]] = None  # (size it was built at, the same entries on every rank)
 
     @property
     def size(self) -> int:
@@ -562,6 +564,7 @@ class CudaExecutionEngine(ExecutionEngine):
         self.fused_probe = os.environ.get("MINISPARK_FUSED_PROBE", "1") != "0"
         self._probe_declined: Optional[DeviceRel] = None
         self._trace_track: Optional[int] = None
+        self._dense_merges: dict[tuple, "_DenseMerge"] = {}
         # jit="auto": a task tree that comes back is worth kernels compiled for exactly its scans (0.1-0.3 s each, once per
         # process and shape) -- the reference's ThreadEngine compiles every query before it runs it (execution.py:139-160)
         self._specialise_now = False
@@ -827,6 +830,7 @@ class CudaExecutionEngine(ExecutionEngine):
         for i, c in enumerate(missing):
             if entry.schema[c][1] == ColumnType.STRING:
                 d = DictHandle(self.ctx, dict_slots[i])
+                d.persistent = True
                 self._table_dicts.append(d)
                 dicts.append(d)
             else:
@@ -993,7 +997,7 @@ class CudaExecutionEngine(ExecutionEngine):
         spread = source.partitioned and self.comm.world > 1  # the rows are spread over the ranks: partial results must merge
         partitioned = False
         if ngroups and spread:  # dense tables merge across ranks without moving rows (_DenseMerge)
-            merge = _DenseMerge(self, prog.group_dict, desc, kinds, len(prog.agg_kinds))
+            merge = self._dense_merge(prog.group_dict, desc, kinds, prog.agg_kinds)
             handle, _ = merge.run(desc)
             self._note_kernel()
             self.last_stats["exchange"] = merge.exchange_kind
@@ -1017,6 +1021,20 @@ class CudaExecutionEngine(ExecutionEngine):
         rel.partitioned = partitioned
         return rel
 
+    def _dense_merge(self, group_dict: DictHandle, desc: N.ScanDesc, kinds: Any, agg_kinds: list[int]) -> "_DenseMerge":
+        """The cross-rank merge set-up of a dense GROUP BY (unified key dictionary, code permutations, exchange buffers) --
+        kept per key dictionary and accumulator layout when the key is a table column (several host collectives otherwise
+        repeat for every query)."""
+        stride, count_slot = C.c_int32(), C.c_int32()
+        self.ctx.call("msc_dense_layout", C.byref(desc), kinds, len(agg_kinds), C.byref(stride), C.byref(count_slot))
+        key = (group_dict.serial, group_dict.size, stride.value, count_slot.value, tuple(agg_kinds))
+        merge = self._dense_merges.get(key) if group_dict.persistent else None
+        if merge is None:
+            merge = _DenseMerge(self, group_dict, desc, kinds, len(agg_kinds), persistent=group_dict.persistent, jit=False)
+            if group_dict.persistent:
+                self._dense_merges[key] = merge
+        return merge
+
     def _dense_groups(self, prog: L.AggregateProgram) -> tuple[int, int]:
         """(groups of the dense table or 0 for hash mode, capacity hint).  Dense mode needs a dictionary-coded key and a
         table that fits shared memory; with several ranks all of them must take the same decision."""
@@ -1025,7 +1043,7 @@ class CudaExecutionEngine(ExecutionEngine):
         size = prog.group_dict.size
         limit = size
         if self.comm.world > 1:
-            limit = max(self.comm.all_gather_object(size))
+            limit = max(r[0] for r in self._gather_counts([size]))
         dense = limit > 0 and (limit + 1) * (len(prog.agg_kinds) + 1) <= DENSE_MAX_CELLS
         if self.comm.world == 1:
             dense = dense and size > 0
@@ -1045,10 +1063,13 @@ class CudaExecutionEngine(ExecutionEngine):
         consumer can walk the right side itself: its own filters, then the probe (MSC_OP_PROBE), then everything above the
         join, with left columns read through the matched row.  Neither side's rows nor the pair list are materialised beyond
         the (filtered) build side; output order is the right side's row order, which is the reference's right-row-major
-        order.  None: not applicable here (several ranks, duplicate build keys, expressions that must be evaluated on
-        unmatched rows too) -- the caller runs the materialising join."""
-        if self.comm.world > 1:
-            return None
+        order.  None: not applicable here (duplicate build keys, expressions that must be evaluated on unmatched rows too, a
+        build side too large to give every rank a copy) -- the caller runs the materialising join.
+
+        Several ranks: the (filtered) build side is BROADCAST -- every rank receives all of its rows over NVLink
+        (_gather_rows) and probes it with its own part of the probe side, which never moves.  The reference's task is
+        called BroadcastHashJoinTask but shuffles both sides (plan.py:186-189); with the probe side several times the
+        build side, sending the small side everywhere moves less than co-partitioning both."""
         right = join.right
         rsel = right if isinstance(right, L.LSelect) else L.identity_select(right)
         if not all(L._cannot_raise(e) for e in rsel.outputs) or any(_has_concat(e) for e in [*exprs, *rsel.outputs, *rsel.filters]):
@@ -1056,19 +1077,33 @@ class CudaExecutionEngine(ExecutionEngine):
         nl = len(join.left.schema)
         left_needed = sorted(i for i in needed if i < nl)
         lrel = self._join_side(join.left, left_needed, join.left_key, None)
+        key_dict = lrel.cols[-1].dict  # (a STR key is joined on its code in this dictionary)
+        broadcast = False
+        if self.comm.world > 1 and lrel.partitioned:
+            limit = int(os.environ.get("MSC_BROADCAST_JOIN_MAX", str(32 << 20)))
+            total = sum(r[0] for r in self._gather_counts([lrel.nrows]))
+            if total > limit:
+                self._probe_declined = lrel
+                return None
+            if join.left_key.type == L.STR:  # the key travels as a code: of a dictionary every rank shares
+                key_dict = self._unified_dictionary(key_dict)
+                lrel = self._join_side(join.left, left_needed, L.ETranslate(L.STR, join.left_key, "join"), {"join": key_dict})
+            lrel = self._gather_rows(lrel)
+            broadcast = True
         table, unique = C.c_void_p(), C.c_int32()
         self.ctx.call("msc_join_build", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.byref(table), C.byref(unique))
         self._note_kernel("hash join: build")
         trel = self._track(DeviceRel.from_handle(self.ctx, table.value, [L.INT], [None]))
         if not unique.value:
-            self._probe_declined = lrel  # (the materialising join reuses the build side it already has)
+            if not broadcast:
+                self._probe_declined = lrel  # (the materialising join reuses the build side it already has)
             return None
         inputs: list[L.Expr] = [L.EInput(_LTYPE_OF[t], _PROBE_BASE + i) for i, (_, t) in enumerate(join.left.schema)] + list(rsel.outputs)
         new_exprs = [L.substitute(e, inputs) for e in exprs]
         rkey = L.substitute(join.right_key, list(rsel.outputs))
         targets = None
         if rkey.type == L.STR:  # joined on the code in the LEFT key column's dictionary
-            targets = {"join": lrel.cols[-1].dict}
+            targets = {"join": key_dict}
             rkey = L.ECode(L.INT, L.ETranslate(L.STR, rkey, "join"))
         rneeded: set[int] = set()
         for e in [*new_exprs, *rsel.filters, rkey]:
@@ -1083,7 +1118,7 @@ class CudaExecutionEngine(ExecutionEngine):
         source.probe_key = rkey
         source.probe_table = trel.cols[0].ptr
         source.translate_targets = targets
-        self.last_stats["join"] = "lookup fused into the consuming scan (MSC_OP_PROBE)"
+        self.last_stats["join"] = "lookup fused into the consuming scan (MSC_OP_PROBE)" + (", build side broadcast to every rank" if broadcast else "")
         return source, new_exprs
 
     def _join_source(self, join: L.LJoin, needed: set[int]) -> _Source:
@@ -1129,10 +1164,18 @@ class CudaExecutionEngine(ExecutionEngine):
         return _Source(prel.nrows, columns, index_vectors=[prel.cols[0], prel.cols[1]], keep=[lrel, rrel, prel], partitioned=partitioned)
 
     def _unified_dictionary(self, local: DictHandle) -> DictHandle:
-        """The same dictionary on every rank: the sorted union of all ranks' entries (code = position)."""
+        """The same dictionary on every rank: the sorted union of all ranks' entries (code = position).  For a table column's
+        dictionary the result is kept (every rank runs the same queries on the same tables, so all keep or rebuild alike)."""
+        if local.persistent and local._unified is not None and local._unified[0] == local.size and local._unified[1].handle:
+            return local._unified[1]
         universe, _ = unify_keys(self.comm.all_gather_object(local.export()))
         unified = DictHandle(self.ctx).load(universe)
-        self._query_dicts.append(unified)
+        if local.persistent:
+            unified.persistent = True
+            local._unified = (local.size, unified)
+            self._table_dicts.append(unified)
+        else:
+            self._query_dicts.append(unified)
         return unified
 
     def _rank_independent(self, rel: DeviceRel) -> DeviceRel:
@@ -1175,6 +1218,11 @@ class CudaExecutionEngine(ExecutionEngine):
         wrapped.partitioned = rel.partitioned
         return wrapped
 
+    def _gather_counts(self, values: list[int]) -> list[list[int]]:
+        """[rank][i] = values[i] of that rank: through the peer control blocks where available, else a host collective."""
+        sh = self._peer_shuffle()
+        return sh.allgather_ints(values) if sh else self.comm.all_gather_counts(values)
+
     def _peer_shuffle(self) -> Any:
         """The library's exchange over NVLink peer memory, set up collectively on first use (False: not available)."""
         if self._shuffle is None:
@@ -1185,7 +1233,7 @@ class CudaExecutionEngine(ExecutionEngine):
                     self._shuffle = sh
         return self._shuffle
 
-    def _exchange_rows(self, rel: DeviceRel, key_col: Optional[int]) -> DeviceRel:
+    def _exchange_rows(self, rel: DeviceRel, key_col: Optional[int], lower_bounds: Optional[list[int]] = None) -> DeviceRel:
         """One shuffle: every row to rank hash(column key_col) % world, or with key_col None every row to every rank
         (rows arrive ordered by sending rank, then input order).  The reference writes and re-reads shuffle files here
         (tasks.py:347-375, 144-150); this is a push over NVLink into the receiver's memory (csrc/shuffle.cu), or one group
@@ -1194,15 +1242,16 @@ class CudaExecutionEngine(ExecutionEngine):
         ltypes, dicts = [c.ltype for c in rel.cols], [c.dict for c in rel.cols]
         sh = self._peer_shuffle()
         t0 = time.perf_counter()
+        how = " (all rows to all ranks)" if key_col is None else (" (range partitioned: sorted partial results)" if lower_bounds else " (hash partitioned)")
         if sh:
-            handle, _ = sh.exchange(rel.handle, key_col)
+            handle, _ = sh.exchange(rel.handle, key_col, lower_bounds)
             out = self._track(DeviceRel.from_handle(self.ctx, handle, ltypes, dicts))
             out.keep.append(rel)
-            self.last_stats["exchange"] = "nvlink peer push" + (" (all rows to all ranks)" if key_col is None else " (hash partitioned)")
+            self.last_stats["exchange"] = "nvlink peer push" + how
             matrix = sh.last_matrix
         else:
-            out, matrix = self._exchange_rows_nccl(rel, key_col)
-            self.last_stats["exchange"] = "nccl send/recv group" + (" (all rows to all ranks)" if key_col is None else " (hash partitioned)")
+            out, matrix = self._exchange_rows_nccl(rel, key_col, lower_bounds)
+            self.last_stats["exchange"] = "nccl send/recv group" + how
         self.last_stats.setdefault("exchanges", []).append(self.last_stats["exchange"])
         widths = sum(N.PHYS_WIDTH[c.phys] for c in rel.cols)
         me = self.comm.rank
@@ -1214,7 +1263,7 @@ class CudaExecutionEngine(ExecutionEngine):
         out.partitioned = key_col is not None
         return out
 
-    def _exchange_rows_nccl(self, rel: DeviceRel, key_col: Optional[int]) -> tuple[DeviceRel, list[list[int]]]:
+    def _exchange_rows_nccl(self, rel: DeviceRel, key_col: Optional[int], lower_bounds: Optional[list[int]] = None) -> tuple[DeviceRel, list[list[int]]]:
         import torch  # noqa: PLC0415
 
         comm = self.comm
@@ -1224,7 +1273,11 @@ class CudaExecutionEngine(ExecutionEngine):
         else:
             host_counts = (C.c_uint64 * comm.world)()
             part = C.c_void_p()
-            self.ctx.call("msc_partition", C.c_void_p(rel.handle), key_col, comm.world, host_counts, C.byref(part))
+            if lower_bounds is not None:
+                self.ctx.call("msc_partition_range", C.c_void_p(rel.handle), key_col, comm.world, (C.c_int64 * comm.world)(*lower_bounds), host_counts,
+                              C.byref(part))
+            else:
+                self.ctx.call("msc_partition", C.c_void_p(rel.handle), key_col, comm.world, host_counts, C.byref(part))
             prel = self._track(DeviceRel.from_handle(self.ctx, part.value, [c.ltype for c in rel.cols], [c.dict for c in rel.cols]))
             counts = [int(c) for c in host_counts]
             cols = [self._torch_column(c, prel.nrows) for c in prel.cols]
@@ -1289,17 +1342,28 @@ class CudaExecutionEngine(ExecutionEngine):
         key_dict = raw.cols[0].dict
         global_dict = None
         if key_dict is not None:  # unify string keys through their dictionary entries
-            universe, _ = unify_keys(comm.all_gather_object(key_dict.export()))
-            global_dict = DictHandle(self.ctx).load(universe)
-            self._query_dicts.append(global_dict)
+            global_dict = self._unified_dictionary(key_dict)
             source = _Source(raw.nrows, dict(enumerate(raw.cols)), keep=[raw])
             resolver = _ScanResolver(self, source, {"global": global_dict})
             outs = [L.ECode(L.INT, L.ETranslate(L.STR, L.EInput(L.STR, 0), "global"))]
             outs += [L.EInput(t, i + 1) for i, t in enumerate(slot_types)]
             prog = L.compile_project(resolver, [], outs)
             raw = self._scan_project(resolver, prog, [L.INT, *slot_types])
-        small = max(r[0] for r in comm.all_gather_counts([raw.nrows])) <= int(os.environ.get("MSC_EXCHANGE_GATHER_MAX", "65536"))
-        gathered = self._exchange_rows(raw, None if small else 0)
+        # what every rank holds: rows, and -- when its pre-aggregation streamed over the runs of a sorted key (MSC_SCAN_KIND_RUNS),
+        # so that its partial rows ascend -- the first and last key
+        ascending = bool(self.ctx.stats().last_agg_runs) and group_type in (L.INT, L.TS) and raw.nrows > 0
+        first = last = 0
+        if ascending:
+            import numpy as np  # noqa: PLC0415
+
+            ends = np.zeros(2, dtype=np.int64)
+            self.ctx.call("msc_memcpy_d2h", ends[0:1].ctypes.data_as(C.c_void_p), C.c_void_p(raw.cols[0].ptr), 8)
+            self.ctx.call("msc_memcpy_d2h", ends[1:2].ctypes.data_as(C.c_void_p), C.c_void_p(raw.cols[0].ptr + 8 * (raw.nrows - 1)), 8)
+            first, last = int(ends[0]), int(ends[1])
+        per_rank = [tuple(r) for r in self._gather_counts([int(ascending or raw.nrows == 0), raw.nrows, first, last])]
+        small = max(r[1] for r in per_rank) <= int(os.environ.get("MSC_EXCHANGE_GATHER_MAX", "65536"))
+        bounds = None if small or os.environ.get("MSC_EXCHANGE_RANGE", "1") == "0" else range_bounds([(bool(r[0]), r[1], r[2], r[3]) for r in per_rank])
+        gathered = self._exchange_rows(raw, None if small else 0, bounds)
         # final aggregate over the partial rows: SUM of sums / counts, MIN of mins, MAX of maxes
         merge_kind = {N.K["MSC_AGG_SUM_F"]: "sum", N.K["MSC_AGG_SUM_I"]: "sum", N.K["MSC_AGG_MIN_F"]: "min", N.K["MSC_AGG_MIN_I"]: "min",
                       N.K["MSC_AGG_MAX_F"]: "max", N.K["MSC_AGG_MAX_I"]: "max"}
@@ -1308,7 +1372,10 @@ class CudaExecutionEngine(ExecutionEngine):
         prog2 = L.compile_aggregate(resolver, [], L.EInput(L.INT, 0), [(merge_kind[k], L.EInput(t, i + 1)) for i, (k, t) in enumerate(zip(agg_kinds, slot_types))])
         desc = resolver.desc(prog2.program)
         out = C.c_void_p()
-        self.ctx.call("msc_scan_aggregate", C.byref(desc), 0, N.int32_array(prog2.agg_kinds), len(prog2.agg_kinds), max(gathered.nrows, 1), C.byref(out))
+        # (no capacity hint after a range-partitioned exchange: the rows a rank received ascend, so the library's run count
+        # finds every run to be one group and streams over them instead of probing a table)
+        hint = 0 if bounds is not None else max(gathered.nrows, 1)
+        self.ctx.call("msc_scan_aggregate", C.byref(desc), 0, N.int32_array(prog2.agg_kinds), len(prog2.agg_kinds), hint, C.byref(out))
         self._note_kernel()
         # prog2 may carry one accumulator more than asked for (the hidden COUNT of the regvm encoding): type every
         # column the library returns, then keep the requested ones in order
@@ -1330,12 +1397,13 @@ class _DenseMerge:
     without a row ever leaving its GPU."""
 
     def __init__(self, engine: "CudaExecutionEngine", group_dict: DictHandle, desc: N.ScanDesc, kinds, naggs: int,  # noqa: ANN001
-                 persistent: bool = False) -> None:
+                 persistent: bool = False, jit: bool = True) -> None:
         import torch  # noqa: PLC0415
 
         self.engine = engine
-        self.kinds, self.naggs = kinds, naggs
-        self.persistent = persistent
+        self.kinds, self.naggs = N.int32_array(list(kinds)[:naggs]), naggs  # (own copy: the object may outlive the caller's array)
+        self.persistent = persistent  # the unified dictionary lives as long as the engine (prepared queries, cached set-ups)
+        self.jit = jit and persistent  # prepared queries always run on a kernel specialised for them
         comm = engine.comm
         stride, count_slot = C.c_int32(), C.c_int32()
         engine.ctx.call("msc_dense_layout", C.byref(desc), kinds, naggs, C.byref(stride), C.byref(count_slot))
@@ -1377,7 +1445,8 @@ class _DenseMerge:
         import torch.distributed as dist  # noqa: PLC0415
 
         e = self.engine
-        flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0) | (N.K["MSC_DENSE_JIT"] if self.persistent and e.jit != "never" else 0)
+        want_jit = e.jit != "never" and (self.jit or e._specialise_now or e.jit == "always")
+        flags = N.K["MSC_DENSE_ASYNC"] | (N.K["MSC_DENSE_EXACT"] if exact else 0) | (N.K["MSC_DENSE_JIT"] if want_jit else 0)
         if self.nlocal > 0:
             e.ctx.call("msc_scan_dense_table", C.byref(desc), self.nlocal, self.kinds, self.naggs, C.c_void_p(self.local.data_ptr()), flags)
         if self.shuffle:

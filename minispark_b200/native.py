@@ -90,6 +90,8 @@ class Stats(C.Structure):
         ("last_scan_regs", C.c_int32),
         ("jit_compiles", C.c_uint64),
         ("last_jit_compile_ms", C.c_double),
+        ("last_agg_runs", C.c_int32),
+        ("_pad", C.c_int32),
     ]
 
 
@@ -205,6 +207,10 @@ _SIGNATURES = {
     "msc_shuffle_slot_detach": (C.c_int, [C.c_void_p, C.c_int32]),
     "msc_shuffle_slot_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]),
     "msc_shuffle_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "msc_shuffle_begin_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_uint64, C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint64)]),
+    "msc_partition_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_void_p)]),
     "msc_shuffle_finish": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "msc_shuffle_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "msc_shuffle_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),

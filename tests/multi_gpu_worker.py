@@ -11,6 +11,7 @@ import time
 from pathlib import Path
 
 os.environ["TZ"] = "UTC"
+os.environ.setdefault("MSC_SCAN_RUNS_MIN_ROWS", "1")  # the streaming aggregate over sorted runs also for this test's small tables
 time.tzset()
 ROOT = Path(__file__).resolve().parent.parent
 for p in (ROOT, ROOT / "tests", ROOT / "bench"):
@@ -77,15 +78,25 @@ def main() -> None:
         # high-cardinality GROUP BY through hash partitioning + the row exchange: ranks hold disjoint sets of keys ...
         os.environ["MSC_EXCHANGE_GATHER_MAX"] = "0"
         rel, schema = engine.execute_to_device(high_card(engine).task)
-        assert engine.last_stats["exchange"].startswith("nvlink peer push (hash" if peer else "nccl send/recv group (hash"), engine.last_stats
+        # (lineitem is clustered by l_orderkey and sharded in row order: the partial results ascend, ranks keep their key ranges)
+        assert engine.last_stats["exchange"].startswith("nvlink peer push (range" if peer else "nccl send/recv group (range"), engine.last_stats
         assert engine.last_stats["result_partitioned"] is True and rel.partitioned
-        assert engine.last_stats["exchange_rows_sent"] > 0
+        assert engine.last_stats["exchange_rows_sent"] <= 1  # at most the one key that straddles two ranks changes rank
         mine = rel.column_numpy(0).tolist()
         engine.release_query()
         gathered: list = [None] * world
         dist.all_gather_object(gathered, mine)
         keys = [k for part in gathered for k in part]
         assert len(keys) == len(set(keys)), "a key was aggregated on two ranks"
+        # ... the same with hashed routing (what unsorted keys get): about half of the partial rows change rank
+        os.environ["MSC_EXCHANGE_RANGE"] = "0"
+        rel, schema = engine.execute_to_device(high_card(engine).task)
+        assert "(hash partitioned)" in engine.last_stats["exchange"] and engine.last_stats["exchange_rows_sent"] > rel.nrows // 4
+        hashed = rel.column_numpy(0).tolist()
+        engine.release_query()
+        os.environ.pop("MSC_EXCHANGE_RANGE")
+        dist.all_gather_object(gathered, hashed)
+        assert sorted(k for part in gathered for k in part) == sorted(keys)
         # ... and collect() gathers them: every rank returns the complete result
         full = high_card(engine).collect()
         assert engine.last_stats["result_partitioned"] is False

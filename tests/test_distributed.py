@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from minispark_b200.distributed import Comm, exchange_plan, shard_blocks, unify_keys
+from minispark_b200.distributed import Comm, exchange_plan, range_bounds, shard_blocks, unify_keys
 
 
 def test_shard_blocks_cover_every_block_once():
@@ -29,6 +29,16 @@ def test_unify_keys_and_exchange_plan():
     assert maps == [[1, 2], [0, 1], []]
     send, recv = exchange_plan([[1, 2], [3, 4]], rank=1)
     assert send == [3, 4] and recv == [2, 4]
+
+
+def test_range_bounds_for_sorted_partial_results():
+    """(sorted?, rows, first key, last key) per rank -> the key range every rank receives, or None (hash instead)."""
+    # a clustered table sharded in row order: rank r keeps its keys; key 50 straddles ranks 0 and 1 and ends up on rank 1
+    assert range_bounds([(True, 10, 1, 50), (True, 10, 50, 90), (True, 0, 0, 0), (True, 5, 95, 99)]) == [1, 50, 95, 95]
+    assert range_bounds([(True, 10, 1, 60), (True, 10, 50, 90)]) is None      # ranges interleave
+    assert range_bounds([(True, 10, 1, 40), (False, 10, 50, 90)]) is None     # a rank whose rows do not ascend
+    assert range_bounds([(True, 0, 0, 0), (True, 0, 0, 0)]) == [(1 << 63) - 1] * 2
+    assert range_bounds([(True, 3, -9, -2)]) == [-9]
 
 
 def _free_port() -> int:

@@ -102,6 +102,39 @@ def test_partition_is_exact_and_stable(ctx, nparts, nrows, key_kind):
     ctx.lib.msc_rel_free(C.c_void_p(rel))
 
 
+@pytest.mark.parametrize("nparts", [1, 2, 8])
+@pytest.mark.parametrize("sorted_keys", [True, False])
+def test_partition_by_key_range(ctx, nparts, sorted_keys):
+    """msc_partition_range: partition p = keys in [lower_bounds[p], lower_bounds[p + 1]); stable, so a sorted input stays
+    sorted inside every partition (what the final aggregate after a shuffle of sorted partial results relies on)."""
+    cols, physes, dtypes = _table(50_001, 3 * nparts, "i64")
+    if sorted_keys:
+        order = np.argsort(cols[0], kind="stable")
+        cols = [c[order] for c in cols]
+    qs = np.quantile(cols[0], [i / nparts for i in range(nparts)]).astype(np.int64)
+    qs[0] = 12345  # (entry 0 is ignored: the first partition has no lower bound)
+    if nparts > 2:
+        qs[2] = qs[1]  # an empty range
+    rel = _upload(ctx, cols, physes)
+    counts = (C.c_uint64 * nparts)()
+    out = C.c_void_p()
+    ctx.call("msc_partition_range", C.c_void_p(rel), 0, nparts, (C.c_int64 * nparts)(*qs.tolist()), counts, C.byref(out))
+    got = _download(ctx, out.value, dtypes)
+    part = np.zeros(len(cols[0]), dtype=np.int64)
+    for p in range(1, nparts):
+        part += cols[0] >= qs[p]
+    assert [int(c) for c in counts] == np.bincount(part, minlength=nparts).tolist()
+    order = np.argsort(part, kind="stable")
+    for g, c in zip(got, cols):
+        assert np.array_equal(g, c[order])
+    if sorted_keys:
+        assert np.all(np.diff(got[0]) >= 0)
+    ctx.lib.msc_rel_free(out)
+    ctx.lib.msc_rel_free(C.c_void_p(rel))
+    with pytest.raises(N.NativeError):  # bounds must not decrease
+        ctx.call("msc_partition_range", C.c_void_p(0), 0, 3, (C.c_int64 * 3)(0, 5, 4), counts, C.byref(out))
+
+
 def test_partition_rejects_bad_arguments(ctx):
     cols, physes, _ = _table(10, 1, "i64")
     rel = _upload(ctx, cols, physes)
