@@ -63,10 +63,12 @@ def build(force: bool = False, verbose: bool = True) -> Path:
         objs = list(pool.map(lambda s: _compile(s, verbose), SOURCES))
     newest = max(o.stat().st_mtime for o in objs)
     if force or not LIB.exists() or LIB.stat().st_mtime < newest:
-        cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+        # (--cudart shared: the runtime stays in libcudart.so instead of being embedded, entry-point name table and all)
+        cmd = [_nvcc(), "-shared", "--cudart", "shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
+        subprocess.run(["strip", "--strip-unneeded", str(LIB)], check=False)
     return LIB
 
 

@@ -134,6 +134,7 @@ struct DevTmp {
 #define MSC_DEVERR_STRLEN 8
 #define MSC_DEVERR_TABLE_FULL 16
 #define MSC_DEVERR_PEER_TIMEOUT 32
+#define MSC_DEVERR_IO 64
 
 // ---- prefix sums (scan.cu exports these for the other translation units) -------------------
 // out[i] = sum_{j<i} in[j] for i in [0, n]; out has n+1 elements (out[n] = total).

@@ -69,7 +69,8 @@ int msc_device_error_rc(msc_ctx* ctx, int e) {
   if (e & MSC_DEVERR_OVERFLOW) return ctx->fail(MSC_ERR_OVERFLOW, "int too big to convert");
   if (e & MSC_DEVERR_COLLISION) return ctx->fail(MSC_ERR_COLLISION, "string hash collision in dictionary");
   if (e & MSC_DEVERR_STRLEN) return ctx->fail(MSC_ERR_STRLEN, "string longer than 255 bytes");
-  if (e & MSC_DEVERR_PEER_TIMEOUT) return ctx->fail(MSC_ERR_PEER, "a peer GPU did not deliver its partial aggregate in time");
+  if (e & MSC_DEVERR_PEER_TIMEOUT) return ctx->fail(MSC_ERR_PEER, "a peer GPU did not deliver its part of an exchange in time");
+  if (e & MSC_DEVERR_IO) return ctx->fail(MSC_ERR_IO, "malformed BlockFile: a string block's lengths exceed its bytes");
   return ctx->fail(MSC_ERR_ARG, "hash table full");
 }
 

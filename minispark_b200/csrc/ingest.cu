@@ -43,7 +43,7 @@ struct msc_table {
 namespace {
 
 int read_at(msc_table* t, uint64_t off, void* dst, size_t n) {
-  if (off + n > t->size) return t->ctx->fail(MSC_ERR_IO, "BlockFile truncated");
+  if (n > t->size || off > t->size - n) return t->ctx->fail(MSC_ERR_IO, "BlockFile truncated");  // (overflow-safe: both come from the file)
   if (t->image) {
     memcpy(dst, t->image + off, n);
     return MSC_OK;
@@ -82,13 +82,14 @@ int parse_table(msc_table* t) {
   for (uint32_t b = 0; b < nblocks; ++b) {
     BlockInfo bi;
     bi.start = starts[b];
+    if (bi.start >= t->size) return ctx->fail(MSC_ERR_IO, "block start beyond end of file");
     MSC_TRY(read_at(t, bi.start, &bi.rows, 4));
     uint64_t p = bi.start + 4;
     for (int c = 0; c < ncols; ++c) {
       uint64_t nbytes = 0;
       MSC_TRY(read_at(t, p, &nbytes, 8));
       p += 8;
-      if (p + nbytes > t->size) return ctx->fail(MSC_ERR_IO, "column payload runs past end of file");
+      if (nbytes > t->size || p > t->size - nbytes) return ctx->fail(MSC_ERR_IO, "column payload runs past end of file");
       const int ty = t->types[c];
       if (ty != MSC_T_STRING) {
         const uint64_t w = (ty == MSC_T_TIMESTAMP) ? 8 : 4;
@@ -104,6 +105,12 @@ int parse_table(msc_table* t) {
     t->blocks.push_back(std::move(bi));
   }
   return MSC_OK;
+}
+
+// a STRING block's u8 lengths must add up to no more than the bytes that follow them (else the encoder would read past
+// the staged block): offsets[rows] is their sum
+__global__ void check_string_total_kernel(const uint64_t* total, uint64_t limit, int* err) {
+  if (*total > limit) atomicOr(err, MSC_DEVERR_IO);
 }
 
 __global__ void widen_i32_kernel(const int* in, long long* out, uint64_t n) {
@@ -341,6 +348,10 @@ extern "C" int msc_table_load(msc_ctx* ctx, msc_table* t, const int32_t* cols, i
         const uint8_t* lens = stage[sset].as<uint8_t>();
         const uint8_t* body = lens + bi.rows;
         rc = msc_exclusive_scan_u8_u64(ctx, lens, offs[sset].as<uint64_t>(), bi.rows);
+        if (rc == MSC_OK) {
+          check_string_total_kernel<<<1, 1, 0, ctx->stream>>>(offs[sset].as<uint64_t>() + bi.rows, bi.col_bytes[fc] - bi.rows, ctx->d_err);
+          ctx->stats.launches += 1;
+        }
         if (rc == MSC_OK)
           rc = msc_dict_encode_u8_async(ctx, dicts[c], offs[sset].as<uint64_t>(), lens, body, bi.rows, bi.col_bytes[fc] - bi.rows,
                                         static_cast<uint32_t*>(col.data) + row_off);

@@ -966,11 +966,32 @@ class CudaExecutionEngine(ExecutionEngine):
         nf = len(sel.filters)
         source, exprs = self._prepare(sel.child, [*sel.filters, *sel.outputs])
         filters, outputs = exprs[:nf], exprs[nf:]
-        resolver = _ScanResolver(self, source, translate_targets)
-        prog = L.compile_project(resolver, filters, outputs, probe=resolver.probe_spec(), pre_filters=source.pre_filters)
-        rel = self._scan_project(resolver, prog, [e.type for e in outputs])
+        rel = self._project(source, filters, outputs, translate_targets)
         rel.keep.extend(source.keep)
         return rel
+
+    def _project(self, source: _Source, filters: list[L.Expr], outputs: list[L.Expr], translate_targets: Optional[dict[str, DictHandle]]) -> DeviceRel:
+        """One filter + project scan -- or several over the same rows when the outputs exceed what one scan can bind
+        (MSC_VM_MAX_OUT output columns, MSC_VM_MAX_STAGED staged / MSC_VM_MAX_GATHER gathered inputs: `SELECT *` over a wide
+        join).  Every pass evaluates the same filters and compaction is stable, so the passes' columns line up row by row."""
+        try:
+            if len(outputs) > N.K["MSC_VM_MAX_OUT"]:
+                raise L.LoweringError("too many output columns in one projection")
+            resolver = _ScanResolver(self, source, translate_targets)
+            prog = L.compile_project(resolver, filters, outputs, probe=resolver.probe_spec(), pre_filters=source.pre_filters)
+            return self._scan_project(resolver, prog, [e.type for e in outputs])
+        except L.LoweringError as err:
+            splittable = any(t in str(err) for t in ("too many output columns", "more columns than one scan", "gathers more columns"))
+            if len(outputs) < 2 or not splittable:
+                raise
+        half = len(outputs) // 2
+        first = self._project(source, filters, outputs[:half], translate_targets)
+        second = self._project(source, filters, outputs[half:], translate_targets)
+        if first.nrows != second.nrows:
+            raise ExecutionError("projection passes disagree on the surviving rows")
+        rel = DeviceRel(self.ctx, None, first.nrows, [*first.cols, *second.cols], keep=[first, second])
+        rel.partitioned = first.partitioned
+        return self._materialised(rel)
 
     def _run_aggregate(self, agg: L.LAggregate) -> DeviceRel:
         child = agg.child

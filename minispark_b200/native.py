@@ -227,6 +227,27 @@ def declared_symbols() -> list[str]:
     return re.findall(r"^MSC_API\s+[\w\s\*]+?\b(msc_[a-z0-9_]+)\(", HEADER.read_text(), flags=re.M)
 
 
+def _preload_cudart() -> None:
+    """The library links the CUDA runtime dynamically (build.py): make sure libcudart.so.12 is in the process before it is
+    dlopen'ed, wherever this installation keeps it (the dynamic linker's own search path comes first)."""
+    candidates = ["libcudart.so.12"]
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.cuda_runtime")
+        for root in (spec.submodule_search_locations or []) if spec else []:
+            candidates.append(str(Path(root) / "lib" / "libcudart.so.12"))
+    except Exception:  # noqa: BLE001
+        pass
+    candidates += ["/usr/local/cuda/lib64/libcudart.so.12", "/usr/local/cuda/targets/x86_64-linux/lib/libcudart.so.12"]
+    for cand in candidates:
+        try:
+            C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            return
+        except OSError:
+            continue
+
+
 def load() -> C.CDLL:
     """dlopen the library and attach prototypes.  Raises if it has not been built."""
     global _lib
@@ -234,6 +255,7 @@ def load() -> C.CDLL:
         return _lib
     if not LIB_PATH.exists():
         raise NativeError(-1, f"{LIB_PATH} is missing: run `python -m minispark_b200.build` (there is no CPU fallback)")
+    _preload_cudart()
     lib = C.CDLL(str(LIB_PATH))
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(lib, name)

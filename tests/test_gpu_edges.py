@@ -129,3 +129,62 @@ def test_string_lengths_0_and_254_and_wide_dictionary(tmp_path):
         O.assert_rows_equal(q1(e).collect(), O.run_task(q1().task, wire=True))
         O.assert_rows_equal(q2(e).collect(), O.run_task(q2().task, wire=True))
         O.assert_rows_equal(q3(e).collect(), O.run_task(q3().task, wire=True), ordered=True)
+
+
+def test_result_blockfile_spans_several_blocks(tmp_path, monkeypatch):
+    """A result larger than a row-block is written as several blocks (reference io.py:74-109 splits at ROWS_PER_BLOCK; its
+    own test patches the constant, tests/test_io.py) and reads back through the reference-format reader, row for row."""
+    import minispark_b200.io as mio
+
+    monkeypatch.setattr(mio, "ROWS_PER_BLOCK", 1000)
+    table = _write(tmp_path / "t.bin", 4321)
+    ns = cases.namespace()
+    with CudaExecutionEngine() as engine:
+        df = ns.DataFrame(engine).table(table).filter(ns.Col("i") > -900).select(ns.Col("k"), ns.Col("i"), (ns.Col("x") * 2).alias("x2"))
+        jobs = engine.execute_full_task(df.task)
+        files = [f.file_path for j in jobs for f in j.output_files]
+        assert len(files) == 1
+        bf = BlockFile(files[0])
+        want = O.run_task(ns.DataFrame(None).table(table).filter(ns.Col("i") > -900).select(ns.Col("k"), ns.Col("i"), (ns.Col("x") * 2).alias("x2")).task, wire=True)
+        assert len(bf.block_starts) == -(-len(want) // 1000) and len(bf.block_starts) >= 4
+        O.assert_rows_equal(list(engine.collect_results(jobs)), want, ordered=True)
+
+
+def test_select_star_over_a_wide_join_is_split_into_passes(tmp_path):
+    """More output columns than one scan binds (MSC_VM_MAX_OUT = 24): `SELECT *` over the join of two 14-column tables runs
+    as several passes over the same rows whose columns are stitched together (the reference has no such limit)."""
+    ncols = 14
+    rng = np.random.default_rng(11)
+    n = 3000
+
+    def table(path, prefix, keys):
+        schema = [(f"{prefix}{c}", ColumnType.INTEGER if c % 3 else ColumnType.FLOAT) for c in range(ncols)]
+        schema[1] = (f"{prefix}1", ColumnType.STRING)
+        cols = []
+        for c, (_, t) in enumerate(schema):
+            if c == 0:
+                cols.append(keys)
+            elif t == ColumnType.STRING:
+                cols.append([f"s{int(v)}" for v in rng.integers(0, 9, len(keys))])
+            elif t == ColumnType.FLOAT:
+                cols.append((rng.integers(0, 800, len(keys)) / 8.0).tolist())
+            else:
+                cols.append(rng.integers(-99, 99, len(keys)).tolist())
+        schema[0] = (f"{prefix}0", ColumnType.INTEGER)
+        cols[0] = list(keys)
+        BlockFile(path, schema).write_data(tuple(cols))
+        return str(path)
+
+    a = table(tmp_path / "a.bin", "a", list(range(200)))
+    b = table(tmp_path / "b.bin", "b", rng.integers(0, 260, n).tolist())
+    ns = cases.namespace()
+
+    def q(e):
+        return ns.DataFrame(e).table(a).join(ns.DataFrame().table(b), on=ns.Col("a0") == ns.Col("b0"), how="inner").filter(ns.Col("b2") > -50)
+
+    want = O.run_task(q(None).task, wire=True)
+    assert len(want[0]) == 2 * ncols and len(want) > 100
+    for fused in (True, False):
+        with CudaExecutionEngine() as engine:
+            engine.fused_probe = fused
+            O.assert_rows_equal(q(engine).collect(), want)
