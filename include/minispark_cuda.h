@@ -403,16 +403,25 @@ MSC_API int msc_dense_fused_peer(msc_ctx* ctx, const msc_scan_desc* scan, const 
                          const msc_peer_spec* peer, msc_rel** final_rel, int32_t* nonfinite);
 /* ---- prepared dense aggregate ---------------------------------------------------------------------------------------
  * msc_dense_fused / msc_dense_fused_peer with everything that does not change between passes done once: programs
- * validated and copied, accumulator table and result relation allocated, kernel compiled.  A pass is then ONE kernel
+ * validated and copied, accumulator table and result relations allocated, kernel compiled.  A pass is then ONE kernel
  * launch (the kernel's finish leaves the table's identities behind for the next pass), one 24-byte read and one host
  * wait.  *out == NULL with MSC_OK: this query cannot be fused (see msc_dense_fused).  The result relation handed out by
- * msc_prepared_run belongs to the prepared object and is overwritten by the next pass; `peer` may be NULL (one GPU),
- * `epoch` is ignored then. */
+ * msc_prepared_run / msc_prepared_wait belongs to the prepared object and is overwritten MSC_PREPARED_RING passes later;
+ * `peer` may be NULL (one GPU), `epoch` is ignored then. */
 typedef struct msc_prepared msc_prepared;
 MSC_API int msc_prepared_create(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups, const int32_t* agg_kinds, int32_t naggs,
                         const msc_scan_desc* final_scan, const int32_t* final_cols, const int32_t* out_phys, int32_t nout,
                         const msc_peer_spec* peer, msc_prepared** out);
 MSC_API int msc_prepared_run(msc_prepared* p, int32_t flags, uint64_t epoch, msc_rel** result, uint64_t* nrows, int32_t* nonfinite);
+/* The same in two halves, so that the host can run ahead of the device: msc_prepared_enqueue launches a pass (kernel +
+ * the 24-byte read of its row count into pinned memory) and returns; msc_prepared_wait collects the OLDEST pass still in
+ * flight.  At most MSC_PREPARED_RING passes may be in flight; a collected result stays valid until that many later passes
+ * have been enqueued.  Back-to-back passes keep the device busy across the host's per-pass work (launch latency, the
+ * wait, the caller's own code) -- and with several ranks keep every rank's next kernel queued behind its current one, so
+ * that the in-kernel exchange waits for the slowest GPU, not for the slowest host. */
+#define MSC_PREPARED_RING 4
+MSC_API int msc_prepared_enqueue(msc_prepared* p, int32_t flags, uint64_t epoch);
+MSC_API int msc_prepared_wait(msc_prepared* p, msc_rel** result, uint64_t* nrows, int32_t* nonfinite);
 MSC_API void msc_prepared_free(msc_prepared* p);
 /* table -> relation: group id (U32) + the first naggs accumulators of every group whose count_slot is non-zero */
 MSC_API int msc_dense_compact(msc_ctx* ctx, const void* table, int32_t ngroups, int32_t stride, const int32_t* agg_kinds,

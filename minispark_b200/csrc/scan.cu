@@ -1125,7 +1125,14 @@ struct msc_prepared {
   DensePlan dp;
   unsigned long long* table = nullptr;  // [ngroups][stride]; holds the identities between passes (the finish resets it)
   size_t table_bytes = 0;
-  msc_rel* result = nullptr;            // its columns are rewritten by every pass
+  // A ring of result relations: passes may be enqueued ahead of the host (msc_prepared_enqueue) and collected in order
+  // (msc_prepared_wait); pass k writes ring[k % kRing], so a result lives until kRing later passes have been enqueued.
+  static constexpr int kRing = 4;
+  msc_rel* ring[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t done[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t k0[kRing] = {nullptr, nullptr, nullptr, nullptr}, k1[kRing] = {nullptr, nullptr, nullptr, nullptr};  // around each pass's kernel
+  unsigned long long* h_meta = nullptr;  // pinned, 3 words per ring entry: {rows, non-finite SUM, device error word}
+  uint64_t issued = 0, collected = 0;
   bool table_clean = false;
   bool has_peer = false;
   msc_peer_spec peer;
@@ -1167,16 +1174,36 @@ extern "C" int msc_prepared_create(msc_ctx* ctx, const msc_scan_desc* scan, int3
     MSC_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), ctx->stream));
   }
   // compile both variants' worth lazily: the masked one now (the common case), the exact one if a pass ever needs it
-  msc_rel* rel = new_rel(ctx, static_cast<uint64_t>(out_groups));
-  int rc = add_cols(ctx, rel, out_phys, nout, static_cast<uint64_t>(out_groups));
-  if (rc == MSC_OK) rc = msc_alloc(ctx, 3 * sizeof(unsigned long long), reinterpret_cast<void**>(&rel->d_meta));
+  int rc = MSC_OK;
+  auto drop = [&]() {
+    for (int i = 0; i < msc_prepared::kRing; ++i) {
+      if (p->ring[i]) msc_rel_free(p->ring[i]);
+      if (p->done[i]) cudaEventDestroy(p->done[i]);
+      if (p->k0[i]) cudaEventDestroy(p->k0[i]);
+      if (p->k1[i]) cudaEventDestroy(p->k1[i]);
+      p->ring[i] = nullptr;
+      p->done[i] = p->k0[i] = p->k1[i] = nullptr;
+    }
+    if (p->h_meta) cudaFreeHost(p->h_meta);
+    p->h_meta = nullptr;
+  };
+  for (int i = 0; rc == MSC_OK && i < msc_prepared::kRing; ++i) {
+    p->ring[i] = new_rel(ctx, static_cast<uint64_t>(out_groups));
+    rc = add_cols(ctx, p->ring[i], out_phys, nout, static_cast<uint64_t>(out_groups));
+    if (rc == MSC_OK) rc = msc_alloc(ctx, 3 * sizeof(unsigned long long), reinterpret_cast<void**>(&p->ring[i]->d_meta));
+    if (rc == MSC_OK && (cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&p->k0[i]) != cudaSuccess ||
+                         cudaEventCreate(&p->k1[i]) != cudaSuccess))
+      rc = ctx->fail(MSC_ERR_CUDA, "cudaEventCreate failed");
+  }
+  if (rc == MSC_OK && cudaHostAlloc(reinterpret_cast<void**>(&p->h_meta), sizeof(unsigned long long) * 3 * msc_prepared::kRing, cudaHostAllocDefault) != cudaSuccess)
+    rc = ctx->fail(MSC_ERR_CUDA, "cudaHostAlloc failed");
   p->table_bytes = sizeof(unsigned long long) * ngroups * p->dp.stride;
   if (rc == MSC_OK) rc = msc_alloc(ctx, p->table_bytes, reinterpret_cast<void**>(&p->table));
   if (rc != MSC_OK) {
-    msc_rel_free(rel);
+    drop();
     return rc;
   }
-  p->result = rel;
+  msc_rel* rel = p->ring[0];
   void* outs[MSC_VM_MAX_OUT];
   for (int i = 0; i < nout; ++i) outs[i] = rel->cols[i].data;
   msc_peer_spec probe;
@@ -1191,7 +1218,7 @@ extern "C" int msc_prepared_create(msc_ctx* ctx, const msc_scan_desc* scan, int3
   rc = jit_dense_launch(ctx, scan, ngroups, naggs, p->dp.stride, p->dp.kinds, p->dp.init, p->table, false, &masked, &fin);
   if (rc != MSC_OK) {
     const bool declined = (rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) || (rc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0);
-    msc_rel_free(rel);
+    drop();
     msc_free(ctx, p->table, p->table_bytes);
     return declined ? MSC_OK : rc;
   }
@@ -1199,36 +1226,82 @@ extern "C" int msc_prepared_create(msc_ctx* ctx, const msc_scan_desc* scan, int3
   return MSC_OK;
 }
 
-extern "C" int msc_prepared_run(msc_prepared* p, int32_t flags, uint64_t epoch, msc_rel** result, uint64_t* nrows, int32_t* nonfinite) {
-  if (!p || !result || !nrows || !nonfinite) return MSC_ERR_ARG;
+extern "C" int msc_prepared_enqueue(msc_prepared* p, int32_t flags, uint64_t epoch) {
+  if (!p) return MSC_ERR_ARG;
   msc_ctx* ctx = p->ctx;
+  if (p->issued - p->collected >= static_cast<uint64_t>(msc_prepared::kRing)) return ctx->fail(MSC_ERR_ARG, "too many passes in flight: msc_prepared_wait first");
   static const bool masked_enabled = !(getenv("MSC_SCAN_MASKED") && atoi(getenv("MSC_SCAN_MASKED")) == 0);
-  msc_rel* rel = p->result;
+  const int slot = static_cast<int>(p->issued % msc_prepared::kRing);
+  msc_rel* rel = p->ring[slot];
   void* outs[MSC_VM_MAX_OUT];
   for (int i = 0; i < p->nout; ++i) outs[i] = rel->cols[i].data;
   p->peer.epoch = epoch;
   p->peer.compile_only = 0;
-  JitFinish fin{&p->fin, p->fin_cols, p->out_phys, p->nout, p->dp.count_slot, outs, rel->d_meta, ctx->d_ticket, p->has_peer ? &p->peer : nullptr};
+  // the finish writes {rows, non-finite, error word} straight into pinned host memory (unified addressing): no copy
+  // between two passes' kernels, the host only waits for the pass's event
+  JitFinish fin{&p->fin, p->fin_cols, p->out_phys, p->nout, p->dp.count_slot, outs, p->h_meta + 3 * slot, ctx->d_ticket, p->has_peer ? &p->peer : nullptr};
   MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
   if (!p->table_clean) {
     dense_init_kernel<<<1, 256, 0, ctx->stream>>>(p->table, p->ngroups, p->dp.stride, dense_meta(p->dp));
     ctx->stats.launches += 1;
   }
-  p->table_clean = false;
   bool masked = !(flags & MSC_DENSE_EXACT) && masked_enabled;
+  p->table_clean = false;
+  MSC_CUDA(ctx, cudaEventRecord(p->k0[slot], ctx->stream));
   MSC_TRY(jit_dense_launch(ctx, &p->scan, p->ngroups, p->naggs, p->dp.stride, p->dp.kinds, p->dp.init, p->table, true, &masked, &fin));
-  rel->pending = true;
-  msc_rel* rels[1] = {rel};
-  MSC_TRY(msc_rel_settle(ctx, rels, 1, nonfinite));
-  p->table_clean = true;  // the finish left the identities behind
+  MSC_CUDA(ctx, cudaEventRecord(p->k1[slot], ctx->stream));
+  p->table_clean = true;  // (stream order: the finish has left the identities behind by the time the next pass starts)
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  MSC_CUDA(ctx, cudaEventRecord(p->done[slot], ctx->stream));
+  p->issued += 1;
+  return MSC_OK;
+}
+
+extern "C" int msc_prepared_wait(msc_prepared* p, msc_rel** result, uint64_t* nrows, int32_t* nonfinite) {
+  if (!p || !result || !nrows || !nonfinite) return MSC_ERR_ARG;
+  msc_ctx* ctx = p->ctx;
+  if (p->collected == p->issued) return ctx->fail(MSC_ERR_ARG, "no pass in flight");
+  const int slot = static_cast<int>(p->collected % msc_prepared::kRing);
+  MSC_CUDA(ctx, cudaEventSynchronize(p->done[slot]));
+  p->collected += 1;
+  const unsigned long long* h = p->h_meta + 3 * slot;
+  msc_rel* rel = p->ring[slot];
+  rel->nrows = h[0];
+  rel->pending = false;
+  *nonfinite = h[1] != 0;
   *result = rel;
   *nrows = rel->nrows;
+  {
+    float ms = 0;  // this pass's kernel alone (its own event pair: later passes may be in flight already)
+    if (cudaEventElapsedTime(&ms, p->k0[slot], p->k1[slot]) == cudaSuccess) {
+      ctx->stats.last_scan_ms = ms;
+      ctx->stats.last_kernel_ms = ms;
+    }
+  }
+  if (h[2]) {
+    MSC_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    return msc_device_error_rc(ctx, static_cast<int>(h[2]));
+  }
   return MSC_OK;
+}
+
+extern "C" int msc_prepared_run(msc_prepared* p, int32_t flags, uint64_t epoch, msc_rel** result, uint64_t* nrows, int32_t* nonfinite) {
+  if (!p || !result || !nrows || !nonfinite) return MSC_ERR_ARG;
+  if (p->issued != p->collected) return p->ctx->fail(MSC_ERR_ARG, "passes in flight: collect them with msc_prepared_wait first");
+  MSC_TRY(msc_prepared_enqueue(p, flags, epoch));
+  return msc_prepared_wait(p, result, nrows, nonfinite);
 }
 
 extern "C" void msc_prepared_free(msc_prepared* p) {
   if (!p) return;
-  if (p->result) msc_rel_free(p->result);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (int i = 0; i < msc_prepared::kRing; ++i) {
+    if (p->ring[i]) msc_rel_free(p->ring[i]);
+    if (p->done[i]) cudaEventDestroy(p->done[i]);
+    if (p->k0[i]) cudaEventDestroy(p->k0[i]);
+    if (p->k1[i]) cudaEventDestroy(p->k1[i]);
+  }
+  if (p->h_meta) cudaFreeHost(p->h_meta);
   if (p->table) msc_free(p->ctx, p->table, p->table_bytes);
   delete p;
 }

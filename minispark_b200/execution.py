@@ -1505,7 +1505,8 @@ class _PreparedPass:
     def __init__(self, engine: "CudaExecutionEngine", handle: int, out_types: list[str], out_dicts: list) -> None:
         self.engine, self.handle = engine, handle
         self.out_types, self.out_dicts = out_types, out_dicts
-        self.cols: Optional[list[DeviceColumn]] = None
+        self._cols_of: dict[int, list[DeviceColumn]] = {}
+        self.in_flight = 0
         engine._closers.append(self.close)
 
     def close(self) -> None:
@@ -1513,6 +1514,15 @@ class _PreparedPass:
         if self.handle and getattr(e, "ctx", None) is not None:
             e.ctx.lib.msc_prepared_free(C.c_void_p(self.handle))
         self.handle = 0
+
+    def _rel(self, res: C.c_void_p, nrows: int) -> DeviceRel:
+        cols = self._cols_of.get(res.value)
+        if cols is None:  # (the library rotates a few result relations: remember each one's column pointers)
+            n = len(self.out_types)
+            binds = (N.ColBind * n)()
+            self.engine.ctx.check(self.engine.ctx.lib.msc_rel_cols(res, binds, n))
+            cols = self._cols_of[res.value] = [DeviceColumn(binds[i].data or 0, binds[i].phys, self.out_types[i], self.out_dicts[i]) for i in range(n)]
+        return DeviceRel(self.engine.ctx, res.value, nrows, cols, owned=False)
 
     def run(self, epoch: int, bump: Any = None) -> DeviceRel:
         """One pass; repeats it with the exact kernel when the masked one met a non-finite value.  `bump` supplies the
@@ -1526,12 +1536,20 @@ class _PreparedPass:
                 break
             if bump is not None:
                 epoch = bump()
-        if self.cols is None:
-            n = len(self.out_types)
-            binds = (N.ColBind * n)()
-            e.ctx.check(e.ctx.lib.msc_rel_cols(res, binds, n))
-            self.cols = [DeviceColumn(binds[i].data or 0, binds[i].phys, self.out_types[i], self.out_dicts[i]) for i in range(n)]
-        return DeviceRel(e.ctx, res.value, nrows.value, self.cols, owned=False)
+        return self._rel(res, nrows.value)
+
+    def enqueue(self, epoch: int) -> None:
+        """Launch a pass without waiting for it (at most MSC_PREPARED_RING in flight); collect it with wait()."""
+        self.engine.ctx.check(self.engine.ctx.lib.msc_prepared_enqueue(C.c_void_p(self.handle), 0, epoch))
+        self.in_flight += 1
+
+    def wait(self) -> tuple[DeviceRel, bool]:
+        """The oldest pass in flight: (its result, whether a SUM came out non-finite -- then the result must not be used)."""
+        e = self.engine
+        res, nrows, nonfinite = C.c_void_p(), C.c_uint64(), C.c_int32()
+        self.in_flight -= 1
+        e.ctx.check(e.ctx.lib.msc_prepared_wait(C.c_void_p(self.handle), C.byref(res), C.byref(nrows), C.byref(nonfinite)))
+        return self._rel(res, nrows.value), bool(nonfinite.value)
 
 
 class _PeerExchange:
@@ -1739,6 +1757,32 @@ class PreparedAggregate:
         e._track(DeviceRel(e.ctx, raw_h, 0, []))
         final = e._track(DeviceRel.from_handle(e.ctx, out2.value, [x.type for x in self.plan.outputs], prog2.out_dicts))
         return final, st.last_kernel_ms
+
+    def _async_pass(self) -> Optional[_PreparedPass]:
+        """The library-side prepared pass that can run ahead of the host: after the passes that set it up (two on one GPU,
+        three with several ranks: NCCL merge, then the collective set-up of the in-kernel exchange)."""
+        if self.merge is None:
+            return self._prep if self._prep else None
+        return self._peer.pass_ if self._peer and self._peer.ok else None
+
+    def enqueue(self) -> bool:
+        """Launch one pass without waiting for its result; False when this query has no asynchronous form (yet): use run()."""
+        p = self._async_pass()
+        if p is None or p.in_flight >= N.K["MSC_PREPARED_RING"]:
+            return False
+        p.enqueue(self._peer._next_epoch() if self.merge is not None else 0)
+        return True
+
+    def wait(self) -> DeviceRel:
+        """Result of the oldest pass in flight.  A non-finite SUM out of the masked kernel (identical on every rank) drains
+        the passes still in flight and repeats the pass the exact way."""
+        p = self._async_pass()
+        final, nonfinite = p.wait()
+        if nonfinite:
+            while p.in_flight:
+                p.wait()
+            final, _ = self.run()
+        return final
 
     def _run_chain(self) -> tuple[DeviceRel, float]:
         """Second and later passes on one GPU: the whole chain in one library call (msc_dense_chain)."""

@@ -172,6 +172,8 @@ _SIGNATURES = {
     "msc_prepared_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
                             C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_prepared_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
+    "msc_prepared_enqueue": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64]),
+    "msc_prepared_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "msc_prepared_free": (None, [C.c_void_p]),
     "msc_rel_nrows_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_rel_settle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int32)]),
