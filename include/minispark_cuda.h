@@ -473,7 +473,11 @@ MSC_API int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nleft
  * table as a LUT operand, build-side columns read through MSC_SRC_GATHER_T).  *out_table is a relation that owns the table
  * (free it with msc_rel_free; its one column's data pointer is what goes into msc_scan_desc.luts[]).  *unique == 0: some
  * key occurs more than once on the build side -- such a join must use msc_hash_join, which emits every pair. */
-MSC_API int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, msc_rel** out_table, int32_t* unique);
+MSC_API int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, msc_rel** out_table, int32_t* unique, int32_t* slot_bytes);
+/* *slot_bytes = 8 (compact table: every key is a sign-extended 32-bit value) or 16.  A PROBE instruction may promise the
+ * compact format to the kernel generator by setting MSC_PROBE_COMPACT in its LUT operand's index (the specialised kernel
+ * then carries only that format's code and state); the interpreter reads the format from the table's header either way. */
+#define MSC_PROBE_COMPACT 2048
 
 /* ---- shuffle partitioning: replaces WriteToShufflePartitions.write (tasks.py:347-375) and zig
  * fill_buckets (task_utils.zig:53-98).  Rows are routed by hash(key) % nparts; every column is

@@ -206,7 +206,10 @@ struct Gen {
     }
     switch (kind) {
       case MSC_SRC_TEMP: s = temp(idx); break;
-      case MSC_SRC_STAGED: s = in_finish ? "f" + std::to_string(idx) : "c" + std::to_string(idx) + "[r]"; break;
+      case MSC_SRC_STAGED:
+        if (tail_mode) s = "ldrow<" + std::to_string(sd->staged[idx].phys) + ">(sb + " + std::to_string(tail_lay.off[idx]) + ", row)";
+        else s = in_finish ? "f" + std::to_string(idx) : "c" + std::to_string(idx) + "[r]";
+        break;
       case MSC_SRC_CONST: s = (in_finish ? "p.fconsts[" : "p.consts[") + std::to_string(idx) + "]"; break;
       case MSC_SRC_GATHER:
         s = "gather_at<" + std::to_string(sd->gather[idx & 63].phys) + ">(p.gather[" + std::to_string(idx & 63) + "], c" +
@@ -265,13 +268,19 @@ struct Gen {
           *ok = false;
           return "0ll";
         }
-        return "join_probe(p.luts[" + std::to_string(opnd_b & 0xfff) + "], " + a + ", valid)";
+        return std::string("join_probe<") + ((opnd_b & MSC_PROBE_COMPACT) ? "true" : "false") + ">(p.luts[" + std::to_string(opnd_b & 0x7ff) + "], " + a +
+               ", valid, keep_policy)";
       default: *ok = false; return "0ll";
     }
   }
 
   bool temp_arrays = false;  // project scans run the program in two row loops, so temporaries are arrays over the rows
-  std::string temp(int idx) { return (in_finish ? "ft" : "t") + std::to_string(idx) + (temp_arrays ? "[r]" : ""); }
+  bool tail_mode = false;    // the compacted tail of a probing scan: one surviving row per lane, staged values read by row index
+  Layout tail_lay;
+  std::string temp(int idx) {
+    if (tail_mode) return "w" + std::to_string(idx);
+    return (in_finish ? "ft" : "t") + std::to_string(idx) + (temp_arrays ? "[r]" : "");
+  }
   std::string acc(int g, int s) { return "a" + std::to_string(g) + "_" + std::to_string(s); }
   std::string cnt(int g, int s) { return "n" + std::to_string(g) + "_" + std::to_string(s); }
 
@@ -393,6 +402,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_scan(const __g
     for (u32 k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + (u64)k * nw, lane);
   }
   const u64 nrows = p.nrows_dev ? *p.nrows_dev : p.nrows;
+  const u64 keep_policy = l2_keep_policy();  // (join-table reads ask L2 to keep their lines)
   bool bad = false;
   u32 stage = 0, parity = 0;
   for (u32 k = 0; k < ntiles_w; ++k) {
@@ -703,6 +713,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
   i64* red = reinterpret_cast<i64*>(smem + SMEM_HEADER + NW * (NSTAGES * STAGE_BYTES));  // [NW][NG * STRIDE]
   // one-hot f64 masks: row e = 0 is "no group" (filtered out / past the end / code out of range), row g + 1 selects group g
   double* mlut = reinterpret_cast<double*>(red + NW * NG * STRIDE);  // [NG + 1][NGP]
+  u32* queue = reinterpret_cast<u32*>(&mlut[(NG + 1) * NGP]) + warp * (2 * WT);  // (probing scans only: survivors of a tile)
   if (lane == 0) {
     for (u32 st = 0; st < NSTAGES; ++st) mbar_init(&full[st], 1);
     mbar_fence_init();
@@ -716,6 +727,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     for (u32 k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + (u64)k * nw, lane);
   }
   const u64 nrows = p.nrows_dev ? *p.nrows_dev : p.nrows;
+  const u64 keep_policy = l2_keep_policy();  // (join-table reads ask L2 to keep their lines)
   bool bad = false;
 )";
     for (int g = 0; g < ngroups; ++g)
@@ -779,7 +791,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     bool ok = true, grouped = false;
     if (probe_pc >= 0) {
       for (int t = 0; t < sd->ntemps; ++t) o << "    i64 t" << t << "[R];\n";
-      o << "    JoinProbe pq[R]; u32 vm = 0;\n#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = (vmask >> r) & 1u;\n";
+      o << "    JoinProbe<" << (((sd->code[probe_pc + 1] >> 16) & MSC_PROBE_COMPACT) ? "true" : "false") << "> pq[R]; u32 vm = 0;\n#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = (vmask >> r) & 1u;\n";
       for (int t = 0; t < sd->ntemps; ++t) o << "      t" << t << "[r] = 0;\n";
       for (int pc = 0; pc < probe_pc; pc += 2) {
         const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
@@ -799,11 +811,76 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       {
         const uint32_t w1 = sd->code[probe_pc + 1];
         const std::string a = operand(w1 & 0xffffu, &ok);
-        o << "      join_probe_issue(p.luts[" << ((w1 >> 16) & 0xfff) << "], " << a << ", valid, pq[r]);  // instruction "
+        o << "      join_probe_issue(p.luts[" << ((w1 >> 16) & 0x7ff) << "], " << a << ", valid, pq[r], keep_policy);  // instruction "
           << probe_pc / 2 << ", first half\n";
       }
       o << "      vm |= (valid ? 1u : 0u) << r;\n    }\n";
     }
+    // Compacted tail: when the instruction after the probe is its match filter (FILTER <- probe >= 0) and nothing later reads a
+    // temporary computed before the probe, the rows that found a partner are queued per warp (tile row, build row) and the rest
+    // of the program -- gathers, GROUP, aggregates -- runs once per SURVIVOR, a lane each, instead of once per scanned row.
+    // A selective join (config 5: 4 % of the probe side's rows survive) then pays the expensive half for those rows only.
+    bool compact_tail = false;
+    int probe_dst = 0;
+    if (probe_pc >= 0) {
+      probe_dst = (sd->code[probe_pc] >> 13) & 0x7f;
+      const uint32_t n0 = sd->code[probe_pc + 2], n1 = sd->code[probe_pc + 3];
+      const bool match_filter = (n0 & 0x3f) == MSC_OP_GE_I && ((n0 >> 6) & 7) == MSC_DST_FILTER && ((n0 >> 9) & 0xf) == 0 &&
+                                (n1 & 0xffffu) == static_cast<uint32_t>((MSC_SRC_TEMP << 12) | probe_dst) && ((n1 >> 28) & 7) == MSC_SRC_CONST &&
+                                sd->consts[(n1 >> 16) & 0xfff] == 0;
+      uint32_t early = 0;  // temporaries written before the probe
+      for (int pc = 0; pc < probe_pc; pc += 2) {
+        const uint32_t w0 = sd->code[pc];
+        if (((w0 >> 6) & 7) == MSC_DST_TEMP) early |= 1u << ((w0 >> 13) & 0x7f);
+        if ((w0 >> 9) & 0xf) early |= 1u << (((w0 >> 9) & 0xf) - 1);
+      }
+      bool reads_early = false;
+      for (int pc = probe_pc + 4; pc + 1 < sd->ncode; pc += 2) {
+        const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
+        if ((w0 & 0x3f) == MSC_OP_END) break;
+        for (int side = 0; side < 2; ++side) {
+          const uint32_t opnd = (w1 >> (16 * side)) & 0xffffu;
+          const int kind = (opnd >> 12) & 7, idx = opnd & 0xfff;
+          if (kind == MSC_SRC_TEMP && ((early >> idx) & 1u) && idx != probe_dst) reads_early = true;
+          if (kind == MSC_SRC_GATHER_T && (idx >> 6) != probe_dst && ((early >> (idx >> 6)) & 1u)) reads_early = true;
+        }
+        const int dk = (w0 >> 6) & 7;  // a later instruction that rewrites an early temporary makes it "late" from there on: keep it simple
+        if (dk == MSC_DST_TEMP && ((early >> ((w0 >> 13) & 0x7f)) & 1u)) reads_early = true;
+      }
+      static const bool compaction_enabled = !(getenv("MSC_JIT_COMPACT_TAIL") && atoi(getenv("MSC_JIT_COMPACT_TAIL")) == 0);
+      compact_tail = match_filter && !reads_early && compaction_enabled && fin == nullptr;
+    }
+    if (compact_tail) {
+      const uint32_t w1 = sd->code[probe_pc + 1];
+      o << "    u32 hits = 0;\n#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      const bool valid = (vm >> r) & 1u;\n"
+        << "      t" << probe_dst << "[r] = join_probe_resolve(p.luts[" << ((w1 >> 16) & 0x7ff) << "], pq[r], valid, keep_policy);  // instruction " << probe_pc / 2
+        << ", second half\n      if (valid && t" << probe_dst << "[r] >= 0) hits |= 1u << r;  // instruction " << probe_pc / 2 + 1 << "\n    }\n";
+      o << R"(    u32 survivors;
+    {
+      u32 at = warp_exclusive_scan(__popc(hits), lane, &survivors);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((hits >> r) & 1u) {
+          queue[2 * at] = (r / 4) * 128 + 4 * lane + (r % 4);
+)" << "          queue[2 * at + 1] = static_cast<u32>(t" << probe_dst << R"([r]);
+          ++at;
+        }
+    }
+    __syncwarp();
+    for (u32 e = lane; e < survivors; e += 32) {
+      const u32 row = queue[2 * e];
+      bool valid = true;
+      int grp = -1;
+)";
+      if (masked) {
+        o << "      double";
+        for (int g = 0; g < (ngroups + 1) / 2 * 2; ++g) o << (g ? ", m" : " m") << g << " = 0.0";
+        o << ";\n";
+      }
+      for (int t = 0; t < sd->ntemps; ++t) o << "      i64 w" << t << " = " << (t == probe_dst ? "queue[2 * e + 1]" : "0") << ";\n";
+      tail_mode = true;
+      tail_lay = lay;
+    } else {
     o << "#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = "
       << (probe_pc >= 0 ? "(vm >> r) & 1u" : (valid_bits ? "(vmask >> r) & 1u" : "true")) << ";\n      int grp = -1;\n";
     if (masked) {
@@ -815,10 +892,11 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       for (int t = 0; t < sd->ntemps; ++t) o << "      i64 t" << t << " = 0;\n";
     } else {
       const uint32_t w0 = sd->code[probe_pc], w1 = sd->code[probe_pc + 1];
-      o << "      " << temp((w0 >> 13) & 0x7f) << " = join_probe_resolve(p.luts[" << ((w1 >> 16) & 0xfff) << "], pq[r], valid);  // instruction "
+      o << "      " << temp((w0 >> 13) & 0x7f) << " = join_probe_resolve(p.luts[" << ((w1 >> 16) & 0x7ff) << "], pq[r], valid, keep_policy);  // instruction "
         << probe_pc / 2 << ", second half\n";
     }
-    for (int pc = probe_pc >= 0 ? probe_pc + 2 : 0; pc + 1 < sd->ncode; pc += 2) {
+    }
+    for (int pc = probe_pc >= 0 ? probe_pc + (compact_tail ? 4 : 2) : 0; pc + 1 < sd->ncode; pc += 2) {
       const uint32_t w0 = sd->code[pc], w1 = sd->code[pc + 1];
       const int op = w0 & 0x3f;
       if (op == MSC_OP_END) break;
@@ -872,6 +950,8 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       return false;
     }
     o << "    }\n";
+    if (compact_tail) o << "    __syncwarp();  // the queue is rewritten by the next tile\n";
+    tail_mode = false;
     // fold the tile's u32 row counts into their i64 accumulators (8 rows per lane and tile: no overflow)
     for (int g = 0; g < ngroups; ++g)
       for (int s = 0; s < stride; ++s)
@@ -1331,7 +1411,7 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
       return ctx->fail(MSC_ERR_ARG, "jit: " + why);
     const Layout lay = stage_layout(sd);
     const size_t smem = 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes + static_cast<size_t>(NW) * ngroups * stride * 8 +
-                        static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8;
+                        static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8 + (program_probes(sd) ? static_cast<size_t>(NW) * 2 * 256 * 4 : 0);
     Kernel* k = nullptr;
     MSC_TRY(load_kernel(ctx, source, "msc_jit_dense", smem, &k));
     sit = shapes().emplace(skey, ShapeEntry{k, *masked}).first;

@@ -335,8 +335,8 @@ extern "C" int msc_hash_join(msc_ctx* ctx, const int64_t* left_keys, uint64_t nl
 
 // The build half alone, for scans that probe per row (MSC_OP_PROBE): a 1-column relation that owns [header][slots].
 // Compact 8-byte slots first (32-bit keys: INTEGER columns, dictionary codes); a key outside that range rebuilds wide.
-extern "C" int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, msc_rel** out_table, int32_t* unique) {
-  if (!ctx || !out_table || !unique || (nkeys && !keys)) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+extern "C" int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, msc_rel** out_table, int32_t* unique, int32_t* slot_bytes) {
+  if (!ctx || !out_table || !unique || !slot_bytes || (nkeys && !keys)) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
   if (nkeys >= NIL) return ctx->fail(MSC_ERR_ARG, "join side exceeds 2^32-1 rows");
   uint64_t cap = 64;
   while (cap < nkeys + nkeys / 2) cap <<= 1;  // load <= 2/3: the smaller the table, the more of it stays in L2
@@ -383,6 +383,7 @@ extern "C" int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys,
       continue;
     }
     *unique = h->duplicates == 0;
+    *slot_bytes = compact ? 8 : 16;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
     *out_table = rel;

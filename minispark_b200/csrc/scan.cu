@@ -301,7 +301,7 @@ int validate_operand(msc_ctx* ctx, const msc_scan_desc* sd, uint32_t operand, bo
       return MSC_OK;
     case MSC_SRC_LUT:
       if (!allow_lut) return ctx->fail(MSC_ERR_ARG, "operand: LUT reference outside a LUT instruction");
-      return idx < sd->nluts ? MSC_OK : ctx->fail(MSC_ERR_ARG, "operand: bad LUT");
+      return (idx & ~MSC_PROBE_COMPACT) < sd->nluts ? MSC_OK : ctx->fail(MSC_ERR_ARG, "operand: bad LUT");
     default: return ctx->fail(MSC_ERR_ARG, "operand: unknown kind");
   }
 }

@@ -1021,7 +1021,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
       } else if (op == MSC_OP_LUT32) {
         op_lut<R, uint32_t>(a, reinterpret_cast<const uint32_t*>(p.luts[(w1 >> 16) & 0xfff]), vmask);
       } else if (op == MSC_OP_PROBE) {
-        op_probe<R>(a, p.luts[(w1 >> 16) & 0xfff], vmask);
+        op_probe<R>(a, p.luts[(w1 >> 16) & 0x7ff], vmask);  // (bit 11 = MSC_PROBE_COMPACT: a promise to the kernel generator)
       }
       const int tee = (w0 >> 9) & 0xf;
       if (tee) store_temp<R>(c, tee - 1, a);

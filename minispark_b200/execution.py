@@ -326,6 +326,7 @@ class _Source:
         self.pre_filters: list[L.Expr] = []
         self.probe_key: Optional[L.Expr] = None
         self.probe_table: Optional[int] = None
+        self.probe_compact = False
         self.translate_targets: Optional[dict[str, "DictHandle"]] = None
 
 
@@ -384,7 +385,7 @@ class _ScanResolver:
     def probe_spec(self) -> Optional[L.ProbeSpec]:
         if self.source.probe_key is None:
             return None
-        return L.ProbeSpec(self.source.probe_key, self._lut(self.source.probe_table))
+        return L.ProbeSpec(self.source.probe_key, self._lut(self.source.probe_table), self.source.probe_compact)
 
     def literal_code(self, dict_id: DictHandle, text: str) -> int:
         return dict_id.literal_code(text)
@@ -1111,8 +1112,8 @@ class CudaExecutionEngine(ExecutionEngine):
                 lrel = self._join_side(join.left, left_needed, L.ETranslate(L.STR, join.left_key, "join"), {"join": key_dict})
             lrel = self._gather_rows(lrel)
             broadcast = True
-        table, unique = C.c_void_p(), C.c_int32()
-        self.ctx.call("msc_join_build", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.byref(table), C.byref(unique))
+        table, unique, slot_bytes = C.c_void_p(), C.c_int32(), C.c_int32()
+        self.ctx.call("msc_join_build", C.c_void_p(lrel.cols[-1].ptr), lrel.nrows, C.byref(table), C.byref(unique), C.byref(slot_bytes))
         self._note_kernel("hash join: build")
         trel = self._track(DeviceRel.from_handle(self.ctx, table.value, [L.INT], [None]))
         if not unique.value:
@@ -1138,6 +1139,7 @@ class CudaExecutionEngine(ExecutionEngine):
         source.pre_filters = list(rsel.filters)
         source.probe_key = rkey
         source.probe_table = trel.cols[0].ptr
+        source.probe_compact = slot_bytes.value == 8
         source.translate_targets = targets
         self.last_stats["join"] = "lookup fused into the consuming scan (MSC_OP_PROBE)" + (", build side broadcast to every rank" if broadcast else "")
         return source, new_exprs

@@ -546,6 +546,7 @@ class ProbeSpec:
     build-side columns (bindings with probe=True) are read through the matched build row."""
     key: "Expr"
     lut: int
+    compact: bool = False  # the table has 8-byte slots (32-bit keys): lets a specialised kernel compile that format only
 
 
 class Resolver(Protocol):
@@ -895,7 +896,7 @@ class ProgramBuilder:
         else:
             a, frees = self.operand(spec.key)
         t = self.alloc()
-        self.emit("PROBE", a, src(SRC_LUT, spec.lut), DST_TEMP, t)
+        self.emit("PROBE", a, src(SRC_LUT, spec.lut | (K["MSC_PROBE_COMPACT"] if spec.compact else 0)), DST_TEMP, t)
         self.release(frees)
         self.emit("GE_I", src(SRC_TEMP, t), src(SRC_CONST, self.const(0)), DST_FILTER)
         self.probe_temp = t

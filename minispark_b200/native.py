@@ -200,7 +200,7 @@ _SIGNATURES = {
     "msc_dict_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "msc_str_concat": (C.c_int, [C.c_void_p, C.POINTER(ConcatPart), C.c_int32, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_hash_join": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
-    "msc_join_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "msc_join_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "msc_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]),
     "msc_shuffle_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
     "msc_shuffle_attach": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -337,18 +337,20 @@ def test_fused_join_probe_compiles(tmp_path):
         src = buf.value.decode()
         assert rc == 0, src
         # the dense scan splits its row loop around the probe: all of a lane's table reads are issued, then resolved
-        assert "join_probe_issue(p.luts[0], c1[r], valid, pq[r])" in src
-        assert "t0[r] = join_probe_resolve(p.luts[0], pq[r], valid)" in src
-        assert "gather_at<2>(p.gather[0], t0[r], valid && t0[r] >= 0)" in src
+        assert "join_probe_issue(p.luts[0], c1[r], valid, pq[r], keep_policy)" in src and "JoinProbe<false> pq[R]" in src
+        assert "t0[r] = join_probe_resolve(p.luts[0], pq[r], valid, keep_policy)" in src
+        # ... and the rows that found a partner are queued: the gathers and aggregates run once per survivor, a lane each
+        assert "queue[2 * at + 1] = static_cast<u32>(t0[r])" in src and "for (u32 e = lane; e < survivors; e += 32)" in src
+        assert "gather_at<2>(p.gather[0], w0, valid && w0 >= 0)" in src and "ldrow<5>(sb + " in src
         compile_source(src)
     res2 = _ProbeResolver()
     proj = L.compile_project(res2, [L.EBin(L.BOOL, "gt", L.EInput(L.FLOAT, 2), L.EConst(L.FLOAT, 10.0))],
-                             [L.EInput(L.INT, 0), L.EInput(L.STR, 100), L.EInput(L.FLOAT, 2)], probe=L.ProbeSpec(L.EInput(L.INT, 0), 0), pre_filters=[])
+                             [L.EInput(L.INT, 0), L.EInput(L.STR, 100), L.EInput(L.FLOAT, 2)], probe=L.ProbeSpec(L.EInput(L.INT, 0), 0, compact=True), pre_filters=[])
     assert any("RANK" in t for t in proj.program.text), proj.program.text
     d2 = _probe_desc(proj, res2)
     for count_only in (1, 0):
         rc = lib.msc_jit_project_source(C.byref(d2), count_only, N.int32_array(proj.out_phys), len(proj.out_phys), buf, len(buf), C.byref(n))
         src = buf.value.decode()
         assert rc == 0, src
-        assert "join_probe(p.luts[0]" in src
+        assert "join_probe<true>(p.luts[0]" in src
         compile_source(src)
