@@ -538,6 +538,13 @@ MSC_API void msc_shuffle_free(msc_shuffle* sh);
 /* ---- results: replaces WriteToLocalFileTask.write (tasks.py:399-410) / zig BlockFile.appendData
  * (block_file.zig:413-456).  INTEGER narrows to i32 (error on overflow), FLOAT to f32. ------- */
 MSC_API int msc_rel_copy_column(msc_ctx* ctx, msc_rel* r, int32_t col, void* host_dst, size_t cap_bytes);
+/* Rows `rows[0..nreq)` (nreq <= 4) of a relation as raw 64-bit values, out[nreq][ncols] (integers sign / zero extended, F32
+ * widened to F64 bits), and the fold of one row of partial aggregates into row `row`: column i takes values[i] by
+ * kinds[i] = MSC_AGG_* (kinds[i] < 0: untouched).  Together they are the final aggregate of a shuffle whose partial results
+ * ascend by key on every rank and follow each other in rank order: only the group that straddles two ranks has a partner,
+ * so its row is read, sent (msc_shuffle_allgather) and folded instead of re-aggregating everything (plan.py:190-199). */
+MSC_API int msc_rel_read_rows(msc_ctx* ctx, msc_rel* r, const uint64_t* rows, int32_t nreq, int64_t* out);
+MSC_API int msc_rel_fold_row(msc_ctx* ctx, msc_rel* r, uint64_t row, const int64_t* values, const int32_t* kinds);
 typedef struct msc_out_col {
   const char* name;
   int32_t type;      /* MSC_T_* */

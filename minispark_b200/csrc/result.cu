@@ -157,3 +157,103 @@ extern "C" int msc_write_blockfile(msc_ctx* ctx, msc_rel* r, const msc_out_col* 
   if (fflush(fc.f) != 0) return ctx->fail(MSC_ERR_IO, "flush failed");
   return MSC_OK;
 }
+
+
+// ---- single rows of a relation, as raw 64-bit values: what the boundary merge of sorted partial aggregates needs (the one
+// group that straddles two ranks) -- reading a row costs one tiny kernel and one host wait, folding one a tiny kernel.
+namespace {
+
+struct RowCols {
+  const void* data[MSC_VM_MAX_OUT + 1];
+  int phys[MSC_VM_MAX_OUT + 1];
+  int kind[MSC_VM_MAX_OUT + 1];
+  int ncols;
+};
+
+__device__ __forceinline__ long long row_value(const void* col, int phys, uint64_t i) {
+  switch (phys) {
+    case MSC_P_U8: return static_cast<const uint8_t*>(col)[i];
+    case MSC_P_U16: return static_cast<const uint16_t*>(col)[i];
+    case MSC_P_U32: return static_cast<const uint32_t*>(col)[i];
+    case MSC_P_I32: return static_cast<const int*>(col)[i];
+    case MSC_P_F32: return __double_as_longlong(static_cast<double>(static_cast<const float*>(col)[i]));
+    default: return static_cast<const long long*>(col)[i];
+  }
+}
+
+__global__ void read_rows_kernel(RowCols c, const uint64_t* rows, int nreq, long long* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nreq * c.ncols) return;
+  out[i] = row_value(c.data[i % c.ncols], c.phys[i % c.ncols], rows[i / c.ncols]);
+}
+
+// accumulator columns are 64-bit (I64 / F64); kind < 0: leave the column alone (the key)
+__global__ void fold_row_kernel(RowCols c, uint64_t row, const long long* values) {
+  const int i = threadIdx.x;
+  if (i >= c.ncols || c.kind[i] < 0) return;
+  long long* cell = static_cast<long long*>(const_cast<void*>(c.data[i])) + row;
+  const long long cur = *cell, v = values[i];
+  long long r = cur;
+  switch (c.kind[i]) {
+    case MSC_AGG_SUM_F: r = __double_as_longlong(__longlong_as_double(cur) + __longlong_as_double(v)); break;
+    case MSC_AGG_SUM_I: r = cur + v; break;
+    case MSC_AGG_MIN_F: r = __longlong_as_double(v) < __longlong_as_double(cur) ? v : cur; break;
+    case MSC_AGG_MAX_F: r = __longlong_as_double(v) > __longlong_as_double(cur) ? v : cur; break;
+    case MSC_AGG_MIN_I: r = v < cur ? v : cur; break;
+    default: r = v > cur ? v : cur; break;
+  }
+  *cell = r;
+}
+
+int row_cols(msc_ctx* ctx, msc_rel* r, RowCols* c) {
+  if (r->cols.size() > MSC_VM_MAX_OUT + 1) return ctx->fail(MSC_ERR_ARG, "too many columns");
+  c->ncols = static_cast<int>(r->cols.size());
+  for (int i = 0; i < c->ncols; ++i) {
+    c->data[i] = r->cols[i].data;
+    c->phys[i] = r->cols[i].phys;
+    c->kind[i] = -1;
+  }
+  return MSC_OK;
+}
+
+}  // namespace
+
+extern "C" int msc_rel_read_rows(msc_ctx* ctx, msc_rel* r, const uint64_t* rows, int32_t nreq, int64_t* out) {
+  if (!ctx || !r || !rows || !out || nreq < 1 || nreq > 4) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  for (int i = 0; i < nreq; ++i)
+    if (rows[i] >= r->nrows) return ctx->fail(MSC_ERR_ARG, "row out of range");
+  RowCols c;
+  MSC_TRY(row_cols(ctx, r, &c));
+  const int n = nreq * c.ncols;
+  DevTmp d_rows(ctx), d_out(ctx);
+  MSC_TRY(d_rows.alloc(sizeof(uint64_t) * 4));
+  MSC_TRY(d_out.alloc(sizeof(long long) * n));
+  unsigned long long* h = ctx->h_scratch;  // pinned, 16 words
+  for (int i = 0; i < nreq; ++i) h[i] = rows[i];
+  MSC_CUDA(ctx, cudaMemcpyAsync(d_rows.p, h, sizeof(uint64_t) * nreq, cudaMemcpyHostToDevice, ctx->stream));
+  read_rows_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(c, d_rows.as<uint64_t>(), nreq, d_out.as<long long>());
+  ctx->stats.launches += 1;
+  MSC_CUDA(ctx, cudaMemcpyAsync(out, d_out.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MSC_CUDA(ctx, cudaGetLastError());
+  return MSC_OK;
+}
+
+extern "C" int msc_rel_fold_row(msc_ctx* ctx, msc_rel* r, uint64_t row, const int64_t* values, const int32_t* kinds) {
+  if (!ctx || !r || !values || !kinds || row >= r->nrows) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  RowCols c;
+  MSC_TRY(row_cols(ctx, r, &c));
+  for (int i = 0; i < c.ncols; ++i) {
+    c.kind[i] = kinds[i];
+    if (kinds[i] >= 0 && r->cols[i].phys != MSC_P_I64 && r->cols[i].phys != MSC_P_F64) return ctx->fail(MSC_ERR_ARG, "accumulator columns are 64-bit");
+    if (kinds[i] > MSC_AGG_MAX_I) return ctx->fail(MSC_ERR_ARG, "bad aggregate kind");
+  }
+  DevTmp d_vals(ctx);
+  MSC_TRY(d_vals.alloc(sizeof(long long) * c.ncols));
+  MSC_CUDA(ctx, cudaMemcpyAsync(d_vals.p, values, sizeof(long long) * c.ncols, cudaMemcpyHostToDevice, ctx->stream));
+  MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (`values` is the caller's pageable memory)
+  fold_row_kernel<<<1, 32, 0, ctx->stream>>>(c, row, d_vals.as<long long>());
+  ctx->stats.launches += 1;
+  MSC_CUDA(ctx, cudaGetLastError());
+  return MSC_OK;
+}

@@ -79,6 +79,26 @@ def range_bounds(per_rank: Sequence[tuple[bool, int, int, int]]) -> Optional[lis
     return bounds
 
 
+def boundary_plan(per_rank: Sequence[tuple[int, int, int]], bounds: Sequence[int], rank: int) -> tuple[bool, list[int]]:
+    """The shuffle of sorted, rank-ordered partial aggregates (range_bounds) without moving rows: per_rank[r] = (rows, first
+    key, last key) of rank r's partial result, whose keys are unique on the rank.  A group can only be shared by a rank's
+    LAST row and the first row of the rank that owns the key (the last rank whose range starts at or below it).  Returns for
+    `rank`: (its last row belongs to a later rank: drop it, the ranks whose last row must be folded into its first row --
+    in rank order)."""
+    world = len(per_rank)
+
+    def owner(key: int) -> int:
+        r = 0
+        for i in range(1, world):
+            if key >= bounds[i]:
+                r = i
+        return r
+
+    moving = [per_rank[s][0] > 0 and owner(per_rank[s][2]) != s for s in range(world)]
+    incoming = [s for s in range(world) if moving[s] and owner(per_rank[s][2]) == rank]
+    return moving[rank], incoming
+
+
 def exchange_plan(counts_matrix: Sequence[Sequence[int]], rank: int) -> tuple[list[int], list[int]]:
     """(send_counts, recv_counts) of ``rank`` given counts_matrix[src][dst] rows routed src -> dst."""
     world = len(counts_matrix)

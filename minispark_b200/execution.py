@@ -31,7 +31,7 @@ from typing import TYPE_CHECKING, Any, Iterable, Optional
 
 from . import lowering as L
 from . import native as N
-from .distributed import Comm, PeerShuffle, invert_code_maps, range_bounds, shard_blocks, unify_keys
+from .distributed import Comm, PeerShuffle, boundary_plan, invert_code_maps, range_bounds, shard_blocks, unify_keys
 from .constants import ColumnType, Row, Schema
 from .io import BlockFile
 from .jobs import JobResult, OutputFile
@@ -1372,20 +1372,40 @@ class CudaExecutionEngine(ExecutionEngine):
             outs += [L.EInput(t, i + 1) for i, t in enumerate(slot_types)]
             prog = L.compile_project(resolver, [], outs)
             raw = self._scan_project(resolver, prog, [L.INT, *slot_types])
-        # what every rank holds: rows, and -- when its pre-aggregation streamed over the runs of a sorted key (MSC_SCAN_KIND_RUNS),
-        # so that its partial rows ascend -- the first and last key
-        ascending = bool(self.ctx.stats().last_agg_runs) and group_type in (L.INT, L.TS) and raw.nrows > 0
-        first = last = 0
+        # what every rank holds: rows, and -- when its pre-aggregation streamed over the runs of a sorted key (msc_stats.last_agg_runs),
+        # so that its partial rows ascend and no key repeats on the rank -- the first key and the whole last row
+        ascending = bool(self.ctx.stats().last_agg_runs) and group_type in (L.INT, L.TS) and raw.nrows > 0 and raw.handle is not None
+        ncols = len(raw.cols)
+        first, last_row = 0, [0] * ncols
         if ascending:
-            import numpy as np  # noqa: PLC0415
-
-            ends = np.zeros(2, dtype=np.int64)
-            self.ctx.call("msc_memcpy_d2h", ends[0:1].ctypes.data_as(C.c_void_p), C.c_void_p(raw.cols[0].ptr), 8)
-            self.ctx.call("msc_memcpy_d2h", ends[1:2].ctypes.data_as(C.c_void_p), C.c_void_p(raw.cols[0].ptr + 8 * (raw.nrows - 1)), 8)
-            first, last = int(ends[0]), int(ends[1])
-        per_rank = [tuple(r) for r in self._gather_counts([int(ascending or raw.nrows == 0), raw.nrows, first, last])]
+            out = (C.c_int64 * (2 * ncols))()
+            self.ctx.call("msc_rel_read_rows", C.c_void_p(raw.handle), (C.c_uint64 * 2)(0, raw.nrows - 1), 2, out)
+            first, last_row = int(out[0]), [int(out[ncols + i]) for i in range(ncols)]
+        everyone = self._gather_counts([int(ascending or raw.nrows == 0), raw.nrows, first, *last_row])
+        per_rank = [(r[0], r[1], r[2], r[3]) for r in everyone]
         small = max(r[1] for r in per_rank) <= int(os.environ.get("MSC_EXCHANGE_GATHER_MAX", "65536"))
         bounds = None if small or os.environ.get("MSC_EXCHANGE_RANGE", "1") == "0" else range_bounds([(bool(r[0]), r[1], r[2], r[3]) for r in per_rank])
+        if bounds is not None and os.environ.get("MSC_EXCHANGE_BOUNDARY", "1") != "0":
+            # Sorted partial results whose key ranges follow each other in rank order: only a group that straddles two ranks has a
+            # partner anywhere.  Its row -- the last row of the earlier rank -- is folded into the owner's first row and dropped
+            # where it came from; no other row moves and nothing is re-aggregated (the reference would shuffle every partial row
+            # and aggregate them again, plan.py:190-199).  Every rank decides from the same gathered numbers.
+            drop_last, incoming = boundary_plan([(r[1], r[2], r[3]) for r in everyone], bounds, comm.rank)
+            kinds = N.int32_array([-1, *agg_kinds])
+            for s in incoming:
+                values = (C.c_int64 * ncols)(*everyone[s][3:3 + ncols])
+                self.ctx.call("msc_rel_fold_row", C.c_void_p(raw.handle), 0, values, kinds)
+            if drop_last:
+                raw.nrows -= 1
+            self.last_stats["exchange"] = "boundary rows over nvlink peer control blocks (sorted partial results: no other row moves)"
+            self.last_stats.setdefault("exchanges", []).append(self.last_stats["exchange"])
+            self.last_stats["exchange_rows_sent"] = int(drop_last)
+            self.last_stats["exchange_bytes_sent"] = int(drop_last) * 8 * ncols
+            self.last_stats["exchange_host_s"] = 0.0
+            if global_dict is not None:
+                raw.cols[0] = DeviceColumn(raw.cols[0].ptr, raw.cols[0].phys, group_type, global_dict)
+            raw.partitioned = True
+            return raw
         gathered = self._exchange_rows(raw, None if small else 0, bounds)
         # final aggregate over the partial rows: SUM of sums / counts, MIN of mins, MAX of maxes
         merge_kind = {N.K["MSC_AGG_SUM_F"]: "sum", N.K["MSC_AGG_SUM_I"]: "sum", N.K["MSC_AGG_MIN_F"]: "min", N.K["MSC_AGG_MIN_I"]: "min",

@@ -218,6 +218,8 @@ _SIGNATURES = {
     "msc_shuffle_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),
     "msc_shuffle_free": (None, [C.c_void_p]),
     "msc_rel_copy_column": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
+    "msc_rel_read_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int64)]),
+    "msc_rel_fold_row": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "msc_write_blockfile": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(OutCol), C.c_int32, C.c_char_p, C.c_uint32]),
 }
 

@@ -78,11 +78,21 @@ def main() -> None:
         # high-cardinality GROUP BY through hash partitioning + the row exchange: ranks hold disjoint sets of keys ...
         os.environ["MSC_EXCHANGE_GATHER_MAX"] = "0"
         rel, schema = engine.execute_to_device(high_card(engine).task)
-        # (lineitem is clustered by l_orderkey and sharded in row order: the partial results ascend, ranks keep their key ranges)
-        assert engine.last_stats["exchange"].startswith("nvlink peer push (range" if peer else "nccl send/recv group (range"), engine.last_stats
+        # (lineitem is clustered by l_orderkey and sharded in row order: the partial results ascend and the ranks' key ranges
+        # follow each other, so only the group that straddles two ranks is merged -- its row travels, nothing else does)
+        assert engine.last_stats["exchange"].startswith("boundary rows"), engine.last_stats
         assert engine.last_stats["result_partitioned"] is True and rel.partitioned
-        assert engine.last_stats["exchange_rows_sent"] <= 1  # at most the one key that straddles two ranks changes rank
+        assert engine.last_stats["exchange_rows_sent"] <= 1
         mine = rel.column_numpy(0).tolist()
+        boundary_rows = {tuple(rel.column_numpy(i).tolist()) for i in range(len(schema))}
+        engine.release_query()
+        # the same through the general machinery: a range-partitioned exchange of all partial rows + a streaming final aggregate
+        os.environ["MSC_EXCHANGE_BOUNDARY"] = "0"
+        rel, schema = engine.execute_to_device(high_card(engine).task)
+        os.environ.pop("MSC_EXCHANGE_BOUNDARY")
+        assert engine.last_stats["exchange"].startswith("nvlink peer push (range" if peer else "nccl send/recv group (range"), engine.last_stats
+        assert engine.last_stats["exchange_rows_sent"] <= 1  # at most the one key that straddles two ranks changes rank
+        assert {tuple(rel.column_numpy(i).tolist()) for i in range(len(schema))} == boundary_rows
         engine.release_query()
         gathered: list = [None] * world
         dist.all_gather_object(gathered, mine)
