@@ -479,6 +479,13 @@ MSC_API int msc_join_build(msc_ctx* ctx, const int64_t* keys, uint64_t nkeys, ms
  * then carries only that format's code and state); the interpreter reads the format from the table's header either way. */
 #define MSC_PROBE_COMPACT 2048
 
+/* msc_join_build without materialising the build side: ONE scan over its base rows whose program holds the side's filters
+ * (then a RANK, as in msc_scan_project) and GROUP <- key; the rows that pass insert (key, their base row number) into a
+ * compact table (a count pass sizes it when the scan filters).  Build-side columns are then read from the BASE columns
+ * through the probe's match.  *usable == 0 (and *out_table == NULL): a key repeats or does not fit 32 bits -- build the
+ * general way (materialise, msc_join_build / msc_hash_join).  *nkeys = rows that passed the filters. */
+MSC_API int msc_scan_join_build(msc_ctx* ctx, const msc_scan_desc* scan, msc_rel** out_table, int32_t* usable, uint64_t* nkeys);
+
 /* ---- shuffle partitioning: replaces WriteToShufflePartitions.write (tasks.py:347-375) and zig
  * fill_buckets (task_utils.zig:53-98).  Rows are routed by hash(key) % nparts; every column is
  * scattered into partition-contiguous order, STABLE (rows of a partition keep their input order, as the reference's

@@ -14,7 +14,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libminispark_cuda.so"
 OBJ_DIR = PKG / "build"
-SOURCES = ["scan_inst_r4_dense.cu", "scan_inst_r8_dense.cu", "scan_inst_r4_hash.cu", "scan_inst_r8_hash.cu", "scan_inst_r8_runs.cu", "scan_inst_r4_count.cu",
+SOURCES = ["scan_inst_r4_dense.cu", "scan_inst_r8_dense.cu", "scan_inst_r4_hash.cu", "scan_inst_r8_hash.cu", "scan_inst_r8_runs.cu", "scan_inst_r4_count.cu", "scan_inst_r4_build.cu",
            "scan_inst_r4_project.cu", "scan_regvm_ng0.cu", "scan_regvm_ng1.cu", "scan_regvm_ng2.cu", "scan_regvm_ng3.cu", "scan_regvm_ng4.cu", "core.cu", "scan.cu", "jit.cu", "strings.cu", "ingest.cu", "join.cu", "shuffle.cu", "result.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",

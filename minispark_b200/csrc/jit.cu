@@ -381,7 +381,7 @@ struct Gen {
       why = "count scan without a filter";
       return false;
     }
-    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
+    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << min_ctas(JIT_MIN_CTAS) << "\n" << kPrelude;
     o << "constexpr int NSTAGES = " << nstages << ";\n";
     emit_layout(lay);
     o << R"(
@@ -504,12 +504,19 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_scan(const __g
     return true;
   }
 
+  // resident CTAs per SM the register allocator is asked to fit (experiments: MSC_JIT_MINCTAS overrides)
+  static int min_ctas(int chosen) {
+    const char* e = getenv("MSC_JIT_MINCTAS");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= 16) ? v : chosen;
+  }
+
   // GROUP BY a sorted integer key column (scan.cu checked: no descents, no filter): every run of equal keys is a group and
   // its run number is its output row (scan_kernel.cuh MODE_RUNS is the interpreted twin).
   bool generate_runs(int key_col) {
     const Layout lay = stage_layout(sd);
     temp_arrays = false;
-    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << JIT_MIN_CTAS << "\n" << kPrelude;
+    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << min_ctas(JIT_MIN_CTAS) << "\n" << kPrelude;
     o << "constexpr int NSTAGES = " << nstages << ";\n";
     emit_layout(lay);
     o << R"(
@@ -533,8 +540,28 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
   bool bad = false;
   i64* out_key = reinterpret_cast<i64*>(p.out[0]);
   u32 stage = 0, parity = 0;
+)";
+    // Two values of a tile live in global memory, not in its staged columns: the number of runs that start before it and
+    // the key of the row before its first.  Both are fetched one tile AHEAD (prof_runs: the two loads, issued where they
+    // were needed, held 23 % of the kernel's stall samples).
+    const int kphys = sd->staged[key_col].phys;
+    const char* kty = kphys == MSC_P_U8 ? "unsigned char" : kphys == MSC_P_U16 ? "unsigned short" : kphys == MSC_P_U32 ? "u32"
+                      : kphys == MSC_P_I32 ? "int" : "i64";
+    o << "  const " << kty << "* key_col = reinterpret_cast<const " << kty << "*>(p.col[" << key_col << "]);\n";
+    o << R"(  u64 next_base = 0;
+  i64 next_before = 0;
+  if (ntiles_w > 0) {
+    next_base = p.tile_offsets[gw];
+    if (lane == 0 && gw > 0) next_before = (i64)key_col[(u64)gw * WT - 1];
+  }
   for (u32 k = 0; k < ntiles_w; ++k) {
     const u64 tile = gw + (u64)k * nw;
+    const u64 base = next_base;  // runs that start before this tile
+    const i64 before = next_before;
+    if (k + 1 < ntiles_w) {
+      next_base = p.tile_offsets[tile + nw];
+      if (lane == 0) next_before = (i64)key_col[(tile + nw) * WT - 1];
+    }
     const unsigned char* sb = stages + stage * STAGE_BYTES;
     while (!mbar_try_wait(&full[stage], parity)) {
     }
@@ -592,19 +619,15 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
       why = ok ? "program has no GROUP" : "operand or opcode outside the generator";
       return false;
     }
-    const int kphys = sd->staged[key_col].phys;
-    const char* kty = kphys == MSC_P_U8 ? "unsigned char" : kphys == MSC_P_U16 ? "unsigned short" : kphys == MSC_P_U32 ? "u32"
-                      : kphys == MSC_P_I32 ? "int" : "i64";
     o << "    // a row starts a run when its key differs from the previous ROW's: rows 4*lane..4*lane+3 of each 128-row half\n";
     o << "    i64 prev0 = __shfl_up_sync(0xffffffffu, key[3], 1), prev1 = __shfl_up_sync(0xffffffffu, key[7], 1);\n";
     o << "    const i64 row127 = __shfl_sync(0xffffffffu, key[3], 31);\n";
-    o << "    if (lane == 0) {\n      prev1 = row127;\n      prev0 = tile_row0 > 0 ? (i64)reinterpret_cast<const " << kty << "*>(p.col[" << key_col
-      << "])[tile_row0 - 1] : ~key[0];\n    }\n";
+    o << "    if (lane == 0) {\n      prev1 = row127;\n      prev0 = tile_row0 > 0 ? before : ~key[0];\n    }\n";
     o << R"(    bool h[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const i64 before = (r == 0) ? prev0 : (r == 4) ? prev1 : key[r > 0 ? r - 1 : 0];
-      h[r] = ((vmask >> r) & 1u) && key[r] != before;
+      const i64 left = (r == 0) ? prev0 : (r == 4) ? prev1 : key[r > 0 ? r - 1 : 0];
+      h[r] = ((vmask >> r) & 1u) && key[r] != left;
     }
     int idx[R];
     {
@@ -616,7 +639,6 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
         if (lane >= o) inc += n;
       }
       const u32 total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - c;
-      const u64 base = p.tile_offsets[tile];  // runs that start before this tile
       u64 run0 = base + (excl & 0xffffu), run1 = base + (total & 0xffffu) + (excl >> 16);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -671,8 +693,10 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
       count_const[naggs] = -1;
     }
 
+    // (a probing scan waits on table reads, not on arithmetic: with few cells a fifth resident CTA hides more of that latency --
+    // config 5: 0.573 -> 0.513 ms)
     // registers: 2 per accumulator cell; up to 32 cells fit 4 CTAs of 128 threads per SM (128 registers), more need 3 (168)
-    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << (ngroups * stride <= JIT_REG_CELLS_4CTAS ? 4 : 3) << "\n" << kPrelude;
+    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << min_ctas(program_probes(sd) && ngroups * stride <= 16 ? 5 : ngroups * stride <= JIT_REG_CELLS_4CTAS ? 4 : 3) << "\n" << kPrelude;
     if (masked) {  // the masks are fixed at GROUP: a later filter would not reach them
       bool grouped_seen = false;
       for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {

@@ -406,7 +406,7 @@ int validate_program(msc_ctx* ctx, const msc_scan_desc* sd, int mode, const int3
         break;
       case MSC_DST_FILTER: case MSC_DST_NONE: break;
       case MSC_DST_GROUP:
-        if (mode != MODE_DENSE && mode != MODE_HASH && mode != MODE_RUNS) return ctx->fail(MSC_ERR_ARG, "GROUP outside an aggregate scan");
+        if (mode != MODE_DENSE && mode != MODE_HASH && mode != MODE_RUNS && mode != MODE_BUILD) return ctx->fail(MSC_ERR_ARG, "GROUP outside an aggregate scan");
         break;
       case MSC_DST_AGG:
         if (mode != MODE_DENSE && mode != MODE_HASH && mode != MODE_RUNS) return ctx->fail(MSC_ERR_ARG, "AGG outside an aggregate scan");
@@ -1599,6 +1599,91 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
   ctx->stats.last_kernel_ms = ms;
   if (sd->nrows > 0 && cudaEventElapsedTime(&ms, ctx->ev_s0, ctx->ev_s1) == cudaSuccess) ctx->stats.last_scan_ms = ms;
   *out = rel;
+  return MSC_OK;
+}
+
+// The build half of a hash join as ONE scan over the build side's base rows: filters, then GROUP <- key; rows that pass
+// insert (key, their row number) into a compact table.  A count pass sizes the table when the scan filters.
+extern "C" int msc_scan_join_build(msc_ctx* ctx, const msc_scan_desc* sd, msc_rel** out_table, int32_t* usable, uint64_t* nkeys_out) {
+  if (!ctx || !sd || !out_table || !usable) return ctx ? ctx->fail(MSC_ERR_ARG, "bad arguments") : MSC_ERR_ARG;
+  MSC_TRY(validate_program(ctx, sd, MODE_BUILD, nullptr, 0, nullptr, 0));
+  if (sd->nrows >= 0xFFFFFFFFull) return ctx->fail(MSC_ERR_ARG, "join side exceeds 2^32-1 rows");
+  *usable = 0;
+  *out_table = nullptr;
+  int rank_pc = -1;
+  bool grouped = false;
+  for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
+    const int op = sd->code[pc] & 0x3f, dk = (sd->code[pc] >> 6) & 7;
+    if (op == MSC_OP_END) break;
+    if (op == MSC_OP_RANK) rank_pc = pc;
+    if (dk == MSC_DST_GROUP) grouped = true;
+    if (dk == MSC_DST_AGG || dk == MSC_DST_OUT) return ctx->fail(MSC_ERR_ARG, "a join build scan has filters and a GROUP (the key) only");
+  }
+  if (!grouped) return ctx->fail(MSC_ERR_ARG, "join build scan without a key");
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  LaunchPlan lp;
+  MSC_TRY(plan_launch(ctx, sd, 4, 0, &lp));
+  uint64_t nkeys = sd->nrows;
+  if (rank_pc >= 0 && sd->nrows > 0) {  // filtered: count the survivors first (the table must be sized for them, not for the base rows)
+    LaunchPlan cp = lp;
+    cp.p.code[rank_pc + 2] = MSC_OP_END;
+    DevTmp counts(ctx), offsets(ctx);
+    MSC_TRY(counts.alloc(sizeof(uint32_t) * cp.p.ntiles));
+    MSC_TRY(offsets.alloc(sizeof(uint64_t) * (cp.p.ntiles + 1)));
+    cp.p.tile_counts = counts.as<uint32_t>();
+    cp.timed = false;
+    MSC_TRY(launch_scan_r<MODE_COUNT>(ctx, &cp));
+    MSC_TRY(msc_exclusive_scan_u32_u64(ctx, counts.as<uint32_t>(), offsets.as<uint64_t>(), cp.p.ntiles));
+    MSC_CUDA(ctx, cudaMemcpyAsync(&nkeys, offsets.as<uint64_t>() + cp.p.ntiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    const int drc = msc_check_device_error(ctx);  // synchronises the stream
+    if (drc != MSC_OK) return drc;
+  }
+  if (nkeys_out) *nkeys_out = nkeys;
+  uint64_t cap = 64, bitmap_bits = 1024;
+  while (cap < nkeys + nkeys / 2) cap <<= 1;
+  while (bitmap_bits < nkeys * 16 && bitmap_bits < (1ull << 32)) bitmap_bits <<= 1;
+  msc_rel* rel = new_rel(ctx, cap);
+  msc_col c;
+  c.phys = MSC_P_U8;
+  c.bytes = sizeof(MscJoinTableHeader) + bitmap_bits / 8 + cap * 8;
+  int rc = msc_alloc(ctx, c.bytes, &c.data);
+  if (rc != MSC_OK) {
+    msc_rel_free(rel);
+    return rc;
+  }
+  rel->cols.push_back(c);
+  MscJoinTableHeader* header = static_cast<MscJoinTableHeader*>(c.data);
+  MscJoinTableHeader* h = reinterpret_cast<MscJoinTableHeader*>(ctx->h_scratch);  // pinned, 16 words
+  *h = MscJoinTableHeader{cap, 0, 8, 0, bitmap_bits, {0, 0, 0}};
+  MSC_CUDA(ctx, cudaMemcpyAsync(header, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
+  char* body = static_cast<char*>(c.data) + sizeof(MscJoinTableHeader);
+  MSC_CUDA(ctx, cudaMemsetAsync(body, 0, bitmap_bits / 8, ctx->stream));
+  MSC_CUDA(ctx, cudaMemsetAsync(body + bitmap_bits / 8, 0xFF, cap * 8, ctx->stream));  // MSC_J_EMPTY8 = all ones
+  lp.p.jheader = header;
+  lp.p.jbitmap = reinterpret_cast<uint32_t*>(body);
+  lp.p.jslots = reinterpret_cast<unsigned long long*>(body + bitmap_bits / 8);
+  lp.p.hcap = cap;
+  if (sd->nrows > 0) {
+    rc = launch_scan_r<MODE_BUILD>(ctx, &lp);
+    if (rc != MSC_OK) {
+      msc_rel_free(rel);
+      return rc;
+    }
+  }
+  MSC_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  MSC_CUDA(ctx, cudaMemcpyAsync(h, header, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+  const int drc = msc_check_device_error(ctx);  // synchronises the stream
+  if (drc != MSC_OK) {
+    msc_rel_free(rel);
+    return drc;
+  }
+  note_times(ctx, sd->nrows > 0);
+  if (h->duplicates || h->wide_keys) {  // not a lookup table after all: the caller builds the general way
+    msc_rel_free(rel);
+    return MSC_OK;
+  }
+  *usable = 1;
+  *out_table = rel;
   return MSC_OK;
 }
 

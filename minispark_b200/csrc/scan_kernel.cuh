@@ -26,7 +26,9 @@ constexpr int MAX_STAGES = 8;
 constexpr int SMEM_HEADER = NW * MAX_STAGES * 8;  // mbarriers: full[warp][stage]
 
 // MODE_RUNS: GROUP BY a sorted key column -- every run of equal keys is a group, its output row is its run number
-enum Mode { MODE_DENSE = 0, MODE_HASH = 1, MODE_COUNT = 2, MODE_PROJECT = 3, MODE_RUNS = 4 };
+// MODE_BUILD: the build half of a hash join as a scan -- rows that pass the filters insert (GROUP value = key, row number)
+// into a compact join table (join_table.cuh) without being materialised
+enum Mode { MODE_DENSE = 0, MODE_HASH = 1, MODE_COUNT = 2, MODE_PROJECT = 3, MODE_RUNS = 4, MODE_BUILD = 5 };
 
 struct StagedCol {
   const unsigned char* base;
@@ -74,6 +76,10 @@ struct ScanParams {
   // MODE_RUNS: staged slot of the key column; tile_offsets[] = runs that start before each warp tile; out[0] = key
   // column of the result (i64), out[1 + a] = accumulator column a, already holding its identity
   int run_key_col;
+  // MODE_BUILD: the compact join table being filled (header, presence bitmap, 8-byte slots)
+  MscJoinTableHeader* jheader;
+  uint32_t* jbitmap;
+  unsigned long long* jslots;
 };
 
 struct LaunchPlan {
@@ -685,6 +691,51 @@ __device__ __forceinline__ void set_group(const Ctx& c, const long long (&x)[R],
       }
       grp[r] = sl;
     }
+  } else if constexpr (MODE == MODE_BUILD) {
+    // key -> row number into the compact table (msc_join_build's format: 8-byte slots row << 32 | (u32)key, presence bitmap).
+    // A key outside the 32-bit range or a second row with the same key only raises its flag: the host then builds the
+    // general way.
+    const uint64_t row0 = c.tile * (32ull * R) + static_cast<uint64_t>(c.lane) * R;
+    const uint64_t mask = c.p.hcap - 1, bmask = c.p.jheader->bitmap_bits - 1;
+    uint32_t k32[R];
+    uint64_t pos[R];
+    bool pend[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      grp[r] = -1;
+      pend[r] = (vmask >> r) & 1u;
+      if (pend[r] && !msc_join_key_is_32bit(x[r])) {
+        c.p.jheader->wide_keys = 1;
+        pend[r] = false;
+      }
+      k32[r] = static_cast<uint32_t>(x[r]);
+      pos[r] = msc_fmix32(k32[r]) & mask;
+      if (pend[r]) {
+        const uint64_t bit = msc_fmix32(k32[r] ^ 0x9e3779b9u) & bmask;
+        atomicOr(&c.p.jbitmap[bit >> 5], 1u << (bit & 31));
+      }
+    }
+    while (true) {  // the lane's R inserts advance together: R atomics in flight per step (cf. the hash aggregate above)
+      unsigned long long prev[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (pend[r]) prev[r] = atomicCAS(&c.p.jslots[pos[r]], MSC_J_EMPTY8, ((row0 + r) << 32) | k32[r]);
+      bool more = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!pend[r]) continue;
+        if (prev[r] == MSC_J_EMPTY8) {
+          pend[r] = false;
+        } else if (static_cast<uint32_t>(prev[r]) == k32[r]) {
+          c.p.jheader->duplicates = 1;
+          pend[r] = false;
+        } else {
+          pos[r] = (pos[r] + 1) & mask;
+          more = true;
+        }
+      }
+      if (!more) break;
+    }
   } else if constexpr (MODE == MODE_RUNS) {
     // Sorted key column (the host checked): a row's group is the number of runs that started at or before it, minus one.
     // Runs before the tile come from a prefix sum over per-tile counts (run_heads_kernel in scan.cu), runs before the
@@ -851,7 +902,7 @@ __host__ __device__ constexpr bool out_valid(int fk, int u32) {
 template <int R, int MODE>
 __device__ __forceinline__ bool run_fast(const Ctx& c, int fast, uint32_t w0, uint32_t w1, uint32_t& vmask, int (&grp)[R],
                                          uint64_t out_pos) {
-  constexpr bool AGG = MODE == MODE_DENSE || MODE == MODE_HASH || MODE == MODE_RUNS;
+  constexpr bool AGG = MODE == MODE_DENSE || MODE == MODE_HASH || MODE == MODE_RUNS;  // (MODE_BUILD takes its GROUP through the generic path)
   switch (fast) {
 #define ARITH_CASE(OPI, AK, BK, DK)                                                      \
   case MSC_FAST_ARITH + (((OPI) * 5 + (AK)) * 5 + (BK)) * 3 + (DK):                      \
@@ -895,7 +946,7 @@ __device__ __forceinline__ bool run_fast(const Ctx& c, int fast, uint32_t w0, ui
 #undef CMP_CASE
 #define GROUP_CASE(UNUSED, FK)                                    \
   case MSC_FAST_GROUP + (FK):                                     \
-    if constexpr (AGG && group_valid(FK)) {                       \
+    if constexpr ((AGG || MODE == MODE_BUILD) && group_valid(FK)) { \
       fast_group<R, MODE, FK>(c, w1, vmask, grp);                 \
       return true;                                                \
     } else {                                                      \

@@ -68,8 +68,15 @@ class ExecutionEngine(AbstractContextManager, ABC):
     def sql(self, query: str) -> "DataFrame":
         from .parser import parse_sql  # noqa: PLC0415
 
-        df = parse_sql(query)
-        df.engine = self
+        # the same text parses to the same (immutable-style) DataFrame: keep it, and with it the fingerprint the engine's plan
+        # cache leaves on its task tree -- a repeated engine.sql(text).collect() skips parsing and fingerprinting
+        cache = self.__dict__.setdefault("_sql_cache", {})
+        df = cache.get(query)
+        if df is None:
+            df = parse_sql(query)
+            df.engine = self
+            if len(cache) < 256:
+                cache[query] = df
         return df
 
 
@@ -564,6 +571,7 @@ class CudaExecutionEngine(ExecutionEngine):
         # materialising both sides and the pair list
         self.fused_probe = os.environ.get("MINISPARK_FUSED_PROBE", "1") != "0"
         self._probe_declined: Optional[DeviceRel] = None
+        self.fused_build = os.environ.get("MINISPARK_FUSED_BUILD", "0") != "0"
         self._trace_track: Optional[int] = None
         self._dense_merges: dict[tuple, "_DenseMerge"] = {}
         # jit="auto": a task tree that comes back is worth kernels compiled for exactly its scans (0.1-0.3 s each, once per
@@ -1098,6 +1106,10 @@ class CudaExecutionEngine(ExecutionEngine):
             return None
         nl = len(join.left.schema)
         left_needed = sorted(i for i in needed if i < nl)
+        fused = self._fused_build(join, left_needed) if self.fused_build else None
+        if fused is not None:
+            trel, left_columns, key_dict, keep_left = fused
+            return self._probe_over(join, exprs, rsel, left_columns, trel, True, key_dict, keep_left, False, scanned_build=True)
         lrel = self._join_side(join.left, left_needed, join.left_key, None)
         key_dict = lrel.cols[-1].dict  # (a STR key is joined on its code in this dictionary)
         broadcast = False
@@ -1120,6 +1132,16 @@ class CudaExecutionEngine(ExecutionEngine):
             if not broadcast:
                 self._probe_declined = lrel  # (the materialising join reuses the build side it already has)
             return None
+        left_columns = {}
+        for pos, i in enumerate(left_needed):
+            c = lrel.cols[pos]
+            left_columns[_PROBE_BASE + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via="probe")
+        return self._probe_over(join, exprs, rsel, left_columns, trel, slot_bytes.value == 8, key_dict, [lrel], broadcast)
+
+    def _probe_over(self, join: L.LJoin, exprs: list[L.Expr], rsel: L.LSelect, left_columns: dict[int, DeviceColumn], trel: DeviceRel,
+                    compact: bool, key_dict: Optional[DictHandle], keep_left: list, broadcast: bool, scanned_build: bool = False) -> tuple[_Source, list[L.Expr]]:
+        """The consuming scan's source for a join whose table is built: the probe side's base rows, its own filters, the probe
+        and the build side's columns behind it."""
         inputs: list[L.Expr] = [L.EInput(_LTYPE_OF[t], _PROBE_BASE + i) for i, (_, t) in enumerate(join.left.schema)] + list(rsel.outputs)
         new_exprs = [L.substitute(e, inputs) for e in exprs]
         rkey = L.substitute(join.right_key, list(rsel.outputs))
@@ -1132,17 +1154,51 @@ class CudaExecutionEngine(ExecutionEngine):
             rneeded |= {i for i in L.expr_inputs(e) if i < _PROBE_BASE}
         rsource = self._source(rsel.child, rneeded)
         columns = dict(rsource.columns)
-        for pos, i in enumerate(left_needed):
-            c = lrel.cols[pos]
-            columns[_PROBE_BASE + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via="probe")
-        source = _Source(rsource.nrows, columns, rsource.index_vectors, keep=[*rsource.keep, lrel, trel], partitioned=rsource.partitioned)
+        columns.update(left_columns)
+        source = _Source(rsource.nrows, columns, rsource.index_vectors, keep=[*rsource.keep, *keep_left, trel], partitioned=rsource.partitioned)
         source.pre_filters = list(rsel.filters)
         source.probe_key = rkey
         source.probe_table = trel.cols[0].ptr
-        source.probe_compact = slot_bytes.value == 8
+        source.probe_compact = compact
         source.translate_targets = targets
-        self.last_stats["join"] = "lookup fused into the consuming scan (MSC_OP_PROBE)" + (", build side broadcast to every rank" if broadcast else "")
+        self.last_stats["join"] = ("lookup fused into the consuming scan (MSC_OP_PROBE)" + (", build side broadcast to every rank" if broadcast else "")
+                                   + (", table built by one scan over the build side's base rows" if scanned_build else ""))
         return source, new_exprs
+
+    def _fused_build(self, join: L.LJoin, left_needed: list[int]) -> Optional[tuple[DeviceRel, dict[int, DeviceColumn], Optional[DictHandle], list]]:
+        """The join table straight from the build side's BASE rows (msc_scan_join_build): its filters and key in one scan, the
+        rows that pass insert (key, base row number); build-side columns are then read from the base table through the match.
+        For `filters over a table` build sides on one rank; None: use the materialising build (which also handles duplicate
+        and wide keys, computed columns, relations that must travel between ranks)."""
+        left = join.left
+        lsel = left if isinstance(left, L.LSelect) else L.identity_select(left)
+        base = lsel.child
+        if not isinstance(base, L.LTable) or self.comm.world > 1:  # (several ranks: the build side's rows must travel)
+            return None
+        if not all(isinstance(lsel.outputs[i], L.EInput) for i in left_needed):
+            return None
+        key = L.substitute(join.left_key, list(lsel.outputs))
+        if not L._cannot_raise(key) or any(_has_concat(e) for e in [key, *lsel.filters]):
+            return None
+        key_out = L.ECode(L.INT, key) if key.type == L.STR else key
+        need: set[int] = {lsel.outputs[i].index for i in left_needed}
+        for e in [key, *lsel.filters]:
+            need |= L.expr_inputs(e)
+        lsource = self._source(base, need)
+        resolver = _ScanResolver(self, lsource)
+        program, key_dict = L.compile_build(resolver, list(lsel.filters), key_out)
+        desc = resolver.desc(program)
+        table, usable, nkeys = C.c_void_p(), C.c_int32(), C.c_uint64()
+        self.ctx.call("msc_scan_join_build", C.byref(desc), C.byref(table), C.byref(usable), C.byref(nkeys))
+        self._note_kernel("hash join: filter + build in one scan")
+        if not usable.value:
+            return None
+        trel = self._track(DeviceRel.from_handle(self.ctx, table.value, [L.INT], [None]))
+        columns = {}
+        for i in left_needed:
+            c = lsource.columns[lsel.outputs[i].index]
+            columns[_PROBE_BASE + i] = DeviceColumn(c.ptr, c.phys, c.ltype, c.dict, via="probe")
+        return trel, columns, key_dict, list(lsource.keep)
 
     def _join_source(self, join: L.LJoin, needed: set[int]) -> _Source:
         nl = len(join.left.schema)

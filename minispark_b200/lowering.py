@@ -1204,6 +1204,20 @@ def compile_regvm(b: "ProgramBuilder", filters: Sequence[Expr], group: Expr, uni
     return words, text
 
 
+def compile_build(resolver: Resolver, filters: Sequence[Expr], key: Expr) -> tuple[Program, Any]:
+    """The build half of a join as a scan (msc_scan_join_build): the side's filters, RANK, GROUP <- key.  Returns the program
+    and the dictionary of a STR key (joined on its code)."""
+    b = ProgramBuilder(resolver)
+    filters = split_conjunctions(filters)
+    b.plan_cse([*filters, key])
+    for f in filters:
+        b.materialize(f, DST_FILTER)
+    if filters:
+        b.emit("RANK")
+    key_dict = b.materialize(key, DST_GROUP)
+    return b.end(), key_dict
+
+
 @dataclass
 class ProjectProgram:
     program: Program

@@ -201,6 +201,7 @@ _SIGNATURES = {
     "msc_str_concat": (C.c_int, [C.c_void_p, C.POINTER(ConcatPart), C.c_int32, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "msc_hash_join": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "msc_join_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "msc_scan_join_build": (C.c_int, [C.c_void_p, C.POINTER(ScanDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "msc_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]),
     "msc_shuffle_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
     "msc_shuffle_attach": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -18,10 +18,11 @@ JOIN_CASES = ["self_join", "join_string_keys", "join_then_filter_group"]
 JOIN_SQL = [c for c in cases.SQL_CASES if "JOIN" in c[1]]
 
 
-@pytest.fixture(params=[True, False], ids=["fused-probe", "pairs"])
+@pytest.fixture(params=["fused", "fused-materialised-build", "pairs"])
 def engine(request):
     with CudaExecutionEngine() as e:
-        e.fused_probe = request.param
+        e.fused_probe = request.param != "pairs"
+        e.fused_build = request.param == "fused"
         yield e
 
 
@@ -123,3 +124,4 @@ def test_star_schema_joins(engine, star, name):
         assert engine.last_stats["join"].startswith("build / probe"), engine.last_stats["join"]
     if engine.fused_probe and name in ("rows_int_key", "agg_int_key", "str_key", "no_build_columns"):
         assert engine.last_stats["join"].startswith("lookup fused"), engine.last_stats["join"]
+        assert ("one scan over the build side" in engine.last_stats["join"]) == engine.fused_build

@@ -258,7 +258,7 @@ def test_streaming_aggregate_over_sorted_runs_compiles(tmp_path):
     src = buf.value.decode()
     assert rc == 0, src
     assert "msc_jit_runs" in src and "fold_segment<0>" in src and "fold_segment<3>" in src   # SUM_F and MAX_F accumulators
-    assert "p.tile_offsets[tile]" in src and "out_key[run0] = key[r]" in src
+    assert "p.tile_offsets[tile + nw]" in src and "out_key[run0] = key[r]" in src   # (run base fetched one tile ahead)
     compile_source(src)
 
 
