@@ -51,6 +51,13 @@ def main() -> None:
         if args.config == 4:
             return ns.DataFrame(e).table(str(lineitem)).group_by(ns.Col("l_orderkey")).agg(
                 ns.F.sum(ns.Col("l_quantity")).alias("q"), ns.F.avg(ns.Col("l_extendedprice")).alias("p"))
+        if args.config in (6, 7, 8, 9):  # dense / mid-cardinality GROUP BY: 7 groups (dictionary key), 50 (numeric key), 1000, 4000
+            key = {6: ns.Col("l_shipmode"), 7: ns.Col("l_quantity"), 8: (ns.Col("l_orderkey") % 1000).alias("k"),
+                   9: (ns.Col("l_orderkey") % 4000).alias("k")}[args.config]
+            return ns.DataFrame(e).table(str(lineitem)).group_by(key).agg(
+                ns.F.sum(ns.Col("l_quantity")).alias("q"), ns.F.sum(ns.Col("l_extendedprice")).alias("p"),
+                ns.F.sum(ns.Col("l_extendedprice") * (ns.Lit(1) - ns.Col("l_discount"))).alias("dp"), ns.F.avg(ns.Col("l_quantity")).alias("aq"),
+                ns.F.avg(ns.Col("l_extendedprice")).alias("ap"), ns.F.avg(ns.Col("l_discount")).alias("ad"), ns.F.count())
         o = ns.DataFrame(e).table(str(orders)).alias("o")
         l = ns.DataFrame().table(str(lineitem)).alias("l")
         return (o.join(l, on=ns.Col("o.o_orderkey") == ns.Col("l.l_orderkey"), how="inner")
@@ -108,6 +115,9 @@ def main() -> None:
                 print(f"config {args.config} sf{args.sf:g} jit={e.jit}: wall {1e3 * total:.3f} ms, inside library calls {1e3 * in_calls:.3f} ms, "
                       f"python {1e3 * (total - in_calls):.3f} ms, {len(log)} calls")
                 print("  join:", e.last_stats.get("join"), "| exchanges:", e.last_stats.get("exchanges"), "| plan:", e.last_stats.get("plan"))
+                print("  aggregate:", e.last_stats.get("agg_mode"), "scan kind", e.last_stats.get("agg_scan_kind"), "scan ms", e.last_stats.get("agg_scan_ms"), "local slots", e.last_stats.get("hash_local_slots"), "attempts", e.last_stats.get("hash_attempts"),
+                      "| groups out:", rel.nrows if hasattr(rel, "nrows") else None)
+                print("  stats:", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in e.last_stats.items() if k not in ("join", "exchanges", "plan")})
                 for name, at, d in log:
                     print(f"  {1e3 * at:8.3f} ms  +{1e3 * d:7.3f}  {name}")
         N.Context.call, N.Context.check = orig_call, orig_check

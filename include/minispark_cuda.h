@@ -220,6 +220,8 @@ typedef struct msc_stats {
   double last_jit_compile_ms; /* host time of the last NVRTC compilation (or on-disk cache hit) */
   int32_t last_agg_runs;    /* != 0: the last msc_scan_aggregate streamed over the runs of a sorted key, so its result rows
                              * ascend by key (what a range-partitioned shuffle of partial results builds on) */
+  int32_t last_hash_local_slots; /* hash aggregate: slots of the CTA-local pre-aggregation table of the last scan (0: none) */
+  int32_t last_hash_attempts;    /* hash aggregate: scans it took to find a table large enough (1 unless the group count was unknown) */
   int32_t _pad;
 } msc_stats;
 #define MSC_SCAN_KIND_VM 0    /* C++ three-address interpreter (scan_kernel.cuh) */
@@ -290,8 +292,13 @@ MSC_API int msc_rel_wrap(msc_ctx* ctx, uint64_t nrows, const msc_colbind* cols, 
  * (tasks.py:270-310) and the generated Zig consumers (templates/plan.zig:113-253). ----------- */
 /* Dense mode (ngroups > 0): MSC_DST_GROUP receives a group id in [0, ngroups).  Hash mode
  * (ngroups == 0): it receives an arbitrary 64-bit key; `hash_capacity_hint` bounds the distinct keys
- * (0 = nrows).  Output relation: column 0 = group id (U32) or key (I64), columns 1..naggs =
+ * (0 = unknown: the table starts small and the scan is repeated with a larger one when it fills up;
+ * with MSC_HASH_HINT_SOFT set the rest is a guess -- e.g. what the same scan produced last time -- that
+ * sizes the first table but is not relied upon).  Rows first meet a CTA-local table in shared memory
+ * (the reference's per-worker dict, tasks.py:347-375) that is folded into the global one at the end.
+ * Output relation: column 0 = group id (U32) or key (I64), columns 1..naggs =
  * accumulators (I64 / F64), one row per group that received at least one row. */
+#define MSC_HASH_HINT_SOFT 9223372036854775808ull
 MSC_API int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* scan, int32_t ngroups,
                        const int32_t* agg_kinds, int32_t naggs, uint64_t hash_capacity_hint,
                        msc_rel** out);

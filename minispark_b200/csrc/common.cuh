@@ -120,6 +120,11 @@ struct DevTmp {
     return msc_alloc(ctx, n, &p);
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) msc_free(ctx, p, n);
+    p = nullptr;
+    n = 0;
+  }
   ~DevTmp() {
     if (p) msc_free(ctx, p, n);
   }

@@ -183,6 +183,11 @@ struct Gen {
   const long long* init;       // [stride]
   int nstages;
   bool masked;  // SUM_F / COUNT as acc = fma(v, m, acc) with one-hot f64 masks m read from a shared-memory table
+  // Accumulators in shared memory, one private copy per thread ([cell][thread]): a row updates the `stride` cells of ITS group
+  // (load, add, store) instead of every group's register accumulator under a predicate.  Past ~32 cells the register form
+  // issues groups x accumulators FP64 instructions per row and is bound by that pipe, not by HBM (sf10, 7 groups x 6
+  // accumulators: 0.30 ms for 0.78 GB).
+  bool smem_cells = false;
   // fused finish (optional): the final projection over the aggregate's groups, run by the last CTA of the scan
   const msc_scan_desc* fin = nullptr;
   const int32_t* fin_cols = nullptr;  // staged slot of `fin` -> column of the compacted relation (0 = group id, 1 + s = accumulator s)
@@ -286,6 +291,16 @@ struct Gen {
 
   // accumulators are typed: double for the float kinds, i64 otherwise
   void emit_agg(int slot, const std::string& x) {
+    if (smem_cells) {
+      // (cellrow: the row's group, or the trash group NG for rows without one -- straight-line code, no divergence)
+      o << "        { i64* cell = cellrow + " << slot << " * NT; ";
+      if (counted[slot]) o << "*cell += " << count_mul(slot) << ";";
+      else if (kinds[slot] == MSC_AGG_SUM_F) o << "*cell = d2l(l2d(*cell) + l2d(" << x << "));";
+      else if (kinds[slot] == MSC_AGG_SUM_I) o << "*cell += " << x << ";";
+      else o << "*cell = agg_combine<" << kinds[slot] << ">(*cell, " << x << ");";
+      o << " }\n";
+      return;
+    }
     o << "        { const int gsel = valid ? grp : -1;\n";
     for (int g = 0; g < ngroups; ++g) {
       o << "          ";
@@ -696,7 +711,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
     // (a probing scan waits on table reads, not on arithmetic: with few cells a fifth resident CTA hides more of that latency --
     // config 5: 0.573 -> 0.513 ms)
     // registers: 2 per accumulator cell; up to 32 cells fit 4 CTAs of 128 threads per SM (128 registers), more need 3 (168)
-    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << min_ctas(program_probes(sd) && ngroups * stride <= 16 ? 5 : ngroups * stride <= JIT_REG_CELLS_4CTAS ? 4 : 3) << "\n" << kPrelude;
+    o << (program_probes(sd) ? "#define MSC_STREAM_EVICT_FIRST 1\n" : "") << "#define MINCTAS " << min_ctas(program_probes(sd) && ngroups * stride <= 16 ? 5 : (smem_cells || ngroups * stride <= JIT_REG_CELLS_4CTAS) ? 4 : 3) << "\n" << kPrelude;
     if (masked) {  // the masks are fixed at GROUP: a later filter would not reach them
       bool grouped_seen = false;
       for (int pc = 0; pc + 1 < sd->ncode; pc += 2) {
@@ -734,7 +749,16 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   u64* full = reinterpret_cast<u64*>(smem) + warp * 8;
   unsigned char* stages = smem + SMEM_HEADER + warp * (NSTAGES * STAGE_BYTES);
-  i64* red = reinterpret_cast<i64*>(smem + SMEM_HEADER + NW * (NSTAGES * STAGE_BYTES));  // [NW][NG * STRIDE]
+)" << (smem_cells ? R"(  i64* cellbase = reinterpret_cast<i64*>(smem + SMEM_HEADER + NW * (NSTAGES * STAGE_BYTES));  // [(NG + 1) * STRIDE][NT], group NG = trash
+  i64* cells = cellbase + tid;  // this thread's copy of cell c: cells[c * NT] (a warp's 32 copies are 32 consecutive words: no bank conflicts)
+  u32* queue = reinterpret_cast<u32*>(cellbase + (NG + 1) * STRIDE * NT) + warp * (2 * WT);  // (probing scans only: survivors of a tile)
+  if (lane == 0) {
+    for (u32 st = 0; st < NSTAGES; ++st) mbar_init(&full[st], 1);
+    mbar_fence_init();
+  }
+  for (int c = 0; c < (NG + 1) * STRIDE; ++c) cells[c * NT] = INIT[c % STRIDE];
+  __syncthreads();
+)" : R"(  i64* red = reinterpret_cast<i64*>(smem + SMEM_HEADER + NW * (NSTAGES * STAGE_BYTES));  // [NW][NG * STRIDE]
   // one-hot f64 masks: row e = 0 is "no group" (filtered out / past the end / code out of range), row g + 1 selects group g
   double* mlut = reinterpret_cast<double*>(red + NW * NG * STRIDE);  // [NG + 1][NGP]
   u32* queue = reinterpret_cast<u32*>(&mlut[(NG + 1) * NGP]) + warp * (2 * WT);  // (probing scans only: survivors of a tile)
@@ -744,6 +768,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
   }
   for (int i = tid; i < (NG + 1) * NGP; i += NT) mlut[i] = (i / NGP >= 1 && i % NGP == i / NGP - 1) ? 1.0 : 0.0;
   __syncthreads();
+)") << R"(
   const u32 gw = blockIdx.x * NW + warp, nw = gridDim.x * NW;
   const u32 ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
   {
@@ -754,7 +779,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
   const u64 keep_policy = l2_keep_policy();  // (join-table reads ask L2 to keep their lines)
   bool bad = false;
 )";
-    for (int g = 0; g < ngroups; ++g)
+    for (int g = 0; g < ngroups && !smem_cells; ++g)
       for (int s = 0; s < stride; ++s) {
         if (is_float_kind(kinds[s])) o << "  double " << acc(g, s) << " = l2d(INIT[" << s << "]);";
         else o << "  i64 " << acc(g, s) << " = INIT[" << s << "];";
@@ -896,6 +921,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       bool valid = true;
       int grp = -1;
 )";
+      if (smem_cells) o << "      i64* cellrow = cells + NG * (STRIDE * NT);\n";
       if (masked) {
         o << "      double";
         for (int g = 0; g < (ngroups + 1) / 2 * 2; ++g) o << (g ? ", m" : " m") << g << " = 0.0";
@@ -907,6 +933,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     } else {
     o << "#pragma unroll\n    for (int r = 0; r < R; ++r) {\n      bool valid = "
       << (probe_pc >= 0 ? "(vm >> r) & 1u" : (valid_bits ? "(vmask >> r) & 1u" : "true")) << ";\n      int grp = -1;\n";
+    if (smem_cells) o << "      i64* cellrow = cells + NG * (STRIDE * NT);\n";
     if (masked) {
       o << "      double";
       for (int g = 0; g < (ngroups + 1) / 2 * 2; ++g) o << (g ? ", m" : " m") << g << " = 0.0";
@@ -941,9 +968,13 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
       if (tee) o << "        " << temp(tee - 1) << " = x;\n";
       switch (dkind) {
         case MSC_DST_TEMP: o << "        " << temp(dst) << " = x;\n"; break;
-        case MSC_DST_FILTER: o << "        valid = valid && (x != 0);\n"; break;
+        case MSC_DST_FILTER:
+          o << "        valid = valid && (x != 0);\n";
+          if (smem_cells && grouped) o << "        cellrow = cells + ((valid && grp >= 0) ? grp : NG) * (STRIDE * NT);\n";
+          break;
         case MSC_DST_GROUP:
           o << "        grp = (x >= 0 && x < NG) ? (int)x : -1;\n";
+          if (smem_cells) o << "        cellrow = cells + ((valid && grp >= 0) ? grp : NG) * (STRIDE * NT);\n";
           if (masked) {
             o << "        { const double2* mrow = reinterpret_cast<const double2*>(mlut + (valid ? grp + 1 : 0) * NGP);\n";
             for (int g = 0; g < (ngroups + 1) / 2 * 2; g += 2)
@@ -977,7 +1008,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     if (compact_tail) o << "    __syncwarp();  // the queue is rewritten by the next tile\n";
     tail_mode = false;
     // fold the tile's u32 row counts into their i64 accumulators (8 rows per lane and tile: no overflow)
-    for (int g = 0; g < ngroups; ++g)
+    for (int g = 0; g < ngroups && !smem_cells; ++g)
       for (int s = 0; s < stride; ++s)
         if (counted[s] && !masked) o << "    " << acc(g, s) << " += (i64)" << cnt(g, s) << " * " << count_mul(s) << "; " << cnt(g, s) << " = 0;\n";
     o << R"(    __syncwarp();
@@ -989,6 +1020,21 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
   }
   if (bad) atomicOr(p.err, 1);  // MSC_DEVERR_DIV_ZERO
 )";
+    if (smem_cells) {
+      // every thread's copy of a cell, folded by one warp: 4 x 32 consecutive words, a shuffle tree, one atomic per CTA and cell
+      o << R"(  __syncthreads();
+  for (int cell = warp; cell < NG * STRIDE; cell += NW) {
+    const int kind = KIND[cell % STRIDE];
+    const i64* copies = cellbase + cell * NT;
+    i64 v = copies[lane];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) v = agg_combine_k(kind, v, copies[lane + 32 * w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = agg_combine_k(kind, v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0 && v != INIT[cell % STRIDE]) atomic_fold(kind, p.dense_out + cell, v);
+  }
+)";
+    } else {
     if (masked)  // row counts were summed as f64 (exact below 2^53)
       for (int g = 0; g < ngroups; ++g)
         for (int s = 0; s < stride; ++s)
@@ -1007,6 +1053,7 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_dense(const __
     if (v != INIT[cell % STRIDE]) atomic_fold(kind, p.dense_out + cell, v);
   }
 )";
+    }
     if (fin != nullptr && !emit_finish()) return false;
     o << "}\n";
     return true;
@@ -1255,6 +1302,11 @@ int cu_fail(msc_ctx* ctx, const char* what, int rc) {
 int generate(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const int* kinds, const long long* init, int nstages, bool masked,
              std::string* source, std::string* err, const JitFinish* fin = nullptr) {
   Gen g{sd, ngroups, naggs, stride, kinds, init, nstages, masked};
+  g.smem_cells = jit_dense_cells_in_smem(ngroups, stride);
+  if (g.smem_cells && masked) {
+    *err = "the mask-table form keeps its accumulators in registers";
+    return MSC_ERR_ARG;
+  }
   if (fin) {
     g.fin = fin->scan;
     g.fin_cols = fin->cols;
@@ -1273,9 +1325,16 @@ int generate(const msc_scan_desc* sd, int ngroups, int naggs, int stride, const 
 
 }  // namespace
 
+bool jit_dense_cells_in_smem(int ngroups, int stride) {
+  static const int from = getenv("MSC_JIT_SMEM_CELLS_FROM") ? atoi(getenv("MSC_JIT_SMEM_CELLS_FROM")) : JIT_REG_CELLS_4CTAS + 1;
+  return ngroups * stride >= from;
+}
+
 bool jit_dense_supported(const msc_scan_desc* sd, int ngroups, int stride) {
-  // register accumulators: groups x accumulators x 2 registers must leave room for the rows in flight
-  return ngroups >= 1 && ngroups * stride <= JIT_MAX_REG_CELLS && sd->nstaged >= 1 && sd->nstaged <= 24;
+  // register accumulators: groups x accumulators x 2 registers must leave room for the rows in flight; shared-memory cells: a
+  // private copy per thread, 1 KB per cell and CTA
+  const int most = jit_dense_cells_in_smem(ngroups, stride) ? JIT_MAX_SMEM_CELLS : JIT_MAX_REG_CELLS;
+  return ngroups >= 1 && ngroups * stride <= most && sd->nstaged >= 1 && sd->nstaged <= 24;
 }
 
 // masked: try the mask-table variant first, fall back to the exact one when the program does not allow it
@@ -1434,8 +1493,10 @@ int jit_dense_launch(msc_ctx* ctx, const msc_scan_desc* sd, int ngroups, int nag
     if (generate_either(sd, ngroups, naggs, stride, kinds, init, masked, &source, &why, fin) != MSC_OK)
       return ctx->fail(MSC_ERR_ARG, "jit: " + why);
     const Layout lay = stage_layout(sd);
-    const size_t smem = 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes + static_cast<size_t>(NW) * ngroups * stride * 8 +
-                        static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8 + (program_probes(sd) ? static_cast<size_t>(NW) * 2 * 256 * 4 : 0);
+    const size_t acc_bytes = jit_dense_cells_in_smem(ngroups, stride)
+                                 ? static_cast<size_t>(ngroups + 1) * stride * NT * 8
+                                 : static_cast<size_t>(NW) * ngroups * stride * 8 + static_cast<size_t>(ngroups + 1) * ((ngroups + 1) / 2 * 2) * 8;
+    const size_t smem = 4 * 8 * 8 + static_cast<size_t>(NW) * 2 * lay.stage_bytes + acc_bytes + (program_probes(sd) ? static_cast<size_t>(NW) * 2 * 256 * 4 : 0);
     Kernel* k = nullptr;
     MSC_TRY(load_kernel(ctx, source, "msc_jit_dense", smem, &k));
     sit = shapes().emplace(skey, ShapeEntry{k, *masked}).first;

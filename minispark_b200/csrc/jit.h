@@ -9,6 +9,7 @@ namespace mscan {
 
 constexpr int JIT_MAX_REG_CELLS = 56;    // groups x accumulators kept in registers by the specialised kernel
 constexpr int JIT_REG_CELLS_4CTAS = 32;  // up to here 128 registers per thread suffice (4 CTAs per SM), beyond: 168 (3 CTAs)
+constexpr int JIT_MAX_SMEM_CELLS = 96;   // groups x accumulators of the form that keeps them in shared memory, a copy per thread (1 KB per cell and CTA)
 constexpr int JIT_MIN_CTAS = 4;        // __launch_bounds__(128, 4): at most 128 registers per thread
 
 // Optional fused finish of a dense aggregate scan: the last CTA compacts the groups and runs the final projection
@@ -28,6 +29,7 @@ struct JitFinish {
 
 // can this scan run on a specialised kernel at all (cheap checks; the generator may still refuse a program)?
 bool jit_dense_supported(const msc_scan_desc* sd, int ngroups, int stride);
+bool jit_dense_cells_in_smem(int ngroups, int stride);  // which of the two accumulator forms a table of this size gets
 // CUDA C++ source of the specialised kernel (no device needed)
 // masked: SUM_F / COUNT by fma with one-hot f64 masks (1 instruction per group and aggregate instead of 3; a non-finite
 // input leaks into the other groups as NaN, so the caller must check the sums and rerun unmasked -- as for the masked

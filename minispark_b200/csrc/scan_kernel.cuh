@@ -67,6 +67,16 @@ struct ScanParams {
   unsigned long long* htbl;
   uint32_t hshift;
   uint64_t hcap;  // slots, a power of two
+  // CTA-local pre-aggregation in front of htbl (the north_star's "smem pre-aggregation"): lcap slots (a power of two, 0 = off)
+  // of [key] then [naggs accumulators] in shared memory.  A row whose key finds a local slot costs shared-memory atomics
+  // only; a key the local table has no room for goes to htbl directly; the CTA folds its slots into htbl when it is done.
+  // Few groups make every global accumulator a hot spot (50 groups x 7 sums at sf10: 18 ms of same-address atomics).
+  uint32_t lcap;
+  uint32_t _pad1;
+  // optimistic sizing: [0] counts the keys inserted into htbl, [1] != 0 once there are more than hlimit of them -- the
+  // scan then stops early and the host repeats it with a larger table (nullptr: htbl is large enough for any input)
+  unsigned long long* hstate;
+  unsigned long long hlimit;
   // count / project
   uint32_t* tile_counts;
   const uint64_t* tile_offsets;  // nullptr: no filter, output position = row
@@ -94,6 +104,7 @@ template <int R, int MODE>
 int launch_scan(msc_ctx* ctx, LaunchPlan* lp);
 
 constexpr unsigned long long HASH_EMPTY = 0x8000000000000000ULL;
+constexpr int LOCAL_PROBES = 4;  // slots a key may sit away from its home in a CTA-local table
 
 #if defined(__CUDACC__) && !defined(MSCAN_DECL_ONLY)
 // ------------------------------------------------------------------------------------------------
@@ -390,6 +401,47 @@ __device__ __forceinline__ void agg_hash(unsigned long long* htbl, uint32_t hshi
   }
 }
 
+// the same fold on a shared-memory cell (state space spelled out: a generic atomic on a shared address is far slower)
+__device__ __forceinline__ void atomic_fold_shared(int kind, unsigned long long* cell, long long v) {
+  const uint32_t addr = smem_u32(cell);
+  switch (kind) {
+    case MSC_AGG_SUM_F: asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr), "d"(l2d(v)) : "memory"); break;
+    case MSC_AGG_SUM_I: asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); break;
+    case MSC_AGG_MIN_I: asm volatile("red.shared.min.s64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); break;
+    case MSC_AGG_MAX_I: asm volatile("red.shared.max.s64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); break;
+    default: {  // f64 min / max: CAS loop
+      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(cell);
+      while (true) {
+        const long long merged = agg_combine(kind, static_cast<long long>(old), v);
+        if (static_cast<unsigned long long>(merged) == old) break;
+        unsigned long long prev;
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(prev) : "r"(addr), "l"(old), "l"(merged) : "memory");
+        if (prev == old) break;
+        old = prev;
+      }
+    }
+  }
+}
+
+// hash mode behind a CTA-local table: grp >= 0 is a LOCAL slot, grp <= -2 the global slot -2 - grp, -1 no group
+template <int R, int KIND>
+__device__ __forceinline__ void agg_lhash(unsigned long long* lcells, int naggs, unsigned long long* htbl, uint32_t hshift, int a,
+                                          const int (&grp)[R], const long long (&v)[R]) {
+  long long run = v[0];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int nxt = (r + 1 < R) ? r + 1 : r;
+    const bool same_next = (r + 1 < R) && grp[r] != -1 && grp[nxt] == grp[r];
+    if (same_next) {
+      run = agg_combine(KIND, run, v[nxt]);
+    } else {
+      if (grp[r] >= 0) atomic_fold_shared(KIND, lcells + grp[r] * naggs + a, run);
+      else if (grp[r] != -1) atomic_fold(KIND, htbl + 1 + a + (static_cast<uint64_t>(-2 - grp[r]) << hshift), run);
+      run = v[nxt];
+    }
+  }
+}
+
 // exclusive prefix sum of one u32 per lane across the warp; total in *total
 __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, int lane, uint32_t* total) {
   uint32_t inc = v;
@@ -600,13 +652,26 @@ __device__ __forceinline__ void agg_dense_k(const Ctx& c, int slot, const int (&
   }
 }
 
+// local table of a hash scan, at the CTA's accumulator area: keys[lcap], cells[lcap][naggs], then two counters
+__device__ __forceinline__ unsigned long long* local_keys(const Ctx& c) { return reinterpret_cast<unsigned long long*>(c.acc); }
+__device__ __forceinline__ unsigned long long* local_cells(const Ctx& c) { return reinterpret_cast<unsigned long long*>(c.acc) + c.p.lcap; }
+__device__ __forceinline__ uint32_t* local_flags(const Ctx& c) {  // [0] inserts that found no room, [1] != 0: stop trying
+  return reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned long long*>(c.acc) + static_cast<size_t>(c.p.lcap) * (1 + c.p.naggs));
+}
+
+template <int R, int KIND>
+__device__ __forceinline__ void agg_hash_any(const Ctx& c, int a, const int (&grp)[R], const long long (&v)[R]) {
+  if (c.p.lcap) agg_lhash<R, KIND>(local_cells(c), c.p.naggs, c.p.htbl, c.p.hshift, a, grp, v);
+  else agg_hash<R, KIND>(c.p.htbl, c.p.hshift, a, grp, v);
+}
+
 template <int R, int MODE>
 __device__ __forceinline__ void agg_any(const Ctx& c, int slot, int kind, const int (&grp)[R], const long long (&v)[R]) {
   switch (kind) {
 #define AGG_ANY_CASE(KIND)                                                                          \
   case KIND:                                                                                        \
     if constexpr (MODE == MODE_DENSE) agg_dense_k<R, KIND>(c, slot, grp, v);                        \
-    else if constexpr (MODE == MODE_HASH) agg_hash<R, KIND>(c.p.htbl, c.p.hshift, slot, grp, v);     \
+    else if constexpr (MODE == MODE_HASH) agg_hash_any<R, KIND>(c, slot, grp, v);                    \
     else if constexpr (MODE == MODE_RUNS) agg_hash<R, KIND>(static_cast<unsigned long long*>(c.p.out[1 + slot]) - 1, 0, 0, grp, v); \
     break;
     AGG_ANY_CASE(MSC_AGG_SUM_F)
@@ -616,7 +681,7 @@ __device__ __forceinline__ void agg_any(const Ctx& c, int slot, int kind, const 
     AGG_ANY_CASE(MSC_AGG_MIN_I)
     default:
       if constexpr (MODE == MODE_DENSE) agg_dense_k<R, MSC_AGG_MAX_I>(c, slot, grp, v);
-      else if constexpr (MODE == MODE_HASH) agg_hash<R, MSC_AGG_MAX_I>(c.p.htbl, c.p.hshift, slot, grp, v);
+      else if constexpr (MODE == MODE_HASH) agg_hash_any<R, MSC_AGG_MAX_I>(c, slot, grp, v);
       else if constexpr (MODE == MODE_RUNS) agg_hash<R, MSC_AGG_MAX_I>(static_cast<unsigned long long*>(c.p.out[1 + slot]) - 1, 0, 0, grp, v);
       break;
 #undef AGG_ANY_CASE
@@ -648,6 +713,8 @@ __device__ __forceinline__ void set_group(const Ctx& c, const long long (&x)[R],
     uint64_t pos[R];
     bool head[R], pend[R];
     int slot[R];
+    const bool local = c.p.lcap != 0;
+    const bool local_open = local && *reinterpret_cast<volatile uint32_t*>(local_flags(c) + 1) == 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       key[r] = static_cast<unsigned long long>(x[r]);
@@ -656,29 +723,56 @@ __device__ __forceinline__ void set_group(const Ctx& c, const long long (&x)[R],
       const bool prev_valid = r > 0 && ((vmask >> (r > 0 ? r - 1 : 0)) & 1u);
       head[r] = valid && !(prev_valid && key[r] == key[r > 0 ? r - 1 : 0]);
       pend[r] = head[r];
-      pos[r] = msc_mix64(key[r]) & mask;
+      const uint64_t h = msc_mix64(key[r]);
+      pos[r] = h & mask;
       slot[r] = -1;
-    }
-    for (uint64_t step = 0;; ++step) {
-      unsigned long long got[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) got[r] = pend[r] ? atomicCAS(c.p.htbl + (pos[r] << c.p.hshift), HASH_EMPTY, key[r]) : 0ull;
-      bool more = false;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!pend[r]) continue;
-        if (got[r] == HASH_EMPTY || got[r] == key[r]) {
-          slot[r] = static_cast<int>(pos[r]);
-          pend[r] = false;
-        } else {
-          pos[r] = (pos[r] + 1) & mask;
-          more = true;
+      if (local_open && head[r]) {
+        // the CTA's own table first: a read finds a key that is already there, one CAS claims an empty slot
+        unsigned long long* lkeys = local_keys(c);
+        const uint32_t lmask = c.p.lcap - 1;
+        uint32_t lp = static_cast<uint32_t>(h >> 32) & lmask;
+        for (int step = 0; step < LOCAL_PROBES; ++step, lp = (lp + 1) & lmask) {
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(lkeys + lp);
+          if (cur == HASH_EMPTY) asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(cur) : "r"(smem_u32(lkeys + lp)), "l"(HASH_EMPTY), "l"(key[r]) : "memory");
+          if (cur == HASH_EMPTY || cur == key[r]) {
+            slot[r] = static_cast<int>(lp);
+            pend[r] = false;
+            break;
+          }
         }
+        // no room near its home slot: this row goes to the global table; a CTA that keeps failing stops trying (more groups
+        // than local slots: the local probes would only cost time)
+        if (pend[r] && atomicAdd(local_flags(c), 1u) > 4u * c.p.lcap) *reinterpret_cast<volatile uint32_t*>(local_flags(c) + 1) = 1u;
       }
-      if (!more) break;
-      if (step >= c.p.hcap) {  // every slot belongs to another key
-        atomicOr(c.p.err, MSC_DEVERR_TABLE_FULL);
-        break;
+    }
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) any |= pend[r];
+    if (any) {
+      for (uint64_t step = 0;; ++step) {
+        unsigned long long got[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) got[r] = pend[r] ? atomicCAS(c.p.htbl + (pos[r] << c.p.hshift), HASH_EMPTY, key[r]) : 0ull;
+        bool more = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (!pend[r]) continue;
+          if (got[r] == HASH_EMPTY || got[r] == key[r]) {
+            slot[r] = local ? -2 - static_cast<int>(pos[r]) : static_cast<int>(pos[r]);
+            pend[r] = false;
+            if (got[r] == HASH_EMPTY && c.p.hstate != nullptr && atomicAdd(c.p.hstate, 1ull) >= c.p.hlimit)
+              *reinterpret_cast<volatile unsigned long long*>(c.p.hstate + 1) = 1ull;  // more groups than this table was sized for
+          } else {
+            pos[r] = (pos[r] + 1) & mask;
+            more = true;
+          }
+        }
+        if (!more) break;
+        if (step >= 32 && c.p.hstate != nullptr && *reinterpret_cast<volatile unsigned long long*>(c.p.hstate + 1) != 0) break;  // (the scan is being abandoned)
+        if (step >= c.p.hcap) {  // every slot belongs to another key
+          atomicOr(c.p.err, MSC_DEVERR_TABLE_FULL);
+          break;
+        }
       }
     }
     int prev_slot = -1;
@@ -817,7 +911,7 @@ __device__ __forceinline__ void ffetch(const Ctx& c, int idx, long long (&v)[R])
 template <int R, int MODE, int KIND>
 __device__ __forceinline__ void fast_agg(const Ctx& c, int slot, const int (&grp)[R], const long long (&v)[R]) {
   if constexpr (MODE == MODE_DENSE) agg_dense_k<R, KIND>(c, slot, grp, v);
-  else if constexpr (MODE == MODE_HASH) agg_hash<R, KIND>(c.p.htbl, c.p.hshift, slot, grp, v);
+  else if constexpr (MODE == MODE_HASH) agg_hash_any<R, KIND>(c, slot, grp, v);
   // a run's accumulator is element [run] of its output column: agg_hash with one-word slots and no key word
   else if constexpr (MODE == MODE_RUNS) agg_hash<R, KIND>(static_cast<unsigned long long*>(c.p.out[1 + slot]) - 1, 0, 0, grp, v);
 }
@@ -1014,11 +1108,19 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     const int cells = (p.ngroups + 1) * p.naggs;
     for (int c = 0; c < cells; ++c) acc[c * NT + tid] = p.agg_init[c % p.naggs];
   }
+  if constexpr (MODE == MODE_HASH) {
+    if (p.lcap) {
+      unsigned long long* lkeys = reinterpret_cast<unsigned long long*>(acc);
+      for (uint32_t i = tid; i < p.lcap; i += NT) lkeys[i] = HASH_EMPTY;
+      for (uint32_t i = tid; i < p.lcap * p.naggs; i += NT) lkeys[p.lcap + i] = static_cast<unsigned long long>(p.agg_init[i % p.naggs]);
+      if (tid < 2) reinterpret_cast<uint32_t*>(lkeys + static_cast<size_t>(p.lcap) * (1 + p.naggs))[tid] = 0;
+    }
+  }
   __syncthreads();
 
   const uint32_t gw = blockIdx.x * NW + warp;  // global warp id
   const uint32_t nw = gridDim.x * NW;
-  const uint32_t ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
+  uint32_t ntiles_w = (p.ntiles > gw) ? (p.ntiles - gw + nw - 1) / nw : 0;
   {
     const uint32_t pre = ntiles_w < p.nstages ? ntiles_w : p.nstages;
     for (uint32_t k = 0; k < pre; ++k) issue_tile(p, stages, full, k, gw + static_cast<uint64_t>(k) * nw, lane);
@@ -1030,6 +1132,10 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     const uint64_t tile = gw + static_cast<uint64_t>(k) * nw;
     const unsigned char* sbase = stages + static_cast<size_t>(stage) * p.stage_bytes;
     while (!mbar_try_wait(&full[stage], parity)) {
+    }
+    if constexpr (MODE == MODE_HASH) {
+      // the table turned out too small for this input: take what is already on its way into shared memory and leave
+      if (p.hstate != nullptr && *reinterpret_cast<volatile unsigned long long*>(p.hstate + 1) != 0 && ntiles_w > k + p.nstages) ntiles_w = k + p.nstages;
     }
     const uint64_t row0 = tile * WT + static_cast<uint64_t>(lane) * R;
     uint32_t vmask = row_mask<R>(row0, nrows);
@@ -1104,6 +1210,40 @@ __global__ void __launch_bounds__(NT) scan_kernel(const __grid_constant__ ScanPa
     }
   }
 
+  if constexpr (MODE == MODE_HASH) {
+    if (p.lcap) {
+      // fold the CTA's table into the global one: a key costs one find-or-insert and one atomic per accumulator that moved
+      __syncthreads();
+      const unsigned long long* lkeys = reinterpret_cast<const unsigned long long*>(acc);
+      const unsigned long long* lcells = lkeys + p.lcap;
+      const bool abandoned = p.hstate != nullptr && *reinterpret_cast<volatile unsigned long long*>(p.hstate + 1) != 0;
+      const uint64_t mask = p.hcap - 1;
+      for (uint32_t s = tid; s < p.lcap && !abandoned; s += NT) {
+        const unsigned long long key = lkeys[s];
+        if (key == HASH_EMPTY) continue;
+        uint64_t pos = msc_mix64(key) & mask;
+        bool placed = false;
+        for (uint64_t step = 0; step <= p.hcap; ++step, pos = (pos + 1) & mask) {
+          const unsigned long long got = atomicCAS(p.htbl + (pos << p.hshift), HASH_EMPTY, key);
+          if (got == HASH_EMPTY || got == key) {
+            placed = true;
+            if (got == HASH_EMPTY && p.hstate != nullptr && atomicAdd(p.hstate, 1ull) >= p.hlimit)
+              *reinterpret_cast<volatile unsigned long long*>(p.hstate + 1) = 1ull;
+            break;
+          }
+          if (step >= 32 && p.hstate != nullptr && *reinterpret_cast<volatile unsigned long long*>(p.hstate + 1) != 0) break;
+        }
+        if (!placed) {
+          if (p.hstate == nullptr) atomicOr(p.err, MSC_DEVERR_TABLE_FULL);
+          continue;
+        }
+        for (int a = 0; a < p.naggs; ++a) {
+          const long long v = static_cast<long long>(lcells[static_cast<size_t>(s) * p.naggs + a]);
+          if (v != p.agg_init[a]) atomic_fold(p.agg_kind[a], p.htbl + (pos << p.hshift) + 1 + a, v);
+        }
+      }
+    }
+  }
   if constexpr (MODE == MODE_DENSE) {
     __syncthreads();
     const int cells = p.ngroups * p.naggs;  // the trash group is not exported

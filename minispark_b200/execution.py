@@ -1035,11 +1035,18 @@ class CudaExecutionEngine(ExecutionEngine):
             raw = self._track(DeviceRel.from_handle(self.ctx, handle, [group.type, *slot_types], [merge.global_dict] + [None] * len(slot_types)))
         else:
             out = C.c_void_p()
+            if not ngroups and prog.group_dict is None and agg.groups_seen:
+                hint = agg.groups_seen | N.K["MSC_HASH_HINT_SOFT"]  # no dictionary bounds the groups, but this plan has run before
             self.ctx.call("msc_scan_aggregate", C.byref(desc), ngroups, kinds, len(prog.agg_kinds), hint, C.byref(out))
             self._note_kernel("scan: filter + aggregate")
             self.last_stats["agg_scan_kind"] = self.last_stats["scan_kind"]  # later scans (final projection) overwrite scan_kind
+            if not ngroups:
+                st = self.ctx.stats()
+                self.last_stats["hash_local_slots"], self.last_stats["hash_attempts"] = st.last_hash_local_slots, st.last_hash_attempts
             self.last_stats["agg_scan_ms"] = self.last_stats["scan_ms"]
             raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
+            if not ngroups:
+                agg.groups_seen = raw.nrows
             if spread:  # merge the per-rank partial tables (reference: shuffle + final aggregate, plan.py:190-199)
                 raw = self._merge_partials(raw, prog.agg_kinds, slot_types, group.type)
                 partitioned = raw.partitioned

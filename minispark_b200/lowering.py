@@ -318,6 +318,7 @@ class LAggregate(LNode):
     child: LNode = None  # type: ignore[assignment]
     group: Expr = None  # type: ignore[assignment]
     aggs: list[tuple[str, Expr]] = field(default_factory=list)
+    groups_seen: int = field(default=0, compare=False)  # groups this node produced the last time it ran (a cached plan sizes its next hash table with it)
 
     def describe(self, indent: int = 0) -> str:
         pad = " " * indent

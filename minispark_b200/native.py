@@ -91,6 +91,8 @@ class Stats(C.Structure):
         ("jit_compiles", C.c_uint64),
         ("last_jit_compile_ms", C.c_double),
         ("last_agg_runs", C.c_int32),
+        ("last_hash_local_slots", C.c_int32),
+        ("last_hash_attempts", C.c_int32),
         ("_pad", C.c_int32),
     ]
 

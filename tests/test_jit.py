@@ -91,6 +91,24 @@ def test_exact_variant_has_no_mask_arithmetic(tmp_path):
     compile_source(src)
 
 
+def test_more_than_32_cells_keep_their_accumulators_in_shared_memory(tmp_path):
+    """8 groups x 6 accumulators: every thread owns a copy of each cell in shared memory and a row updates its own group's
+    cells only -- no per-group predicated FP64 instruction stream (HBM- not FP64-bound)."""
+    src = q1_source(tmp_path, ngroups=8)
+    assert "constexpr int NG = 8" in src and "cellbase" in src and "cellrow + 0 * NT" in src
+    assert "a0_0" not in src and "mlut" not in src and "addf_if<" not in src.split("msc_jit_dense")[1]
+    cubin = compile_source(src)
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    path = tmp_path / "q1_smem.cubin"
+    path.write_bytes(cubin)
+    sass = subprocess.run([cuobjdump, "-sass", str(path)], capture_output=True, text=True, check=True).stdout
+    loop = sass[sass.index("TRYWAIT"):sass.index("UBLKCP", sass.index("TRYWAIT"))]
+    assert loop.count("DADD") + loop.count("DFMA") <= 8 * 5 * 2   # per row one add per SUM (and the expression arithmetic), not one per group
+    assert "STS" in loop and "LDS" in loop
+
+
 def test_generator_refuses_too_many_cells(tmp_path):
     prog, res = _compile_q1(tmp_path)
     lib = N.load()
