@@ -595,7 +595,7 @@ def python_engine_baseline() -> dict:
 
 
 def run_extras(args: argparse.Namespace, rank: int, world: int, local_rank: int, tools: dict) -> dict:
-    """extra.q1_sharded / extra.highcard / extra.join: every rank runs them (collective); rank 0's dict is printed."""
+    """extra.q1_sharded / extra.highcard / extra.midcard / extra.join: every rank runs them (collective); rank 0's dict is printed."""
     import gen_tpch
     from minispark_b200 import CudaExecutionEngine
 
@@ -604,7 +604,7 @@ def run_extras(args: argparse.Namespace, rank: int, world: int, local_rank: int,
     engine = CudaExecutionEngine(device=local_rank, layout=args.layout)
     try:
         assert engine.shard == (rank, world)
-        for name, fn in (("q1_sharded", extra_q1_sharded), ("highcard", extra_highcard), ("join", extra_join)):
+        for name, fn in (("q1_sharded", extra_q1_sharded), ("highcard", extra_highcard), ("midcard", extra_midcard), ("join", extra_join)):
             t0 = time.perf_counter()
             try:
                 res = fn(args, engine, rank, world, tools)
@@ -747,6 +747,61 @@ def extra_highcard(args, engine, rank: int, world: int, tools: dict) -> dict:  #
             "exchange_gbs": (sent / exch_s / 1e9) if exch_s > 0 else None, "result_partitioned": bool(stats.get("result_partitioned")),
             "timing": "wall clock around execute_to_device (one-shot: lowering + all launches + host waits), device idle on both sides, max over ranks, median of the passes",
             "parity_check": parity}
+
+
+def extra_midcard(args, engine, rank: int, world: int, tools: dict) -> dict:  # noqa: ANN001
+    """GROUP BY with few groups and seven aggregates (six accumulators) on the config-4 lineitem: by l_shipmode (7 groups, a
+    dictionary key: dense table, 49 cells -> the specialised kernel's shared-memory cell form) and by l_quantity (50 groups, a
+    FLOAT key: hash aggregate behind CTA-local tables)."""
+    import numpy as np
+
+    import cases
+    from oracle import ports
+
+    ns = cases.namespace()
+    sf = args.cfg_sf
+    lineitem = ensure_shared_table(f"lineitem_cfg_sf{sf:g}.bin", rank, tools["barrier"], table="lineitem", sf=sf,
+                                   columns=["l_orderkey", "l_quantity", "l_extendedprice", "l_shipmode"])
+    peak, _ = peaks()
+    out: dict = {"sf": sf}
+    for key in ("l_shipmode", "l_quantity"):
+        task = cases.midcard_frame(ns, lineitem, key, engine).task
+        reps = max(min(args.steps, 9), 5)
+        sec, passes, stats, _ = _time_one_shot(engine, task, reps, tools)
+        local_rows = engine._tables[str(lineitem)].nrows
+        total_rows = int(tools["sum_over_ranks"](float(local_rows)))
+        bytes_per_row = _column_bytes(engine, lineitem, [key, "l_quantity", "l_extendedprice"] if key != "l_quantity" else ["l_quantity", "l_extendedprice"])
+        # (a one-shot hash aggregate is followed by its final projection, whose launch overwrites kernel_ms: take the aggregate scan's own time)
+        kernel_ms = tools["max_over_ranks"](float((stats.get("agg_scan_ms") if stats.get("agg_mode") == "hash" else stats.get("kernel_ms")) or 0.0))
+        rel, schema = engine.execute_to_device(task, replicate=True)
+        names = [n for n, _ in schema]
+        cols = {n: rel.column_numpy(i) for i, n in enumerate(names)}
+        keys = [rel.cols[0].dict.export()[c] for c in cols[key].tolist()] if key == "l_shipmode" else [float(v) for v in cols[key].tolist()]
+        engine.release_query()
+        parity = "not checked on this rank"
+        if rank == 0:
+            want = ports.groupby(lineitem, key)
+            ref = {g["key"]: g for g in want["groups"]}
+            assert want["rows"] == total_rows and sorted(keys) == sorted(ref), (want["rows"], total_rows, len(keys), len(ref))
+            for i, k in enumerate(keys):
+                g = ref[k]
+                assert int(cols["n"][i]) == g["count"] and float(cols["min_p"][i]) == g["min_p"] and float(cols["max_p"][i]) == g["max_p"], (key, k)
+                for name in ("sum_q", "sum_p", "sum_pq"):
+                    assert abs(float(cols[name][i]) - g[name]) <= 1e-9 * abs(g[name]), (key, k, name, float(cols[name][i]), g[name])
+                assert abs(float(cols["avg_p"][i]) - g["sum_p"] / g["count"]) <= 1e-9 * abs(g["sum_p"] / g["count"]), (key, k)
+            parity = f"ok: {len(keys)} groups vs oracle/cfg_port.c (f64) over the whole file: COUNT / MIN / MAX exact, SUM and AVG within 1e-9"
+        gbs = total_rows * bytes_per_row / sec / 1e9
+        out[key] = {"workload": f"GROUP BY {key}: COUNT, SUM x3, MIN, MAX, AVG on ONE lineitem sf{sf:g} ({total_rows} rows), engine sharding",
+                    "rows": total_rows, "groups": len(keys), "ms": 1e3 * sec, "passes_ms": [round(1e3 * t, 3) for t in passes], "rows_per_s": total_rows / sec,
+                    "bytes_per_row_scanned": bytes_per_row, "algorithmic_bytes": total_rows * bytes_per_row,
+                    "scanned_gbs_all_gpus": gbs, "frac_of_peak_all_gpus": gbs / (peak * world),
+                    "kernel_ms": kernel_ms, "kernel_frac_of_peak_all_gpus": (total_rows * bytes_per_row / (kernel_ms * 1e-3) / 1e9 / (peak * world)) if kernel_ms else None,
+                    "agg_mode": stats.get("agg_mode"), "scan_kind": stats.get("scan_kind"), "scan_smem": stats.get("scan_smem"),
+                    "hash_local_slots": stats.get("hash_local_slots") if stats.get("agg_mode") == "hash" else None,
+                    "plan": stats.get("plan"), "parity_check": parity}
+    out["timing"] = ("ms: wall clock around execute_to_device, device idle on both sides, max over ranks, median of the passes; kernel_ms: CUDA events around "
+                     "the aggregate scan of the last pass (msc_stats.last_kernel_ms / last_scan_ms), max over ranks")
+    return out
 
 
 def extra_join(args, engine, rank: int, world: int, tools: dict) -> dict:  # noqa: ANN001

@@ -18,6 +18,12 @@ for f in sys.argv[1:]:
         if "error" in v:
             print(f"   {k}: ERROR {v['error'][:300]}")
             continue
+        if k == "midcard":
+            for kk, vv in v.items():
+                if isinstance(vv, dict):
+                    print(f"   midcard {kk}: {vv['ms']:.4f} ms, kernel {vv['kernel_ms']:.4f} ms (frac {vv['kernel_frac_of_peak_all_gpus']:.3f}), {vv['groups']} groups, "
+                          f"{vv['agg_mode']} kind {vv['scan_kind']} local slots {vv['hash_local_slots']} | {vv['parity_check'][:50]}")
+            continue
         ms = v.get("ms", v.get("ms_per_step"))
         frac = v.get("frac_of_peak_all_gpus")
         print(f"   {k}: {ms:.4f} ms" + (f", frac {frac:.3f}" if frac is not None else "") + f", exchange {v.get('exchange')}, wall {v.get('bench_wall_s')} s"

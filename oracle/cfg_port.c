@@ -21,6 +21,8 @@
  *          out.bin = u64 n, then n x i64 key (ascending), n x f64 sum(l_quantity), n x f64 sum(l_extendedprice), n x i64 count
  *        cfg_port join <orders.bin> <lineitem.bin> <lo_us> <hi_us> <needle>
  *          prints one JSON object: {"pairs": joined rows before the filters, "groups": [{"key", "count", "sum"}]}
+ *        cfg_port groupby <lineitem.bin> <key column>
+ *          prints one JSON object: {"rows", "groups": [{"key", "count", "sum_q", "sum_p", "sum_pq", "min_p", "max_p"}]} (keys ascending by bytes)
  */
 #define _GNU_SOURCE
 #include <fcntl.h>
@@ -326,9 +328,112 @@ static int run_join(const char* orders_path, const char* lineitem_path, int64_t 
   return 0;
 }
 
+/* ---- a GROUP BY with few groups (bench.py extra.midcard) ------------------------------------------------------------------
+ * SELECT key, COUNT(), SUM(l_quantity), SUM(l_extendedprice), SUM(l_extendedprice * l_quantity), MIN(l_extendedprice),
+ *        MAX(l_extendedprice) FROM lineitem GROUP BY key        -- key: a STRING, FLOAT or INTEGER column
+ * Same stages as highcard above (tasks.py:270-310, 347-375): values widen from the file's f32 to f64 (io.py:91-94), every
+ * accumulator is f64 / i64, groups are keyed by the value itself. */
+typedef struct {
+  uint8_t key[256];
+  int len; /* -1 = empty slot */
+  long long count;
+  double sum_q, sum_p, sum_pq, min_p, max_p;
+} gcell_t;
+
+static int cmp_gcell(const void* a, const void* b) {
+  const gcell_t *x = a, *y = b;
+  const int n = x->len < y->len ? x->len : y->len;
+  const int c = memcmp(x->key, y->key, n);
+  return c ? c : x->len - y->len;
+}
+
+static int run_groupby(const char* path, const char* keyname) {
+  const double t0 = now_s();
+  file_t f;
+  open_file(&f, path);
+  const int kc = col_index(&f, keyname), qc = col_index(&f, "l_quantity"), pc = col_index(&f, "l_extendedprice");
+  const int ktype = f.types[kc];
+  const uint64_t cap = 1u << 16;
+  gcell_t* cells = malloc(cap * sizeof(gcell_t));
+  if (!cells) die("out of memory");
+  for (uint64_t i = 0; i < cap; ++i) cells[i].len = -1;
+  uint64_t used = 0, rows = 0;
+  for (uint32_t b = 0; b < f.nblocks; ++b) {
+    block_t blk;
+    read_block(&f, b, &blk);
+    const float* q = (const float*)blk.payload[qc];
+    const float* price = (const float*)blk.payload[pc];
+    const uint8_t* lens = blk.payload[kc];
+    const uint8_t* bytes = lens + blk.rows;
+    rows += blk.rows;
+    for (uint32_t r = 0; r < blk.rows; ++r) {
+      const uint8_t* k;
+      int klen;
+      if (ktype == T_STR) {
+        k = bytes;
+        klen = lens[r];
+        bytes += klen;
+      } else {
+        klen = ktype == T_TS ? 8 : 4;
+        k = blk.payload[kc] + (size_t)klen * r;
+      }
+      uint64_t h = 1469598103934665603ULL;
+      for (int i = 0; i < klen; ++i) h = (h ^ k[i]) * 1099511628211ULL;
+      uint64_t pos = mix64(h) & (cap - 1);
+      while (cells[pos].len >= 0 && !(cells[pos].len == klen && memcmp(cells[pos].key, k, klen) == 0)) pos = (pos + 1) & (cap - 1);
+      gcell_t* c = &cells[pos];
+      if (c->len < 0) {
+        if (++used > cap / 2) die("groupby: more than 32768 groups");
+        memcpy(c->key, k, klen);
+        c->len = klen;
+        c->count = 0;
+        c->sum_q = c->sum_p = c->sum_pq = 0.0;
+        c->min_p = 1.0 / 0.0;
+        c->max_p = -1.0 / 0.0;
+      }
+      const double qq = (double)q[r], pp = (double)price[r];
+      c->count += 1;
+      c->sum_q += qq;
+      c->sum_p += pp;
+      c->sum_pq += pp * qq;
+      if (pp < c->min_p) c->min_p = pp;
+      if (pp > c->max_p) c->max_p = pp;
+    }
+  }
+  uint64_t n = 0;
+  for (uint64_t i = 0; i < cap; ++i)
+    if (cells[i].len >= 0) cells[n++] = cells[i];
+  qsort(cells, n, sizeof(gcell_t), cmp_gcell);
+  printf("{\"rows\": %llu, \"seconds\": %.6f, \"groups\": [", (unsigned long long)rows, now_s() - t0);
+  for (uint64_t i = 0; i < n; ++i) {
+    const gcell_t* c = &cells[i];
+    printf("%s{\"key\": ", i ? ", " : "");
+    if (ktype == T_STR) {
+      printf("\"%.*s\"", c->len, (const char*)c->key);
+    } else if (ktype == T_FLOAT) {
+      float v;
+      memcpy(&v, c->key, 4);
+      printf("%.17g", (double)v);
+    } else if (ktype == T_TS) {
+      int64_t v;
+      memcpy(&v, c->key, 8);
+      printf("%lld", (long long)v);
+    } else {
+      int32_t v;
+      memcpy(&v, c->key, 4);
+      printf("%d", v);
+    }
+    printf(", \"count\": %lld, \"sum_q\": %.17g, \"sum_p\": %.17g, \"sum_pq\": %.17g, \"min_p\": %.17g, \"max_p\": %.17g}", c->count, c->sum_q, c->sum_p,
+           c->sum_pq, c->min_p, c->max_p);
+  }
+  printf("]}\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && strcmp(argv[1], "groupby") == 0) return run_groupby(argv[2], argv[3]);
   if (argc == 4 && strcmp(argv[1], "highcard") == 0) return run_highcard(argv[2], argv[3]);
   if (argc == 7 && strcmp(argv[1], "join") == 0) return run_join(argv[2], argv[3], atoll(argv[4]), atoll(argv[5]), argv[6]);
-  fprintf(stderr, "usage: %s highcard <lineitem> <out.bin> | join <orders> <lineitem> <lo_us> <hi_us> <needle>\n", argv[0]);
+  fprintf(stderr, "usage: %s highcard <lineitem> <out.bin> | join <orders> <lineitem> <lo_us> <hi_us> <needle> | groupby <lineitem> <key column>\n", argv[0]);
   return 2;
 }

@@ -280,3 +280,12 @@ WHERE
 GROUP BY
     l_returnflag;
 """
+
+
+def midcard_frame(ns, table, key, engine=None):
+    """The query bench.py's extra.midcard runs (7 aggregates over 6 accumulators) -- shared with the bench so that the port
+    is pinned on exactly what it checks there."""
+    p, q = ns.Col("l_extendedprice"), ns.Col("l_quantity")
+    return ns.DataFrame(engine).table(str(table)).group_by(ns.Col(key)).agg(
+        ns.F.count().alias("n"), ns.F.sum(q).alias("sum_q"), ns.F.sum(p).alias("sum_p"), ns.F.sum(p * q).alias("sum_pq"),
+        ns.F.min(p).alias("min_p"), ns.F.max(p).alias("max_p"), ns.F.avg(p).alias("avg_p"))

@@ -104,3 +104,18 @@ def test_join_port_matches_python_oracle(tpch_pair, lo, hi, needle):
         assert abs(g["sum"] - want[g["key"]]["rev"]) <= 1e-12 * abs(g["sum"])
     nlines = O.run_task(ns.DataFrame(None).table(lineitem).group_by(ns.Col("l_shipmode")).agg(ns.F.count().alias("n")).task)
     assert got["pairs"] == sum(r["n"] for r in nlines)  # every lineitem row has exactly one order
+
+
+@pytest.mark.parametrize("key", ["l_shipmode", "l_quantity", "l_orderkey"])
+def test_groupby_port_matches_python_oracle(tpch_pair, key):
+    lineitem, _, _ = tpch_pair
+    ns = cases.namespace()
+    want = {r[key]: r for r in O.run_task(cases.midcard_frame(ns, lineitem, key).task, wire=False)}
+    got = ports.groupby(lineitem, key)
+    assert got["rows"] == sum(r["n"] for r in want.values()) and {g["key"] for g in got["groups"]} == set(want)
+    for g in got["groups"]:
+        ref = want[g["key"]]
+        assert g["count"] == ref["n"] and g["min_p"] == ref["min_p"] and g["max_p"] == ref["max_p"]
+        for name in ("sum_q", "sum_p", "sum_pq"):
+            assert abs(g[name] - ref[name]) <= 1e-12 * abs(ref[name]), (key, g["key"], name)
+        assert abs(g["sum_p"] / g["count"] - ref["avg_p"]) <= 1e-12 * abs(ref["avg_p"])
