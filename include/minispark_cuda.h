@@ -200,7 +200,10 @@ typedef struct msc_scan_desc {
    * 0: use such a kernel only when this process has already compiled it.  msc_scan_project reads it; the dense
    * aggregate entry points take MSC_DENSE_JIT in their flags instead. */
   int32_t want_jit;
-  int32_t _pad2;
+  /* != 0: the staged columns belong to a loaded table and do not change while it is loaded; the library may then keep what it
+   * derives from them (the run index of a GROUP BY key column: run count, sortedness, runs before every tile) for later scans
+   * of the same column.  0 for relations that are rewritten in place (exchange buffers). */
+  int32_t table_columns;
 } msc_scan_desc;
 
 typedef struct msc_stats {
@@ -222,7 +225,7 @@ typedef struct msc_stats {
                              * ascend by key (what a range-partitioned shuffle of partial results builds on) */
   int32_t last_hash_local_slots; /* hash aggregate: slots of the CTA-local pre-aggregation table of the last scan (0: none) */
   int32_t last_hash_attempts;    /* hash aggregate: scans it took to find a table large enough (1 unless the group count was unknown) */
-  int32_t _pad;
+  int32_t last_run_index_hit;    /* != 0: the last hash aggregate found the run index of its key column (a table column seen before) */
 } msc_stats;
 #define MSC_SCAN_KIND_VM 0    /* C++ three-address interpreter (scan_kernel.cuh) */
 #define MSC_SCAN_KIND_REGVM 1 /* register-resident PTX interpreter (scan_regvm_impl.cuh) */

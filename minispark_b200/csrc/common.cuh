@@ -43,6 +43,17 @@ struct msc_ctx {
   // costs 50 ms to > 1 s.  Freed blocks >= kBigBlock wait here, keyed by size; everything is ordered
   // on `stream`, so a cached block may be handed out again immediately.
   static constexpr size_t kBigBlock = 1 << 20;
+  // Run index of a table's key column (scan.cu, hash aggregate without a hint): how many runs of equal adjacent values it has,
+  // whether it ascends, and the number of runs before every warp tile -- what a GROUP BY on that column needs before it can
+  // stream over the runs.  Derived from immutable table data only (msc_scan_desc.table_columns) and dropped when the memory it
+  // describes is freed (msc_free), like the dictionaries of string columns it is computed once per table, not once per query.
+  struct RunIndex {
+    uint64_t nrows = 0, runs = 0, ntiles = 0;
+    bool sorted = false;
+    void* offsets = nullptr;  // u64[ntiles + 1]
+    size_t offsets_bytes = 0;
+  };
+  std::map<const void*, RunIndex> run_index;
   std::multimap<size_t, void*> big_free;
   std::unordered_map<void*, size_t> big_live;
   size_t big_free_bytes = 0;

@@ -39,6 +39,16 @@ int msc_alloc(msc_ctx* ctx, size_t nbytes, void** out) {
 int msc_free(msc_ctx* ctx, void* p, size_t nbytes) {
   if (!p) return MSC_OK;
   if (nbytes == 0) nbytes = 16;
+  if (!ctx->run_index.empty()) {  // what was derived from this memory goes with it
+    auto it = ctx->run_index.lower_bound(p);
+    while (it != ctx->run_index.end() && static_cast<const char*>(it->first) < static_cast<const char*>(p) + nbytes) {
+      void* offsets = it->second.offsets;
+      const size_t bytes = it->second.offsets_bytes;
+      it = ctx->run_index.erase(it);
+      msc_free(ctx, offsets, bytes);  // (a small block: it cannot itself be the key of an entry)
+      it = ctx->run_index.lower_bound(p);
+    }
+  }
   ctx->stats.device_bytes -= nbytes;
   auto live = ctx->big_live.find(p);
   if (live != ctx->big_live.end()) {
@@ -133,6 +143,9 @@ extern "C" int msc_create(int device, msc_ctx** out) {
 extern "C" void msc_destroy(msc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (auto& e : ctx->run_index)
+    if (e.second.offsets) cudaFreeAsync(e.second.offsets, ctx->stream);
+  ctx->run_index.clear();
   release_cached_blocks(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->ring)

@@ -1464,7 +1464,20 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     if (kphys == MSC_P_U8 || kphys == MSC_P_U16 || kphys == MSC_P_U32 || kphys == MSC_P_I32 || kphys == MSC_P_I64) {
       const void* kdata = sd->staged[key_col].data;
       const uint64_t ntiles = (sd->nrows + RUN_TILE - 1) / RUN_TILE;
+      static const bool index_enabled = !(getenv("MSC_RUN_INDEX") && atoi(getenv("MSC_RUN_INDEX")) == 0);
+      auto cached = (sd->table_columns && index_enabled) ? ctx->run_index.find(kdata) : ctx->run_index.end();
+      if (cached != ctx->run_index.end() && (cached->second.nrows != sd->nrows || cached->second.ntiles != ntiles)) cached = ctx->run_index.end();
       DevTmp d_desc(ctx), rcounts(ctx), roffsets(ctx);
+      uint64_t runs = 0;
+      bool sorted = false;
+      uint64_t* run_offsets = nullptr;
+      if (cached != ctx->run_index.end()) {  // this table column has been looked at before (msc_ctx::RunIndex)
+        runs = cached->second.runs;
+        sorted = cached->second.sorted;
+        run_offsets = static_cast<uint64_t*>(cached->second.offsets);
+        ctx->stats.last_run_index_hit = 1;
+      } else {
+      ctx->stats.last_run_index_hit = 0;
       MSC_TRY(d_desc.alloc(sizeof(unsigned long long)));
       MSC_TRY(rcounts.alloc(sizeof(uint32_t) * ntiles));
       MSC_TRY(roffsets.alloc(sizeof(uint64_t) * (ntiles + 1)));
@@ -1485,8 +1498,29 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
       MSC_CUDA(ctx, cudaMemcpyAsync(h, roffsets.as<uint64_t>() + ntiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
       MSC_CUDA(ctx, cudaMemcpyAsync(h + 1, d_desc.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
       MSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      const uint64_t runs = h[0];
-      const bool sorted = h[1] == 0;
+      runs = h[0];
+      sorted = h[1] == 0;
+      run_offsets = roffsets.as<uint64_t>();
+      if (sd->table_columns && index_enabled) {  // keep it with the table column (a handful of columns: the oldest entry makes room)
+        if (ctx->run_index.size() >= 8) {
+          auto victim = ctx->run_index.begin();
+          void* vo = victim->second.offsets;
+          const size_t vb = victim->second.offsets_bytes;
+          ctx->run_index.erase(victim);
+          msc_free(ctx, vo, vb);
+        }
+        msc_ctx::RunIndex ri;
+        ri.nrows = sd->nrows;
+        ri.runs = runs;
+        ri.ntiles = ntiles;
+        ri.sorted = sorted;
+        ri.offsets = roffsets.p;
+        ri.offsets_bytes = roffsets.n;
+        roffsets.p = nullptr;  // (ownership moves to the index)
+        roffsets.n = 0;
+        ctx->run_index[kdata] = ri;
+      }
+      }
       if (runs > 0 && runs < want) want = runs;
       if (sorted && !filtered && runs_enabled && runs > 0 && runs < (1ull << 31)) {
         // ---- streaming aggregate over the runs of a sorted key ----
@@ -1509,12 +1543,12 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
                                                                      static_cast<unsigned long long>(init[a]), runs);
         }
         ctx->stats.launches += naggs;
-        lp.p.tile_offsets = roffsets.as<uint64_t>();
+        lp.p.tile_offsets = run_offsets;
         lp.p.run_key_col = key_col;
         static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
         bool jitted = false;
         if (jit_mode > 0 && naggs + 1 <= MSC_VM_MAX_OUT && (sd->want_jit != 0 || jit_mode > 1 || jit_runs_cached(ctx, sd, naggs, kinds, key_col))) {
-          rc = jit_runs_launch(ctx, sd, naggs, kinds, key_col, roffsets.as<uint64_t>(), lp.p.out, true);
+          rc = jit_runs_launch(ctx, sd, naggs, kinds, key_col, run_offsets, lp.p.out, true);
           jitted = rc == MSC_OK;
           const bool declined = (rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) || (rc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0);
           if (rc != MSC_OK && !declined) {

@@ -327,6 +327,7 @@ class _Source:
         self.index_vectors = index_vectors or []
         self.keep = keep or []
         self.partitioned = partitioned  # see DeviceRel.partitioned
+        self.table_columns = False  # the columns are a loaded table's own (immutable while it is loaded): msc_scan_desc.table_columns
         # a join fused into this scan (CudaExecutionEngine._probe_source): the scan walks the probe side's rows, runs the
         # probe side's own filters, looks every row's key up in the build side's table and reads build-side columns
         # (via == "probe") through the matched row
@@ -442,6 +443,7 @@ class _ScanResolver:
         d.nluts = len(self.luts)
         d.ntemps = program.ntemps
         d.want_jit = 1 if self.engine.jit == "always" or self.engine._specialise_now else 0
+        d.table_columns = 1 if self.source.table_columns else 0
         d.ncode2 = len(program.regvm)
         d.count_slot2 = program.regvm_count_slot
         for i, w in enumerate(program.regvm):
@@ -870,7 +872,9 @@ class CudaExecutionEngine(ExecutionEngine):
         if isinstance(node, L.LTable):
             entry = self._table(node.path)
             self._ensure_columns(entry, needed)
-            return _Source(entry.nrows, {i: entry.columns[i] for i in needed}, partitioned=self.comm.world > 1)
+            source = _Source(entry.nrows, {i: entry.columns[i] for i in needed}, partitioned=self.comm.world > 1)
+            source.table_columns = True
+            return source
         if isinstance(node, L.LJoin):
             return self._join_source(node, needed)
         rel = self._run(node)
@@ -1043,6 +1047,7 @@ class CudaExecutionEngine(ExecutionEngine):
             if not ngroups:
                 st = self.ctx.stats()
                 self.last_stats["hash_local_slots"], self.last_stats["hash_attempts"] = st.last_hash_local_slots, st.last_hash_attempts
+                self.last_stats["run_index_hit"] = bool(st.last_run_index_hit)
             self.last_stats["agg_scan_ms"] = self.last_stats["scan_ms"]
             raw = self._track(DeviceRel.from_handle(self.ctx, out.value, [group.type, *slot_types], [prog.group_dict] + [None] * len(slot_types)))
             if not ngroups:

@@ -70,7 +70,7 @@ class ScanDesc(C.Structure):
         ("code2", C.c_uint32 * K["MSC_VM_MAX_CODE2"]),
         ("nrows_dev", C.c_void_p),
         ("want_jit", C.c_int32),
-        ("_pad2", C.c_int32),
+        ("table_columns", C.c_int32),
     ]
 
 
@@ -93,7 +93,7 @@ class Stats(C.Structure):
         ("last_agg_runs", C.c_int32),
         ("last_hash_local_slots", C.c_int32),
         ("last_hash_attempts", C.c_int32),
-        ("_pad", C.c_int32),
+        ("last_run_index_hit", C.c_int32),
     ]
 
 
