@@ -26,6 +26,7 @@ def main() -> None:
     ap.add_argument("--config", type=int, default=4)
     ap.add_argument("--jit", default=None)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--profile", type=int, default=0, help="cProfile this many executions instead of the per-call timeline")
     args = ap.parse_args()
     import cases
     import gen_tpch
@@ -77,6 +78,21 @@ def main() -> None:
         for _ in range(3):
             e.execute_to_device(task)
             e.release_query()
+        if args.profile:
+            import cProfile
+            import pstats
+
+            prof = cProfile.Profile()
+            prof.enable()
+            for _ in range(args.profile):
+                e.execute_to_device(task)
+                e.release_query()
+            prof.disable()
+            if rank == 0:
+                st = pstats.Stats(prof)
+                st.sort_stats("tottime").print_stats(28)
+                st.sort_stats("cumulative").print_stats(40)
+            return
         orig_call, orig_check = N.Context.call, N.Context.check
         t_base = [0.0]
 

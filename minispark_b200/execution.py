@@ -27,7 +27,7 @@ from contextlib import AbstractContextManager
 from copy import deepcopy
 from dataclasses import dataclass, field
 from pathlib import Path
-from typing import TYPE_CHECKING, Any, Iterable, Optional
+from typing import TYPE_CHECKING, Any, Callable, Iterable, Optional
 
 from . import lowering as L
 from . import native as N
@@ -351,26 +351,32 @@ class _ScanResolver:
         self._gather_slot: dict[int, int] = {}
         self._bindings: dict[int, L.Binding] = {}
         self.translate_targets = translate_targets or source.translate_targets or {}
+        # where every staged / gathered column came from -- ("col", input index) or ("ivec", k) -- so that a later run of the
+        # same scan over a structurally identical source can rebind the pointers without compiling again (_CompiledScan)
+        self.staged_origin: list[tuple[str, int]] = []
+        self.gather_origin: list[tuple[str, int]] = []
 
-    def _stage(self, col: DeviceColumn) -> int:
+    def _stage(self, col: DeviceColumn, origin: tuple[str, int]) -> int:
         if col.ptr not in self._staged_slot:
             if len(self.staged) >= N.K["MSC_VM_MAX_STAGED"]:
                 raise L.LoweringError("query reads more columns than one scan can stage")
             self._staged_slot[col.ptr] = len(self.staged)
             self.staged.append(col)
+            self.staged_origin.append(origin)
         return self._staged_slot[col.ptr]
 
     def binding(self, index: int) -> L.Binding:
         if index not in self._bindings:
             col = self.source.columns[index]
             if col.via is None:
-                b = L.Binding(col.phys, staged=self._stage(col), dict_id=col.dict)
+                b = L.Binding(col.phys, staged=self._stage(col, ("col", index)), dict_id=col.dict)
             elif col.via == "probe":
                 if col.ptr not in self._gather_slot:
                     if len(self.gather) >= N.K["MSC_VM_MAX_GATHER"]:
                         raise L.LoweringError("query gathers more columns than one scan supports")
                     self._gather_slot[col.ptr] = len(self.gather)
                     self.gather.append(col)
+                    self.gather_origin.append(("col", index))
                 b = L.Binding(col.phys, gather=self._gather_slot[col.ptr], dict_id=col.dict, probe=True)
             else:
                 if col.ptr not in self._gather_slot:
@@ -378,7 +384,8 @@ class _ScanResolver:
                         raise L.LoweringError("query gathers more columns than one scan supports")
                     self._gather_slot[col.ptr] = len(self.gather)
                     self.gather.append(col)
-                b = L.Binding(col.phys, gather=self._gather_slot[col.ptr], index=self._stage(self.source.index_vectors[col.via]),
+                    self.gather_origin.append(("col", index))
+                b = L.Binding(col.phys, gather=self._gather_slot[col.ptr], index=self._stage(self.source.index_vectors[col.via], ("ivec", col.via)),
                               dict_id=col.dict)
             self._bindings[index] = b
         return self._bindings[index]
@@ -450,6 +457,49 @@ class _ScanResolver:
             d.code2[i] = w
         for i, ptr in enumerate(self.luts):
             d.luts[i] = ptr
+        return d
+
+
+class _CompiledScan:
+    """A scan that has been compiled once: its program, its ``msc_scan_desc`` and where every pointer in it came from.
+
+    A repeated one-shot query lowers to the same plan (the plan cache), prepares structurally identical sources and would
+    compile the same programs again -- about 50 us of Python per scan, a fifth of a 1 ms query.  The engine keeps the compiled
+    scan per plan node instead and, when the source of the next run has the same shape (column types, access paths,
+    dictionaries and their sizes, probe form) and the expressions are equal, only rebinds row count and pointers."""
+
+    def __init__(self, node: Any, signature: tuple, pins: list, exprs: tuple, resolver: _ScanResolver, prog: Any, desc: N.ScanDesc) -> None:
+        self.node, self.signature, self.pins, self.exprs = node, signature, pins, exprs  # (node / pins keep the ids in the signature unique)
+        self.prog, self.desc = prog, desc
+        self.staged_origin, self.gather_origin = list(resolver.staged_origin), list(resolver.gather_origin)
+        probe_table = resolver.source.probe_table
+        self.probe_lut = resolver.luts.index(probe_table) if probe_table is not None and probe_table in resolver.luts else -1
+
+    @staticmethod
+    def signature_of(source: _Source, translate_targets: Optional[dict[str, DictHandle]]) -> tuple[tuple, list]:
+        pins: list = []
+        cols = []
+        for i, c in source.columns.items():
+            if c.dict is not None:
+                pins.append(c.dict)
+                cols.append((i, c.phys, c.via, id(c.dict), c.dict.size))
+            else:
+                cols.append((i, c.phys, c.via, 0, 0))
+        targets = translate_targets or source.translate_targets or {}
+        tsig = tuple((k, id(v), v.size) for k, v in targets.items())
+        pins.extend(targets.values())
+        return (tuple(cols), len(source.index_vectors), source.probe_compact, source.probe_table is not None, source.table_columns, tsig), pins
+
+    def rebind(self, engine: "CudaExecutionEngine", source: _Source) -> N.ScanDesc:
+        d = self.desc
+        d.nrows = source.nrows
+        for slot, (kind, at) in enumerate(self.staged_origin):
+            d.staged[slot].data = (source.columns[at] if kind == "col" else source.index_vectors[at]).ptr
+        for slot, (_, at) in enumerate(self.gather_origin):
+            d.gather[slot].data = source.columns[at].ptr
+        if self.probe_lut >= 0:
+            d.luts[self.probe_lut] = source.probe_table
+        d.want_jit = 1 if engine.jit == "always" or engine._specialise_now else 0
         return d
 
 
@@ -568,6 +618,8 @@ class CudaExecutionEngine(ExecutionEngine):
         # here the second execution of an identical aggregate task tree is prepared once (lowering, validated programs, the
         # kernel specialised for it, result buffers) and every later one is a single launch.  fingerprint -> [runs, prepared]
         self._plan_cache: dict[Any, list] = {}
+        self._scan_cache: dict[tuple, _CompiledScan] = {}  # compiled scans per plan node (_CompiledScan)
+        self.scan_cache_enabled = os.environ.get("MINISPARK_SCAN_CACHE", "1") != "0"
         self.plan_cache_enabled = os.environ.get("MINISPARK_PLAN_CACHE", "1") != "0"
         # joins whose build side has no duplicate keys run as a lookup inside the consuming scan (MSC_OP_PROBE) instead of
         # materialising both sides and the pair list
@@ -665,6 +717,7 @@ class CudaExecutionEngine(ExecutionEngine):
             self.last_plan = plan
             self.last_stats["exchange"] = None
             self.last_stats["exchanges"] = []  # every cross-rank step of this query, in order
+            self.last_stats["scans_rebound"] = 0  # scans of this query that reused the program compiled by an earlier run (_CompiledScan)
             self.last_stats["plan"] = "one-shot"
             self._specialise_now = self.jit == "auto" and entry is not None and entry[0] >= 2
             if self._specialise_now:
@@ -780,6 +833,7 @@ class CudaExecutionEngine(ExecutionEngine):
     def drop_table_cache(self, name: Optional[str] = None) -> None:
         """Forget device-resident columns (all tables, or one) so the next query ingests again."""
         self._plan_cache.clear()  # prepared passes are bound to the columns that go away
+        self._scan_cache.clear()  # (and compiled scans pin their dictionaries)
         for key, entry in list(self._tables.items()):
             if name is not None and key != name:
                 continue
@@ -945,17 +999,37 @@ class CudaExecutionEngine(ExecutionEngine):
         col = source.columns[index]
         resolver = _ScanResolver(self, source)
         prog = L.compile_project(resolver, [], [L.EInput(col.ltype, index)])
-        rel = self._scan_project(resolver, prog, [col.ltype])
+        rel = self._scan_project(prog, resolver.desc(prog.program), [col.ltype], source.partitioned)
         return rel.cols[0]
 
-    def _scan_project(self, resolver: _ScanResolver, prog: L.ProjectProgram, ltypes: list[str]) -> DeviceRel:
+    def _compiled_scan(self, key: Optional[tuple], node: Any, source: _Source, translate_targets: Optional[dict[str, DictHandle]], exprs: tuple,
+                       compile_fn: Callable[[_ScanResolver], Any]) -> tuple[Any, N.ScanDesc]:
+        """(program, descriptor) of one scan: compiled now, or the compiled scan of an earlier run of the same plan node rebound
+        to this run's rows (_CompiledScan)."""
+        if key is None or not self.scan_cache_enabled:
+            resolver = _ScanResolver(self, source, translate_targets)
+            prog = compile_fn(resolver)
+            return prog, resolver.desc(prog.program)
+        signature, pins = _CompiledScan.signature_of(source, translate_targets)
+        hit = self._scan_cache.get(key)
+        if hit is not None and hit.signature == signature and hit.exprs == exprs:
+            self.last_stats["scans_rebound"] = self.last_stats.get("scans_rebound", 0) + 1
+            return hit.prog, hit.rebind(self, source)
+        resolver = _ScanResolver(self, source, translate_targets)
+        prog = compile_fn(resolver)
         desc = resolver.desc(prog.program)
+        if len(self._scan_cache) >= 256:
+            self._scan_cache.clear()
+        self._scan_cache[key] = _CompiledScan(node, signature, pins, exprs, resolver, prog, desc)
+        return prog, desc
+
+    def _scan_project(self, prog: L.ProjectProgram, desc: N.ScanDesc, ltypes: list[str], partitioned: bool) -> DeviceRel:
         out = C.c_void_p()
         phys = N.int32_array(prog.out_phys)
         self.ctx.call("msc_scan_project", C.byref(desc), phys, len(prog.out_phys), C.byref(out))
         self._note_kernel("scan: filter + project")
         rel = self._track(DeviceRel.from_handle(self.ctx, out.value, ltypes, prog.out_dicts))
-        rel.partitioned = resolver.source.partitioned
+        rel.partitioned = partitioned
         return rel
 
     def _gpu_track(self) -> int:
@@ -979,20 +1053,22 @@ class CudaExecutionEngine(ExecutionEngine):
         nf = len(sel.filters)
         source, exprs = self._prepare(sel.child, [*sel.filters, *sel.outputs])
         filters, outputs = exprs[:nf], exprs[nf:]
-        rel = self._project(source, filters, outputs, translate_targets)
+        rel = self._project(source, filters, outputs, translate_targets, node=sel)
         rel.keep.extend(source.keep)
         return rel
 
-    def _project(self, source: _Source, filters: list[L.Expr], outputs: list[L.Expr], translate_targets: Optional[dict[str, DictHandle]]) -> DeviceRel:
+    def _project(self, source: _Source, filters: list[L.Expr], outputs: list[L.Expr], translate_targets: Optional[dict[str, DictHandle]],
+                 node: Any = None) -> DeviceRel:
         """One filter + project scan -- or several over the same rows when the outputs exceed what one scan can bind
         (MSC_VM_MAX_OUT output columns, MSC_VM_MAX_STAGED staged / MSC_VM_MAX_GATHER gathered inputs: `SELECT *` over a wide
         join).  Every pass evaluates the same filters and compaction is stable, so the passes' columns line up row by row."""
         try:
             if len(outputs) > N.K["MSC_VM_MAX_OUT"]:
                 raise L.LoweringError("too many output columns in one projection")
-            resolver = _ScanResolver(self, source, translate_targets)
-            prog = L.compile_project(resolver, filters, outputs, probe=resolver.probe_spec(), pre_filters=source.pre_filters)
-            return self._scan_project(resolver, prog, [e.type for e in outputs])
+            prog, desc = self._compiled_scan(
+                ("project", id(node)) if node is not None else None, node, source, translate_targets, (tuple(filters), tuple(outputs), tuple(source.pre_filters), source.probe_key),
+                lambda r: L.compile_project(r, filters, outputs, probe=r.probe_spec(), pre_filters=source.pre_filters))
+            return self._scan_project(prog, desc, [e.type for e in outputs], source.partitioned)
         except L.LoweringError as err:
             splittable = any(t in str(err) for t in ("too many output columns", "more columns than one scan", "gathers more columns"))
             if len(outputs) < 2 or not splittable:
@@ -1020,10 +1096,10 @@ class CudaExecutionEngine(ExecutionEngine):
         nf = len(filters)
         filters, group = exprs[:nf], exprs[nf]
         aggs = [(k, e) for (k, _), e in zip(aggs, exprs[nf + 1:])]
-        resolver = _ScanResolver(self, source)
-        prog = L.compile_aggregate(resolver, filters, group, aggs, probe=resolver.probe_spec(), pre_filters=source.pre_filters)
+        prog, desc = self._compiled_scan(
+            ("aggregate", id(agg)), agg, source, None, (tuple(filters), group, tuple(aggs), tuple(source.pre_filters), source.probe_key),
+            lambda r: L.compile_aggregate(r, filters, group, aggs, probe=r.probe_spec(), pre_filters=source.pre_filters))
         ngroups, hint = self._dense_groups(prog)
-        desc = resolver.desc(prog.program)
         kinds = N.int32_array(prog.agg_kinds)
         # raw result: key + one column per unique accumulator slot; expose it in the aggregate's schema order
         slot_types = [L.FLOAT if k in (N.K["MSC_AGG_SUM_F"], N.K["MSC_AGG_MIN_F"], N.K["MSC_AGG_MAX_F"]) else L.INT for k in prog.agg_kinds]
@@ -1093,10 +1169,13 @@ class CudaExecutionEngine(ExecutionEngine):
 
     def _join_side(self, node: L.LNode, idxs: list[int], key: L.Expr, targets: Optional[dict[str, DictHandle]]) -> DeviceRel:
         """One side of a join as a relation: the needed columns, then the key (a STR key as its dictionary code)."""
-        outs = [L.EInput(_LTYPE_OF[node.schema[i][1]], i) for i in idxs]
-        key_out = L.ECode(L.INT, key) if key.type == L.STR else key
-        schema = [node.schema[i] for i in idxs] + [("__key", ColumnType.INTEGER)]
-        sel = L.fuse_selects(L.LSelect(schema, node, [], [*outs, key_out]))
+        memo = node.__dict__.setdefault("_side_selects", {})  # (the same node object next time: its compiled scan is found again)
+        sel = memo.get((tuple(idxs), key))
+        if sel is None:
+            outs = [L.EInput(_LTYPE_OF[node.schema[i][1]], i) for i in idxs]
+            key_out = L.ECode(L.INT, key) if key.type == L.STR else key
+            schema = [node.schema[i] for i in idxs] + [("__key", ColumnType.INTEGER)]
+            sel = memo[(tuple(idxs), key)] = L.fuse_selects(L.LSelect(schema, node, [], [*outs, key_out]))
         return self._run_select(sel, targets)
 
     def _probe_source(self, join: L.LJoin, exprs: list[L.Expr], needed: set[int]) -> Optional[tuple[_Source, list[L.Expr]]]:
@@ -1285,7 +1364,8 @@ class CudaExecutionEngine(ExecutionEngine):
             outs.append(L.ETranslate(L.STR, L.EInput(L.STR, i), f"x{i}"))
         source = _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel], partitioned=rel.partitioned)
         resolver = _ScanResolver(self, source, targets)
-        return self._scan_project(resolver, L.compile_project(resolver, [], outs), ltypes)
+        prog = L.compile_project(resolver, [], outs)
+        return self._scan_project(prog, resolver.desc(prog.program), ltypes, source.partitioned)
 
     def _local_part(self, rel: DeviceRel) -> DeviceRel:
         """A relation every rank holds in full enters an exchange from rank 0 only (the other ranks contribute no rows)."""
@@ -1439,7 +1519,7 @@ class CudaExecutionEngine(ExecutionEngine):
             outs = [L.ECode(L.INT, L.ETranslate(L.STR, L.EInput(L.STR, 0), "global"))]
             outs += [L.EInput(t, i + 1) for i, t in enumerate(slot_types)]
             prog = L.compile_project(resolver, [], outs)
-            raw = self._scan_project(resolver, prog, [L.INT, *slot_types])
+            raw = self._scan_project(prog, resolver.desc(prog.program), [L.INT, *slot_types], source.partitioned)
         # what every rank holds: rows, and -- when its pre-aggregation streamed over the runs of a sorted key (msc_stats.last_agg_runs),
         # so that its partial rows ascend and no key repeats on the rank -- the first key and the whole last row
         ascending = bool(self.ctx.stats().last_agg_runs) and group_type in (L.INT, L.TS) and raw.nrows > 0 and raw.handle is not None
