@@ -482,11 +482,11 @@ class _CompiledScan:
         for i, c in source.columns.items():
             if c.dict is not None:
                 pins.append(c.dict)
-                cols.append((i, c.phys, c.via, id(c.dict), c.dict.size))
+                cols.append((i, c.phys, c.via, c.dict.serial, c.dict.size))  # (serial: never reused, unlike id())
             else:
                 cols.append((i, c.phys, c.via, 0, 0))
         targets = translate_targets or source.translate_targets or {}
-        tsig = tuple((k, id(v), v.size) for k, v in targets.items())
+        tsig = tuple((k, v.serial, v.size) for k, v in targets.items())
         pins.extend(targets.values())
         return (tuple(cols), len(source.index_vectors), source.probe_compact, source.probe_table is not None, source.table_columns, tsig), pins
 
