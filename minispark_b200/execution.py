@@ -1062,6 +1062,28 @@ class CudaExecutionEngine(ExecutionEngine):
         """One filter + project scan -- or several over the same rows when the outputs exceed what one scan can bind
         (MSC_VM_MAX_OUT output columns, MSC_VM_MAX_STAGED staged / MSC_VM_MAX_GATHER gathered inputs: `SELECT *` over a wide
         join).  Every pass evaluates the same filters and compaction is stable, so the passes' columns line up row by row."""
+        # An unfiltered projection keeps every row, so an output that is just an input column -- in the physical type results
+        # have anyway -- IS that column: it is shared, not copied (the AVG projection over a GROUP BY's 15 M groups read and
+        # wrote the key and the SUM only to pass them on: 56 -> 24 bytes per group).
+        if not filters and not source.pre_filters and source.probe_key is None and not translate_targets and not source.translate_targets \
+                and os.environ.get("MINISPARK_SHARE_COLUMNS", "1") != "0":
+            result_phys = {L.INT: N.P_I64, L.TS: N.P_I64, L.FLOAT: N.P_F64, L.STR: N.P_U32}
+            shared = {j: source.columns[e.index] for j, e in enumerate(outputs)
+                      if isinstance(e, L.EInput) and source.columns[e.index].via is None and source.columns[e.index].phys == result_phys.get(e.type)}
+            if shared:
+                computed = [j for j in range(len(outputs)) if j not in shared]
+                cols: list[Optional[DeviceColumn]] = [shared.get(j) for j in range(len(outputs))]
+                keep: list = []
+                if computed:
+                    part = self._project(source, [], [outputs[j] for j in computed], None, node=node)
+                    if part.nrows != source.nrows:
+                        raise ExecutionError("an unfiltered projection changed the row count")
+                    for j, c in zip(computed, part.cols):
+                        cols[j] = c
+                    keep.append(part)
+                rel = DeviceRel(self.ctx, None, source.nrows, [c for c in cols if c is not None], keep=keep)
+                rel.partitioned = source.partitioned
+                return self._materialised(rel)
         try:
             if len(outputs) > N.K["MSC_VM_MAX_OUT"]:
                 raise L.LoweringError("too many output columns in one projection")
