@@ -80,8 +80,37 @@ class ClockSampler:
         self.device = device
         self.proc: subprocess.Popen | None = None
         self.lines: list[str] = []
+        self.nvml_samples: list[tuple[float, float, int]] = []  # (sm MHz, max sm MHz, event-reason bits) straight from NVML
+        self._stop = threading.Event()
+        self._nvml_thread: threading.Thread | None = None
+
+    def _nvml_loop(self, nvml, handle) -> None:  # noqa: ANN001
+        reasons = getattr(nvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or nvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            smax = float(nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            smax = 0.0
+        while True:
+            try:
+                self.nvml_samples.append((float(nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)), smax, int(reasons(handle))))
+            except Exception:  # noqa: BLE001
+                return
+            if self._stop.wait(0.002):
+                return
 
     def __enter__(self) -> "ClockSampler":
+        # NVML in a thread of this process: a sample every 2 ms, so that even the ~8 ms timed region of an 8-GPU run is covered
+        # (nvidia-smi -lms needs ~0.2 s before its first line: with eight of them starting at once the region was over first)
+        try:
+            import pynvml as nvml
+
+            nvml.nvmlInit()
+            handle = nvml.nvmlDeviceGetHandleByIndex(self.device)
+            self._nvml_thread = threading.Thread(target=self._nvml_loop, args=(nvml, handle), daemon=True)
+            self._nvml_thread.start()
+            return self
+        except Exception:  # noqa: BLE001  (no NVML bindings: the command-line tool instead)
+            self._nvml_thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -97,6 +126,10 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *exc: object) -> None:
+        if self._nvml_thread is not None:
+            self._stop.set()
+            self._nvml_thread.join(timeout=1.0)
+            return
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -108,6 +141,13 @@ class ClockSampler:
     def summary(self) -> dict:
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml_samples:
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}  # nvmlClocksEventReason*
+            for clock, top, mask in self.nvml_samples:
+                sm.append(clock)
+                smax.append(top)
+                reasons.update(name for name, bit in bits.items() if mask & bit)
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm), "source": "nvml, every 2 ms"}
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:

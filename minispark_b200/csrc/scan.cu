@@ -24,6 +24,22 @@ __global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, uin
     p[i] = v;
 }
 
+// the accumulator columns of a streaming aggregate, each filled with its identity, in ONE launch (16-byte stores)
+struct FillCols {
+  unsigned long long* col[MSC_VM_MAX_AGGS];
+  unsigned long long init[MSC_VM_MAX_AGGS];
+  int n;
+};
+__global__ void fill_cols_kernel(const __grid_constant__ FillCols f, uint64_t rows) {
+  const uint64_t pairs = rows / 2, stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (int a = 0; a < f.n; ++a) {
+    const ulonglong2 v = make_ulonglong2(f.init[a], f.init[a]);
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(f.col[a]);  // (column allocations are 256-byte aligned)
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < pairs; i += stride) p[i] = v;
+    if ((rows & 1) && blockIdx.x == 0 && threadIdx.x == 0) f.col[a][rows - 1] = f.init[a];
+  }
+}
+
 // identities, kinds and output columns of a dense aggregate travel as kernel parameters (no staging copies)
 struct DenseMeta {
   long long init[MSC_VM_MAX_AGGS + 1];
@@ -1537,12 +1553,17 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
           return rc;
         }
         lp.p.out[0] = rel->cols[0].data;
+        FillCols fc;
+        fc.n = naggs;
         for (int a = 0; a < naggs; ++a) {
           lp.p.out[1 + a] = rel->cols[1 + a].data;
-          fill_u64_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(static_cast<unsigned long long*>(rel->cols[1 + a].data),
-                                                                     static_cast<unsigned long long>(init[a]), runs);
+          fc.col[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
+          fc.init[a] = static_cast<unsigned long long>(init[a]);
         }
-        ctx->stats.launches += naggs;
+        if (naggs > 0) {
+          fill_cols_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(fc, runs);
+          ctx->stats.launches += 1;
+        }
         lp.p.tile_offsets = run_offsets;
         lp.p.run_key_col = key_col;
         static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
