@@ -35,6 +35,10 @@ def _queries(ns, left, right, engine=None):
     return {
         "join_agg": joined().filter(ns.Col("d.d_w") > 5.0).filter(ns.Col("f.f_tag").like("%AIR%")).group_by(ns.Col("d.d_name")).agg(
             ns.F.count().alias("n"), ns.F.sum(ns.Col("f.f_x")).alias("s")),
+        # 7 groups x 7 accumulator cells behind a fused probe: the specialised kernel's shared-memory-cell form with the compacted tail
+        "join_agg_wide": joined().filter(ns.Col("f.f_tag").like("%A%")).group_by(ns.Col("d.d_name")).agg(
+            ns.F.count().alias("n"), ns.F.sum(ns.Col("f.f_x")).alias("sx"), ns.F.sum(ns.Col("d.d_w")).alias("sw"), ns.F.min(ns.Col("f.f_x")).alias("lo"),
+            ns.F.max(ns.Col("f.f_x")).alias("hi"), ns.F.avg(ns.Col("d.d_w")).alias("aw"), ns.F.sum(ns.Col("f.f_x") * ns.Col("d.d_w")).alias("sxw")),
         "join_select": joined().filter(ns.Col("f.f_x") > 100.0).select(ns.Col("d.d_name"), ns.Col("f.f_x"), (ns.Col("d.d_w") * 2).alias("w2")),
         "hash_agg": ns.DataFrame(engine).table(right).group_by(ns.Col("f_id")).agg(ns.F.sum(ns.Col("f_x")).alias("s"), ns.F.count().alias("n")),
         "filter_project": ns.DataFrame(engine).table(right).filter(ns.Col("f_tag") == "SHIP").select(ns.Col("f_id"), (ns.Col("f_x") + 1).alias("x1")),
