@@ -18,12 +18,6 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, uint64_t n) {
-  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
-    p[i] = v;
-}
-
 // the accumulator columns of a streaming aggregate, each filled with its identity, in ONE launch (16-byte stores)
 struct FillCols {
   unsigned long long* col[MSC_VM_MAX_AGGS];
