@@ -102,6 +102,7 @@ class DictHandle:
         self._translated_from: list[tuple["DictHandle", tuple]] = []  # translation tables other dictionaries cache INTO this one
         self.persistent = False  # a table column's dictionary (lives as long as the engine): results derived from it may be kept
         self._unified: Optional[tuple[int, "DictHandle"]] = None  # (size it was built at, the same entries on every rank)
+        self.same_on_all_ranks = False  # built from the union of all ranks' entries (_unified_dictionary): same size and codes everywhere
 
     @property
     def size(self) -> int:
@@ -276,6 +277,7 @@ class TableEntry:
     schema: Schema
     blocks: list[int]
     nrows: int
+    total_rows: int = 0  # rows of the whole file (all ranks' blocks): known from the footer without asking anybody
     columns: dict[int, DeviceColumn] = field(default_factory=dict)
     rels: list[DeviceRel] = field(default_factory=list)
     keepalive: Any = None  # pinned image for in-memory tables
@@ -859,7 +861,7 @@ class CudaExecutionEngine(ExecutionEngine):
             rows = C.c_uint32()
             self.ctx.check(self.ctx.lib.msc_table_block_rows(C.c_void_p(handle), b, C.byref(rows)))
             local_rows += rows.value
-        return TableEntry(path, stamp, handle, schema, blocks, local_rows, keepalive=keepalive)
+        return TableEntry(path, stamp, handle, schema, blocks, local_rows, total_rows=nrows.value, keepalive=keepalive)
 
     def _table(self, path: Path) -> TableEntry:
         key = str(path)
@@ -1182,7 +1184,7 @@ class CudaExecutionEngine(ExecutionEngine):
             return 0, 0
         size = prog.group_dict.size
         limit = size
-        if self.comm.world > 1:
+        if self.comm.world > 1 and not prog.group_dict.same_on_all_ranks:
             limit = max(r[0] for r in self._gather_counts([size]))
         dense = limit > 0 and (limit + 1) * (len(prog.agg_kinds) + 1) <= DENSE_MAX_CELLS
         if self.comm.world == 1:
@@ -1199,6 +1201,15 @@ class CudaExecutionEngine(ExecutionEngine):
             schema = [node.schema[i] for i in idxs] + [("__key", ColumnType.INTEGER)]
             sel = memo[(tuple(idxs), key)] = L.fuse_selects(L.LSelect(schema, node, [], [*outs, key_out]))
         return self._run_select(sel, targets)
+
+    def _rows_upper_bound(self, node: L.LNode) -> Optional[int]:
+        """Rows the relation of `node` can have over ALL ranks, from file footers alone (every rank computes the same number
+        without a message), or None when only the data can tell."""
+        if isinstance(node, L.LTable):
+            return self._table(node.path).total_rows
+        if isinstance(node, (L.LSelect, L.LAggregate)):
+            return self._rows_upper_bound(node.child)
+        return None
 
     def _probe_source(self, join: L.LJoin, exprs: list[L.Expr], needed: set[int]) -> Optional[tuple[_Source, list[L.Expr]]]:
         """A join as a LOOKUP inside the scan that consumes it.  The reference builds key -> [left rows] and streams the right
@@ -1228,7 +1239,8 @@ class CudaExecutionEngine(ExecutionEngine):
         broadcast = False
         if self.comm.world > 1 and lrel.partitioned:
             limit = int(os.environ.get("MSC_BROADCAST_JOIN_MAX", str(32 << 20)))
-            total = sum(r[0] for r in self._gather_counts([lrel.nrows]))
+            bound = self._rows_upper_bound(join.left)  # (a build side that cannot exceed the limit needs no count exchange)
+            total = bound if bound is not None and bound <= limit else sum(r[0] for r in self._gather_counts([lrel.nrows]))
             if total > limit:
                 self._probe_declined = lrel
                 return None
@@ -1362,6 +1374,7 @@ class CudaExecutionEngine(ExecutionEngine):
             return local._unified[1]
         universe, _ = unify_keys(self.comm.all_gather_object(local.export()))
         unified = DictHandle(self.ctx).load(universe)
+        unified.same_on_all_ranks = True
         if local.persistent:
             unified.persistent = True
             local._unified = (local.size, unified)
@@ -1385,9 +1398,9 @@ class CudaExecutionEngine(ExecutionEngine):
             targets[f"x{i}"] = self._unified_dictionary(c.dict)
             outs.append(L.ETranslate(L.STR, L.EInput(L.STR, i), f"x{i}"))
         source = _Source(rel.nrows, dict(enumerate(rel.cols)), keep=[rel], partitioned=rel.partitioned)
-        resolver = _ScanResolver(self, source, targets)
-        prog = L.compile_project(resolver, [], outs)
-        return self._scan_project(prog, resolver.desc(prog.program), ltypes, source.partitioned)
+        signature, _ = _CompiledScan.signature_of(source, targets)
+        prog, desc = self._compiled_scan(("rank-independent", signature), None, source, targets, tuple(outs), lambda r: L.compile_project(r, [], outs))
+        return self._scan_project(prog, desc, ltypes, source.partitioned)
 
     def _local_part(self, rel: DeviceRel) -> DeviceRel:
         """A relation every rank holds in full enters an exchange from rank 0 only (the other ranks contribute no rows)."""
