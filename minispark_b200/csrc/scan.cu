@@ -1621,7 +1621,7 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     const uint64_t groups = ladder[attempt];
     const bool last = attempt == nladder - 1;
     {
-      uint64_t c = 1ull << 16;
+      uint64_t c = sd->nrows > (1u << 16) ? (1ull << 16) : 64;
       while (c < groups * 2) c <<= 1;
       if (!last && c == tried_cap) continue;  // (a table of this size has just overflowed)
       tried_cap = c;
@@ -1630,7 +1630,10 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
     const bool known = hash_capacity_hint != 0 || (soft_groups > 0 && attempt == 0);  // `groups` is (about) the number of groups, not a guess
     // (never fewer than 2^16 slots: the 1000 groups of sf10 `GROUP BY l_orderkey % 1000` take 2.6 ms in a 4096-slot table and
     // 1.5 ms spread over 65536 slots -- the same number of hot lines, but more L2 slices share their atomics)
-    cap = 1ull << 16;
+    // (a scan of a few thousand rows -- the final aggregate over merged partial results -- keeps a table of its own size:
+    // there is no contention to spread, and initialising / compacting 65536 slots would be most of its time)
+    const uint64_t min_cap = sd->nrows > (1u << 16) ? (1ull << 16) : 64;
+    cap = min_cap;
     while (cap < groups * 2) cap <<= 1;
     if (cap > (1ULL << 31)) return ctx->fail(MSC_ERR_ARG, "hash aggregate: more than 2^30 groups per GPU is not supported");
     uint32_t lcap = 0;
