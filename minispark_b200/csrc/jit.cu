@@ -563,19 +563,20 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
     const char* kty = kphys == MSC_P_U8 ? "unsigned char" : kphys == MSC_P_U16 ? "unsigned short" : kphys == MSC_P_U32 ? "u32"
                       : kphys == MSC_P_I32 ? "int" : "i64";
     o << "  const " << kty << "* key_col = reinterpret_cast<const " << kty << "*>(p.col[" << key_col << "]);\n";
-    o << R"(  u64 next_base = 0;
-  i64 next_before = 0;
-  if (ntiles_w > 0) {
+    // (next_before keeps the column's own type: widening it where it is LOADED made the warp wait for the load right there --
+    // prof_runs, 22 % of the stall samples on that one shift)
+    o << "  u64 next_base = 0;\n  " << kty << " next_before = 0;\n";
+    o << R"(  if (ntiles_w > 0) {
     next_base = p.tile_offsets[gw];
-    if (lane == 0 && gw > 0) next_before = (i64)key_col[(u64)gw * WT - 1];
+    if (lane == 0 && gw > 0) next_before = key_col[(u64)gw * WT - 1];
   }
   for (u32 k = 0; k < ntiles_w; ++k) {
     const u64 tile = gw + (u64)k * nw;
     const u64 base = next_base;  // runs that start before this tile
-    const i64 before = next_before;
+    const i64 before = (i64)next_before;
     if (k + 1 < ntiles_w) {
       next_base = p.tile_offsets[tile + nw];
-      if (lane == 0) next_before = (i64)key_col[(tile + nw) * WT - 1];
+      if (lane == 0) next_before = key_col[(tile + nw) * WT - 1];
     }
     const unsigned char* sb = stages + stage * STAGE_BYTES;
     while (!mbar_try_wait(&full[stage], parity)) {
