@@ -667,10 +667,22 @@ extern "C" __global__ void __launch_bounds__(NT, MINCTAS) msc_jit_runs(const __g
       }
     }
 )";
+    // phase 1: the runs that start in a lane's segments are stored; phase 2, behind the warp's barrier: the leading rows of a
+    // segment are added to the run they continue (fold_store_heads in the prelude)
     for (int a = 0; a < naggs; ++a)
       if (used[a])
-        o << "    fold_segment<" << kinds[a] << ">(reinterpret_cast<u64*>(p.out[" << 1 + a << "]), idx, v" << a << "); fold_segment<" << kinds[a]
-          << ">(reinterpret_cast<u64*>(p.out[" << 1 + a << "]), idx + 4, v" << a << " + 4);\n";
+        o << "    const i64 lead0_" << a << " = fold_store_heads<" << kinds[a] << ">(reinterpret_cast<u64*>(p.out[" << 1 + a << "]), h, idx, v" << a
+          << ", vmask & 0xfu), lead1_" << a << " = fold_store_heads<" << kinds[a] << ">(reinterpret_cast<u64*>(p.out[" << 1 + a << "]), h + 4, idx + 4, v" << a
+          << " + 4, (vmask >> 4) & 0xfu);\n";
+    o << "    __syncwarp();\n    {\n      const long long open_run = (long long)base - 1;  // the run still open when this tile begins: its part goes to the tile's carry cell\n"
+      << "      const bool l0 = (vmask & 1u) && !h[0], l1 = ((vmask >> 4) & 1u) && !h[4];\n";
+    for (int a = 0; a < naggs; ++a)
+      if (used[a]) {
+        const std::string col = "reinterpret_cast<u64*>(p.out[" + std::to_string(1 + a) + "])", carry = "(p.dense_out + " + std::to_string(a) + "ull * ((p.ntiles + 1u) & ~1u) + tile)";  // (rows of even length: 16-byte aligned)
+        o << "      if (l0) atomic_fold(" << kinds[a] << ", idx[0] == open_run ? " << carry << " : " << col << " + idx[0], lead0_" << a << ");\n"
+          << "      if (l1) atomic_fold(" << kinds[a] << ", idx[4] == open_run ? " << carry << " : " << col << " + idx[4], lead1_" << a << ");\n";
+      }
+    o << "    }\n";
     o << R"(    __syncwarp();
     if (k + NSTAGES < ntiles_w) issue_tile(p, stages, full, stage, gw + (u64)(k + NSTAGES) * nw, lane);
     if (++stage == NSTAGES) {
@@ -1571,12 +1583,13 @@ int jit_runs_source(const msc_scan_desc* sd, int naggs, const int* kinds, int ke
 }
 
 int jit_runs_launch(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, const uint64_t* tile_offsets, void* const* outs,
-                    bool timed) {
+                    unsigned long long* carry, bool timed) {
   Kernel* k = nullptr;
   MSC_TRY(runs_kernel(ctx, sd, naggs, kinds, key_col, &k));
   JitParams p;
   MSC_TRY(fill_params(ctx, sd, &p));
   p.tile_offsets = reinterpret_cast<const unsigned long long*>(tile_offsets);
+  p.dense_out = carry;  // [accumulator][tile]: what a tile adds to the run that was open when it began (holding the identities)
   for (int c = 0; c < 1 + naggs; ++c) p.out[c] = outs[c];
   return launch(ctx, *k, &p, timed);
 }

@@ -63,6 +63,6 @@ int jit_project_launch(msc_ctx* ctx, const msc_scan_desc* sd, bool count_only, c
 bool jit_runs_cached(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col);
 int jit_runs_source(const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, std::string* source, std::string* err);
 int jit_runs_launch(msc_ctx* ctx, const msc_scan_desc* sd, int naggs, const int* kinds, int key_col, const uint64_t* tile_offsets, void* const* outs,
-                    bool timed);
+                    unsigned long long* carry, bool timed);
 
 }  // namespace mscan

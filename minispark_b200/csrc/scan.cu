@@ -34,6 +34,46 @@ __global__ void fill_cols_kernel(const __grid_constant__ FillCols f, uint64_t ro
   }
 }
 
+// after the specialised streaming aggregate: carry[a][t] = what tile t added to the run that was open when it began (run number
+// tile_offsets[t] - 1); several tiles may carry into one long run, so the additions are atomic
+struct CarryFold {
+  unsigned long long* col[MSC_VM_MAX_AGGS];
+  unsigned long long init[MSC_VM_MAX_AGGS];
+  int kind[MSC_VM_MAX_AGGS];
+  int n;
+};
+__device__ __forceinline__ void carry_atomic_fold(int kind, unsigned long long* addr, unsigned long long v) {
+  switch (kind) {
+    case MSC_AGG_SUM_F: atomicAdd(reinterpret_cast<double*>(addr), __longlong_as_double(static_cast<long long>(v))); break;
+    case MSC_AGG_SUM_I: atomicAdd(addr, v); break;
+    case MSC_AGG_MIN_I: atomicMin(reinterpret_cast<long long*>(addr), static_cast<long long>(v)); break;
+    case MSC_AGG_MAX_I: atomicMax(reinterpret_cast<long long*>(addr), static_cast<long long>(v)); break;
+    default: {  // f64 min / max: CAS loop
+      unsigned long long old = *addr;
+      while (true) {
+        const double a = __longlong_as_double(static_cast<long long>(old)), b = __longlong_as_double(static_cast<long long>(v));
+        const double m = kind == MSC_AGG_MIN_F ? (b < a ? b : a) : (b > a ? b : a);
+        const unsigned long long merged = static_cast<unsigned long long>(__double_as_longlong(m));
+        if (merged == old) break;
+        const unsigned long long prev = atomicCAS(addr, old, merged);
+        if (prev == old) break;
+        old = prev;
+      }
+    }
+  }
+}
+__global__ void carry_fold_kernel(const unsigned long long* carry, uint64_t cstride, const uint64_t* tile_offsets, uint64_t ntiles,
+                                  const __grid_constant__ CarryFold f) {
+  for (uint64_t t = 1 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < ntiles; t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t before = tile_offsets[t];
+    if (before == 0) continue;
+    for (int a = 0; a < f.n; ++a) {
+      const unsigned long long c = carry[static_cast<uint64_t>(a) * cstride + t];
+      if (c != f.init[a]) carry_atomic_fold(f.kind[a], f.col[a] + (before - 1), c);
+    }
+  }
+}
+
 // identities, kinds and output columns of a dense aggregate travel as kernel parameters (no staging copies)
 struct DenseMeta {
   long long init[MSC_VM_MAX_AGGS + 1];
@@ -1547,31 +1587,55 @@ extern "C" int msc_scan_aggregate(msc_ctx* ctx, const msc_scan_desc* sd, int32_t
           return rc;
         }
         lp.p.out[0] = rel->cols[0].data;
-        FillCols fc;
-        fc.n = naggs;
-        for (int a = 0; a < naggs; ++a) {
-          lp.p.out[1 + a] = rel->cols[1 + a].data;
-          fc.col[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
-          fc.init[a] = static_cast<unsigned long long>(init[a]);
-        }
-        if (naggs > 0) {
-          fill_cols_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(fc, runs);
-          ctx->stats.launches += 1;
-        }
+        for (int a = 0; a < naggs; ++a) lp.p.out[1 + a] = rel->cols[1 + a].data;
         lp.p.tile_offsets = run_offsets;
         lp.p.run_key_col = key_col;
         static const int jit_mode = getenv("MSC_SCAN_JIT") ? atoi(getenv("MSC_SCAN_JIT")) : 1;
         bool jitted = false;
         if (jit_mode > 0 && naggs + 1 <= MSC_VM_MAX_OUT && (sd->want_jit != 0 || jit_mode > 1 || jit_runs_cached(ctx, sd, naggs, kinds, key_col))) {
-          rc = jit_runs_launch(ctx, sd, naggs, kinds, key_col, run_offsets, lp.p.out, true);
+          // The specialised kernel STORES every run's cell before anything is added to it (jit_prelude.inc fold_store_heads): the
+          // result columns need no identity fill.  What a tile adds to the run that was open when it began goes to a carry
+          // cell per (accumulator, tile), folded into the runs by carry_fold_kernel afterwards.
+          DevTmp carry(ctx);
+          const uint64_t cstride = (ntiles + 1) & ~1ull;  // (a row per accumulator, of even length: 16-byte stores fill it)
+          MSC_TRY(carry.alloc(sizeof(unsigned long long) * std::max<uint64_t>(2, static_cast<uint64_t>(naggs) * cstride)));
+          FillCols fc;
+          CarryFold cf;
+          fc.n = cf.n = naggs;
+          for (int a = 0; a < naggs; ++a) {
+            fc.col[a] = carry.as<unsigned long long>() + static_cast<uint64_t>(a) * cstride;
+            fc.init[a] = cf.init[a] = static_cast<unsigned long long>(init[a]);
+            cf.col[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
+            cf.kind[a] = kinds[a];
+          }
+          if (naggs > 0) {
+            fill_cols_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(fc, ntiles);
+            ctx->stats.launches += 1;
+          }
+          rc = jit_runs_launch(ctx, sd, naggs, kinds, key_col, run_offsets, lp.p.out, carry.as<unsigned long long>(), true);
           jitted = rc == MSC_OK;
           const bool declined = (rc == MSC_ERR_ARG && ctx->err.rfind("jit:", 0) == 0) || (rc == MSC_ERR_CUDA && ctx->err.rfind("jit: lib", 0) == 0);
           if (rc != MSC_OK && !declined) {
             msc_rel_free(rel);
             return rc;
           }
+          if (jitted && naggs > 0 && ntiles > 1) {
+            carry_fold_kernel<<<static_cast<unsigned>(std::min<uint64_t>((ntiles + 255) / 256, static_cast<uint64_t>(ctx->sm_count) * 8)), 256, 0, ctx->stream>>>(
+                carry.as<unsigned long long>(), cstride, run_offsets, ntiles, cf);
+            ctx->stats.launches += 1;
+          }
         }
-        if (!jitted) {
+        if (!jitted) {  // the interpreter accumulates every run with atomics: all cells start from the identity
+          FillCols fc;
+          fc.n = naggs;
+          for (int a = 0; a < naggs; ++a) {
+            fc.col[a] = static_cast<unsigned long long*>(rel->cols[1 + a].data);
+            fc.init[a] = static_cast<unsigned long long>(init[a]);
+          }
+          if (naggs > 0) {
+            fill_cols_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(fc, runs);
+            ctx->stats.launches += 1;
+          }
           rc = launch_scan_r<MODE_RUNS>(ctx, &lp);
           if (rc != MSC_OK) {
             msc_rel_free(rel);

@@ -275,7 +275,7 @@ def test_streaming_aggregate_over_sorted_runs_compiles(tmp_path):
     rc = lib.msc_jit_runs_source(C.byref(d), N.int32_array(prog.agg_kinds), len(prog.agg_kinds), key_slot, buf, len(buf), C.byref(n))
     src = buf.value.decode()
     assert rc == 0, src
-    assert "msc_jit_runs" in src and "fold_segment<0>" in src and "fold_segment<3>" in src   # SUM_F and MAX_F accumulators
+    assert "msc_jit_runs" in src and "fold_store_heads<0>(" in src and "fold_store_heads<3>(" in src   # SUM_F and MAX_F accumulators: stored, then added to
     assert "p.tile_offsets[tile + nw]" in src and "out_key[run0] = key[r]" in src   # (run base fetched one tile ahead)
     compile_source(src)
 
