@@ -26,7 +26,8 @@ CAPTURES = [
      "per warp, aggregate per survivor; 5 resident CTAs per SM", SF10_ROWS,
      {"config": "join (extra.join)", "sf": 10.0, "probe_rows": SF10_ROWS, "bytes_per_row_scanned": 9}, 9),
     ("runs", "r02 prof_runs: msc_jit_runs, streaming aggregate over sorted runs, config 4 (GROUP BY l_orderkey), lineitem sf10",
-     "no hash table: run heads by comparison, run numbers by warp scan (tile bases fetched one tile ahead), one atomic per (run, accumulator) segment",
+     "no hash table: run heads by comparison, run numbers by warp scan (tile bases fetched one tile ahead); every run's cell is STORED by the segment "
+     "holding its first row, leading rows are added behind the warp's barrier, tiles carry into earlier runs through carry cells: no identity fill",
      SF10_ROWS, {"config": "highcard (extra.highcard)", "sf": 10.0, "rows": SF10_ROWS, "bytes_per_row_scanned": 12}, 12),
     ("build", "r02 prof_build: join_build8_kernel, compact join table build over the filtered orders side (2.3 M keys), config 5",
      "CAS on 8-byte slots + presence bitmap", BUILD_KEYS, None, 8),
