@@ -142,3 +142,25 @@ def test_a_filter_that_could_raise_stays_above_the_join(tmp_path):
                       "WHERE 100 / o.quantity > 20;".format(**paths))
     join = plan.child
     assert isinstance(join, L.LJoin) and isinstance(join.right, L.LTable) and len(plan.filters) == 1
+
+
+def test_build_scan_program_is_filters_rank_and_the_key(tmp_path):
+    """The build half of a join as one scan (msc_scan_join_build; off by default): the side's own filters, RANK
+    (so that a count pass can stop there) and GROUP <- key -- nothing else."""
+    plan = _q1_plan(tmp_path)
+    table = plan.child.child.child
+    res = StubResolver(table.schema)
+    ltype_of = {"INTEGER": "I", "FLOAT": "F", "TIMESTAMP": "T", "STRING": "S"}
+    res.ltypes = [ltype_of[t.name] for _, t in table.schema]
+    res.dict_of = {i: StubDict(["A", "N", "R"]) for i, t in enumerate(res.ltypes) if t == "S"}
+    names = [n for n, _ in table.schema]
+    qty, ts = names.index("l_quantity"), names.index("l_shipdate")
+    filters = [L.EBin(L.BOOL, "gt", L.EInput(L.FLOAT, qty), L.EConst(L.FLOAT, 25.0)), L.EBin(L.BOOL, "le", L.EInput(L.TS, ts), L.EConst(L.TS, 10**15))]
+    program, key_dict = L.compile_build(res, filters, L.EInput(L.TS, ts))
+    text = program.text
+    assert [line.split(" <- ")[0].split(",")[0] for line in text[:2]] == ["filter", "filter"]
+    assert text[2].startswith("RANK") or "RANK" in text[2]
+    assert text[3].startswith("group <- MOV(") and text[-1] == "END" and len(text) == 5
+    assert key_dict is None
+    unfiltered, _ = L.compile_build(res, [], L.EInput(L.TS, ts))
+    assert len(unfiltered.text) == 2 and unfiltered.text[0].startswith("group <- MOV(")   # no filter: no RANK either
